@@ -1,0 +1,132 @@
+/*
+ * unet_b200.h - C ABI of libunet_b200.so: the B200 (sm_100a) replacement for the U-Net hot path of
+ * masktrump19-sudo/unet-lane-detection.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   README.md:1421-1481   class UNet(nn.Module): __init__/_conv_block/forward  -> plan_* + forward
+ *   src/unet.py:24-42     RKNNLaneInference.preprocess_image (+ README.md:3110-3111 mean/std)
+ *                                                                               -> preprocess_u8
+ *   src/unet.py:44-72     RKNNLaneInference.postprocess_output (sigmoid, > thr, *255) -> forward(mask)
+ *   src/py_utils/rknn_executor.py:26-38  RKNN_model_container.run               -> infer_u8_host
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure; the message is
+ * available from unet_b200_last_error() (thread-local). Nothing here throws or calls exit().
+ * All `*_dev` pointers are caller-owned CUDA device memory; `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream); work is enqueued, not synchronised, unless stated otherwise.
+ * A plan is not thread-safe; distinct plans are independent. The library targets sm_100a only:
+ * on any other device the calls fail with UB_ERR_DEVICE - there is no CPU or library fallback.
+ */
+#ifndef UNET_B200_H
+#define UNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_OK 0
+#define UB_ERR_ARG (-1)     /* bad argument / unsupported shape */
+#define UB_ERR_CUDA (-2)    /* a CUDA runtime or driver call failed */
+#define UB_ERR_DEVICE (-3)  /* not an sm_100 device */
+#define UB_ERR_STATE (-4)   /* plan not bound / weights not set */
+
+#define UB_MAX_LEVELS 6
+
+typedef struct unet_b200_plan unet_b200_plan;
+
+const char* unet_b200_last_error(void);
+int unet_b200_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), UB_ERR_DEVICE otherwise. */
+int unet_b200_device_ok(void);
+
+/* ---- plan: UNet(in_channels, out_channels=1, features) at a fixed HxW and batch capacity ------- *
+ * Mirrors UNet.__init__ (README.md:1424-1447). H and W must be divisible by 2^levels, features
+ * multiples of 64 (32 allowed for level 0 only when it is the stem output), in_channels <= 4,
+ * out_channels == 1. */
+int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
+                          const int* features, int levels);
+void unet_b200_plan_destroy(unet_b200_plan* p);
+/* Bytes of device memory the plan needs for activations (workspace) and packed weights. */
+size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p);
+size_t unet_b200_plan_weight_bytes(const unet_b200_plan* p);
+/* Hand the plan its two caller-owned device buffers (256-byte aligned); builds the TMA tensor maps. */
+int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_dev);
+
+/* Number of 3x3 convolutions (2*(2*levels+1)) and their order:
+ * enc0.0, enc0.3, enc1.0, ..., bottleneck.0, bottleneck.3, dec0.0, dec0.3, ...  (state_dict order
+ * of README.md:1432-1444 with decoder blocks taken at odd indices). */
+int unet_b200_plan_num_convs(const unet_b200_plan* p);
+/* Fold eval-mode BatchNorm into conv `idx` and pack it into the plan's weight buffer.
+ * w: fp32 [Cout][Cin][3][3]; gamma/beta/mean/var: fp32 [Cout] (all four NULL = no BN). */
+int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w_dev, const float* gamma_dev,
+                            const float* beta_dev, const float* mean_dev, const float* var_dev, float eps,
+                            void* stream);
+/* ConvTranspose2d(2f, f, 2, 2) of decoder level idx (0 = deepest): w fp32 [2f][f][2][2], bias fp32 [f]. */
+int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w_dev, const float* bias_dev, void* stream);
+/* Output Conv2d(f0, 1, 1): w fp32 [f0], bias fp32 [1] (read synchronously on `stream`). */
+int unet_b200_plan_set_head(unet_b200_plan* p, const float* w_dev, const float* bias_dev, void* stream);
+
+/* ---- forward (UNet.forward, README.md:1460-1481, eval mode) -------------------------------------- *
+ * x_nhwc4_dev: bf16 [batch][H][W][4] (channels >= in_channels are ignored/zero).
+ * Any of the three outputs may be NULL:
+ *   logits_dev fp32 [batch][H][W]   (== NCHW [batch,1,H,W])
+ *   probs_dev  fp32 [batch][H][W]   sigmoid(logits)
+ *   mask_dev   u8   [batch][H][W]   (sigmoid(logit) > threshold) ? 255 : 0   (src/unet.py:63-67) */
+int unet_b200_forward(unet_b200_plan* p, const void* x_nhwc4_dev, int batch, float* logits_dev, float* probs_dev,
+                      uint8_t* mask_dev, float threshold, void* stream);
+/* Number of kernels one unet_b200_forward call launches (for launch accounting). */
+int unet_b200_forward_launches(const unet_b200_plan* p);
+
+/* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary). */
+int unet_b200_nchw_to_nhwc4(const float* x_dev, int batch, int C, int H, int W, void* y_nhwc4_dev, void* stream);
+
+/* ---- preprocess (src/unet.py:24-42 + in-graph normalisation README.md:3110-3111) ---------------- *
+ * src_dev: uint8 [batch][Hs][Ws][3] with the given row pitch / frame stride in bytes.
+ * cv2.resize(INTER_LINEAR)-exact bilinear resize to HxW, optional R<->B swap (BGR input), then
+ * (x - mean[c]) / std[c] with mean/std given in output (RGB) channel order, written as NHWC4 bf16.
+ * resized_u8_dev (optional, may be NULL) receives the resized uint8 [batch][H][W][3] frame. */
+int unet_b200_preprocess_u8(const uint8_t* src_dev, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride,
+                            int H, int W, int swap_rb, const float* mean3, const float* std3, void* y_nhwc4_dev,
+                            uint8_t* resized_u8_dev, void* stream);
+
+/* ---- executor entry point (RKNN_model_container.run, src/py_utils/rknn_executor.py:26-38) -------- *
+ * HOST uint8 [batch][Hs][Ws][3] frames in, HOST outputs out (any may be NULL). Copies H2D, runs
+ * preprocess + forward on `stream`, copies D2H and synchronises the stream before returning.
+ * staging_dev must hold unet_b200_infer_staging_bytes(...) bytes. */
+size_t unet_b200_infer_staging_bytes(const unet_b200_plan* p, int Hs, int Ws);
+int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging_dev, const uint8_t* frames_host, int batch, int Hs,
+                            int Ws, int swap_rb, const float* mean3, const float* std3, float threshold,
+                            float* logits_host, float* probs_host, uint8_t* mask_host, void* stream);
+
+/* ---- single layers (parity tests and reuse outside a plan) --------------------------------------- *
+ * conv3x3: y = relu?(conv3x3(cat(x0, x1)) + bias); x0/x1 bf16 NHWC [B,H,W,C0|C1] (C1 may be 0, then
+ * x1 is ignored); wp bf16 [Cout][9][C0+C1]; bias fp32 [Cout]; y bf16 [B,H,W,Cout]; pool (optional)
+ * bf16 [B,H/2,W/2,Cout] = maxpool2x2(y). C0, C1, Cout multiples of 64. */
+int unet_b200_conv3x3(const void* x0_dev, int C0, const void* x1_dev, int C1, const void* wp_dev,
+                      const float* bias_dev, int B, int H, int W, int Cout, int relu, void* y_dev, void* pool_dev,
+                      void* stream);
+/* convT2x2: y[b,2h+dy,2w+dx,co] = bias[co] + sum_ci x[b,h,w,ci]*w[ci,co,dy,dx]; wp bf16 [4f][Cin]. */
+int unet_b200_convT2x2(const void* x_dev, int Cin, const void* wp_dev, const float* bias_dev, int B, int H, int W,
+                       int f, void* y_dev, void* stream);
+/* Packing helpers producing the layouts above from PyTorch-layout fp32 tensors. */
+int unet_b200_pack_conv3x3(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* mean_dev,
+                           const float* var_dev, float eps, int Cout, int Cin, void* wp_dev, float* bias_dev,
+                           void* stream);
+int unet_b200_pack_convT2x2(const float* w_dev, int Cin, int f, void* wp_dev, void* stream);
+/* Stem conv (Cin <= 4) on NHWC4 input; ws fp32 [9][4][Cout] from pack_stem. */
+int unet_b200_pack_stem(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* mean_dev,
+                        const float* var_dev, float eps, int Cout, int Cin, float* ws_dev, float* bias_dev,
+                        void* stream);
+int unet_b200_stem_conv(const void* x_nhwc4_dev, const float* ws_dev, const float* bias_dev, int B, int H, int W,
+                        int Cin, int Cout, int relu, void* y_dev, void* stream);
+/* 1x1 head on bf16 NHWC [npix][C]: w fp32 [C] (device), bias by value. Outputs optional. */
+int unet_b200_head(const void* x_dev, const float* w_dev, float bias, size_t npix, int C, float* logits_dev,
+                   float* probs_dev, uint8_t* mask_dev, float threshold, void* stream);
+int unet_b200_maxpool2x2(const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H */

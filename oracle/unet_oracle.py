@@ -1,0 +1,236 @@
+"""CPU oracle for the U-Net hot path of masktrump19-sudo/unet-lane-detection.
+
+TEST INFRASTRUCTURE ONLY. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package never does (it fails loudly when
+its CUDA library is missing instead).
+
+Parity status: the reference ships NO golden vectors or tests for this path, so
+the oracle is pinned against (a) the structural facts the reference states - 31,037,633 parameters
+(README.md:2288), output shape [1,1,224,224] (README.md:1489-1490) - and (b) outputs of the
+reference's own `class UNet` listing executed verbatim in the build container
+(tests/golden/make_golden.py -> tests/golden/*.npz). cv2.resize parity of the preprocess is pinned
+against cv2 itself on the reference's sample images (same script).
+
+Each function cites the reference lines it restates (paths relative to the reference tree).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+IMAGENET_MEAN_255 = (123.675, 116.28, 103.53)   # README.md:3110 (RKNN config mean_values)
+IMAGENET_STD_255 = (58.395, 57.12, 57.375)      # README.md:3111 (RKNN config std_values)
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# Model: restates README.md:1421-1481 (class UNet). Attribute names and registration order are part
+# of the contract (state_dict keys), so they are kept; the body is restated.
+# --------------------------------------------------------------------------------------------------
+def double_conv(cin: int, cout: int) -> nn.Sequential:
+    """README.md:1449-1458: (Conv3x3 pad 1 no bias -> BatchNorm2d -> ReLU) x 2."""
+    layers = []
+    for a, b in ((cin, cout), (cout, cout)):
+        layers += [nn.Conv2d(a, b, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(b), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
+
+
+class UNetOracle(nn.Module):
+    def __init__(self, in_channels: int = 3, out_channels: int = 1, features=(64, 128, 256, 512)):
+        super().__init__()
+        features = list(features)
+        # registration order of README.md:1427-1447: encoder list, decoder list, pool, bottleneck, output
+        self.encoder_blocks = nn.ModuleList()
+        self.decoder_blocks = nn.ModuleList()
+        self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
+        c = in_channels
+        for f in features:
+            self.encoder_blocks.append(double_conv(c, f))
+            c = f
+        self.bottleneck = double_conv(features[-1], 2 * features[-1])
+        for f in features[::-1]:
+            self.decoder_blocks.append(nn.ConvTranspose2d(2 * f, f, kernel_size=2, stride=2))
+            self.decoder_blocks.append(double_conv(2 * f, f))
+        self.output = nn.Conv2d(features[0], out_channels, kernel_size=1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """README.md:1460-1481. Returns logits (no sigmoid)."""
+        kept = []
+        for block in self.encoder_blocks:
+            x = block(x)
+            kept.append(x)
+            x = self.pool(x)
+        x = self.bottleneck(x)
+        for level in range(len(self.decoder_blocks) // 2):
+            up = self.decoder_blocks[2 * level](x)
+            skip = kept[-1 - level]
+            x = self.decoder_blocks[2 * level + 1](torch.cat([skip, up], dim=1))  # skip first (README.md:1478)
+        return self.output(x)
+
+
+def randomize_bn_(model: nn.Module, seed: int = 1) -> None:
+    """make BN non-trivial so a wrong fold is visible.
+    gamma~U(0.5,1.5), beta~N(0,0.1), mean~N(0,0.1), var~U(0.5,1.5)."""
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            n = m.num_features
+            with torch.no_grad():
+                m.weight.copy_(torch.rand(n, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+
+
+def scale_head_(model: nn.Module, gain: float) -> None:
+    """Give the logits a realistic scale (random init leaves |logit| ~ 1e-2)."""
+    with torch.no_grad():
+        model.output.weight.mul_(gain)
+
+
+# --------------------------------------------------------------------------------------------------
+# Loss: restates README.md:1855-1893 (BCEDiceLoss).
+# --------------------------------------------------------------------------------------------------
+class BCEDiceLossOracle(nn.Module):
+    def __init__(self, bce_weight=0.5, dice_weight=0.5, pos_weight=None, smooth=1e-6):
+        super().__init__()
+        self.bce_weight, self.dice_weight, self.smooth = bce_weight, dice_weight, smooth
+        self.bce = nn.BCEWithLogitsLoss(pos_weight=pos_weight)
+
+    def forward(self, pred, target):
+        target = target.float()
+        bce = self.bce(pred, target)
+        p = torch.sigmoid(pred).reshape(-1)
+        t = target.reshape(-1)
+        dice = 1 - (2.0 * (p * t).sum() + self.smooth) / (p.sum() + t.sum() + self.smooth)
+        return self.bce_weight * bce + self.dice_weight * dice, bce, dice
+
+
+def compute_dice_oracle(pred_mask: torch.Tensor, target: torch.Tensor, smooth: float = 1e-6) -> float:
+    """README.md:2115-2120 (validation Dice on thresholded masks)."""
+    p = pred_mask.reshape(-1).float()
+    t = target.reshape(-1).float()
+    return float((2.0 * (p * t).sum() + smooth) / (p.sum() + t.sum() + smooth))
+
+
+# --------------------------------------------------------------------------------------------------
+# Pre / post-processing: restates src/unet.py:24-72.
+# --------------------------------------------------------------------------------------------------
+def _linear_taps(dn: int, sn: int):
+    """cv2 INTER_LINEAR tap positions and 11-bit fixed-point weights for one axis (uint8 path)."""
+    scale = sn / dn
+    f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    f = f - s
+    lo = s < 0
+    f[lo], s[lo] = 0.0, 0
+    hi = s >= sn - 1
+    f[hi], s[hi] = 0.0, sn - 1
+    w1 = np.rint(f * np.float32(2048)).astype(np.int32)
+    w0 = np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int32)
+    return s, np.minimum(s + 1, sn - 1), w0, w1
+
+
+def resize_bilinear_u8(img: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """Bit-exact numpy model of cv2.resize(img, (dw, dh)) for uint8 HxWxC, default INTER_LINEAR
+    (src/unet.py:33). Verified against cv2 4.13 for down-scales; see tests/golden/make_golden.py."""
+    if img.ndim == 2:
+        return resize_bilinear_u8(img[:, :, None], dh, dw)[:, :, 0]
+    sh, sw = img.shape[:2]
+    x0, x1, ax0, ax1 = _linear_taps(dw, sw)
+    y0, y1, by0, by1 = _linear_taps(dh, sh)
+    s = img.astype(np.int32)
+    horiz = s[:, x0, :] * ax0[None, :, None] + s[:, x1, :] * ax1[None, :, None]
+    top, bot = horiz[y0], horiz[y1]
+    out = (((by0[:, None, None] * (top >> 4)) >> 16) + ((by1[:, None, None] * (bot >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def preprocess_oracle(image_u8: np.ndarray, size=(224, 224), swap_rb: bool = False):
+    """src/unet.py:24-42: resize to the model input, keep uint8, add the batch dim -> (1,H,W,3).
+    swap_rb models the caller's BGR->RGB (src/unet_ros_node.py:310). Returns (uint8 NHWC, original_shape)."""
+    original_shape = image_u8.shape[:2]
+    img = resize_bilinear_u8(image_u8, size[0], size[1])
+    if swap_rb:
+        img = img[:, :, ::-1]
+    return np.ascontiguousarray(img)[None], original_shape
+
+
+def normalize_oracle(frames_u8_nhwc: np.ndarray) -> np.ndarray:
+    """In-graph normalisation of the deployed model (README.md:3110-3111): (x - mean) / std -> NCHW fp32."""
+    x = frames_u8_nhwc.astype(np.float32)
+    x = (x - np.asarray(IMAGENET_MEAN_255, np.float32)) / np.asarray(IMAGENET_STD_255, np.float32)
+    return np.ascontiguousarray(x.transpose(0, 3, 1, 2))
+
+
+def postprocess_oracle(output, original_shape, threshold: float = 0.5) -> np.ndarray:
+    """src/unet.py:44-72: take [0,0], int8->f32, sigmoid iff values leave [0,1], strict '>' threshold,
+    *255 uint8, resize back to the source size."""
+    mask = output[0] if isinstance(output, (list, tuple)) and len(output) > 0 else output
+    mask = np.asarray(mask)
+    if mask.ndim == 4:
+        mask = mask[0, 0]
+    elif mask.ndim == 3:
+        mask = mask[0]
+    if mask.dtype == np.int8:
+        mask = mask.astype(np.float32)
+    if mask.max() > 1.0 or mask.min() < 0.0:
+        mask = 1 / (1 + np.exp(-mask))
+    binary = (mask > threshold).astype(np.uint8) * 255
+    return resize_bilinear_u8(binary, original_shape[0], original_shape[1])
+
+
+# --------------------------------------------------------------------------------------------------
+# Layer-level helpers used by the kernel parity tests.
+# --------------------------------------------------------------------------------------------------
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def fold_bn(conv_w: torch.Tensor, bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm folded into the preceding bias-free conv: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)."""
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return conv_w * s[:, None, None, None], bn.bias - bn.running_mean * s
+
+
+@torch.no_grad()
+def forward_bf16_emulated(model: UNetOracle, x: torch.Tensor, return_feats: bool = False):
+    """The same network evaluated with the B200 path's rounding points: folded weights rounded to
+    bf16, activations rounded to bf16 at every layer boundary, fp32 accumulation, fp32 head.
+    This is NOT the parity target (that is model(x) in fp32); it separates 'bf16 by design' error
+    from kernel bugs in the per-layer tests."""
+    feats = {}
+
+    def block(seq, t, name):
+        for k, (ci, bi) in enumerate(((0, 1), (3, 4))):
+            w, b = fold_bn(seq[ci].weight, seq[bi])
+            t = bf16_round(F.relu(F.conv2d(t, bf16_round(w), b, padding=1)))
+            feats[f"{name}.{k}"] = t
+        return t
+
+    t = bf16_round(x)
+    kept = []
+    for i, enc in enumerate(model.encoder_blocks):
+        t = block(enc, t, f"enc{i}")
+        kept.append(t)
+        t = F.max_pool2d(t, 2)
+    t = block(model.bottleneck, t, "bott")
+    for level in range(len(model.decoder_blocks) // 2):
+        up = model.decoder_blocks[2 * level]
+        t = bf16_round(F.conv_transpose2d(t, bf16_round(up.weight), up.bias, stride=2))
+        feats[f"up{level}"] = t
+        t = block(model.decoder_blocks[2 * level + 1], torch.cat([kept[-1 - level], t], dim=1), f"dec{level}")
+    logits = F.conv2d(t, model.output.weight, model.output.bias)
+    return (logits, feats) if return_feats else logits
+
+
+def mask_agreement(logits_a: torch.Tensor, logits_b: torch.Tensor, threshold: float = 0.5, band: float = 0.0):
+    """Fraction of pixels whose thresholded masks agree; pixels with |logit_b - logit(thr)| < band excluded."""
+    z = float(np.log(threshold / (1 - threshold)))
+    a, b = logits_a.reshape(-1) > z, logits_b.reshape(-1) > z
+    keep = (logits_b.reshape(-1) - z).abs() >= band
+    if keep.sum() == 0:
+        return 1.0
+    return float((a[keep] == b[keep]).float().mean())

@@ -1,0 +1,17 @@
+"""unet-lane-detection_b200: B200 (sm_100a) U-Net hot path behind the reference's interfaces.
+
+    from unet_lane_detection_b200 import UNet, B200_model_container
+
+`UNet` mirrors the reference's nn.Module (README.md:1421-1481); `B200_model_container` mirrors the
+executor plugin API (src/py_utils/rknn_executor.py). Both drive libunet_b200.so (hand-written CUDA,
+C ABI in include/unet_b200.h) and raise if it is missing - there is no CPU fallback.
+"""
+from . import _lib  # noqa: F401  (raises ImportError when the CUDA library has not been built)
+from .ops import (  # noqa: F401
+    conv3x3, convT2x2, head, maxpool2x2, nchw_to_nhwc4, pack_conv3x3, pack_convT2x2, pack_stem, preprocess_u8,
+    stem_conv,
+)
+from .unet import UNet  # noqa: F401
+from .executor import B200_model_container, B200LaneInference  # noqa: F401
+
+__all__ = ["UNet", "B200_model_container", "B200LaneInference"]

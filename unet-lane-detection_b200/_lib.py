@@ -1,0 +1,69 @@
+"""ctypes binding of libunet_b200.so (include/unet_b200.h). No torch types cross this boundary:
+tensors are passed as raw device pointers plus sizes, the stream as a void*.
+
+The product path has no fallback: if the library is missing this module raises at import.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libunet_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python unet-lane-detection_b200/build.py` "
+        "(nvcc, sm_100a). There is no CPU / PyTorch fallback for the B200 U-Net path."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+_SIGS = {
+    "unet_b200_last_error": (C.c_char_p, []),
+    "unet_b200_version": (i32, []),
+    "unet_b200_device_ok": (i32, []),
+    "unet_b200_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
+    "unet_b200_plan_destroy": (None, [vp]),
+    "unet_b200_plan_workspace_bytes": (sz, [vp]),
+    "unet_b200_plan_weight_bytes": (sz, [vp]),
+    "unet_b200_plan_bind": (i32, [vp, vp, vp]),
+    "unet_b200_plan_num_convs": (i32, [vp]),
+    "unet_b200_plan_set_conv": (i32, [vp, i32, vp, vp, vp, vp, vp, f32, vp]),
+    "unet_b200_plan_set_convT": (i32, [vp, i32, vp, vp, vp]),
+    "unet_b200_plan_set_head": (i32, [vp, vp, vp, vp]),
+    "unet_b200_forward": (i32, [vp, vp, i32, vp, vp, vp, f32, vp]),
+    "unet_b200_forward_launches": (i32, [vp]),
+    "unet_b200_nchw_to_nhwc4": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_preprocess_u8": (i32, [vp, i32, i32, i32, sz, sz, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, vp]),
+    "unet_b200_infer_staging_bytes": (sz, [vp, i32, i32]),
+    "unet_b200_infer_u8_host": (i32, [vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), f32, vp, vp, vp, vp]),
+    "unet_b200_conv3x3": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "unet_b200_convT2x2": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_pack_conv3x3": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
+    "unet_b200_pack_convT2x2": (i32, [vp, i32, i32, vp, vp]),
+    "unet_b200_pack_stem": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
+    "unet_b200_stem_conv": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_head": (i32, [vp, vp, f32, sz, i32, vp, vp, vp, f32, vp]),
+    "unet_b200_maxpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+}
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTS = tuple(_SIGS.keys())
+
+
+class UnetB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise UnetB200Error(f"libunet_b200 error {rc}: {lib.unet_b200_last_error().decode()}")
+
+
+def f3(vals):
+    return (f32 * 3)(*[float(v) for v in vals])

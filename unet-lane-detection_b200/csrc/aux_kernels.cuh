@@ -1,0 +1,340 @@
+// Bandwidth-bound and SIMT kernels around the tensor-core convolutions:
+// weight packing (BN fold), layout conversion, uint8 preprocess (cv2-exact bilinear + normalise),
+// the Cin<=4 stem convolution, the 1x1 head + sigmoid + threshold mask, stand-alone 2x2 max-pool.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing. Reference layouts: Conv2d weight [Cout][Cin][3][3] (README.md:1452,1455),
+// BatchNorm2d eval fold  w' = w * g/sqrt(var+eps),  b' = beta - mean * g/sqrt(var+eps),
+// ConvTranspose2d weight [Cin][Cout][2][2] + bias (README.md:1441-1443).
+// ------------------------------------------------------------------------------------------------
+
+// -> wp[Cout][9][Cin] bf16 (K index = tap*Cin + ci), bias[Cout] fp32. gamma==nullptr: no BN (scale 1, bias 0).
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, int Cout, int Cin,
+                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int total = Cout * 9 * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Cin;
+    const int tap = (i / Cin) % 9;
+    const int co = i / (9 * Cin);
+    float s = 1.f;
+    if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
+    wp[i] = __float2bfloat16_rn(w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s);
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout; co += gridDim.x * blockDim.x) {
+    float bv = 0.f;
+    if (gamma != nullptr) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    bias[co] = bv;
+  }
+}
+
+// Stem (Cin <= 4): -> ws[9][4][Cout] fp32 (zero for ci >= Cin), bias[Cout].
+__global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, int Cout, int Cin,
+                                 float* __restrict__ ws, float* __restrict__ bias) {
+  const int total = 9 * 4 * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout;
+    const int ci = (i / Cout) % 4;
+    const int tap = i / (4 * Cout);
+    float s = 1.f;
+    if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
+    float v = 0.f;
+    if (ci < Cin) {
+      // round through bf16 so the stem uses the same weight precision as the tensor-core layers
+      v = __bfloat162float(__float2bfloat16_rn(w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s));
+    }
+    ws[i] = v;
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout; co += gridDim.x * blockDim.x) {
+    float bv = 0.f;
+    if (gamma != nullptr) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    bias[co] = bv;
+  }
+}
+
+// ConvTranspose2d(Cin, f, 2, 2): -> wp[(dy*2+dx)*f + co][Cin] bf16 (GEMM N = 4f, K = Cin).
+__global__ void pack_convT_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wp) {
+  const int total = 4 * f * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Cin;
+    const int n = i / Cin;
+    const int co = n % f;
+    const int quad = n / f;
+    wp[i] = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * f + co) * 4 + quad]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 [B,C<=4,H,W] -> NHWC4 bf16 [B,H,W,4] (missing channels zero). Module-boundary transform.
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, int B, int C, int H, int W,
+                                     uint2* __restrict__ y) {
+  const size_t hw = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / hw, p = i - b * hw;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < C; ++k) c[k] = __ldg(x + (b * C + k) * hw + p);
+    y[i] = make_uint2(pack_bf16x2(c[0], c[1]), pack_bf16x2(c[2], c[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Preprocess (north_star (d)): uint8 HWC frames -> bilinear resize to HxW exactly as cv2.resize
+// INTER_LINEAR does on uint8 (11-bit fixed-point taps; src/unet.py:33) -> optional R<->B swap
+// (BGR->RGB, src/unet_ros_node.py:310) -> (x - mean)/std (README.md:3110-3111) -> NHWC4 bf16.
+// One block per output row; the two source rows it needs are staged in shared memory so global
+// reads are fully coalesced regardless of the horizontal scale.
+// ------------------------------------------------------------------------------------------------
+struct PreArgs {
+  const uint8_t* src;  // [B, Hs, Ws, 3], row pitch in bytes
+  size_t pitch;        // bytes between source rows
+  size_t frame_stride; // bytes between source frames
+  int B, Hs, Ws, H, W;
+  int swap_rb;
+  float mean[3], inv_std[3];  // in output channel order
+  uint2* dst;          // [B,H,W] x (4 bf16)
+  uint8_t* dst_u8;     // optional [B,H,W,3] resized uint8 (pre-normalisation), for parity tests
+};
+
+__device__ __forceinline__ void resize_coef(int d, int dn, int sn, int& s0, int& s1, int& a0, int& a1) {
+  const double scale = static_cast<double>(sn) / dn;
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s = static_cast<int>(floorf(f));
+  f -= s;
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  a1 = __float2int_rn(f * 2048.f);
+  a0 = __float2int_rn((1.f - f) * 2048.f);
+  s0 = s;
+  s1 = min(s + 1, sn - 1);
+}
+
+__global__ void preprocess_u8_kernel(const PreArgs a) {
+  extern __shared__ uint8_t rows[];  // 2 x Ws*3 bytes
+  const int y = blockIdx.x % a.H;
+  const int b = blockIdx.x / a.H;
+  int sy0, sy1, by0, by1;
+  resize_coef(y, a.H, a.Hs, sy0, sy1, by0, by1);
+  const int row_bytes = a.Ws * 3;
+  const uint8_t* r0 = a.src + b * a.frame_stride + sy0 * a.pitch;
+  const uint8_t* r1 = a.src + b * a.frame_stride + sy1 * a.pitch;
+  for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) {
+    rows[i] = __ldg(r0 + i);
+    rows[row_bytes + i] = __ldg(r1 + i);
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
+    int sx0, sx1, ax0, ax1;
+    resize_coef(x, a.W, a.Ws, sx0, sx1, ax0, ax1);
+    int px[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = rows[sx0 * 3 + c] * ax0 + rows[sx1 * 3 + c] * ax1;
+      const int h1 = rows[row_bytes + sx0 * 3 + c] * ax0 + rows[row_bytes + sx1 * 3 + c] * ax1;
+      int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      px[c] = min(max(v, 0), 255);
+    }
+    if (a.swap_rb) { const int t = px[0]; px[0] = px[2]; px[2] = t; }
+    const size_t o = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+    if (a.dst_u8 != nullptr) {
+      a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
+      a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
+      a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+    }
+    const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
+    const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
+    const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
+    a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: Conv3x3(pad 1) + folded BN + ReLU for Cin <= 4 (README.md:1452 with in_channels=3).
+// K = 27 is too thin for a 64-wide UMMA K block, and the layer is write-bandwidth bound
+// (reads 8 B/pixel, writes 128 B/pixel), so it runs on the FP32 pipes: 16x16 pixel tile per block,
+// each thread owns 2 horizontally adjacent pixels x 32 output channels, weights broadcast from smem.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const uint2* __restrict__ x, const float* __restrict__ ws, const float* __restrict__ bias,
+                 int B, int H, int W, int Cin, int Cout, int relu, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sm[];
+  float* sw = sm;                       // [9][4][Cout]
+  float* sb = sw + 36 * Cout;           // [Cout]
+  float4* st = reinterpret_cast<float4*>(sb + Cout);  // [18][18] input pixels (4 ch fp32)
+  const int tiles_w = (W + 15) / 16, tiles_h = (H + 15) / 16;
+  const int tile = blockIdx.x;
+  const int w0 = (tile % tiles_w) * 16;
+  const int h0 = ((tile / tiles_w) % tiles_h) * 16;
+  const int b = tile / (tiles_w * tiles_h);
+  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) sw[i] = ws[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  for (int i = threadIdx.x; i < 18 * 18; i += blockDim.x) {
+    const int hh = h0 + i / 18 - 1, ww = w0 + i % 18 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+      const uint2 r = __ldg(x + (static_cast<size_t>(b) * H + hh) * W + ww);
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+      const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+      v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+    }
+    st[i] = v;
+  }
+  __syncthreads();
+  const int cgroups = Cout / 32;
+  for (int task = threadIdx.x; task < 128 * cgroups; task += blockDim.x) {
+    const int cg = task / 128;
+    const int pp = task % 128;
+    const int px = (pp % 8) * 2, py = pp / 8;
+    float acc0[32], acc1[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      acc0[j] = sb[cg * 32 + j];
+      acc1[j] = acc0[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      // 4 input pixels of this row feed the 3 horizontal taps of both output pixels
+      float4 in[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) in[k] = st[(py + r) * 18 + px + k];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float* wt = sw + ((r * 3 + s) * 4) * Cout + cg * 32;
+        const float i0[3] = {in[s].x, in[s].y, in[s].z};
+        const float i1[3] = {in[s + 1].x, in[s + 1].y, in[s + 1].z};
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + ci * Cout + j4 * 4);
+            acc0[j4 * 4 + 0] = fmaf(i0[ci], wv.x, acc0[j4 * 4 + 0]);
+            acc0[j4 * 4 + 1] = fmaf(i0[ci], wv.y, acc0[j4 * 4 + 1]);
+            acc0[j4 * 4 + 2] = fmaf(i0[ci], wv.z, acc0[j4 * 4 + 2]);
+            acc0[j4 * 4 + 3] = fmaf(i0[ci], wv.w, acc0[j4 * 4 + 3]);
+            acc1[j4 * 4 + 0] = fmaf(i1[ci], wv.x, acc1[j4 * 4 + 0]);
+            acc1[j4 * 4 + 1] = fmaf(i1[ci], wv.y, acc1[j4 * 4 + 1]);
+            acc1[j4 * 4 + 2] = fmaf(i1[ci], wv.z, acc1[j4 * 4 + 2]);
+            acc1[j4 * 4 + 3] = fmaf(i1[ci], wv.w, acc1[j4 * 4 + 3]);
+          }
+        }
+        // 4th input channel (only present when in_channels == 4)
+        if (Cin > 3) {
+          const float a0 = in[s].w, a1 = in[s + 1].w;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + 3 * Cout + j4 * 4);
+            acc0[j4 * 4 + 0] = fmaf(a0, wv.x, acc0[j4 * 4 + 0]);
+            acc0[j4 * 4 + 1] = fmaf(a0, wv.y, acc0[j4 * 4 + 1]);
+            acc0[j4 * 4 + 2] = fmaf(a0, wv.z, acc0[j4 * 4 + 2]);
+            acc0[j4 * 4 + 3] = fmaf(a0, wv.w, acc0[j4 * 4 + 3]);
+            acc1[j4 * 4 + 0] = fmaf(a1, wv.x, acc1[j4 * 4 + 0]);
+            acc1[j4 * 4 + 1] = fmaf(a1, wv.y, acc1[j4 * 4 + 1]);
+            acc1[j4 * 4 + 2] = fmaf(a1, wv.z, acc1[j4 * 4 + 2]);
+            acc1[j4 * 4 + 3] = fmaf(a1, wv.w, acc1[j4 * 4 + 3]);
+          }
+        }
+      }
+    }
+    const int hh = h0 + py, ww = w0 + px;
+    if (hh < H) {
+#pragma unroll
+      for (int pix = 0; pix < 2; ++pix) {
+        if (ww + pix < W) {
+          const float* acc = pix == 0 ? acc0 : acc1;
+          uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(b) * H + hh) * W + ww + pix) * Cout + cg * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = relu ? fmaxf(acc[j * 8 + k], 0.f) : acc[j * 8 + k];
+            dst[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head (north_star (c)): Conv2d(f0, 1, 1)+bias (README.md:1447,1481) -> logits; optional sigmoid ->
+// probabilities; optional mask = (sigmoid(z) > thr) * 255 uint8 (src/unet.py:63-67, strict '>').
+// 8 lanes share one pixel (16 B = 8 channels each per step) so every warp load is contiguous.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, float bias, size_t npix, int C,
+            float* __restrict__ logits, float* __restrict__ probs, uint8_t* __restrict__ mask, float thr) {
+  const int sub = threadIdx.x & 7;
+  const size_t gstride = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
+  const size_t g0 = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3;
+  const size_t iters = (npix + gstride - 1) / gstride;  // uniform trip count: every lane joins the shuffles
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t p = g0 + it * gstride;
+    const bool live = p < npix;
+    float acc = 0.f;
+    if (live) {
+      const uint4* row = reinterpret_cast<const uint4*>(x + p * C);
+      for (int c8 = sub; c8 < C / 8; c8 += 8) {
+        const uint4 r = __ldg(row + c8);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c8 * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c8 * 8 + 4));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+        acc = fmaf(__low2float(h[0]), w0.x, acc);
+        acc = fmaf(__high2float(h[0]), w0.y, acc);
+        acc = fmaf(__low2float(h[1]), w0.z, acc);
+        acc = fmaf(__high2float(h[1]), w0.w, acc);
+        acc = fmaf(__low2float(h[2]), w1.x, acc);
+        acc = fmaf(__high2float(h[2]), w1.y, acc);
+        acc = fmaf(__low2float(h[3]), w1.z, acc);
+        acc = fmaf(__high2float(h[3]), w1.w, acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (live && sub == 0) {
+      const float z = acc + bias;
+      if (logits != nullptr) logits[p] = z;
+      if (probs != nullptr || mask != nullptr) {
+        const float s = 1.f / (1.f + expf(-z));
+        if (probs != nullptr) probs[p] = s;
+        if (mask != nullptr) mask[p] = (s > thr) ? 255 : 0;
+      }
+    }
+  }
+}
+
+// Stand-alone 2x2/2 max-pool on NHWC bf16 (used when the pool is not fused into a conv epilogue).
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ y) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = i % C8;
+    size_t r = i / C8;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const size_t b = r / Ho;
+    const size_t base = ((b * H + 2 * ho) * W + 2 * wo) * C8 + c;
+    const uint4 a0 = __ldg(x + base), a1 = __ldg(x + base + C8);
+    const uint4 a2 = __ldg(x + base + static_cast<size_t>(W) * C8), a3 = __ldg(x + base + static_cast<size_t>(W) * C8 + C8);
+    uint4 o;
+    o.x = bf16x2_max(bf16x2_max(a0.x, a1.x), bf16x2_max(a2.x, a3.x));
+    o.y = bf16x2_max(bf16x2_max(a0.y, a1.y), bf16x2_max(a2.y, a3.y));
+    o.z = bf16x2_max(bf16x2_max(a0.z, a1.z), bf16x2_max(a2.z, a3.z));
+    o.w = bf16x2_max(bf16x2_max(a0.w, a1.w), bf16x2_max(a2.w, a3.w));
+    y[i] = o;
+  }
+}
+
+}  // namespace ub

@@ -1,0 +1,682 @@
+// C ABI of libunet_b200.so (see include/unet_b200.h). Host-side plan: layer table, workspace layout,
+// TMA tensor maps, launches. No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/unet_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_umma.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define UB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(UB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                        \
+  } while (0)
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// bf16 NHWC activation [Bc][H][W][C] -> 4-D map (C, W, H, B), box (64, TW, TH, TB), 128B swizzle, zero OOB fill.
+int make_act_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C, int TW, int TH, int TB) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bc};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // a box may not exceed the tensor extent along the batch axis; the kernel is told the smaller byte count
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)(TB < Bc ? TB : Bc)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled(act B=%d H=%d W=%d C=%d box %dx%dx%d) -> %d", Bc, H, W, C, TW,
+                TH, TB, (int)r);
+  }
+  return UB_OK;
+}
+
+// bf16 weights [N][K] K-major -> 2-D map (K, N), box (64, block_n).
+int make_w_map(CUtensorMap* m, const void* base, int N, int K, int block_n) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled(w N=%d K=%d) -> %d", N, K, (int)r);
+  return UB_OK;
+}
+
+int pow2_divisor(int v, int cap) {
+  int p = 1;
+  while (p * 2 <= cap && v % (p * 2) == 0) p *= 2;
+  return p;
+}
+
+// 128-pixel box: TW | W (<= 16 so the fused pool's partners stay inside a warp), TH | H, rest from batch.
+void pick_tile(int H, int W, int* TW, int* TH, int* TB) {
+  *TW = pow2_divisor(W, 16);
+  *TH = pow2_divisor(H, 128 / *TW);
+  *TB = 128 / (*TW * *TH);
+}
+
+int pick_block_n(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64; }
+
+int g_num_sms = 0;
+int g_attr_done[3] = {0, 0, 0};
+
+int device_check() {
+  int dev = 0;
+  UB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  UB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    return fail(UB_ERR_DEVICE, "device '%s' is sm_%d%d; libunet_b200 runs on sm_100 only (no fallback)", prop.name,
+                prop.major, prop.minor);
+  }
+  g_num_sms = prop.multiProcessorCount;
+  return UB_OK;
+}
+
+template <int BN>
+int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ub::ConvArgs& args,
+                  int slot, cudaStream_t st) {
+  using Cfg = ub::ConvCfg<BN>;
+  if (!g_attr_done[slot]) {
+    UB_CUDA(cudaFuncSetAttribute(ub::conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+    g_attr_done[slot] = 1;
+  }
+  const int total = args.tiles_w * args.tiles_h * args.tiles_b * args.n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  ub::conv_umma_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, w, args);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int launch_conv(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                const ub::ConvArgs& args, cudaStream_t st) {
+  if (g_num_sms == 0) {
+    int rc = device_check();
+    if (rc != UB_OK) return rc;
+  }
+  switch (block_n) {
+    case 64: return launch_conv_t<64>(a0, a1, w, args, 0, st);
+    case 128: return launch_conv_t<128>(a0, a1, w, args, 1, st);
+    case 256: return launch_conv_t<256>(a0, a1, w, args, 2, st);
+  }
+  return fail(UB_ERR_ARG, "unsupported BLOCK_N %d", block_n);
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- plan -------------------------------------------------------------------------------------------
+enum LayerKind { L_STEM, L_CONV, L_CONVT };
+
+struct Layer {
+  LayerKind kind;
+  int H, W;          // GEMM-row grid (input spatial size)
+  int C0, C1, Cout;  // conv: Cin split / Cout.  convT: C0 = Cin, Cout = f
+  int relu;
+  int in0, in1, out, pool;  // activation buffer ids (-1 = none; in0 == -2: network input)
+  size_t w_off, b_off;      // offsets into the weight buffer
+  int block_n, TW, TH, TB;
+  bool set;
+  CUtensorMap mA0, mA1, mW;
+};
+
+struct Buf {
+  int H, W, C;
+  size_t off;
+};
+
+}  // namespace
+
+struct unet_b200_plan {
+  int Bc, H, W, in_ch, levels;
+  int feat[UB_MAX_LEVELS];
+  std::vector<Layer> layers;
+  std::vector<int> conv_ids;   // layer index of 3x3 conv #i (stem included as conv 0)
+  std::vector<int> convt_ids;  // layer index of ConvT #i
+  std::vector<Buf> bufs;
+  int final_buf;
+  size_t ws_bytes, wt_bytes;
+  size_t head_w_off;
+  float head_bias;
+  bool head_set;
+  uint8_t* ws;
+  uint8_t* wt;
+};
+
+namespace {
+
+int add_buf(unet_b200_plan* p, int H, int W, int C) {
+  Buf b;
+  b.H = H;
+  b.W = W;
+  b.C = C;
+  b.off = p->ws_bytes;
+  p->ws_bytes += align_up((size_t)p->Bc * H * W * C * 2, 1024);
+  p->bufs.push_back(b);
+  return (int)p->bufs.size() - 1;
+}
+
+void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, int Cout, int in0, int in1, int out,
+              int pool) {
+  Layer l;
+  memset(&l, 0, sizeof(l));
+  l.kind = kind;
+  l.H = H;
+  l.W = W;
+  l.C0 = C0;
+  l.C1 = C1;
+  l.Cout = Cout;
+  l.relu = (kind != L_CONVT);
+  l.in0 = in0;
+  l.in1 = in1;
+  l.out = out;
+  l.pool = pool;
+  l.set = false;
+  l.w_off = p->wt_bytes;
+  if (kind == L_STEM) {
+    p->wt_bytes += align_up((size_t)36 * Cout * 4, 256);
+  } else if (kind == L_CONV) {
+    p->wt_bytes += align_up((size_t)Cout * 9 * (C0 + C1) * 2, 256);
+  } else {
+    p->wt_bytes += align_up((size_t)4 * Cout * C0 * 2, 256);
+  }
+  l.b_off = p->wt_bytes;
+  p->wt_bytes += align_up((size_t)Cout * 4, 256);
+  if (kind != L_STEM) {
+    pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+    l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
+  }
+  p->layers.push_back(l);
+  if (kind == L_CONVT) {
+    p->convt_ids.push_back((int)p->layers.size() - 1);
+  } else {
+    p->conv_ids.push_back((int)p->layers.size() - 1);
+  }
+}
+
+ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bias, void* out, void* pool) {
+  ub::ConvArgs a;
+  a.a_bytes = 128 * l.TW * l.TH * (l.TB < batch_cap ? l.TB : batch_cap);
+  a.B = batch;
+  a.H = l.H;
+  a.W = l.W;
+  a.TW = l.TW;
+  a.TH = l.TH;
+  a.TB = l.TB;
+  a.tiles_w = (l.W + l.TW - 1) / l.TW;
+  a.tiles_h = (l.H + l.TH - 1) / l.TH;
+  a.tiles_b = (batch + l.TB - 1) / l.TB;
+  const int N = (l.kind == L_CONV) ? l.Cout : 4 * l.Cout;
+  a.n_tiles = N / l.block_n;
+  a.taps = (l.kind == L_CONV) ? 9 : 1;
+  a.kc0 = l.C0 / 64;
+  a.kc1 = l.C1 / 64;
+  a.epi = (l.kind == L_CONV) ? ub::EPI_STORE : ub::EPI_CONVT;
+  a.relu = l.relu;
+  a.Cout = l.Cout;
+  a.bias = bias;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  return a;
+}
+
+int grid_for(size_t work_items, int threads) {
+  size_t g = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * 16;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* unet_b200_last_error(void) { return g_err; }
+int unet_b200_version(void) { return 100; }
+int unet_b200_device_ok(void) { return device_check(); }
+
+int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
+                          const int* features, int levels) {
+  if (out == nullptr || features == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (levels < 1 || levels > UB_MAX_LEVELS) return fail(UB_ERR_ARG, "levels must be in [1,%d]", UB_MAX_LEVELS);
+  if (max_batch < 1) return fail(UB_ERR_ARG, "max_batch must be >= 1");
+  if (in_channels < 1 || in_channels > 4) return fail(UB_ERR_ARG, "in_channels must be in [1,4] (got %d)", in_channels);
+  if (out_channels != 1) return fail(UB_ERR_ARG, "out_channels must be 1 (got %d)", out_channels);
+  if (H % (1 << levels) != 0 || W % (1 << levels) != 0) {
+    return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
+  }
+  for (int i = 0; i < levels; ++i) {
+    if (features[i] % 64 != 0 || features[i] <= 0) {
+      return fail(UB_ERR_ARG, "features[%d]=%d must be a positive multiple of 64", i, features[i]);
+    }
+  }
+  unet_b200_plan* p = new (std::nothrow) unet_b200_plan();
+  if (p == nullptr) return fail(UB_ERR_ARG, "out of host memory");
+  p->Bc = max_batch;
+  p->H = H;
+  p->W = W;
+  p->in_ch = in_channels;
+  p->levels = levels;
+  p->ws_bytes = 0;
+  p->wt_bytes = 0;
+  p->ws = nullptr;
+  p->wt = nullptr;
+  p->head_set = false;
+  p->head_bias = 0.f;
+  for (int i = 0; i < levels; ++i) p->feat[i] = features[i];
+
+  // encoder (README.md:1432-1434, 1464-1467)
+  int cur = -2;  // network input
+  int cin = in_channels;
+  std::vector<int> skips;
+  for (int i = 0; i < levels; ++i) {
+    const int h = H >> i, w = W >> i, f = features[i];
+    const int ea = add_buf(p, h, w, f);
+    const int sk = add_buf(p, h, w, f);
+    const int pl = add_buf(p, h / 2, w / 2, f);
+    if (i == 0) {
+      add_conv(p, L_STEM, h, w, cin, 0, f, cur, -1, ea, -1);
+    } else {
+      add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ea, -1);
+    }
+    add_conv(p, L_CONV, h, w, f, 0, f, ea, -1, sk, pl);
+    skips.push_back(sk);
+    cur = pl;
+    cin = f;
+  }
+  // bottleneck (README.md:1437, 1470)
+  {
+    const int h = H >> levels, w = W >> levels, f = features[levels - 1] * 2;
+    const int ba = add_buf(p, h, w, f);
+    const int bb = add_buf(p, h, w, f);
+    add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ba, -1);
+    add_conv(p, L_CONV, h, w, f, 0, f, ba, -1, bb, -1);
+    cur = bb;
+    cin = f;
+  }
+  // decoder (README.md:1440-1444, 1473-1479): ConvT, then double conv over cat([skip, up])
+  for (int j = 0; j < levels; ++j) {
+    const int i = levels - 1 - j;
+    const int h = H >> i, w = W >> i, f = features[i];
+    const int up = add_buf(p, h, w, f);
+    const int da = add_buf(p, h, w, f);
+    const int db = add_buf(p, h, w, f);
+    add_conv(p, L_CONVT, h / 2, w / 2, cin, 0, f, cur, -1, up, -1);
+    add_conv(p, L_CONV, h, w, f, f, f, skips[i], up, da, -1);
+    add_conv(p, L_CONV, h, w, f, 0, f, da, -1, db, -1);
+    cur = db;
+    cin = f;
+  }
+  p->final_buf = cur;
+  p->head_w_off = p->wt_bytes;
+  p->wt_bytes += align_up((size_t)features[0] * 4, 256);
+  *out = p;
+  return UB_OK;
+}
+
+void unet_b200_plan_destroy(unet_b200_plan* p) { delete p; }
+size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p) { return p ? p->ws_bytes : 0; }
+size_t unet_b200_plan_weight_bytes(const unet_b200_plan* p) { return p ? p->wt_bytes : 0; }
+int unet_b200_plan_num_convs(const unet_b200_plan* p) { return p ? (int)p->conv_ids.size() : 0; }
+
+int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_dev) {
+  if (p == nullptr || workspace_dev == nullptr || weights_dev == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if ((reinterpret_cast<uintptr_t>(workspace_dev) & 255) || (reinterpret_cast<uintptr_t>(weights_dev) & 255)) {
+    return fail(UB_ERR_ARG, "workspace and weight buffers must be 256-byte aligned");
+  }
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  p->ws = static_cast<uint8_t*>(workspace_dev);
+  p->wt = static_cast<uint8_t*>(weights_dev);
+  for (Layer& l : p->layers) {
+    if (l.kind == L_STEM) continue;
+    const Buf& b0 = p->bufs[l.in0];
+    rc = make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+    if (l.C1 > 0) {
+      const Buf& b1 = p->bufs[l.in1];
+      rc = make_act_map(&l.mA1, p->ws + b1.off, p->Bc, l.H, l.W, l.C1, l.TW, l.TH, l.TB);
+    } else {
+      l.mA1 = l.mA0;
+    }
+    if (rc != UB_OK) return rc;
+    if (l.kind == L_CONV) {
+      rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.block_n);
+    } else {
+      rc = make_w_map(&l.mW, p->wt + l.w_off, 4 * l.Cout, l.C0, l.block_n);
+    }
+    if (rc != UB_OK) return rc;
+  }
+  return UB_OK;
+}
+
+int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const float* gamma, const float* beta,
+                            const float* mean, const float* var, float eps, void* stream) {
+  if (p == nullptr || w == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (p->wt == nullptr) return fail(UB_ERR_STATE, "plan_bind must be called before set_conv");
+  if (idx < 0 || idx >= (int)p->conv_ids.size()) return fail(UB_ERR_ARG, "conv index %d out of range", idx);
+  Layer& l = p->layers[p->conv_ids[idx]];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* bias = reinterpret_cast<float*>(p->wt + l.b_off);
+  if (l.kind == L_STEM) {
+    ub::pack_stem_kernel<<<grid_for(36 * l.Cout, 256), 256, 0, st>>>(w, gamma, beta, mean, var, eps, l.Cout, l.C0,
+                                                                     reinterpret_cast<float*>(p->wt + l.w_off), bias);
+  } else {
+    const int cin = l.C0 + l.C1;
+    ub::pack_conv3x3_kernel<<<grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st>>>(
+        w, gamma, beta, mean, var, eps, l.Cout, cin, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
+  }
+  UB_CUDA(cudaGetLastError());
+  l.set = true;
+  return UB_OK;
+}
+
+int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w, const float* bias, void* stream) {
+  if (p == nullptr || w == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (p->wt == nullptr) return fail(UB_ERR_STATE, "plan_bind must be called before set_convT");
+  if (idx < 0 || idx >= (int)p->convt_ids.size()) return fail(UB_ERR_ARG, "convT index %d out of range", idx);
+  Layer& l = p->layers[p->convt_ids[idx]];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ub::pack_convT_kernel<<<grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st>>>(
+      w, l.C0, l.Cout, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off));
+  UB_CUDA(cudaGetLastError());
+  UB_CUDA(cudaMemcpyAsync(p->wt + l.b_off, bias, (size_t)l.Cout * 4, cudaMemcpyDeviceToDevice, st));
+  l.set = true;
+  return UB_OK;
+}
+
+int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias, void* stream) {
+  if (p == nullptr || w == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (p->wt == nullptr) return fail(UB_ERR_STATE, "plan_bind must be called before set_head");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UB_CUDA(cudaMemcpyAsync(p->wt + p->head_w_off, w, (size_t)p->feat[0] * 4, cudaMemcpyDeviceToDevice, st));
+  UB_CUDA(cudaMemcpyAsync(&p->head_bias, bias, 4, cudaMemcpyDeviceToHost, st));
+  UB_CUDA(cudaStreamSynchronize(st));
+  p->head_set = true;
+  return UB_OK;
+}
+
+int unet_b200_forward_launches(const unet_b200_plan* p) { return p ? (int)p->layers.size() + 1 : 0; }
+
+int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
+                      float threshold, void* stream) {
+  if (p == nullptr || x == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (p->ws == nullptr) return fail(UB_ERR_STATE, "plan is not bound");
+  if (batch < 1 || batch > p->Bc) return fail(UB_ERR_ARG, "batch %d outside [1,%d]", batch, p->Bc);
+  if (!p->head_set) return fail(UB_ERR_STATE, "head weights not set");
+  for (const Layer& l : p->layers) {
+    if (!l.set) return fail(UB_ERR_STATE, "layer weights not set");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (Layer& l : p->layers) {
+    const float* bias = reinterpret_cast<const float*>(p->wt + l.b_off);
+    void* out = p->ws + p->bufs[l.out].off;
+    void* pool = l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr;
+    if (l.kind == L_STEM) {
+      const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
+      const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
+      ub::stem_conv_kernel<<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(x),
+                                                      reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch, l.H,
+                                                      l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
+      UB_CUDA(cudaGetLastError());
+    } else {
+      ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, pool);
+      int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, st);
+      if (rc != UB_OK) return rc;
+    }
+  }
+  const Buf& fb = p->bufs[p->final_buf];
+  const size_t npix = (size_t)batch * fb.H * fb.W;
+  ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
+      p->head_bias, npix, fb.C, logits, probs, mask, threshold);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_nchw_to_nhwc4(const float* x, int batch, int C, int H, int W, void* y, void* stream) {
+  if (x == nullptr || y == nullptr || C < 1 || C > 4) return fail(UB_ERR_ARG, "bad argument");
+  const size_t n = (size_t)batch * H * W;
+  ub::nchw_to_nhwc4_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, batch, C, H, W, reinterpret_cast<uint2*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride, int H,
+                            int W, int swap_rb, const float* mean3, const float* std3, void* y, uint8_t* resized,
+                            void* stream) {
+  if (src == nullptr || y == nullptr || mean3 == nullptr || std3 == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (batch < 1 || Hs < 1 || Ws < 1 || H < 1 || W < 1) return fail(UB_ERR_ARG, "bad size");
+  if ((size_t)Ws * 3 * 2 > 200 * 1024) return fail(UB_ERR_ARG, "source row too wide for shared-memory staging");
+  ub::PreArgs a;
+  a.src = src;
+  a.pitch = pitch;
+  a.frame_stride = frame_stride;
+  a.B = batch;
+  a.Hs = Hs;
+  a.Ws = Ws;
+  a.H = H;
+  a.W = W;
+  a.swap_rb = swap_rb;
+  for (int c = 0; c < 3; ++c) {
+    a.mean[c] = mean3[c];
+    a.inv_std[c] = 1.f / std3[c];
+  }
+  a.dst = reinterpret_cast<uint2*>(y);
+  a.dst_u8 = resized;
+  const size_t smem = (size_t)Ws * 3 * 2;
+  if (smem > 48 * 1024) {
+    UB_CUDA(cudaFuncSetAttribute(ub::preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  ub::preprocess_u8_kernel<<<batch * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+size_t unet_b200_infer_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
+  if (p == nullptr) return 0;
+  const size_t npix = (size_t)p->Bc * p->H * p->W;
+  size_t n = align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // frames
+  n += align_up(npix * 8, 256);                           // NHWC4 bf16
+  n += 2 * align_up(npix * 4, 256);                       // logits, probs
+  n += align_up(npix, 256);                               // mask
+  return n;
+}
+
+int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* frames, int batch, int Hs, int Ws,
+                            int swap_rb, const float* mean3, const float* std3, float threshold, float* logits_h,
+                            float* probs_h, uint8_t* mask_h, void* stream) {
+  if (p == nullptr || staging == nullptr || frames == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (batch < 1 || batch > p->Bc) return fail(UB_ERR_ARG, "batch %d outside [1,%d]", batch, p->Bc);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t npix_c = (size_t)p->Bc * p->H * p->W;
+  const size_t npix = (size_t)batch * p->H * p->W;
+  uint8_t* s = static_cast<uint8_t*>(staging);
+  uint8_t* d_frames = s;
+  s += align_up((size_t)p->Bc * Hs * Ws * 3, 256);
+  void* d_x = s;
+  s += align_up(npix_c * 8, 256);
+  float* d_logits = reinterpret_cast<float*>(s);
+  s += align_up(npix_c * 4, 256);
+  float* d_probs = reinterpret_cast<float*>(s);
+  s += align_up(npix_c * 4, 256);
+  uint8_t* d_mask = s;
+  const size_t frame_bytes = (size_t)Hs * Ws * 3;
+  UB_CUDA(cudaMemcpyAsync(d_frames, frames, frame_bytes * batch, cudaMemcpyHostToDevice, st));
+  int rc = unet_b200_preprocess_u8(d_frames, batch, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3,
+                                   std3, d_x, nullptr, st);
+  if (rc != UB_OK) return rc;
+  rc = unet_b200_forward(p, d_x, batch, logits_h ? d_logits : nullptr, probs_h ? d_probs : nullptr,
+                         mask_h ? d_mask : nullptr, threshold, st);
+  if (rc != UB_OK) return rc;
+  if (logits_h) UB_CUDA(cudaMemcpyAsync(logits_h, d_logits, npix * 4, cudaMemcpyDeviceToHost, st));
+  if (probs_h) UB_CUDA(cudaMemcpyAsync(probs_h, d_probs, npix * 4, cudaMemcpyDeviceToHost, st));
+  if (mask_h) UB_CUDA(cudaMemcpyAsync(mask_h, d_mask, npix, cudaMemcpyDeviceToHost, st));
+  UB_CUDA(cudaStreamSynchronize(st));
+  return UB_OK;
+}
+
+// ---- single layers ----------------------------------------------------------------------------------
+int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void* wp, const float* bias, int B, int H,
+                      int W, int Cout, int relu, void* y, void* pool, void* stream) {
+  if (x0 == nullptr || wp == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0 || C0 <= 0 || C1 < 0 || Cout <= 0) {
+    return fail(UB_ERR_ARG, "C0=%d C1=%d Cout=%d must be multiples of 64", C0, C1, Cout);
+  }
+  if (C1 > 0 && x1 == nullptr) return fail(UB_ERR_ARG, "x1 is null but C1 > 0");
+  if (pool != nullptr && ((H | W) & 1)) return fail(UB_ERR_ARG, "fused pool needs even H and W");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  Layer l;
+  memset(&l, 0, sizeof(l));
+  l.kind = L_CONV;
+  l.H = H;
+  l.W = W;
+  l.C0 = C0;
+  l.C1 = C1;
+  l.Cout = Cout;
+  l.relu = relu;
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  l.block_n = pick_block_n(Cout);
+  if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
+  rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
+  if (rc != UB_OK) return rc;
+  if (C1 > 0) {
+    rc = make_act_map(&l.mA1, x1, B, H, W, C1, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+  } else {
+    l.mA1 = l.mA0;
+  }
+  rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
+  if (rc != UB_OK) return rc;
+  ub::ConvArgs a = conv_args(l, B, B, bias, y, pool);
+  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias, int B, int H, int W, int f, void* y,
+                       void* stream) {
+  if (x == nullptr || wp == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin % 64 != 0 || f % 64 != 0 || Cin <= 0 || f <= 0) return fail(UB_ERR_ARG, "Cin=%d f=%d must be multiples of 64", Cin, f);
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  Layer l;
+  memset(&l, 0, sizeof(l));
+  l.kind = L_CONVT;
+  l.H = H;
+  l.W = W;
+  l.C0 = Cin;
+  l.C1 = 0;
+  l.Cout = f;
+  l.relu = 0;
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  l.block_n = pick_block_n(4 * f);
+  rc = make_act_map(&l.mA0, x, B, H, W, Cin, l.TW, l.TH, l.TB);
+  if (rc != UB_OK) return rc;
+  l.mA1 = l.mA0;
+  rc = make_w_map(&l.mW, wp, 4 * f, Cin, l.block_n);
+  if (rc != UB_OK) return rc;
+  ub::ConvArgs a = conv_args(l, B, B, bias, y, nullptr);
+  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                           float eps, int Cout, int Cin, void* wp, float* bias, void* stream) {
+  if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  ub::pack_conv3x3_kernel<<<grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gamma, beta, mean, var, eps, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wp), bias);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_pack_convT2x2(const float* w, int Cin, int f, void* wp, void* stream) {
+  if (w == nullptr || wp == nullptr) return fail(UB_ERR_ARG, "null argument");
+  ub::pack_convT_kernel<<<grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wp));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_pack_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                        float eps, int Cout, int Cin, float* ws, float* bias, void* stream) {
+  if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
+  ub::pack_stem_kernel<<<grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_stem_conv(const void* x, const float* ws, const float* bias, int B, int H, int W, int Cin, int Cout,
+                        int relu, void* y, void* stream) {
+  if (x == nullptr || ws == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
+  const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
+  const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
+  ub::stem_conv_kernel<<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(x), ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_head(const void* x, const float* w, float bias, size_t npix, int C, float* logits, float* probs,
+                   uint8_t* mask, float threshold, void* stream) {
+  if (x == nullptr || w == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C % 8 != 0) return fail(UB_ERR_ARG, "head C=%d must be a multiple of 8", C);
+  ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), w, bias, npix, C, logits, probs, mask, threshold);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_maxpool2x2(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  if (x == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C % 8 != 0 || ((H | W) & 1)) return fail(UB_ERR_ARG, "maxpool needs C %% 8 == 0 and even H, W");
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  ub::maxpool2x2_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), B, H, W, C / 8, reinterpret_cast<uint4*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""Drop-in `UNet` (reference README.md:1421-1481) whose eval forward runs on libunet_b200.so.
+
+Same constructor signature, same submodule / parameter / buffer names, shapes, dtypes and
+registration order (so state_dict()/load_state_dict() interchange with reference checkpoints,
+SURVEY.md Appendix A), same forward contract: float NCHW [B,in_channels,H,W] -> logits
+[B,out_channels,H,W]. The parameters live in ordinary nn.Conv2d / nn.BatchNorm2d / nn.ConvTranspose2d
+containers, but those modules' own forward() is never called: forward() folds BN into the weights,
+packs them for the tensor-core kernels and runs the hand-written CUDA path. CPU tensors, or a
+missing/unsupported device, raise - there is no PyTorch/cuDNN fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ._lib import check, f3, lib
+from .ops import MEAN_255, STD_255
+
+
+class _Engine:
+    """One bound plan: (device, batch capacity, H, W) + workspace + packed weights."""
+
+    def __init__(self, model: "UNet", device: torch.device, cap: int, H: int, W: int):
+        feats = (C.c_int * len(model.features))(*model.features)
+        handle = C.c_void_p()
+        check(lib.unet_b200_plan_create(C.byref(handle), cap, H, W, model.in_channels, model.out_channels, feats,
+                                        len(model.features)))
+        self.handle = handle
+        self.cap, self.H, self.W, self.device = cap, H, W, device
+        self.workspace = torch.empty(lib.unet_b200_plan_workspace_bytes(handle), dtype=torch.uint8, device=device)
+        self.weights = torch.zeros(lib.unet_b200_plan_weight_bytes(handle), dtype=torch.uint8, device=device)
+        check(lib.unet_b200_plan_bind(handle, self.workspace.data_ptr(), self.weights.data_ptr()))
+        self.weights_key = None
+        self.launches = lib.unet_b200_forward_launches(handle)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            lib.unet_b200_plan_destroy(h)
+            self.handle = None
+
+
+class UNet(nn.Module):
+    """U-Net for lane segmentation; signature of the reference's class (README.md:1424)."""
+
+    def __init__(self, in_channels=3, out_channels=1, features=[64, 128, 256, 512]):  # noqa: B006 (reference signature)
+        super().__init__()
+        self.in_channels, self.out_channels, self.features = in_channels, out_channels, list(features)
+        self.encoder_blocks = nn.ModuleList()
+        self.decoder_blocks = nn.ModuleList()
+        self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
+        c = in_channels
+        for f in self.features:
+            self.encoder_blocks.append(self._conv_block(c, f))
+            c = f
+        self.bottleneck = self._conv_block(self.features[-1], self.features[-1] * 2)
+        for f in reversed(self.features):
+            self.decoder_blocks.append(nn.ConvTranspose2d(f * 2, f, kernel_size=2, stride=2))
+            self.decoder_blocks.append(self._conv_block(f * 2, f))
+        self.output = nn.Conv2d(self.features[0], out_channels, kernel_size=1)
+        # B200 runtime state (not part of the state_dict)
+        self.b200_chunk = 32  # frames per pass through the plan (bounds the workspace; tune for L2 reuse)
+        self._engines = {}
+        self.gpu_launches = 0
+
+    def _conv_block(self, in_channels, out_channels):
+        return nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, 3, padding=1, bias=False),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, 3, padding=1, bias=False),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        )
+
+    # ------------------------------------------------------------------ engine / weights
+    def _double_convs(self):
+        """3x3 convs with their BatchNorms in plan order (include/unet_b200.h: plan_num_convs)."""
+        blocks = list(self.encoder_blocks) + [self.bottleneck] + [self.decoder_blocks[i] for i in range(1, len(self.decoder_blocks), 2)]
+        for blk in blocks:
+            yield blk[0], blk[1]
+            yield blk[3], blk[4]
+
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _engine(self, device, H, W, batch):
+        cap = min(max(1, int(self.b200_chunk)), batch) if batch < self.b200_chunk else int(self.b200_chunk)
+        key = (str(device), cap, H, W)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, device, cap, H, W)
+            self._engines[key] = eng
+        wkey = self._weights_key()
+        if eng.weights_key != wkey:
+            self._pack(eng)
+            eng.weights_key = wkey
+        return eng
+
+    def _pack(self, eng):
+        st = torch.cuda.current_stream().cuda_stream
+        keep = []
+
+        def dev32(t):
+            t = t.detach().to(device=eng.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        for i, (conv, bn) in enumerate(self._double_convs()):
+            check(lib.unet_b200_plan_set_conv(eng.handle, i, dev32(conv.weight), dev32(bn.weight), dev32(bn.bias),
+                                              dev32(bn.running_mean), dev32(bn.running_var), float(bn.eps), st))
+        for j in range(len(self.features)):
+            up = self.decoder_blocks[2 * j]
+            check(lib.unet_b200_plan_set_convT(eng.handle, j, dev32(up.weight), dev32(up.bias), st))
+        check(lib.unet_b200_plan_set_head(eng.handle, dev32(self.output.weight.reshape(-1)), dev32(self.output.bias), st))
+        torch.cuda.current_stream().synchronize()
+
+    def _check_input(self, t, what):
+        if not t.is_cuda:
+            raise RuntimeError(f"UNet (B200): {what} is on {t.device}; the B200 path runs on CUDA sm_100 only and has "
+                               "no CPU fallback - move the model and input with .to('cuda')")
+
+    # ------------------------------------------------------------------ forward paths
+    def forward(self, x):
+        """Eval-mode forward on the B200 kernels: float NCHW -> logits NCHW (README.md:1460-1481)."""
+        if self.training:
+            raise RuntimeError("UNet (B200): the training-mode forward (batch-statistics BatchNorm) is not built yet; "
+                               "call .eval() for inference")
+        self._check_input(x, "input")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        xin = x.detach().to(torch.float32).contiguous()
+        x4 = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=x.device)
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, self.in_channels, H, W, x4.data_ptr(), st))
+        self.gpu_launches += 1
+        logits = self.forward_nhwc4(x4, want=("logits",))[0]
+        return logits.reshape(B, 1, H, W).to(x.dtype)
+
+    def forward_nhwc4(self, x4, threshold=0.5, want=("logits",)):
+        """x4: bf16 [B,H,W,4] normalised input. Returns (logits, probs, mask) with None for outputs not in `want`."""
+        self._check_input(x4, "input")
+        B, H, W, _ = x4.shape
+        dev = x4.device
+        eng = self._engine(dev, H, W, B)
+        logits = torch.empty(B, H, W, dtype=torch.float32, device=dev) if "logits" in want else None
+        probs = torch.empty(B, H, W, dtype=torch.float32, device=dev) if "probs" in want else None
+        mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if "mask" in want else None
+        st = torch.cuda.current_stream().cuda_stream
+        for b0 in range(0, B, eng.cap):
+            n = min(eng.cap, B - b0)
+            check(lib.unet_b200_forward(
+                eng.handle, x4[b0:b0 + n].data_ptr(), n,
+                None if logits is None else logits[b0:].data_ptr(),
+                None if probs is None else probs[b0:].data_ptr(),
+                None if mask is None else mask[b0:].data_ptr(), float(threshold), st))
+            self.gpu_launches += eng.launches
+        return logits, probs, mask
+
+    @torch.no_grad()
+    def predict_mask(self, frames_u8, threshold=0.5, swap_rb=False, size=(224, 224), want=("mask",)):
+        """Fused inference pipeline on device-resident uint8 frames [B,Hs,Ws,3]:
+        cv2-exact resize + normalise (src/unet.py:24-42, README.md:3110-3111) -> U-Net -> sigmoid ->
+        (p > threshold)*255 (src/unet.py:63-67). Returns (logits, probs, mask) like forward_nhwc4."""
+        self._check_input(frames_u8, "frames")
+        B, Hs, Ws, _ = frames_u8.shape
+        x4 = torch.empty(B, size[0], size[1], 4, dtype=torch.bfloat16, device=frames_u8.device)
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.unet_b200_preprocess_u8(frames_u8.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, size[0], size[1],
+                                          int(swap_rb), f3(MEAN_255), f3(STD_255), x4.data_ptr(), None, st))
+        self.gpu_launches += 1
+        return self.forward_nhwc4(x4, threshold=threshold, want=want)
