@@ -78,6 +78,15 @@ int unet_b200_forward(unet_b200_plan* p, const void* x_nhwc4_dev, int batch, flo
                       uint8_t* mask_dev, float threshold, void* stream);
 /* Number of kernels one unet_b200_forward call launches (for launch accounting). */
 int unet_b200_forward_launches(const unet_b200_plan* p);
+/* Same as unet_b200_forward, but brackets every kernel with CUDA events on `stream`, synchronises,
+ * and returns the per-kernel durations in ms_out[0 .. plan_num_layers) (last entry = head kernel). */
+int unet_b200_forward_profile(unet_b200_plan* p, const void* x_nhwc4_dev, int batch, float* logits_dev,
+                              float* probs_dev, uint8_t* mask_dev, float threshold, void* stream, float* ms_out,
+                              int n_out);
+int unet_b200_plan_num_layers(const unet_b200_plan* p);
+/* info8 = {kind (0 stem, 1 conv3x3, 2 convT2x2, 3 head), H, W, Cin, Cout, taps, BLOCK_N, fused_pool} of kernel idx;
+ * H, W are the GEMM-row grid (input resolution). */
+int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
 
 /* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary). */
 int unet_b200_nchw_to_nhwc4(const float* x_dev, int batch, int C, int H, int W, void* y_nhwc4_dev, void* stream);

@@ -1,0 +1,165 @@
+"""GPU (B200): every kernel of the hot path, through the C ABI, against the CPU oracle on the same
+seeded inputs. Tolerances: conv/convT outputs are bf16 -> at most 1 bf16 ulp of the value range plus
+accumulation-order noise (2e-2 * max(1, |ref|max)); integer/uint8 work (resize, pool, mask) is bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+bf = O.bf16_round
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import unet_lane_detection_b200 as mod
+    from unet_lane_detection_b200._lib import lib
+    assert lib.unet_b200_device_ok() == 0, lib.unet_b200_last_error()
+    return mod
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def nchw(y):
+    return y.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def close(got, ref, tol):
+    d = (got.float().cpu() - ref.float().cpu()).abs().max().item()
+    lim = tol * max(1.0, ref.abs().max().item())
+    assert d <= lim, f"max|d|={d:.4e} > {lim:.4e}"
+
+
+def conv_case(U, B, H, W, C0, C1, Cout, pool=False, relu=True, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x0 = bf(torch.randn(B, C0, H, W, generator=g))
+    x1 = bf(torch.randn(B, C1, H, W, generator=g)) if C1 else None
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) / (3.0 * (C0 + C1) ** 0.5)
+    ga, be = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+    mu, va = torch.randn(Cout, generator=g) * 0.1, torch.rand(Cout, generator=g) + 0.5
+    wp, bias = U.pack_conv3x3(w.cuda(), (ga.cuda(), be.cuda(), mu.cuda(), va.cuda(), 1e-5))
+    s = ga / torch.sqrt(va + 1e-5)
+    ref = F.conv2d(torch.cat([x0, x1], 1) if C1 else x0, bf(w * s[:, None, None, None]), be - mu * s, padding=1)
+    if relu:
+        ref = F.relu(ref)
+    out = U.conv3x3(nhwc(x0), wp, bias, x1=nhwc(x1) if C1 else None, relu=relu, pool=pool)
+    y = out[0] if pool else out
+    close(nchw(y), bf(ref), 2e-2)
+    if pool:
+        assert torch.equal(nchw(out[1]), F.max_pool2d(nchw(y), 2)), "fused 2x2 max-pool is not bit-exact"
+
+
+# every 3x3 conv shape of the default network at a small batch
+@pytest.mark.parametrize("B,H,C0,Cout", [(1, 224, 64, 64), (1, 112, 64, 128), (1, 112, 128, 128), (2, 56, 128, 256),
+                                         (2, 56, 256, 256), (8, 28, 256, 512), (8, 28, 512, 512), (32, 14, 512, 1024),
+                                         (32, 14, 1024, 1024)])
+def test_conv3x3_network_shapes(U, B, H, C0, Cout):
+    conv_case(U, B, H, H, C0, 0, Cout)
+
+
+@pytest.mark.parametrize("B,H,W,f", [(1, 224, 224, 64), (1, 112, 112, 128), (2, 56, 56, 256), (8, 28, 28, 512)])
+def test_conv3x3_concat_is_two_source_k_loop(U, B, H, W, f):
+    """decoder conv0 = conv over cat([skip, up]) without materialising the concat (README.md:1478: skip first)."""
+    conv_case(U, B, H, W, f, f, f)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 224, 224, 64), (1, 112, 112, 128), (2, 56, 56, 256), (8, 28, 28, 512)])
+def test_conv3x3_fused_pool(U, B, H, W, C):
+    conv_case(U, B, H, W, C, 0, C, pool=True)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (3, 14, 14), (5, 28, 28), (1, 60, 80), (1, 480, 640), (7, 8, 24)])
+def test_conv3x3_ragged_batches_and_sizes(U, B, H, W):
+    """Batch sizes that do not fill the pixel box, non-square and camera-resolution grids."""
+    conv_case(U, B, H, W, 64, 0, 64, pool=(H % 2 == 0 and W % 2 == 0))
+
+
+def test_conv3x3_no_relu_and_no_bn(U):
+    conv_case(U, 1, 32, 32, 64, 0, 128, relu=False)
+    x = bf(torch.randn(1, 64, 16, 16))
+    w = torch.randn(64, 64, 3, 3) / 24
+    wp, bias = U.pack_conv3x3(w.cuda())
+    assert bias.abs().max().item() == 0.0
+    close(nchw(U.conv3x3(nhwc(x), wp, bias, relu=False)), bf(F.conv2d(x, bf(w), padding=1)), 2e-2)
+
+
+def test_conv3x3_linearity(U):
+    """Size-independent property: without bias/ReLU the kernel is linear in its input (power-of-two scaling is exact)."""
+    x = bf(torch.randn(2, 64, 56, 56))
+    w = torch.randn(128, 64, 3, 3) / 24
+    wp, bias = U.pack_conv3x3(w.cuda())
+    y1 = U.conv3x3(nhwc(x), wp, bias, relu=False)
+    y2 = U.conv3x3(nhwc(x * 4), wp, bias, relu=False)
+    assert torch.equal(y2.float(), y1.float() * 4)
+
+
+@pytest.mark.parametrize("B,H,Cin,f", [(32, 14, 1024, 512), (8, 28, 512, 256), (2, 56, 256, 128), (1, 112, 128, 64), (3, 14, 128, 64)])
+def test_convT2x2(U, B, H, Cin, f):
+    g = torch.Generator().manual_seed(1)
+    x = bf(torch.randn(B, Cin, H, H, generator=g))
+    w = torch.randn(Cin, f, 2, 2, generator=g) / Cin ** 0.5
+    b = torch.randn(f, generator=g) * 0.1
+    y = U.convT2x2(nhwc(x), U.pack_convT2x2(w.cuda()), b.cuda())
+    close(nchw(y), bf(F.conv_transpose2d(x, bf(w), b, stride=2)), 2e-2)
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(3, 64, 224, 224), (3, 64, 32, 48), (1, 64, 16, 16), (4, 128, 24, 40), (3, 32, 16, 16)])
+def test_stem_conv(U, cin, cout, H, W):
+    g = torch.Generator().manual_seed(2)
+    x = bf(torch.randn(2, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 3, 3, generator=g) / 5
+    ga, be = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    mu, va = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    ws, bias = U.pack_stem(w.cuda(), (ga.cuda(), be.cuda(), mu.cuda(), va.cuda(), 1e-5))
+    s = ga / torch.sqrt(va + 1e-5)
+    ref = F.relu(F.conv2d(x, bf(w * s[:, None, None, None]), be - mu * s, padding=1))
+    x4 = U.nchw_to_nhwc4(x.cuda())
+    assert x4[..., cin:].abs().max().item() == 0.0
+    close(nchw(U.stem_conv(x4, ws, bias, cin)), bf(ref), 1e-2)
+
+
+def test_head_logits_probs_mask(U):
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn(3, 64, 40, 56, generator=g))
+    w, b = torch.randn(64, generator=g) / 8, 0.1
+    lg, pr, mk = U.head(nhwc(x), w.cuda(), b, 0.5)
+    ref = (x * w[None, :, None, None]).sum(1) + b
+    close(lg, ref, 1e-5)
+    close(pr, torch.sigmoid(ref), 1e-6)
+    # the mask must be exactly what the reference post-process makes of the kernel's own probabilities
+    want = O.postprocess_oracle([pr.cpu().numpy()[:1, None]], (40, 56), 0.5)
+    assert np.array_equal(mk[0].cpu().numpy(), want)
+    lg2, _, mk2 = U.head(nhwc(x), w.cuda(), b, 0.7, want=("logits", "mask"))
+    assert torch.equal((mk2 > 0).cpu(), torch.sigmoid(lg2.cpu()) > 0.7) or \
+        ((mk2 > 0).cpu() != (torch.sigmoid(lg2.cpu()) > 0.7)).float().mean() < 1e-5
+
+
+@pytest.mark.parametrize("hs,ws", [(480, 640), (224, 224), (685, 1055), (960, 1280), (448, 448)])
+def test_preprocess_is_cv2_exact(U, hs, ws):
+    rng = np.random.default_rng(hs)
+    img = rng.integers(0, 256, (2, hs, ws, 3), dtype=np.uint8)
+    y, r = U.preprocess_u8(torch.from_numpy(img).cuda(), swap_rb=True, return_resized=True)
+    want = np.stack([O.preprocess_oracle(im, (224, 224), swap_rb=True)[0][0] for im in img])
+    assert np.array_equal(r.cpu().numpy(), want)                      # uint8 resize + BGR->RGB: bit-exact
+    norm = torch.from_numpy(O.normalize_oracle(want)).permute(0, 2, 3, 1)
+    assert (y[..., :3].float().cpu() - bf(norm)).abs().max().item() <= 2 ** -6   # one bf16 ulp at |x| < 4
+    assert y[..., 3].abs().max().item() == 0.0
+
+
+def test_preprocess_golden_images(U, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    for k in ("synthetic_480x640", "picture_684x1054", "frame_224x224"):
+        _, r = U.preprocess_u8(torch.from_numpy(g[k + "_src"][None]).cuda(), return_resized=True)
+        assert np.array_equal(r[0].cpu().numpy(), g[k + "_resized"]), k
+
+
+def test_maxpool(U):
+    x = bf(torch.randn(2, 64, 28, 36))
+    assert torch.equal(nchw(U.maxpool2x2(nhwc(x))), F.max_pool2d(x, 2))

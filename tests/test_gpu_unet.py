@@ -1,0 +1,161 @@
+"""GPU (B200): the whole hot path through the drop-in module / executor against the oracle and the
+golden fixtures generated from the reference listing."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL_BF16 = 2e-2   # BASELINE.json north_star: logits within 2e-2 abs on random-init weights (bf16 path)
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import unet_lane_detection_b200 as mod
+    return mod
+
+
+def make_pair(U, feats, gain=1.0, seed=0):
+    torch.manual_seed(seed)
+    ref = O.UNetOracle(3, 1, feats).eval()
+    O.randomize_bn_(ref, seed=1)
+    if gain != 1.0:
+        O.scale_head_(ref, gain)
+    net = U.UNet(3, 1, feats)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda().eval()
+
+
+def test_golden_logits_from_reference_listing(U, golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    for tag, feats in (("f64x2", [64, 128]), ("default", [64, 128, 256, 512])):
+        _, net = make_pair(U, feats, gain=40.0)
+        x = torch.from_numpy(g[f"{tag}_x"])
+        with torch.no_grad():
+            y = net(x.cuda()).cpu()
+        ref = torch.from_numpy(g[f"{tag}_logits"])
+        assert y.shape == ref.shape
+        # head gain 40 makes |logit| ~ O(1): tolerance is relative to the logit range here
+        assert (y - ref).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, ref.abs().max().item())
+
+
+def test_full_size_random_init_parity(U):
+    """configs[0] weights (seed-0 default init, BN randomised) at 224x224: the north_star gate."""
+    ref, net = make_pair(U, [64, 128, 256, 512])
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert y.shape == (2, 1, 224, 224) and y.dtype == torch.float32
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_BF16
+    # mask agreement: random-init logits hug zero, so report against the bf16 noise floor of the oracle itself
+    yem = O.forward_bf16_emulated(ref, x)
+    floor = O.mask_agreement(yem, y32)
+    got = O.mask_agreement(y, y32)
+    assert got >= min(0.999, floor - 0.002), f"mask agreement {got:.5f} (bf16-emulated oracle floor {floor:.5f})"
+    band = 4 * (yem - y32).abs().max().item()
+    assert O.mask_agreement(y, y32, band=band) >= 0.9999
+
+
+def test_full_size_realistic_logit_scale(U):
+    """Same weights with the head scaled so |logit| ~ O(1): >= 99.9 % thresholded-mask agreement (north_star)."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(99))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, y32.abs().max().item())
+    assert O.mask_agreement(y, y32) >= 0.999
+
+
+def test_pipeline_matches_reference_pipeline(U):
+    """uint8 camera frames -> preprocess -> net -> sigmoid -> >thr*255, vs src/unet.py:24-72 restated in the oracle."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (3, 480, 640, 3), dtype=np.uint8)
+    logits, probs, mask = net.predict_mask(torch.from_numpy(frames).cuda(), threshold=0.5, swap_rb=True,
+                                           want=("logits", "probs", "mask"))
+    pre = np.concatenate([O.preprocess_oracle(f, (224, 224), swap_rb=True)[0] for f in frames])
+    with torch.no_grad():
+        z = ref(torch.from_numpy(O.normalize_oracle(pre)))
+    assert (logits.cpu() - z[:, 0]).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, z.abs().max().item())
+    want = np.stack([O.postprocess_oracle([z[i:i + 1].numpy()], (224, 224), 0.5) for i in range(3)])
+    agree = (mask.cpu().numpy() == want).mean()
+    assert agree >= 0.999, agree
+    # the mask is bit-exactly the reference post-process applied to the kernel's own probabilities
+    own = np.stack([O.postprocess_oracle([probs[i:i + 1, None].cpu().numpy()], (224, 224), 0.5) for i in range(3)])
+    assert np.array_equal(mask.cpu().numpy(), own)
+    assert set(np.unique(mask.cpu().numpy())) <= {0, 255}
+
+
+def test_chunking_and_permutation_invariance(U):
+    """Size-independent properties at a larger batch: results do not depend on how the batch is chunked or ordered."""
+    _, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    frames = torch.randint(0, 256, (21, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(7)).cuda()
+    net.b200_chunk = 32
+    l_a, _, m_a = net.predict_mask(frames, want=("logits", "mask"))
+    net.b200_chunk = 8                      # 21 = 8 + 8 + 5: ragged last chunk
+    l_b, _, m_b = net.predict_mask(frames, want=("logits", "mask"))
+    assert torch.equal(l_a, l_b) and torch.equal(m_a, m_b)
+    perm = torch.randperm(21, generator=torch.Generator().manual_seed(8)).cuda()
+    l_c, _, _ = net.predict_mask(frames[perm].contiguous(), want=("logits",))
+    assert torch.equal(l_c, l_b[perm])
+    net.b200_chunk = 32
+
+
+def test_batch_one_and_weight_updates(U):
+    ref, net = make_pair(U, [64, 128], gain=40.0)
+    x = torch.randn(1, 3, 32, 32)
+    with torch.no_grad():
+        y0 = net(x.cuda()).cpu()
+        assert (y0 - ref(x)).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, ref(x).abs().max().item())
+        # in-place parameter updates (optimizer.step / load_state_dict) must invalidate the packed weights
+        ref.output.bias.add_(1.0)
+        net.load_state_dict(ref.state_dict())
+        y1 = net(x.cuda()).cpu()
+    assert (y1 - y0 - 1.0).abs().max().item() < 1e-5
+
+
+def test_camera_resolution_config5_smoke(U):
+    """configs[4] geometry (480x640) on a small batch: same kernels, different tensor maps."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    x = torch.randn(1, 3, 480, 640, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, y32.abs().max().item())
+
+
+def test_executor_contract(U, tmp_path):
+    """RKNN_model_container contract (src/py_utils/rknn_executor.py:26-42): list in, list of ndarray out, release()."""
+    ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    path = tmp_path / "best_model.pth"
+    torch.save({"epoch": 1, "model_state_dict": ref.state_dict()}, path)
+    box = U.B200_model_container(str(path))
+    rng = np.random.default_rng(3)
+    frame = rng.integers(0, 256, (1, 224, 224, 3), dtype=np.uint8)
+    out = box.run([frame])
+    assert isinstance(out, list) and out[0].shape == (1, 1, 224, 224) and out[0].dtype == np.float32
+    assert out[0].min() >= 0.0 and out[0].max() <= 1.0                 # probabilities: sigmoid is inside the graph
+    assert np.array_equal(box.run(frame)[0], out[0])                    # bare array is wrapped (rknn_executor.py:31-34)
+    with torch.no_grad():
+        z = ref(torch.from_numpy(O.normalize_oracle(frame)))
+    mask_ref = O.postprocess_oracle([torch.sigmoid(z).numpy()], (224, 224), 0.5)
+    mask_got = O.postprocess_oracle(out, (224, 224), 0.5)               # the caller's own post-process on our output
+    assert (mask_ref == mask_got).mean() >= 0.999
+    box.release()
+    assert box.run([frame]) == []                                       # run after release (rknn_executor.py:27-29)
+
+
+def test_infer_host_equals_device_path(U):
+    _, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    frames = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
+    _, _, m_dev = net.predict_mask(frames.cuda(), want=("mask",))
+    m_host = torch.empty(5, 224, 224, dtype=torch.uint8).pin_memory()
+    net.infer_host(frames.pin_memory(), mask_out=m_host)
+    assert torch.equal(m_host, m_dev.cpu())

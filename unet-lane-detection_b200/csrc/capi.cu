@@ -438,8 +438,8 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
 
 int unet_b200_forward_launches(const unet_b200_plan* p) { return p ? (int)p->layers.size() + 1 : 0; }
 
-int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
-                      float threshold, void* stream) {
+static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
+                        float threshold, cudaStream_t st, std::vector<cudaEvent_t>* ev) {
   if (p == nullptr || x == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (p->ws == nullptr) return fail(UB_ERR_STATE, "plan is not bound");
   if (batch < 1 || batch > p->Bc) return fail(UB_ERR_ARG, "batch %d outside [1,%d]", batch, p->Bc);
@@ -447,7 +447,8 @@ int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits
   for (const Layer& l : p->layers) {
     if (!l.set) return fail(UB_ERR_STATE, "layer weights not set");
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t ei = 0;
+  if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
   for (Layer& l : p->layers) {
     const float* bias = reinterpret_cast<const float*>(p->wt + l.b_off);
     void* out = p->ws + p->bufs[l.out].off;
@@ -464,6 +465,7 @@ int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits
       int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, st);
       if (rc != UB_OK) return rc;
     }
+    if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
   }
   const Buf& fb = p->bufs[p->final_buf];
   const size_t npix = (size_t)batch * fb.H * fb.W;
@@ -471,6 +473,50 @@ int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits
       reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
       p->head_bias, npix, fb.C, logits, probs, mask, threshold);
   UB_CUDA(cudaGetLastError());
+  if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
+  return UB_OK;
+}
+
+int unet_b200_forward(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
+                      float threshold, void* stream) {
+  return forward_impl(p, x, batch, logits, probs, mask, threshold, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int unet_b200_forward_profile(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
+                              float threshold, void* stream, float* ms_out, int n_out) {
+  if (p == nullptr || ms_out == nullptr) return fail(UB_ERR_ARG, "null argument");
+  const int n = (int)p->layers.size() + 1;
+  if (n_out < n) return fail(UB_ERR_ARG, "ms_out holds %d entries, need %d", n_out, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) UB_CUDA(cudaEventCreate(&e));
+  int rc = forward_impl(p, x, batch, logits, probs, mask, threshold, st, &ev);
+  if (rc == UB_OK) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(UB_ERR_CUDA, "profile sync failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == UB_OK) {
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int unet_b200_plan_num_layers(const unet_b200_plan* p) { return p ? (int)p->layers.size() + 1 : 0; }
+
+int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8) {
+  if (p == nullptr || info8 == nullptr) return fail(UB_ERR_ARG, "null argument");
+  const int n = (int)p->layers.size();
+  if (idx < 0 || idx > n) return fail(UB_ERR_ARG, "layer index %d out of range", idx);
+  if (idx == n) {  // head
+    const Buf& fb = p->bufs[p->final_buf];
+    const int v[8] = {3, fb.H, fb.W, fb.C, 1, 1, 0, 0};
+    memcpy(info8, v, sizeof(v));
+    return UB_OK;
+  }
+  const Layer& l = p->layers[idx];
+  const int v[8] = {(int)l.kind, l.H, l.W, l.C0 + l.C1, l.Cout, l.kind == L_CONVT ? 1 : 9, l.block_n, l.pool >= 0};
+  memcpy(info8, v, sizeof(v));
   return UB_OK;
 }
 

@@ -171,3 +171,58 @@ class UNet(nn.Module):
                                           int(swap_rb), f3(MEAN_255), f3(STD_255), x4.data_ptr(), None, st))
         self.gpu_launches += 1
         return self.forward_nhwc4(x4, threshold=threshold, want=want)
+
+    # ------------------------------------------------------------------ host-buffer entry (executor path)
+    def infer_host(self, frames_host, threshold=0.5, swap_rb=False, size=(224, 224), mask_out=None, probs_out=None,
+                   logits_out=None):
+        """Reference-facing call with HOST buffers (RKNN_model_container.run contract): uint8 frames
+        [B,Hs,Ws,3] on the host (pinned for full PCIe speed) -> host outputs. H2D copy, preprocess, U-Net,
+        mask and D2H copy all go through unet_b200_infer_u8_host; returns after the results are on the host."""
+        if frames_host.is_cuda or frames_host.dtype != torch.uint8 or not frames_host.is_contiguous():
+            raise ValueError("frames_host must be a contiguous uint8 CPU tensor [B,Hs,Ws,3]")
+        B, Hs, Ws, _ = frames_host.shape
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("UNet (B200): model parameters are not on a CUDA device (no CPU fallback)")
+        eng = self._engine(dev, size[0], size[1], B)
+        skey = (Hs, Ws)
+        if getattr(eng, "staging_key", None) != skey:
+            eng.staging = torch.empty(lib.unet_b200_infer_staging_bytes(eng.handle, Hs, Ws), dtype=torch.uint8, device=dev)
+            eng.staging_key = skey
+        st = torch.cuda.current_stream().cuda_stream
+        npix = size[0] * size[1]
+        for b0 in range(0, B, eng.cap):
+            n = min(eng.cap, B - b0)
+            check(lib.unet_b200_infer_u8_host(
+                eng.handle, eng.staging.data_ptr(), frames_host[b0:b0 + n].data_ptr(), n, Hs, Ws, int(swap_rb),
+                f3(MEAN_255), f3(STD_255), float(threshold),
+                None if logits_out is None else logits_out.data_ptr() + b0 * npix * 4,
+                None if probs_out is None else probs_out.data_ptr() + b0 * npix * 4,
+                None if mask_out is None else mask_out.data_ptr() + b0 * npix, st))
+            self.gpu_launches += eng.launches + 1
+        return mask_out, probs_out, logits_out
+
+    def profile_layers(self, x4):
+        """Per-kernel durations (ms, CUDA events on the current stream) of one pass over x4 [B<=chunk,H,W,4],
+        with each kernel's shape info and algorithmic FLOPs. Used by bench.py for the roofline line."""
+        B, H, W, _ = x4.shape
+        eng = self._engine(x4.device, H, W, B)
+        if B > eng.cap:
+            raise ValueError(f"profile_layers takes at most one chunk ({eng.cap} frames)")
+        n = lib.unet_b200_plan_num_layers(eng.handle)
+        ms = (C.c_float * n)()
+        mask = torch.empty(B, H, W, dtype=torch.uint8, device=x4.device)
+        check(lib.unet_b200_forward_profile(eng.handle, x4.data_ptr(), B, None, None, mask.data_ptr(), 0.5,
+                                            torch.cuda.current_stream().cuda_stream, ms, n))
+        rows = []
+        kinds = {0: "stem", 1: "conv3x3", 2: "convT2x2", 3: "head"}
+        for i in range(n):
+            info = (C.c_int * 8)()
+            check(lib.unet_b200_plan_layer_info(eng.handle, i, info))
+            kind, h, w, cin, cout, taps, block_n, pool = list(info)
+            mult = 4 if kind == 2 else 1
+            cin_eff = self.in_channels if kind == 0 else cin
+            flops = 2.0 * B * h * w * cout * mult * taps * cin_eff
+            rows.append({"kind": kinds[kind], "H": h, "W": w, "Cin": cin, "Cout": cout, "block_n": block_n,
+                         "fused_pool": bool(pool), "ms": float(ms[i]), "flops": flops})
+        return rows
