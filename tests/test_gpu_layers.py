@@ -120,7 +120,7 @@ def test_stem_conv(U, cin, cout, H, W):
     s = ga / torch.sqrt(va + 1e-5)
     ref = F.relu(F.conv2d(x, bf(w * s[:, None, None, None]), be - mu * s, padding=1))
     x4 = U.nchw_to_nhwc4(x.cuda())
-    assert x4[..., cin:].abs().max().item() == 0.0
+    assert cin == 4 or x4[..., cin:].abs().max().item() == 0.0
     close(nchw(U.stem_conv(x4, ws, bias, cin)), bf(ref), 1e-2)
 
 
