@@ -84,9 +84,16 @@ int unet_b200_forward_profile(unet_b200_plan* p, const void* x_nhwc4_dev, int ba
                               float* probs_dev, uint8_t* mask_dev, float threshold, void* stream, float* ms_out,
                               int n_out);
 int unet_b200_plan_num_layers(const unet_b200_plan* p);
-/* info8 = {kind (0 stem, 1 conv3x3, 2 convT2x2, 3 head), H, W, Cin, Cout, taps, BLOCK_N, fused_pool} of kernel idx;
+/* info8 = {kind (0 stem, 1 conv3x3, 2 convT2x2, 3 head), H, W, Cin, Cout, taps, BLOCK_N,
+ * flags (1 fused pool | 2 halo kernel | 4 fused head)} of kernel idx;
  * H, W are the GEMM-row grid (input resolution). */
 int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
+
+/* Process-wide kernel-selection switches, read when a plan is created / a single-layer call is made:
+ *   "halo" (default 1)      3x3 convs with Cout 64/128 and W % 8 == 0 run on the halo-patch kernel
+ *   "fuse_head" (default 1) the 1x1 head + sigmoid + mask run in the last conv's epilogue when it is a halo layer
+ * Both paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
+int unet_b200_set_option(const char* name, int value);
 
 /* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary). */
 int unet_b200_nchw_to_nhwc4(const float* x_dev, int batch, int C, int H, int W, void* y_nhwc4_dev, void* stream);

@@ -163,3 +163,23 @@ def test_preprocess_golden_images(U, golden_dir):
 def test_maxpool(U):
     x = bf(torch.randn(2, 64, 28, 36))
     assert torch.equal(nchw(U.maxpool2x2(nhwc(x))), F.max_pool2d(x, 2))
+
+
+def _set(U, name, v):
+    from unet_lane_detection_b200._lib import check, lib
+    check(lib.unet_b200_set_option(name.encode(), v))
+
+
+@pytest.mark.parametrize("halo", [0, 1])
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,pool", [(2, 224, 224, 64, 0, 64, True), (1, 224, 224, 64, 64, 64, False),
+                                                   (2, 112, 112, 64, 0, 128, False), (2, 112, 112, 128, 0, 128, True),
+                                                   (1, 112, 112, 128, 128, 128, False), (3, 24, 40, 64, 0, 64, True),
+                                                   (1, 480, 640, 64, 0, 64, True), (1, 120, 160, 128, 0, 128, True)])
+def test_conv3x3_halo_and_per_tap_kernels(U, halo, B, H, W, C0, C1, Cout, pool):
+    """Both 3x3 kernels (halo patch + shifted descriptors / one TMA box per tap) on the shapes the plan routes to the
+    halo kernel, including resident (<= 2 channel blocks) and streamed weights, partial tiles (H % 16 != 0)."""
+    _set(U, "halo", halo)
+    try:
+        conv_case(U, B, H, W, C0, C1, Cout, pool=pool, seed=halo + 3)
+    finally:
+        _set(U, "halo", 1)

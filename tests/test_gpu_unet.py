@@ -159,3 +159,31 @@ def test_infer_host_equals_device_path(U):
     m_host = torch.empty(5, 224, 224, dtype=torch.uint8).pin_memory()
     net.infer_host(frames.pin_memory(), mask_out=m_host)
     assert torch.equal(m_host, m_dev.cpu())
+
+
+def test_fused_head_and_halo_switches_agree(U):
+    """The fused (1x1 head in the last conv's epilogue) and unfused paths, and the two 3x3 kernels, give the same net."""
+    from unet_lane_detection_b200._lib import check, lib
+    ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    frames = torch.randint(0, 256, (3, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).cuda()
+    outs = {}
+    try:
+        for halo, fuse in ((1, 1), (1, 0), (0, 0)):
+            check(lib.unet_b200_set_option(b"halo", halo))
+            check(lib.unet_b200_set_option(b"fuse_head", fuse))
+            net = U.UNet(3, 1, [64, 128, 256, 512])
+            net.load_state_dict(ref.state_dict())
+            net = net.cuda().eval()
+            outs[(halo, fuse)] = net.predict_mask(frames, want=("logits", "probs", "mask"))
+    finally:
+        check(lib.unet_b200_set_option(b"halo", 1))
+        check(lib.unet_b200_set_option(b"fuse_head", 1))
+    la, pa, ma = outs[(1, 1)]
+    lb, pb, mb = outs[(1, 0)]
+    lc, _, mc = outs[(0, 0)]
+    assert (la - lb).abs().max().item() < 1e-4          # same activations, different summation order in the head
+    assert (ma != mb).float().mean().item() < 1e-4
+    assert (la - lc).abs().max().item() < 2e-2 * max(1.0, lc.abs().max().item())   # different K order in the convs
+    assert (ma != mc).float().mean().item() < 2e-3
+    own = (pa > 0.5).to(torch.uint8) * 255
+    assert torch.equal(ma, own)

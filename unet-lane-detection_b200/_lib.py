@@ -37,6 +37,7 @@ _SIGS = {
     "unet_b200_forward_profile": (i32, [vp, vp, i32, vp, vp, vp, f32, vp, C.POINTER(f32), i32]),
     "unet_b200_plan_num_layers": (i32, [vp]),
     "unet_b200_plan_layer_info": (i32, [vp, i32, C.POINTER(i32)]),
+    "unet_b200_set_option": (i32, [C.c_char_p, i32]),
     "unet_b200_nchw_to_nhwc4": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_preprocess_u8": (i32, [vp, i32, i32, i32, sz, sz, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, vp]),
     "unet_b200_infer_staging_bytes": (sz, [vp, i32, i32]),

@@ -8,6 +8,7 @@
 
 #include "../../include/unet_b200.h"
 #include "aux_kernels.cuh"
+#include "conv_halo.cuh"
 #include "conv_umma.cuh"
 
 namespace {
@@ -81,6 +82,29 @@ int make_w_map(CUtensorMap* m, const void* base, int N, int K, int block_n) {
   return UB_OK;
 }
 
+// Halo'd patch map for conv_halo.cuh: same tensor, box (64 ch, 10 px, 18 rows, 1 image).
+int make_halo_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bc};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, 10, 18, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled(halo B=%d H=%d W=%d C=%d) -> %d", Bc, H, W, C, (int)r);
+  return UB_OK;
+}
+
+int g_opt_halo = 1;       // use conv_halo_kernel where eligible
+int g_opt_fuse_head = 1;  // fold the 1x1 head into the last conv's epilogue where eligible
+
+bool halo_eligible(int H, int W, int C0, int C1, int Cout) {
+  (void)H;
+  return g_opt_halo && (W % 8 == 0) && (Cout == 64 || Cout == 128) && (C0 % 64 == 0) && (C1 % 64 == 0);
+}
+
 int pow2_divisor(int v, int cap) {
   int p = 1;
   while (p * 2 <= cap && v % (p * 2) == 0) p *= 2;
@@ -128,6 +152,36 @@ int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   return UB_OK;
 }
 
+int g_hattr_done[2] = {0, 0};
+
+template <int BN>
+int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, ub::HaloArgs args, int slot,
+                  cudaStream_t st) {
+  using Cfg = ub::HaloCfg<BN>;
+  if (!g_hattr_done[slot]) {
+    UB_CUDA(cudaFuncSetAttribute(ub::conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+    g_hattr_done[slot] = 1;
+  }
+  args.resident = (3 * (args.kc0 + args.kc1) <= Cfg::B_STAGES) ? 1 : 0;
+  const int total = args.tiles_w * args.tiles_h * args.B;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  ub::conv_halo_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, w, args);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                const ub::HaloArgs& args, cudaStream_t st) {
+  if (g_num_sms == 0) {
+    int rc = device_check();
+    if (rc != UB_OK) return rc;
+  }
+  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, args, 0, st);
+  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, args, 1, st);
+  return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
+}
+
 int launch_conv(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                 const ub::ConvArgs& args, cudaStream_t st) {
   if (g_num_sms == 0) {
@@ -156,6 +210,8 @@ struct Layer {
   size_t w_off, b_off;      // offsets into the weight buffer
   int block_n, TW, TH, TB;
   bool set;
+  bool halo;       // runs on conv_halo_kernel
+  bool fuse_head;  // last conv: 1x1 head + sigmoid + mask evaluated in its epilogue
   CUtensorMap mA0, mA1, mW;
 };
 
@@ -224,6 +280,8 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   if (kind != L_STEM) {
     pick_tile(H, W, &l.TW, &l.TH, &l.TB);
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
+    l.halo = (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);
+    if (l.halo) l.block_n = Cout;
   }
   p->layers.push_back(l);
   if (kind == L_CONVT) {
@@ -231,6 +289,25 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   } else {
     p->conv_ids.push_back((int)p->layers.size() - 1);
   }
+}
+
+ub::HaloArgs halo_args(const Layer& l, int batch, const float* bias, void* out, void* pool) {
+  ub::HaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = batch;
+  a.H = l.H;
+  a.W = l.W;
+  a.tiles_w = (l.W + 7) / 8;
+  a.tiles_h = (l.H + 15) / 16;
+  a.kc0 = l.C0 / 64;
+  a.kc1 = l.C1 / 64;
+  a.epi = ub::HEPI_STORE;
+  a.relu = l.relu;
+  a.Cout = l.Cout;
+  a.bias = bias;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  return a;
 }
 
 ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bias, void* out, void* pool) {
@@ -348,6 +425,10 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
     cin = f;
   }
   p->final_buf = cur;
+  {
+    Layer& last = p->layers.back();
+    last.fuse_head = g_opt_fuse_head && last.kind == L_CONV && last.halo;
+  }
   p->head_w_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)features[0] * 4, 256);
   *out = p;
@@ -371,11 +452,13 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
   for (Layer& l : p->layers) {
     if (l.kind == L_STEM) continue;
     const Buf& b0 = p->bufs[l.in0];
-    rc = make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0, l.TW, l.TH, l.TB);
+    rc = l.halo ? make_halo_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0)
+                : make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0, l.TW, l.TH, l.TB);
     if (rc != UB_OK) return rc;
     if (l.C1 > 0) {
       const Buf& b1 = p->bufs[l.in1];
-      rc = make_act_map(&l.mA1, p->ws + b1.off, p->Bc, l.H, l.W, l.C1, l.TW, l.TH, l.TB);
+      rc = l.halo ? make_halo_map(&l.mA1, p->ws + b1.off, p->Bc, l.H, l.W, l.C1)
+                  : make_act_map(&l.mA1, p->ws + b1.off, p->Bc, l.H, l.W, l.C1, l.TW, l.TH, l.TB);
     } else {
       l.mA1 = l.mA0;
     }
@@ -436,7 +519,22 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
   return UB_OK;
 }
 
-int unet_b200_forward_launches(const unet_b200_plan* p) { return p ? (int)p->layers.size() + 1 : 0; }
+int unet_b200_forward_launches(const unet_b200_plan* p) {
+  if (p == nullptr) return 0;
+  return (int)p->layers.size() + (p->layers.back().fuse_head ? 0 : 1);
+}
+
+int unet_b200_set_option(const char* name, int value) {
+  if (name == nullptr) return fail(UB_ERR_ARG, "null option name");
+  if (strcmp(name, "halo") == 0) {
+    g_opt_halo = value;
+  } else if (strcmp(name, "fuse_head") == 0) {
+    g_opt_fuse_head = value;
+  } else {
+    return fail(UB_ERR_ARG, "unknown option '%s'", name);
+  }
+  return UB_OK;
+}
 
 static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
                         float threshold, cudaStream_t st, std::vector<cudaEvent_t>* ev) {
@@ -460,6 +558,19 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
                                                       reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch, l.H,
                                                       l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
       UB_CUDA(cudaGetLastError());
+    } else if (l.halo) {
+      ub::HaloArgs a = halo_args(l, batch, bias, out, pool);
+      if (l.fuse_head) {
+        a.epi = ub::HEPI_HEAD;
+        a.head_w = reinterpret_cast<const float*>(p->wt + p->head_w_off);
+        a.head_b = p->head_bias;
+        a.thr = threshold;
+        a.logits = logits;
+        a.probs = probs;
+        a.mask = mask;
+      }
+      int rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, a, st);
+      if (rc != UB_OK) return rc;
     } else {
       ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, pool);
       int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, st);
@@ -467,12 +578,14 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     }
     if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
   }
-  const Buf& fb = p->bufs[p->final_buf];
-  const size_t npix = (size_t)batch * fb.H * fb.W;
-  ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
-      p->head_bias, npix, fb.C, logits, probs, mask, threshold);
-  UB_CUDA(cudaGetLastError());
+  if (!p->layers.back().fuse_head) {
+    const Buf& fb = p->bufs[p->final_buf];
+    const size_t npix = (size_t)batch * fb.H * fb.W;
+    ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
+        p->head_bias, npix, fb.C, logits, probs, mask, threshold);
+    UB_CUDA(cudaGetLastError());
+  }
   if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
   return UB_OK;
 }
@@ -515,7 +628,8 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8) {
     return UB_OK;
   }
   const Layer& l = p->layers[idx];
-  const int v[8] = {(int)l.kind, l.H, l.W, l.C0 + l.C1, l.Cout, l.kind == L_CONVT ? 1 : 9, l.block_n, l.pool >= 0};
+  const int v[8] = {(int)l.kind, l.H, l.W, l.C0 + l.C1, l.Cout, l.kind == L_CONVT ? 1 : 9, l.block_n,
+                    (l.pool >= 0 ? 1 : 0) | (l.halo ? 2 : 0) | (l.fuse_head ? 4 : 0)};
   memcpy(info8, v, sizeof(v));
   return UB_OK;
 }
@@ -625,6 +739,22 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
   l.relu = relu;
   pick_tile(H, W, &l.TW, &l.TH, &l.TB);
   l.block_n = pick_block_n(Cout);
+  if (halo_eligible(H, W, C0, C1, Cout)) {
+    l.halo = true;
+    l.block_n = Cout;
+    rc = make_halo_map(&l.mA0, x0, B, H, W, C0);
+    if (rc != UB_OK) return rc;
+    if (C1 > 0) {
+      rc = make_halo_map(&l.mA1, x1, B, H, W, C1);
+      if (rc != UB_OK) return rc;
+    } else {
+      l.mA1 = l.mA0;
+    }
+    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
+    if (rc != UB_OK) return rc;
+    ub::HaloArgs ha = halo_args(l, B, bias, y, pool);
+    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, ha, static_cast<cudaStream_t>(stream));
+  }
   if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
   rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
   if (rc != UB_OK) return rc;

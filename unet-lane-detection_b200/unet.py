@@ -224,5 +224,5 @@ class UNet(nn.Module):
             cin_eff = self.in_channels if kind == 0 else cin
             flops = 2.0 * B * h * w * cout * mult * taps * cin_eff
             rows.append({"kind": kinds[kind], "H": h, "W": w, "Cin": cin, "Cout": cout, "block_n": block_n,
-                         "fused_pool": bool(pool), "ms": float(ms[i]), "flops": flops})
+                         "fused_pool": bool(pool & 1), "halo": bool(pool & 2), "fused_head": bool(pool & 4), "ms": float(ms[i]), "flops": flops})
         return rows
