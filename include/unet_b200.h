@@ -92,6 +92,7 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
 /* Process-wide kernel-selection switches, read when a plan is created / a single-layer call is made:
  *   "halo" (default 1)      3x3 convs with Cout 64/128 and W % 8 == 0 run on the halo-patch kernel
  *   "fuse_head" (default 1) the 1x1 head + sigmoid + mask run in the last conv's epilogue when it is a halo layer
+ *   "stem_umma" (default 1) the Cin<=4 -> 64 stem runs on tensor cores (in-kernel im2col) instead of the FP32 pipes
  * Both paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
 int unet_b200_set_option(const char* name, int value);
 
@@ -137,6 +138,12 @@ int unet_b200_pack_stem(const float* w_dev, const float* gamma_dev, const float*
                         void* stream);
 int unet_b200_stem_conv(const void* x_nhwc4_dev, const float* ws_dev, const float* bias_dev, int B, int H, int W,
                         int Cin, int Cout, int relu, void* y_dev, void* stream);
+/* Tensor-core stem (Cout == 64): wp bf16 [64][64] with k = tap*4 + ci from pack_stem_tc. */
+int unet_b200_pack_stem_tc(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* mean_dev,
+                           const float* var_dev, float eps, int Cout, int Cin, void* wp_dev, float* bias_dev,
+                           void* stream);
+int unet_b200_stem_conv_tc(const void* x_nhwc4_dev, const void* wp_dev, const float* bias_dev, int B, int H, int W,
+                           int relu, void* y_dev, void* stream);
 /* 1x1 head on bf16 NHWC [npix][C]: w fp32 [C] (device), bias by value. Outputs optional. */
 int unet_b200_head(const void* x_dev, const float* w_dev, float bias, size_t npix, int C, float* logits_dev,
                    float* probs_dev, uint8_t* mask_dev, float threshold, void* stream);

@@ -183,3 +183,18 @@ def test_conv3x3_halo_and_per_tap_kernels(U, halo, B, H, W, C0, C1, Cout, pool):
         conv_case(U, B, H, W, C0, C1, Cout, pool=pool, seed=halo + 3)
     finally:
         _set(U, "halo", 1)
+
+
+@pytest.mark.parametrize("cin,B,H,W", [(3, 2, 224, 224), (3, 1, 32, 48), (1, 3, 16, 16), (4, 1, 24, 40), (3, 1, 480, 640), (3, 5, 28, 36)])
+def test_stem_conv_tensor_core(U, cin, B, H, W):
+    """Tensor-core stem (in-kernel im2col, K = 36 padded to 48) vs the oracle; partial tiles when H % 16 or W % 8 != 0."""
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn(B, cin, H, W, generator=g))
+    w = torch.randn(64, cin, 3, 3, generator=g) / 5
+    ga, be = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    mu, va = torch.randn(64, generator=g) * 0.1, torch.rand(64, generator=g) + 0.5
+    wp, bias = U.pack_stem_tc(w.cuda(), (ga.cuda(), be.cuda(), mu.cuda(), va.cuda(), 1e-5))
+    s = ga / torch.sqrt(va + 1e-5)
+    ref = F.relu(F.conv2d(x, bf(w * s[:, None, None, None]), be - mu * s, padding=1))
+    y = U.stem_conv_tc(U.nchw_to_nhwc4(x.cuda()), wp, bias)
+    close(nchw(y), bf(ref), 1e-2)

@@ -8,8 +8,8 @@ C ABI in include/unet_b200.h) and raise if it is missing - there is no CPU fallb
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library has not been built)
 from .ops import (  # noqa: F401
-    conv3x3, convT2x2, head, maxpool2x2, nchw_to_nhwc4, pack_conv3x3, pack_convT2x2, pack_stem, preprocess_u8,
-    stem_conv,
+    conv3x3, convT2x2, head, maxpool2x2, nchw_to_nhwc4, pack_conv3x3, pack_convT2x2, pack_stem, pack_stem_tc, preprocess_u8,
+    stem_conv, stem_conv_tc,
 )
 from .unet import UNet  # noqa: F401
 from .executor import B200_model_container, B200LaneInference  # noqa: F401

@@ -48,6 +48,8 @@ _SIGS = {
     "unet_b200_pack_convT2x2": (i32, [vp, i32, i32, vp, vp]),
     "unet_b200_pack_stem": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
     "unet_b200_stem_conv": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_pack_stem_tc": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
+    "unet_b200_stem_conv_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_head": (i32, [vp, vp, f32, sz, i32, vp, vp, vp, f32, vp]),
     "unet_b200_maxpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
 }

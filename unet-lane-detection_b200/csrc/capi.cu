@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "conv_halo.cuh"
 #include "conv_umma.cuh"
+#include "stem_umma.cuh"
 
 namespace {
 
@@ -97,8 +98,71 @@ int make_halo_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C)
   return UB_OK;
 }
 
+// NHWC bf16 [Bc][H][W][C] viewed as (C, W, H, B) with a (64, bw, bh, 1) box: TMA-store target of the staged epilogues.
+int make_box_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bc};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled(box B=%d H=%d W=%d C=%d %dx%d) -> %d", Bc, H, W, C, bw, bh, (int)r);
+  return UB_OK;
+}
+
+// Tile-box (64, TW, TH, TB) store view of an NHWC bf16 tensor with arbitrary pixel strides (in elements):
+// used for conv outputs, pooled outputs and the four (dy,dx) quads of a ConvT output.
+int make_tile_store_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C, size_t sw, size_t sh, size_t sb,
+                        int TW, int TH, int TB) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bc};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)(TB < Bc ? TB : Bc)};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled(store B=%d H=%d W=%d C=%d) -> %d", Bc, H, W, C, (int)r);
+  return UB_OK;
+}
+
+struct Layer;
+int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc);
+
+// Shared-memory carve-up of conv_halo_kernel: prefer resident weights, then deeper patch / staging rings.
+bool halo_smem_plan(int block_n, int kc, int pool, int head, ub::HaloArgs* a) {
+  const int need = 9 * kc;
+  static const int cand[5][2] = {{4, 2}, {3, 2}, {3, 1}, {2, 2}, {2, 1}};  // (a_stages, n_stg)
+  if (need <= ub::HaloCfg::MAX_B) {
+    for (const auto& c : cand) {
+      const int ns = head ? 0 : c[1];
+      if (ub::halo_smem_bytes(block_n, c[0], need, ns, pool) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 1; a->a_stages = c[0]; a->b_stages = need; a->n_stg = ns;
+        return true;
+      }
+    }
+  }
+  // streamed weights: keep three patch stages, one staging tile, and give the weight ring whatever is left
+  static const int scand[4][2] = {{3, 1}, {3, 2}, {2, 1}, {2, 2}};
+  for (const auto& c : scand) {
+    const int ns = head ? 0 : c[1];
+    for (int b = 12; b >= 4; --b) {
+      if (ub::halo_smem_bytes(block_n, c[0], b, ns, pool) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 0; a->a_stages = c[0]; a->b_stages = b; a->n_stg = ns;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
 int g_opt_halo = 1;       // use conv_halo_kernel where eligible
 int g_opt_fuse_head = 1;  // fold the 1x1 head into the last conv's epilogue where eligible
+int g_opt_stem_umma = 1;  // run the Cout == 64 stem on tensor cores (stem_umma.cuh) instead of the FP32-pipe kernel
 
 bool halo_eligible(int H, int W, int C0, int C1, int Cout) {
   (void)H;
@@ -124,6 +188,7 @@ int g_num_sms = 0;
 int g_attr_done[3] = {0, 0, 0};
 
 int device_check() {
+  if (g_num_sms > 0) return UB_OK;  // cudaGetDeviceProperties is slow; the process is pinned to one device
   int dev = 0;
   UB_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -137,17 +202,20 @@ int device_check() {
 }
 
 template <int BN>
-int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const ub::ConvArgs& args,
-                  int slot, cudaStream_t st) {
+int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap* mo,
+                  const ub::ConvArgs& args, int slot, cudaStream_t st) {
   using Cfg = ub::ConvCfg<BN>;
   if (!g_attr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
+                                 Cfg::SMEM_LIMIT));
     g_attr_done[slot] = 1;
   }
+  ub::ConvArgs args2 = args;
+  Cfg::plan(args.taps, args.pool, &args2.stages, &args2.n_stg);
+  const int smem = Cfg::smem_bytes(args2.stages, args2.n_stg, args2.pool);
   const int total = args.tiles_w * args.tiles_h * args.tiles_b * args.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_umma_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, w, args);
+  ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(a0, a1, w, mo[0], mo[1], mo[2], mo[3], args2);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -155,43 +223,72 @@ int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
 int g_hattr_done[2] = {0, 0};
 
 template <int BN>
-int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, ub::HaloArgs args, int slot,
-                  cudaStream_t st) {
-  using Cfg = ub::HaloCfg<BN>;
+int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
+                  const CUtensorMap& mp, ub::HaloArgs args, int slot, cudaStream_t st) {
   if (!g_hattr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
+                                 ub::HaloCfg::SMEM_LIMIT));
     g_hattr_done[slot] = 1;
   }
-  args.resident = (3 * (args.kc0 + args.kc1) <= Cfg::B_STAGES) ? 1 : 0;
+  if (!halo_smem_plan(BN, args.kc0 + args.kc1, args.pool, args.epi == ub::HEPI_HEAD, &args)) {
+    return fail(UB_ERR_ARG, "no shared-memory plan for halo conv (N=%d, KC=%d)", BN, args.kc0 + args.kc1);
+  }
+  const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, args.n_stg, args.pool);
   const int total = args.tiles_w * args.tiles_h * args.B;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_halo_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(a0, a1, w, args);
+  ub::conv_halo_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, mp, args);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
-int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
-                const ub::HaloArgs& args, cudaStream_t st) {
+int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
+                const CUtensorMap& mp, const ub::HaloArgs& args, cudaStream_t st) {
   if (g_num_sms == 0) {
     int rc = device_check();
     if (rc != UB_OK) return rc;
   }
-  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, args, 0, st);
-  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, args, 1, st);
+  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, mp, args, 0, st);
+  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, mp, args, 1, st);
   return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
 }
 
-int launch_conv(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+int g_sattr_done = 0;
+
+int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x, const float* bias, int B, int H, int W,
+                     int relu, cudaStream_t st) {
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  if (!g_sattr_done) {
+    UB_CUDA(cudaFuncSetAttribute(ub::stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ub::StemCfg::SMEM_BYTES));
+    g_sattr_done = 1;
+  }
+  ub::StemArgs a;
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  a.tiles_w = (W + 7) / 8;
+  a.tiles_h = (H + 15) / 16;
+  a.relu = relu;
+  a.x = reinterpret_cast<const uint2*>(x);
+  a.bias = bias;
+  const int total = a.tiles_w * a.tiles_h * B;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  ub::stem_umma_kernel<<<grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st>>>(mw, mo, a);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int launch_conv(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap* mo,
                 const ub::ConvArgs& args, cudaStream_t st) {
   if (g_num_sms == 0) {
     int rc = device_check();
     if (rc != UB_OK) return rc;
   }
   switch (block_n) {
-    case 64: return launch_conv_t<64>(a0, a1, w, args, 0, st);
-    case 128: return launch_conv_t<128>(a0, a1, w, args, 1, st);
-    case 256: return launch_conv_t<256>(a0, a1, w, args, 2, st);
+    case 64: return launch_conv_t<64>(a0, a1, w, mo, args, 0, st);
+    case 128: return launch_conv_t<128>(a0, a1, w, mo, args, 1, st);
+    case 256: return launch_conv_t<256>(a0, a1, w, mo, args, 2, st);
   }
   return fail(UB_ERR_ARG, "unsupported BLOCK_N %d", block_n);
 }
@@ -212,13 +309,45 @@ struct Layer {
   bool set;
   bool halo;       // runs on conv_halo_kernel
   bool fuse_head;  // last conv: 1x1 head + sigmoid + mask evaluated in its epilogue
+  bool stem_tc;    // stem on tensor cores (Cout == 64)
   CUtensorMap mA0, mA1, mW;
+  CUtensorMap mOut, mPool;  // TMA-store targets (halo layers)
+  CUtensorMap mO[4];        // TMA-store targets of conv_umma_kernel: {out, pool, -, -} or the four ConvT quads
 };
 
 struct Buf {
   int H, W, C;
   size_t off;
 };
+
+// Store views for a conv_umma_kernel layer. Conv: out (+ pooled out). ConvT: quad (dy,dx) of the [B,2H,2W,f] output is
+// the tensor (f, W, H, B) at base + (dy*2W + dx)*f with pixel strides (2f, 4W*f, 4HW*f).
+int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc) {
+  int rc;
+  if (l.kind == L_CONV) {
+    const size_t C = l.Cout;
+    rc = make_tile_store_map(&l.mO[0], out, Bc, l.H, l.W, l.Cout, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+    if (pool != nullptr) {
+      const int Hp = l.H / 2, Wp = l.W / 2;
+      rc = make_tile_store_map(&l.mO[1], pool, Bc, Hp, Wp, l.Cout, C, (size_t)Wp * C, (size_t)Hp * Wp * C, l.TW / 2, l.TH / 2, l.TB);
+      if (rc != UB_OK) return rc;
+    } else {
+      l.mO[1] = l.mO[0];
+    }
+    l.mO[2] = l.mO[0];
+    l.mO[3] = l.mO[0];
+  } else {
+    const size_t f = l.Cout;
+    for (int qd = 0; qd < 4; ++qd) {
+      const int dy = qd >> 1, dx = qd & 1;
+      uint8_t* base = static_cast<uint8_t*>(out) + ((size_t)dy * 2 * l.W + dx) * f * 2;
+      rc = make_tile_store_map(&l.mO[qd], base, Bc, l.H, l.W, l.Cout, 2 * f, (size_t)4 * l.W * f, (size_t)4 * l.H * l.W * f, l.TW, l.TH, l.TB);
+      if (rc != UB_OK) return rc;
+    }
+  }
+  return UB_OK;
+}
 
 }  // namespace
 
@@ -277,6 +406,7 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   }
   l.b_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)Cout * 4, 256);
+  if (kind == L_STEM) l.stem_tc = g_opt_stem_umma && Cout == 64;
   if (kind != L_STEM) {
     pick_tile(H, W, &l.TW, &l.TH, &l.TB);
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
@@ -303,10 +433,10 @@ ub::HaloArgs halo_args(const Layer& l, int batch, const float* bias, void* out, 
   a.kc1 = l.C1 / 64;
   a.epi = ub::HEPI_STORE;
   a.relu = l.relu;
+  a.pool = (pool != nullptr) ? 1 : 0;
   a.Cout = l.Cout;
   a.bias = bias;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out);
-  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  (void)out;
   return a;
 }
 
@@ -331,8 +461,8 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.relu = l.relu;
   a.Cout = l.Cout;
   a.bias = bias;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out);
-  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  a.pool = (pool != nullptr) ? 1 : 0;
+  (void)out;
   return a;
 }
 
@@ -450,7 +580,15 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
   p->ws = static_cast<uint8_t*>(workspace_dev);
   p->wt = static_cast<uint8_t*>(weights_dev);
   for (Layer& l : p->layers) {
-    if (l.kind == L_STEM) continue;
+    if (l.kind == L_STEM) {
+      if (l.stem_tc) {
+        rc = make_w_map(&l.mW, p->wt + l.w_off, 64, 64, 64);
+        if (rc != UB_OK) return rc;
+        rc = make_box_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, 64, 8, 16);
+        if (rc != UB_OK) return rc;
+      }
+      continue;
+    }
     const Buf& b0 = p->bufs[l.in0];
     rc = l.halo ? make_halo_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0)
                 : make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0, l.TW, l.TH, l.TB);
@@ -463,6 +601,22 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
       l.mA1 = l.mA0;
     }
     if (rc != UB_OK) return rc;
+    if (!l.halo) {
+      rc = make_umma_store_maps(l, p->ws + p->bufs[l.out].off, l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr, p->Bc);
+      if (rc != UB_OK) return rc;
+    }
+    if (l.halo) {
+      const Buf& bo = p->bufs[l.out];
+      rc = make_box_map(&l.mOut, p->ws + bo.off, p->Bc, l.H, l.W, l.Cout, 8, 16);
+      if (rc != UB_OK) return rc;
+      if (l.pool >= 0) {
+        const Buf& bp = p->bufs[l.pool];
+        rc = make_box_map(&l.mPool, p->ws + bp.off, p->Bc, l.H / 2, l.W / 2, l.Cout, 4, 8);
+        if (rc != UB_OK) return rc;
+      } else {
+        l.mPool = l.mOut;
+      }
+    }
     if (l.kind == L_CONV) {
       rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.block_n);
     } else {
@@ -481,7 +635,10 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
   Layer& l = p->layers[p->conv_ids[idx]];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* bias = reinterpret_cast<float*>(p->wt + l.b_off);
-  if (l.kind == L_STEM) {
+  if (l.kind == L_STEM && l.stem_tc) {
+    ub::pack_stem_umma_kernel<<<grid_for(64 * l.Cout, 256), 256, 0, st>>>(
+        w, gamma, beta, mean, var, eps, l.Cout, l.C0, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
+  } else if (l.kind == L_STEM) {
     ub::pack_stem_kernel<<<grid_for(36 * l.Cout, 256), 256, 0, st>>>(w, gamma, beta, mean, var, eps, l.Cout, l.C0,
                                                                      reinterpret_cast<float*>(p->wt + l.w_off), bias);
   } else {
@@ -530,6 +687,8 @@ int unet_b200_set_option(const char* name, int value) {
     g_opt_halo = value;
   } else if (strcmp(name, "fuse_head") == 0) {
     g_opt_fuse_head = value;
+  } else if (strcmp(name, "stem_umma") == 0) {
+    g_opt_stem_umma = value;
   } else {
     return fail(UB_ERR_ARG, "unknown option '%s'", name);
   }
@@ -551,7 +710,10 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     const float* bias = reinterpret_cast<const float*>(p->wt + l.b_off);
     void* out = p->ws + p->bufs[l.out].off;
     void* pool = l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr;
-    if (l.kind == L_STEM) {
+    if (l.kind == L_STEM && l.stem_tc) {
+      int rc = launch_stem_umma(l.mW, l.mOut, x, bias, batch, l.H, l.W, l.relu, st);
+      if (rc != UB_OK) return rc;
+    } else if (l.kind == L_STEM) {
       const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
       const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
       ub::stem_conv_kernel<<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(x),
@@ -569,11 +731,11 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
         a.probs = probs;
         a.mask = mask;
       }
-      int rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, a, st);
+      int rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, l.mPool, a, st);
       if (rc != UB_OK) return rc;
     } else {
       ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, pool);
-      int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, st);
+      int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, st);
       if (rc != UB_OK) return rc;
     }
     if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
@@ -752,8 +914,16 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
     }
     rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
     if (rc != UB_OK) return rc;
+    rc = make_box_map(&l.mOut, y, B, H, W, Cout, 8, 16);
+    if (rc != UB_OK) return rc;
+    if (pool != nullptr) {
+      rc = make_box_map(&l.mPool, pool, B, H / 2, W / 2, Cout, 4, 8);
+      if (rc != UB_OK) return rc;
+    } else {
+      l.mPool = l.mOut;
+    }
     ub::HaloArgs ha = halo_args(l, B, bias, y, pool);
-    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, ha, static_cast<cudaStream_t>(stream));
+    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, l.mPool, ha, static_cast<cudaStream_t>(stream));
   }
   if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
   rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
@@ -766,8 +936,10 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
   }
   rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
   if (rc != UB_OK) return rc;
+  rc = make_umma_store_maps(l, y, pool, B);
+  if (rc != UB_OK) return rc;
   ub::ConvArgs a = conv_args(l, B, B, bias, y, pool);
-  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, static_cast<cudaStream_t>(stream));
+  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias, int B, int H, int W, int f, void* y,
@@ -792,8 +964,10 @@ int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias
   l.mA1 = l.mA0;
   rc = make_w_map(&l.mW, wp, 4 * f, Cin, l.block_n);
   if (rc != UB_OK) return rc;
+  rc = make_umma_store_maps(l, y, nullptr, B);
+  if (rc != UB_OK) return rc;
   ub::ConvArgs a = conv_args(l, B, B, bias, y, nullptr);
-  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, a, static_cast<cudaStream_t>(stream));
+  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
@@ -833,6 +1007,29 @@ int unet_b200_stem_conv(const void* x, const float* ws, const float* bias, int B
       reinterpret_cast<const uint2*>(x), ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
+}
+
+int unet_b200_pack_stem_tc(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                           float eps, int Cout, int Cin, void* wp, float* bias, void* stream) {
+  if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin < 1 || Cin > 4 || Cout != 64) return fail(UB_ERR_ARG, "tensor-core stem needs Cin in [1,4] and Cout == 64");
+  ub::pack_stem_umma_kernel<<<grid_for((size_t)64 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gamma, beta, mean, var, eps, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wp), bias);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_stem_conv_tc(const void* x, const void* wp, const float* bias, int B, int H, int W, int relu, void* y,
+                           void* stream) {
+  if (x == nullptr || wp == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  CUtensorMap mw, mo;
+  rc = make_w_map(&mw, wp, 64, 64, 64);
+  if (rc != UB_OK) return rc;
+  rc = make_box_map(&mo, y, B, H, W, 64, 8, 16);
+  if (rc != UB_OK) return rc;
+  return launch_stem_umma(mw, mo, x, bias, B, H, W, relu, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_head(const void* x, const float* w, float bias, size_t npix, int C, float* logits, float* probs,

@@ -1,0 +1,230 @@
+// Stem convolution on tensor cores: Conv2d(Cin<=4 -> 64, 3x3, pad 1) + folded BN + ReLU
+// (README.md:1452 with in_channels = 3), NHWC4 bf16 input -> NHWC bf16 output.
+//
+// K = 9 taps x 4 (padded) channels = 36, far below a 64-deep TMA K block, so the im2col tile is built
+// by producer warps instead of TMA: each thread assembles one 128-byte row (pixel) of the A operand -
+// taps 2j,2j+1 form 16-byte chunk j, chunks 0..5 cover K = 48 (columns 36..47 are zero) - and writes
+// it in the 128B-swizzled layout the UMMA descriptor expects. Three K=16 MMAs per 128-pixel tile.
+// The layer is bound by writing its 128 B/pixel output, so everything else is sized to stay out of
+// the way: 2 x 4 producer warps (alternating tiles), 4 operand stages, 4 TMEM accumulator stages,
+// 8 epilogue warps with double-buffered staging + TMA store.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+struct StemArgs {
+  int B, H, W;
+  int tiles_w, tiles_h;   // 8-pixel x 16-row tiles per image
+  int relu;
+  const uint2* x;         // [B,H,W] x 4 bf16
+  const float* bias;      // [64]
+};
+
+struct StemCfg {
+  static constexpr int N = 64;
+  static constexpr int A_STAGES = 4, ACC_STAGES = 4;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = N * 128;
+  static constexpr int THREADS = 17 * 32;  // warp 0 MMA, warps 1..8 epilogue, warps 9..16 producers
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 2 * 16384 + 512 + 1024;
+};
+
+// Weights for the stem GEMM: wp[co][k] bf16, k = tap*4 + ci (zero for ci >= Cin and k >= 36), bias fp32.
+__global__ void pack_stem_umma_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ mean,
+                                      const float* __restrict__ var, float eps, int Cout, int Cin,
+                                      __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int total = Cout * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % 64, co = i / 64;
+    const int tap = k / 4, ci = k % 4;
+    float v = 0.f;
+    if (tap < 9 && ci < Cin) {
+      float s = 1.f;
+      if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
+      v = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s;
+    }
+    wp[i] = __float2bfloat16_rn(v);
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout; co += gridDim.x * blockDim.x) {
+    float bv = 0.f;
+    if (gamma != nullptr) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    bias[co] = bv;
+  }
+}
+
+__global__ void __launch_bounds__(StemCfg::THREADS, 1)
+stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
+  using Cfg = StemCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smA + Cfg::A_STAGES * Cfg::A_BYTES;
+  uint8_t* smS = smB + Cfg::B_BYTES;  // [2][16 KB] output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + 2 * 16384);
+  uint64_t* a_full = bars;                       // [4] producers (128 arrivals) -> MMA
+  uint64_t* a_empty = a_full + Cfg::A_STAGES;    // [4] MMA -> producers
+  uint64_t* tfull = a_empty + Cfg::A_STAGES;     // [4] MMA -> epilogue
+  uint64_t* tempty = tfull + Cfg::ACC_STAGES;    // [4] epilogue (256 arrivals) -> MMA
+  uint64_t* w_full = tempty + Cfg::ACC_STAGES;   // [1] weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);  // [64]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < Cfg::A_STAGES; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 256);
+    }
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::ACC_STAGES * Cfg::N);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 96) sbias[threadIdx.x - 32] = a.bias[threadIdx.x - 32];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int total_tiles = tiles_per_img * a.B;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ MMA issuer (+ one-off weight load)
+    if (elect_one()) {
+      mbar_expect_tx(w_full, Cfg::B_BYTES);
+      tma_load_2d(smB, &tmW, w_full, 0, 0);
+      mbar_wait(w_full, 0);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128, Cfg::N);
+      const uint64_t d_hi = make_sw128_kmajor_desc(0, 1024, 0);
+      const uint64_t db = d_hi + (smem_u32(smB) >> 4);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int s = it & (Cfg::A_STAGES - 1);
+        const int acc = it & (Cfg::ACC_STAGES - 1);
+        mbar_wait(&tempty[acc], ((it / Cfg::ACC_STAGES) & 1) ^ 1);
+        mbar_wait(&a_full[s], (it / Cfg::A_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = d_hi + (smem_u32(smA + s * Cfg::A_BYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + acc * Cfg::N;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, k != 0);
+        umma_commit(&a_empty[s]);
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 9) {
+    // ------------------------------------------------------------ im2col producers: group pg builds tiles it = pg, pg+2, ...
+    const int pg = (warp - 9) >> 2;
+    const int m = ((warp - 9) & 3) * 32 + lane;  // row of the A tile == pixel of the 16x8 tile
+    const int tw = m & 7, th = m >> 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != pg) continue;
+      const int s = it & (Cfg::A_STAGES - 1);
+      const int b = t / tiles_per_img;
+      const int ti = t - b * tiles_per_img;
+      const int w = (ti % a.tiles_w) * 8 + tw;
+      const int h = (ti / a.tiles_w) * 16 + th;
+      // gather the 3x3 neighbourhood (zero outside the image) before waiting for the slot
+      uint2 tap[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int hh = h + r - 1, ww = w + c - 1;
+          uint2 v = make_uint2(0u, 0u);
+          if (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) v = __ldg(a.x + (static_cast<size_t>(b) * a.H + hh) * a.W + ww);
+          tap[r * 3 + c] = v;
+        }
+      }
+      mbar_wait_parked(&a_empty[s], ((it / Cfg::A_STAGES) & 1) ^ 1, 2000);
+      const uint32_t row = smem_u32(smA + s * Cfg::A_BYTES + m * 128);
+      const int sw = m & 7;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        st_shared_v4(row + ((j ^ sw) << 4), tap[2 * j].x, tap[2 * j].y, tap[2 * j + 1].x, tap[2 * j + 1].y);
+      }
+      st_shared_v4(row + ((4 ^ sw) << 4), tap[8].x, tap[8].y, 0u, 0u);
+      st_shared_v4(row + ((5 ^ sw) << 4), 0u, 0u, 0u, 0u);
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&a_full[s]);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: warps 1..8; (q, cg) owns rows 32q.. and chunk cg
+    const int q = warp & 3;
+    const int cg = (warp - 1) >> 2;
+    const int m = q * 32 + lane;
+    const bool store_thread = (threadIdx.x == 32);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & (Cfg::ACC_STAGES - 1);
+      const int b = t / tiles_per_img;
+      const int ti = t - b * tiles_per_img;
+      const int w0 = (ti % a.tiles_w) * 8;
+      const int h0 = (ti / a.tiles_w) * 16;
+      uint8_t* stg = smS + (it & 1) * 16384;
+      if (store_thread) bulk_wait_group_read<1>();
+      named_bar_sync(1, 256);
+      mbar_wait(&tfull[acc], (it / Cfg::ACC_STAGES) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::N + cg * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      const float4* bias4 = reinterpret_cast<const float4*>(sbias + cg * 32);
+      uint32_t p[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = bias4[j];
+        float x0 = __uint_as_float(v[4 * j + 0]) + bb.x;
+        float x1 = __uint_as_float(v[4 * j + 1]) + bb.y;
+        float x2 = __uint_as_float(v[4 * j + 2]) + bb.z;
+        float x3 = __uint_as_float(v[4 * j + 3]) + bb.w;
+        if (a.relu) {
+          x0 = fmaxf(x0, 0.f);
+          x1 = fmaxf(x1, 0.f);
+          x2 = fmaxf(x2, 0.f);
+          x3 = fmaxf(x3, 0.f);
+        }
+        p[2 * j] = pack_bf16x2(x0, x1);
+        p[2 * j + 1] = pack_bf16x2(x2, x3);
+      }
+      const uint32_t row = smem_u32(stg + m * 128);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        st_shared_v4(row + (((cg * 4 + j) ^ (m & 7)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (store_thread) {
+        tma_store_4d(&tmOut, stg, 0, w0, h0, b);
+        bulk_commit_group();
+      }
+    }
+    if (store_thread) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::ACC_STAGES * Cfg::N);
+  }
+}
+
+}  // namespace ub

@@ -57,6 +57,27 @@ def pack_stem(w, bn=None):
     return ws, bias
 
 
+def pack_stem_tc(w, bn=None):
+    """Tensor-core stem weights: w fp32 [64,Cin<=4,3,3] (+ eval BN) -> (wp bf16 [64,64], bias fp32 [64])."""
+    _req(w, torch.float32, "w")
+    cout, cin = w.shape[:2]
+    wp = torch.empty(cout, 64, dtype=torch.bfloat16, device=w.device)
+    bias = torch.empty(cout, dtype=torch.float32, device=w.device)
+    g, b, m, v, eps = bn if bn is not None else (None, None, None, None, 0.0)
+    check(lib.unet_b200_pack_stem_tc(w.data_ptr(), _p(g), _p(b), _p(m), _p(v), eps, cout, cin, wp.data_ptr(),
+                                     bias.data_ptr(), _stream()))
+    return wp, bias
+
+
+def stem_conv_tc(x4, wp, bias, relu=True):
+    _req(x4, torch.bfloat16, "x4")
+    B, H, W, _ = x4.shape
+    y = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x4.device)
+    check(lib.unet_b200_stem_conv_tc(x4.data_ptr(), wp.data_ptr(), bias.data_ptr(), B, H, W, int(relu), y.data_ptr(),
+                                     _stream()))
+    return y
+
+
 def pack_convT2x2(w):
     """w fp32 [Cin,f,2,2] -> wp bf16 [4f, Cin]."""
     _req(w, torch.float32, "w")
