@@ -133,26 +133,22 @@ int make_tile_store_map(CUtensorMap* m, const void* base, int Bc, int H, int W, 
 struct Layer;
 int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc);
 
-// Shared-memory carve-up of conv_halo_kernel: prefer resident weights, then deeper patch / staging rings.
-bool halo_smem_plan(int block_n, int kc, int pool, int head, ub::HaloArgs* a) {
-  const int need = 9 * kc;
-  static const int cand[5][2] = {{4, 2}, {3, 2}, {3, 1}, {2, 2}, {2, 1}};  // (a_stages, n_stg)
+// Shared-memory carve-up of conv_halo_kernel: prefer resident weights, then the deepest patch ring that fits.
+bool halo_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
+  const int need = 3 * kc;  // weight stages (3 taps each)
   if (need <= ub::HaloCfg::MAX_B) {
-    for (const auto& c : cand) {
-      const int ns = head ? 0 : c[1];
-      if (ub::halo_smem_bytes(block_n, c[0], need, ns, pool) <= ub::HaloCfg::SMEM_LIMIT) {
-        a->resident = 1; a->a_stages = c[0]; a->b_stages = need; a->n_stg = ns;
+    for (int as = 4; as >= 2; --as) {
+      if (ub::halo_smem_bytes(block_n, as, need, head) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 1; a->a_stages = as; a->b_stages = need;
         return true;
       }
     }
   }
-  // streamed weights: keep three patch stages, one staging tile, and give the weight ring whatever is left
-  static const int scand[4][2] = {{3, 1}, {3, 2}, {2, 1}, {2, 2}};
-  for (const auto& c : scand) {
-    const int ns = head ? 0 : c[1];
-    for (int b = 12; b >= 4; --b) {
-      if (ub::halo_smem_bytes(block_n, c[0], b, ns, pool) <= ub::HaloCfg::SMEM_LIMIT) {
-        a->resident = 0; a->a_stages = c[0]; a->b_stages = b; a->n_stg = ns;
+  // streamed weights: a full kernel (3 stages) in flight first, then as many patch stages as fit
+  for (int b = 3; b >= 2; --b) {
+    for (int as = 3; as >= 2; --as) {
+      if (ub::halo_smem_bytes(block_n, as, b, head) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 0; a->a_stages = as; a->b_stages = b;
         return true;
       }
     }
@@ -211,8 +207,8 @@ int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     g_attr_done[slot] = 1;
   }
   ub::ConvArgs args2 = args;
-  Cfg::plan(args.taps, args.pool, &args2.stages, &args2.n_stg);
-  const int smem = Cfg::smem_bytes(args2.stages, args2.n_stg, args2.pool);
+  args2.stages = Cfg::plan_stages();
+  const int smem = Cfg::smem_bytes(args2.stages);
   const int total = args.tiles_w * args.tiles_h * args.tiles_b * args.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(a0, a1, w, mo[0], mo[1], mo[2], mo[3], args2);
@@ -224,31 +220,33 @@ int g_hattr_done[2] = {0, 0};
 
 template <int BN>
 int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
-                  const CUtensorMap& mp, ub::HaloArgs args, int slot, cudaStream_t st) {
+                  ub::HaloArgs args, int slot, cudaStream_t st) {
   if (!g_hattr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ub::HaloCfg::SMEM_LIMIT));
     g_hattr_done[slot] = 1;
   }
-  if (!halo_smem_plan(BN, args.kc0 + args.kc1, args.pool, args.epi == ub::HEPI_HEAD, &args)) {
+  const int head = args.epi == ub::HEPI_HEAD;
+  if (head && BN != 64) return fail(UB_ERR_ARG, "the fused head epilogue needs Cout == 64");
+  if (!halo_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
     return fail(UB_ERR_ARG, "no shared-memory plan for halo conv (N=%d, KC=%d)", BN, args.kc0 + args.kc1);
   }
-  const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, args.n_stg, args.pool);
+  const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head);
   const int total = args.tiles_w * args.tiles_h * args.B;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_halo_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, mp, args);
+  ub::conv_halo_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, args);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
 int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
-                const CUtensorMap& mp, const ub::HaloArgs& args, cudaStream_t st) {
+                const ub::HaloArgs& args, cudaStream_t st) {
   if (g_num_sms == 0) {
     int rc = device_check();
     if (rc != UB_OK) return rc;
   }
-  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, mp, args, 0, st);
-  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, mp, args, 1, st);
+  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, args, 0, st);
+  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, args, 1, st);
   return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
 }
 
@@ -324,17 +322,15 @@ struct Buf {
 // the tensor (f, W, H, B) at base + (dy*2W + dx)*f with pixel strides (2f, 4W*f, 4HW*f).
 int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc) {
   int rc;
+  (void)pool;
+  // one TMEM lane quarter (32 rows) of the tile box, see conv_args(): sub-box (TW, sh, sb)
+  const int sb = l.TB >= 4 ? l.TB / 4 : 1;
+  const int sh = l.TB >= 4 ? l.TH : (l.TB == 2 ? l.TH / 2 : l.TH / 4);
   if (l.kind == L_CONV) {
     const size_t C = l.Cout;
-    rc = make_tile_store_map(&l.mO[0], out, Bc, l.H, l.W, l.Cout, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, l.TH, l.TB);
+    rc = make_tile_store_map(&l.mO[0], out, Bc, l.H, l.W, l.Cout, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, sh, sb);
     if (rc != UB_OK) return rc;
-    if (pool != nullptr) {
-      const int Hp = l.H / 2, Wp = l.W / 2;
-      rc = make_tile_store_map(&l.mO[1], pool, Bc, Hp, Wp, l.Cout, C, (size_t)Wp * C, (size_t)Hp * Wp * C, l.TW / 2, l.TH / 2, l.TB);
-      if (rc != UB_OK) return rc;
-    } else {
-      l.mO[1] = l.mO[0];
-    }
+    l.mO[1] = l.mO[0];
     l.mO[2] = l.mO[0];
     l.mO[3] = l.mO[0];
   } else {
@@ -342,7 +338,7 @@ int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc) {
     for (int qd = 0; qd < 4; ++qd) {
       const int dy = qd >> 1, dx = qd & 1;
       uint8_t* base = static_cast<uint8_t*>(out) + ((size_t)dy * 2 * l.W + dx) * f * 2;
-      rc = make_tile_store_map(&l.mO[qd], base, Bc, l.H, l.W, l.Cout, 2 * f, (size_t)4 * l.W * f, (size_t)4 * l.H * l.W * f, l.TW, l.TH, l.TB);
+      rc = make_tile_store_map(&l.mO[qd], base, Bc, l.H, l.W, l.Cout, 2 * f, (size_t)4 * l.W * f, (size_t)4 * l.H * l.W * f, l.TW, sh, sb);
       if (rc != UB_OK) return rc;
     }
   }
@@ -433,7 +429,7 @@ ub::HaloArgs halo_args(const Layer& l, int batch, const float* bias, void* out, 
   a.kc1 = l.C1 / 64;
   a.epi = ub::HEPI_STORE;
   a.relu = l.relu;
-  a.pool = (pool != nullptr) ? 1 : 0;
+  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
   a.Cout = l.Cout;
   a.bias = bias;
   (void)out;
@@ -461,7 +457,17 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.relu = l.relu;
   a.Cout = l.Cout;
   a.bias = bias;
-  a.pool = (pool != nullptr) ? 1 : 0;
+  a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  if (l.TB >= 4) {
+    a.sub_b = l.TB / 4;
+    a.sub_h = l.TH;
+  } else if (l.TB == 2) {
+    a.sub_b = 1;
+    a.sub_h = l.TH / 2;
+  } else {
+    a.sub_b = 1;
+    a.sub_h = l.TH / 4;
+  }
   (void)out;
   return a;
 }
@@ -557,7 +563,7 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   p->final_buf = cur;
   {
     Layer& last = p->layers.back();
-    last.fuse_head = g_opt_fuse_head && last.kind == L_CONV && last.halo;
+    last.fuse_head = g_opt_fuse_head && last.kind == L_CONV && last.halo && last.Cout == 64;
   }
   p->head_w_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)features[0] * 4, 256);
@@ -584,7 +590,7 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
       if (l.stem_tc) {
         rc = make_w_map(&l.mW, p->wt + l.w_off, 64, 64, 64);
         if (rc != UB_OK) return rc;
-        rc = make_box_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, 64, 8, 16);
+        rc = make_box_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, 64, 8, 4);
         if (rc != UB_OK) return rc;
       }
       continue;
@@ -607,15 +613,8 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
     }
     if (l.halo) {
       const Buf& bo = p->bufs[l.out];
-      rc = make_box_map(&l.mOut, p->ws + bo.off, p->Bc, l.H, l.W, l.Cout, 8, 16);
+      rc = make_box_map(&l.mOut, p->ws + bo.off, p->Bc, l.H, l.W, l.Cout, 8, 4);
       if (rc != UB_OK) return rc;
-      if (l.pool >= 0) {
-        const Buf& bp = p->bufs[l.pool];
-        rc = make_box_map(&l.mPool, p->ws + bp.off, p->Bc, l.H / 2, l.W / 2, l.Cout, 4, 8);
-        if (rc != UB_OK) return rc;
-      } else {
-        l.mPool = l.mOut;
-      }
     }
     if (l.kind == L_CONV) {
       rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.block_n);
@@ -731,7 +730,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
         a.probs = probs;
         a.mask = mask;
       }
-      int rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, l.mPool, a, st);
+      int rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, a, st);
       if (rc != UB_OK) return rc;
     } else {
       ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, pool);
@@ -914,16 +913,10 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
     }
     rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
     if (rc != UB_OK) return rc;
-    rc = make_box_map(&l.mOut, y, B, H, W, Cout, 8, 16);
+    rc = make_box_map(&l.mOut, y, B, H, W, Cout, 8, 4);
     if (rc != UB_OK) return rc;
-    if (pool != nullptr) {
-      rc = make_box_map(&l.mPool, pool, B, H / 2, W / 2, Cout, 4, 8);
-      if (rc != UB_OK) return rc;
-    } else {
-      l.mPool = l.mOut;
-    }
     ub::HaloArgs ha = halo_args(l, B, bias, y, pool);
-    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, l.mPool, ha, static_cast<cudaStream_t>(stream));
+    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, static_cast<cudaStream_t>(stream));
   }
   if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
   rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
@@ -1027,7 +1020,7 @@ int unet_b200_stem_conv_tc(const void* x, const void* wp, const float* bias, int
   CUtensorMap mw, mo;
   rc = make_w_map(&mw, wp, 64, 64, 64);
   if (rc != UB_OK) return rc;
-  rc = make_box_map(&mo, y, B, H, W, 64, 8, 16);
+  rc = make_box_map(&mo, y, B, H, W, 64, 8, 4);
   if (rc != UB_OK) return rc;
   return launch_stem_umma(mw, mo, x, bias, B, H, W, relu, static_cast<cudaStream_t>(stream));
 }

@@ -13,11 +13,12 @@
 // (c0, w0+dx, h0+dy, b0) with zero OOB fill *is* the im2col tile for tap (dy,dx).
 //
 // Warp roles (320 threads): warp 0 = TMA producer (one elected thread), warp 1 = TMEM owner + MMA
-// issuer (one elected thread), warps 2..9 = epilogue: two warps per TMEM lane quarter, each taking
-// every other 32-column chunk. Persistent over tiles; two TMEM accumulator stages so the epilogue of
-// tile i overlaps the MMAs of tile i+1. The epilogue leaves through shared memory: bias/ReLU/bf16 ->
-// 128B-swizzled staging tile of 64 channels -> one TMA store (which also clips partial tiles).
+// issuer (one elected thread), warps 2..9 = epilogue: two warps per TMEM lane quarter. Persistent over
+// tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Epilogue work is cut into warp-private units of 32 rows x 64 columns (epilogue.cuh): registers ->
+// 4 KB swizzled staging tile -> TMA store of the quarter's sub-box (the tensor map clips partial tiles).
 #pragma once
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub {
@@ -32,8 +33,10 @@ struct ConvArgs {
   int taps;                       // 9 (3x3, pad 1) or 1 (pointwise)
   int kc0, kc1;                   // 64-channel blocks taken from source 0 / source 1
   int epi;                        // EPI_*
-  int relu, pool;
-  int stages, n_stg;              // shared-memory split: operand ring depth / number of 16 KB output staging tiles (1, 2 or 4)
+  int relu;
+  int stages;                     // operand ring depth (shared-memory split chosen by the host)
+  int sub_h, sub_b;               // rows / images of the 32-row sub-box one TMEM lane quarter covers (sub_w == TW)
+  __nv_bfloat16* pool_out;        // EPI_STORE, optional: [B,H/2,W/2,Cout] = maxpool2x2(out), written from registers
   int a_bytes;                    // bytes one A box load delivers (128 rows x 128 B unless TB exceeds the batch dim)
   int Cout;                       // EPI_STORE: channels of out; EPI_CONVT: f (out channels of the ConvT)
   const float* bias;              // [Cout]
@@ -51,17 +54,13 @@ struct ConvCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_LIMIT = 232448;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
-  __host__ __device__ static constexpr int smem_bytes(int stages, int n_stg, int pool) {
-    return stages * STAGE_BYTES + n_stg * (16384 + (pool ? 4096 : 0)) + BAR_BYTES + 1024;
+  static constexpr int STG_BYTES = 8 * 4096;  // one private 4 KB staging tile per epilogue warp
+  __host__ __device__ static constexpr int smem_bytes(int stages) {
+    return stages * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   }
-  // Compute-bound 3x3 convs: deepest operand ring, one staging tile. Epilogue-bound pointwise GEMMs (ConvT): a short
-  // ring and four staging tiles so TMA stores overlap the next halves' TMEM reads.
-  static void plan(int taps, int pool, int* stages, int* n_stg) {
-    *n_stg = (taps == 1) ? 4 : 1;
-    int s = (SMEM_LIMIT - BAR_BYTES - 1024 - *n_stg * (16384 + (pool ? 4096 : 0))) / STAGE_BYTES;
-    if (s > MAX_STAGES) s = MAX_STAGES;
-    if (taps == 1 && s > 4) s = 4;
-    *stages = s;
+  static int plan_stages() {
+    int s = (SMEM_LIMIT - BAR_BYTES - 1024 - STG_BYTES) / STAGE_BYTES;
+    return s > MAX_STAGES ? MAX_STAGES : s;
   }
 };
 
@@ -78,9 +77,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smS = smem + STAGES * Cfg::STAGE_BYTES;  // [n_stg][16 KB] output staging
-  uint8_t* smP = smS + a.n_stg * 16384;             // [n_stg][4 KB] pooled staging (if pool)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + (a.pool ? a.n_stg * 4096 : 0));
+  uint8_t* smS = smem + STAGES * Cfg::STAGE_BYTES;  // [8 warps][4 KB] private output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + Cfg::STG_BYTES);
   uint64_t* full = bars;                // [MAXS] TMA -> MMA
   uint64_t* empty = bars + MAXS;        // [MAXS] MMA -> TMA
   uint64_t* tfull = bars + 2 * MAXS;    // [2] MMA -> epilogue
@@ -101,7 +99,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 256);
+      mbar_init(&tempty[s], HALVES == 1 ? 128 : 256);
     }
     fence_mbar_init();
   }
@@ -192,22 +190,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue: 8 warps; (q, cg) owns rows 32q..32q+31 and
-    // the 32-column chunks with (chunk & 1) == cg. Output leaves one 64-channel half at a time.
+    // ------------------------------------------------------------ epilogue: 8 warps, warp-private units (epilogue.cuh)
+    // warp (q, cg): TMEM lane quarter q; of a tile's 64-column halves it takes cg, cg+2, ... (BLOCK_N == 64: the two
+    // warps of a quarter alternate tiles instead, i.e. warp group cg owns accumulator stage cg).
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int tw = m % a.TW;
     const int th = (m / a.TW) % a.TH;
     const int tb = m / (a.TW * a.TH);
-    const bool store_thread = (threadIdx.x == 64);
-    const int pw = a.TW >> 1, ph = a.TH >> 1;
-    const int prow = (tb * ph + (th >> 1)) * pw + (tw >> 1);  // row in the pooled [TB][TH/2][TW/2] tile
+    uint8_t* stg = smS + (warp - 2) * 4096;
+    // the quarter's 32 rows form a (TW, sub_h, sub_b) sub-box of the tile at this offset
+    int off_h = 0, off_b = 0;
+    if (a.TB >= 4) {
+      off_b = q * a.sub_b;
+    } else if (a.TB == 2) {
+      off_b = q >> 1;
+      off_h = (q & 1) * a.sub_h;
+    } else {
+      off_h = q * a.sub_h;
+    }
     const bool pool_writer = ((tw | th) & 1) == 0;
     int it = 0;
-    uint32_t nstore = 0;  // halves stored so far by this CTA (selects the staging tile)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
+      if (HALVES == 1 && acc != cg) continue;
       const int n_tile = t % a.n_tiles;
       const int m_tile = t / a.n_tiles;
       const int w0 = (m_tile % a.tiles_w) * a.TW;
@@ -217,95 +224,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int hf = 0; hf < HALVES; ++hf, ++nstore) {
-        const int sb = nstore & (a.n_stg - 1);
-        uint8_t* stg = smS + sb * 16384;
-        uint8_t* pstg = smP + sb * 4096;
-        // staging tile `sb` is free once the store issued n_stg halves ago has finished reading it
-        if (store_thread) {
-          if (a.n_stg == 4) {
-            bulk_wait_group_read<3>();
-          } else if (a.n_stg == 2) {
-            bulk_wait_group_read<1>();
-          } else {
-            bulk_wait_group_read<0>();
-          }
+      for (int hf = (HALVES == 1 ? 0 : cg); hf < HALVES; hf += 2) {
+        const int n = n_tile * BLOCK_N + hf * 64;  // first GEMM column of the unit
+        int bias_off = n, quad = 0, co = n;
+        if (a.epi == EPI_CONVT) {  // column n -> (quad = dy*2+dx, co): bias is per co, each quad is its own store view
+          quad = n / a.Cout;
+          co = n - quad * a.Cout;
+          bias_off = co;
         }
-        named_bar_sync(1, 256);
-        const int c = hf * 2 + cg;                    // this warp's 32-column chunk of the half
-        const int n = n_tile * BLOCK_N + c * 32;      // first GEMM column of the chunk
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        int bias_off = n;
-        if (a.epi == EPI_CONVT) bias_off = n % a.Cout;  // column n -> (quad, co): bias is per co
-        const float4* bias4 = reinterpret_cast<const float4*>(a.bias + bias_off);
-        float4 bb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
-        tmem_ld_wait();
-        uint32_t p[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x0 = __uint_as_float(v[4 * j + 0]) + bb[j].x;
-          float x1 = __uint_as_float(v[4 * j + 1]) + bb[j].y;
-          float x2 = __uint_as_float(v[4 * j + 2]) + bb[j].z;
-          float x3 = __uint_as_float(v[4 * j + 3]) + bb[j].w;
-          if (a.relu) {
-            x0 = fmaxf(x0, 0.f);
-            x1 = fmaxf(x1, 0.f);
-            x2 = fmaxf(x2, 0.f);
-            x3 = fmaxf(x3, 0.f);
-          }
-          p[2 * j] = pack_bf16x2(x0, x1);
-          p[2 * j + 1] = pack_bf16x2(x2, x3);
-        }
-        const int j0 = cg * 4;
-        const uint32_t row = smem_u32(stg + m * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          st_shared_v4(row + (((j0 + j) ^ (m & 7)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-        }
-        if (a.pool) {
-          // 2x2 window partners are lane^1 (w) and lane^TW (h): both inside this warp for TW <= 16.
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            uint32_t x = p[j];
-            x = bf16x2_max(x, __shfl_xor_sync(0xffffffffu, x, 1));
-            x = bf16x2_max(x, __shfl_xor_sync(0xffffffffu, x, a.TW));
-            p[j] = x;
-          }
-          if (pool_writer) {
-            const uint32_t prw = smem_u32(pstg + prow * 128);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              st_shared_v4(prw + (((j0 + j) ^ (prow & 7)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-            }
-          }
-        }
-        if (hf == HALVES - 1) {
-          // all of this thread's TMEM reads for the tile are done: hand the accumulator back to the MMA warp
+        uint32_t p[32];
+        epi_load_unit(t_row + hf * 64, a.bias + bias_off, a.relu, p);
+        if (hf + 2 >= HALVES) {
+          // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty[acc]);
         }
+        if (lane == 0) bulk_wait_group_read<0>();  // the previous unit's TMA store has finished reading the staging tile
+        __syncwarp();
+        epi_stage_row(stg, lane, p);
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(2, 256);
-        if (store_thread) {
-          const int nh = n_tile * BLOCK_N + hf * 64;  // first GEMM column of this half
-          if (a.epi == EPI_STORE) {
-            tma_store_4d(&tmO0, stg, nh, w0, h0, b0);
-            if (a.pool) tma_store_4d(&tmO1, pstg, nh, w0 >> 1, h0 >> 1, b0);
-          } else {
-            // ConvT: column nh -> (quad = dy*2+dx, co); each quad is a strided view of the upsampled output
-            const int quad = nh / a.Cout;
-            const int co = nh - quad * a.Cout;
-            const CUtensorMap* mq = quad == 0 ? &tmO0 : quad == 1 ? &tmO1 : quad == 2 ? &tmO2 : &tmO3;
-            tma_store_4d(mq, stg, co, w0, h0, b0);
-          }
+        __syncwarp();
+        if (lane == 0) {
+          const CUtensorMap* mo = quad == 0 ? &tmO0 : quad == 1 ? &tmO1 : quad == 2 ? &tmO2 : &tmO3;
+          tma_store_4d(mo, stg, co, w0, h0 + off_h, b0 + off_b);
           bulk_commit_group();
+        }
+        if (a.pool_out != nullptr) {
+          // 2x2 window partners are lane^1 (w) and lane^TW (h): both inside this warp's quarter
+          epi_pool2x2(p, a.TW);
+          const int w = w0 + tw, h = h0 + th, b = b0 + tb;
+          if (pool_writer && w < a.W && h < a.H && b < a.B) {
+            uint4* dst = reinterpret_cast<uint4*>(
+                a.pool_out + ((static_cast<size_t>(b) * (a.H >> 1) + (h >> 1)) * (a.W >> 1) + (w >> 1)) * a.Cout + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+          }
         }
       }
     }
-    if (store_thread) bulk_wait_group_read<0>();
+    if (lane == 0) bulk_wait_group_read<0>();
   }
 
   tc_fence_before();

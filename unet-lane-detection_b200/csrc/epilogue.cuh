@@ -1,0 +1,69 @@
+// Warp-private epilogue shared by the tcgen05 kernels.
+//
+// Work unit = 32 accumulator rows (one TMEM lane quarter) x 64 columns. A unit is owned by ONE warp:
+// tcgen05.ld -> +bias -> ReLU -> bf16 -> 4 KB 128B-swizzled staging tile private to the warp ->
+// fence.proxy.async -> __syncwarp -> lane 0 issues the TMA store of that 32-row sub-box (and of the
+// 2x2 max-pooled 8-row sub-box). No CTA-wide barrier is involved, so the eight epilogue warps drift
+// freely and TMA stores of one unit overlap the TMEM reads of the next.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+struct EpiWarp {
+  uint8_t* stg;    // 4 KB staging tile of this warp (1024-byte aligned)
+  uint8_t* pstg;   // 1 KB pooled staging tile of this warp (1024-byte aligned), or nullptr
+  int lane;
+};
+
+// Reads the 64 columns starting at `taddr` (this warp's lane quarter), applies bias (+ReLU) and packs to bf16.
+// p[0..15] = columns 0..31, p[16..31] = columns 32..63 (two bf16 per register).
+__device__ __forceinline__ void epi_load_unit(uint32_t taddr, const float* __restrict__ bias64, int relu, uint32_t (&p)[32]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    const float4* bias4 = reinterpret_cast<const float4*>(bias64 + c * 32);
+    float4 bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x0 = __uint_as_float(v[4 * j + 0]) + bb[j].x;
+      float x1 = __uint_as_float(v[4 * j + 1]) + bb[j].y;
+      float x2 = __uint_as_float(v[4 * j + 2]) + bb[j].z;
+      float x3 = __uint_as_float(v[4 * j + 3]) + bb[j].w;
+      if (relu) {
+        x0 = fmaxf(x0, 0.f);
+        x1 = fmaxf(x1, 0.f);
+        x2 = fmaxf(x2, 0.f);
+        x3 = fmaxf(x3, 0.f);
+      }
+      p[c * 16 + 2 * j] = pack_bf16x2(x0, x1);
+      p[c * 16 + 2 * j + 1] = pack_bf16x2(x2, x3);
+    }
+  }
+}
+
+// Row `lane` of the warp's staging tile <- 64 bf16 (128 B), 16-byte chunks XOR-swizzled by (row & 7) as TMA expects.
+__device__ __forceinline__ void epi_stage_row(uint8_t* tile, int row, const uint32_t (&p)[32]) {
+  const uint32_t base = smem_u32(tile + row * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    st_shared_v4(base + ((j ^ (row & 7)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+  }
+}
+
+// 2x2 max over the window partners lane^1 (w) and lane^xor_h (h); afterwards every lane of a window holds the max.
+__device__ __forceinline__ void epi_pool2x2(uint32_t (&p)[32], int xor_h) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    uint32_t x = p[j];
+    x = bf16x2_max(x, __shfl_xor_sync(0xffffffffu, x, 1));
+    x = bf16x2_max(x, __shfl_xor_sync(0xffffffffu, x, xor_h));
+    p[j] = x;
+  }
+}
+
+}  // namespace ub

@@ -9,6 +9,7 @@
 // the way: 2 x 4 producer warps (alternating tiles), 4 operand stages, 4 TMEM accumulator stages,
 // 8 epilogue warps with double-buffered staging + TMA store.
 #pragma once
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub {
@@ -27,7 +28,7 @@ struct StemCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = N * 128;
   static constexpr int THREADS = 17 * 32;  // warp 0 MMA, warps 1..8 epilogue, warps 9..16 producers
-  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 2 * 16384 + 512 + 1024;
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 8 * 4096 + 512 + 1024;
 };
 
 // Weights for the stem GEMM: wp[co][k] bf16, k = tap*4 + ci (zero for ci >= Cin and k >= 36), bias fp32.
@@ -61,15 +62,14 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smA + Cfg::A_STAGES * Cfg::A_BYTES;
-  uint8_t* smS = smB + Cfg::B_BYTES;  // [2][16 KB] output staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + 2 * 16384);
+  uint8_t* smS = smB + Cfg::B_BYTES;  // [8 warps][4 KB] private output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + 8 * 4096);
   uint64_t* a_full = bars;                       // [4] producers (128 arrivals) -> MMA
   uint64_t* a_empty = a_full + Cfg::A_STAGES;    // [4] MMA -> producers
   uint64_t* tfull = a_empty + Cfg::A_STAGES;     // [4] MMA -> epilogue
-  uint64_t* tempty = tfull + Cfg::ACC_STAGES;    // [4] epilogue (256 arrivals) -> MMA
+  uint64_t* tempty = tfull + Cfg::ACC_STAGES;    // [4] epilogue (128 arrivals: one warp group per tile) -> MMA
   uint64_t* w_full = tempty + Cfg::ACC_STAGES;   // [1] weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);  // [64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,7 +83,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     }
     for (int s = 0; s < Cfg::ACC_STAGES; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 256);
+      mbar_init(&tempty[s], 128);
     }
     mbar_init(w_full, 1);
     fence_mbar_init();
@@ -92,7 +92,6 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     tmem_alloc(tmem_slot, Cfg::ACC_STAGES * Cfg::N);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 32 && threadIdx.x < 96) sbias[threadIdx.x - 32] = a.bias[threadIdx.x - 32];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,59 +163,36 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       mbar_arrive(&a_full[s]);
     }
   } else {
-    // ------------------------------------------------------------ epilogue: warps 1..8; (q, cg) owns rows 32q.. and chunk cg
+    // ------------------------------------------------------------ epilogue: warps 1..8, warp-private units (epilogue.cuh);
+    // the two warps of a TMEM lane quarter alternate tiles (group cg takes tiles with it % 2 == cg)
     const int q = warp & 3;
     const int cg = (warp - 1) >> 2;
-    const int m = q * 32 + lane;
-    const bool store_thread = (threadIdx.x == 32);
+    uint8_t* stg = smS + (warp - 1) * 4096;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != cg) continue;
       const int acc = it & (Cfg::ACC_STAGES - 1);
       const int b = t / tiles_per_img;
       const int ti = t - b * tiles_per_img;
       const int w0 = (ti % a.tiles_w) * 8;
       const int h0 = (ti / a.tiles_w) * 16;
-      uint8_t* stg = smS + (it & 1) * 16384;
-      if (store_thread) bulk_wait_group_read<1>();
-      named_bar_sync(1, 256);
       mbar_wait(&tfull[acc], (it / Cfg::ACC_STAGES) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::N + cg * 32, v);
-      tmem_ld_wait();
+      uint32_t p[32];
+      epi_load_unit(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::N, a.bias, a.relu, p);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      const float4* bias4 = reinterpret_cast<const float4*>(sbias + cg * 32);
-      uint32_t p[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bb = bias4[j];
-        float x0 = __uint_as_float(v[4 * j + 0]) + bb.x;
-        float x1 = __uint_as_float(v[4 * j + 1]) + bb.y;
-        float x2 = __uint_as_float(v[4 * j + 2]) + bb.z;
-        float x3 = __uint_as_float(v[4 * j + 3]) + bb.w;
-        if (a.relu) {
-          x0 = fmaxf(x0, 0.f);
-          x1 = fmaxf(x1, 0.f);
-          x2 = fmaxf(x2, 0.f);
-          x3 = fmaxf(x3, 0.f);
-        }
-        p[2 * j] = pack_bf16x2(x0, x1);
-        p[2 * j + 1] = pack_bf16x2(x2, x3);
-      }
-      const uint32_t row = smem_u32(stg + m * 128);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        st_shared_v4(row + (((cg * 4 + j) ^ (m & 7)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-      }
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+      epi_stage_row(stg, lane, p);
       fence_proxy_async();
-      named_bar_sync(2, 256);
-      if (store_thread) {
-        tma_store_4d(&tmOut, stg, 0, w0, h0, b);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&tmOut, stg, 0, w0, h0 + 4 * q, b);
         bulk_commit_group();
       }
     }
-    if (store_thread) bulk_wait_group_read<0>();
+    if (lane == 0) bulk_wait_group_read<0>();
   }
 
   tc_fence_before();

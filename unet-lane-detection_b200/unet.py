@@ -59,7 +59,7 @@ class UNet(nn.Module):
             self.decoder_blocks.append(self._conv_block(f * 2, f))
         self.output = nn.Conv2d(self.features[0], out_channels, kernel_size=1)
         # B200 runtime state (not part of the state_dict)
-        self.b200_chunk = 32  # frames per pass through the plan (bounds the workspace; tune for L2 reuse)
+        self.b200_chunk = 128  # frames per pass through the plan (bounds the workspace; tune for L2 reuse)
         self._engines = {}
         self.gpu_launches = 0
 
