@@ -238,16 +238,27 @@ def main():
         else:
             for a, b in zip(rows, r):
                 a["ms"] = min(a["ms"], b["ms"])
-    conv_rows = [r for r in rows if r["kind"] in ("conv3x3", "convT2x2")]
-    conv_flops = sum(r["flops"] for r in conv_rows)
-    conv_ms = sum(r["ms"] for r in conv_rows)
     all_ms = sum(r["ms"] for r in rows)
-    achieved = conv_flops / (conv_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None,
-                "kernel": "conv_umma_kernel<64|128|256> (22 launches per pass: 17 conv3x3 + 4 convT + fused pool/concat)",
-                "peak_source": peaks["source"] + " bf16_tflops_sustained", "share_of_step": conv_ms / all_ms,
-                "flops_per_launch_set": conv_flops, "ms_per_launch_set": conv_ms,
+
+    def fam(sel):
+        rs = [r for r in rows if sel(r)]
+        fl, ms_ = sum(r["flops"] for r in rs), sum(r["ms"] for r in rs)
+        return {"launches": len(rs), "tflops": fl / (ms_ / 1e3) / 1e12 if ms_ > 0 else 0.0, "share_of_step": ms_ / all_ms,
+                "flops": fl, "ms": ms_}
+
+    # dominant kernel = conv_umma_kernel<256> (about half of the step, see profiles/r1_ncu_launches_bench.csv)
+    dom = fam(lambda r: r["kind"] in ("conv3x3", "convT2x2") and r["block_n"] == 256 and not r.get("halo"))
+    halo64 = fam(lambda r: r.get("halo") and r["block_n"] == 64)
+    halo128 = fam(lambda r: r.get("halo") and r["block_n"] == 128)
+    allconv = fam(lambda r: r["kind"] in ("conv3x3", "convT2x2"))
+    roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": dom["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                "kernel": f"conv_umma_kernel<256> ({dom['launches']} launches per pass: 3x3 convs with Cout>=256 + 4 ConvT)",
+                "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass": dom["ms"],
+                "timing": f"CUDA events around every kernel of one {int(x4.shape[0])}-frame pass on the launching stream, min of 3",
+                "traffic_note": "ncu --set full per-launch DRAM bytes are in profiles/r1_ncu_full_*.txt (no re-reads: dec3.conv0 reads 411 MB = its two inputs)",
+                "other_kernels": {"conv_halo_kernel<64>": halo64, "conv_halo_kernel<128>": halo128, "all_tensor_core_convs": allconv},
                 "whole_net_frac_of_peak": (value / world) * FLOPS_PER_FRAME / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
