@@ -166,6 +166,11 @@ def main():
         run_reference(args)
         return
 
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -282,9 +287,12 @@ def main():
         v, sps, threads = time_cpu_reference(8, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"8 frames/step x 3 steps ({sps * 3:.1f} s) of the oracle fp32 PyTorch CPU pipeline"}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
