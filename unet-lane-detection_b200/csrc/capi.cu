@@ -198,8 +198,8 @@ int device_check() {
 }
 
 template <int BN>
-int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap* mo,
-                  const ub::ConvArgs& args, int slot, cudaStream_t st) {
+int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args, int slot,
+                  cudaStream_t st) {
   using Cfg = ub::ConvCfg<BN>;
   if (!g_attr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -211,7 +211,7 @@ int launch_conv_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   const int smem = Cfg::smem_bytes(args2.stages);
   const int total = args.tiles_w * args.tiles_h * args.tiles_b * args.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(a0, a1, w, mo[0], mo[1], mo[2], mo[3], args2);
+  ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -277,16 +277,16 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
   return UB_OK;
 }
 
-int launch_conv(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap* mo,
-                const ub::ConvArgs& args, cudaStream_t st) {
+int launch_conv(int block_n, const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args,
+                cudaStream_t st) {
   if (g_num_sms == 0) {
     int rc = device_check();
     if (rc != UB_OK) return rc;
   }
   switch (block_n) {
-    case 64: return launch_conv_t<64>(a0, a1, w, mo, args, 0, st);
-    case 128: return launch_conv_t<128>(a0, a1, w, mo, args, 1, st);
-    case 256: return launch_conv_t<256>(a0, a1, w, mo, args, 2, st);
+    case 64: return launch_conv_t<64>(ma, w, mo, args, 0, st);
+    case 128: return launch_conv_t<128>(ma, w, mo, args, 1, st);
+    case 256: return launch_conv_t<256>(ma, w, mo, args, 2, st);
   }
   return fail(UB_ERR_ARG, "unsupported BLOCK_N %d", block_n);
 }
@@ -453,6 +453,8 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.taps = (l.kind == L_CONV) ? 9 : 1;
   a.kc0 = l.C0 / 64;
   a.kc1 = l.C1 / 64;
+  a.kc2 = 0;
+  a.kc3 = 0;
   a.epi = (l.kind == L_CONV) ? ub::EPI_STORE : ub::EPI_CONVT;
   a.relu = l.relu;
   a.Cout = l.Cout;
@@ -734,7 +736,8 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
       if (rc != UB_OK) return rc;
     } else {
       ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, pool);
-      int rc = launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, st);
+      const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
+      int rc = launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
       if (rc != UB_OK) return rc;
     }
     if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
@@ -932,7 +935,8 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
   rc = make_umma_store_maps(l, y, pool, B);
   if (rc != UB_OK) return rc;
   ub::ConvArgs a = conv_args(l, B, B, bias, y, pool);
-  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
+  const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
+  return launch_conv(l.block_n, ma, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias, int B, int H, int W, int f, void* y,
@@ -960,7 +964,8 @@ int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias
   rc = make_umma_store_maps(l, y, nullptr, B);
   if (rc != UB_OK) return rc;
   ub::ConvArgs a = conv_args(l, B, B, bias, y, nullptr);
-  return launch_conv(l.block_n, l.mA0, l.mA1, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
+  const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
+  return launch_conv(l.block_n, ma, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,

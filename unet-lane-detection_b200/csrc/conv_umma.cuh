@@ -31,7 +31,7 @@ struct ConvArgs {
   int tiles_w, tiles_h, tiles_b;  // number of boxes along each axis
   int n_tiles;                    // N / BLOCK_N
   int taps;                       // 9 (3x3, pad 1) or 1 (pointwise)
-  int kc0, kc1;                   // 64-channel blocks taken from source 0 / source 1
+  int kc0, kc1, kc2, kc3;         // 64-channel blocks taken from activation sources 0..3 (concat / ConvT-dgrad quads)
   int epi;                        // EPI_*
   int relu;
   int stages;                     // operand ring depth (shared-memory split chosen by the host)
@@ -67,6 +67,7 @@ struct ConvCfg {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
                  const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                  const __grid_constant__ CUtensorMap tmO3, const ConvArgs a) {
@@ -112,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kchunks = a.kc0 + a.kc1;
+  const int kchunks = a.kc0 + a.kc1 + a.kc2 + a.kc3;
   const int num_kb = a.taps * kchunks;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int total_tiles = m_tiles * a.n_tiles;
@@ -142,8 +143,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_expect_tx(&full[stage], a.a_bytes + Cfg::B_BYTES);
             if (ch < a.kc0) {
               tma_load_4d(sA, &tmA0, &full[stage], ch * 64, w0 + dx, h0 + dy, b0);
-            } else {
+            } else if (ch < a.kc0 + a.kc1) {
               tma_load_4d(sA, &tmA1, &full[stage], (ch - a.kc0) * 64, w0 + dx, h0 + dy, b0);
+            } else if (ch < a.kc0 + a.kc1 + a.kc2) {
+              tma_load_4d(sA, &tmA2, &full[stage], (ch - a.kc0 - a.kc1) * 64, w0 + dx, h0 + dy, b0);
+            } else {
+              tma_load_4d(sA, &tmA3, &full[stage], (ch - a.kc0 - a.kc1 - a.kc2) * 64, w0 + dx, h0 + dy, b0);
             }
             tma_load_2d(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N);
             if (++stage == STAGES) {

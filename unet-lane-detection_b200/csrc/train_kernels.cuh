@@ -1,0 +1,470 @@
+// Bandwidth-bound kernels of the training step (reference: README.md:2060-2084 train_one_epoch,
+// 1855-1893 BCEDiceLoss, 2173-2174 AdamW). All tensors NHWC bf16 unless noted; per-channel statistics fp32.
+// BatchNorm runs in training mode: batch statistics, biased variance for normalisation, unbiased for the
+// running buffer, momentum 0.1 (PyTorch defaults used by nn.BatchNorm2d in README.md:1453,1456).
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h[i]);
+    f[2 * i + 1] = __high2float(h[i]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// Thread mapping shared by the per-channel reductions: C8 = C/8 threads cover one pixel (8 channels each), a block of
+// 256 threads covers 256/C8 pixels per step; requires C8 to divide 256 (C in {64,128,256,512,1024,2048}).
+// Per-block partial sums are combined through shared memory, then one atomicAdd per channel per block.
+
+// sum[c] += sum_p y[p][c], sumsq[c] += sum_p y[p][c]^2
+__global__ void __launch_bounds__(256)
+chan_stats_kernel(const uint4* __restrict__ y, size_t npix, int C8, float* __restrict__ sum, float* __restrict__ sumsq) {
+  extern __shared__ float red[];  // [2][256][8]
+  const int cl = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int ppb = 256 / C8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+    float f[8];
+    unpack8(__ldg(y + p * C8 + cl), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += f[i];
+      ss[i] = fmaf(f[i], f[i], ss[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 8 + i] = s[i];
+    red[2048 + threadIdx.x * 8 + i] = ss[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < ppb; ++j) {
+      a += red[(j * C8 + c / 8) * 8 + (c & 7)];
+      b += red[2048 + (j * C8 + c / 8) * 8 + (c & 7)];
+    }
+    atomicAdd(sum + c, a);
+    atomicAdd(sumsq + c, b);
+  }
+}
+
+// Per channel: batch mean / biased var -> scale = gamma*invstd, shift = beta - mean*scale; running stats update.
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count, float eps,
+                                   float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sum[c] / count;
+  const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  const float is = rsqrtf(var + eps);
+  mean[c] = m;
+  invstd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// a = relu(y*scale + shift)
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                     size_t n8, int C8, uint4* __restrict__ a) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8) * 8;
+    float f[8];
+    unpack8(__ldg(y + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c + k), __ldg(shift + c + k)), 0.f);
+    a[i] = pack8(f);
+  }
+}
+
+// Backward of (BN train + ReLU), pass 1: g = dA * [y*scale+shift > 0];  s1[c] += sum g, s2[c] += sum g * xhat.
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, size_t npix, int C8, float* __restrict__ s1,
+                          float* __restrict__ s2) {
+  extern __shared__ float red[];
+  const int cl = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int ppb = 256 / C8;
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale[cl * 8 + i];
+    sh[i] = shift[cl * 8 + i];
+    mu[i] = mean[cl * 8 + i];
+    is[i] = invstd[cl * 8 + i];
+  }
+  float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+    float fy[8], fd[8];
+    unpack8(__ldg(y + p * C8 + cl), fy);
+    unpack8(__ldg(dA + p * C8 + cl), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fd[i] : 0.f;
+      a1[i] += g;
+      a2[i] = fmaf(g, (fy[i] - mu[i]) * is[i], a2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 8 + i] = a1[i];
+    red[2048 + threadIdx.x * 8 + i] = a2[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < ppb; ++j) {
+      a += red[(j * C8 + c / 8) * 8 + (c & 7)];
+      b += red[2048 + (j * C8 + c / 8) * 8 + (c & 7)];
+    }
+    atomicAdd(s1 + c, a);
+    atomicAdd(s2 + c, b);
+  }
+}
+
+// pass 2: dY = gamma*invstd * (g - s1/N - xhat * s2/N)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ y, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ s1, const float* __restrict__ s2,
+                         float inv_count, size_t n8, int C8, uint4* __restrict__ dY) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8) * 8;
+    float fy[8], fd[8], o[8];
+    unpack8(__ldg(y + i), fy);
+    unpack8(__ldg(dA + i), fd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sc = __ldg(scale + c + k);
+      const float g = fmaf(fy[k], sc, __ldg(shift + c + k)) > 0.f ? fd[k] : 0.f;
+      const float xh = (fy[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k);
+      o[k] = sc * (g - __ldg(s1 + c + k) * inv_count - xh * __ldg(s2 + c + k) * inv_count);
+    }
+    dY[i] = pack8(o);
+  }
+}
+
+// Max-pool backward merged with the skip connection's other gradient:
+// dA[b,h,w,c] = (d_skip ? d_skip[b,h,w,c] : 0) + (pixel is the FIRST maximum of its 2x2 window ? dP[b,h/2,w/2,c] : 0)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip, int B,
+                       int H, int W, int C8, uint4* __restrict__ dA) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = i % C8;
+    size_t r = i / C8;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const size_t b = r / Ho;
+    const size_t base = ((b * H + 2 * ho) * W + 2 * wo) * C8 + c;
+    const size_t off[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
+    float v[4][8], g[8], o[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8(__ldg(a + base + off[k]), v[k]);
+    unpack8(__ldg(dP + i), g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (d_skip != nullptr) {
+        unpack8(__ldg(d_skip + base + off[k]), o[k]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[k][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int best = 0;
+      float m = v[0][e];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        if (v[k][e] > m) {  // strict '>' keeps the first maximum in (row, col) scan order, as ATen does
+          m = v[k][e];
+          best = k;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k == best) o[k][e] += g[e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dA[base + off[k]] = pack8(o[k]);
+  }
+}
+
+// Head backward: dA[p][c] = dz[p] * w[c] (bf16);  dw[c] += sum_p dz[p] * a[p][c];  db += sum_p dz[p]
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
+                uint4* __restrict__ dA, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float red[];
+  const int cl = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int ppb = 256 / C8;
+  float wv[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = w[cl * 8 + i];
+  float bsum = 0.f;
+  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+    const float g = __ldg(dz + p);
+    float fa[8], o[8];
+    unpack8(__ldg(a + p * C8 + cl), fa);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = fmaf(g, fa[i], acc[i]);
+      o[i] = g * wv[i];
+    }
+    dA[p * C8 + cl] = pack8(o);
+    if (cl == 0) bsum += g;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  red[2048 + threadIdx.x] = bsum;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float s = 0.f;
+    for (int j = 0; j < ppb; ++j) s += red[(j * C8 + c / 8) * 8 + (c & 7)];
+    atomicAdd(dw + c, s);
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int j = 0; j < 256; ++j) s += red[2048 + j];
+    atomicAdd(db, s);
+  }
+}
+
+// BCEWithLogits(pos_weight) + Dice (README.md:1868-1893), pass 1: sums[0..3] += {sum bce_i, sum sigma*t, sum sigma, sum t}
+__global__ void __launch_bounds__(256)
+bce_dice_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight,
+                       double* __restrict__ sums) {
+  __shared__ double red[4][256];
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float x = z[i], y = t[i];
+    const float lw = 1.f + (pos_weight - 1.f) * y;
+    const float bce = (1.f - y) * x + lw * (log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f));
+    const float sg = 1.f / (1.f + expf(-x));
+    s0 += bce;
+    s1 += sg * y;
+    s2 += sg;
+    s3 += y;
+  }
+  red[0][threadIdx.x] = s0;
+  red[1][threadIdx.x] = s1;
+  red[2][threadIdx.x] = s2;
+  red[3][threadIdx.x] = s3;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int j = 0; j < 256; ++j) s += red[threadIdx.x][j];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+// pass 2: losses[0..2] = {total, bce, dice};  dz = d total / d z
+__global__ void __launch_bounds__(256)
+bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight, float bce_w,
+                     float dice_w, float smooth, const double* __restrict__ sums, float* __restrict__ dz,
+                     float* __restrict__ losses) {
+  const double inter = sums[1], S = sums[2], T = sums[3];
+  const double num = 2.0 * inter + smooth, den = S + T + smooth;
+  const float inv_n = 1.f / static_cast<float>(n);
+  const float k_den = static_cast<float>(1.0 / den), k_ratio = static_cast<float>(num / (den * den));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float bce = static_cast<float>(sums[0] / static_cast<double>(n));
+    const float dice = static_cast<float>(1.0 - num / den);
+    losses[0] = bce_w * bce + dice_w * dice;
+    losses[1] = bce;
+    losses[2] = dice;
+  }
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float x = z[i], y = t[i];
+    const float sg = 1.f / (1.f + expf(-x));
+    const float dbce = (sg * (1.f + (pos_weight - 1.f) * y) - pos_weight * y) * inv_n;
+    // dice = 1 - num/den: d/dsigma = -(2t*den - num)/den^2 ; dsigma/dz = sigma(1-sigma)
+    const float ddice = -(2.f * y * k_den - k_ratio) * sg * (1.f - sg);
+    dz[i] = bce_w * dbce + dice_w * ddice;
+  }
+}
+
+// AdamW (torch.optim.AdamW semantics, README.md:2173-2174) on flat fp32 arrays; grad is pre-multiplied by grad_scale (1/world).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_scale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
+// dgrad weights: wd[ci][tap'][co] = w[co][ci][8 - tap'] (180-degree rotated, in/out swapped), bf16; w fp32 [Cout][Cin][3][3]
+__global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wd) {
+  const int total = Cin * 9 * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout;
+    const int tp = (i / Cout) % 9;
+    const int ci = i / (9 * Cout);
+    wd[i] = __float2bfloat16_rn(w[(static_cast<size_t>(co) * Cin + ci) * 9 + (8 - tp)]);
+  }
+}
+
+// ConvT dgrad weights: wd[ci][(quad, co)] = w[ci][co][quad] (GEMM N = Cin rows, K = 4f); w fp32 [Cin][f][2][2]
+__global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wd) {
+  const int total = Cin * 4 * f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % f;
+    const int quad = (i / f) % 4;
+    const int ci = i / (4 * f);
+    wd[i] = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * f + co) * 4 + quad]);
+  }
+}
+
+// packed fp32 gradients -> PyTorch layouts: conv gp[co][tap][ci] -> g[co][ci][tap]; convT gp[quad][co][ci] -> g[ci][co][quad]
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ gp, int Cout, int Cin, float* __restrict__ g) {
+  const int total = Cout * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9;
+    const int ci = (i / 9) % Cin;
+    const int co = i / (9 * Cin);
+    g[i] = gp[(static_cast<size_t>(co) * 9 + tap) * Cin + ci];
+  }
+}
+__global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, int f, float* __restrict__ g) {
+  const int total = Cin * f * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int quad = i % 4;
+    const int co = (i / 4) % f;
+    const int ci = i / (4 * f);
+    g[i] = gp[(static_cast<size_t>(quad) * f + co) * Cin + ci];
+  }
+}
+
+// per-channel sum of a bf16 NHWC tensor (ConvT bias gradient): out[c] += sum_p x[p][c]
+__global__ void __launch_bounds__(256)
+chan_sum_kernel(const uint4* __restrict__ x, size_t npix, int C8, float* __restrict__ out) {
+  extern __shared__ float red[];
+  const int cl = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int ppb = 256 / C8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+    float f[8];
+    unpack8(__ldg(x + p * C8 + cl), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float a = 0.f;
+    for (int j = 0; j < ppb; ++j) a += red[(j * C8 + c / 8) * 8 + (c & 7)];
+    atomicAdd(out + c, a);
+  }
+}
+
+// Stem weight gradient (Cin <= 4, Cout <= 128): dW[co][ci][tap] += sum_p dy[p][co] * x4[p+shift(tap)][ci]
+// x4: NHWC4 bf16 network input. Persistent blocks walk 16x16 pixel tiles; a thread owns up to 5 (co, tap) items x 4 input
+// channels in registers across ALL its tiles and flushes them with one atomicAdd each at the end.
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const uint2* __restrict__ x4, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int Cin, int Cout,
+                  float* __restrict__ dw /* fp32 [Cout][Cin][3][3] */) {
+  extern __shared__ float sm[];
+  float4* st = reinterpret_cast<float4*>(sm);                 // [18][18] input pixels (4 ch fp32)
+  float* sd = sm + 18 * 18 * 4;                                // [256 px][Cout] dy tile (fp32)
+  const int tiles_w = (W + 15) / 16, tiles_h = (H + 15) / 16;
+  const int total_tiles = tiles_w * tiles_h * B;
+  const int n_items = Cout * 9;
+  float acc[5][4];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int w0 = (tile % tiles_w) * 16;
+    const int h0 = ((tile / tiles_w) % tiles_h) * 16;
+    const int b = tile / (tiles_w * tiles_h);
+    __syncthreads();  // previous tile's smem fully consumed
+    for (int i = threadIdx.x; i < 18 * 18; i += blockDim.x) {
+      const int hh = h0 + i / 18 - 1, ww = w0 + i % 18 - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        const uint2 r = __ldg(x4 + (static_cast<size_t>(b) * H + hh) * W + ww);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+        v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      }
+      st[i] = v;
+    }
+    for (int i = threadIdx.x; i < 256 * Cout; i += blockDim.x) {
+      const int px = i / Cout, co = i % Cout;
+      const int hh = h0 + px / 16, ww = w0 + px % 16;
+      float v = 0.f;
+      if (hh < H && ww < W) v = __bfloat162float(dy[((static_cast<size_t>(b) * H + hh) * W + ww) * Cout + co]);
+      sd[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int item = threadIdx.x + k * 256;
+      if (item < n_items) {
+        const int co = item % Cout, tap = item / Cout;
+        const int r = tap / 3, s = tap % 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int px = 0; px < 256; ++px) {
+          const float g = sd[px * Cout + co];
+          const float4 xi = st[(px / 16 + r) * 18 + (px % 16) + s];
+          a0 = fmaf(g, xi.x, a0);
+          a1 = fmaf(g, xi.y, a1);
+          a2 = fmaf(g, xi.z, a2);
+          a3 = fmaf(g, xi.w, a3);
+        }
+        acc[k][0] += a0;
+        acc[k][1] += a1;
+        acc[k][2] += a2;
+        acc[k][3] += a3;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int item = threadIdx.x + k * 256;
+    if (item < n_items) {
+      const int co = item % Cout, tap = item / Cout;
+      for (int ci = 0; ci < Cin; ++ci) atomicAdd(dw + (static_cast<size_t>(co) * Cin + ci) * 9 + tap, acc[k][ci]);
+    }
+  }
+}
+
+}  // namespace ub

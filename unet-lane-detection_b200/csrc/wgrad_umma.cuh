@@ -1,0 +1,220 @@
+// Weight-gradient GEMM on tcgen05 tensor cores, directly on NHWC bf16 tensors (no transposes):
+//
+//   dW[co][tap][ci] += sum over pixels p of  dy[p][co] * x[p + shift(tap)][ci]        (README.md:2078 loss.backward())
+//
+// The reduction dimension (pixels) is the strided one in NHWC, so both operands are fed to the tensor core in
+// MN-major form: a TMA box (64 ch, TW, TH, TB) lands in shared memory as [128 pixel rows][64 channels], which is
+// exactly a 128B-swizzled MN-major UMMA block (8-row K groups 1024 B apart, 64-channel MN blocks LBO apart).
+// tools/mn_probe.cu verified the descriptor convention on B200.
+//
+// One CTA owns one output tile D[M = 128 "ci rows"][N = BLOCK_N co] of one tap over a slice of the pixel tiles
+// (split-K), then adds it to the fp32 gradient with red.global.add. The 128 rows are either 2 x 64 input channels
+// (Cin >= 128, possibly from two source tensors for the decoder concat) or, for Cin == 64, the SAME 64 channels at
+// two different taps (two shifted boxes), so M = 128 is always full.
+// Also used for ConvTranspose2d weight gradients: "taps" are the four (dy,dx) quads and the dy operand is read
+// through the strided quad views of the upsampled gradient.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+struct WgradArgs {
+  int B, H, W;                    // pixel grid of the reduction (conv: activation size; ConvT: input size)
+  int TW, TH, TB;
+  int tiles_w, tiles_h, tiles_b;
+  int taps;                       // 9 (3x3 conv), 4 (ConvT quads: dy operand view selected by tap), 1
+  int shift;                      // 1: tap -> spatial shift (tap/3-1, tap%3-1) of the x operand (3x3 conv)
+  int pair_taps;                  // 1: rows 0..63 = tap 2*m_tile, rows 64..127 = tap 2*m_tile+1 (Cin == 64)
+  int m_tiles;                    // Cin/128, or ceil(taps/2) when pair_taps
+  int n_tiles;                    // Cout / BLOCK_N
+  int ksplit;                     // CTAs sharing one output tile
+  int c_split;                    // channels of x source 0 (the rest come from source 1)
+  int Cin, Cout;
+  long long s_co, s_tap;          // dW index = co*s_co + tap*s_tap + ci
+  int a_bytes;                    // bytes of one x / dy box (16384 unless TB exceeds the batch)
+  float* dw;                      // fp32 gradient, accumulated atomically
+};
+
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int NB = BLOCK_N / 64;
+  static constexpr int STAGE_BYTES = (2 + NB) * 16384;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static_assert(STAGES >= 2, "need at least two stages");
+};
+
+// MN-major, 128B-swizzle shared-memory descriptor: LBO = bytes between 64-wide MN blocks, SBO = bytes between 8-row K groups.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                  const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
+                  const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const WgradArgs a) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NB = Cfg::NB;
+  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* done = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX0);
+    tma_prefetch_desc(&tmD0);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item: (output tile, K slice)
+  int wi = blockIdx.x;
+  const int ks = wi % a.ksplit;
+  wi /= a.ksplit;
+  const int n_tile = wi % a.n_tiles;
+  wi /= a.n_tiles;
+  const int m_tile = wi % a.m_tiles;
+  const int tap_o = a.pair_taps ? 0 : wi / a.m_tiles;  // tap of this tile (pair mode: taps come from m_tile)
+  const int ptiles = a.tiles_w * a.tiles_h * a.tiles_b;
+  const int k_lo = static_cast<int>(static_cast<long long>(ptiles) * ks / a.ksplit);
+  const int k_hi = static_cast<int>(static_cast<long long>(ptiles) * (ks + 1) / a.ksplit);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_lo; kt < k_hi; ++kt) {
+        const int w0 = (kt % a.tiles_w) * a.TW;
+        const int h0 = ((kt / a.tiles_w) % a.tiles_h) * a.TH;
+        const int b0 = (kt / (a.tiles_w * a.tiles_h)) * a.TB;
+        mbar_wait_parked(&empty[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + 2 * 16384;
+        mbar_expect_tx(&full[stage], (2 + NB) * a.a_bytes);
+        // x operand: two 64-row blocks
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          int tap = tap_o, c = m_tile * 128 + hb * 64;
+          if (a.pair_taps) {
+            tap = m_tile * 2 + hb;
+            if (tap >= a.taps) tap = a.taps - 1;  // odd tap count: the last block is a duplicate whose rows are dropped
+            c = 0;
+          }
+          int dy = 0, dx = 0;
+          if (a.shift) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          if (c < a.c_split) {
+            tma_load_4d(sA + hb * 16384, &tmX0, &full[stage], c, w0 + dx, h0 + dy, b0);
+          } else {
+            tma_load_4d(sA + hb * 16384, &tmX1, &full[stage], c - a.c_split, w0 + dx, h0 + dy, b0);
+          }
+        }
+        // dy operand: NB 64-channel blocks (ConvT: through the quad view of this tile's tap)
+        const CUtensorMap* md = &tmD0;
+        if (a.taps == 4) md = tap_o == 0 ? &tmD0 : tap_o == 1 ? &tmD1 : tap_o == 2 ? &tmD2 : &tmD3;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          tma_load_4d(sB + nb * 16384, md, &full[stage], n_tile * BLOCK_N + nb * 64, w0, h0, b0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // both operands MN-major: bits 15 / 16 of the instruction descriptor
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N) | (1u << 15) | (1u << 16);
+      const uint64_t d_hi = make_sw128_mnmajor_desc(0, 16384, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_lo; kt < k_hi; ++kt) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = d_hi + (sA >> 4);
+        const uint64_t db = d_hi + ((sA + 2 * 16384) >> 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // 16 pixel rows per MMA = two 8-row groups = 2048 B
+          umma_f16(tmem_base, da + j * 128, db + j * 128, idesc, (kt > k_lo || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue: 4 warps, fp32 atomic accumulation
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    int tap = tap_o, ci = m_tile * 128 + m;
+    bool live = k_hi > k_lo;
+    if (a.pair_taps) {
+      tap = m_tile * 2 + (m >> 6);
+      ci = m & 63;
+      live = live && tap < a.taps;
+    }
+    float* base = a.dw + static_cast<long long>(tap) * a.s_tap + ci;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = n_tile * BLOCK_N + c * 32 + j;
+          atomicAdd(base + static_cast<long long>(co) * a.s_co, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace ub
