@@ -149,6 +149,79 @@ int unet_b200_head(const void* x_dev, const float* w_dev, float bias, size_t npi
                    float* probs_dev, uint8_t* mask_dev, float threshold, void* stream);
 int unet_b200_maxpool2x2(const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream);
 
+/* ---- training step (README.md:2060-2084 train_one_epoch, model.train(): BatchNorm uses batch statistics) --------- *
+ * A trainer is a fixed-batch plan that keeps every layer's activations for the backward pass.
+ * Parameters and gradients are FLAT fp32 device arrays in model.parameters() order (registration order of
+ * README.md:1427-1447: encoder_blocks.i.{0.weight,1.weight,1.bias,3.weight,4.weight,4.bias}, decoder_blocks.2j.{weight,
+ * bias}, decoder_blocks.2j+1.{...}, bottleneck.{...}, output.{weight,bias}); tensor i starts at
+ * trainer_tensor_offset(i) and the array holds trainer_num_params() floats. Features must be powers of two in
+ * [64,1024], features[0] <= 128; batch must give every level's 128-pixel box a multiple of 16 rows. */
+typedef struct unet_b200_trainer unet_b200_trainer;
+int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, int in_channels, int out_channels,
+                             const int* features, int levels);
+void unet_b200_trainer_destroy(unet_b200_trainer* t);
+size_t unet_b200_trainer_workspace_bytes(const unet_b200_trainer* t);
+long long unet_b200_trainer_num_params(const unet_b200_trainer* t);
+int unet_b200_trainer_num_tensors(const unet_b200_trainer* t);
+long long unet_b200_trainer_tensor_offset(const unet_b200_trainer* t, int idx); /* idx == num_tensors: total */
+/* workspace_dev: caller-owned, 1024-byte aligned, trainer_workspace_bytes() bytes. */
+int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev);
+/* UNet.forward in train mode (README.md:1460-1481 under model.train()): x bf16 NHWC4 [batch][H][W][4] -> logits fp32
+ * [batch][H][W]. running_mean / running_var: HOST arrays of plan_num_convs device pointers (fp32 [C] each, plan conv
+ * order) updated with `momentum` and the unbiased batch variance as nn.BatchNorm2d does; either may be NULL. */
+int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4_dev, const float* params_dev,
+                            float* const* running_mean, float* const* running_var, float momentum, float eps,
+                            float* logits_dev, void* stream);
+/* loss.backward() (README.md:2078) from d loss / d logits (fp32 [batch][H][W]): overwrites grads_dev (flat, same layout
+ * as params_dev) with the gradient of every parameter. Needs the activations of the preceding train_forward. */
+int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits_dev, const float* params_dev, float* grads_dev,
+                             void* stream);
+/* BCEDiceLoss (README.md:1855-1893): losses3_dev = {total, bce, dice}; dlogits_dev (optional) = d total / d logits.
+ * target fp32, same shape as logits; scratch4_dev: 4 doubles. */
+int unet_b200_bce_dice_loss(const float* logits_dev, const float* target_dev, size_t n, float pos_weight, float bce_weight,
+                            float dice_weight, float smooth, double* scratch4_dev, float* losses3_dev, float* dlogits_dev,
+                            void* stream);
+/* torch.optim.AdamW step (README.md:2173-2174) on flat fp32 arrays; grads are multiplied by grad_scale first
+ * (1/world_size after a gradient all-reduce(sum)); step counts from 1. */
+int unet_b200_adamw_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, size_t n,
+                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                         void* stream);
+
+/* ---- single training ops (same kernels the trainer runs; exposed for parity tests and reuse) ------------------------ *
+ * All activations bf16 NHWC, gradients of activations bf16 NHWC, weight gradients fp32 in the PyTorch layout and
+ * ACCUMULATED into dw (zero it first). */
+/* dgrad operand of a 3x3 conv: wd bf16 [Cin][9][Cout], wd[ci][t][co] = w[co][ci][8-t]; the input gradient is then
+ * unet_b200_conv3x3(dy, Cout, NULL, 0, wd, zero_bias, ..., Cout=Cin, relu=0). */
+int unet_b200_pack_conv3x3_dgrad(const float* w_dev, int Cout, int Cin, void* wd_dev, void* stream);
+/* dgrad operand of ConvTranspose2d(Cin, f, 2, 2): wd bf16 [Cin][4f], wd[ci][q*f+co] = w[ci][co][q]. */
+int unet_b200_pack_convT2x2_dgrad(const float* w_dev, int Cin, int f, void* wd_dev, void* stream);
+/* dw[Cout][C0+C1][3][3] += conv-weight gradient for x = cat(x0, x1) [B,H,W,C0|C1] and dy [B,H,W,Cout].
+ * C0+C1 must be 64 or a multiple of 128 (with C0 a multiple of 64). */
+int unet_b200_conv3x3_wgrad(const void* x0_dev, int C0, const void* x1_dev, int C1, const void* dy_dev, int B, int H, int W,
+                            int Cout, float* dw_dev, void* stream);
+/* Stem: x NHWC4 bf16, dy [B,H,W,Cout] -> dw[Cout][Cin][3][3] += ... (Cout == 64 on tensor cores, else Cout <= 128). */
+int unet_b200_stem_wgrad(const void* x_nhwc4_dev, const void* dy_dev, int B, int H, int W, int Cin, int Cout, float* dw_dev,
+                         void* stream);
+/* ConvT backward. x [B,H,W,Cin]; dup = gradient w.r.t. the [B,2H,2W,f] output with a pixel pitch of dup_pitch elements
+ * (>= f: it may be a channel slice of a wider tensor). dw fp32 [Cin][f][2][2] +=, dbias fp32 [f] += (optional). */
+int unet_b200_convT2x2_wgrad(const void* x_dev, int Cin, const void* dup_dev, int dup_pitch, int B, int H, int W, int f,
+                             float* dw_dev, float* dbias_dev, void* stream);
+int unet_b200_convT2x2_dgrad(const void* dup_dev, int dup_pitch, const void* wd_dev, int B, int H, int W, int Cin, int f,
+                             void* dx_dev, void* stream);
+/* BatchNorm2d (training mode) + ReLU (+ optional 2x2 max-pool) on a raw conv output y [B,H,W,C]:
+ * stats4 fp32 [4][C] receives {mean, invstd, scale, shift}; running stats (optional) are updated with `momentum`;
+ * scratch2: 2*C doubles. a = relu(y*scale+shift); pool (optional) = maxpool2x2(a). */
+int unet_b200_bn_relu_train_fwd(const void* y_dev, const float* gamma_dev, const float* beta_dev, int B, int H, int W, int C,
+                                float eps, float momentum, float* running_mean_dev, float* running_var_dev, void* a_dev,
+                                void* pool_dev, float* stats4_dev, double* scratch2_dev, void* stream);
+/* Backward of the same: g holds d loss / d a on entry and d loss / d y on return (in place); dgamma/dbeta fp32 [C]. */
+int unet_b200_bn_relu_bwd(void* g_dev, const void* y_dev, const float* stats4_dev, int B, int H, int W, int C,
+                          float* dgamma_dev, float* dbeta_dev, void* stream);
+/* dA = dskip (optional, pixel pitch skip_pitch elements) + max-pool backward of dP through a [B,H,W,C]
+ * (first maximum in scan order wins, as ATen). */
+int unet_b200_maxpool2x2_bwd(const void* a_dev, const void* dP_dev, const void* dskip_dev, int skip_pitch, int B, int H,
+                             int W, int C, void* dA_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

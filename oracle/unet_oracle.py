@@ -226,6 +226,61 @@ def forward_bf16_emulated(model: UNetOracle, x: torch.Tensor, return_feats: bool
     return (logits, feats) if return_feats else logits
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding point for activations: the value is rounded forward, its gradient backward (both live in bf16)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return bf16_round(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bf16_round(g)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """bf16 rounding point for weights: the operand copy is bf16, the weight gradient stays fp32."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return bf16_round(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def forward_train_bf16_emulated(model: UNetOracle, x: torch.Tensor) -> torch.Tensor:
+    """Training-mode forward (batch-statistics BatchNorm, README.md:2062) with the B200 path's rounding points,
+    differentiable: conv operands, raw conv outputs y, activations a = relu(bn(y)) and every activation gradient are
+    rounded to bf16; statistics, accumulation, weight gradients and the head stay fp32. Like forward_bf16_emulated this
+    is NOT the parity target (model(x) in fp32 is); it separates rounding-by-design (ReLU / max-pool decisions that flip
+    on near-ties) from kernel bugs in the gradient tests. Running statistics of `model` are updated as a side effect."""
+    r, rw = _RoundBoth.apply, _RoundFwd.apply
+
+    def block(seq, t):
+        for ci, bi in ((0, 1), (3, 4)):
+            bn = seq[bi]
+            y = r(F.conv2d(t, rw(seq[ci].weight), None, padding=1))
+            t = r(F.relu(F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)))
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+        return t
+
+    t = r(x)
+    kept = []
+    for enc in model.encoder_blocks:
+        t = block(enc, t)
+        kept.append(t)
+        t = F.max_pool2d(t, 2)
+    t = block(model.bottleneck, t)
+    for level in range(len(model.decoder_blocks) // 2):
+        up = model.decoder_blocks[2 * level]
+        t = r(F.conv_transpose2d(t, rw(up.weight), up.bias, stride=2))
+        t = block(model.decoder_blocks[2 * level + 1], torch.cat([kept[-1 - level], t], dim=1))
+    return F.conv2d(t, model.output.weight, model.output.bias)
+
+
 def mask_agreement(logits_a: torch.Tensor, logits_b: torch.Tensor, threshold: float = 0.5, band: float = 0.0):
     """Fraction of pixels whose thresholded masks agree; pixels with |logit_b - logit(thr)| < band excluded."""
     z = float(np.log(threshold / (1 - threshold)))

@@ -1,0 +1,313 @@
+"""GPU (B200): the training step - every backward kernel against a plain PyTorch fp32
+reference of the same op on the same bf16 inputs, the fused loss against the golden values produced by the reference's
+own BCEDiceLoss listing, AdamW against torch.optim.AdamW, and the whole step against the oracle (fp32 and
+bf16-emulated)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances. Operands are the SAME bf16 values on both sides, so the per-kernel checks only see fp32 accumulation-order
+# differences (weight gradients, statistics) or one bf16 rounding of the result (activation gradients).
+WGRAD_REL = 2e-3       # relative L2 error of an fp32 weight gradient
+ACT_REL = 6e-3         # max |err| / max |ref| of a bf16-rounded activation (gradient): 2^-8 plus accumulation noise
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import unet_lane_detection_b200 as mod
+    return mod
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def nhwc(t):  # NCHW fp32 (CPU) -> NHWC bf16 (CUDA)
+    return bf(t).permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def nchw(t):  # NHWC (CUDA) -> NCHW fp32 (CPU)
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def rel_max(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return bf(torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).float()
+
+
+# ---------------------------------------------------------------------------------------------- wgrad / dgrad
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", [
+    (2, 16, 16, 64, 0, 64),      # Cin == 64: two taps share one 128-row tile
+    (3, 24, 40, 128, 0, 128),    # ragged tiles, batch not a multiple of the tile
+    (2, 16, 16, 64, 64, 64),     # decoder concat: two sources
+    (2, 8, 8, 256, 0, 256),      # BLOCK_N 256, batch folded into the pixel tile
+    (4, 4, 4, 256, 256, 256),    # deepest levels: 4x4 maps, 8 images per tile
+    (1, 32, 16, 128, 0, 64),
+])
+def test_conv3x3_wgrad(U, B, H, W, C0, C1, Cout):
+    x = rnd(B, C0 + C1, H, W, seed=1)
+    dy = rnd(B, Cout, H, W, seed=2, scale=0.1)
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, C0 + C1, 3, 3), dy, padding=1)
+    x0 = nhwc(x[:, :C0])
+    x1 = nhwc(x[:, C0:]) if C1 else None
+    got = U.ops.conv3x3_wgrad(x0, nhwc(dy), x1).cpu()
+    assert rel_l2(got, ref) <= WGRAD_REL, rel_l2(got, ref)
+    # accumulation semantics: a second call adds
+    assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (2, 16, 24, 128, 64), (3, 8, 8, 256, 512), (2, 32, 32, 64, 128)])
+def test_conv3x3_dgrad(U, B, H, W, Cin, Cout):
+    w = rnd(Cout, Cin, 3, 3, seed=3, scale=0.05)
+    dy = rnd(B, Cout, H, W, seed=4)
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w, dy, padding=1)
+    wd = U.ops.pack_conv3x3_dgrad(w.cuda())
+    got = nchw(U.ops.conv3x3_dgrad(nhwc(dy), wd))
+    assert rel_max(got, ref) <= ACT_REL, rel_max(got, ref)
+
+
+def test_stem_wgrad(U):
+    for B, H, W, cout in ((3, 32, 24, 64), (2, 16, 16, 128), (5, 16, 8, 64)):
+        x = rnd(B, 3, H, W, seed=5)
+        dy = rnd(B, cout, H, W, seed=6, scale=0.1)
+        ref = torch.nn.grad.conv2d_weight(x, (cout, 3, 3, 3), dy, padding=1)
+        x4 = U.ops.nchw_to_nhwc4(x.cuda())
+        got = U.ops.stem_wgrad(x4, nhwc(dy), 3).cpu()
+        assert rel_l2(got, ref) <= WGRAD_REL, (cout, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("B,H,W,f,sliced", [(2, 8, 8, 64, True), (3, 4, 12, 128, True), (2, 8, 8, 64, False), (8, 2, 2, 256, True)])
+def test_convT_backward(U, B, H, W, f, sliced):
+    cin = 2 * f
+    x = rnd(B, cin, H, W, seed=7)
+    w = rnd(cin, f, 2, 2, seed=8, scale=0.05)
+    dup = rnd(B, f, 2 * H, 2 * W, seed=9, scale=0.1)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = torch.zeros(f, requires_grad=True)
+    F.conv_transpose2d(xr, wr, br, stride=2).backward(dup)
+    # the gradient lives in the LAST f channels of a [B,2H,2W,2f] concat gradient (sliced) or stands alone
+    d = nhwc(dup)
+    if sliced:
+        d = torch.cat([torch.full_like(d, 7.0), d], dim=3).contiguous()
+    dw, db = U.ops.convT2x2_wgrad(nhwc(x), d, f)
+    assert rel_l2(dw.cpu(), wr.grad) <= WGRAD_REL
+    assert rel_l2(db.cpu(), br.grad) <= WGRAD_REL
+    dx = nchw(U.ops.convT2x2_dgrad(d, U.ops.pack_convT2x2_dgrad(w.cuda()), f))
+    assert rel_max(dx, xr.grad) <= ACT_REL
+
+
+# ---------------------------------------------------------------------------------------------- BN / pool
+@pytest.mark.parametrize("B,H,W,C,pool", [(4, 16, 16, 64, True), (3, 8, 12, 128, False), (8, 4, 4, 1024, False), (2, 32, 32, 64, False)])
+def test_bn_relu_train_forward_backward(U, B, H, W, C, pool):
+    y = rnd(B, C, H, W, seed=10) * 1.7 + 0.3
+    y = bf(y).float()
+    g = torch.Generator().manual_seed(11)
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a_ref = F.relu(F.batch_norm(yr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5))
+    rm_d, rv_d = rm.cuda(), rv.cuda()
+    a, p, stats = U.ops.bn_relu_train_fwd(nhwc(y), gamma.cuda(), beta.cuda(), 1e-5, 0.1, rm_d, rv_d, pool=pool)
+    assert rel_max(nchw(a), a_ref.detach()) <= ACT_REL
+    assert rel_l2(rm_d.cpu(), rm_ref) <= 1e-5 and rel_l2(rv_d.cpu(), rv_ref) <= 1e-5
+    if pool:
+        assert torch.equal(nchw(p), F.max_pool2d(nchw(a), 2))      # bit-exact pool of the kernel's own activation
+    dA = rnd(B, C, H, W, seed=12, scale=0.1)
+    a_ref.backward(dA)
+    dY, dgamma, dbeta = U.ops.bn_relu_bwd(nhwc(dA), nhwc(y), stats)
+    assert rel_l2(dgamma.cpu(), gr.grad) <= WGRAD_REL and rel_l2(dbeta.cpu(), br.grad) <= WGRAD_REL
+    assert rel_max(nchw(dY), yr.grad) <= ACT_REL
+
+
+def test_maxpool_backward_ties_and_skip(U):
+    B, H, W, C = 3, 8, 12, 64
+    a = F.relu(rnd(B, C, H, W, seed=13))            # ReLU output: many exact-zero ties inside windows
+    a[:, :, 0:2, 0:2] = 1.5                          # an all-equal window
+    dP = rnd(B, C, H // 2, W // 2, seed=14)
+    dskip = rnd(B, C, H, W, seed=15)
+    ar = a.clone().requires_grad_(True)
+    F.max_pool2d(ar, 2).backward(dP)
+    ref = bf(ar.grad + dskip).float()
+    skip_wide = torch.cat([nhwc(dskip), torch.full((B, H, W, C), 3.0, dtype=torch.bfloat16, device="cuda")], dim=3).contiguous()
+    got = nchw(U.ops.maxpool2x2_bwd(nhwc(a), nhwc(dP), skip_wide))
+    assert torch.equal(got, ref)                     # bit-exact, including which element of a tie receives the gradient
+    got2 = nchw(U.ops.maxpool2x2_bwd(nhwc(a), nhwc(dP)))
+    assert torch.equal(got2, bf(ar.grad).float())
+
+
+# ---------------------------------------------------------------------------------------------- loss / optimizer
+def test_fused_loss_matches_reference_listing_golden(U, golden_dir):
+    g = np.load(os.path.join(golden_dir, "loss_small.npz"))
+    keys = set(g.files)
+    logits, target = torch.from_numpy(g["logits"]), torch.from_numpy(g["target"])
+    losses, dz = U.bce_dice_loss(logits.cuda(), target.cuda(), pos_weight=float(g["pos_weight"]) if "pos_weight" in keys else 3.0)
+    want = torch.tensor([float(g["total"]), float(g["bce"]), float(g["dice"])])
+    assert (losses.cpu() - want).abs().max().item() <= 2e-6
+    assert rel_l2(dz.cpu().reshape(-1), torch.from_numpy(g["grad"]).reshape(-1)) <= 1e-5
+
+
+def test_fused_loss_large_and_extreme_logits(U):
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(4, 1, 224, 224, generator=gen) * 8            # saturating sigmoids on both sides
+    t = (torch.rand(4, 1, 224, 224, generator=gen) < 0.085).float()
+    crit = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]), smooth=1e-6)
+    zr = z.clone().requires_grad_(True)
+    tot, bce, dice = crit(zr, t)
+    tot.backward()
+    losses, dz = U.bce_dice_loss(z.cuda(), t.cuda())
+    assert (losses.cpu() - torch.stack([tot, bce, dice]).detach()).abs().max().item() <= 1e-5
+    assert rel_l2(dz.cpu(), zr.grad) <= 1e-5
+    # all-negative target (empty mask): Dice term must stay finite
+    losses0, dz0 = U.bce_dice_loss(z.cuda(), torch.zeros_like(t).cuda())
+    assert torch.isfinite(losses0).all() and torch.isfinite(dz0).all()
+
+
+def test_adamw_kernel_matches_torch(U):
+    gen = torch.Generator().manual_seed(5)
+    n = 100_003
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-4, weight_decay=1e-4)      # README.md:2173-2174
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        gr = torch.randn(n, generator=gen) * (10.0 ** torch.randint(-4, 2, (n,), generator=gen).float())
+        ref.grad = gr.clone()
+        opt.step()
+        U.ops.adamw_step(p, (gr * 2).cuda(), m, v, step, grad_scale=0.5)   # grad_scale folds the 1/world of a summed all-reduce
+        assert (p.cpu() - ref.detach()).abs().max().item() <= 5e-7, step   # 1-2 ulp at |p| ~ 4
+
+
+# ---------------------------------------------------------------------------------------------- whole step
+def make_train_pair(U, feats, seed=0, gain=10.0):
+    torch.manual_seed(seed)
+    ref = O.UNetOracle(3, 1, feats).train()
+    O.randomize_bn_(ref, seed=1)
+    O.scale_head_(ref, gain)
+    net = U.UNet(3, 1, feats)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda().train()
+
+
+@pytest.mark.parametrize("feats,H,W,B", [([64, 128], 32, 48, 4), ([64, 128, 256, 512], 64, 64, 8)])
+def test_train_step_against_oracle(U, feats, H, W, B):
+    """model.train(); loss = criterion(model(x), y); loss.backward() - README.md:2071-2078 - through the drop-in module
+    with the oracle's own criterion, against the fp32 oracle and against the oracle with the B200 rounding points."""
+    ref, net = make_train_pair(U, feats)
+    emu = copy.deepcopy(ref)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, 3, H, W, generator=g)
+    y = (torch.rand(B, 1, H, W, generator=g) < 0.085).float()           # 8.5 % positives (README.md:2534)
+    crit = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]), smooth=1e-6)
+    out_ref = ref(x)
+    loss_ref = crit(out_ref, y)[0]
+    loss_ref.backward()
+    crit(O.forward_train_bf16_emulated(emu, x), y)[0].backward()
+
+    out = net(x.cuda())
+    assert out.shape == (B, 1, H, W) and out.requires_grad
+    crit_gpu = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]).cuda(), smooth=1e-6)
+    loss = crit_gpu(out, y.cuda())[0]
+    loss.backward()
+    rng = max(1.0, out_ref.abs().max().item())
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= 2e-2 * rng * 1.5   # batch-stat BN amplifies bf16 noise
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    for (n, p), (_, q), (_, e) in zip(ref.named_parameters(), net.named_parameters(), emu.named_parameters()):
+        assert q.grad is not None and q.grad.shape == p.grad.shape, n
+        gq = q.grad.detach().cpu()
+        err, floor = rel_l2(gq, p.grad), rel_l2(e.grad, p.grad)
+        # not worse than the same network evaluated in PyTorch with bf16 rounding at the same places
+        assert err <= 1.3 * floor + 0.02, (n, err, floor)
+        assert F.cosine_similarity(gq.reshape(-1), p.grad.reshape(-1), dim=0).item() >= 0.85, n
+    # the last layers see no ReLU / pool decision flips: tight
+    assert rel_l2(net.output.weight.grad.cpu(), ref.output.weight.grad) <= 5e-3
+    assert rel_l2(net.output.bias.grad.cpu(), ref.output.bias.grad) <= 5e-3
+    # BatchNorm buffers follow nn.BatchNorm2d (momentum 0.1, unbiased running variance, num_batches_tracked)
+    for (n, b), (_, c) in zip(ref.named_buffers(), net.named_buffers()):
+        if n.endswith("num_batches_tracked"):
+            assert int(b) == int(c) == 1
+        else:
+            assert rel_l2(c.detach().cpu(), b) <= 5e-3, n
+
+
+def test_fused_step_trains_and_eval_sees_new_weights(U):
+    """FusedTrainStep (loss + backward + AdamW kernels): loss goes down on a fixed batch; eval() afterwards uses the
+    updated parameters and running statistics (packed inference weights are refreshed)."""
+    ref, net = make_train_pair(U, [64, 128], gain=1.0)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 3, 32, 32, generator=g).cuda()
+    y = torch.zeros(8, 1, 32, 32)
+    y[:, :, 8:24, 12:20] = 1.0
+    y = y.cuda()
+    net.eval()
+    with torch.no_grad():
+        before = net(x).clone()
+    net.train()
+    step = U.FusedTrainStep(net, lr=1e-3)
+    first = step.step(x, y).cpu()
+    for _ in range(30):
+        last = step.step(x, y)
+    last = last.cpu()
+    assert torch.isfinite(last).all() and last[0].item() < 0.8 * first[0].item(), (first, last)
+    net.eval()
+    with torch.no_grad():
+        after = net(x)
+    assert (after - before).abs().max().item() > 1e-2
+    # state_dict round trip into the oracle reproduces the eval logits: parameters and BN buffers are ordinary tensors
+    ref.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x.cpu())
+    assert (after.cpu() - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
+def test_fused_step_equals_autograd_path(U):
+    """The fused step's gradients are the autograd path's gradients (same kernels), and one AdamW step matches
+    torch.optim.AdamW applied to those gradients."""
+    _, net_a = make_train_pair(U, [64, 128])
+    _, net_b = make_train_pair(U, [64, 128])
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(4, 3, 32, 32, generator=g).cuda()
+    y = (torch.rand(4, 1, 32, 32, generator=g) < 0.2).float().cuda()
+    opt = torch.optim.AdamW(net_a.parameters(), lr=1e-4, weight_decay=1e-4)
+    crit = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]).cuda(), smooth=1e-6)
+    opt.zero_grad()
+    crit(net_a(x), y)[0].backward()
+    step = U.FusedTrainStep(net_b)
+    step.step(x, y)
+    ga = torch.cat([p.grad.reshape(-1) for p in net_a.parameters()])
+    assert rel_l2(step.last_grads, ga) <= 1e-2      # atomics: summation order differs run to run, a few bf16 roundings flip
+    opt.step()
+    pa = torch.cat([p.detach().reshape(-1) for p in net_a.parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in net_b.parameters()])
+    assert (pa - pb).abs().max().item() <= 2.5e-4   # first Adam step moves every weight by ~lr; sign flips of ~0 grads allowed
+    assert ((pa - pb).abs() > 1e-6).float().mean().item() < 0.05
+
+
+def test_train_mode_errors(U):
+    _, net = make_train_pair(U, [64, 128])
+    with pytest.raises(RuntimeError):
+        net(torch.randn(2, 3, 32, 32))                       # CPU tensor: no fallback
+    with pytest.raises(Exception):
+        net(torch.randn(1, 3, 8, 8).cuda())                  # batch too small for the 2x2 level's pixel box

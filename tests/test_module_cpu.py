@@ -44,11 +44,55 @@ def test_no_cpu_fallback():
     m = U.UNet(3, 1, [64, 128]).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 3, 32, 32))
-    m.train()
-    with pytest.raises(RuntimeError, match="training-mode"):
+    m.train()                                                  # the training path has no CPU fallback either
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 3, 32, 32))
     with pytest.raises(ValueError):
         U.ops.conv3x3(torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16), torch.zeros(64, 9, 64), torch.zeros(64))
+
+
+def test_flat_parameters_keep_identity_and_state_dict():
+    """training.flatten_parameters_: every Parameter becomes a view of one flat fp32 buffer (parameters() order) without
+    changing identity, values, names or the state_dict - the optimizer created before flattening stays valid."""
+    from unet_lane_detection_b200.training import flatten_parameters_
+    torch.manual_seed(0)
+    m = U.UNet(3, 1, [64, 128])
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-4)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    ids = [id(p) for p in m.parameters()]
+    flat = flatten_parameters_(m)
+    assert flat.numel() == sum(p.numel() for p in m.parameters())
+    assert [id(p) for p in m.parameters()] == ids
+    off = 0
+    for p in m.parameters():
+        assert p.data_ptr() == flat.data_ptr() + 4 * off
+        off += p.numel()
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    assert flatten_parameters_(m) is flat                      # idempotent
+    flat.add_(1.0)                                             # a kernel writing the flat buffer updates every parameter
+    assert torch.equal(m.output.bias.detach(), before["output.bias"] + 1.0)
+    assert {id(p) for g in opt.param_groups for p in g["params"]} == set(ids)
+
+
+def test_trainer_layout_matches_parameters():
+    """The C library's flat parameter layout (unet_b200_trainer_tensor_offset) is model.parameters() order."""
+    import ctypes as C
+    from unet_lane_detection_b200._lib import check, lib
+    for feats in ([64, 128], [64, 128, 256, 512]):
+        m = U.UNet(3, 1, feats)
+        h = C.c_void_p()
+        check(lib.unet_b200_trainer_create(C.byref(h), 8, 64, 64, 3, 1, (C.c_int * len(feats))(*feats), len(feats)))
+        nt = lib.unet_b200_trainer_num_tensors(h)
+        offs = [lib.unet_b200_trainer_tensor_offset(h, i) for i in range(nt + 1)]
+        sizes = [p.numel() for p in m.parameters()]
+        assert nt == len(sizes) and [b - a for a, b in zip(offs, offs[1:])] == sizes
+        assert lib.unet_b200_trainer_num_params(h) == sum(sizes)
+        assert lib.unet_b200_trainer_workspace_bytes(h) > 0
+        lib.unet_b200_trainer_destroy(h)
+    h = C.c_void_p()
+    assert lib.unet_b200_trainer_create(C.byref(h), 8, 64, 64, 3, 1, (C.c_int * 2)(64, 192), 2) != 0   # not a power of two
+    assert b"features" in lib.unet_b200_last_error()
 
 
 def test_executor_rejects_without_gpu():

@@ -13,5 +13,6 @@ from .ops import (  # noqa: F401
 )
 from .unet import UNet  # noqa: F401
 from .executor import B200_model_container, B200LaneInference  # noqa: F401
+from .training import FusedTrainStep, bce_dice_loss  # noqa: F401
 
-__all__ = ["UNet", "B200_model_container", "B200LaneInference"]
+__all__ = ["UNet", "B200_model_container", "B200LaneInference", "FusedTrainStep", "bce_dice_loss"]

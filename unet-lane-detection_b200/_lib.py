@@ -52,6 +52,26 @@ _SIGS = {
     "unet_b200_stem_conv_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_head": (i32, [vp, vp, f32, sz, i32, vp, vp, vp, f32, vp]),
     "unet_b200_maxpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_trainer_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
+    "unet_b200_trainer_destroy": (None, [vp]),
+    "unet_b200_trainer_workspace_bytes": (sz, [vp]),
+    "unet_b200_trainer_num_params": (C.c_longlong, [vp]),
+    "unet_b200_trainer_num_tensors": (i32, [vp]),
+    "unet_b200_trainer_tensor_offset": (C.c_longlong, [vp, i32]),
+    "unet_b200_trainer_bind": (i32, [vp, vp]),
+    "unet_b200_train_forward": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), f32, f32, vp, vp]),
+    "unet_b200_train_backward": (i32, [vp, vp, vp, vp, vp]),
+    "unet_b200_bce_dice_loss": (i32, [vp, vp, sz, f32, f32, f32, f32, vp, vp, vp, vp]),
+    "unet_b200_adamw_step": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
+    "unet_b200_pack_conv3x3_dgrad": (i32, [vp, i32, i32, vp, vp]),
+    "unet_b200_pack_convT2x2_dgrad": (i32, [vp, i32, i32, vp, vp]),
+    "unet_b200_conv3x3_wgrad": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_stem_wgrad": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_convT2x2_wgrad": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "unet_b200_convT2x2_dgrad": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_bn_relu_train_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "unet_b200_bn_relu_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "unet_b200_maxpool2x2_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -474,6 +474,71 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   return a;
 }
 
+// Build the tensor maps of one stand-alone 3x3 conv (or ConvT when kind == L_CONVT) on explicit device pointers.
+// x1 may be null (C1 == 0). Used by the single-layer entry points and by the trainer (train_capi.cuh).
+int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const void* x1, int C1, const void* wp, void* y,
+                     void* pool, int B, int H, int W, int Cout, int relu, bool allow_halo) {
+  memset(&l, 0, sizeof(l));
+  l.kind = kind;
+  l.H = H;
+  l.W = W;
+  l.C0 = C0;
+  l.C1 = C1;
+  l.Cout = Cout;
+  l.relu = relu;
+  l.set = true;
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  int rc;
+  if (kind == L_CONVT) {
+    l.block_n = pick_block_n(4 * Cout);
+    rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+    l.mA1 = l.mA0;
+    rc = make_w_map(&l.mW, wp, 4 * Cout, C0, l.block_n);
+    if (rc != UB_OK) return rc;
+    return make_umma_store_maps(l, y, nullptr, B);
+  }
+  l.block_n = pick_block_n(Cout);
+  if (allow_halo && halo_eligible(H, W, C0, C1, Cout)) {
+    l.halo = true;
+    l.block_n = Cout;
+    rc = make_halo_map(&l.mA0, x0, B, H, W, C0);
+    if (rc != UB_OK) return rc;
+    if (C1 > 0) {
+      rc = make_halo_map(&l.mA1, x1, B, H, W, C1);
+      if (rc != UB_OK) return rc;
+    } else {
+      l.mA1 = l.mA0;
+    }
+    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
+    if (rc != UB_OK) return rc;
+    return make_box_map(&l.mOut, y, B, H, W, Cout, 8, 4);
+  }
+  if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
+  rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
+  if (rc != UB_OK) return rc;
+  if (C1 > 0) {
+    rc = make_act_map(&l.mA1, x1, B, H, W, C1, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+  } else {
+    l.mA1 = l.mA0;
+  }
+  rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
+  if (rc != UB_OK) return rc;
+  return make_umma_store_maps(l, y, pool, B);
+}
+
+// Launch a layer prepared by conv_layer_setup (maps were built for batch capacity Bc).
+int conv_layer_launch(const Layer& l, int batch, int Bc, const float* bias, void* y, void* pool, cudaStream_t st) {
+  if (l.halo) {
+    ub::HaloArgs ha = halo_args(l, batch, bias, y, pool);
+    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, st);
+  }
+  ub::ConvArgs a = conv_args(l, batch, Bc, bias, y, pool);
+  const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
+  return launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
+}
+
 int grid_for(size_t work_items, int threads) {
   size_t g = (work_items + threads - 1) / threads;
   const size_t cap = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * 16;
@@ -893,50 +958,9 @@ int unet_b200_conv3x3(const void* x0, int C0, const void* x1, int C1, const void
   int rc = device_check();
   if (rc != UB_OK) return rc;
   Layer l;
-  memset(&l, 0, sizeof(l));
-  l.kind = L_CONV;
-  l.H = H;
-  l.W = W;
-  l.C0 = C0;
-  l.C1 = C1;
-  l.Cout = Cout;
-  l.relu = relu;
-  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
-  l.block_n = pick_block_n(Cout);
-  if (halo_eligible(H, W, C0, C1, Cout)) {
-    l.halo = true;
-    l.block_n = Cout;
-    rc = make_halo_map(&l.mA0, x0, B, H, W, C0);
-    if (rc != UB_OK) return rc;
-    if (C1 > 0) {
-      rc = make_halo_map(&l.mA1, x1, B, H, W, C1);
-      if (rc != UB_OK) return rc;
-    } else {
-      l.mA1 = l.mA0;
-    }
-    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
-    if (rc != UB_OK) return rc;
-    rc = make_box_map(&l.mOut, y, B, H, W, Cout, 8, 4);
-    if (rc != UB_OK) return rc;
-    ub::HaloArgs ha = halo_args(l, B, bias, y, pool);
-    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, static_cast<cudaStream_t>(stream));
-  }
-  if (pool != nullptr && (l.TW < 2 || l.TH < 2)) return fail(UB_ERR_ARG, "tile %dx%d cannot fuse the pool", l.TW, l.TH);
-  rc = make_act_map(&l.mA0, x0, B, H, W, C0, l.TW, l.TH, l.TB);
+  rc = conv_layer_setup(l, L_CONV, x0, C0, x1, C1, wp, y, pool, B, H, W, Cout, relu, true);
   if (rc != UB_OK) return rc;
-  if (C1 > 0) {
-    rc = make_act_map(&l.mA1, x1, B, H, W, C1, l.TW, l.TH, l.TB);
-    if (rc != UB_OK) return rc;
-  } else {
-    l.mA1 = l.mA0;
-  }
-  rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
-  if (rc != UB_OK) return rc;
-  rc = make_umma_store_maps(l, y, pool, B);
-  if (rc != UB_OK) return rc;
-  ub::ConvArgs a = conv_args(l, B, B, bias, y, pool);
-  const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
-  return launch_conv(l.block_n, ma, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
+  return conv_layer_launch(l, B, B, bias, y, pool, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias, int B, int H, int W, int f, void* y,
@@ -946,26 +970,9 @@ int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias
   int rc = device_check();
   if (rc != UB_OK) return rc;
   Layer l;
-  memset(&l, 0, sizeof(l));
-  l.kind = L_CONVT;
-  l.H = H;
-  l.W = W;
-  l.C0 = Cin;
-  l.C1 = 0;
-  l.Cout = f;
-  l.relu = 0;
-  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
-  l.block_n = pick_block_n(4 * f);
-  rc = make_act_map(&l.mA0, x, B, H, W, Cin, l.TW, l.TH, l.TB);
+  rc = conv_layer_setup(l, L_CONVT, x, Cin, nullptr, 0, wp, y, nullptr, B, H, W, f, 0, false);
   if (rc != UB_OK) return rc;
-  l.mA1 = l.mA0;
-  rc = make_w_map(&l.mW, wp, 4 * f, Cin, l.block_n);
-  if (rc != UB_OK) return rc;
-  rc = make_umma_store_maps(l, y, nullptr, B);
-  if (rc != UB_OK) return rc;
-  ub::ConvArgs a = conv_args(l, B, B, bias, y, nullptr);
-  const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
-  return launch_conv(l.block_n, ma, l.mW, l.mO, a, static_cast<cudaStream_t>(stream));
+  return conv_layer_launch(l, B, B, bias, y, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
@@ -1051,3 +1058,5 @@ int unet_b200_maxpool2x2(const void* x, int B, int H, int W, int C, void* y, voi
 }
 
 }  // extern "C"
+
+#include "train_capi.cuh"

@@ -1,0 +1,951 @@
+// Training step of the U-Net on B200 (included at the end of capi.cu; uses its file-local helpers).
+//
+// Reference: README.md:2060-2084 train_one_epoch (model.train(): BatchNorm uses batch statistics, README.md:2062),
+// README.md:1855-1893 BCEDiceLoss, README.md:2173-2174 AdamW. The trainer owns a fixed-batch workspace that keeps
+// every layer's raw conv output y, its post-BN/ReLU activation a and one gradient buffer per activation.
+//
+// forward :  for each 3x3 conv   y = conv(x) [tcgen05 implicit GEMM, same kernels as inference, no bias]
+//                                 batch stats of y -> scale/shift (+ running stats) -> a = relu(y*scale+shift) (+ 2x2 pool)
+//            ConvT / concat / head as in inference (concat never materialised)
+// backward:  head -> for each conv in reverse: BN+ReLU backward (two passes, in place) -> wgrad (MN-major tcgen05 GEMM,
+//            fp32 atomics straight into the PyTorch-layout gradient) -> dgrad (the forward conv kernel on rotated weights);
+//            ConvT backward = 4-source 1-tap GEMM over the quad views; max-pool backward merged with the skip gradient.
+// Parameters and gradients are flat fp32 arrays in model.parameters() order (README.md:1427-1447 registration order).
+#pragma once
+#include "train_kernels.cuh"
+#include "wgrad_umma.cuh"
+#include "stem_wgrad_umma.cuh"
+
+namespace {
+
+struct TConv {
+  int H, W, C0, C1, Cout;
+  bool stem, pooled;
+  uint8_t *x0, *x1;   // inputs (bf16 NHWC); stem: the trainer's copy of the network input (NHWC4)
+  uint8_t *y, *a, *p; // raw conv output, relu(bn(y)), maxpool(a) (or null)
+  uint8_t *g;         // gradient w.r.t. a, then (in place) w.r.t. y
+  uint8_t *dx;        // dgrad target [B,H,W,C0+C1] (null: stem)
+  uint8_t *wp, *wd;   // packed forward / dgrad weights (bf16)
+  long long w_off, gamma_off, beta_off;
+  double *sum, *sumsq;
+  float *s1, *s2, *mean, *invstd, *scale, *shift;
+  Layer fwd, dg;
+  CUtensorMap wX0, wX1, wD;
+  ub::WgradArgs wa;
+  int w_bn, w_grid;
+};
+
+struct TConvT {
+  int H, W, Cin, f;   // input grid
+  uint8_t *x, *y;     // input activation [B,H,W,Cin]; output up [B,2H,2W,f]
+  uint8_t *dup;       // gradient w.r.t. up: channels [f,2f) of the concat gradient (pixel pitch 2f elements)
+  uint8_t *dx;        // gradient w.r.t. x (= g of the producing conv)
+  uint8_t *wp, *wd;
+  long long w_off, b_off;
+  Layer fwd, dg;
+  CUtensorMap dgA[4];
+  CUtensorMap wX, wDq[4];
+  ub::WgradArgs wa;
+  int w_bn, w_grid;
+};
+
+}  // namespace
+
+struct unet_b200_trainer {
+  int B, H, W, in_ch, levels;
+  int feat[UB_MAX_LEVELS];
+  std::vector<TConv> convs;    // plan order: enc0.0, enc0.3, ..., bott.0, bott.3, dec0.0, dec0.3, ...
+  std::vector<TConvT> ups;     // decoder order (deepest first)
+  std::vector<int> fwd_order;  // >= 0: conv index; < 0: -(up index) - 1
+  long long n_params;
+  std::vector<long long> tensor_off;  // parameters() order, one entry per tensor (+ total at the end)
+  long long head_w_off, head_b_off;
+  size_t ws_bytes;
+  uint8_t* ws;
+  uint8_t* acc;       // accumulator region zeroed every step
+  size_t acc_bytes;
+  float* zero_bias;
+  uint8_t* x_in;      // copy of the network input (NHWC4 bf16)
+  bool fwd_done;
+};
+
+namespace {
+
+struct Bump {
+  uintptr_t base;
+  size_t off;
+  uint8_t* take(size_t bytes) {
+    uint8_t* p = reinterpret_cast<uint8_t*>(base + off);
+    off += align_up(bytes, 1024);
+    return p;
+  }
+};
+
+bool pow2_times_64(int c) { return c >= 64 && c <= 2048 && (c & (c - 1)) == 0; }
+
+// One pass over the network assigning workspace addresses (base == 0: size computation only).
+void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
+  Bump bp{base, 0};
+  const size_t B = t->B;
+  t->zero_bias = reinterpret_cast<float*>(bp.take(4096 * 4));
+  t->x_in = bp.take(B * t->H * t->W * 8);
+  // accumulators (zeroed per step): per conv sum, sumsq (double) + s1, s2 (float)
+  t->acc = reinterpret_cast<uint8_t*>(base + bp.off);
+  for (TConv& c : t->convs) {
+    c.sum = reinterpret_cast<double*>(bp.take((size_t)c.Cout * 8));
+    c.sumsq = reinterpret_cast<double*>(bp.take((size_t)c.Cout * 8));
+    c.s1 = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+    c.s2 = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+  }
+  t->acc_bytes = base + bp.off - reinterpret_cast<uintptr_t>(t->acc);
+  for (TConv& c : t->convs) {
+    c.mean = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+    c.invstd = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+    c.scale = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+    c.shift = reinterpret_cast<float*>(bp.take((size_t)c.Cout * 4));
+    const size_t cin = c.C0 + c.C1;
+    c.wp = bp.take(c.stem ? (size_t)(c.Cout == 64 ? 64 * 64 * 2 : 36 * c.Cout * 4) : (size_t)c.Cout * 9 * cin * 2);
+    c.wd = c.stem ? nullptr : bp.take((size_t)c.Cout * 9 * cin * 2);
+    const size_t act = B * c.H * c.W * c.Cout * 2;
+    c.y = bp.take(act);
+    c.a = bp.take(act);
+    c.g = bp.take(act);
+    c.p = c.pooled ? bp.take(act / 4) : nullptr;
+  }
+  for (TConvT& u : t->ups) {
+    u.wp = bp.take((size_t)4 * u.f * u.Cin * 2);
+    u.wd = bp.take((size_t)4 * u.f * u.Cin * 2);
+    u.y = bp.take(B * 4 * u.H * u.W * u.f * 2);
+  }
+  // wiring
+  const int L = t->levels;
+  uint8_t* cur = t->x_in;
+  for (int i = 0; i < L; ++i) {
+    TConv& c0 = t->convs[2 * i];
+    TConv& c1 = t->convs[2 * i + 1];
+    c0.x0 = cur;
+    c0.x1 = nullptr;
+    c1.x0 = c0.a;
+    c1.x1 = nullptr;
+    c1.dx = c0.g;
+    c0.dx = (i > 0) ? bp.take(B * c0.H * c0.W * c0.C0 * 2) : nullptr;  // gradient w.r.t. the pooled input
+    cur = c1.p;
+  }
+  {
+    TConv& b0 = t->convs[2 * L];
+    TConv& b1 = t->convs[2 * L + 1];
+    b0.x0 = cur;
+    b0.x1 = nullptr;
+    b0.dx = bp.take(B * b0.H * b0.W * b0.C0 * 2);
+    b1.x0 = b0.a;
+    b1.x1 = nullptr;
+    b1.dx = b0.g;
+  }
+  TConv* prev = &t->convs[2 * L + 1];
+  for (int j = 0; j < L; ++j) {
+    const int i = L - 1 - j;
+    TConvT& u = t->ups[j];
+    TConv& d0 = t->convs[2 * L + 2 + 2 * j];
+    TConv& d1 = t->convs[2 * L + 3 + 2 * j];
+    TConv& skip = t->convs[2 * i + 1];
+    uint8_t* dcat = bp.take(B * d0.H * d0.W * 2 * u.f * 2);
+    u.x = prev->a;
+    u.dx = prev->g;
+    u.dup = dcat + (size_t)u.f * 2;
+    d0.x0 = skip.a;
+    d0.x1 = u.y;
+    d0.dx = dcat;
+    d1.x0 = d0.a;
+    d1.x1 = nullptr;
+    d1.dx = d0.g;
+    prev = &d1;
+  }
+  t->ws_bytes = bp.off;
+}
+
+template <int BN>
+int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
+                   int slot, cudaStream_t st) {
+  static int attr_done[3] = {0, 0, 0};
+  using Cfg = ub::WgradCfg<BN>;
+  if (!attr_done[slot]) {
+    UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done[slot] = 1;
+  }
+  ub::wgrad_umma_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(x0, x1, d[0], d[1], d[2], d[3], a);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int launch_wgrad(int bn, const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
+                 cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_wgrad_t<64>(x0, x1, d, a, grid, 0, st);
+    case 128: return launch_wgrad_t<128>(x0, x1, d, a, grid, 1, st);
+    case 256: return launch_wgrad_t<256>(x0, x1, d, a, grid, 2, st);
+  }
+  return fail(UB_ERR_ARG, "unsupported wgrad BLOCK_N %d", bn);
+}
+
+// Common part of the weight-gradient launch geometry: pixel tiles, split-K, grid.
+int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int taps, int* bn, int* grid) {
+  memset(&a, 0, sizeof(a));
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  pick_tile(H, W, &a.TW, &a.TH, &a.TB);
+  const int tb_eff = a.TB < B ? a.TB : B;
+  const int rows = a.TW * a.TH * tb_eff;
+  if (rows % 16 != 0) {
+    return fail(UB_ERR_ARG, "wgrad: batch %d too small for the %dx%d level (pixel box of %d rows; need a multiple of 16)", B, H,
+                W, rows);
+  }
+  a.k_mmas = rows / 16;
+  a.a_bytes = rows * 128;
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  a.tiles_b = (B + a.TB - 1) / a.TB;
+  a.taps = taps;
+  a.Cin = Cin;
+  a.Cout = Cout;
+  *bn = pick_block_n(Cout);
+  a.n_tiles = Cout / *bn;
+  if (taps == 9 && Cin == 64) {
+    a.pair_taps = 1;
+    a.m_tiles = 5;
+  } else {
+    if (Cin % 128 != 0) return fail(UB_ERR_ARG, "wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
+    a.pair_taps = 0;
+    a.m_tiles = Cin / 128;
+  }
+  const int tiles = (a.pair_taps ? 1 : taps) * a.m_tiles * a.n_tiles;
+  const int ptiles = a.tiles_w * a.tiles_h * a.tiles_b;
+  int ks = g_num_sms / tiles;
+  if (ks < 1) ks = 1;
+  if (ks > ptiles) ks = ptiles;
+  a.ksplit = ks;
+  *grid = tiles * ks;
+  return UB_OK;
+}
+
+// weight gradient of a 3x3 conv: dW[co][ci][tap] += sum_p dY[p][co] * x[p + shift(tap)][ci]   (x = cat(x0, x1), dY = c.g)
+int setup_conv_wgrad(TConv& c, int B) {
+  const int cin = c.C0 + c.C1;
+  int rc = wgrad_geometry(c.wa, B, c.H, c.W, cin, c.Cout, 9, &c.w_bn, &c.w_grid);
+  if (rc != UB_OK) return rc;
+  c.wa.shift = 1;
+  c.wa.c_split = c.C0;
+  c.wa.s_co = (long long)cin * 9;
+  c.wa.s_ci = 9;
+  c.wa.s_tap = 1;
+  rc = make_act_map(&c.wX0, c.x0, B, c.H, c.W, c.C0, c.wa.TW, c.wa.TH, c.wa.TB);
+  if (rc != UB_OK) return rc;
+  if (c.C1 > 0) {
+    rc = make_act_map(&c.wX1, c.x1, B, c.H, c.W, c.C1, c.wa.TW, c.wa.TH, c.wa.TB);
+    if (rc != UB_OK) return rc;
+  } else {
+    c.wX1 = c.wX0;
+  }
+  return make_act_map(&c.wD, c.g, B, c.H, c.W, c.Cout, c.wa.TW, c.wa.TH, c.wa.TB);
+}
+
+// Backward of ConvTranspose2d(2x2, stride 2): maps for the 4-source dgrad GEMM and the 4-quad weight gradient.
+// u.dup points at the gradient w.r.t. the upsampled tensor, whose pixel pitch is `pitch` elements (2f when it is the
+// upper half of the concat gradient, f when it stands alone).
+int setup_up_backward(TConvT& u, int B, size_t pitch = 0) {
+  if (pitch == 0) pitch = 2 * (size_t)u.f;
+  const size_t W2 = 2 * (size_t)u.W, H2 = 2 * (size_t)u.H;
+  int rc;
+  Layer& l = u.dg;
+  memset(&l, 0, sizeof(l));
+  l.kind = L_CONV;
+  l.H = u.H;
+  l.W = u.W;
+  l.C0 = u.f;
+  l.Cout = u.Cin;
+  l.relu = 0;
+  l.set = true;
+  pick_tile(u.H, u.W, &l.TW, &l.TH, &l.TB);
+  l.block_n = pick_block_n(u.Cin);
+  for (int q = 0; q < 4; ++q) {
+    const int dy = q >> 1, dx = q & 1;
+    uint8_t* base = u.dup + ((size_t)dy * W2 + dx) * pitch * 2;
+    rc = make_tile_store_map(&u.dgA[q], base, B, u.H, u.W, u.f, 2 * pitch, 2 * W2 * pitch, H2 * W2 * pitch, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+  }
+  if (u.wd != nullptr && u.dx != nullptr) {
+    rc = make_w_map(&l.mW, u.wd, u.Cin, 4 * u.f, l.block_n);
+    if (rc != UB_OK) return rc;
+    rc = make_umma_store_maps(l, u.dx, nullptr, B);
+    if (rc != UB_OK) return rc;
+  }
+  // weight gradient: dW[ci][co][quad] += sum_p x[p][ci] * dUp_quad[p][co]
+  if (u.x != nullptr) {
+    rc = wgrad_geometry(u.wa, B, u.H, u.W, u.Cin, u.f, 4, &u.w_bn, &u.w_grid);
+    if (rc != UB_OK) return rc;
+    u.wa.shift = 0;
+    u.wa.c_split = u.Cin;
+    u.wa.s_ci = 4 * (long long)u.f;
+    u.wa.s_co = 4;
+    u.wa.s_tap = 1;
+    rc = make_act_map(&u.wX, u.x, B, u.H, u.W, u.Cin, u.wa.TW, u.wa.TH, u.wa.TB);
+    if (rc != UB_OK) return rc;
+    for (int q = 0; q < 4; ++q) {
+      const int dy = q >> 1, dx = q & 1;
+      uint8_t* base = u.dup + ((size_t)dy * W2 + dx) * pitch * 2;
+      rc = make_tile_store_map(&u.wDq[q], base, B, u.H, u.W, u.f, 2 * pitch, 2 * W2 * pitch, H2 * W2 * pitch, u.wa.TW, u.wa.TH,
+                               u.wa.TB);
+      if (rc != UB_OK) return rc;
+    }
+  }
+  return UB_OK;
+}
+
+int trainer_build_maps(unet_b200_trainer* t) {
+  const int B = t->B;
+  int rc;
+  for (TConv& c : t->convs) {
+    const int cin = c.C0 + c.C1;
+    if (c.stem) {
+      memset(&c.fwd, 0, sizeof(c.fwd));
+      if (c.Cout == 64) {
+        rc = make_w_map(&c.fwd.mW, c.wp, 64, 64, 64);
+        if (rc != UB_OK) return rc;
+        rc = make_box_map(&c.fwd.mOut, c.y, B, c.H, c.W, 64, 8, 4);
+        if (rc != UB_OK) return rc;
+        rc = make_box_map(&c.wD, c.g, B, c.H, c.W, 64, 8, 16);  // dY tiles of the tensor-core stem weight gradient
+        if (rc != UB_OK) return rc;
+      }
+      continue;
+    }
+    rc = conv_layer_setup(c.fwd, L_CONV, c.x0, c.C0, c.x1, c.C1, c.wp, c.y, nullptr, B, c.H, c.W, c.Cout, 0, true);
+    if (rc != UB_OK) return rc;
+    rc = conv_layer_setup(c.dg, L_CONV, c.g, c.Cout, nullptr, 0, c.wd, c.dx, nullptr, B, c.H, c.W, cin, 0, true);
+    if (rc != UB_OK) return rc;
+    rc = setup_conv_wgrad(c, B);
+    if (rc != UB_OK) return rc;
+  }
+  for (TConvT& u : t->ups) {
+    rc = conv_layer_setup(u.fwd, L_CONVT, u.x, u.Cin, nullptr, 0, u.wp, u.y, nullptr, B, u.H, u.W, u.f, 0, false);
+    if (rc != UB_OK) return rc;
+    rc = setup_up_backward(u, B);
+    if (rc != UB_OK) return rc;
+  }
+  return UB_OK;
+}
+
+int chan_grid(size_t npix, int C8) {
+  const int ppb = 256 / C8;
+  size_t g = (npix + ppb - 1) / ppb;
+  const size_t cap = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float* params, float* const* running_mean,
+                         float* const* running_var, float momentum, float eps, cudaStream_t st) {
+  const int B = t->B;
+  int rc;
+  if (c.stem) {
+    if (c.Cout == 64) {
+      rc = launch_stem_umma(c.fwd.mW, c.fwd.mOut, c.x0, t->zero_bias, B, c.H, c.W, 0, st);
+      if (rc != UB_OK) return rc;
+    } else {
+      const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
+      const size_t smem = (size_t)(36 * c.Cout + c.Cout) * 4 + 18 * 18 * 16;
+      ub::stem_conv_kernel<<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0), reinterpret_cast<const float*>(c.wp),
+                                                      t->zero_bias, B, c.H, c.W, c.C0, c.Cout, 0,
+                                                      reinterpret_cast<__nv_bfloat16*>(c.y));
+      UB_CUDA(cudaGetLastError());
+    }
+  } else {
+    rc = conv_layer_launch(c.fwd, B, B, t->zero_bias, c.y, nullptr, st);
+    if (rc != UB_OK) return rc;
+  }
+  const size_t npix = (size_t)B * c.H * c.W;
+  const int C8 = c.Cout / 8;
+  ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(c.y), npix, C8, c.sum,
+                                                                         c.sumsq);
+  UB_CUDA(cudaGetLastError());
+  ub::bn_finalize_kernel<<<(c.Cout + 127) / 128, 128, 0, st>>>(
+      c.sum, c.sumsq, (float)npix, eps, momentum, params + c.gamma_off, params + c.beta_off, c.mean, c.invstd, c.scale, c.shift,
+      running_mean ? running_mean[bn_idx] : nullptr, running_var ? running_var[bn_idx] : nullptr, c.Cout);
+  UB_CUDA(cudaGetLastError());
+  if (c.pooled) {
+    const size_t n = npix / 4 * C8;
+    ub::bn_relu_apply_pool_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, B, c.H,
+                                                                    c.W, C8, reinterpret_cast<uint4*>(c.a),
+                                                                    reinterpret_cast<uint4*>(c.p));
+  } else {
+    const size_t n8 = npix * C8;
+    ub::bn_relu_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, n8, C8,
+                                                                reinterpret_cast<uint4*>(c.a));
+  }
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+// BatchNorm(train)+ReLU backward on c.g in place (dA -> dY); d gamma / d beta are written when the pointers are given.
+int conv_bn_backward(const TConv& c, int B, float* dgamma, float* dbeta, cudaStream_t st) {
+  const size_t npix = (size_t)B * c.H * c.W;
+  const int C8 = c.Cout / 8;
+  const uint4* g4 = reinterpret_cast<const uint4*>(c.g);
+  const uint4* y4 = reinterpret_cast<const uint4*>(c.y);
+  ub::bn_relu_bwd_reduce_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
+                                                                                 C8, c.s1, c.s2);
+  UB_CUDA(cudaGetLastError());
+  const size_t n8 = npix * C8;
+  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, c.s1, c.s2,
+                                                                  1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g));
+  UB_CUDA(cudaGetLastError());
+  // d gamma = sum g * xhat, d beta = sum g
+  if (dgamma) UB_CUDA(cudaMemcpyAsync(dgamma, c.s2, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, st));
+  if (dbeta) UB_CUDA(cudaMemcpyAsync(dbeta, c.s1, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, st));
+  return UB_OK;
+}
+
+// Weight gradient of one conv (3x3 on tensor cores, stem on tensor cores for Cout == 64), accumulated into dw (PyTorch layout).
+int conv_wgrad_launch(const TConv& c, int B, float* dw, cudaStream_t st) {
+  if (c.stem && c.Cout == 64) {
+    static int attr_done_tc = 0;
+    if (!attr_done_tc) {
+      UB_CUDA(cudaFuncSetAttribute(ub::stem_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   ub::StemWgradCfg::SMEM_BYTES));
+      attr_done_tc = 1;
+    }
+    ub::StemWgradArgs sa;
+    sa.B = B;
+    sa.H = c.H;
+    sa.W = c.W;
+    sa.Cin = c.C0;
+    sa.tiles_w = (c.W + 7) / 8;
+    sa.tiles_h = (c.H + 15) / 16;
+    sa.x = reinterpret_cast<const uint2*>(c.x0);
+    sa.dw = dw;
+    const int pairs = (sa.tiles_w * sa.tiles_h * B + 1) / 2;
+    const int grid = pairs < g_num_sms ? pairs : g_num_sms;
+    ub::stem_wgrad_umma_kernel<<<grid, ub::StemWgradCfg::THREADS, ub::StemWgradCfg::SMEM_BYTES, st>>>(c.wD, sa);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
+  if (c.stem) {
+    if (c.Cout > 128) return fail(UB_ERR_ARG, "stem weight gradient supports Cout <= 128");
+    const size_t smem = (size_t)(18 * 18 * 4 + 256 * c.Cout) * 4;
+    static int attr_done = 0;
+    if (!attr_done) {
+      UB_CUDA(cudaFuncSetAttribute(ub::stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (18 * 18 * 4 + 256 * 128) * 4));
+      attr_done = 1;
+    }
+    const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
+    const int grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
+    ub::stem_wgrad_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0),
+                                                    reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, dw);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
+  ub::WgradArgs wa = c.wa;
+  wa.dw = dw;
+  const CUtensorMap d[4] = {c.wD, c.wD, c.wD, c.wD};
+  return launch_wgrad(c.w_bn, c.wX0, c.wX1, d, wa, c.w_grid, st);
+}
+
+int trainer_conv_backward(unet_b200_trainer* t, TConv& c, float* grads, cudaStream_t st) {
+  const int B = t->B;
+  int rc = conv_bn_backward(c, B, grads + c.gamma_off, grads + c.beta_off, st);
+  if (rc != UB_OK) return rc;
+  rc = conv_wgrad_launch(c, B, grads + c.w_off, st);
+  if (rc != UB_OK) return rc;
+  if (c.dx != nullptr) {
+    rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st);
+    if (rc != UB_OK) return rc;
+  }
+  return UB_OK;
+}
+
+// ConvT backward pieces on prepared maps: bias gradient + weight gradient, and the input gradient.
+int up_wgrad_launch(const TConvT& u, int B, int pitch8, float* dw, float* dbias, cudaStream_t st) {
+  const size_t npix_up = (size_t)B * 4 * u.H * u.W;
+  const int C8 = u.f / 8;
+  if (dbias != nullptr) {
+    ub::chan_sum_kernel<<<chan_grid(npix_up, C8), 256, 2048 * 4, st>>>(reinterpret_cast<const uint4*>(u.dup), pitch8, npix_up, C8,
+                                                                       dbias);
+    UB_CUDA(cudaGetLastError());
+  }
+  ub::WgradArgs wa = u.wa;
+  wa.dw = dw;
+  return launch_wgrad(u.w_bn, u.wX, u.wX, u.wDq, wa, u.w_grid, st);
+}
+
+// dX[b,h,w,ci] = sum_quad sum_co dUp[b,2h+dy,2w+dx,co] * w[ci][co][quad]: 1-tap GEMM, K walks the four quad views
+int up_dgrad_launch(const TConvT& u, int B, const float* zero_bias, cudaStream_t st) {
+  ub::ConvArgs a = conv_args(u.dg, B, B, zero_bias, u.dx, nullptr);
+  a.taps = 1;
+  a.kc0 = a.kc1 = a.kc2 = a.kc3 = u.f / 64;
+  return launch_conv(u.dg.block_n, u.dgA, u.dg.mW, u.dg.mO, a, st);
+}
+
+int trainer_up_backward(unet_b200_trainer* t, TConvT& u, float* grads, cudaStream_t st) {
+  int rc = up_wgrad_launch(u, t->B, 2 * (u.f / 8), grads + u.w_off, grads + u.b_off, st);
+  if (rc != UB_OK) return rc;
+  return up_dgrad_launch(u, t->B, t->zero_bias, st);
+}
+
+float* g_zero_bias = nullptr;  // 4096 zero floats for the single-op entry points (allocated once per process)
+int get_zero_bias(float** out) {
+  if (g_zero_bias == nullptr) {
+    UB_CUDA(cudaMalloc(&g_zero_bias, 4096 * 4));
+    UB_CUDA(cudaMemset(g_zero_bias, 0, 4096 * 4));
+  }
+  *out = g_zero_bias;
+  return UB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, int in_channels, int out_channels,
+                             const int* features, int levels) {
+  if (out == nullptr || features == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (levels < 1 || levels > UB_MAX_LEVELS) return fail(UB_ERR_ARG, "levels must be in [1,%d]", UB_MAX_LEVELS);
+  if (batch < 1) return fail(UB_ERR_ARG, "batch must be >= 1");
+  if (in_channels < 1 || in_channels > 4) return fail(UB_ERR_ARG, "in_channels must be in [1,4] (got %d)", in_channels);
+  if (out_channels != 1) return fail(UB_ERR_ARG, "out_channels must be 1 (got %d)", out_channels);
+  if (H % (1 << levels) != 0 || W % (1 << levels) != 0) {
+    return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
+  }
+  for (int i = 0; i < levels; ++i) {
+    if (!pow2_times_64(features[i]) || features[i] > 1024) {
+      return fail(UB_ERR_ARG, "training needs features[%d]=%d in {64,128,256,512,1024}", i, features[i]);
+    }
+  }
+  if (features[0] > 128) return fail(UB_ERR_ARG, "training needs features[0] <= 128 (stem weight gradient)");
+  unet_b200_trainer* t = new (std::nothrow) unet_b200_trainer();
+  if (t == nullptr) return fail(UB_ERR_ARG, "out of host memory");
+  t->B = batch;
+  t->H = H;
+  t->W = W;
+  t->in_ch = in_channels;
+  t->levels = levels;
+  t->ws = nullptr;
+  t->fwd_done = false;
+  for (int i = 0; i < levels; ++i) t->feat[i] = features[i];
+
+  auto mk = [&](int h, int w, int c0, int c1, int cout, bool stem, bool pooled) {
+    TConv c;
+    memset(&c, 0, sizeof(c));
+    c.H = h;
+    c.W = w;
+    c.C0 = c0;
+    c.C1 = c1;
+    c.Cout = cout;
+    c.stem = stem;
+    c.pooled = pooled;
+    t->convs.push_back(c);
+  };
+  int cin = in_channels;
+  for (int i = 0; i < levels; ++i) {
+    const int h = H >> i, w = W >> i, f = features[i];
+    mk(h, w, cin, 0, f, i == 0, false);
+    mk(h, w, f, 0, f, false, true);
+    cin = f;
+  }
+  {
+    const int h = H >> levels, w = W >> levels, f = 2 * features[levels - 1];
+    mk(h, w, cin, 0, f, false, false);
+    mk(h, w, f, 0, f, false, false);
+    cin = f;
+  }
+  for (int j = 0; j < levels; ++j) {
+    const int i = levels - 1 - j;
+    const int h = H >> i, w = W >> i, f = features[i];
+    TConvT u;
+    memset(&u, 0, sizeof(u));
+    u.H = h / 2;
+    u.W = w / 2;
+    u.Cin = cin;
+    u.f = f;
+    if (cin != 2 * f) {
+      delete t;
+      return fail(UB_ERR_ARG, "decoder level %d: ConvT input channels %d != 2*%d", j, cin, f);
+    }
+    t->ups.push_back(u);
+    mk(h, w, f, f, f, false, false);
+    mk(h, w, f, 0, f, false, false);
+    cin = f;
+  }
+  // forward order and parameters() order (encoder, decoder, bottleneck, output: README.md:1427-1447)
+  for (int i = 0; i < 2 * levels + 2; ++i) t->fwd_order.push_back(i);
+  for (int j = 0; j < levels; ++j) {
+    t->fwd_order.push_back(-(j + 1));
+    t->fwd_order.push_back(2 * levels + 2 + 2 * j);
+    t->fwd_order.push_back(2 * levels + 3 + 2 * j);
+  }
+  long long off = 0;
+  auto conv_params = [&](TConv& c) {
+    const long long cn = c.C0 + c.C1;
+    c.w_off = off;
+    t->tensor_off.push_back(off);
+    off += (long long)c.Cout * cn * 9;
+    c.gamma_off = off;
+    t->tensor_off.push_back(off);
+    off += c.Cout;
+    c.beta_off = off;
+    t->tensor_off.push_back(off);
+    off += c.Cout;
+  };
+  for (int i = 0; i < 2 * levels; ++i) conv_params(t->convs[i]);
+  for (int j = 0; j < levels; ++j) {
+    TConvT& u = t->ups[j];
+    u.w_off = off;
+    t->tensor_off.push_back(off);
+    off += (long long)u.Cin * u.f * 4;
+    u.b_off = off;
+    t->tensor_off.push_back(off);
+    off += u.f;
+    conv_params(t->convs[2 * levels + 2 + 2 * j]);
+    conv_params(t->convs[2 * levels + 3 + 2 * j]);
+  }
+  conv_params(t->convs[2 * levels]);
+  conv_params(t->convs[2 * levels + 1]);
+  t->head_w_off = off;
+  t->tensor_off.push_back(off);
+  off += features[0];
+  t->head_b_off = off;
+  t->tensor_off.push_back(off);
+  off += 1;
+  t->tensor_off.push_back(off);
+  t->n_params = off;
+  trainer_layout(t, 0);
+  *out = t;
+  return UB_OK;
+}
+
+void unet_b200_trainer_destroy(unet_b200_trainer* t) { delete t; }
+size_t unet_b200_trainer_workspace_bytes(const unet_b200_trainer* t) { return t ? t->ws_bytes : 0; }
+long long unet_b200_trainer_num_params(const unet_b200_trainer* t) { return t ? t->n_params : 0; }
+int unet_b200_trainer_num_tensors(const unet_b200_trainer* t) { return t ? (int)t->tensor_off.size() - 1 : 0; }
+long long unet_b200_trainer_tensor_offset(const unet_b200_trainer* t, int idx) {
+  if (t == nullptr || idx < 0 || idx >= (int)t->tensor_off.size()) return -1;
+  return t->tensor_off[idx];
+}
+
+int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
+  if (t == nullptr || workspace_dev == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(UB_ERR_ARG, "workspace must be 1024-byte aligned");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  t->ws = static_cast<uint8_t*>(workspace_dev);
+  trainer_layout(t, reinterpret_cast<uintptr_t>(workspace_dev));
+  UB_CUDA(cudaMemset(t->zero_bias, 0, 4096 * 4));
+  t->fwd_done = false;
+  return trainer_build_maps(t);
+}
+
+int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const float* params, float* const* running_mean,
+                            float* const* running_var, float momentum, float eps, float* logits, void* stream) {
+  if (t == nullptr || x_nhwc4 == nullptr || params == nullptr || logits == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (t->ws == nullptr) return fail(UB_ERR_STATE, "trainer is not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = t->B;
+  UB_CUDA(cudaMemcpyAsync(t->x_in, x_nhwc4, (size_t)B * t->H * t->W * 8, cudaMemcpyDeviceToDevice, st));
+  UB_CUDA(cudaMemsetAsync(t->acc, 0, t->acc_bytes, st));
+  // bf16 operand copies of the current fp32 parameters: forward layout and the rotated/transposed dgrad layout
+  for (TConv& c : t->convs) {
+    const int cin = c.C0 + c.C1;
+    const float* w = params + c.w_off;
+    if (c.stem && c.Cout == 64) {
+      ub::pack_stem_umma_kernel<<<grid_for(64 * 64, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, c.C0,
+                                                                         reinterpret_cast<__nv_bfloat16*>(c.wp), c.s1 /*bias scratch*/);
+    } else if (c.stem) {
+      ub::pack_stem_kernel<<<grid_for(36 * c.Cout, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, c.C0,
+                                                                       reinterpret_cast<float*>(c.wp), c.s1);
+    } else {
+      const size_t n = (size_t)c.Cout * 9 * cin;
+      ub::pack_conv3x3_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, cin,
+                                                                reinterpret_cast<__nv_bfloat16*>(c.wp), c.s1);
+      ub::pack_conv3x3_dgrad_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, c.Cout, cin, reinterpret_cast<__nv_bfloat16*>(c.wd));
+    }
+    UB_CUDA(cudaGetLastError());
+  }
+  for (TConvT& u : t->ups) {
+    const size_t n = (size_t)4 * u.f * u.Cin;
+    ub::pack_convT_kernel<<<grid_for(n, 256), 256, 0, st>>>(params + u.w_off, u.Cin, u.f, reinterpret_cast<__nv_bfloat16*>(u.wp));
+    ub::pack_convT_dgrad_kernel<<<grid_for(n, 256), 256, 0, st>>>(params + u.w_off, u.Cin, u.f,
+                                                                  reinterpret_cast<__nv_bfloat16*>(u.wd));
+    UB_CUDA(cudaGetLastError());
+  }
+  // (the pack kernels' bias output is all zeros without BN; it lands in s1, which stays zero for the backward)
+  int rc;
+  for (int id : t->fwd_order) {
+    if (id >= 0) {
+      rc = trainer_conv_forward(t, t->convs[id], id, params, running_mean, running_var, momentum, eps, st);
+    } else {
+      TConvT& u = t->ups[-id - 1];
+      rc = conv_layer_launch(u.fwd, B, B, params + u.b_off, u.y, nullptr, st);
+    }
+    if (rc != UB_OK) return rc;
+  }
+  const TConv& last = t->convs.back();
+  const size_t npix = (size_t)B * last.H * last.W;
+  ub::head_fwd_train_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(last.a),
+                                                                     params + t->head_w_off, params + t->head_b_off, npix,
+                                                                     last.Cout / 8, logits);
+  UB_CUDA(cudaGetLastError());
+  t->fwd_done = true;
+  return UB_OK;
+}
+
+int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads, void* stream) {
+  if (t == nullptr || dlogits == nullptr || params == nullptr || grads == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (!t->fwd_done) return fail(UB_ERR_STATE, "train_backward needs a preceding train_forward");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = t->B, L = t->levels;
+  UB_CUDA(cudaMemsetAsync(grads, 0, (size_t)t->n_params * 4, st));
+  TConv& last = t->convs.back();
+  {
+    const size_t npix = (size_t)B * last.H * last.W;
+    const int C8 = last.Cout / 8;
+    ub::head_bwd_kernel<<<chan_grid(npix, C8), 256, (2048 + 256) * 4, st>>>(
+        reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g),
+        grads + t->head_w_off, grads + t->head_b_off);
+    UB_CUDA(cudaGetLastError());
+  }
+  int rc;
+  for (int j = L - 1; j >= 0; --j) {
+    rc = trainer_conv_backward(t, t->convs[2 * L + 3 + 2 * j], grads, st);
+    if (rc != UB_OK) return rc;
+    rc = trainer_conv_backward(t, t->convs[2 * L + 2 + 2 * j], grads, st);
+    if (rc != UB_OK) return rc;
+    rc = trainer_up_backward(t, t->ups[j], grads, st);
+    if (rc != UB_OK) return rc;
+  }
+  rc = trainer_conv_backward(t, t->convs[2 * L + 1], grads, st);
+  if (rc != UB_OK) return rc;
+  rc = trainer_conv_backward(t, t->convs[2 * L], grads, st);
+  if (rc != UB_OK) return rc;
+  for (int i = L - 1; i >= 0; --i) {
+    TConv& c1 = t->convs[2 * i + 1];
+    const TConv& next0 = t->convs[2 * i + 2];                 // consumer of the pooled tensor (next encoder level / bottleneck)
+    const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
+    const int C8 = c1.Cout / 8;
+    const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
+    ub::maxpool_bwd_add_kernel<<<grid_for(n, 256), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
+        2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
+    UB_CUDA(cudaGetLastError());
+    rc = trainer_conv_backward(t, c1, grads, st);
+    if (rc != UB_OK) return rc;
+    rc = trainer_conv_backward(t, t->convs[2 * i], grads, st);
+    if (rc != UB_OK) return rc;
+  }
+  t->fwd_done = false;
+  return UB_OK;
+}
+
+int unet_b200_bce_dice_loss(const float* logits, const float* target, size_t n, float pos_weight, float bce_weight,
+                            float dice_weight, float smooth, double* scratch4, float* losses3, float* dlogits, void* stream) {
+  if (logits == nullptr || target == nullptr || scratch4 == nullptr || losses3 == nullptr) return fail(UB_ERR_ARG, "null argument");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UB_CUDA(cudaMemsetAsync(scratch4, 0, 4 * sizeof(double), st));
+  ub::bce_dice_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, scratch4);
+  UB_CUDA(cudaGetLastError());
+  ub::bce_dice_grad_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, bce_weight, dice_weight,
+                                                             smooth, scratch4, dlogits, losses3);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (step < 1) return fail(UB_ERR_ARG, "step counts from 1");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  ub::adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                                   beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+// ---- single training ops (parity tests; the trainer above runs the same code on prebuilt maps) --------------------
+int unet_b200_pack_conv3x3_dgrad(const float* w, int Cout, int Cin, void* wd, void* stream) {
+  if (w == nullptr || wd == nullptr) return fail(UB_ERR_ARG, "null argument");
+  ub::pack_conv3x3_dgrad_kernel<<<grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wd));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_pack_convT2x2_dgrad(const float* w, int Cin, int f, void* wd, void* stream) {
+  if (w == nullptr || wd == nullptr) return fail(UB_ERR_ARG, "null argument");
+  ub::pack_convT_dgrad_kernel<<<grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wd));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dy, int B, int H, int W, int Cout,
+                            float* dw, void* stream) {
+  if (x0 == nullptr || dy == nullptr || dw == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0 || C0 <= 0 || C1 < 0) return fail(UB_ERR_ARG, "channels must be multiples of 64");
+  if (C1 > 0 && x1 == nullptr) return fail(UB_ERR_ARG, "x1 is null but C1 > 0");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  TConv c;
+  memset(&c, 0, sizeof(c));
+  c.H = H;
+  c.W = W;
+  c.C0 = C0;
+  c.C1 = C1;
+  c.Cout = Cout;
+  c.x0 = static_cast<uint8_t*>(const_cast<void*>(x0));
+  c.x1 = static_cast<uint8_t*>(const_cast<void*>(x1));
+  c.g = static_cast<uint8_t*>(const_cast<void*>(dy));
+  rc = setup_conv_wgrad(c, B);
+  if (rc != UB_OK) return rc;
+  return conv_wgrad_launch(c, B, dw, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_stem_wgrad(const void* x4, const void* dy, int B, int H, int W, int Cin, int Cout, float* dw, void* stream) {
+  if (x4 == nullptr || dy == nullptr || dw == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  TConv c;
+  memset(&c, 0, sizeof(c));
+  c.stem = true;
+  c.H = H;
+  c.W = W;
+  c.C0 = Cin;
+  c.Cout = Cout;
+  c.x0 = static_cast<uint8_t*>(const_cast<void*>(x4));
+  c.g = static_cast<uint8_t*>(const_cast<void*>(dy));
+  if (Cout == 64) {
+    rc = make_box_map(&c.wD, c.g, B, H, W, 64, 8, 16);
+    if (rc != UB_OK) return rc;
+  }
+  return conv_wgrad_launch(c, B, dw, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_convT2x2_wgrad(const void* x, int Cin, const void* dup, int dup_pitch, int B, int H, int W, int f, float* dw,
+                             float* dbias, void* stream) {
+  if (x == nullptr || dup == nullptr || dw == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin % 128 != 0 || f % 64 != 0 || dup_pitch < f || dup_pitch % 8 != 0) return fail(UB_ERR_ARG, "bad channel counts / pitch");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  TConvT u;
+  memset(&u, 0, sizeof(u));
+  u.H = H;
+  u.W = W;
+  u.Cin = Cin;
+  u.f = f;
+  u.x = static_cast<uint8_t*>(const_cast<void*>(x));
+  u.dup = static_cast<uint8_t*>(const_cast<void*>(dup));
+  rc = setup_up_backward(u, B, (size_t)dup_pitch);
+  if (rc != UB_OK) return rc;
+  return up_wgrad_launch(u, B, dup_pitch / 8, dw, dbias, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_convT2x2_dgrad(const void* dup, int dup_pitch, const void* wd, int B, int H, int W, int Cin, int f, void* dx,
+                             void* stream) {
+  if (dup == nullptr || wd == nullptr || dx == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin % 64 != 0 || f % 64 != 0 || dup_pitch < f || dup_pitch % 8 != 0) return fail(UB_ERR_ARG, "bad channel counts / pitch");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  float* zb;
+  rc = get_zero_bias(&zb);
+  if (rc != UB_OK) return rc;
+  TConvT u;
+  memset(&u, 0, sizeof(u));
+  u.H = H;
+  u.W = W;
+  u.Cin = Cin;
+  u.f = f;
+  u.dup = static_cast<uint8_t*>(const_cast<void*>(dup));
+  u.wd = static_cast<uint8_t*>(const_cast<void*>(wd));
+  u.dx = static_cast<uint8_t*>(dx);
+  rc = setup_up_backward(u, B, (size_t)dup_pitch);
+  if (rc != UB_OK) return rc;
+  return up_dgrad_launch(u, B, zb, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* beta, int B, int H, int W, int C, float eps,
+                                float momentum, float* running_mean, float* running_var, void* a, void* pool, float* stats4,
+                                double* scratch2, void* stream) {
+  if (y == nullptr || gamma == nullptr || beta == nullptr || a == nullptr || stats4 == nullptr || scratch2 == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  if (!pow2_times_64(C)) return fail(UB_ERR_ARG, "C=%d must be a power of two in [64,2048]", C);
+  if (pool != nullptr && ((H | W) & 1)) return fail(UB_ERR_ARG, "pooling needs even H and W");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t npix = (size_t)B * H * W;
+  const int C8 = C / 8;
+  UB_CUDA(cudaMemsetAsync(scratch2, 0, (size_t)2 * C * sizeof(double), st));
+  ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(y), npix, C8, scratch2,
+                                                                         scratch2 + C);
+  UB_CUDA(cudaGetLastError());
+  ub::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch2, scratch2 + C, (float)npix, eps, momentum, gamma, beta, stats4,
+                                                          stats4 + C, stats4 + 2 * C, stats4 + 3 * C, running_mean, running_var, C);
+  UB_CUDA(cudaGetLastError());
+  if (pool != nullptr) {
+    ub::bn_relu_apply_pool_kernel<<<grid_for(npix / 4 * C8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
+                                                                                stats4 + 3 * C, B, H, W, C8,
+                                                                                reinterpret_cast<uint4*>(a),
+                                                                                reinterpret_cast<uint4*>(pool));
+  } else {
+    ub::bn_relu_apply_kernel<<<grid_for(npix * C8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
+                                                                       stats4 + 3 * C, npix * C8, C8, reinterpret_cast<uint4*>(a));
+  }
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_bn_relu_bwd(void* g, const void* y, const float* stats4, int B, int H, int W, int C, float* dgamma, float* dbeta,
+                          void* stream) {
+  if (g == nullptr || y == nullptr || stats4 == nullptr || dgamma == nullptr || dbeta == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (!pow2_times_64(C)) return fail(UB_ERR_ARG, "C=%d must be a power of two in [64,2048]", C);
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TConv c;
+  memset(&c, 0, sizeof(c));
+  c.H = H;
+  c.W = W;
+  c.Cout = C;
+  c.g = static_cast<uint8_t*>(g);
+  c.y = static_cast<uint8_t*>(const_cast<void*>(y));
+  float* s4 = const_cast<float*>(stats4);
+  c.mean = s4;
+  c.invstd = s4 + C;
+  c.scale = s4 + 2 * C;
+  c.shift = s4 + 3 * C;
+  c.s1 = dbeta;   // the reductions accumulate straight into the outputs
+  c.s2 = dgamma;
+  UB_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+  UB_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
+  return conv_bn_backward(c, B, nullptr, nullptr, st);
+}
+
+int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, int skip_pitch, int B, int H, int W, int C,
+                             void* dA, void* stream) {
+  if (a == nullptr || dP == nullptr || dA == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C % 8 != 0 || ((H | W) & 1) || (dskip != nullptr && (skip_pitch < C || skip_pitch % 8 != 0))) return fail(UB_ERR_ARG, "bad shape");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  const int C8 = C / 8;
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * C8;
+  ub::maxpool_bwd_add_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(dP), reinterpret_cast<const uint4*>(dskip),
+      dskip ? skip_pitch / 8 : C8, B, H, W, C8, reinterpret_cast<uint4*>(dA));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+}  // extern "C"

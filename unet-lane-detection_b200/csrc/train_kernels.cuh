@@ -25,7 +25,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // sum[c] += sum_p y[p][c], sumsq[c] += sum_p y[p][c]^2
 __global__ void __launch_bounds__(256)
-chan_stats_kernel(const uint4* __restrict__ y, size_t npix, int C8, float* __restrict__ sum, float* __restrict__ sumsq) {
+chan_stats_kernel(const uint4* __restrict__ y, size_t npix, int C8, double* __restrict__ sum, double* __restrict__ sumsq) {
   extern __shared__ float red[];  // [2][256][8]
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -52,21 +52,23 @@ chan_stats_kernel(const uint4* __restrict__ y, size_t npix, int C8, float* __res
       a += red[(j * C8 + c / 8) * 8 + (c & 7)];
       b += red[2048 + (j * C8 + c / 8) * 8 + (c & 7)];
     }
-    atomicAdd(sum + c, a);
-    atomicAdd(sumsq + c, b);
+    atomicAdd(sum + c, static_cast<double>(a));
+    atomicAdd(sumsq + c, static_cast<double>(b));
   }
 }
 
 // Per channel: batch mean / biased var -> scale = gamma*invstd, shift = beta - mean*scale; running stats update.
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count, float eps,
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, float count, float eps,
                                    float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float m = sum[c] / count;
-  const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  const double md = sum[c] / static_cast<double>(count);
+  const double vd = sumsq[c] / static_cast<double>(count) - md * md;
+  const float m = static_cast<float>(md);
+  const float var = fmaxf(static_cast<float>(vd), 0.f);
   const float is = rsqrtf(var + eps);
   mean[c] = m;
   invstd[c] = is;
@@ -80,18 +82,68 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   }
 }
 
-// a = relu(y*scale + shift)
+// a = relu(y*scale + shift). The grid stride is a multiple of C8 (C8 | 256), so a thread's channel group never changes
+// and its eight scale/shift pairs live in registers.
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                      size_t n8, int C8, uint4* __restrict__ a) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C8) * 8;
+  const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int c = static_cast<int>(i0 % C8) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c + k);
+    sh[k] = __ldg(shift + c + k);
+  }
+  for (size_t i = i0; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float f[8];
     unpack8(__ldg(y + i), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], __ldg(scale + c + k), __ldg(shift + c + k)), 0.f);
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
     a[i] = pack8(f);
+  }
+}
+
+// a = relu(y*scale + shift) and p = maxpool2x2(a) in one pass (encoder conv1: README.md:1464-1467 in train mode).
+// One thread = one 2x2 window x 8 channels.
+__global__ void __launch_bounds__(256)
+bn_relu_apply_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int B,
+                          int H, int W, int C8, uint4* __restrict__ a, uint4* __restrict__ pl) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int c8 = static_cast<int>(i0 % C8);  // loop-invariant: the grid stride is a multiple of C8
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c8 * 8 + k);
+    sh[k] = __ldg(shift + c8 * 8 + k);
+  }
+  for (size_t i = i0; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t r = i / C8;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const size_t b = r / Ho;
+    const size_t base = ((b * H + 2 * ho) * W + 2 * wo) * C8 + c8;
+    const size_t off[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
+    float mx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = 0.f;  // post-ReLU values are >= 0
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+      unpack8(__ldg(y + base + off[q]), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      const uint4 pk = pack8(f);
+      a[base + off[q]] = pk;
+      float fr[8];
+      unpack8(pk, fr);  // pool the bf16-rounded values so p == maxpool(a) bit-exactly
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx[k] = fmaxf(mx[k], fr[k]);
+    }
+    pl[i] = pack8(mx);
   }
 }
 
@@ -142,24 +194,31 @@ bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict_
   }
 }
 
-// pass 2: dY = gamma*invstd * (g - s1/N - xhat * s2/N)
+// pass 2: dY = gamma*invstd * (g - s1/N - xhat * s2/N) = sc*g + k1*y + k0 with per-channel
+//   k1 = -sc*invstd*s2/N,  k0 = -sc*s1/N - k1*mean   (held in registers: the thread's channel group is loop-invariant)
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ y, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ s1, const float* __restrict__ s2,
                          float inv_count, size_t n8, int C8, uint4* __restrict__ dY) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C8) * 8;
+  const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int c = static_cast<int>(i0 % C8) * 8;
+  float sc[8], sh[8], k1[8], k0[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c + k);
+    sh[k] = __ldg(shift + c + k);
+    k1[k] = -sc[k] * __ldg(invstd + c + k) * __ldg(s2 + c + k) * inv_count;
+    k0[k] = -sc[k] * __ldg(s1 + c + k) * inv_count - k1[k] * __ldg(mean + c + k);
+  }
+  for (size_t i = i0; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float fy[8], fd[8], o[8];
     unpack8(__ldg(y + i), fy);
     unpack8(__ldg(dA + i), fd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float sc = __ldg(scale + c + k);
-      const float g = fmaf(fy[k], sc, __ldg(shift + c + k)) > 0.f ? fd[k] : 0.f;
-      const float xh = (fy[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k);
-      o[k] = sc * (g - __ldg(s1 + c + k) * inv_count - xh * __ldg(s2 + c + k) * inv_count);
+      const float g = fmaf(fy[k], sc[k], sh[k]) > 0.f ? fd[k] : 0.f;
+      o[k] = fmaf(sc[k], g, fmaf(k1[k], fy[k], k0[k]));
     }
     dY[i] = pack8(o);
   }
@@ -168,8 +227,9 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
 // Max-pool backward merged with the skip connection's other gradient:
 // dA[b,h,w,c] = (d_skip ? d_skip[b,h,w,c] : 0) + (pixel is the FIRST maximum of its 2x2 window ? dP[b,h/2,w/2,c] : 0)
 __global__ void __launch_bounds__(256)
-maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip, int B,
-                       int H, int W, int C8, uint4* __restrict__ dA) {
+maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip,
+                       int skip_pitch8 /* uint4 per pixel of d_skip (>= C8: it may be the first half of a concat gradient) */,
+                       int B, int H, int W, int C8, uint4* __restrict__ dA) {
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -186,10 +246,12 @@ maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP
 #pragma unroll
     for (int k = 0; k < 4; ++k) unpack8(__ldg(a + base + off[k]), v[k]);
     unpack8(__ldg(dP + i), g);
+    const size_t pix0 = (b * H + 2 * ho) * W + 2 * wo;
+    const size_t poff[4] = {0, 1, (size_t)W, (size_t)W + 1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (d_skip != nullptr) {
-        unpack8(__ldg(d_skip + base + off[k]), o[k]);
+        unpack8(__ldg(d_skip + (pix0 + poff[k]) * skip_pitch8 + c), o[k]);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[k][e] = 0.f;
@@ -213,6 +275,31 @@ maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) dA[base + off[k]] = pack8(o[k]);
+  }
+}
+
+// Head forward in training (README.md:1481): logits[p] = bias + sum_c a[p][c] * w[c]; 8 lanes share one pixel.
+__global__ void __launch_bounds__(256)
+head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias, size_t npix,
+                      int C8, float* __restrict__ logits) {
+  const int sub = threadIdx.x & 7;
+  const size_t stride = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
+  // the loop bound is warp-uniform (p0 is the warp's first pixel) so the shuffles always see all 32 lanes
+  for (size_t p0 = ((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5) << 2; p0 < npix; p0 += stride) {
+    const size_t p = p0 + ((threadIdx.x & 31) >> 3);
+    float acc = 0.f;
+    if (p < npix) {
+      for (int c = sub; c < C8; c += 8) {
+        float f[8];
+        unpack8(__ldg(a + p * C8 + c), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(f[k], __ldg(w + c * 8 + k), acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0 && p < npix) logits[p] = acc + __ldg(bias);
   }
 }
 
@@ -301,6 +388,7 @@ bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, s
     losses[1] = bce;
     losses[2] = dice;
   }
+  if (dz == nullptr) return;  // loss values only
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float x = z[i], y = t[i];
@@ -374,7 +462,7 @@ __global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, 
 
 // per-channel sum of a bf16 NHWC tensor (ConvT bias gradient): out[c] += sum_p x[p][c]
 __global__ void __launch_bounds__(256)
-chan_sum_kernel(const uint4* __restrict__ x, size_t npix, int C8, float* __restrict__ out) {
+chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, float* __restrict__ out) {
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -382,7 +470,7 @@ chan_sum_kernel(const uint4* __restrict__ x, size_t npix, int C8, float* __restr
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
     float f[8];
-    unpack8(__ldg(x + p * C8 + cl), f);
+    unpack8(__ldg(x + p * pitch8 + cl), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += f[i];
   }

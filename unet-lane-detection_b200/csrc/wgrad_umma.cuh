@@ -30,7 +30,8 @@ struct WgradArgs {
   int ksplit;                     // CTAs sharing one output tile
   int c_split;                    // channels of x source 0 (the rest come from source 1)
   int Cin, Cout;
-  long long s_co, s_tap;          // dW index = co*s_co + tap*s_tap + ci
+  long long s_co, s_ci, s_tap;    // dW index = co*s_co + ci*s_ci + tap*s_tap (PyTorch layouts are written directly)
+  int k_mmas;                     // 16-pixel MMAs per box = box rows / 16 (8 unless TB exceeds the batch)
   int a_bytes;                    // bytes of one x / dy box (16384 unless TB exceeds the batch)
   float* dw;                      // fp32 gradient, accumulated atomically
 };
@@ -167,7 +168,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         const uint64_t da = d_hi + (sA >> 4);
         const uint64_t db = d_hi + ((sA + 2 * 16384) >> 4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < a.k_mmas; ++j) {
           // 16 pixel rows per MMA = two 8-row groups = 2048 B
           umma_f16(tmem_base, da + j * 128, db + j * 128, idesc, (kt > k_lo || j > 0) ? 1u : 0u);
         }
@@ -193,7 +194,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       ci = m & 63;
       live = live && tap < a.taps;
     }
-    float* base = a.dw + static_cast<long long>(tap) * a.s_tap + ci;
+    float* base = a.dw + static_cast<long long>(tap) * a.s_tap + static_cast<long long>(ci) * a.s_ci;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t v[32];

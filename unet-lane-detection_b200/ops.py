@@ -162,3 +162,126 @@ def preprocess_u8(frames, size=(224, 224), swap_rb=False, mean=MEAN_255, std=STD
     check(lib.unet_b200_preprocess_u8(frames.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, H, W, int(swap_rb), f3(mean),
                                       f3(std), y.data_ptr(), _p(r), _stream()))
     return (y, r) if return_resized else y
+
+
+# ------------------------------------------------------------------------------------------------
+# Training ops (include/unet_b200.h "single training ops"): thin wrappers used by the parity tests.
+# ------------------------------------------------------------------------------------------------
+def pack_conv3x3_dgrad(w):
+    """w fp32 [Cout,Cin,3,3] -> wd bf16 [Cin,9,Cout] (rotated 180 degrees, in/out swapped)."""
+    _req(w, torch.float32, "w")
+    cout, cin = w.shape[:2]
+    wd = torch.empty(cin, 9, cout, dtype=torch.bfloat16, device=w.device)
+    check(lib.unet_b200_pack_conv3x3_dgrad(w.data_ptr(), cout, cin, wd.data_ptr(), _stream()))
+    return wd
+
+
+def conv3x3_dgrad(dy, wd):
+    """Input gradient of a bias-free 3x3 conv: dy bf16 [B,H,W,Cout], wd from pack_conv3x3_dgrad -> dx bf16 [B,H,W,Cin]."""
+    zero = torch.zeros(wd.shape[0], dtype=torch.float32, device=dy.device)
+    return conv3x3(dy, wd, zero, relu=False)
+
+
+def conv3x3_wgrad(x0, dy, x1=None):
+    """dW fp32 [Cout, C0+C1, 3, 3] for x = cat(x0, x1) and dy."""
+    _req(x0, torch.bfloat16, "x0")
+    _req(dy, torch.bfloat16, "dy")
+    B, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else _req(x1, torch.bfloat16, "x1").shape[3]
+    cout = dy.shape[3]
+    dw = torch.zeros(cout, C0 + C1, 3, 3, dtype=torch.float32, device=x0.device)
+    check(lib.unet_b200_conv3x3_wgrad(x0.data_ptr(), C0, _p(x1), C1, dy.data_ptr(), B, H, W, cout, dw.data_ptr(), _stream()))
+    return dw
+
+
+def stem_wgrad(x4, dy, cin):
+    _req(x4, torch.bfloat16, "x4")
+    _req(dy, torch.bfloat16, "dy")
+    B, H, W, _ = x4.shape
+    cout = dy.shape[3]
+    dw = torch.zeros(cout, cin, 3, 3, dtype=torch.float32, device=x4.device)
+    check(lib.unet_b200_stem_wgrad(x4.data_ptr(), dy.data_ptr(), B, H, W, cin, cout, dw.data_ptr(), _stream()))
+    return dw
+
+
+def pack_convT2x2_dgrad(w):
+    _req(w, torch.float32, "w")
+    cin, f = w.shape[:2]
+    wd = torch.empty(cin, 4 * f, dtype=torch.bfloat16, device=w.device)
+    check(lib.unet_b200_pack_convT2x2_dgrad(w.data_ptr(), cin, f, wd.data_ptr(), _stream()))
+    return wd
+
+
+def _dup_view(dup, f):
+    """dup: bf16 [B,2H,2W,P] holding the ConvT output gradient in its LAST f channels (P >= f)."""
+    _req(dup, torch.bfloat16, "dup")
+    pitch = dup.shape[3]
+    return dup.data_ptr() + (pitch - f) * 2, pitch
+
+
+def convT2x2_wgrad(x, dup, f):
+    """x bf16 [B,H,W,Cin]; dup bf16 [B,2H,2W,P] (gradient in the last f channels) -> (dW fp32 [Cin,f,2,2], dbias fp32 [f])."""
+    _req(x, torch.bfloat16, "x")
+    B, H, W, cin = x.shape
+    ptr, pitch = _dup_view(dup, f)
+    dw = torch.zeros(cin, f, 2, 2, dtype=torch.float32, device=x.device)
+    db = torch.zeros(f, dtype=torch.float32, device=x.device)
+    check(lib.unet_b200_convT2x2_wgrad(x.data_ptr(), cin, ptr, pitch, B, H, W, f, dw.data_ptr(), db.data_ptr(), _stream()))
+    return dw, db
+
+
+def convT2x2_dgrad(dup, wd, f):
+    ptr, pitch = _dup_view(dup, f)
+    B, H2, W2, _ = dup.shape
+    cin = wd.shape[0]
+    dx = torch.empty(B, H2 // 2, W2 // 2, cin, dtype=torch.bfloat16, device=dup.device)
+    check(lib.unet_b200_convT2x2_dgrad(ptr, pitch, wd.data_ptr(), B, H2 // 2, W2 // 2, cin, f, dx.data_ptr(), _stream()))
+    return dx
+
+
+def bn_relu_train_fwd(y, gamma, beta, eps=1e-5, momentum=0.1, running_mean=None, running_var=None, pool=False):
+    """y bf16 [B,H,W,C] -> (a, pooled or None, stats fp32 [4,C] = mean, invstd, scale, shift)."""
+    _req(y, torch.bfloat16, "y")
+    B, H, W, C = y.shape
+    a = torch.empty_like(y)
+    p = torch.empty(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=y.device) if pool else None
+    stats = torch.empty(4, C, dtype=torch.float32, device=y.device)
+    scratch = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    check(lib.unet_b200_bn_relu_train_fwd(y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H, W, C, float(eps),
+                                          float(momentum), _p(running_mean), _p(running_var), a.data_ptr(), _p(p),
+                                          stats.data_ptr(), scratch.data_ptr(), _stream()))
+    return a, p, stats
+
+
+def bn_relu_bwd(dA, y, stats):
+    """dA bf16 [B,H,W,C] (not modified) -> (dY bf16, dgamma fp32 [C], dbeta fp32 [C])."""
+    _req(dA, torch.bfloat16, "dA")
+    _req(y, torch.bfloat16, "y")
+    B, H, W, C = y.shape
+    g = dA.clone()
+    dgamma = torch.empty(C, dtype=torch.float32, device=y.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=y.device)
+    check(lib.unet_b200_bn_relu_bwd(g.data_ptr(), y.data_ptr(), stats.data_ptr(), B, H, W, C, dgamma.data_ptr(),
+                                    dbeta.data_ptr(), _stream()))
+    return g, dgamma, dbeta
+
+
+def maxpool2x2_bwd(a, dP, dskip=None):
+    """a bf16 [B,H,W,C], dP bf16 [B,H/2,W/2,C], dskip bf16 [B,H,W,P>=C] (its FIRST C channels are added) -> dA."""
+    _req(a, torch.bfloat16, "a")
+    _req(dP, torch.bfloat16, "dP")
+    B, H, W, C = a.shape
+    dA = torch.empty_like(a)
+    pitch = C if dskip is None else _req(dskip, torch.bfloat16, "dskip").shape[3]
+    check(lib.unet_b200_maxpool2x2_bwd(a.data_ptr(), dP.data_ptr(), _p(dskip), pitch, B, H, W, C, dA.data_ptr(), _stream()))
+    return dA
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4,
+               grad_scale=1.0):
+    """In-place torch.optim.AdamW step on flat fp32 tensors."""
+    for t, n in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, n)
+    check(lib.unet_b200_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), params.numel(),
+                                   float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                   float(grad_scale), _stream()))

@@ -61,6 +61,7 @@ class UNet(nn.Module):
         # B200 runtime state (not part of the state_dict)
         self.b200_chunk = 128  # frames per pass through the plan (bounds the workspace; tune for L2 reuse)
         self._engines = {}
+        self._b200_epoch = 0  # bumped whenever a kernel updates parameters / BN buffers in place
         self.gpu_launches = 0
 
     def _conv_block(self, in_channels, out_channels):
@@ -82,7 +83,7 @@ class UNet(nn.Module):
             yield blk[3], blk[4]
 
     def _weights_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return (self._b200_epoch,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _engine(self, device, H, W, batch):
         cap = min(max(1, int(self.b200_chunk)), batch) if batch < self.b200_chunk else int(self.b200_chunk)
@@ -122,13 +123,15 @@ class UNet(nn.Module):
 
     # ------------------------------------------------------------------ forward paths
     def forward(self, x):
-        """Eval-mode forward on the B200 kernels: float NCHW -> logits NCHW (README.md:1460-1481)."""
-        if self.training:
-            raise RuntimeError("UNet (B200): the training-mode forward (batch-statistics BatchNorm) is not built yet; "
-                               "call .eval() for inference")
+        """Forward on the B200 kernels: float NCHW -> logits NCHW (README.md:1460-1481).
+        eval(): BatchNorm folded into the weights. train(): batch-statistics BatchNorm, activations kept, and the
+        result carries a grad_fn whose backward runs the B200 backward kernels (training.py)."""
         self._check_input(x, "input")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise ValueError(f"expected [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        if self.training:
+            from .training import forward_train_autograd
+            return forward_train_autograd(self, x)
         B, _, H, W = x.shape
         xin = x.detach().to(torch.float32).contiguous()
         x4 = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=x.device)
