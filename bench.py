@@ -149,6 +149,52 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_FRAME  # forward + dgrad + wgrad
+
+
+def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=False):
+    """BASELINE.json configs[3]: U-Net training step (BCE+Dice, AdamW), bf16 tensor-core convs, `batch` samples per GPU,
+    NCCL all-reduce of the flat fp32 gradient when world > 1. Returns a dict for the JSON line."""
+    import torch
+    import unet_lane_detection_b200 as U
+    torch.manual_seed(0)
+    net = U.UNet(3, 1, FEATURES).to(dev).train()
+    g = torch.Generator(device="cpu").manual_seed(42 + rank)           # README.md:2248 seed + rank
+    x_host = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    y_host = (torch.rand(batch, 1, 224, 224, generator=g) < 0.085).float().pin_memory()   # 8.5 % positives (README.md:2534)
+    x, y = x_host.to(dev), y_host.to(dev)
+    step = U.FusedTrainStep(net)                                        # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
+    box = {}
+
+    def run_dev():
+        box["loss"] = step.step(x, y)
+
+    def run_host():                                                     # README.md:2067-2081: .to(device) ... loss.item()
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        box["loss_host"] = step.step(xd, yd).tolist()
+
+    for _ in range(max(warmup, 3)):
+        run_dev()
+    ms = timed(run_dev, steps)
+    loss = box["loss"].tolist()
+    value = world * batch * steps / (ms / 1e3)
+    out = {"metric": "unet224_train_samples_per_sec", "value": value, "unit": "samples/s", "ms_per_step": ms / steps,
+           "batch_per_gpu": batch, "tflops_per_gpu": value / world * TRAIN_FLOPS_PER_SAMPLE / 1e12,
+           "flops_per_sample": TRAIN_FLOPS_PER_SAMPLE, "loss_after": loss,
+           "collective": "none" if world == 1 else f"NCCL all-reduce(sum) of the flat fp32 gradient ({31037633 * 4 / 1e6:.0f} MB) per step",
+           "config": "BASELINE.json configs[3]: BCE+Dice (pos_weight 3), AdamW lr 1e-4 wd 1e-4, BatchNorm batch statistics per replica"}
+    if host_inputs:
+        run_host()
+        ms_h = timed(run_host, steps)
+        out["e2e"] = {"value": world * batch * steps / (ms_h / 1e3), "unit": "samples/s", "ms_per_step": ms_h / steps,
+                      "h2d_bytes_per_step": batch * 224 * 224 * 4 * 4, "d2h_bytes_per_step": 12,
+                      "api": "FusedTrainStep.step on pinned host tensors, loss read back every step"}
+    del step, net
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +203,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="frames per pass through the plan")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE.json headline (configs[1]); train: the training step of configs[3] as the metric")
+    ap.add_argument("--train-batch", type=int, default=64, help="samples per GPU per training step (configs[3])")
+    ap.add_argument("--no-train", action="store_true", help="infer mode: skip the secondary training-step measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-kernel profile table to this JSON file")
     args = ap.parse_args()
@@ -208,6 +258,34 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+
+    if args.mode == "train":
+        peaks = load_peaks()
+        sampler = ClockSampler(index=int(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]) if rank == 0 else 0)
+        if rank == 0:
+            sampler.start()
+        tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True)
+        clocks = sampler.summary() if rank == 0 else None
+        line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": tr["config"], "batch_per_gpu": args.train_batch, "parallelism": f"data-parallel x{world}",
+                           "collective": tr["collective"],
+                           "l2_policy": f"activations + gradients {args.train_batch * 3 * 64.1:.0f} MB per step >> 126 MB L2"},
+                "e2e": tr["e2e"], "gpu_launches": None, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": tr["tflops_per_gpu"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": tr["tflops_per_gpu"] / peaks["bf16_sustained"], "traffic": None,
+                             "kernel": "whole training step (forward + dgrad + wgrad GEMMs = 3x forward FLOPs; BN/loss/AdamW passes are HBM-bound extras)",
+                             "peak_source": peaks["source"] + " bf16_tflops_sustained"},
+                "loss_after": tr["loss_after"]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            os.dup2(2, 1)
+            dist.destroy_process_group()
+        return
 
     def step_device():
         model.predict_mask(frames_dev, threshold=0.5, want=("mask",))
@@ -283,6 +361,11 @@ def main():
                 "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host (pinned host buffers)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    if not args.no_train:
+        del frames_dev
+        model._engines.clear()
+        torch.cuda.empty_cache()
+        line["train"] = measure_train(dev, world, rank, args.train_batch, min(args.steps, 10), 3, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sps, threads = time_cpu_reference(8, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

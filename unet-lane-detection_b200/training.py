@@ -165,6 +165,18 @@ def bce_dice_loss(logits, target, pos_weight=3.0, bce_weight=0.5, dice_weight=0.
     return losses, dz
 
 
+def allreduce_gradients(flat_grads, group=None):
+    """Data-parallel exchange step: ONE all-reduce(sum) of the flat fp32 gradient buffer (NCCL over NVLink on GPUs, gloo in
+    the CPU tests). Returns the factor the optimizer must apply to the summed gradient (1/world) - the scaling is folded
+    into the AdamW kernel instead of a separate pass over the buffer."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
 class FusedTrainStep:
     """zero_grad -> forward -> BCEDiceLoss -> backward -> (all-reduce) -> AdamW.step, README.md:2071-2079 with the
     criterion / optimizer of README.md:2169-2174, all on the B200 kernels. Data-parallel: pass a process group (or
@@ -206,13 +218,11 @@ class FusedTrainStep:
         eng, logits = train_forward(model, x4)
         losses, dz = bce_dice_loss(logits, masks.reshape(logits.shape), **self.loss_cfg)
         grads = train_backward(model, eng, dz)
-        world = self._world()
-        if world > 1:
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=self.group)
+        grad_scale = allreduce_gradients(grads, self.group)
         self.step_count += 1
         check(lib.unet_b200_adamw_step(flat.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                        flat.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                                       float(self.weight_decay), self.step_count, 1.0 / world,
+                                       float(self.weight_decay), self.step_count, grad_scale,
                                        torch.cuda.current_stream().cuda_stream))
         model._b200_epoch += 1  # the kernel wrote the parameters behind autograd's back: repack before the next eval
         self.last_grads = grads
