@@ -187,6 +187,11 @@ int unet_b200_adamw_step(float* params_dev, const float* grads_dev, float* exp_a
                          float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                          void* stream);
 
+/* Same, with the step count read from device memory (int32, >= 1) so the call can be captured in a CUDA graph. */
+int unet_b200_adamw_step_dev(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, size_t n,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, const int* step_dev,
+                             float grad_scale, void* stream);
+
 /* ---- single training ops (same kernels the trainer runs; exposed for parity tests and reuse) ------------------------ *
  * All activations bf16 NHWC, gradients of activations bf16 NHWC, weight gradients fp32 in the PyTorch layout and
  * ACCUMULATED into dw (zero it first). */

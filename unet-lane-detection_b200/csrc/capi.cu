@@ -253,7 +253,7 @@ int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const
 int g_sattr_done = 0;
 
 int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x, const float* bias, int B, int H, int W,
-                     int relu, cudaStream_t st) {
+                     int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
   if (!g_sattr_done) {
@@ -270,6 +270,8 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
   a.relu = relu;
   a.x = reinterpret_cast<const uint2*>(x);
   a.bias = bias;
+  a.stat_sum = stat_sum;
+  a.stat_sumsq = stat_sumsq;
   const int total = a.tiles_w * a.tiles_h * B;
   const int grid = total < g_num_sms ? total : g_num_sms;
   ub::stem_umma_kernel<<<grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st>>>(mw, mo, a);
@@ -460,6 +462,8 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.Cout = l.Cout;
   a.bias = bias;
   a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
+  a.stat_sum = nullptr;
+  a.stat_sumsq = nullptr;
   if (l.TB >= 4) {
     a.sub_b = l.TB / 4;
     a.sub_h = l.TH;
@@ -529,12 +533,17 @@ int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const voi
 }
 
 // Launch a layer prepared by conv_layer_setup (maps were built for batch capacity Bc).
-int conv_layer_launch(const Layer& l, int batch, int Bc, const float* bias, void* y, void* pool, cudaStream_t st) {
+int conv_layer_launch(const Layer& l, int batch, int Bc, const float* bias, void* y, void* pool, cudaStream_t st,
+                      double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
   if (l.halo) {
     ub::HaloArgs ha = halo_args(l, batch, bias, y, pool);
+    ha.stat_sum = stat_sum;
+    ha.stat_sumsq = stat_sumsq;
     return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, st);
   }
   ub::ConvArgs a = conv_args(l, batch, Bc, bias, y, pool);
+  a.stat_sum = stat_sum;
+  a.stat_sumsq = stat_sumsq;
   const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
   return launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
 }

@@ -42,6 +42,8 @@ struct HaloArgs {
   float* logits;            // [B,H,W] or null
   float* probs;             // [B,H,W] or null
   uint8_t* mask;            // [B,H,W] or null
+  double* stat_sum;         // HEPI_STORE, optional (training): per-channel sum / sum of squares of the bf16 output
+  double* stat_sumsq;
 };
 
 struct HaloCfg {
@@ -239,6 +241,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int th = m >> 3;
     uint8_t* stg = smS + (warp - 2) * 4096;
     const bool pool_writer = ((tw | th) & 1) == 0;
+    float st0[4] = {0.f, 0.f, 0.f, 0.f};  // fused batch statistics of this warp's 64-column group (epilogue.cuh)
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -276,6 +279,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int j = 0; j < 8; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
           }
         }
+        if (a.stat_sum != nullptr) epi_stats_accumulate(stg, lane, __ballot_sync(0xffffffffu, valid), st0);
       } else {
         // HEPI_HEAD (BLOCK_N == 64): 1x1 conv over the bf16-rounded activations (same rounding point as the unfused path)
         float z = a.head_b;
@@ -300,6 +304,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
       }
+    }
+    if (a.stat_sum != nullptr && a.epi == HEPI_STORE) {
+      epi_stats_flush(a.stat_sum, a.stat_sumsq, (HALVES == 1 ? 0 : cg) * 64, lane, st0);
     }
     if (lane == 0) bulk_wait_group_read<0>();
   }

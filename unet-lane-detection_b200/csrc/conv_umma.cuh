@@ -40,6 +40,8 @@ struct ConvArgs {
   int a_bytes;                    // bytes one A box load delivers (128 rows x 128 B unless TB exceeds the batch dim)
   int Cout;                       // EPI_STORE: channels of out; EPI_CONVT: f (out channels of the ConvT)
   const float* bias;              // [Cout]
+  double* stat_sum;               // EPI_STORE, optional (training): per-channel sum / sum of squares of the bf16 output,
+  double* stat_sumsq;             //   accumulated atomically ([Cout] each, zeroed by the caller)
 };
 
 constexpr int CONV_THREADS = 320;
@@ -216,6 +218,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       off_h = q * a.sub_h;
     }
     const bool pool_writer = ((tw | th) & 1) == 0;
+    // fused batch statistics: two accumulator sets (a warp serves at most two 64-column groups of a tile), flushed
+    // when the tile's column block changes (never, when gridDim.x is a multiple of n_tiles) and at the end
+    float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};
+    int st_ntile = -1;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -225,6 +231,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int w0 = (m_tile % a.tiles_w) * a.TW;
       const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
       const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
+      uint32_t vmask = 0;
+      if (a.stat_sum != nullptr) {
+        vmask = __ballot_sync(0xffffffffu, (w0 + tw < a.W) && (h0 + th < a.H) && (b0 + tb < a.B));
+        if (n_tile != st_ntile) {
+          if (st_ntile >= 0) {
+            const int c0 = st_ntile * BLOCK_N + (HALVES == 1 ? 0 : cg) * 64;
+            epi_stats_flush(a.stat_sum, a.stat_sumsq, c0, lane, st0);
+            if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c0 + 128, lane, st1);
+          }
+          st_ntile = n_tile;
+        }
+      }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -265,7 +283,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int j = 0; j < 8; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
           }
         }
+        // (after the pool: the accumulator registers p[] are dead here, the staging tile still holds the unit)
+        if (a.stat_sum != nullptr) {
+          if (hf == (HALVES == 1 ? 0 : cg)) {
+            epi_stats_accumulate(stg, lane, vmask, st0);
+          } else {
+            epi_stats_accumulate(stg, lane, vmask, st1);
+          }
+        }
       }
+    }
+    if (a.stat_sum != nullptr && st_ntile >= 0) {
+      const int c0 = st_ntile * BLOCK_N + (HALVES == 1 ? 0 : cg) * 64;
+      epi_stats_flush(a.stat_sum, a.stat_sumsq, c0, lane, st0);
+      if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c0 + 128, lane, st1);
     }
     if (lane == 0) bulk_wait_group_read<0>();
   }

@@ -55,6 +55,39 @@ __device__ __forceinline__ void epi_stage_row(uint8_t* tile, int row, const uint
   }
 }
 
+// ---- fused BatchNorm batch statistics (training forward) -------------------------------------------------------------
+// Per-channel sum and sum of squares of the unit that was just staged, taken from the bf16-ROUNDED values in the staging
+// tile (the statistics BatchNorm will normalise with are those of the tensor it actually reads). Lane L owns channels
+// 2L, 2L+1 of the 64-column unit and walks the 32 rows; rows whose pixel lies outside the tensor (clipped by the TMA store)
+// are skipped through the warp-uniform `valid_mask` (bit r = row r is a real pixel). acc = {s0, ss0, s1, ss1}.
+__device__ __forceinline__ void epi_stats_accumulate(const uint8_t* tile, int lane, uint32_t valid_mask, float (&acc)[4]) {
+  const uint32_t base = smem_u32(tile) + (lane & 3) * 4;
+  const int chunk = lane >> 2;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    if ((valid_mask >> r) & 1u) {
+      uint32_t w;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
+      const float lo = __low2float(h), hi = __high2float(h);
+      acc[0] += lo;
+      acc[1] = fmaf(lo, lo, acc[1]);
+      acc[2] += hi;
+      acc[3] = fmaf(hi, hi, acc[3]);
+    }
+  }
+}
+// Adds the lane's partial sums for channels col + 2*lane, +1 to the global double accumulators and clears them.
+__device__ __forceinline__ void epi_stats_flush(double* __restrict__ sum, double* __restrict__ sumsq, int col, int lane,
+                                                float (&acc)[4]) {
+  const int c = col + 2 * lane;
+  atomicAdd(sum + c, static_cast<double>(acc[0]));
+  atomicAdd(sumsq + c, static_cast<double>(acc[1]));
+  atomicAdd(sum + c + 1, static_cast<double>(acc[2]));
+  atomicAdd(sumsq + c + 1, static_cast<double>(acc[3]));
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+}
+
 // 2x2 max over the window partners lane^1 (w) and lane^xor_h (h); afterwards every lane of a window holds the max.
 __device__ __forceinline__ void epi_pool2x2(uint32_t (&p)[32], int xor_h) {
 #pragma unroll

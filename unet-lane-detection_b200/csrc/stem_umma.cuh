@@ -20,6 +20,8 @@ struct StemArgs {
   int relu;
   const uint2* x;         // [B,H,W] x 4 bf16
   const float* bias;      // [64]
+  double* stat_sum;       // optional (training): per-channel sum / sum of squares of the bf16 output
+  double* stat_sumsq;
 };
 
 struct StemCfg {
@@ -168,6 +170,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int q = warp & 3;
     const int cg = (warp - 1) >> 2;
     uint8_t* stg = smS + (warp - 1) * 4096;
+    float st0[4] = {0.f, 0.f, 0.f, 0.f};  // fused batch statistics (epilogue.cuh)
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       if ((it & 1) != cg) continue;
@@ -191,7 +194,12 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         tma_store_4d(&tmOut, stg, 0, w0, h0 + 4 * q, b);
         bulk_commit_group();
       }
+      if (a.stat_sum != nullptr) {
+        const bool valid = (w0 + (lane & 7) < a.W) && (h0 + 4 * q + (lane >> 3) < a.H);
+        epi_stats_accumulate(stg, lane, __ballot_sync(0xffffffffu, valid), st0);
+      }
     }
+    if (a.stat_sum != nullptr) epi_stats_flush(a.stat_sum, a.stat_sumsq, 0, lane, st0);
     if (lane == 0) bulk_wait_group_read<0>();
   }
 

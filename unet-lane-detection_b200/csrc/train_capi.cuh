@@ -346,9 +346,11 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
                          float* const* running_var, float momentum, float eps, cudaStream_t st) {
   const int B = t->B;
   int rc;
+  // the tensor-core kernels accumulate the per-channel batch statistics of their bf16 output in the epilogue
+  bool stats_done = true;
   if (c.stem) {
     if (c.Cout == 64) {
-      rc = launch_stem_umma(c.fwd.mW, c.fwd.mOut, c.x0, t->zero_bias, B, c.H, c.W, 0, st);
+      rc = launch_stem_umma(c.fwd.mW, c.fwd.mOut, c.x0, t->zero_bias, B, c.H, c.W, 0, st, c.sum, c.sumsq);
       if (rc != UB_OK) return rc;
     } else {
       const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
@@ -357,16 +359,19 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
                                                       t->zero_bias, B, c.H, c.W, c.C0, c.Cout, 0,
                                                       reinterpret_cast<__nv_bfloat16*>(c.y));
       UB_CUDA(cudaGetLastError());
+      stats_done = false;
     }
   } else {
-    rc = conv_layer_launch(c.fwd, B, B, t->zero_bias, c.y, nullptr, st);
+    rc = conv_layer_launch(c.fwd, B, B, t->zero_bias, c.y, nullptr, st, c.sum, c.sumsq);
     if (rc != UB_OK) return rc;
   }
   const size_t npix = (size_t)B * c.H * c.W;
   const int C8 = c.Cout / 8;
-  ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(c.y), npix, C8, c.sum,
-                                                                         c.sumsq);
-  UB_CUDA(cudaGetLastError());
+  if (!stats_done) {
+    ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(c.y), npix, C8, c.sum,
+                                                                           c.sumsq);
+    UB_CUDA(cudaGetLastError());
+  }
   ub::bn_finalize_kernel<<<(c.Cout + 127) / 128, 128, 0, st>>>(
       c.sum, c.sumsq, (float)npix, eps, momentum, params + c.gamma_off, params + c.beta_off, c.mean, c.invstd, c.scale, c.shift,
       running_mean ? running_mean[bn_idx] : nullptr, running_var ? running_var[bn_idx] : nullptr, c.Cout);
@@ -767,7 +772,22 @@ int unet_b200_adamw_step(float* params, const float* grads, float* exp_avg, floa
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   ub::adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                                   beta2, eps, weight_decay, bc1, bc2, grad_scale);
+                                                                                   beta2, eps, weight_decay, bc1, bc2, grad_scale,
+                                                                                   nullptr);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || step_dev == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  ub::adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                                   beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
+                                                                                   step_dev);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }

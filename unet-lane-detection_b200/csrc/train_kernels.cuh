@@ -401,9 +401,19 @@ bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, s
 }
 
 // AdamW (torch.optim.AdamW semantics, README.md:2173-2174) on flat fp32 arrays; grad is pre-multiplied by grad_scale (1/world).
+// step_dev (optional): the step count lives in device memory (CUDA-graph replays cannot change kernel arguments), and the
+// bias corrections are derived from it here; otherwise bc1/bc2 come from the host.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_scale) {
+             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_scale,
+             const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const float st = static_cast<float>(*step_dev);
+    bc1 = 1.f - powf(beta1, st);
+    bc2 = 1.f - powf(beta2, st);
+  }
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -412,8 +422,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-    pi -= (lr / bc1) * (mi / denom);
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    pi -= step_size * (mi / denom);
     p[i] = pi;
   }
 }

@@ -181,49 +181,94 @@ class FusedTrainStep:
     """zero_grad -> forward -> BCEDiceLoss -> backward -> (all-reduce) -> AdamW.step, README.md:2071-2079 with the
     criterion / optimizer of README.md:2169-2174, all on the B200 kernels. Data-parallel: pass a process group (or
     initialise torch.distributed) and gradients are summed over ranks with ONE NCCL all-reduce of the flat buffer;
-    BatchNorm statistics and the loss stay per replica (the reference is single-device)."""
+    BatchNorm statistics and the loss stay per replica (the reference is single-device).
+
+    cuda_graph=True: the ~270 kernel launches of a step are captured once per (input shape, hyper-parameters) and
+    replayed; the first step of a configuration runs eagerly, the second captures. Results are the same kernels
+    either way. `lr` may be changed between steps (a scheduler): the graph is re-captured for the new value."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, bce_weight=0.5, dice_weight=0.5,
-                 pos_weight=3.0, smooth=1e-6, process_group=None):
+                 pos_weight=3.0, smooth=1e-6, process_group=None, cuda_graph=True):
         self.model = model
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.loss_cfg = dict(pos_weight=pos_weight, bce_weight=bce_weight, dice_weight=dice_weight, smooth=smooth)
         self.group = process_group
+        self.cuda_graph = cuda_graph
         self.step_count = 0
+        self.step_dev = None       # int32 device copy of step_count (read by the AdamW kernel)
         self.exp_avg = None
         self.exp_avg_sq = None
-        self.gpu_launches = 0
+        self.last_grads = None
+        self._graphs = {}
+        self._seen = set()
 
     def _world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def step(self, images, masks):
-        """images: float NCHW [B,3,H,W] (or bf16 NHWC4 [B,H,W,4]); masks: [B,1,H,W] / [B,H,W] in {0,1}.
-        Returns a device tensor [total, bce, dice] (no host sync)."""
+    def _prepare(self, device):
+        flat = flatten_parameters_(self.model)
+        if self.exp_avg is None or self.exp_avg.numel() != flat.numel() or self.exp_avg.device != flat.device:
+            self.exp_avg = torch.zeros_like(flat)
+            self.exp_avg_sq = torch.zeros_like(flat)
+            self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=device)
+        return flat
+
+    def _run(self, images, masks):
+        """All kernels of one step on the current stream (eager or under graph capture)."""
         model = self.model
-        if not model.training:
-            raise RuntimeError("FusedTrainStep.step needs model.train()")
         if images.dtype == torch.bfloat16 and images.dim() == 4 and images.shape[-1] == 4:
-            x4 = images.contiguous()
+            x4 = images
         else:
             B, _, H, W = images.shape
-            xin = images.detach().to(torch.float32).contiguous()
+            xin = images if images.dtype == torch.float32 else images.to(torch.float32)
             x4 = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=images.device)
             check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, model.in_channels, H, W, x4.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream))
         flat = flatten_parameters_(model)
-        if self.exp_avg is None or self.exp_avg.numel() != flat.numel():
-            self.exp_avg = torch.zeros_like(flat)
-            self.exp_avg_sq = torch.zeros_like(flat)
         eng, logits = train_forward(model, x4)
         losses, dz = bce_dice_loss(logits, masks.reshape(logits.shape), **self.loss_cfg)
         grads = train_backward(model, eng, dz)
         grad_scale = allreduce_gradients(grads, self.group)
+        self.step_dev.add_(1)
+        check(lib.unet_b200_adamw_step_dev(flat.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                           flat.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                           float(self.weight_decay), self.step_dev.data_ptr(), grad_scale,
+                                           torch.cuda.current_stream().cuda_stream))
+        return losses, grads
+
+    def step(self, images, masks):
+        """images: float NCHW [B,3,H,W] (or bf16 NHWC4 [B,H,W,4]); masks: [B,1,H,W] / [B,H,W] in {0,1}.
+        Returns a device tensor [total, bce, dice] (no host sync; with cuda_graph it is overwritten by the next step)."""
+        model = self.model
+        if not model.training:
+            raise RuntimeError("FusedTrainStep.step needs model.train()")
+        if not images.is_cuda or not masks.is_cuda:
+            raise RuntimeError("FusedTrainStep (B200): inputs must be CUDA tensors - there is no CPU fallback")
+        images = images.detach().contiguous()
+        masks = masks.detach().contiguous().to(torch.float32)
+        flat = self._prepare(images.device)
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), flat.data_ptr(), float(self.lr), float(self.weight_decay),
+               tuple(self.betas), float(self.eps))
         self.step_count += 1
-        check(lib.unet_b200_adamw_step(flat.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                       flat.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                                       float(self.weight_decay), self.step_count, grad_scale,
-                                       torch.cuda.current_stream().cuda_stream))
-        model._b200_epoch += 1  # the kernel wrote the parameters behind autograd's back: repack before the next eval
-        self.last_grads = grads
+        if not self.cuda_graph or key not in self._seen:
+            self._seen.add(key)                    # first step of a configuration: eager (creates engines, sets attributes)
+            losses, self.last_grads = self._run(images, masks)
+        else:
+            entry = self._graphs.get(key)
+            if entry is None:
+                sx, sy = torch.empty_like(images), torch.empty_like(masks)
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):
+                    out = self._run(sx, sy)
+                entry = (graph, sx, sy, out)
+                self._graphs[key] = entry
+            graph, sx, sy, (losses, grads) = entry
+            if sx.data_ptr() != images.data_ptr():
+                sx.copy_(images, non_blocking=True)
+            if sy.data_ptr() != masks.data_ptr():
+                sy.copy_(masks, non_blocking=True)
+            graph.replay()
+            self.last_grads = grads
+        model._b200_epoch += 1  # kernels wrote parameters / BN buffers behind autograd's back: repack before the next eval
         return losses
