@@ -19,14 +19,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--hw", nargs=2, type=int, default=[224, 224])
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--per-launch", default=None, help="substring: list every launch of matching kernels in order")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph")
+    ap.add_argument("--opt", action="append", default=[], help="library switch name=value (unet_b200_set_option)")
     args = ap.parse_args()
+    from unet_lane_detection_b200._lib import check, lib
+    for o in args.opt:
+        k, v = o.split("=")
+        check(lib.unet_b200_set_option(k.encode(), int(v)))
     torch.manual_seed(0)
     net = U.UNet(3, 1, [64, 128, 256, 512]).cuda().train()
     B, (H, W) = args.batch, args.hw
     g = torch.Generator(device="cuda").manual_seed(42)
     x = torch.randn(B, 3, H, W, device="cuda", generator=g)
     y = (torch.rand(B, 1, H, W, device="cuda", generator=g) < 0.085).float()
-    step = U.FusedTrainStep(net)
+    step = U.FusedTrainStep(net, cuda_graph=not args.eager)
     for _ in range(3):
         losses = step.step(x, y)
     torch.cuda.synchronize()
@@ -51,6 +58,11 @@ def main():
                 k = ev.name[:90]
                 t, n = agg.get(k, (0.0, 0))
                 agg[k] = (t + ev.device_time_total if hasattr(ev, "device_time_total") else t + ev.cuda_time_total, n + 1)
+        if args.per_launch:
+            evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and args.per_launch in ev.name]
+            evs.sort(key=lambda e: e.time_range.start)
+            for i, ev in enumerate(evs):
+                print(f"  #{i:2d} {ev.device_time_total:8.1f} us  {ev.name[:70]}")
         tot = sum(t for t, _ in agg.values())
         for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"{t / 1e3:9.3f} ms {100 * t / tot:5.1f}% x{n:3d}  {k}")

@@ -163,6 +163,8 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
   t->ws_bytes = bp.off;
 }
 
+int g_opt_wgrad_rows64 = 1;  // A/B switch: 64-pixel reduction tiles for BLOCK_N == 256
+
 template <int BN>
 int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
                    int slot, cudaStream_t st) {
@@ -193,7 +195,14 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   a.B = B;
   a.H = H;
   a.W = W;
-  pick_tile(H, W, &a.TW, &a.TH, &a.TB);
+  *bn = pick_block_n(Cout);
+  // reduction tile = a box of 128 pixels, or 64 for the wide tiles: (2 + BLOCK_N/64) boxes per stage must leave room for a
+  // ring deep enough to hide the L2 latency (BLOCK_N 256: 4 stages of 48 KB instead of 2 of 96 KB)
+  const int rows_full = (*bn == 256 && g_opt_wgrad_rows64) ? 64 : 128;
+  a.TW = pow2_divisor(W, 16);
+  a.TH = pow2_divisor(H, rows_full / a.TW);
+  a.TB = rows_full / (a.TW * a.TH);
+  a.blk_bytes = rows_full * 128;
   const int tb_eff = a.TB < B ? a.TB : B;
   const int rows = a.TW * a.TH * tb_eff;
   if (rows % 16 != 0) {
@@ -208,8 +217,9 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   a.taps = taps;
   a.Cin = Cin;
   a.Cout = Cout;
-  *bn = pick_block_n(Cout);
   a.n_tiles = Cout / *bn;
+  a.stages = ub::WGRAD_RING_BYTES / ((2 + *bn / 64) * a.blk_bytes);
+  if (a.stages > ub::WGRAD_MAX_STAGES) a.stages = ub::WGRAD_MAX_STAGES;
   if (taps == 9 && Cin == 64) {
     a.pair_taps = 1;
     a.m_tiles = 5;
@@ -390,22 +400,20 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   return UB_OK;
 }
 
-// BatchNorm(train)+ReLU backward on c.g in place (dA -> dY); d gamma / d beta are written when the pointers are given.
+// BatchNorm(train)+ReLU backward on c.g in place (dA -> dY). dbeta / dgamma are the (pre-zeroed) fp32 accumulators of
+// sum g and sum g*xhat - in the trainer they are the gradient slots of beta and gamma themselves.
 int conv_bn_backward(const TConv& c, int B, float* dgamma, float* dbeta, cudaStream_t st) {
   const size_t npix = (size_t)B * c.H * c.W;
   const int C8 = c.Cout / 8;
   const uint4* g4 = reinterpret_cast<const uint4*>(c.g);
   const uint4* y4 = reinterpret_cast<const uint4*>(c.y);
   ub::bn_relu_bwd_reduce_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
-                                                                                 C8, c.s1, c.s2);
+                                                                                 C8, dbeta, dgamma);
   UB_CUDA(cudaGetLastError());
   const size_t n8 = npix * C8;
-  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, c.s1, c.s2,
+  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, dbeta, dgamma,
                                                                   1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g));
   UB_CUDA(cudaGetLastError());
-  // d gamma = sum g * xhat, d beta = sum g
-  if (dgamma) UB_CUDA(cudaMemcpyAsync(dgamma, c.s2, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, st));
-  if (dbeta) UB_CUDA(cudaMemcpyAsync(dbeta, c.s1, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, st));
   return UB_OK;
 }
 
@@ -946,11 +954,9 @@ int unet_b200_bn_relu_bwd(void* g, const void* y, const float* stats4, int B, in
   c.invstd = s4 + C;
   c.scale = s4 + 2 * C;
   c.shift = s4 + 3 * C;
-  c.s1 = dbeta;   // the reductions accumulate straight into the outputs
-  c.s2 = dgamma;
   UB_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
   UB_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
-  return conv_bn_backward(c, B, nullptr, nullptr, st);
+  return conv_bn_backward(c, B, dgamma, dbeta, st);
 }
 
 int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, int skip_pitch, int B, int H, int W, int C,

@@ -166,7 +166,30 @@ bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict_
     is[i] = invstd[cl * 8 + i];
   }
   float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+  // four pixels per trip: eight independent 16-byte loads in flight per thread (the pass is HBM-latency bound otherwise)
+  const size_t stride = static_cast<size_t>(gridDim.x) * ppb;
+  size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl;
+  for (; p + 3 * stride < npix; p += 4 * stride) {
+    uint4 ry[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ry[u] = __ldg(y + (p + u * stride) * C8 + cl);
+      rd[u] = __ldg(dA + (p + u * stride) * C8 + cl);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float fy[8], fd[8];
+      unpack8(ry[u], fy);
+      unpack8(rd[u], fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float g = fmaf(fy[i], sc[i], sh[i]) > 0.f ? fd[i] : 0.f;
+        a1[i] += g;
+        a2[i] = fmaf(g, (fy[i] - mu[i]) * is[i], a2[i]);
+      }
+    }
+  }
+  for (; p < npix; p += stride) {
     float fy[8], fd[8];
     unpack8(__ldg(y + p * C8 + cl), fy);
     unpack8(__ldg(dA + p * C8 + cl), fd);

@@ -32,17 +32,24 @@ struct WgradArgs {
   int Cin, Cout;
   long long s_co, s_ci, s_tap;    // dW index = co*s_co + ci*s_ci + tap*s_tap (PyTorch layouts are written directly)
   int k_mmas;                     // 16-pixel MMAs per box = box rows / 16 (8 unless TB exceeds the batch)
-  int a_bytes;                    // bytes of one x / dy box (16384 unless TB exceeds the batch)
+  int a_bytes;                    // bytes one x / dy box load delivers (box rows * 128; fewer rows when TB exceeds the batch)
+  int blk_bytes;                  // shared-memory pitch of one 64-channel box (full box rows * 128) = LBO of the descriptors
+  int stages;                     // operand ring depth chosen by the host (<= WGRAD_MAX_STAGES)
   float* dw;                      // fp32 gradient, accumulated atomically
 };
+
+constexpr int WGRAD_MAX_STAGES = 8;
+constexpr int WGRAD_RING_BYTES = 192 * 1024;
 
 template <int BLOCK_N>
 struct WgradCfg {
   static constexpr int NB = BLOCK_N / 64;
-  static constexpr int STAGE_BYTES = (2 + NB) * 16384;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
-  static_assert(STAGES >= 2, "need at least two stages");
+  static constexpr int SMEM_BYTES = WGRAD_RING_BYTES + 256 + 1024;
+  // ring depth for a given box size (host + device)
+  __host__ __device__ static constexpr int stages_for(int blk_bytes) {
+    const int s = WGRAD_RING_BYTES / ((2 + NB) * blk_bytes);
+    return s > WGRAD_MAX_STAGES ? WGRAD_MAX_STAGES : s;
+  }
 };
 
 // MN-major, 128B-swizzle shared-memory descriptor: LBO = bytes between 64-wide MN blocks, SBO = bytes between 8-row K groups.
@@ -62,17 +69,19 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
                   const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
                   const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const WgradArgs a) {
   using Cfg = WgradCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
   constexpr int NB = Cfg::NB;
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  const int STAGES = a.stages;
+  const int BLK = a.blk_bytes;
+  const int STAGE_BYTES = (2 + NB) * BLK;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WGRAD_RING_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* done = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* empty = bars + WGRAD_MAX_STAGES;
+  uint64_t* done = bars + 2 * WGRAD_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WGRAD_MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,8 +126,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         const int h0 = ((kt / a.tiles_w) % a.tiles_h) * a.TH;
         const int b0 = (kt / (a.tiles_w * a.tiles_h)) * a.TB;
         mbar_wait_parked(&empty[stage], phase ^ 1);
-        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sB = sA + 2 * 16384;
+        uint8_t* sA = smem + stage * STAGE_BYTES;
+        uint8_t* sB = sA + 2 * BLK;
         mbar_expect_tx(&full[stage], (2 + NB) * a.a_bytes);
         // x operand: two 64-row blocks
 #pragma unroll
@@ -135,9 +144,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             dx = tap % 3 - 1;
           }
           if (c < a.c_split) {
-            tma_load_4d(sA + hb * 16384, &tmX0, &full[stage], c, w0 + dx, h0 + dy, b0);
+            tma_load_4d(sA + hb * BLK, &tmX0, &full[stage], c, w0 + dx, h0 + dy, b0);
           } else {
-            tma_load_4d(sA + hb * 16384, &tmX1, &full[stage], c - a.c_split, w0 + dx, h0 + dy, b0);
+            tma_load_4d(sA + hb * BLK, &tmX1, &full[stage], c - a.c_split, w0 + dx, h0 + dy, b0);
           }
         }
         // dy operand: NB 64-channel blocks (ConvT: through the quad view of this tile's tap)
@@ -145,7 +154,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         if (a.taps == 4) md = tap_o == 0 ? &tmD0 : tap_o == 1 ? &tmD1 : tap_o == 2 ? &tmD2 : &tmD3;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          tma_load_4d(sB + nb * 16384, md, &full[stage], n_tile * BLOCK_N + nb * 64, w0, h0, b0);
+          tma_load_4d(sB + nb * BLK, md, &full[stage], n_tile * BLOCK_N + nb * 64, w0, h0, b0);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -158,15 +167,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     if (elect_one()) {
       // both operands MN-major: bits 15 / 16 of the instruction descriptor
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N) | (1u << 15) | (1u << 16);
-      const uint64_t d_hi = make_sw128_mnmajor_desc(0, 16384, 1024);
+      const uint64_t d_hi = make_sw128_mnmajor_desc(0, BLK, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = k_lo; kt < k_hi; ++kt) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
         const uint64_t da = d_hi + (sA >> 4);
-        const uint64_t db = d_hi + ((sA + 2 * 16384) >> 4);
+        const uint64_t db = d_hi + ((sA + 2 * BLK) >> 4);
 #pragma unroll
         for (int j = 0; j < a.k_mmas; ++j) {
           // 16 pixel rows per MMA = two 8-row groups = 2048 B
