@@ -181,6 +181,11 @@ int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits_dev, con
 int unet_b200_bce_dice_loss(const float* logits_dev, const float* target_dev, size_t n, float pos_weight, float bce_weight,
                             float dice_weight, float smooth, double* scratch4_dev, float* losses3_dev, float* dlogits_dev,
                             void* stream);
+/* validate() metrics (README.md:2086-2120) in one pass: out4_dev = {total loss, bce, dice loss, compute_dice(sigmoid(z) >
+ * threshold, target)}; scratch6_dev: 6 doubles. */
+int unet_b200_validation_metrics(const float* logits_dev, const float* target_dev, size_t n, float pos_weight,
+                                 float bce_weight, float dice_weight, float smooth, float threshold, double* scratch6_dev,
+                                 float* out4_dev, void* stream);
 /* torch.optim.AdamW step (README.md:2173-2174) on flat fp32 arrays; grads are multiplied by grad_scale first
  * (1/world_size after a gradient all-reduce(sum)); step counts from 1. */
 int unet_b200_adamw_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, size_t n,

@@ -14,5 +14,7 @@ from .ops import (  # noqa: F401
 from .unet import UNet  # noqa: F401
 from .executor import B200_model_container, B200LaneInference  # noqa: F401
 from .training import FusedTrainStep, bce_dice_loss  # noqa: F401
+from .loop import cosine_warm_restarts_lr, fit, train_one_epoch, validate, validation_metrics  # noqa: F401
 
-__all__ = ["UNet", "B200_model_container", "B200LaneInference", "FusedTrainStep", "bce_dice_loss"]
+__all__ = ["UNet", "B200_model_container", "B200LaneInference", "FusedTrainStep", "bce_dice_loss", "fit", "train_one_epoch",
+           "validate", "validation_metrics", "cosine_warm_restarts_lr"]

@@ -62,6 +62,7 @@ _SIGS = {
     "unet_b200_train_forward": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), f32, f32, vp, vp]),
     "unet_b200_train_backward": (i32, [vp, vp, vp, vp, vp]),
     "unet_b200_bce_dice_loss": (i32, [vp, vp, sz, f32, f32, f32, f32, vp, vp, vp, vp]),
+    "unet_b200_validation_metrics": (i32, [vp, vp, sz, f32, f32, f32, f32, f32, vp, vp, vp]),
     "unet_b200_adamw_step": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
     "unet_b200_adamw_step_dev": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]),
     "unet_b200_pack_conv3x3_dgrad": (i32, [vp, i32, i32, vp, vp]),

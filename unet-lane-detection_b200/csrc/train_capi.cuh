@@ -771,6 +771,20 @@ int unet_b200_bce_dice_loss(const float* logits, const float* target, size_t n, 
   return UB_OK;
 }
 
+int unet_b200_validation_metrics(const float* logits, const float* target, size_t n, float pos_weight, float bce_weight,
+                                 float dice_weight, float smooth, float threshold, double* scratch6, float* out4, void* stream) {
+  if (logits == nullptr || target == nullptr || scratch6 == nullptr || out4 == nullptr) return fail(UB_ERR_ARG, "null argument");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UB_CUDA(cudaMemsetAsync(scratch6, 0, 6 * sizeof(double), st));
+  ub::val_metrics_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, threshold, scratch6);
+  UB_CUDA(cudaGetLastError());
+  ub::val_metrics_finalize_kernel<<<1, 1, 0, st>>>(scratch6, n, bce_weight, dice_weight, smooth, out4);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
 int unet_b200_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
   if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return fail(UB_ERR_ARG, "null argument");

@@ -395,6 +395,46 @@ bce_dice_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t,
   }
 }
 
+// Validation metrics (README.md:2086-2120 validate + compute_dice) in one pass over the logits:
+// sums[0..5] += {sum bce_i, sum sigma*t, sum sigma, sum t, sum [sigma > thr]*t, sum [sigma > thr]}
+__global__ void __launch_bounds__(256)
+val_metrics_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight, float thr,
+                          double* __restrict__ sums) {
+  __shared__ double red[6][256];
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float x = z[i], y = t[i];
+    const float lw = 1.f + (pos_weight - 1.f) * y;
+    s[0] += (1.f - y) * x + lw * (log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f));
+    const float sg = 1.f / (1.f + expf(-x));
+    s[1] += sg * y;
+    s[2] += sg;
+    s[3] += y;
+    const float pm = sg > thr ? 1.f : 0.f;  // strict '>' as torch.sigmoid(outputs) > 0.5 (README.md:2103)
+    s[4] += pm * y;
+    s[5] += pm;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) red[k][threadIdx.x] = s[k];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double a = 0;
+    for (int j = 0; j < 256; ++j) a += red[threadIdx.x][j];
+    atomicAdd(sums + threadIdx.x, a);
+  }
+}
+// out[0..3] = {total loss, bce, dice loss, dice score of the thresholded prediction}
+__global__ void val_metrics_finalize_kernel(const double* __restrict__ sums, size_t n, float bce_w, float dice_w, float smooth,
+                                            float* __restrict__ out) {
+  const double bce = sums[0] / static_cast<double>(n);
+  const double dice = 1.0 - (2.0 * sums[1] + smooth) / (sums[2] + sums[3] + smooth);
+  out[0] = static_cast<float>(bce_w * bce + dice_w * dice);
+  out[1] = static_cast<float>(bce);
+  out[2] = static_cast<float>(dice);
+  out[3] = static_cast<float>((2.0 * sums[4] + smooth) / (sums[5] + sums[3] + smooth));
+}
+
 // pass 2: losses[0..2] = {total, bce, dice};  dz = d total / d z
 __global__ void __launch_bounds__(256)
 bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight, float bce_w,

@@ -272,3 +272,42 @@ class FusedTrainStep:
             self.last_grads = grads
         model._b200_epoch += 1  # kernels wrote parameters / BN buffers behind autograd's back: repack before the next eval
         return losses
+
+    # ------------------------------------------------------------------ optimizer state in torch.optim.AdamW's format
+    def state_dict(self):
+        """Same structure torch.optim.AdamW.state_dict() produces for optimizer = AdamW(model.parameters(), ...)
+        (the 'optimizer_state_dict' of README.md:2208-2213), so either optimizer can resume from the other's file."""
+        params = list(self.model.parameters())
+        state = {}
+        if self.exp_avg is not None and self.step_count > 0:
+            off = 0
+            for i, p in enumerate(params):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+                off += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": True, "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = group["lr"], tuple(group["betas"]), group["eps"], group["weight_decay"]
+        params = list(self.model.parameters())
+        flat = self._prepare(params[0].device)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count = 0
+        off = 0
+        for i, p in enumerate(params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1).to(flat.device))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(flat.device))
+                self.step_count = int(st["step"])
+            off += n
+        self.step_dev.fill_(self.step_count)
+        self._graphs.clear()
