@@ -108,6 +108,20 @@ int unet_b200_preprocess_u8(const uint8_t* src_dev, int batch, int Hs, int Ws, s
                             int H, int W, int swap_rb, const float* mean3, const float* std3, void* y_nhwc4_dev,
                             uint8_t* resized_u8_dev, void* stream);
 
+/* ---- IPM front end of the ROS node fused into the preprocess (src/unet_ros_node.py:297-313) --------------------- *
+ * cv2.warpPerspective(bgr, M, (Ww, Hw)) -> BGR2RGB (swap_rb) -> cv2.resize to HxW -> normalise -> NHWC4 bf16, bit-exact
+ * with cv2's uint8 arithmetic; the Hw x Ww bird's-eye image is not materialised unless warped_u8_dev is given
+ * ([batch][Hw][Ww][3], source channel order). m_inv9: HOST, row-major 3x3 double INVERSE map (dst -> src), i.e.
+ * cv::invert of the matrix the reference passes to warpPerspective. y_nhwc4_dev may be NULL when only the warp is wanted. */
+int unet_b200_preprocess_warp_u8(const uint8_t* src_dev, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride,
+                                 const double* m_inv9, int Hw, int Ww, int H, int W, int swap_rb, const float* mean3,
+                                 const float* std3, void* y_nhwc4_dev, uint8_t* resized_u8_dev, uint8_t* warped_u8_dev,
+                                 void* stream);
+/* Mask back to the caller's resolution (src/unet.py:70): dst [batch][Hd][Wd] = cv2.resize(src [batch][Hs][Ws]) for
+ * single-channel uint8, INTER_LINEAR, bit-exact (including cv2's border-row rule and its 2x2-decimation special case). */
+int unet_b200_resize_gray_u8(const uint8_t* src_dev, int batch, int Hs, int Ws, uint8_t* dst_dev, int Hd, int Wd,
+                             void* stream);
+
 /* ---- executor entry point (RKNN_model_container.run, src/py_utils/rknn_executor.py:26-38) -------- *
  * HOST uint8 [batch][Hs][Ws][3] frames in, HOST outputs out (any may be NULL). Copies H2D, runs
  * preprocess + forward on `stream`, copies D2H and synchronises the stream before returning.

@@ -118,34 +118,111 @@ def compute_dice_oracle(pred_mask: torch.Tensor, target: torch.Tensor, smooth: f
 # --------------------------------------------------------------------------------------------------
 # Pre / post-processing: restates src/unet.py:24-72.
 # --------------------------------------------------------------------------------------------------
-def _linear_taps(dn: int, sn: int):
-    """cv2 INTER_LINEAR tap positions and 11-bit fixed-point weights for one axis (uint8 path)."""
+def _linear_taps(dn: int, sn: int, clamp_weights: bool = True):
+    """cv2 INTER_LINEAR tap positions and 11-bit fixed-point weights for one axis (uint8 path, resize.cpp).
+    Horizontal axis (clamp_weights=True): a tap that falls outside the row is folded into its neighbour (fx = 0).
+    Vertical axis (clamp_weights=False): cv2 keeps the weights and only clips the ROW INDICES, so at the top / bottom
+    border both taps read the same row with weights (1-fy, fy) - two truncations instead of one."""
     scale = sn / dn
     f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int32)
     f = f - s
-    lo = s < 0
-    f[lo], s[lo] = 0.0, 0
-    hi = s >= sn - 1
-    f[hi], s[hi] = 0.0, sn - 1
+    if clamp_weights:
+        lo = s < 0
+        f[lo], s[lo] = 0.0, 0
+        hi = s >= sn - 1
+        f[hi], s[hi] = 0.0, sn - 1
     w1 = np.rint(f * np.float32(2048)).astype(np.int32)
     w0 = np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int32)
-    return s, np.minimum(s + 1, sn - 1), w0, w1
+    return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), w0, w1
 
 
 def resize_bilinear_u8(img: np.ndarray, dh: int, dw: int) -> np.ndarray:
-    """Bit-exact numpy model of cv2.resize(img, (dw, dh)) for uint8 HxWxC, default INTER_LINEAR
-    (src/unet.py:33). Verified against cv2 4.13 for down-scales; see tests/golden/make_golden.py."""
+    """Bit-exact numpy model of cv2.resize(img, (dw, dh)) for uint8 HxW[xC], default INTER_LINEAR (src/unet.py:33, :70),
+    verified against cv2 4.13 for down- AND up-scaling (tests/golden/make_golden.py). Special cases of cv::resize:
+    equal sizes copy; an exact 2x2 decimation is computed as INTER_AREA ((a+b+c+d+2)>>2)."""
     if img.ndim == 2:
         return resize_bilinear_u8(img[:, :, None], dh, dw)[:, :, 0]
     sh, sw = img.shape[:2]
-    x0, x1, ax0, ax1 = _linear_taps(dw, sw)
-    y0, y1, by0, by1 = _linear_taps(dh, sh)
+    if (sh, sw) == (dh, dw):
+        return img.copy()
     s = img.astype(np.int32)
+    if sh == 2 * dh and sw == 2 * dw:
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    x0, x1, ax0, ax1 = _linear_taps(dw, sw, True)
+    y0, y1, by0, by1 = _linear_taps(dh, sh, False)
     horiz = s[:, x0, :] * ax0[None, :, None] + s[:, x1, :] * ax1[None, :, None]
     top, bot = horiz[y0], horiz[y1]
     out = (((by0[:, None, None] * (top >> 4)) >> 16) + ((by1[:, None, None] * (bot >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def invert3x3(m: np.ndarray) -> np.ndarray:
+    """cv::invert of a 3x3 double matrix (closed form with the reciprocal determinant) - the inverse map that
+    cv2.warpPerspective builds from its argument. Bit-equal to cv2.invert (make_golden.py)."""
+    S = np.asarray(m, dtype=np.float64)
+    det = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0])
+           + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    d = 1.0 / det
+    t = np.empty(9, dtype=np.float64)
+    t[0] = (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d
+    t[1] = (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d
+    t[2] = (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d
+    t[3] = (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d
+    t[4] = (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d
+    t[5] = (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d
+    t[6] = (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d
+    t[7] = (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d
+    t[8] = (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d
+    return t.reshape(3, 3)
+
+
+def warp_perspective_u8(src: np.ndarray, m_inv: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """Bit-exact numpy model of cv2.warpPerspective(src, M, (dw, dh)) (src/unet_ros_node.py:300-301: INTER_LINEAR,
+    BORDER_CONSTANT 0) given m_inv = invert3x3(M). Follows imgwarp.cpp: destination coordinates are evaluated in double
+    per 64-pixel column block (X0 + M0*x1)*W with W = 32/(W0 + M6*x1), rounded to 1/32 pixel; the four taps are blended
+    with 15-bit integer weights (32-ax)(32-ay)*32 ... and rounded with +2^14 >> 15; taps outside the image are 0."""
+    Hs, Ws = src.shape[:2]
+    m = np.asarray(m_inv, dtype=np.float64).reshape(-1)
+    yd = np.arange(dh, dtype=np.float64)[:, None]
+    xd = np.arange(dw)[None, :]
+    xb = (xd // 64) * 64
+    x1 = (xd - xb).astype(np.float64)
+    xb = xb.astype(np.float64)
+    X0 = m[0] * xb + m[1] * yd + m[2]
+    Y0 = m[3] * xb + m[4] * yd + m[5]
+    W0 = m[6] * xb + m[7] * yd + m[8]
+    W = W0 + m[6] * x1
+    with np.errstate(divide="ignore"):
+        W = np.where(W != 0, 32.0 / W, 0.0)
+    fX = np.maximum(-2147483648.0, np.minimum(2147483647.0, (X0 + m[0] * x1) * W))
+    fY = np.maximum(-2147483648.0, np.minimum(2147483647.0, (Y0 + m[3] * x1) * W))
+    X = np.rint(fX).astype(np.int64)
+    Y = np.rint(fY).astype(np.int64)
+    sx = np.clip(X >> 5, -32768, 32767)
+    sy = np.clip(Y >> 5, -32768, 32767)
+    ax, ay = X & 31, Y & 31
+    s = src.astype(np.int64)
+    if s.ndim == 2:
+        s = s[:, :, None]
+
+    def tap(yy, xx):
+        inside = (xx >= 0) & (xx < Ws) & (yy >= 0) & (yy < Hs)
+        return s[np.clip(yy, 0, Hs - 1), np.clip(xx, 0, Ws - 1)] * inside[..., None]
+
+    acc = (tap(sy, sx) * ((32 - ax) * (32 - ay) * 32)[..., None] + tap(sy, sx + 1) * (ax * (32 - ay) * 32)[..., None]
+           + tap(sy + 1, sx) * ((32 - ax) * ay * 32)[..., None] + tap(sy + 1, sx + 1) * (ax * ay * 32)[..., None])
+    out = np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+    return out.reshape(dh, dw, *src.shape[2:])
+
+
+def ipm_preprocess_oracle(bgr_u8: np.ndarray, m_inv: np.ndarray, warp_size=(1055, 685), size=(224, 224)):
+    """src/unet_ros_node.py:297-313 up to the network input: warpPerspective to warp_size (w, h) -> resize to the same
+    size (a copy) -> BGR2RGB -> RKNNLaneInference.preprocess_image (resize to the model input, src/unet.py:24-42).
+    Returns (uint8 NHWC [1,H,W,3] RGB, (h, w) of the warped image = the size the mask is resized back to)."""
+    warped = warp_perspective_u8(bgr_u8, m_inv, warp_size[0], warp_size[1])
+    rgb = np.ascontiguousarray(warped[:, :, ::-1])
+    return preprocess_oracle(rgb, size)
 
 
 def preprocess_oracle(image_u8: np.ndarray, size=(224, 224), swap_rb: bool = False):

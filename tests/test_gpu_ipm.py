@@ -1,0 +1,109 @@
+"""GPU (B200): the camera-side steps around the network - IPM warp fused into the preprocess and
+the mask up-resize - bit-exact against cv2's own outputs (tests/golden/ipm.npz) and against the oracle on full images."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import unet_lane_detection_b200 as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return np.load(os.path.join(golden_dir, "ipm.npz")), mod
+
+
+def test_warp_perspective_bit_exact(U, G):
+    g, mod = G
+    syn = mod.ipm_synthetic_frame(77)
+    frames = torch.from_numpy(np.stack([syn, syn[::-1].copy()])).cuda()
+    got = U.ops.warp_perspective_u8(frames, g["M"], (1055, 685)).cpu().numpy()
+    assert np.array_equal(got[0][300:364, 400:528], g["syn_warp_crop"])            # cv2's own pixels
+    assert int(got[0].astype(np.int64).sum()) == int(g["syn_warp_sum"])
+    assert np.array_equal(got[1], O.warp_perspective_u8(syn[::-1].copy(), g["Minv"], 1055, 685))
+    # a different target size and a matrix whose denominator crosses zero inside the image (W = 0 -> coordinates 0)
+    m2 = np.array([[1.1, 0.2, -30.0], [0.05, 0.9, 12.0], [0.0, -0.004, 1.0]])
+    got2 = U.ops.warp_perspective_u8(frames[:1], m2, (333, 257)).cpu().numpy()[0]
+    assert np.array_equal(got2, O.warp_perspective_u8(syn, O.invert3x3(m2), 333, 257))
+
+
+def test_fused_ipm_preprocess_bit_exact(U, G):
+    g, mod = G
+    syn = mod.ipm_synthetic_frame(77)
+    x4, r = U.ops.preprocess_warp_u8(torch.from_numpy(syn[None]).cuda(), g["M"], (1055, 685), (224, 224), swap_rb=True,
+                                     return_resized=True)
+    assert np.array_equal(r[0].cpu().numpy(), g["syn_resized"])                    # == cv2 pipeline of the ROS node
+    want = torch.from_numpy(O.normalize_oracle(g["syn_resized"][None])).permute(0, 2, 3, 1)
+    assert (x4[..., :3].float().cpu() - want).abs().max().item() <= 2e-2           # one bf16 rounding of |x| <= 2.7
+    assert (x4[..., 3] == 0).all()
+    half = torch.from_numpy(g["real_src_half"][None].copy()).cuda()                # the reference's camera frame (decimated)
+    _, r2 = U.ops.preprocess_warp_u8(half, g["M"], (1055, 685), (224, 224), swap_rb=True, return_resized=True)
+    assert np.array_equal(r2[0].cpu().numpy(), g["real_half_resized"])
+    # 2x2-decimation special case of cv::resize between the warped image and the network input
+    _, r3 = U.ops.preprocess_warp_u8(half, g["M"], (448, 448), (224, 224), swap_rb=False, return_resized=True)
+    w = O.warp_perspective_u8(g["real_src_half"], g["Minv"], 448, 448)
+    assert np.array_equal(r3[0].cpu().numpy(), O.resize_bilinear_u8(w, 224, 224))
+
+
+def test_mask_resize_bit_exact(U, G):
+    g, _ = G
+    m = torch.from_numpy(g["mask224"][None].copy()).cuda()
+    assert np.array_equal(U.ops.resize_gray_u8(m, (685, 1055))[0].cpu().numpy(), g["mask_up"])
+    for tag in ("up2x", "area2x", "same", "ragged"):
+        src, dst = g[f"gray_{tag}_src"], g[f"gray_{tag}_dst"]
+        got = U.ops.resize_gray_u8(torch.from_numpy(src[None].copy()).cuda(), dst.shape)
+        assert np.array_equal(got[0].cpu().numpy(), dst), tag
+    rnd = np.random.default_rng(3).integers(0, 256, (3, 224, 224), dtype=np.uint8)
+    got = U.ops.resize_gray_u8(torch.from_numpy(rnd).cuda(), (480, 640)).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], O.resize_bilinear_u8(rnd[i], 480, 640))
+
+
+def test_preprocess_upscale_and_decimation_now_exact(U):
+    """The plain preprocess (src/unet.py:33) for sources SMALLER than the model input and for the 2x2-decimation case."""
+    rng = np.random.default_rng(8)
+    for hs, ws in ((100, 130), (448, 448), (224, 224), (225, 223)):
+        f = rng.integers(0, 256, (2, hs, ws, 3), dtype=np.uint8)
+        _, r = U.ops.preprocess_u8(torch.from_numpy(f).cuda(), (224, 224), return_resized=True)
+        for i in range(2):
+            assert np.array_equal(r[i].cpu().numpy(), O.resize_bilinear_u8(f[i], 224, 224)), (hs, ws)
+
+
+def test_lane_pipeline_matches_reference_callback(U, G, tmp_path):
+    """B200LanePipeline.process == the steps of LaneSegmentationROS.image_callback (src/unet_ros_node.py:297-321) with the
+    oracle network in the middle: masks agree >= 99.9 % at the bird's-eye resolution."""
+    g, mod = G
+    torch.manual_seed(0)
+    ref = O.UNetOracle(3, 1, [64, 128, 256, 512]).eval()
+    O.randomize_bn_(ref, seed=1)
+    O.scale_head_(ref, 40.0)
+    path = tmp_path / "best_model.pth"
+    torch.save({"epoch": 1, "model_state_dict": ref.state_dict()}, path)
+    pipe = U.B200LanePipeline(str(path), g["M"], threshold=0.5)
+    frames = np.stack([mod.ipm_synthetic_frame(77), mod.ipm_synthetic_frame(78)])
+    masks = pipe.process(frames)
+    assert masks.shape == (2, 685, 1055) and masks.dtype == np.uint8
+    for i in range(2):
+        x, shape = O.ipm_preprocess_oracle(frames[i], g["Minv"])
+        with torch.no_grad():
+            z = ref(torch.from_numpy(O.normalize_oracle(x)))
+        want = O.postprocess_oracle([z.numpy()], shape, 0.5)
+        assert (masks[i] == want).mean() >= 0.999
+    single = pipe.process(frames[0])
+    assert np.array_equal(single, masks[0])
+    pipe.release()

@@ -101,3 +101,34 @@ def test_bf16_emulation_is_close_to_fp32():
         y = m(x)
     ye = O.forward_bf16_emulated(m, x)
     assert (y - ye).abs().max().item() < 0.05 * max(1.0, y.abs().max().item())
+
+
+def _golden_mod(golden_dir):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_ipm_front_end_matches_cv2_goldens(golden_dir):
+    """src/unet_ros_node.py:297-313: warpPerspective -> BGR2RGB -> resize, against outputs of cv2 itself (ipm.npz)."""
+    g = np.load(os.path.join(golden_dir, "ipm.npz"))
+    assert np.array_equal(O.invert3x3(g["M"]), g["Minv"])
+    syn = _golden_mod(golden_dir).ipm_synthetic_frame(77)
+    warped = O.warp_perspective_u8(syn, g["Minv"], 1055, 685)
+    assert np.array_equal(warped[300:364, 400:528], g["syn_warp_crop"])
+    assert int(warped.astype(np.int64).sum()) == int(g["syn_warp_sum"])
+    got, shape = O.ipm_preprocess_oracle(syn, g["Minv"])
+    assert shape == (685, 1055) and np.array_equal(got[0], g["syn_resized"])
+    got, _ = O.ipm_preprocess_oracle(g["real_src_half"], g["Minv"])
+    assert np.array_equal(got[0], g["real_half_resized"])
+
+
+def test_resize_up_and_special_cases_match_cv2_goldens(golden_dir):
+    """src/unet.py:70 mask up-resize and the shapes cv::resize special-cases (border rows, 2x2 decimation, copy)."""
+    g = np.load(os.path.join(golden_dir, "ipm.npz"))
+    assert np.array_equal(O.resize_bilinear_u8(g["mask224"], 685, 1055), g["mask_up"])
+    for tag in ("up2x", "area2x", "same", "ragged"):
+        dst = g[f"gray_{tag}_dst"]
+        assert np.array_equal(O.resize_bilinear_u8(g[f"gray_{tag}_src"], dst.shape[0], dst.shape[1]), dst), tag

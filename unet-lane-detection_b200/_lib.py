@@ -40,6 +40,9 @@ _SIGS = {
     "unet_b200_set_option": (i32, [C.c_char_p, i32]),
     "unet_b200_nchw_to_nhwc4": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_preprocess_u8": (i32, [vp, i32, i32, i32, sz, sz, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, vp]),
+    "unet_b200_preprocess_warp_u8": (i32, [vp, i32, i32, i32, sz, sz, C.POINTER(C.c_double), i32, i32, i32, i32, i32,
+                                           C.POINTER(f32), C.POINTER(f32), vp, vp, vp, vp]),
+    "unet_b200_resize_gray_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, vp]),
     "unet_b200_infer_staging_bytes": (sz, [vp, i32, i32]),
     "unet_b200_infer_u8_host": (i32, [vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), f32, vp, vp, vp, vp]),
     "unet_b200_conv3x3": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),

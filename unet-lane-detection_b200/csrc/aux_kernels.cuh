@@ -105,17 +105,27 @@ struct PreArgs {
   uint8_t* dst_u8;     // optional [B,H,W,3] resized uint8 (pre-normalisation), for parity tests
 };
 
-__device__ __forceinline__ void resize_coef(int d, int dn, int sn, int& s0, int& s1, int& a0, int& a1) {
+// cv2 INTER_LINEAR (uint8) taps of one axis. Horizontal axis (clamp_weights): a tap outside the row is folded into its
+// neighbour (fx = 0). Vertical axis: cv2 keeps the weights and only clips the ROW INDICES (resize.cpp), so border rows
+// blend the same row twice with two truncations - modelled exactly.
+__device__ __forceinline__ void resize_coef(int d, int dn, int sn, bool clamp_weights, int& s0, int& s1, int& a0, int& a1) {
   const double scale = static_cast<double>(sn) / dn;
   float f = static_cast<float>((d + 0.5) * scale - 0.5);
   int s = static_cast<int>(floorf(f));
   f -= s;
-  if (s < 0) { f = 0.f; s = 0; }
-  if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  if (clamp_weights) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+  }
   a1 = __float2int_rn(f * 2048.f);
   a0 = __float2int_rn((1.f - f) * 2048.f);
-  s0 = s;
-  s1 = min(s + 1, sn - 1);
+  s0 = min(max(s, 0), sn - 1);
+  s1 = min(max(s + 1, 0), sn - 1);
+}
+// Vertical + horizontal blend of the four (already horizontally weighted) sums, as VResizeLinear does.
+__device__ __forceinline__ int resize_blend(int h0, int h1, int by0, int by1) {
+  const int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  return min(max(v, 0), 255);
 }
 
 __global__ void preprocess_u8_kernel(const PreArgs a) {
@@ -123,7 +133,14 @@ __global__ void preprocess_u8_kernel(const PreArgs a) {
   const int y = blockIdx.x % a.H;
   const int b = blockIdx.x / a.H;
   int sy0, sy1, by0, by1;
-  resize_coef(y, a.H, a.Hs, sy0, sy1, by0, by1);
+  resize_coef(y, a.H, a.Hs, false, sy0, sy1, by0, by1);
+  // cv::resize special cases: equal sizes copy (the taps below reduce to that), and an exact 2x2 decimation is computed
+  // as INTER_AREA = (a + b + c + d + 2) >> 2
+  const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
+  if (area2) {
+    sy0 = 2 * y;
+    sy1 = 2 * y + 1;
+  }
   const int row_bytes = a.Ws * 3;
   const uint8_t* r0 = a.src + b * a.frame_stride + sy0 * a.pitch;
   const uint8_t* r1 = a.src + b * a.frame_stride + sy1 * a.pitch;
@@ -134,14 +151,18 @@ __global__ void preprocess_u8_kernel(const PreArgs a) {
   __syncthreads();
   for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
     int sx0, sx1, ax0, ax1;
-    resize_coef(x, a.W, a.Ws, sx0, sx1, ax0, ax1);
+    resize_coef(x, a.W, a.Ws, true, sx0, sx1, ax0, ax1);
     int px[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int h0 = rows[sx0 * 3 + c] * ax0 + rows[sx1 * 3 + c] * ax1;
-      const int h1 = rows[row_bytes + sx0 * 3 + c] * ax0 + rows[row_bytes + sx1 * 3 + c] * ax1;
-      int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      px[c] = min(max(v, 0), 255);
+      if (area2) {
+        px[c] = (rows[(2 * x) * 3 + c] + rows[(2 * x + 1) * 3 + c] + rows[row_bytes + (2 * x) * 3 + c] +
+                 rows[row_bytes + (2 * x + 1) * 3 + c] + 2) >> 2;
+      } else {
+        const int h0 = rows[sx0 * 3 + c] * ax0 + rows[sx1 * 3 + c] * ax1;
+        const int h1 = rows[row_bytes + sx0 * 3 + c] * ax0 + rows[row_bytes + sx1 * 3 + c] * ax1;
+        px[c] = resize_blend(h0, h1, by0, by1);
+      }
     }
     if (a.swap_rb) { const int t = px[0]; px[0] = px[2]; px[2] = t; }
     const size_t o = (static_cast<size_t>(b) * a.H + y) * a.W + x;
@@ -154,6 +175,174 @@ __global__ void preprocess_u8_kernel(const PreArgs a) {
     const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
     const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
     a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IPM front end of the ROS node fused into the preprocess (src/unet_ros_node.py:297-313 + src/unet.py:24-42):
+//   cv2.warpPerspective(bgr, M, (Ww, Hw))  ->  [cv2.resize to the same size = copy]  ->  BGR2RGB  ->
+//   cv2.resize(rgb, (W, H))  ->  (x - mean)/std  ->  NHWC4 bf16
+// The Hw x Ww bird's-eye image is never materialised: each network-input pixel needs 2x2 warped pixels, each of which
+// is evaluated on the fly from 2x2 source pixels with cv2's exact arithmetic (imgwarp.cpp): destination coordinates in
+// double per 64-column block, rounded to 1/32 pixel, 15-bit integer blend weights, +2^14 >> 15, BORDER_CONSTANT 0.
+// m = inverse map (dst -> src) as cv::invert produces it from the matrix handed to warpPerspective.
+// ------------------------------------------------------------------------------------------------
+struct WarpPreArgs {
+  const uint8_t* src;   // [B, Hs, Ws, 3] BGR, row pitch in bytes
+  size_t pitch, frame_stride;
+  int B, Hs, Ws;        // camera frame
+  int Hw, Ww;           // warped (bird's-eye) image
+  int H, W;             // network input
+  int swap_rb;
+  double m[9];
+  float mean[3], inv_std[3];
+  uint2* dst;           // [B,H,W] x (4 bf16)
+  uint8_t* dst_u8;      // optional [B,H,W,3] resized uint8 frame (after the channel swap)
+};
+
+__device__ __forceinline__ void warp_pixel_u8(const uint8_t* __restrict__ frame, size_t pitch, int Hs, int Ws,
+                                              const double* __restrict__ m, int xd, int yd, int (&out)[3]) {
+  const int xb = (xd >> 6) << 6;
+  const double x1 = static_cast<double>(xd - xb), xbd = static_cast<double>(xb), ydd = static_cast<double>(yd);
+  // explicit round-to-nearest mul/add: no FMA contraction, the roundings must be cv2's
+  const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xbd), __dmul_rn(m[1], ydd)), m[2]);
+  const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xbd), __dmul_rn(m[4], ydd)), m[5]);
+  const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xbd), __dmul_rn(m[7], ydd)), m[8]);
+  double Wd = __dadd_rn(W0, __dmul_rn(m[6], x1));
+  Wd = (Wd != 0.0) ? __ddiv_rn(32.0, Wd) : 0.0;
+  const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], x1)), Wd)));
+  const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], x1)), Wd)));
+  const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+  const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+  const int ax = X & 31, ay = Y & 31;
+  const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+  const bool x0in = sx >= 0 && sx < Ws, x1in = sx + 1 >= 0 && sx + 1 < Ws;
+  const bool y0in = sy >= 0 && sy < Hs, y1in = sy + 1 >= 0 && sy + 1 < Hs;
+  const uint8_t* r0 = frame + static_cast<size_t>(y0in ? sy : 0) * pitch;
+  const uint8_t* r1 = frame + static_cast<size_t>(y1in ? sy + 1 : 0) * pitch;
+  const int c0 = (x0in ? sx : 0) * 3, c1 = (x1in ? sx + 1 : 0) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v00 = (y0in && x0in) ? __ldg(r0 + c0 + c) : 0;
+    const int v01 = (y0in && x1in) ? __ldg(r0 + c1 + c) : 0;
+    const int v10 = (y1in && x0in) ? __ldg(r1 + c0 + c) : 0;
+    const int v11 = (y1in && x1in) ? __ldg(r1 + c1 + c) : 0;
+    const int acc = v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11;
+    out[c] = min(max((acc + (1 << 14)) >> 15, 0), 255);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_preprocess_u8_kernel(const WarpPreArgs a) {
+  const size_t total = static_cast<size_t>(a.B) * a.H * a.W;
+  const bool area2 = (a.Hw == 2 * a.H) && (a.Ww == 2 * a.W);
+  double m[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = a.m[k];
+  for (size_t o = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; o < total;
+       o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(o % a.W);
+    const int y = static_cast<int>((o / a.W) % a.H);
+    const int b = static_cast<int>(o / (static_cast<size_t>(a.W) * a.H));
+    const uint8_t* frame = a.src + b * a.frame_stride;
+    int sy0, sy1, by0, by1, sx0, sx1, ax0, ax1;
+    resize_coef(y, a.H, a.Hw, false, sy0, sy1, by0, by1);
+    resize_coef(x, a.W, a.Ww, true, sx0, sx1, ax0, ax1);
+    if (area2) {
+      sy0 = 2 * y;
+      sy1 = 2 * y + 1;
+      sx0 = 2 * x;
+      sx1 = 2 * x + 1;
+    }
+    int p00[3], p01[3], p10[3], p11[3], px[3];
+    warp_pixel_u8(frame, a.pitch, a.Hs, a.Ws, m, sx0, sy0, p00);
+    warp_pixel_u8(frame, a.pitch, a.Hs, a.Ws, m, sx1, sy0, p01);
+    warp_pixel_u8(frame, a.pitch, a.Hs, a.Ws, m, sx0, sy1, p10);
+    warp_pixel_u8(frame, a.pitch, a.Hs, a.Ws, m, sx1, sy1, p11);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (area2) {
+        px[c] = (p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2;
+      } else {
+        px[c] = resize_blend(p00[c] * ax0 + p01[c] * ax1, p10[c] * ax0 + p11[c] * ax1, by0, by1);
+      }
+    }
+    if (a.swap_rb) { const int t = px[0]; px[0] = px[2]; px[2] = t; }
+    if (a.dst_u8 != nullptr) {
+      a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
+      a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
+      a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+    }
+    const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
+    const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
+    const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
+    a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+  }
+}
+
+// Stand-alone warp (the bird's-eye image itself, e.g. for display): dst [B,Hw,Ww,3] = cv2.warpPerspective(src, M).
+__global__ void __launch_bounds__(256)
+warp_perspective_u8_kernel(const WarpPreArgs a, uint8_t* __restrict__ dst) {
+  const size_t total = static_cast<size_t>(a.B) * a.Hw * a.Ww;
+  double m[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = a.m[k];
+  for (size_t o = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; o < total;
+       o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(o % a.Ww);
+    const int y = static_cast<int>((o / a.Ww) % a.Hw);
+    const int b = static_cast<int>(o / (static_cast<size_t>(a.Ww) * a.Hw));
+    int p[3];
+    warp_pixel_u8(a.src + b * a.frame_stride, a.pitch, a.Hs, a.Ws, m, x, y, p);
+    dst[o * 3 + 0] = static_cast<uint8_t>(p[0]);
+    dst[o * 3 + 1] = static_cast<uint8_t>(p[1]);
+    dst[o * 3 + 2] = static_cast<uint8_t>(p[2]);
+  }
+}
+
+// Mask back to the source resolution (src/unet.py:70): cv2.resize(mask_u8 [Hs,Ws] -> [Hd,Wd]), INTER_LINEAR, exact.
+// One thread per 4 consecutive output pixels (one 32-bit store); the 224x224 source stays in L1/L2.
+__global__ void __launch_bounds__(256)
+resize_gray_u8_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, uint8_t* __restrict__ dst, int Hd, int Wd) {
+  const int wq = (Wd + 3) / 4;
+  const size_t total = static_cast<size_t>(B) * Hd * wq;
+  const bool area2 = (Hs == 2 * Hd) && (Ws == 2 * Wd);
+  const bool same = (Hs == Hd) && (Ws == Wd);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xq = static_cast<int>(i % wq);
+    const int y = static_cast<int>((i / wq) % Hd);
+    const int b = static_cast<int>(i / (static_cast<size_t>(wq) * Hd));
+    const uint8_t* s = src + static_cast<size_t>(b) * Hs * Ws;
+    int sy0, sy1, by0, by1;
+    resize_coef(y, Hd, Hs, false, sy0, sy1, by0, by1);
+    uint8_t* drow = dst + (static_cast<size_t>(b) * Hd + y) * Wd;
+    uint32_t pack = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = xq * 4 + k;
+      int v = 0;
+      if (x < Wd) {
+        if (same) {
+          v = __ldg(s + static_cast<size_t>(y) * Ws + x);
+        } else if (area2) {
+          const uint8_t* r0 = s + static_cast<size_t>(2 * y) * Ws + 2 * x;
+          v = (__ldg(r0) + __ldg(r0 + 1) + __ldg(r0 + Ws) + __ldg(r0 + Ws + 1) + 2) >> 2;
+        } else {
+          int sx0, sx1, ax0, ax1;
+          resize_coef(x, Wd, Ws, true, sx0, sx1, ax0, ax1);
+          const uint8_t* r0 = s + static_cast<size_t>(sy0) * Ws;
+          const uint8_t* r1 = s + static_cast<size_t>(sy1) * Ws;
+          v = resize_blend(__ldg(r0 + sx0) * ax0 + __ldg(r0 + sx1) * ax1, __ldg(r1 + sx0) * ax0 + __ldg(r1 + sx1) * ax1, by0, by1);
+        }
+      }
+      pack |= static_cast<uint32_t>(v) << (8 * k);
+    }
+    if ((Wd & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(drow + xq * 4) = pack;
+    } else {
+      for (int k = 0; k < 4 && xq * 4 + k < Wd; ++k) drow[xq * 4 + k] = static_cast<uint8_t>(pack >> (8 * k));
+    }
   }
 }
 

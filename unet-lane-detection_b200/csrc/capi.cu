@@ -915,6 +915,56 @@ int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_
   return UB_OK;
 }
 
+int unet_b200_preprocess_warp_u8(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride,
+                                 const double* m_inv9, int Hw, int Ww, int H, int W, int swap_rb, const float* mean3,
+                                 const float* std3, void* y, uint8_t* resized, uint8_t* warped, void* stream) {
+  if (src == nullptr || m_inv9 == nullptr || mean3 == nullptr || std3 == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (y == nullptr && warped == nullptr) return fail(UB_ERR_ARG, "nothing to compute: y and warped are both null");
+  if (batch < 1 || Hs < 1 || Ws < 1 || Hw < 1 || Ww < 1 || H < 1 || W < 1) return fail(UB_ERR_ARG, "bad size");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  ub::WarpPreArgs a;
+  a.src = src;
+  a.pitch = pitch;
+  a.frame_stride = frame_stride;
+  a.B = batch;
+  a.Hs = Hs;
+  a.Ws = Ws;
+  a.Hw = Hw;
+  a.Ww = Ww;
+  a.H = H;
+  a.W = W;
+  a.swap_rb = swap_rb;
+  for (int k = 0; k < 9; ++k) a.m[k] = m_inv9[k];
+  for (int c = 0; c < 3; ++c) {
+    a.mean[c] = mean3[c];
+    a.inv_std[c] = 1.f / std3[c];
+  }
+  a.dst = reinterpret_cast<uint2*>(y);
+  a.dst_u8 = resized;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y != nullptr) {
+    ub::warp_preprocess_u8_kernel<<<grid_for((size_t)batch * H * W, 256), 256, 0, st>>>(a);
+    UB_CUDA(cudaGetLastError());
+  }
+  if (warped != nullptr) {
+    ub::warp_perspective_u8_kernel<<<grid_for((size_t)batch * Hw * Ww, 256), 256, 0, st>>>(a, warped);
+    UB_CUDA(cudaGetLastError());
+  }
+  return UB_OK;
+}
+
+int unet_b200_resize_gray_u8(const uint8_t* src, int batch, int Hs, int Ws, uint8_t* dst, int Hd, int Wd, void* stream) {
+  if (src == nullptr || dst == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (batch < 1 || Hs < 1 || Ws < 1 || Hd < 1 || Wd < 1) return fail(UB_ERR_ARG, "bad size");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  const size_t work = (size_t)batch * Hd * ((Wd + 3) / 4);
+  ub::resize_gray_u8_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, batch, Hs, Ws, dst, Hd, Wd);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
 size_t unet_b200_infer_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
   if (p == nullptr) return 0;
   const size_t npix = (size_t)p->Bc * p->H * p->W;

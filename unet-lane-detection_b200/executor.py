@@ -10,6 +10,7 @@ probabilities float32 [B,1,H,W] out.
 import numpy as np
 import torch
 
+from .ops import MEAN_255, STD_255, preprocess_warp_u8, resize_gray_u8
 from .unet import UNet
 
 
@@ -78,12 +79,46 @@ class B200LaneInference:
             with torch.cuda.device(self.model.device):
                 d = torch.from_numpy(np.ascontiguousarray(image)[None]).to(self.model.device)
                 _, _, mask = net.predict_mask(d, threshold=threshold, size=self.input_size, want=("mask",))
+                if tuple(original_shape) != tuple(self.input_size):
+                    # mask back to the source size (src/unet.py:70), cv2-exact, on the device
+                    mask = resize_gray_u8(mask, (int(original_shape[0]), int(original_shape[1])))
                 mask = mask[0].cpu().numpy()
         except Exception as e:  # reference behaviour: zero mask + elapsed time (src/unet.py:89-92)
             print(f"Inference error: {e}")
             return np.zeros(original_shape, dtype=np.uint8), time.time() - t0
         dt = time.time() - t0
-        if tuple(original_shape) != tuple(self.input_size):
-            import cv2  # mask up-resize back to the source size (src/unet.py:70) stays on the host for now
-            mask = cv2.resize(mask, (original_shape[1], original_shape[0]))
         return mask, dt
+
+
+class B200LanePipeline:
+    """The per-frame work of LaneSegmentationROS.image_callback (src/unet_ros_node.py:292-321) without ROS:
+    bgr8 camera frame -> cv2.warpPerspective to the bird's-eye view -> (same-size resize = copy) -> BGR2RGB ->
+    RKNNLaneInference.predict (resize to 224x224, network, sigmoid, > threshold, x255, resize back to the bird's-eye size).
+    Everything between the H2D copy of the frame and the D2H copy of the mask runs on the GPU; uint8 steps are bit-exact
+    with cv2. Batched: `process(frames_bgr [B,Hs,Ws,3]) -> masks uint8 [B,685,1055]`."""
+
+    def __init__(self, model_path, perspective_matrix, threshold=0.5, warp_size=(1055, 685), input_size=(224, 224),
+                 target=None, device_id=None):
+        self.container = B200_model_container(model_path, target, device_id)
+        self.matrix = np.asarray(perspective_matrix, dtype=np.float64).reshape(3, 3)
+        self.threshold, self.warp_size, self.input_size = threshold, tuple(warp_size), tuple(input_size)
+
+    @torch.no_grad()
+    def process_device(self, frames_bgr):
+        """frames uint8 [B,Hs,Ws,3] on the GPU -> masks uint8 [B,warp_h,warp_w] on the GPU."""
+        net = self.container.model
+        x4 = preprocess_warp_u8(frames_bgr, self.matrix, self.warp_size, self.input_size, swap_rb=True, mean=MEAN_255, std=STD_255)
+        net.gpu_launches += 1
+        _, _, mask = net.forward_nhwc4(x4, threshold=self.threshold, want=("mask",))
+        net.gpu_launches += 1
+        return resize_gray_u8(mask, (self.warp_size[1], self.warp_size[0]))
+
+    def process(self, frames_bgr):
+        single = frames_bgr.ndim == 3
+        arr = np.ascontiguousarray(frames_bgr[None] if single else frames_bgr)
+        with torch.cuda.device(self.container.device):
+            out = self.process_device(torch.from_numpy(arr).to(self.container.device)).cpu().numpy()
+        return out[0] if single else out
+
+    def release(self):
+        self.container.release()

@@ -285,3 +285,65 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.
     check(lib.unet_b200_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), params.numel(),
                                    float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                    float(grad_scale), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# Camera-side steps of the ROS node (src/unet_ros_node.py:297-313) and the mask up-resize (src/unet.py:70).
+# ------------------------------------------------------------------------------------------------
+def invert3x3(m):
+    """cv::invert of a 3x3 double matrix (closed form, reciprocal determinant): the inverse map cv2.warpPerspective
+    derives from its matrix argument. Host-side, float64, bit-equal to cv2.invert."""
+    import numpy as np
+    S = np.asarray(m, dtype=np.float64)
+    det = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0])
+           + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    d = 1.0 / det
+    t = [(S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d, (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d,
+         (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d, (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d,
+         (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d, (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d,
+         (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d, (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d,
+         (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d]
+    return np.asarray(t, dtype=np.float64).reshape(3, 3)
+
+
+def _m9(matrix):
+    import ctypes as C
+    inv = invert3x3(matrix).reshape(-1)
+    return (C.c_double * 9)(*[float(v) for v in inv])
+
+
+def preprocess_warp_u8(frames, matrix, warp_size=(1055, 685), size=(224, 224), swap_rb=True, mean=MEAN_255, std=STD_255,
+                       return_resized=False):
+    """frames uint8 [B,Hs,Ws,3] BGR (CUDA); matrix: the 3x3 perspective matrix handed to cv2.warpPerspective;
+    warp_size (w, h) as in cv2. Returns NHWC4 bf16 [B,H,W,4] (+ the resized uint8 RGB frames)."""
+    _req(frames, torch.uint8, "frames")
+    B, Hs, Ws, c = frames.shape
+    if c != 3:
+        raise ValueError("frames must be [B,Hs,Ws,3]")
+    H, W = size
+    y = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=frames.device)
+    r = torch.empty(B, H, W, 3, dtype=torch.uint8, device=frames.device) if return_resized else None
+    check(lib.unet_b200_preprocess_warp_u8(frames.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, _m9(matrix), warp_size[1],
+                                           warp_size[0], H, W, int(swap_rb), f3(mean), f3(std), y.data_ptr(), _p(r), None,
+                                           _stream()))
+    return (y, r) if return_resized else y
+
+
+def warp_perspective_u8(frames, matrix, warp_size=(1055, 685)):
+    """cv2.warpPerspective(frame, matrix, warp_size) for a batch of uint8 [B,Hs,Ws,3] frames (bit-exact)."""
+    _req(frames, torch.uint8, "frames")
+    B, Hs, Ws, _ = frames.shape
+    out = torch.empty(B, warp_size[1], warp_size[0], 3, dtype=torch.uint8, device=frames.device)
+    check(lib.unet_b200_preprocess_warp_u8(frames.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, _m9(matrix), warp_size[1],
+                                           warp_size[0], 1, 1, 0, f3(MEAN_255), f3(STD_255), None, None, out.data_ptr(),
+                                           _stream()))
+    return out
+
+
+def resize_gray_u8(masks, size):
+    """cv2.resize(mask, (w, h)) for uint8 [B,Hs,Ws] masks; size = (h, w). Bit-exact INTER_LINEAR."""
+    _req(masks, torch.uint8, "masks")
+    B, Hs, Ws = masks.shape
+    out = torch.empty(B, size[0], size[1], dtype=torch.uint8, device=masks.device)
+    check(lib.unet_b200_resize_gray_u8(masks.data_ptr(), B, Hs, Ws, out.data_ptr(), size[0], size[1], _stream()))
+    return out
