@@ -43,7 +43,8 @@ int unet_b200_device_ok(void);
 
 /* ---- plan: UNet(in_channels, out_channels=1, features) at a fixed HxW and batch capacity ------- *
  * Mirrors UNet.__init__ (README.md:1424-1447). H and W must be divisible by 2^levels, features
- * multiples of 64 (32 allowed for level 0 only when it is the stem output), in_channels <= 4,
+ * multiples of 32 (widths that are not multiples of 64 - the deployed topology [32,64,128] - are stored zero-extended to
+ * the next multiple of 64; results are unchanged), in_channels <= 4,
  * out_channels == 1. */
 int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
                           const int* features, int levels);

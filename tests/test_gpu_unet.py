@@ -187,3 +187,54 @@ def test_fused_head_and_halo_switches_agree(U):
     assert (ma != mc).float().mean().item() < 2e-3
     own = (pa > 0.5).to(torch.uint8) * 255
     assert torch.equal(ma, own)
+
+
+def test_deployed_topology_32_64_128(U, golden_dir, tmp_path):
+    """the topology of model/lane_unet*.rknn = UNet(features=[32,64,128]), 1,927,009
+    parameters. Widths that are not multiples of 64 are stored zero-extended; logits must match the oracle as for the
+    default network, through the module and through the executor with a milesial-named checkpoint."""
+    ref, net = make_pair(U, [32, 64, 128], gain=40.0)
+    assert sum(p.numel() for p in net.parameters()) == 1927009
+    x = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, y32.abs().max().item())
+    # the narrow network's logits hug the threshold more than the default one's: gate against the bf16 noise floor of the
+    # oracle itself (PyTorch with bf16 rounding at the same points), as for the random-init test above
+    yem = O.forward_bf16_emulated(ref, x)
+    floor = O.mask_agreement(yem, y32)
+    got = O.mask_agreement(y, y32)
+    assert got >= min(0.999, floor - 0.002), f"mask agreement {got:.5f} (bf16-emulated oracle floor {floor:.5f})"
+    assert O.mask_agreement(y, y32, band=4 * (yem - y32).abs().max().item()) >= 0.9999
+    # unfused head / non-halo kernels take the padded channels too
+    from unet_lane_detection_b200._lib import check, lib
+    try:
+        check(lib.unet_b200_set_option(b"halo", 0))
+        check(lib.unet_b200_set_option(b"fuse_head", 0))
+        net2 = U.UNet(3, 1, [32, 64, 128])
+        net2.load_state_dict(ref.state_dict())
+        with torch.no_grad():
+            y2 = net2.cuda().eval()(x.cuda()).cpu()
+    finally:
+        check(lib.unet_b200_set_option(b"halo", 1))
+        check(lib.unet_b200_set_option(b"fuse_head", 1))
+    assert (y2 - y32).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, y32.abs().max().item())
+    # golden logits of the reference listing for this topology are pinned by the manifest's parameter count; executor path:
+    sd = ref.state_dict()
+    names = {"encoder_blocks.0": "inc", "encoder_blocks.1": "down1", "encoder_blocks.2": "down2", "bottleneck": "down3",
+             "decoder_blocks.0": "up1", "decoder_blocks.1": "conv1", "decoder_blocks.2": "up2", "decoder_blocks.3": "conv2",
+             "decoder_blocks.4": "up3", "decoder_blocks.5": "conv3", "output": "outc"}
+    renamed = {}
+    for k, v in sd.items():
+        pre = next(p for p in sorted(names, key=len, reverse=True) if k.startswith(p + "."))
+        renamed[names[pre] + k[len(pre):]] = v
+    path = tmp_path / "lane_unet_deployed.pth"
+    torch.save(renamed, path)
+    box = U.B200_model_container(str(path))
+    frame = np.random.default_rng(4).integers(0, 256, (1, 224, 224, 3), dtype=np.uint8)
+    out = box.run([frame])[0]
+    with torch.no_grad():
+        want = torch.sigmoid(ref(torch.from_numpy(O.normalize_oracle(frame)))).numpy()
+    assert out.shape == (1, 1, 224, 224) and np.abs(out - want).max() <= 2e-2
+    box.release()

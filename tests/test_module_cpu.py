@@ -111,3 +111,33 @@ def test_shard_ranges_cover_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_deployed_topology_key_remap_round_trip():
+    """checkpoints of the deployed [32,64,128] topology (block names inc/down*/up*/conv*/outc as found
+    inside model/lane_unet*.rknn) are remapped positionally onto the reference listing's keys."""
+    from unet_lane_detection_b200.executor import _features_from_state_dict, remap_milesial_state_dict
+    torch.manual_seed(0)
+    ref = O.UNetOracle(3, 1, [32, 64, 128])
+    assert sum(p.numel() for p in ref.parameters()) == 1927009            # SURVEY.md Appendix C / D3
+    sd = ref.state_dict()
+    names = {"encoder_blocks.0": "inc", "encoder_blocks.1": "down1", "encoder_blocks.2": "down2", "bottleneck": "down3",
+             "decoder_blocks.0": "up1", "decoder_blocks.1": "conv1", "decoder_blocks.2": "up2", "decoder_blocks.3": "conv2",
+             "decoder_blocks.4": "up3", "decoder_blocks.5": "conv3", "output": "outc"}
+    inner = {"0": "double_conv.0", "1": "double_conv.1", "3": "double_conv.3", "4": "double_conv.4"}
+    renamed = {}
+    for k, v in sd.items():
+        pre = next(p for p in sorted(names, key=len, reverse=True) if k.startswith(p + "."))
+        rest = k[len(pre) + 1:].split(".")
+        if rest[0] in inner and len(rest) > 1:
+            rest[0] = inner[rest[0]]
+        renamed[names[pre] + "." + ".".join(rest)] = v
+    assert not any(k.startswith("encoder_blocks") for k in renamed)
+    back = remap_milesial_state_dict(renamed)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert _features_from_state_dict(back) == ([32, 64, 128], 3, 1)
+    m = U.UNet(3, 1, [32, 64, 128])
+    m.load_state_dict(back)
+    assert remap_milesial_state_dict(sd) is sd
+    with pytest.raises(ValueError):
+        remap_milesial_state_dict({"foo.weight": torch.zeros(1)})

@@ -33,6 +33,58 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __
   }
 }
 
+// Zero-padded variants used by the plan when a logical channel count is not a multiple of 64 (the deployed topology
+// features [32,64,128]): the tensor is stored with 64-aligned channels whose extra entries are
+// exactly zero (zero weights and zero bias produce relu(0) = 0), so results are unchanged.
+// conv: logical w[Cout_l][C0_l + C1_l][3][3], sources 0 / 1 padded to C0_p / C1_p -> wp[Cout_p][9][C0_p + C1_p].
+__global__ void pack_conv3x3_pad_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const float* __restrict__ mean,
+                                        const float* __restrict__ var, float eps, int Cout_l, int C0_l, int C1_l, int Cout_p,
+                                        int C0_p, int C1_p, __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int Cin_p = C0_p + C1_p, Cin_l = C0_l + C1_l;
+  const int total = Cout_p * 9 * Cin_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cp = i % Cin_p;
+    const int tap = (i / Cin_p) % 9;
+    const int co = i / (9 * Cin_p);
+    int ci = -1;
+    if (cp < C0_p) {
+      if (cp < C0_l) ci = cp;
+    } else if (cp - C0_p < C1_l) {
+      ci = C0_l + (cp - C0_p);
+    }
+    float v = 0.f;
+    if (co < Cout_l && ci >= 0) {
+      float s = 1.f;
+      if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
+      v = w[(static_cast<size_t>(co) * Cin_l + ci) * 9 + tap] * s;
+    }
+    wp[i] = __float2bfloat16_rn(v);
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout_p; co += gridDim.x * blockDim.x) {
+    float bv = 0.f;
+    if (gamma != nullptr && co < Cout_l) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    bias[co] = bv;
+  }
+}
+// ConvT: logical w[Cin_l][f_l][2][2] -> wp[(quad*f_p + co)][Cin_p], bias_p[f_p] (bias may be null: not written).
+__global__ void pack_convT_pad_kernel(const float* __restrict__ w, const float* __restrict__ b, int Cin_l, int f_l, int Cin_p,
+                                      int f_p, __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_p) {
+  const int total = 4 * f_p * Cin_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Cin_p;
+    const int n = i / Cin_p;
+    const int co = n % f_p;
+    const int quad = n / f_p;
+    float v = 0.f;
+    if (ci < Cin_l && co < f_l) v = w[(static_cast<size_t>(ci) * f_l + co) * 4 + quad];
+    wp[i] = __float2bfloat16_rn(v);
+  }
+  if (bias_p != nullptr) {
+    for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < f_p; co += gridDim.x * blockDim.x) bias_p[co] = co < f_l ? b[co] : 0.f;
+  }
+}
+
 // Stem (Cin <= 4): -> ws[9][4][Cout] fp32 (zero for ci >= Cin), bias[Cout].
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ mean,

@@ -302,7 +302,8 @@ enum LayerKind { L_STEM, L_CONV, L_CONVT };
 struct Layer {
   LayerKind kind;
   int H, W;          // GEMM-row grid (input spatial size)
-  int C0, C1, Cout;  // conv: Cin split / Cout.  convT: C0 = Cin, Cout = f
+  int C0, C1, Cout;  // conv: Cin split / Cout.  convT: C0 = Cin, Cout = f   (physical: multiples of 64 except the stem input)
+  int lC0, lC1, lCout;  // logical channel counts of the reference tensors (<= physical; extra channels are exact zeros)
   int relu;
   int in0, in1, out, pool;  // activation buffer ids (-1 = none; in0 == -2: network input)
   size_t w_off, b_off;      // offsets into the weight buffer
@@ -380,7 +381,7 @@ int add_buf(unet_b200_plan* p, int H, int W, int C) {
 }
 
 void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, int Cout, int in0, int in1, int out,
-              int pool) {
+              int pool, int lC0 = -1, int lC1 = -1, int lCout = -1) {
   Layer l;
   memset(&l, 0, sizeof(l));
   l.kind = kind;
@@ -389,6 +390,9 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   l.C0 = C0;
   l.C1 = C1;
   l.Cout = Cout;
+  l.lC0 = lC0 < 0 ? C0 : lC0;
+  l.lC1 = lC1 < 0 ? C1 : lC1;
+  l.lCout = lCout < 0 ? Cout : lCout;
   l.relu = (kind != L_CONVT);
   l.in0 = in0;
   l.in1 = in1;
@@ -576,10 +580,14 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
     return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
   }
   for (int i = 0; i < levels; ++i) {
-    if (features[i] % 64 != 0 || features[i] <= 0) {
-      return fail(UB_ERR_ARG, "features[%d]=%d must be a positive multiple of 64", i, features[i]);
+    if (features[i] % 32 != 0 || features[i] <= 0) {
+      return fail(UB_ERR_ARG, "features[%d]=%d must be a positive multiple of 32", i, features[i]);
     }
   }
+  // physical channel counts: 64-aligned (one 128-byte swizzled row per pixel and channel block); a logical width such as
+  // the deployed topology's 32 is stored zero-extended, see pack_conv3x3_pad_kernel
+  int fp[UB_MAX_LEVELS];
+  for (int i = 0; i < levels; ++i) fp[i] = (features[i] + 63) / 64 * 64;
   unet_b200_plan* p = new (std::nothrow) unet_b200_plan();
   if (p == nullptr) return fail(UB_ERR_ARG, "out of host memory");
   p->Bc = max_batch;
@@ -597,45 +605,48 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
 
   // encoder (README.md:1432-1434, 1464-1467)
   int cur = -2;  // network input
-  int cin = in_channels;
+  int cin = in_channels, lcin = in_channels;
   std::vector<int> skips;
   for (int i = 0; i < levels; ++i) {
-    const int h = H >> i, w = W >> i, f = features[i];
+    const int h = H >> i, w = W >> i, f = fp[i], lf = features[i];
     const int ea = add_buf(p, h, w, f);
     const int sk = add_buf(p, h, w, f);
     const int pl = add_buf(p, h / 2, w / 2, f);
     if (i == 0) {
-      add_conv(p, L_STEM, h, w, cin, 0, f, cur, -1, ea, -1);
+      add_conv(p, L_STEM, h, w, cin, 0, f, cur, -1, ea, -1, lcin, 0, lf);
     } else {
-      add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ea, -1);
+      add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ea, -1, lcin, 0, lf);
     }
-    add_conv(p, L_CONV, h, w, f, 0, f, ea, -1, sk, pl);
+    add_conv(p, L_CONV, h, w, f, 0, f, ea, -1, sk, pl, lf, 0, lf);
     skips.push_back(sk);
     cur = pl;
     cin = f;
+    lcin = lf;
   }
   // bottleneck (README.md:1437, 1470)
   {
-    const int h = H >> levels, w = W >> levels, f = features[levels - 1] * 2;
+    const int h = H >> levels, w = W >> levels, lf = features[levels - 1] * 2, f = (lf + 63) / 64 * 64;
     const int ba = add_buf(p, h, w, f);
     const int bb = add_buf(p, h, w, f);
-    add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ba, -1);
-    add_conv(p, L_CONV, h, w, f, 0, f, ba, -1, bb, -1);
+    add_conv(p, L_CONV, h, w, cin, 0, f, cur, -1, ba, -1, lcin, 0, lf);
+    add_conv(p, L_CONV, h, w, f, 0, f, ba, -1, bb, -1, lf, 0, lf);
     cur = bb;
     cin = f;
+    lcin = lf;
   }
   // decoder (README.md:1440-1444, 1473-1479): ConvT, then double conv over cat([skip, up])
   for (int j = 0; j < levels; ++j) {
     const int i = levels - 1 - j;
-    const int h = H >> i, w = W >> i, f = features[i];
+    const int h = H >> i, w = W >> i, f = fp[i], lf = features[i];
     const int up = add_buf(p, h, w, f);
     const int da = add_buf(p, h, w, f);
     const int db = add_buf(p, h, w, f);
-    add_conv(p, L_CONVT, h / 2, w / 2, cin, 0, f, cur, -1, up, -1);
-    add_conv(p, L_CONV, h, w, f, f, f, skips[i], up, da, -1);
-    add_conv(p, L_CONV, h, w, f, 0, f, da, -1, db, -1);
+    add_conv(p, L_CONVT, h / 2, w / 2, cin, 0, f, cur, -1, up, -1, lcin, 0, lf);
+    add_conv(p, L_CONV, h, w, f, f, f, skips[i], up, da, -1, lf, lf, lf);
+    add_conv(p, L_CONV, h, w, f, 0, f, da, -1, db, -1, lf, 0, lf);
     cur = db;
     cin = f;
+    lcin = lf;
   }
   p->final_buf = cur;
   {
@@ -643,7 +654,7 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
     last.fuse_head = g_opt_fuse_head && last.kind == L_CONV && last.halo && last.Cout == 64;
   }
   p->head_w_off = p->wt_bytes;
-  p->wt_bytes += align_up((size_t)features[0] * 4, 256);
+  p->wt_bytes += align_up((size_t)fp[0] * 4, 256);
   *out = p;
   return UB_OK;
 }
@@ -712,15 +723,20 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* bias = reinterpret_cast<float*>(p->wt + l.b_off);
   if (l.kind == L_STEM && l.stem_tc) {
-    ub::pack_stem_umma_kernel<<<grid_for(64 * l.Cout, 256), 256, 0, st>>>(
-        w, gamma, beta, mean, var, eps, l.Cout, l.C0, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
+    // logical Cout rows are written; rows / bias entries of padded channels keep the zeros the buffer was created with
+    UB_CUDA(cudaMemsetAsync(p->wt + l.w_off, 0, (size_t)64 * 64 * 2, st));
+    UB_CUDA(cudaMemsetAsync(bias, 0, (size_t)l.Cout * 4, st));
+    ub::pack_stem_umma_kernel<<<grid_for(64 * l.lCout, 256), 256, 0, st>>>(
+        w, gamma, beta, mean, var, eps, l.lCout, l.C0, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
   } else if (l.kind == L_STEM) {
+    if (l.lCout != l.Cout) return fail(UB_ERR_ARG, "stem width %d needs the tensor-core stem (option stem_umma)", l.lCout);
     ub::pack_stem_kernel<<<grid_for(36 * l.Cout, 256), 256, 0, st>>>(w, gamma, beta, mean, var, eps, l.Cout, l.C0,
                                                                      reinterpret_cast<float*>(p->wt + l.w_off), bias);
   } else {
     const int cin = l.C0 + l.C1;
-    ub::pack_conv3x3_kernel<<<grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st>>>(
-        w, gamma, beta, mean, var, eps, l.Cout, cin, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
+    ub::pack_conv3x3_pad_kernel<<<grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st>>>(
+        w, gamma, beta, mean, var, eps, l.lCout, l.lC0, l.lC1, l.Cout, l.C0, l.C1,
+        reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
   }
   UB_CUDA(cudaGetLastError());
   l.set = true;
@@ -733,10 +749,10 @@ int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w, const f
   if (idx < 0 || idx >= (int)p->convt_ids.size()) return fail(UB_ERR_ARG, "convT index %d out of range", idx);
   Layer& l = p->layers[p->convt_ids[idx]];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ub::pack_convT_kernel<<<grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st>>>(
-      w, l.C0, l.Cout, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off));
+  ub::pack_convT_pad_kernel<<<grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st>>>(
+      w, bias, l.lC0, l.lCout, l.C0, l.Cout, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off),
+      reinterpret_cast<float*>(p->wt + l.b_off));
   UB_CUDA(cudaGetLastError());
-  UB_CUDA(cudaMemcpyAsync(p->wt + l.b_off, bias, (size_t)l.Cout * 4, cudaMemcpyDeviceToDevice, st));
   l.set = true;
   return UB_OK;
 }
@@ -745,6 +761,7 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
   if (p == nullptr || w == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (p->wt == nullptr) return fail(UB_ERR_STATE, "plan_bind must be called before set_head");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UB_CUDA(cudaMemsetAsync(p->wt + p->head_w_off, 0, (size_t)((p->feat[0] + 63) / 64 * 64) * 4, st));
   UB_CUDA(cudaMemcpyAsync(p->wt + p->head_w_off, w, (size_t)p->feat[0] * 4, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemcpyAsync(&p->head_bias, bias, 4, cudaMemcpyDeviceToHost, st));
   UB_CUDA(cudaStreamSynchronize(st));

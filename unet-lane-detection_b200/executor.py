@@ -24,6 +24,52 @@ def _features_from_state_dict(sd):
     return feats, int(sd["encoder_blocks.0.0.weight"].shape[1]), int(sd["output.weight"].shape[0])
 
 
+def remap_milesial_state_dict(sd):
+    """Checkpoints of the DEPLOYED topology name their blocks `inc / down1..N / up1..N / conv1..N / outc`
+    (the tensor names inside model/lane_unet*.rknn); the python source of that variant is not in
+    the reference tree, so the mapping is positional: the tensors of each source block are assigned, in order and with a
+    shape check, to the corresponding block of the reference listing's layout (README.md:1424-1447):
+      inc -> encoder_blocks.0, down_i -> encoder_blocks.i (the last down -> bottleneck),
+      up_j -> decoder_blocks.2(j-1) (ConvTranspose2d), conv_j -> decoder_blocks.2(j-1)+1, outc -> output.
+    Returns a new dict with the reference keys; dicts that already use them are returned unchanged."""
+    if any(k.startswith("encoder_blocks.") for k in sd):
+        return sd
+    blocks = {}
+    for k, v in sd.items():
+        blocks.setdefault(k.split(".")[0], []).append((k, v))
+    downs = sorted((b for b in blocks if b.startswith("down")), key=lambda b: int(b[4:]))
+    ups = sorted((b for b in blocks if b.startswith("up")), key=lambda b: int(b[2:]))
+    convs = sorted((b for b in blocks if b.startswith("conv")), key=lambda b: int(b[4:]))
+    if "inc" not in blocks or "outc" not in blocks or not downs or len(ups) != len(downs) or len(convs) != len(ups):
+        raise ValueError("state_dict uses neither the reference keys (encoder_blocks.*) nor inc/down*/up*/conv*/outc")
+    pairs = [("inc", "encoder_blocks.0")] + [(d, f"encoder_blocks.{i + 1}") for i, d in enumerate(downs[:-1])]
+    pairs.append((downs[-1], "bottleneck"))
+    for j, (u, c) in enumerate(zip(ups, convs)):
+        pairs += [(u, f"decoder_blocks.{2 * j}"), (c, f"decoder_blocks.{2 * j + 1}")]
+    pairs.append(("outc", "output"))
+    bn_keys = ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")
+    out = {}
+    for src, dst in pairs:
+        tensors = blocks[src]
+        if dst.startswith(("encoder_blocks", "bottleneck")) or (dst.startswith("decoder_blocks") and int(dst.split(".")[1]) % 2 == 1):
+            slots = []
+            for conv_i, bn_i in ((0, 1), (3, 4)):
+                slots.append(f"{dst}.{conv_i}.weight")
+                slots += [f"{dst}.{bn_i}.{k}" for k in bn_keys]
+            have_nbt = any(k.endswith("num_batches_tracked") for k, _ in tensors)
+            if not have_nbt:
+                slots = [t for t in slots if not t.endswith("num_batches_tracked")]
+            if any(v.dim() == 1 and k.endswith("bias") and i == 1 for i, (k, v) in enumerate(tensors)):
+                raise ValueError(f"block '{src}' has biased convolutions (BatchNorm already folded): not the train-form UNet")
+        else:
+            slots = [f"{dst}.weight", f"{dst}.bias"]
+        if len(slots) != len(tensors):
+            raise ValueError(f"block '{src}' holds {len(tensors)} tensors, expected {len(slots)} for '{dst}'")
+        for slot, (_, v) in zip(slots, tensors):
+            out[slot] = v
+    return out
+
+
 class B200_model_container:
     def __init__(self, model_path, target=None, device_id=None, output="probs"):
         if not torch.cuda.is_available():
@@ -34,9 +80,10 @@ class B200_model_container:
         else:
             ckpt = torch.load(model_path, map_location="cpu", weights_only=True)
             sd = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt
+            sd = remap_milesial_state_dict(sd)
             feats, cin, cout = _features_from_state_dict(sd)
             model = UNet(cin, cout, feats)
-            model.load_state_dict(sd)
+            model.load_state_dict(sd, strict=all(k in sd for k in model.state_dict()))
         self.model = model.to(dev).eval()
         self.device = dev
         self.output = output  # "probs" (deployed graph has the sigmoid inside) or "logits"
