@@ -132,6 +132,14 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging_dev, const uint8_t*
                             int Ws, int swap_rb, const float* mean3, const float* std3, float threshold,
                             float* logits_host, float* probs_host, uint8_t* mask_host, void* stream);
 
+/* Same contract for ANY number of frames: the batch is cut into chunks of the plan's capacity and the H2D copy of chunk
+ * i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i (two staging slots, two internal copy streams created
+ * on first use). Host buffers should be pinned. staging_dev: unet_b200_infer_stream_staging_bytes(...) bytes. */
+size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int Ws);
+int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging_dev, const uint8_t* frames_host, int total, int Hs,
+                                   int Ws, int swap_rb, const float* mean3, const float* std3, float threshold,
+                                   float* logits_host, float* probs_host, uint8_t* mask_host, void* stream);
+
 /* ---- single layers (parity tests and reuse outside a plan) --------------------------------------- *
  * conv3x3: y = relu?(conv3x3(cat(x0, x1)) + bias); x0/x1 bf16 NHWC [B,H,W,C0|C1] (C1 may be 0, then
  * x1 is ignored); wp bf16 [Cout][9][C0+C1]; bias fp32 [Cout]; y bf16 [B,H,W,Cout]; pool (optional)

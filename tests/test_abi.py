@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu():
     lib.unet_b200_plan_destroy(h)
     bad = (C.c_int * 2)(64, 100)
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 1, bad, 2) == -1
-    assert b"multiple of 64" in lib.unet_b200_last_error()
+    assert b"multiple of 32" in lib.unet_b200_last_error()
     assert lib.unet_b200_plan_create(C.byref(h), 8, 100, 224, 3, 1, feats, 4) == -1   # H not divisible by 16
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 5, 1, feats, 4) == -1   # in_channels > 4
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 2, feats, 4) == -1   # out_channels != 1

@@ -365,6 +365,10 @@ struct unet_b200_plan {
   bool head_set;
   uint8_t* ws;
   uint8_t* wt;
+  // copy/compute overlap of the host-buffer entry point (created on first use, destroyed with the plan)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr},
+              ev_out_free[2] = {nullptr, nullptr}, ev_start = nullptr;
 };
 
 namespace {
@@ -659,7 +663,19 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   return UB_OK;
 }
 
-void unet_b200_plan_destroy(unet_b200_plan* p) { delete p; }
+void unet_b200_plan_destroy(unet_b200_plan* p) {
+  if (p == nullptr) return;
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_in_free[i]) cudaEventDestroy(p->ev_in_free[i]);
+    if (p->ev_cmp[i]) cudaEventDestroy(p->ev_cmp[i]);
+    if (p->ev_out_free[i]) cudaEventDestroy(p->ev_out_free[i]);
+  }
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
+  delete p;
+}
 size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p) { return p ? p->ws_bytes : 0; }
 size_t unet_b200_plan_weight_bytes(const unet_b200_plan* p) { return p ? p->wt_bytes : 0; }
 int unet_b200_plan_num_convs(const unet_b200_plan* p) { return p ? (int)p->conv_ids.size() : 0; }
@@ -1021,6 +1037,90 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* fra
   if (logits_h) UB_CUDA(cudaMemcpyAsync(logits_h, d_logits, npix * 4, cudaMemcpyDeviceToHost, st));
   if (probs_h) UB_CUDA(cudaMemcpyAsync(probs_h, d_probs, npix * 4, cudaMemcpyDeviceToHost, st));
   if (mask_h) UB_CUDA(cudaMemcpyAsync(mask_h, d_mask, npix, cudaMemcpyDeviceToHost, st));
+  UB_CUDA(cudaStreamSynchronize(st));
+  return UB_OK;
+}
+
+// ---- host-buffer entry point with copy/compute overlap over chunks ----------------------------------------------------
+size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
+  if (p == nullptr) return 0;
+  const size_t npix = (size_t)p->Bc * p->H * p->W;
+  size_t n = 2 * align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // two frame slots
+  n += align_up(npix * 8, 256);                               // NHWC4 bf16 (consumed by the stem before the next chunk's preprocess)
+  n += 2 * (2 * align_up(npix * 4, 256) + align_up(npix, 256));  // two output slots: logits, probs, mask
+  return n;
+}
+
+int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8_t* frames, int total, int Hs, int Ws,
+                                   int swap_rb, const float* mean3, const float* std3, float threshold, float* logits_h,
+                                   float* probs_h, uint8_t* mask_h, void* stream) {
+  if (p == nullptr || staging == nullptr || frames == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (total < 1) return fail(UB_ERR_ARG, "total must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->s_in == nullptr) {
+    UB_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    UB_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      UB_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+      UB_CUDA(cudaEventCreateWithFlags(&p->ev_in_free[i], cudaEventDisableTiming));
+      UB_CUDA(cudaEventCreateWithFlags(&p->ev_cmp[i], cudaEventDisableTiming));
+      UB_CUDA(cudaEventCreateWithFlags(&p->ev_out_free[i], cudaEventDisableTiming));
+    }
+    UB_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+  }
+  const size_t npix_c = (size_t)p->Bc * p->H * p->W;
+  const size_t frame_bytes = (size_t)Hs * Ws * 3;
+  uint8_t* s = static_cast<uint8_t*>(staging);
+  uint8_t* d_frames[2];
+  for (int i = 0; i < 2; ++i) {
+    d_frames[i] = s;
+    s += align_up((size_t)p->Bc * frame_bytes, 256);
+  }
+  void* d_x = s;
+  s += align_up(npix_c * 8, 256);
+  float *d_logits[2], *d_probs[2];
+  uint8_t* d_mask[2];
+  for (int i = 0; i < 2; ++i) {
+    d_logits[i] = reinterpret_cast<float*>(s);
+    s += align_up(npix_c * 4, 256);
+    d_probs[i] = reinterpret_cast<float*>(s);
+    s += align_up(npix_c * 4, 256);
+    d_mask[i] = s;
+    s += align_up(npix_c, 256);
+  }
+  // the side streams start after whatever the caller already queued on `stream`
+  UB_CUDA(cudaEventRecord(p->ev_start, st));
+  UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+  UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
+  const int hw = p->H * p->W;
+  int it = 0;
+  for (int b0 = 0; b0 < total; b0 += p->Bc, ++it) {
+    const int n = total - b0 < p->Bc ? total - b0 : p->Bc;
+    const int slot = it & 1;
+    const size_t npix = (size_t)n * hw;
+    // H2D of chunk `it` (runs while chunk it-1 computes); the slot is free once chunk it-2's preprocess has read it
+    if (it >= 2) UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_in_free[slot], 0));
+    UB_CUDA(cudaMemcpyAsync(d_frames[slot], frames + (size_t)b0 * frame_bytes, frame_bytes * n, cudaMemcpyHostToDevice, p->s_in));
+    UB_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+    // compute
+    UB_CUDA(cudaStreamWaitEvent(st, p->ev_in[slot], 0));
+    int rc = unet_b200_preprocess_u8(d_frames[slot], n, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3, std3, d_x,
+                                     nullptr, st);
+    if (rc != UB_OK) return rc;
+    UB_CUDA(cudaEventRecord(p->ev_in_free[slot], st));
+    if (it >= 2) UB_CUDA(cudaStreamWaitEvent(st, p->ev_out_free[slot], 0));  // chunk it-2's results have left the slot
+    rc = unet_b200_forward(p, d_x, n, logits_h ? d_logits[slot] : nullptr, probs_h ? d_probs[slot] : nullptr,
+                           mask_h ? d_mask[slot] : nullptr, threshold, st);
+    if (rc != UB_OK) return rc;
+    UB_CUDA(cudaEventRecord(p->ev_cmp[slot], st));
+    // D2H of chunk `it` (runs while chunk it+1 computes)
+    UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[slot], 0));
+    if (logits_h) UB_CUDA(cudaMemcpyAsync(logits_h + (size_t)b0 * hw, d_logits[slot], npix * 4, cudaMemcpyDeviceToHost, p->s_out));
+    if (probs_h) UB_CUDA(cudaMemcpyAsync(probs_h + (size_t)b0 * hw, d_probs[slot], npix * 4, cudaMemcpyDeviceToHost, p->s_out));
+    if (mask_h) UB_CUDA(cudaMemcpyAsync(mask_h + (size_t)b0 * hw, d_mask[slot], npix, cudaMemcpyDeviceToHost, p->s_out));
+    UB_CUDA(cudaEventRecord(p->ev_out_free[slot], p->s_out));
+  }
+  UB_CUDA(cudaStreamSynchronize(p->s_out));
   UB_CUDA(cudaStreamSynchronize(st));
   return UB_OK;
 }

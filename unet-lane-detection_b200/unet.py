@@ -190,19 +190,15 @@ class UNet(nn.Module):
         eng = self._engine(dev, size[0], size[1], B)
         skey = (Hs, Ws)
         if getattr(eng, "staging_key", None) != skey:
-            eng.staging = torch.empty(lib.unet_b200_infer_staging_bytes(eng.handle, Hs, Ws), dtype=torch.uint8, device=dev)
+            eng.staging = torch.empty(lib.unet_b200_infer_stream_staging_bytes(eng.handle, Hs, Ws), dtype=torch.uint8, device=dev)
             eng.staging_key = skey
         st = torch.cuda.current_stream().cuda_stream
-        npix = size[0] * size[1]
-        for b0 in range(0, B, eng.cap):
-            n = min(eng.cap, B - b0)
-            check(lib.unet_b200_infer_u8_host(
-                eng.handle, eng.staging.data_ptr(), frames_host[b0:b0 + n].data_ptr(), n, Hs, Ws, int(swap_rb),
-                f3(MEAN_255), f3(STD_255), float(threshold),
-                None if logits_out is None else logits_out.data_ptr() + b0 * npix * 4,
-                None if probs_out is None else probs_out.data_ptr() + b0 * npix * 4,
-                None if mask_out is None else mask_out.data_ptr() + b0 * npix, st))
-            self.gpu_launches += eng.launches + 1
+        # one call for the whole batch: chunks of eng.cap frames, copies of neighbouring chunks overlap the kernels
+        check(lib.unet_b200_infer_u8_host_stream(
+            eng.handle, eng.staging.data_ptr(), frames_host.data_ptr(), B, Hs, Ws, int(swap_rb), f3(MEAN_255), f3(STD_255),
+            float(threshold), None if logits_out is None else logits_out.data_ptr(),
+            None if probs_out is None else probs_out.data_ptr(), None if mask_out is None else mask_out.data_ptr(), st))
+        self.gpu_launches += ((B + eng.cap - 1) // eng.cap) * (eng.launches + 1)
         return mask_out, probs_out, logits_out
 
     def profile_layers(self, x4):
