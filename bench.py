@@ -207,6 +207,8 @@ def main():
                     help="infer: BASELINE.json headline (configs[1]); train: the training step of configs[3] as the metric")
     ap.add_argument("--train-batch", type=int, default=64, help="samples per GPU per training step (configs[3])")
     ap.add_argument("--no-train", action="store_true", help="infer mode: skip the secondary training-step measurement")
+    ap.add_argument("--hw", nargs=2, type=int, default=[224, 224], metavar=("H", "W"),
+                    help="network input size; 480 640 = BASELINE.json configs[4] (camera resolution, use --batch 16 --chunk 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-kernel profile table to this JSON file")
     args = ap.parse_args()
@@ -236,10 +238,12 @@ def main():
     model = build_model_cpu().to(dev)
     model.b200_chunk = args.chunk
     B = args.batch
+    H, W = args.hw
+    flops_per_frame = FLOPS_PER_FRAME * (H * W) / (224 * 224)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    frames_host = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    frames_host = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory()
     frames_dev = frames_host.to(dev)
-    mask_host = torch.empty(B, 224, 224, dtype=torch.uint8).pin_memory()
+    mask_host = torch.empty(B, H, W, dtype=torch.uint8).pin_memory()
 
     def barrier():
         if world > 1:
@@ -288,10 +292,10 @@ def main():
         return
 
     def step_device():
-        model.predict_mask(frames_dev, threshold=0.5, want=("mask",))
+        model.predict_mask(frames_dev, threshold=0.5, size=(H, W), want=("mask",))
 
     def step_host():
-        model.infer_host(frames_host, threshold=0.5, mask_out=mask_host)
+        model.infer_host(frames_host, threshold=0.5, size=(H, W), mask_out=mask_host)
 
     for _ in range(args.warmup):
         step_device()
@@ -311,7 +315,7 @@ def main():
 
     # roofline of the dominant kernel family (tcgen05 implicit-GEMM convs), from per-kernel CUDA events
     peaks = load_peaks()
-    x4 = torch.empty(min(args.chunk, B), 224, 224, 4, dtype=torch.bfloat16, device=dev).normal_()
+    x4 = torch.empty(min(args.chunk, B), H, W, 4, dtype=torch.bfloat16, device=dev).normal_()
     model.profile_layers(x4)
     rows = None
     for _ in range(3):
@@ -342,7 +346,7 @@ def main():
                 "timing": f"CUDA events around every kernel of one {int(x4.shape[0])}-frame pass on the launching stream, min of 3",
                 "traffic_note": "ncu --set full per-launch DRAM bytes are in profiles/r1_ncu_full_*.txt (no re-reads: dec3.conv0 reads 411 MB = its two inputs)",
                 "other_kernels": {"conv_halo_kernel<64>": halo64, "conv_halo_kernel<128>": halo128, "all_tensor_core_convs": allconv},
-                "whole_net_frac_of_peak": (value / world) * FLOPS_PER_FRAME / 1e12 / peaks["bf16_sustained"]}
+                "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
         with open(args.layers_out, "w") as f:
@@ -352,21 +356,25 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"U-Net 224x224 bf16 inference, features {FEATURES}, batch {B}/GPU, fused preprocess + mask threshold "
-                               "(BASELINE.json configs[1])", "batch_per_gpu": B, "chunk": args.chunk,
+        "config": {"workload": f"U-Net {H}x{W} bf16 inference, features {FEATURES}, batch {B}/GPU, fused preprocess + mask threshold "
+                               + ("(BASELINE.json configs[1])" if (H, W) == (224, 224) else "(BASELINE.json configs[4] geometry)"),
+                   "batch_per_gpu": B, "chunk": args.chunk,
                    "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2_policy": f"inputs+activations >> L2: {B * 224 * 224 * 3 / 1e6:.0f} MB frames and "
-                                f"{args.chunk * 64.1:.0f} MB activations per chunk vs 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 224 * 224 * 3, "d2h_bytes_per_step": B * 224 * 224,
-                "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host (pinned host buffers)"},
+                   "l2_policy": f"inputs+activations >> L2: {B * H * W * 3 / 1e6:.0f} MB frames and "
+                                f"{min(args.chunk, B) * 64.1 * H * W / (224 * 224):.0f} MB activations per chunk vs 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 3, "d2h_bytes_per_step": B * H * W,
+                "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host_stream (pinned host buffers, copies overlapped with compute)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    if (H, W) != (224, 224):
+        line["metric"] = f"unet{H}x{W}_inference_frames_per_sec"
+        args.no_train = True
     if not args.no_train:
         del frames_dev
         model._engines.clear()
         torch.cuda.empty_cache()
         line["train"] = measure_train(dev, world, rank, args.train_batch, min(args.steps, 10), 3, timed)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and (H, W) == (224, 224):
         v, sps, threads = time_cpu_reference(8, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"8 frames/step x 3 steps ({sps * 3:.1f} s) of the oracle fp32 PyTorch CPU pipeline"}
