@@ -20,7 +20,10 @@ import threading
 import time
 
 # one process per GPU: pin the visible device before CUDA initialises (the C-ABI library carries its own runtime)
-if "LOCAL_RANK" in os.environ and os.environ.get("UB_BENCH_PIN", "1") == "1":
+# (the NVLink gradient exchange maps the peers' buffers, so every GPU has to stay visible: no pinning there)
+PINNED = ("LOCAL_RANK" in os.environ and os.environ.get("UB_BENCH_PIN", "1") == "1"
+          and ("train" not in sys.argv or "nccl" in sys.argv))
+if PINNED:
     _vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     _ids = _vis.split(",") if _vis else None
     _lr = int(os.environ["LOCAL_RANK"])
@@ -152,7 +155,7 @@ def run_reference(args):
 TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_FRAME  # forward + dgrad + wgrad
 
 
-def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=False):
+def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=False, exchange="auto"):
     """BASELINE.json configs[3]: U-Net training step (BCE+Dice, AdamW), bf16 tensor-core convs, `batch` samples per GPU,
     NCCL all-reduce of the flat fp32 gradient when world > 1. Returns a dict for the JSON line."""
     import torch
@@ -163,7 +166,7 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
     x_host = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
     y_host = (torch.rand(batch, 1, 224, 224, generator=g) < 0.085).float().pin_memory()   # 8.5 % positives (README.md:2534)
     x, y = x_host.to(dev), y_host.to(dev)
-    step = U.FusedTrainStep(net)                                        # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
+    step = U.FusedTrainStep(net, exchange=exchange)                     # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
     box = {}
 
     def run_dev():
@@ -182,7 +185,14 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
     out = {"metric": "unet224_train_samples_per_sec", "value": value, "unit": "samples/s", "ms_per_step": ms / steps,
            "batch_per_gpu": batch, "tflops_per_gpu": value / world * TRAIN_FLOPS_PER_SAMPLE / 1e12,
            "flops_per_sample": TRAIN_FLOPS_PER_SAMPLE, "loss_after": loss,
-           "collective": "none" if world == 1 else f"NCCL all-reduce(sum) of the flat fp32 gradient ({31037633 * 4 / 1e6:.0f} MB) per step",
+           "exchange": step.exchange,
+           "collective": "none" if world == 1 else (
+               f"NCCL all-reduce(sum) of the flat fp32 gradient ({31037633 * 4 / 1e6:.0f} MB) per step" if step.exchange == "nccl" else
+               "none: ONE kernel sums the owned gradient shard over the peers' buffers (NVLink loads), applies AdamW (ZeRO-1 "
+               "sharded state) and stores the parameters to all replicas (NVLink stores); two device-side barriers per step"
+               if step.exchange == "nvlink" else
+               "none: NVLink P2P gradient atomics to the owner replica inside the backward kernels, sharded AdamW, parameter "
+               "stores to all replicas; two device-side barriers per step"),
            "config": "BASELINE.json configs[3]: BCE+Dice (pos_weight 3), AdamW lr 1e-4 wd 1e-4, BatchNorm batch statistics per replica"}
     if host_inputs:
         run_host()
@@ -206,6 +216,9 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE.json headline (configs[1]); train: the training step of configs[3] as the metric")
     ap.add_argument("--train-batch", type=int, default=64, help="samples per GPU per training step (configs[3])")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink", "nvlink_push"],
+                    help="training, N > 1: gradient exchange (auto = nvlink when the ranks can map each other's memory). nvlink: one kernel = reduce-scatter by NVLink loads + sharded AdamW + "
+                         "all-gather by NVLink stores; nvlink_push: gradient atomics go to the owner GPU inside the backward kernels")
     ap.add_argument("--no-train", action="store_true", help="infer mode: skip the secondary training-step measurement")
     ap.add_argument("--hw", nargs=2, type=int, default=[224, 224], metavar=("H", "W"),
                     help="network input size; 480 640 = BASELINE.json configs[4] (camera resolution, use --batch 16 --chunk 16)")
@@ -230,7 +243,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU pipeline)")
-    torch.cuda.set_device(0 if "LOCAL_RANK" in os.environ and os.environ.get("UB_BENCH_PIN", "1") == "1" else int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(0 if PINNED else int(os.environ.get("LOCAL_RANK", "0")))
     dev = torch.device("cuda", torch.cuda.current_device())
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -268,7 +281,8 @@ def main():
         sampler = ClockSampler(index=int(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]) if rank == 0 else 0)
         if rank == 0:
             sampler.start()
-        tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True)
+        tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True,
+                           exchange=args.exchange)
         clocks = sampler.summary() if rank == 0 else None
         line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",

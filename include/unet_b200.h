@@ -199,6 +199,25 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4_dev, const
  * as params_dev) with the gradient of every parameter. Needs the activations of the preceding train_forward. */
 int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits_dev, const float* params_dev, float* grads_dev,
                              void* stream);
+/* Data-parallel training over NVLink without a separate collective (replaces loss.backward() + DDP all-reduce +
+ * optimizer.step() of README.md:2076-2079 when world > 1). The flat gradient is cut into `world` contiguous shards of
+ * S = roundup4(ceil(n/world)) elements, rank r owning [r*S, min(n,(r+1)*S)). Buffers are peer-mapped (torch symmetric
+ * memory / CUDA IPC): *_bases_dev are device arrays of the `world` base pointers as mapped in THIS process.
+ *
+ * push: train_backward_p2p sends every gradient atomic of the backward straight to the OWNER rank's buffer through
+ *   grad_bases_dev[owner], i.e. the reduce-scatter happens inside the wgrad / BN / bias epilogues. grads_local
+ *   (== grad_bases_dev[rank]) is NOT cleared here; adamw_step_p2p(grad_bases_dev = NULL) clears the owned shard after use.
+ * pull: plain train_backward into the local (peer-mapped) buffer, then adamw_step_p2p(grad_bases_dev != NULL) sums the
+ *   owned shard over all ranks' buffers with 16-byte NVLink loads.
+ * Either way AdamW runs on the owned shard only (optimizer state exists only for the shard, exp_avg*_shard_dev hold S
+ * elements) and stores the new values into EVERY rank's flat parameter buffer: the all-gather is those NVLink stores.
+ * The caller puts a device-side barrier across ranks between the backward and adamw_step_p2p, and after the latter. */
+int unet_b200_train_backward_p2p(unet_b200_trainer* t, const float* dlogits_dev, const float* params_dev, float* grads_local_dev,
+                                 float* const* grad_bases_dev, int world, void* stream);
+int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_bases_dev, int world, int rank,
+                             float* grads_local_dev, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev, long long n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale,
+                             void* stream);
 /* BCEDiceLoss (README.md:1855-1893): losses3_dev = {total, bce, dice}; dlogits_dev (optional) = d total / d logits.
  * target fp32, same shape as logits; scratch4_dev: 4 doubles. */
 int unet_b200_bce_dice_loss(const float* logits_dev, const float* target_dev, size_t n, float pos_weight, float bce_weight,

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, exchange="nccl"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -24,31 +24,52 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(8, 3, 32, 32, generator=g).cuda()
     y = (torch.rand(8, 1, 32, 32, generator=g) < 0.2).float().cuda()
-    step = U.FusedTrainStep(net, lr=1e-3)
-    for _ in range(3):
+    step = U.FusedTrainStep(net, lr=1e-3, exchange=exchange)
+    gsum = None
+    for i in range(3):
+        step.keep_grad_shard = i == 0
         losses = step.step(x, y)
+        if i == 0:   # summed gradient of the first step (parameters still identical to the single-GPU run)
+            if exchange != "nccl":
+                shards = [torch.empty_like(step.last_grad_shard) for _ in range(world)]
+                dist.all_gather(shards, step.last_grad_shard)
+                gsum = torch.cat(shards)[:step.nvlink.n].cpu()
+            else:
+                gsum = step.last_grads.clone().cpu()
+    torch.cuda.synchronize()
     flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     others = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(others, flat)
-    q.put((rank, float((others[0] - others[1]).abs().max()), flat.cpu(), losses.cpu()))
-    dist.destroy_process_group()
+    q.put((rank, float((others[0] - others[1]).abs().max()), flat.cpu(), losses.cpu(), gsum))
+    q.close()
+    q.join_thread()
+    try:
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
-def test_two_gpu_step_matches_single_gpu():
+@pytest.mark.parametrize("exchange", ["nccl", "nvlink", "nvlink_push"])
+def test_two_gpu_step_matches_single_gpu(exchange):
+    """nccl: all-reduce of the flat gradient; nvlink: sharded AdamW whose kernel sums the peers' gradient shards over NVLink
+    and stores the new parameters to all replicas (no collective call); nvlink_push: gradient atomics routed to the owner
+    replica inside the backward kernels instead."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 33500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 33500 + (os.getpid() % 2000) + {"nccl": 0, "nvlink": 7, "nvlink_push": 14}[exchange]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
     # replicas stay in lock step up to the run-to-run noise of fp32 atomics (identical all-reduced gradients are applied
     # to identical parameters; the only divergence is each replica's own forward nondeterminism in later steps)
-    assert res[0][1] < 5e-3, res[0][1]
+    assert res[0][1] < 2 * 3 * 1e-3 + 2e-4, res[0][1]
     # single-GPU reference in this process
     import unet_lane_detection_b200 as U
     torch.manual_seed(0)
@@ -57,8 +78,19 @@ def test_two_gpu_step_matches_single_gpu():
     x = torch.randn(8, 3, 32, 32, generator=g).cuda()
     y = (torch.rand(8, 1, 32, 32, generator=g) < 0.2).float().cuda()
     step = U.FusedTrainStep(net, lr=1e-3)
-    for _ in range(3):
+    g1 = None
+    for i in range(3):
         losses = step.step(x, y)
+        if i == 0:
+            g1 = step.last_grads.clone().cpu()
+    # the exchanged gradient of step 1 is world x the single-GPU gradient (same batch on both replicas): this is the
+    # parity check of the reduce-scatter fused into the backward kernels (nvlink) / of the all-reduce (nccl)
+    gerr = (res[0][4] - 2.0 * g1).abs().max().item() / (2.0 * g1.abs().max().item())
+    assert gerr < 2e-3, gerr
     flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
-    assert (flat - res[0][2]).abs().max().item() < 5e-3
+    # AdamW normalises every element's gradient to ~ +-lr per step, so an element whose gradient is at the fp32-atomics noise
+    # floor may move the other way: the worst case is 2*lr per step (3 steps -> 6e-3); on average the replicas agree far better
+    diff = (flat - res[0][2]).abs()
+    assert diff.max().item() < 2 * 3 * 1e-3 + 2e-4, diff.max().item()
+    assert diff.mean().item() < 5e-4, diff.mean().item()
     assert (losses.cpu() - res[0][3]).abs().max().item() < 5e-3

@@ -66,6 +66,8 @@ _SIGS = {
     "unet_b200_trainer_bind": (i32, [vp, vp]),
     "unet_b200_train_forward": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), f32, f32, vp, vp]),
     "unet_b200_train_backward": (i32, [vp, vp, vp, vp, vp]),
+    "unet_b200_train_backward_p2p": (i32, [vp, vp, vp, vp, vp, i32, vp]),
+    "unet_b200_adamw_step_p2p": (i32, [vp, vp, i32, i32, vp, vp, vp, C.c_longlong, f32, f32, f32, f32, f32, vp, f32, vp]),
     "unet_b200_bce_dice_loss": (i32, [vp, vp, sz, f32, f32, f32, f32, vp, vp, vp, vp]),
     "unet_b200_validation_metrics": (i32, [vp, vp, sz, f32, f32, f32, f32, f32, vp, vp, vp]),
     "unet_b200_adamw_step": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),

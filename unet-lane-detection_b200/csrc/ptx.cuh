@@ -208,6 +208,22 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);   // M / 16
 }
 
+// ---------------------------------------------------------------- gradient routing (data-parallel training)
+// Every parameter-gradient contribution is added with an fp32 atomic at `flat index` of the flat gradient. Single GPU: the
+// local buffer. Data parallel over NVLink: the flat gradient is cut into `world` contiguous shards; the atomic goes
+// STRAIGHT to the owner GPU's buffer through its peer-mapped pointer (red.global.add.f32 over NVLink), so the
+// reduce-scatter of the gradients happens inside the backward kernels - there is no separate collective.
+struct GradRoute {
+  float* const* bases;  // device array [world]: flat-gradient base pointer of every rank as mapped in THIS process; null = local only
+  float* local;         // this rank's flat gradient
+  unsigned shard;       // elements per owner shard (ceil(n / world)); unused when bases == null
+};
+__device__ __forceinline__ void grad_add(const GradRoute& r, long long idx, float v) {
+  float* base = r.local;
+  if (r.bases != nullptr) base = r.bases[static_cast<unsigned>(idx) / r.shard];
+  atomicAdd(base + idx, v);
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

@@ -18,7 +18,8 @@ struct StemWgradArgs {
   int B, H, W, Cin;
   int tiles_w, tiles_h;  // 8-pixel x 16-row tiles per image
   const uint2* x;        // [B,H,W] x 4 bf16
-  float* dw;             // fp32 [64][Cin][3][3], accumulated atomically
+  GradRoute route;       // gradient destination (ptx.cuh)
+  long long off;         // flat index of dW [64][Cin][3][3]
 };
 
 struct StemWgradCfg {
@@ -156,7 +157,7 @@ stem_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const StemWgradA
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int tp = k >> 2, ci = k & 3;
-          if (ci < a.Cin) atomicAdd(a.dw + (static_cast<size_t>(co) * a.Cin + ci) * 9 + tp, __uint_as_float(v[k]));
+          if (ci < a.Cin) grad_add(a.route, a.off + (static_cast<long long>(co) * a.Cin + ci) * 9 + tp, __uint_as_float(v[k]));
         }
       }
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col0 + 32, v);
@@ -164,7 +165,7 @@ stem_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const StemWgradA
       if (pairs > static_cast<int>(blockIdx.x)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // tap 8
-          if (k < a.Cin) atomicAdd(a.dw + (static_cast<size_t>(co) * a.Cin + k) * 9 + 8, __uint_as_float(v[k]));
+          if (k < a.Cin) grad_add(a.route, a.off + (static_cast<long long>(co) * a.Cin + k) * 9 + 8, __uint_as_float(v[k]));
         }
       }
     }

@@ -400,25 +400,28 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   return UB_OK;
 }
 
-// BatchNorm(train)+ReLU backward on c.g in place (dA -> dY). dbeta / dgamma are the (pre-zeroed) fp32 accumulators of
-// sum g and sum g*xhat - in the trainer they are the gradient slots of beta and gamma themselves.
-int conv_bn_backward(const TConv& c, int B, float* dgamma, float* dbeta, cudaStream_t st) {
+// BatchNorm(train)+ReLU backward on c.g in place (dA -> dY). The per-channel sums (sum g -> d beta, sum g*xhat -> d gamma)
+// are accumulated locally in s1 / s2 (zeroed by the caller) - the apply pass needs THIS replica's sums - and then published
+// into the flat gradient at off_gamma / off_beta through `route` (which may point at another GPU).
+int conv_bn_backward(const TConv& c, int B, float* s1, float* s2, const ub::GradRoute& route, long long off_gamma,
+                     long long off_beta, cudaStream_t st) {
   const size_t npix = (size_t)B * c.H * c.W;
   const int C8 = c.Cout / 8;
   const uint4* g4 = reinterpret_cast<const uint4*>(c.g);
   const uint4* y4 = reinterpret_cast<const uint4*>(c.y);
   ub::bn_relu_bwd_reduce_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
-                                                                                 C8, dbeta, dgamma);
+                                                                                 C8, s1, s2);
   UB_CUDA(cudaGetLastError());
   const size_t n8 = npix * C8;
-  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, dbeta, dgamma,
-                                                                  1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g));
+  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, s1, s2,
+                                                                  1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g), route,
+                                                                  off_gamma, off_beta);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
 // Weight gradient of one conv (3x3 on tensor cores, stem on tensor cores for Cout == 64), accumulated into dw (PyTorch layout).
-int conv_wgrad_launch(const TConv& c, int B, float* dw, cudaStream_t st) {
+int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long long off, cudaStream_t st) {
   if (c.stem && c.Cout == 64) {
     static int attr_done_tc = 0;
     if (!attr_done_tc) {
@@ -434,7 +437,8 @@ int conv_wgrad_launch(const TConv& c, int B, float* dw, cudaStream_t st) {
     sa.tiles_w = (c.W + 7) / 8;
     sa.tiles_h = (c.H + 15) / 16;
     sa.x = reinterpret_cast<const uint2*>(c.x0);
-    sa.dw = dw;
+    sa.route = route;
+    sa.off = off;
     const int pairs = (sa.tiles_w * sa.tiles_h * B + 1) / 2;
     const int grid = pairs < g_num_sms ? pairs : g_num_sms;
     ub::stem_wgrad_umma_kernel<<<grid, ub::StemWgradCfg::THREADS, ub::StemWgradCfg::SMEM_BYTES, st>>>(c.wD, sa);
@@ -452,21 +456,22 @@ int conv_wgrad_launch(const TConv& c, int B, float* dw, cudaStream_t st) {
     const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
     const int grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
     ub::stem_wgrad_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0),
-                                                    reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, dw);
+                                                    reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, route, off);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
   ub::WgradArgs wa = c.wa;
-  wa.dw = dw;
+  wa.route = route;
+  wa.off = off;
   const CUtensorMap d[4] = {c.wD, c.wD, c.wD, c.wD};
   return launch_wgrad(c.w_bn, c.wX0, c.wX1, d, wa, c.w_grid, st);
 }
 
-int trainer_conv_backward(unet_b200_trainer* t, TConv& c, float* grads, cudaStream_t st) {
+int trainer_conv_backward(unet_b200_trainer* t, TConv& c, const ub::GradRoute& route, cudaStream_t st) {
   const int B = t->B;
-  int rc = conv_bn_backward(c, B, grads + c.gamma_off, grads + c.beta_off, st);
+  int rc = conv_bn_backward(c, B, c.s1, c.s2, route, c.gamma_off, c.beta_off, st);
   if (rc != UB_OK) return rc;
-  rc = conv_wgrad_launch(c, B, grads + c.w_off, st);
+  rc = conv_wgrad_launch(c, B, route, c.w_off, st);
   if (rc != UB_OK) return rc;
   if (c.dx != nullptr) {
     rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st);
@@ -476,16 +481,18 @@ int trainer_conv_backward(unet_b200_trainer* t, TConv& c, float* grads, cudaStre
 }
 
 // ConvT backward pieces on prepared maps: bias gradient + weight gradient, and the input gradient.
-int up_wgrad_launch(const TConvT& u, int B, int pitch8, float* dw, float* dbias, cudaStream_t st) {
+int up_wgrad_launch(const TConvT& u, int B, int pitch8, const ub::GradRoute& route, long long off_w, long long off_b,
+                    cudaStream_t st) {
   const size_t npix_up = (size_t)B * 4 * u.H * u.W;
   const int C8 = u.f / 8;
-  if (dbias != nullptr) {
+  if (off_b >= 0) {
     ub::chan_sum_kernel<<<chan_grid(npix_up, C8), 256, 2048 * 4, st>>>(reinterpret_cast<const uint4*>(u.dup), pitch8, npix_up, C8,
-                                                                       dbias);
+                                                                       route, off_b);
     UB_CUDA(cudaGetLastError());
   }
   ub::WgradArgs wa = u.wa;
-  wa.dw = dw;
+  wa.route = route;
+  wa.off = off_w;
   return launch_wgrad(u.w_bn, u.wX, u.wX, u.wDq, wa, u.w_grid, st);
 }
 
@@ -497,8 +504,8 @@ int up_dgrad_launch(const TConvT& u, int B, const float* zero_bias, cudaStream_t
   return launch_conv(u.dg.block_n, u.dgA, u.dg.mW, u.dg.mO, a, st);
 }
 
-int trainer_up_backward(unet_b200_trainer* t, TConvT& u, float* grads, cudaStream_t st) {
-  int rc = up_wgrad_launch(u, t->B, 2 * (u.f / 8), grads + u.w_off, grads + u.b_off, st);
+int trainer_up_backward(unet_b200_trainer* t, TConvT& u, const ub::GradRoute& route, cudaStream_t st) {
+  int rc = up_wgrad_launch(u, t->B, 2 * (u.f / 8), route, u.w_off, u.b_off, st);
   if (rc != UB_OK) return rc;
   return up_dgrad_launch(u, t->B, t->zero_bias, st);
 }
@@ -709,33 +716,35 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   return UB_OK;
 }
 
-int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads, void* stream) {
-  if (t == nullptr || dlogits == nullptr || params == nullptr || grads == nullptr) return fail(UB_ERR_ARG, "null argument");
+static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const float* params, const ub::GradRoute& route,
+                               bool zero_local, cudaStream_t st) {
+  if (t == nullptr || dlogits == nullptr || params == nullptr || route.local == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (!t->fwd_done) return fail(UB_ERR_STATE, "train_backward needs a preceding train_forward");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = t->B, L = t->levels;
-  UB_CUDA(cudaMemsetAsync(grads, 0, (size_t)t->n_params * 4, st));
+  if (zero_local) UB_CUDA(cudaMemsetAsync(route.local, 0, (size_t)t->n_params * 4, st));
+  // s1 received the pack kernels' (all-zero) bias in the forward and s2 was cleared with the accumulator region: both are
+  // zero here, once per forward/backward pair
   TConv& last = t->convs.back();
   {
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
     ub::head_bwd_kernel<<<chan_grid(npix, C8), 256, (2048 + 256) * 4, st>>>(
-        reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g),
-        grads + t->head_w_off, grads + t->head_b_off);
+        reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g), route,
+        t->head_w_off, t->head_b_off);
     UB_CUDA(cudaGetLastError());
   }
   int rc;
   for (int j = L - 1; j >= 0; --j) {
-    rc = trainer_conv_backward(t, t->convs[2 * L + 3 + 2 * j], grads, st);
+    rc = trainer_conv_backward(t, t->convs[2 * L + 3 + 2 * j], route, st);
     if (rc != UB_OK) return rc;
-    rc = trainer_conv_backward(t, t->convs[2 * L + 2 + 2 * j], grads, st);
+    rc = trainer_conv_backward(t, t->convs[2 * L + 2 + 2 * j], route, st);
     if (rc != UB_OK) return rc;
-    rc = trainer_up_backward(t, t->ups[j], grads, st);
+    rc = trainer_up_backward(t, t->ups[j], route, st);
     if (rc != UB_OK) return rc;
   }
-  rc = trainer_conv_backward(t, t->convs[2 * L + 1], grads, st);
+  rc = trainer_conv_backward(t, t->convs[2 * L + 1], route, st);
   if (rc != UB_OK) return rc;
-  rc = trainer_conv_backward(t, t->convs[2 * L], grads, st);
+  rc = trainer_conv_backward(t, t->convs[2 * L], route, st);
   if (rc != UB_OK) return rc;
   for (int i = L - 1; i >= 0; --i) {
     TConv& c1 = t->convs[2 * i + 1];
@@ -747,12 +756,49 @@ int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits, const f
         reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
         2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
     UB_CUDA(cudaGetLastError());
-    rc = trainer_conv_backward(t, c1, grads, st);
+    rc = trainer_conv_backward(t, c1, route, st);
     if (rc != UB_OK) return rc;
-    rc = trainer_conv_backward(t, t->convs[2 * i], grads, st);
+    rc = trainer_conv_backward(t, t->convs[2 * i], route, st);
     if (rc != UB_OK) return rc;
   }
   t->fwd_done = false;
+  return UB_OK;
+}
+
+int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads, void* stream) {
+  ub::GradRoute route{nullptr, grads, 0u};
+  return train_backward_impl(t, dlogits, params, route, true, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_train_backward_p2p(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads_local,
+                                 float* const* grad_bases_dev, int world, void* stream) {
+  if (grad_bases_dev == nullptr || world < 1) return fail(UB_ERR_ARG, "bad peer table");
+  if (t == nullptr) return fail(UB_ERR_ARG, "null argument");
+  const unsigned shard = (unsigned)(((t->n_params + world - 1) / world + 3) / 4 * 4);   // as in adamw_step_p2p
+  ub::GradRoute route{grad_bases_dev, grads_local, shard};
+  return train_backward_impl(t, dlogits, params, route, false, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_bases_dev, int world, int rank,
+                             float* grads_local, float* exp_avg_shard,
+                             float* exp_avg_sq_shard, long long n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+  if (param_bases_dev == nullptr || grads_local == nullptr || exp_avg_shard == nullptr || exp_avg_sq_shard == nullptr ||
+      step_dev == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  if (world < 1 || rank < 0 || rank >= world) return fail(UB_ERR_ARG, "bad rank / world");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  const long long shard = ((n + world - 1) / world + 3) / 4 * 4;   // multiple of 4: 16-byte accesses stay aligned
+  const long long lo = shard * rank;
+  long long hi = lo + shard;
+  if (hi > n) hi = n;
+  if (hi <= lo) return UB_OK;
+  ub::adamw_shard_allgather_kernel<<<grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param_bases_dev, grad_bases_dev, world, rank, grads_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay,
+      grad_scale, step_dev);
+  UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
@@ -850,7 +896,7 @@ int unet_b200_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, cons
   c.g = static_cast<uint8_t*>(const_cast<void*>(dy));
   rc = setup_conv_wgrad(c, B);
   if (rc != UB_OK) return rc;
-  return conv_wgrad_launch(c, B, dw, static_cast<cudaStream_t>(stream));
+  return conv_wgrad_launch(c, B, ub::GradRoute{nullptr, dw, 0u}, 0, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_stem_wgrad(const void* x4, const void* dy, int B, int H, int W, int Cin, int Cout, float* dw, void* stream) {
@@ -871,7 +917,7 @@ int unet_b200_stem_wgrad(const void* x4, const void* dy, int B, int H, int W, in
     rc = make_box_map(&c.wD, c.g, B, H, W, 64, 8, 16);
     if (rc != UB_OK) return rc;
   }
-  return conv_wgrad_launch(c, B, dw, static_cast<cudaStream_t>(stream));
+  return conv_wgrad_launch(c, B, ub::GradRoute{nullptr, dw, 0u}, 0, static_cast<cudaStream_t>(stream));
 }
 
 int unet_b200_convT2x2_wgrad(const void* x, int Cin, const void* dup, int dup_pitch, int B, int H, int W, int f, float* dw,
@@ -890,7 +936,15 @@ int unet_b200_convT2x2_wgrad(const void* x, int Cin, const void* dup, int dup_pi
   u.dup = static_cast<uint8_t*>(const_cast<void*>(dup));
   rc = setup_up_backward(u, B, (size_t)dup_pitch);
   if (rc != UB_OK) return rc;
-  return up_wgrad_launch(u, B, dup_pitch / 8, dw, dbias, static_cast<cudaStream_t>(stream));
+  // dw and dbias are separate caller buffers: two local routes
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dbias != nullptr) {
+    const size_t npix_up = (size_t)B * 4 * H * W;
+    ub::chan_sum_kernel<<<chan_grid(npix_up, f / 8), 256, 2048 * 4, st>>>(reinterpret_cast<const uint4*>(u.dup), dup_pitch / 8,
+                                                                          npix_up, f / 8, ub::GradRoute{nullptr, dbias, 0u}, 0);
+    UB_CUDA(cudaGetLastError());
+  }
+  return up_wgrad_launch(u, B, dup_pitch / 8, ub::GradRoute{nullptr, dw, 0u}, 0, -1, st);
 }
 
 int unet_b200_convT2x2_dgrad(const void* dup, int dup_pitch, const void* wd, int B, int H, int W, int Cin, int f, void* dx,
@@ -970,7 +1024,8 @@ int unet_b200_bn_relu_bwd(void* g, const void* y, const float* stats4, int B, in
   c.shift = s4 + 3 * C;
   UB_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
   UB_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
-  return conv_bn_backward(c, B, dgamma, dbeta, st);
+  // the outputs double as the local accumulators; nothing to publish
+  return conv_bn_backward(c, B, dbeta, dgamma, ub::GradRoute{nullptr, nullptr, 0u}, 0, 0, st);
 }
 
 int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, int skip_pitch, int B, int H, int W, int C,

@@ -223,7 +223,15 @@ __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__ y, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ s1, const float* __restrict__ s2,
-                         float inv_count, size_t n8, int C8, uint4* __restrict__ dY) {
+                         float inv_count, size_t n8, int C8, uint4* __restrict__ dY, GradRoute route, long long off_gamma,
+                         long long off_beta) {
+  // block 0 also publishes d gamma = sum g*xhat (s2) and d beta = sum g (s1) into the (possibly remote) flat gradient
+  if (blockIdx.x == 0 && route.local != nullptr) {
+    for (int ch = threadIdx.x; ch < C8 * 8; ch += blockDim.x) {
+      grad_add(route, off_gamma + ch, s2[ch]);
+      grad_add(route, off_beta + ch, s1[ch]);
+    }
+  }
   const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const int c = static_cast<int>(i0 % C8) * 8;
   float sc[8], sh[8], k1[8], k0[8];
@@ -329,7 +337,7 @@ head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, 
 // Head backward: dA[p][c] = dz[p] * w[c] (bf16);  dw[c] += sum_p dz[p] * a[p][c];  db += sum_p dz[p]
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
-                uint4* __restrict__ dA, float* __restrict__ dw, float* __restrict__ db) {
+                uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b) {
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -357,12 +365,12 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
   for (int c = threadIdx.x; c < C8 * 8; c += 256) {
     float s = 0.f;
     for (int j = 0; j < ppb; ++j) s += red[(j * C8 + c / 8) * 8 + (c & 7)];
-    atomicAdd(dw + c, s);
+    grad_add(route, off_w + c, s);
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int j = 0; j < 256; ++j) s += red[2048 + j];
-    atomicAdd(db, s);
+    grad_add(route, off_b, s);
   }
 }
 
@@ -491,6 +499,76 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// Data-parallel AdamW over NVLink (ZeRO-1 style): this rank owns flat elements [lo, hi) (lo a multiple of 4). The step is
+// applied to the owned shard only - optimizer state exists only for the shard - and the new parameter value is stored into
+// EVERY rank's parameter buffer through the peer-mapped pointers (the all-gather is these stores). Two ways to get the
+// summed gradient of the shard:
+//  * push (grad_bases == null): the backward kernels already added every replica's contribution straight into the owner's
+//    buffer (GradRoute); `grads` holds the sum and is cleared here for the next step;
+//  * pull (grad_bases != null): every replica accumulated locally; the sum over ranks is formed here from coalesced 16-byte
+//    loads of the peers' buffers over NVLink (the reduce-scatter is these loads). Nothing is cleared (the next backward
+//    zeroes its local buffer after the closing barrier).
+__device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, float lr, float wd, float beta1, float beta2,
+                                           float eps, float step_size, float inv_sqrt_bc2) {
+  float pi = p * (1.f - lr * wd);
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  pi -= step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+  p = pi;
+  return pi;
+}
+
+__global__ void __launch_bounds__(256)
+adamw_shard_allgather_kernel(float* const* __restrict__ param_bases, float* const* __restrict__ grad_bases, int world, int rank,
+                             float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v, long long lo, long long hi,
+                             float lr, float beta1, float beta2, float eps, float wd, float grad_scale,
+                             const int* __restrict__ step_dev) {
+  const float st = static_cast<float>(*step_dev);
+  const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  float* plocal = param_bases[rank];
+  const long long n4 = (hi - lo) / 4;   // full float4 groups; the (< 4 element) tail of the last shard is done by block 0
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = lo + 4 * q;
+    float4 g;
+    if (grad_bases != nullptr) {
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {
+        const float4 t = *reinterpret_cast<const float4*>(grad_bases[(rank + r) % world] + i);   // own buffer first
+        g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
+      }
+    } else {
+      g = *reinterpret_cast<const float4*>(grads + i);
+      *reinterpret_cast<float4*>(grads + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 p4 = *reinterpret_cast<const float4*>(plocal + i);
+    float4 m4 = *reinterpret_cast<const float4*>(m + 4 * q);
+    float4 v4 = *reinterpret_cast<const float4*>(v + 4 * q);
+    adamw_one(p4.x, g.x * grad_scale, m4.x, v4.x, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.y, g.y * grad_scale, m4.y, v4.y, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.z, g.z * grad_scale, m4.z, v4.z, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.w, g.w * grad_scale, m4.w, v4.w, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    *reinterpret_cast<float4*>(m + 4 * q) = m4;
+    *reinterpret_cast<float4*>(v + 4 * q) = v4;
+    for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(param_bases[(rank + r) % world] + i) = p4;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = lo + 4 * n4 + threadIdx.x; i < hi; i += blockDim.x) {
+      float g = 0.f;
+      if (grad_bases != nullptr) {
+        for (int r = 0; r < world; ++r) g += grad_bases[r][i];
+      } else {
+        g = grads[i];
+        grads[i] = 0.f;
+      }
+      float pi = plocal[i];
+      adamw_one(pi, g * grad_scale, m[i - lo], v[i - lo], lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+      for (int r = 0; r < world; ++r) param_bases[r][i] = pi;
+    }
+  }
+}
+
 // dgrad weights: wd[ci][tap'][co] = w[co][ci][8 - tap'] (180-degree rotated, in/out swapped), bf16; w fp32 [Cout][Cin][3][3]
 __global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wd) {
   const int total = Cin * 9 * Cout;
@@ -535,7 +613,7 @@ __global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, 
 
 // per-channel sum of a bf16 NHWC tensor (ConvT bias gradient): out[c] += sum_p x[p][c]
 __global__ void __launch_bounds__(256)
-chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, float* __restrict__ out) {
+chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, GradRoute route, long long off) {
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -553,7 +631,7 @@ chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, s
   for (int c = threadIdx.x; c < C8 * 8; c += 256) {
     float a = 0.f;
     for (int j = 0; j < ppb; ++j) a += red[(j * C8 + c / 8) * 8 + (c & 7)];
-    atomicAdd(out + c, a);
+    grad_add(route, off + c, a);
   }
 }
 
@@ -562,7 +640,7 @@ chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, s
 // channels in registers across ALL its tiles and flushes them with one atomicAdd each at the end.
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const uint2* __restrict__ x4, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int Cin, int Cout,
-                  float* __restrict__ dw /* fp32 [Cout][Cin][3][3] */) {
+                  GradRoute route, long long off /* dW fp32 [Cout][Cin][3][3] */) {
   extern __shared__ float sm[];
   float4* st = reinterpret_cast<float4*>(sm);                 // [18][18] input pixels (4 ch fp32)
   float* sd = sm + 18 * 18 * 4;                                // [256 px][Cout] dy tile (fp32)
@@ -623,7 +701,7 @@ stem_wgrad_kernel(const uint2* __restrict__ x4, const __nv_bfloat16* __restrict_
     const int item = threadIdx.x + k * 256;
     if (item < n_items) {
       const int co = item % Cout, tap = item / Cout;
-      for (int ci = 0; ci < Cin; ++ci) atomicAdd(dw + (static_cast<size_t>(co) * Cin + ci) * 9 + tap, acc[k][ci]);
+      for (int ci = 0; ci < Cin; ++ci) grad_add(route, off + (static_cast<long long>(co) * Cin + ci) * 9 + tap, acc[k][ci]);
     }
   }
 }

@@ -35,7 +35,8 @@ struct WgradArgs {
   int a_bytes;                    // bytes one x / dy box load delivers (box rows * 128; fewer rows when TB exceeds the batch)
   int blk_bytes;                  // shared-memory pitch of one 64-channel box (full box rows * 128) = LBO of the descriptors
   int stages;                     // operand ring depth chosen by the host (<= WGRAD_MAX_STAGES)
-  float* dw;                      // fp32 gradient, accumulated atomically
+  GradRoute route;                // where gradient atomics go (local buffer, or the owner rank's buffer over NVLink)
+  long long off;                  // flat index of this tensor's first element
 };
 
 constexpr int WGRAD_MAX_STAGES = 8;
@@ -203,7 +204,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       ci = m & 63;
       live = live && tap < a.taps;
     }
-    float* base = a.dw + static_cast<long long>(tap) * a.s_tap + static_cast<long long>(ci) * a.s_ci;
+    const long long base = a.off + static_cast<long long>(tap) * a.s_tap + static_cast<long long>(ci) * a.s_ci;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t v[32];
@@ -213,7 +214,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int co = n_tile * BLOCK_N + c * 32 + j;
-          atomicAdd(base + static_cast<long long>(co) * a.s_co, __uint_as_float(v[j]));
+          grad_add(a.route, base + static_cast<long long>(co) * a.s_co, __uint_as_float(v[j]));
         }
       }
     }

@@ -45,9 +45,10 @@ class _TrainEngine:
             self.handle = None
 
 
-def flatten_parameters_(model):
+def flatten_parameters_(model, alloc=None):
     """Make every parameter of `model` a view into one contiguous fp32 buffer (parameters() order) and return it.
-    Parameter objects keep their identity, so optimizers created before or after stay valid."""
+    Parameter objects keep their identity, so optimizers created before or after stay valid. `alloc(n, device)` lets the
+    caller place the buffer (e.g. in NVLink-shared symmetric memory); once placed, later calls keep it."""
     params = list(model.parameters())
     flat = getattr(model, "_b200_flat", None)
     off, ok = 0, flat is not None
@@ -61,7 +62,8 @@ def flatten_parameters_(model):
     if ok:
         return flat
     dev = params[0].device
-    flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    n_total = sum(p.numel() for p in params)
+    flat = alloc(n_total, dev) if alloc is not None else torch.empty(n_total, dtype=torch.float32, device=dev)
     off = 0
     with torch.no_grad():
         for p in params:
@@ -177,6 +179,92 @@ def allreduce_gradients(flat_grads, group=None):
     return 1.0 / world
 
 
+def _pick_exchange(group=None):
+    """'nvlink' if every rank of `group` can map every other rank's memory (one host, same set of visible GPUs, one
+    distinct device per rank), else 'nccl'. The same answer on every rank (decided from an all-gather)."""
+    import os
+    import socket
+    if not torch.cuda.is_available() or dist.get_backend(group) != "nccl":
+        return "nccl"   # i.e. dist.all_reduce on whatever backend the group has (gloo in the CPU tests)
+    me = (socket.gethostname(), os.environ.get("CUDA_VISIBLE_DEVICES", ""), torch.cuda.current_device(), torch.cuda.device_count())
+    world = dist.get_world_size(group)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, me, group=group)
+    same_view = len({(h, v, n) for h, v, _, n in everyone}) == 1
+    distinct = len({d for _, _, d, _ in everyone}) == world
+    return "nvlink" if same_view and distinct else "nccl"
+
+
+class NvlinkExchange:
+    """Gradient exchange without a collective call (one process per GPU, NVLink / NVSwitch peer access):
+
+    * the flat gradient and the flat parameters live in torch symmetric memory, so every rank holds the peer-mapped base
+      pointers of all replicas;
+    * backward: every gradient atomic goes straight to the OWNER rank's gradient shard (GradRoute in csrc/ptx.cuh) -
+      the reduce-scatter is fused into the wgrad / BN / bias-gradient kernels;
+    * device-side barrier (symmetric-memory signal pads, on the stream);
+    * AdamW on the owned shard only (ZeRO-1: moments exist only for the shard) whose stores go to ALL replicas'
+      parameter buffers - the all-gather is fused into the optimizer kernel; then a second barrier.
+
+    Per step and GPU: (world-1)/world of 124 MB leaves over NVLink during the backward and the same again during the
+    optimizer, fully overlapped with compute; NCCL's ring all-reduce moves twice that after the backward has finished."""
+
+    def __init__(self, model, group=None, mode="pull"):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.mode = mode
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        params = list(model.parameters())
+        dev = params[0].device
+        self.n = sum(p.numel() for p in params)
+        self.shard = ((self.n + self.world - 1) // self.world + 3) // 4 * 4   # as unet_b200_adamw_step_p2p cuts it
+        # parameters: symmetric, identical on every rank (rank 0's values win, as DDP does at construction)
+        if getattr(model, "_b200_flat_symm", None) is None:
+            model._b200_flat = None
+            flat = flatten_parameters_(model, alloc=lambda n, d: symm_mem.empty(n, dtype=torch.float32, device=d))
+            model._b200_flat_symm = symm_mem.rendezvous(flat, self.group)
+        self.params = flatten_parameters_(model)
+        self.hdl_p = model._b200_flat_symm
+        dist.broadcast(self.params, src=dist.get_global_rank(self.group, 0), group=self.group)
+        self.grads = symm_mem.empty(self.shard * self.world, dtype=torch.float32, device=dev)
+        self.grads.zero_()
+        self.hdl_g = symm_mem.rendezvous(self.grads, self.group)
+        self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def backward(self, model, eng, dlogits):
+        st = torch.cuda.current_stream().cuda_stream
+        if self.mode == "push":
+            check(lib.unet_b200_train_backward_p2p(eng.handle, dlogits.data_ptr(), self.params.data_ptr(), self.grads.data_ptr(),
+                                                   self.hdl_g.buffer_ptrs_dev, self.world, st))
+        else:
+            check(lib.unet_b200_train_backward(eng.handle, dlogits.data_ptr(), self.params.data_ptr(), self.grads.data_ptr(), st))
+        self.hdl_g.barrier(channel=0)      # push: every replica's atomics have landed; pull: every replica's gradient is complete
+
+    def optimizer_step(self, step_dev, lr, betas, eps, weight_decay):
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.unet_b200_adamw_step_p2p(self.hdl_p.buffer_ptrs_dev, self.hdl_g.buffer_ptrs_dev if self.mode == "pull" else None,
+                                           self.world, self.rank, self.grads.data_ptr(),
+                                           self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.n, float(lr), float(betas[0]),
+                                           float(betas[1]), float(eps), float(weight_decay), step_dev.data_ptr(),
+                                           1.0 / self.world, st))
+        # every replica holds the new parameters before the next forward reads them (pull: and nobody still reads this
+        # replica's gradient when the next backward clears it)
+        self.hdl_p.barrier(channel=1)
+
+    def reduced_shard(self):
+        """Sum over replicas of this rank's gradient shard, valid between backward() and optimizer_step() (tests)."""
+        lo, hi = self.rank * self.shard, (self.rank + 1) * self.shard
+        if self.mode == "push":
+            return self.grads[lo:hi].clone()
+        full = [torch.empty_like(self.grads) for _ in range(self.world)]
+        dist.all_gather(full, self.grads, group=self.group)
+        return torch.stack(full).sum(0)[lo:hi]
+
+
 class FusedTrainStep:
     """zero_grad -> forward -> BCEDiceLoss -> backward -> (all-reduce) -> AdamW.step, README.md:2071-2079 with the
     criterion / optimizer of README.md:2169-2174, all on the B200 kernels. Data-parallel: pass a process group (or
@@ -188,7 +276,20 @@ class FusedTrainStep:
     either way. `lr` may be changed between steps (a scheduler): the graph is re-captured for the new value."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, bce_weight=0.5, dice_weight=0.5,
-                 pos_weight=3.0, smooth=1e-6, process_group=None, cuda_graph=True):
+                 pos_weight=3.0, smooth=1e-6, process_group=None, cuda_graph=True, exchange="auto"):
+        """exchange (world > 1):
+        "nvlink"      no collective call: ONE kernel sums the owned gradient shard over the peers' buffers (NVLink loads),
+                      applies AdamW on it (ZeRO-1: moments exist only for the shard) and stores the new parameters to all
+                      replicas (NVLink stores); two device-side barriers per step, all of it inside the CUDA graph;
+        "nvlink_push" gradient atomics go to the owner replica inside the backward kernels instead (measured slower: the
+                      4-byte remote atomics of the wgrad epilogues are not coalesced);
+        "nccl"        one all-reduce of the flat gradient after the backward, full AdamW on every replica;
+        "auto"        nvlink when every rank of the group sits on its own visible GPU of one host (peer mapping possible),
+                      else nccl (e.g. processes pinned with CUDA_VISIBLE_DEVICES to one device each)."""
+        if exchange not in ("auto", "nccl", "nvlink", "nvlink_push"):
+            raise ValueError("exchange must be 'auto', 'nccl', 'nvlink' or 'nvlink_push'")
+        self.exchange = exchange
+        self.nvlink = None
         self.model = model
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.loss_cfg = dict(pos_weight=pos_weight, bce_weight=bce_weight, dice_weight=dice_weight, smooth=smooth)
@@ -199,6 +300,8 @@ class FusedTrainStep:
         self.exp_avg = None
         self.exp_avg_sq = None
         self.last_grads = None
+        self.keep_grad_shard = False   # nvlink exchange: keep a copy of the reduced gradient shard of every step (tests)
+        self.last_grad_shard = None
         self._graphs = {}
         self._seen = set()
 
@@ -206,6 +309,14 @@ class FusedTrainStep:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def _prepare(self, device):
+        if self.exchange == "auto":
+            self.exchange = "nccl" if self._world() == 1 else _pick_exchange(self.group)
+        if self.exchange != "nccl" and self.nvlink is None and self._world() > 1:
+            self.nvlink = NvlinkExchange(self.model, self.group, mode="push" if self.exchange == "nvlink_push" else "pull")
+            self.step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=device)
+            self.exp_avg, self.exp_avg_sq = self.nvlink.exp_avg, self.nvlink.exp_avg_sq
+        if self.nvlink is not None:
+            return flatten_parameters_(self.model)
         flat = flatten_parameters_(self.model)
         if self.exp_avg is None or self.exp_avg.numel() != flat.numel() or self.exp_avg.device != flat.device:
             self.exp_avg = torch.zeros_like(flat)
@@ -227,6 +338,13 @@ class FusedTrainStep:
         flat = flatten_parameters_(model)
         eng, logits = train_forward(model, x4)
         losses, dz = bce_dice_loss(logits, masks.reshape(logits.shape), **self.loss_cfg)
+        if self.nvlink is not None:
+            self.nvlink.backward(model, eng, dz)
+            if self.keep_grad_shard:
+                self.last_grad_shard = self.nvlink.reduced_shard()
+            self.step_dev.add_(1)
+            self.nvlink.optimizer_step(self.step_dev, self.lr, self.betas, self.eps, self.weight_decay)
+            return losses, self.nvlink.grads
         grads = train_backward(model, eng, dz)
         grad_scale = allreduce_gradients(grads, self.group)
         self.step_dev.add_(1)
@@ -250,7 +368,8 @@ class FusedTrainStep:
         key = (tuple(images.shape), images.dtype, tuple(masks.shape), flat.data_ptr(), float(self.lr), float(self.weight_decay),
                tuple(self.betas), float(self.eps))
         self.step_count += 1
-        if not self.cuda_graph or key not in self._seen:
+        use_graph = self.cuda_graph
+        if not use_graph or key not in self._seen:
             self._seen.add(key)                    # first step of a configuration: eager (creates engines, sets attributes)
             losses, self.last_grads = self._run(images, masks)
         else:
@@ -279,13 +398,19 @@ class FusedTrainStep:
         (the 'optimizer_state_dict' of README.md:2208-2213), so either optimizer can resume from the other's file."""
         params = list(self.model.parameters())
         state = {}
-        if self.exp_avg is not None and self.step_count > 0:
+        exp_avg, exp_avg_sq = self.exp_avg, self.exp_avg_sq
+        if self.nvlink is not None:   # moments are sharded over the replicas: gather them for the checkpoint
+            full = [torch.empty(self.nvlink.shard * self.nvlink.world, dtype=torch.float32, device=exp_avg.device) for _ in range(2)]
+            dist.all_gather_into_tensor(full[0], self.exp_avg, group=self.group)
+            dist.all_gather_into_tensor(full[1], self.exp_avg_sq, group=self.group)
+            exp_avg, exp_avg_sq = full
+        if exp_avg is not None and self.step_count > 0:
             off = 0
             for i, p in enumerate(params):
                 n = p.numel()
                 state[i] = {"step": torch.tensor(float(self.step_count)),
-                            "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
-                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+                            "exp_avg": exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": exp_avg_sq[off:off + n].view(p.shape).clone()}
                 off += n
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
