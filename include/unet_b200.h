@@ -274,6 +274,30 @@ int unet_b200_bn_relu_bwd(void* g_dev, const void* y_dev, const float* stats4_de
 int unet_b200_maxpool2x2_bwd(const void* a_dev, const void* dP_dev, const void* dskip_dev, int skip_pitch, int B, int H,
                              int W, int C, void* dA_dev, void* stream);
 
+/* ---- split-precision ("fp32-class") layers: the 1e-4 logit gate of the fp32 path (BASELINE.json north_star) -------------
+ * Replaces the same reference ops as the bf16 entry points above (README.md:1449-1458 conv block, :1441-1443 ConvT,
+ * :1429 pool) at higher precision. Every activation and (BN-folded) weight v is carried as two bf16 numbers
+ * hi = bf16(v), lo = bf16(v - hi); a product is hi*hi + lo*hi + hi*lo accumulated in fp32 on the tensor cores (the same
+ * tcgen05 implicit-GEMM kernel, three K passes). Activation tensors are bf16 [B,H,W,2C] = [hi C | lo C].
+ * C0 / C1 / Cin / Cout / f are LOGICAL channel counts (multiples of 64). */
+int unet_b200_pack_conv3x3_split(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* mean_dev,
+                                 const float* var_dev, float eps, int Cout, int C0, int C1, void* wp_dev /* bf16 [Cout][9][3*(C0+C1)] */,
+                                 float* bias_dev, void* stream);
+int unet_b200_conv3x3_split(const void* x0_dev, int C0, const void* x1_dev, int C1, const void* wp_dev, const float* bias_dev,
+                            int B, int H, int W, int Cout, int relu, void* y_dev /* [B,H,W,2*Cout] */, void* stream);
+int unet_b200_pack_convT2x2_split(const float* w_dev, int Cin, int f, void* wp_dev /* bf16 [4f][3*Cin] */, void* stream);
+int unet_b200_convT2x2_split(const void* x_dev, int Cin, const void* wp_dev, const float* bias_dev, int B, int H, int W, int f,
+                             void* y_dev /* [B,2H,2W,2f] */, void* stream);
+/* Stem on the fp32 pipes straight from the module's fp32 NCHW input; weights from unet_b200_pack_stem_fp32 (same layout as
+ * unet_b200_pack_stem, [9][4][Cout] fp32, without the bf16 rounding). */
+int unet_b200_pack_stem_fp32(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* mean_dev,
+                             const float* var_dev, float eps, int Cout, int Cin, float* ws_dev, float* bias_dev, void* stream);
+int unet_b200_stem_conv_split(const float* x_nchw_dev, const float* ws_dev, const float* bias_dev, int B, int H, int W, int Cin,
+                              int Cout, int relu, void* y_dev /* [B,H,W,2*Cout] */, void* stream);
+/* 2x2/2 max-pool on hi + lo; x [B,H,W,2C] -> y [B,H/2,W/2,2C]. The head is unet_b200_head with C = 2*f0 and the weight
+ * vector repeated twice. */
+int unet_b200_maxpool2x2_split(const void* x_dev, int B, int H, int W, int C, void* y_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

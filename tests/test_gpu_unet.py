@@ -238,3 +238,78 @@ def test_deployed_topology_32_64_128(U, golden_dir, tmp_path):
         want = torch.sigmoid(ref(torch.from_numpy(O.normalize_oracle(frame)))).numpy()
     assert out.shape == (1, 1, 224, 224) and np.abs(out - want).max() <= 2e-2
     box.release()
+
+
+# ---------------------------------------------------------------- fp32-class path (split-bf16 x3 on the tensor cores)
+LOGIT_TOL_FP32 = 1e-4   # BASELINE.json north_star: logits within 1e-4 on the fp32 path
+
+
+def _split(t):
+    """fp32 NHWC -> bf16 [.., 2C] = [hi | lo]."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def _join(t):
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
+
+
+def test_split_layers_against_torch_fp32(U):
+    """Every split-precision layer entry point against the fp32 torch op on the values the kernel actually sees."""
+    import torch.nn.functional as F
+    ops = U.ops
+    g = torch.Generator().manual_seed(7)
+    B, H, W = 3, 12, 20
+    x0 = torch.randn(B, H, W, 64, generator=g)
+    x1 = torch.randn(B, H, W, 128, generator=g)
+    w = torch.randn(128, 192, 3, 3, generator=g) * 0.05
+    s0, s1 = _split(x0).cuda(), _split(x1).cuda()
+    wp, bias = ops.pack_conv3x3_split(w.cuda(), None, c0=64)
+    y = _join(ops.conv3x3_split(s0, wp, bias, x1=s1, relu=True).cpu())
+    xin = torch.cat([_join(s0.cpu()), _join(s1.cpu())], dim=-1).permute(0, 3, 1, 2).double()
+    ref = F.relu(F.conv2d(xin, w.double(), padding=1)).permute(0, 2, 3, 1).float()
+    assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    # ConvT
+    wt = torch.randn(128, 64, 2, 2, generator=g) * 0.1
+    bt = torch.randn(64, generator=g)
+    up = _join(ops.convT2x2_split(s1, ops.pack_convT2x2_split(wt.cuda()), bt.cuda()).cpu())
+    ref = F.conv_transpose2d(_join(s1.cpu()).permute(0, 3, 1, 2).double(), wt.double(), bt.double(), stride=2).permute(0, 2, 3, 1).float()
+    assert up.shape == ref.shape
+    assert (up - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    # pool: exact on the joined values
+    pl = _join(ops.maxpool2x2_split(s0).cpu())
+    ref = F.max_pool2d(_join(s0.cpu()).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(pl, ref)
+    # stem from the fp32 NCHW input
+    xs = torch.randn(B, 3, H, W, generator=g)
+    wsx = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    ws, sb = ops.pack_stem(wsx.cuda(), None, fp32=True)
+    st = _join(ops.stem_conv_split(xs.cuda(), ws, sb, relu=True).cpu())
+    ref = F.relu(F.conv2d(xs.double(), wsx.double(), padding=1)).permute(0, 2, 3, 1).float()
+    assert (st - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("gain", [1.0, 40.0])
+def test_fp32_path_logits_within_1e4(U, gain):
+    """b200_precision = 'fp32': logits within 1e-4 of the fp32 reference forward (north_star gate of the fp32 path);
+    the fp64 forward of the same weights is the yardstick that shows how much of that is the reference's own rounding."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=gain)
+    net.b200_precision = "fp32"
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(4321))
+    with torch.no_grad():
+        y32 = ref(x)
+        y64 = ref.double()(x.double()).float()
+        ref.float()
+        y = net(x.cuda()).cpu()
+    scale = max(1.0, y32.abs().max().item())
+    err = (y - y32).abs().max().item()
+    print(f"fp32 path: max|err| vs fp32 oracle {err:.3e}, vs fp64 {(y - y64).abs().max().item():.3e}; "
+          f"fp32 oracle vs fp64 {(y32 - y64).abs().max().item():.3e}; |logit| max {scale:.2f}")
+    assert err <= LOGIT_TOL_FP32 * scale
+    assert O.mask_agreement(y, y32) >= 0.999
+    net.b200_precision = "bf16"
+    with torch.no_grad():
+        yb = net(x.cuda()).cpu()
+    assert (yb - y32).abs().max().item() > err   # the bf16 path is the coarser one (sanity: the switch does something)

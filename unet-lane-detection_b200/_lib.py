@@ -57,6 +57,13 @@ _SIGS = {
     "unet_b200_stem_conv_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_head": (i32, [vp, vp, f32, sz, i32, vp, vp, vp, f32, vp]),
     "unet_b200_maxpool2x2": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_conv3x3_split": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_convT2x2_split": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_pack_conv3x3_split": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp]),
+    "unet_b200_pack_convT2x2_split": (i32, [vp, i32, i32, vp, vp]),
+    "unet_b200_pack_stem_fp32": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, vp, vp, vp]),
+    "unet_b200_stem_conv_split": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_maxpool2x2_split": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "unet_b200_trainer_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
     "unet_b200_trainer_destroy": (None, [vp]),
     "unet_b200_trainer_workspace_bytes": (sz, [vp]),

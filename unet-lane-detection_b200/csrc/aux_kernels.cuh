@@ -89,7 +89,7 @@ __global__ void pack_convT_pad_kernel(const float* __restrict__ w, const float* 
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ mean,
                                  const float* __restrict__ var, float eps, int Cout, int Cin,
-                                 float* __restrict__ ws, float* __restrict__ bias) {
+                                 float* __restrict__ ws, float* __restrict__ bias, int keep_fp32 = 0) {
   const int total = 9 * 4 * Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % Cout;
@@ -99,8 +99,9 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
     if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
     float v = 0.f;
     if (ci < Cin) {
-      // round through bf16 so the stem uses the same weight precision as the tensor-core layers
-      v = __bfloat162float(__float2bfloat16_rn(w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s));
+      // round through bf16 so the stem uses the same weight precision as the tensor-core layers (keep_fp32: split path)
+      v = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s;
+      if (!keep_fp32) v = __bfloat162float(__float2bfloat16_rn(v));
     }
     ws[i] = v;
   }
@@ -120,6 +121,98 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, int Cin, int f, _
     const int co = n % f;
     const int quad = n / f;
     wp[i] = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * f + co) * 4 + quad]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split-precision ("fp32-class") path: every activation and weight is carried as hi = bf16(v), lo = bf16(v - hi) (16 mantissa
+// bits) and a product is evaluated as hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the lo*lo term, 2^-18 relative,
+// is dropped). Activation tensors are [B,H,W,2C] = [hi C | lo C]; the conv kernel walks K sources (x[hi|lo] : 2C), (x[hi] : C)
+// per input tensor, so the packed weights are, per tap,  [w_hi (C) | w_hi (C) | w_lo (C)]  for every source.
+// conv: -> wp[Cout][9][3*(C0+C1)] bf16, bias fp32 (BN folded in fp32 BEFORE the split).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ __nv_bfloat16 split_part(float v, int part) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  return part < 2 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void pack_conv3x3_split_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, const float* __restrict__ mean,
+                                          const float* __restrict__ var, float eps, int Cout, int C0, int C1,
+                                          __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int Cin = C0 + C1, K3 = 3 * Cin;
+  const int total = Cout * 9 * K3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % K3;
+    const int tap = (i / K3) % 9;
+    const int co = i / (9 * K3);
+    int part, ci;
+    if (k < 3 * C0) {
+      part = k / C0;
+      ci = k % C0;
+    } else {
+      part = (k - 3 * C0) / C1;
+      ci = C0 + (k - 3 * C0) % C1;
+    }
+    float sc = 1.f;
+    if (gamma != nullptr) sc = gamma[co] / sqrtf(var[co] + eps);
+    wp[i] = split_part(w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * sc, part);
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout; co += gridDim.x * blockDim.x) {
+    float bv = 0.f;
+    if (gamma != nullptr) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    bias[co] = bv;
+  }
+}
+
+// ConvT: w [Cin][f][2][2] -> wp[4f][3*Cin] (row n = quad*f + co; K = [w_hi | w_hi | w_lo]).
+__global__ void pack_convT_split_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wp) {
+  const int K3 = 3 * Cin;
+  const int total = 4 * f * K3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % K3;
+    const int n = i / K3;
+    const int co = n % f;
+    const int quad = n / f;
+    wp[i] = split_part(w[(static_cast<size_t>(k % Cin) * f + co) * 4 + quad], k / Cin);
+  }
+}
+
+// 2x2/2 max-pool of a split tensor [B,H,W,2C]: the maximum is taken on hi + lo (fp32) and the winner's pair is copied.
+__global__ void maxpool2x2_split_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ y) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = i % C8;
+    size_t r = i / C8;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const size_t b = r / Ho;
+    const size_t pix0 = (b * H + 2 * ho) * W + 2 * wo;
+    const size_t offs[4] = {pix0, pix0 + 1, pix0 + W, pix0 + W + 1};
+    float best[8];
+    __nv_bfloat16 bh[8], bl[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 vh = __ldg(x + offs[k] * (2 * C8) + c);
+      const uint4 vl = __ldg(x + offs[k] * (2 * C8) + C8 + c);
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&vh);
+      const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(&vl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = __bfloat162float(h[j]) + __bfloat162float(l[j]);
+        if (k == 0 || v > best[j]) {
+          best[j] = v;
+          bh[j] = h[j];
+          bl[j] = l[j];
+        }
+      }
+    }
+    const size_t po = ((b * Ho + ho) * Wo + wo) * (2 * C8) + c;
+    y[po] = *reinterpret_cast<const uint4*>(bh);
+    y[po + C8] = *reinterpret_cast<const uint4*>(bl);
   }
 }
 
@@ -404,9 +497,12 @@ resize_gray_u8_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, ui
 // (reads 8 B/pixel, writes 128 B/pixel), so it runs on the FP32 pipes: 16x16 pixel tile per block,
 // each thread owns 2 horizontally adjacent pixels x 32 output channels, weights broadcast from smem.
 // ------------------------------------------------------------------------------------------------
+// SPLIT (fp32-class path): x is the module's own fp32 NCHW input (no bf16 rounding of the image) and y is [B,H,W,2*Cout] = [hi | lo].
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-stem_conv_kernel(const uint2* __restrict__ x, const float* __restrict__ ws, const float* __restrict__ bias,
+stem_conv_kernel(const void* __restrict__ xin, const float* __restrict__ ws, const float* __restrict__ bias,
                  int B, int H, int W, int Cin, int Cout, int relu, __nv_bfloat16* __restrict__ y) {
+  const uint2* x = reinterpret_cast<const uint2*>(xin);
   extern __shared__ float sm[];
   float* sw = sm;                       // [9][4][Cout]
   float* sb = sw + 36 * Cout;           // [Cout]
@@ -422,10 +518,17 @@ stem_conv_kernel(const uint2* __restrict__ x, const float* __restrict__ ws, cons
     const int hh = h0 + i / 18 - 1, ww = w0 + i % 18 - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-      const uint2 r = __ldg(x + (static_cast<size_t>(b) * H + hh) * W + ww);
-      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
-      const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
-      v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      if (SPLIT) {
+        const float* xf = reinterpret_cast<const float*>(xin);
+        float c4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < Cin; ++k) c4[k] = __ldg(xf + ((static_cast<size_t>(b) * Cin + k) * H + hh) * W + ww);
+        v = make_float4(c4[0], c4[1], c4[2], c4[3]);
+      } else {
+        const uint2 r = __ldg(x + (static_cast<size_t>(b) * H + hh) * W + ww);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+        v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      }
     }
     st[i] = v;
   }
@@ -491,7 +594,8 @@ stem_conv_kernel(const uint2* __restrict__ x, const float* __restrict__ ws, cons
       for (int pix = 0; pix < 2; ++pix) {
         if (ww + pix < W) {
           const float* acc = pix == 0 ? acc0 : acc1;
-          uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(b) * H + hh) * W + ww + pix) * Cout + cg * 32);
+          uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(b) * H + hh) * W + ww + pix) * (SPLIT ? 2 * Cout : Cout) +
+                                                cg * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v[8];
@@ -499,6 +603,12 @@ stem_conv_kernel(const uint2* __restrict__ x, const float* __restrict__ ws, cons
             for (int k = 0; k < 8; ++k) v[k] = relu ? fmaxf(acc[j * 8 + k], 0.f) : acc[j * 8 + k];
             dst[j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                                 pack_bf16x2(v[6], v[7]));
+            if (SPLIT) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] -= __bfloat162float(__float2bfloat16_rn(v[k]));
+              dst[Cout / 8 + j] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                             pack_bf16x2(v[6], v[7]));
+            }
           }
         }
       }

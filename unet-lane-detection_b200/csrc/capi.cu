@@ -131,7 +131,7 @@ int make_tile_store_map(CUtensorMap* m, const void* base, int Bc, int H, int W, 
 }
 
 struct Layer;
-int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc);
+int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc, int cm = 1);
 
 // Shared-memory carve-up of conv_halo_kernel: prefer resident weights, then the deepest patch ring that fits.
 bool halo_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
@@ -324,25 +324,26 @@ struct Buf {
 
 // Store views for a conv_umma_kernel layer. Conv: out (+ pooled out). ConvT: quad (dy,dx) of the [B,2H,2W,f] output is
 // the tensor (f, W, H, B) at base + (dy*2W + dx)*f with pixel strides (2f, 4W*f, 4HW*f).
-int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc) {
+int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc, int cm) {
+  // cm = 2: split-precision tensors, 2*Cout physical channels [hi | lo] per pixel (the kernel stores lo at channel Cout + co)
   int rc;
   (void)pool;
   // one TMEM lane quarter (32 rows) of the tile box, see conv_args(): sub-box (TW, sh, sb)
   const int sb = l.TB >= 4 ? l.TB / 4 : 1;
   const int sh = l.TB >= 4 ? l.TH : (l.TB == 2 ? l.TH / 2 : l.TH / 4);
   if (l.kind == L_CONV) {
-    const size_t C = l.Cout;
-    rc = make_tile_store_map(&l.mO[0], out, Bc, l.H, l.W, l.Cout, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, sh, sb);
+    const size_t C = (size_t)cm * l.Cout;
+    rc = make_tile_store_map(&l.mO[0], out, Bc, l.H, l.W, (int)C, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, sh, sb);
     if (rc != UB_OK) return rc;
     l.mO[1] = l.mO[0];
     l.mO[2] = l.mO[0];
     l.mO[3] = l.mO[0];
   } else {
-    const size_t f = l.Cout;
+    const size_t f = (size_t)cm * l.Cout;
     for (int qd = 0; qd < 4; ++qd) {
       const int dy = qd >> 1, dx = qd & 1;
       uint8_t* base = static_cast<uint8_t*>(out) + ((size_t)dy * 2 * l.W + dx) * f * 2;
-      rc = make_tile_store_map(&l.mO[qd], base, Bc, l.H, l.W, l.Cout, 2 * f, (size_t)4 * l.W * f, (size_t)4 * l.H * l.W * f, l.TW, sh, sb);
+      rc = make_tile_store_map(&l.mO[qd], base, Bc, l.H, l.W, (int)f, 2 * f, (size_t)4 * l.W * f, (size_t)4 * l.H * l.W * f, l.TW, sh, sb);
       if (rc != UB_OK) return rc;
     }
   }
@@ -473,6 +474,7 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.pool_out = reinterpret_cast<__nv_bfloat16*>(pool);
   a.stat_sum = nullptr;
   a.stat_sumsq = nullptr;
+  a.split = 0;
   if (l.TB >= 4) {
     a.sub_b = l.TB / 4;
     a.sub_h = l.TH;
@@ -827,7 +829,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     } else if (l.kind == L_STEM) {
       const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
       const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
-      ub::stem_conv_kernel<<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(x),
+      ub::stem_conv_kernel<false><<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(x),
                                                       reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch, l.H,
                                                       l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
       UB_CUDA(cudaGetLastError());
@@ -1187,7 +1189,7 @@ int unet_b200_stem_conv(const void* x, const float* ws, const float* bias, int B
   if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
   const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
   const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
-  ub::stem_conv_kernel<<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  ub::stem_conv_kernel<false><<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint2*>(x), ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1231,6 +1233,118 @@ int unet_b200_maxpool2x2(const void* x, int B, int H, int W, int C, void* y, voi
   if (C % 8 != 0 || ((H | W) & 1)) return fail(UB_ERR_ARG, "maxpool needs C %% 8 == 0 and even H, W");
   const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 8);
   ub::maxpool2x2_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), B, H, W, C / 8, reinterpret_cast<uint4*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+// ---- split-precision (fp32-class) single layers: tensors are [B,H,W,2C] = [hi C | lo C] bf16 (aux_kernels.cuh) ----------
+namespace {
+int split_layer_launch(LayerKind kind, const void* x0, int C0, const void* x1, int C1, const void* wp, const float* bias, int B,
+                       int H, int W, int Cout, int relu, void* y, cudaStream_t st) {
+  Layer l;
+  memset(&l, 0, sizeof(l));
+  l.kind = kind;
+  l.H = H;
+  l.W = W;
+  l.C0 = C0;
+  l.C1 = C1;
+  l.Cout = Cout;
+  l.relu = relu;
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  const int N = (kind == L_CONV) ? Cout : 4 * Cout;
+  l.block_n = pick_block_n(N);
+  CUtensorMap m0, m1;
+  int rc = make_act_map(&m0, x0, B, H, W, 2 * C0, l.TW, l.TH, l.TB);
+  if (rc != UB_OK) return rc;
+  m1 = m0;
+  if (C1 > 0) {
+    rc = make_act_map(&m1, x1, B, H, W, 2 * C1, l.TW, l.TH, l.TB);
+    if (rc != UB_OK) return rc;
+  }
+  rc = make_w_map(&l.mW, wp, N, (kind == L_CONV ? 9 : 1) * 3 * (C0 + C1), l.block_n);
+  if (rc != UB_OK) return rc;
+  rc = make_umma_store_maps(l, y, nullptr, B, 2);
+  if (rc != UB_OK) return rc;
+  ub::ConvArgs a = conv_args(l, B, B, bias, y, nullptr);
+  // K sources: x0[hi|lo], x0[hi], x1[hi|lo], x1[hi]  against  [w_hi | w_hi | w_lo] per source
+  a.kc0 = 2 * C0 / 64;
+  a.kc1 = C0 / 64;
+  a.kc2 = 2 * C1 / 64;
+  a.kc3 = C1 / 64;
+  a.split = 1;
+  const CUtensorMap ma[4] = {m0, m0, m1, m1};
+  return launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
+}
+}  // namespace
+
+int unet_b200_conv3x3_split(const void* x0, int C0, const void* x1, int C1, const void* wp, const float* bias, int B, int H,
+                            int W, int Cout, int relu, void* y, void* stream) {
+  if (x0 == nullptr || wp == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0 || C0 <= 0 || C1 < 0 || Cout <= 0) {
+    return fail(UB_ERR_ARG, "C0=%d C1=%d Cout=%d must be multiples of 64", C0, C1, Cout);
+  }
+  if (C1 > 0 && x1 == nullptr) return fail(UB_ERR_ARG, "x1 is null but C1 > 0");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  return split_layer_launch(L_CONV, x0, C0, x1, C1, wp, bias, B, H, W, Cout, relu, y, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_convT2x2_split(const void* x, int Cin, const void* wp, const float* bias, int B, int H, int W, int f, void* y,
+                             void* stream) {
+  if (x == nullptr || wp == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin % 64 != 0 || f % 64 != 0 || Cin <= 0 || f <= 0) return fail(UB_ERR_ARG, "Cin=%d f=%d must be multiples of 64", Cin, f);
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  return split_layer_launch(L_CONVT, x, Cin, nullptr, 0, wp, bias, B, H, W, f, 0, y, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_pack_conv3x3_split(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                                 float eps, int Cout, int C0, int C1, void* wp, float* bias, void* stream) {
+  if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C0 <= 0 || C1 < 0) return fail(UB_ERR_ARG, "bad channel split");
+  ub::pack_conv3x3_split_kernel<<<grid_for((size_t)Cout * 27 * (C0 + C1), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gamma, beta, mean, var, eps, Cout, C0, C1, reinterpret_cast<__nv_bfloat16*>(wp), bias);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_pack_convT2x2_split(const float* w, int Cin, int f, void* wp, void* stream) {
+  if (w == nullptr || wp == nullptr) return fail(UB_ERR_ARG, "null argument");
+  ub::pack_convT_split_kernel<<<grid_for((size_t)12 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wp));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_pack_stem_fp32(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                             float eps, int Cout, int Cin, float* ws, float* bias, void* stream) {
+  if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
+  ub::pack_stem_kernel<<<grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 1);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_stem_conv_split(const float* x_nchw, const float* ws, const float* bias, int B, int H, int W, int Cin, int Cout,
+                              int relu, void* y, void* stream) {
+  if (x_nchw == nullptr || ws == nullptr || bias == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
+  if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
+  const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
+  const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
+  ub::stem_conv_kernel<true><<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_maxpool2x2_split(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  if (x == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (C % 8 != 0 || ((H | W) & 1)) return fail(UB_ERR_ARG, "maxpool needs C %% 8 == 0 and even H, W");
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  ub::maxpool2x2_split_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(x), B, H, W, C / 8, reinterpret_cast<uint4*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;

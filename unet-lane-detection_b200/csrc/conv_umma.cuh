@@ -42,6 +42,9 @@ struct ConvArgs {
   const float* bias;              // [Cout]
   double* stat_sum;               // EPI_STORE, optional (training): per-channel sum / sum of squares of the bf16 output,
   double* stat_sumsq;             //   accumulated atomically ([Cout] each, zeroed by the caller)
+  int split;                      // 1: fp32-class path - the output tensor has 2*Cout channels [hi | lo] (epilogue.cuh
+                                  //    epi_load_unit_part); inputs are such tensors too (the host lists hi|lo and hi again as
+                                  //    K sources against weights [w_hi | w_hi | w_lo]). No fused pool / statistics.
 };
 
 constexpr int CONV_THREADS = 320;
@@ -256,7 +259,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           bias_off = co;
         }
         uint32_t p[32];
-        epi_load_unit(t_row + hf * 64, a.bias + bias_off, a.relu, p);
+        if (a.split) {
+          // hi part first (stored at channel co), the lo part below (stored at channel Cout + co)
+          epi_load_unit_part(t_row + hf * 64, a.bias + bias_off, a.relu, 0, p);
+          if (lane == 0) bulk_wait_group_read<0>();
+          __syncwarp();
+          epi_stage_row(stg, lane, p);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const CUtensorMap* mo = quad == 0 ? &tmO0 : quad == 1 ? &tmO1 : quad == 2 ? &tmO2 : &tmO3;
+            tma_store_4d(mo, stg, co, w0, h0 + off_h, b0 + off_b);
+            bulk_commit_group();
+          }
+          epi_load_unit_part(t_row + hf * 64, a.bias + bias_off, a.relu, 1, p);
+          co += a.Cout;
+        } else {
+          epi_load_unit(t_row + hf * 64, a.bias + bias_off, a.relu, p);
+        }
         if (hf + 2 >= HALVES) {
           // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           tc_fence_before();

@@ -46,6 +46,35 @@ __device__ __forceinline__ void epi_load_unit(uint32_t taddr, const float* __res
   }
 }
 
+// Split-precision variant (fp32-class path, conv_umma.cuh `split`): the fp32 value x after bias (+ReLU) leaves as TWO bf16
+// numbers, hi = bf16(x) and lo = bf16(x - hi), i.e. 16 mantissa bits; the next layer multiplies hi and lo separately.
+// Two TMEM reads of the same columns instead of 64 live fp32 registers. part 0 -> hi, part 1 -> lo.
+__device__ __forceinline__ void epi_load_unit_part(uint32_t taddr, const float* __restrict__ bias64, int relu, int part,
+                                                   uint32_t (&p)[32]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    const float4* bias4 = reinterpret_cast<const float4*>(bias64 + c * 32);
+    float4 bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = __ldg(bias4 + j);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x[4] = {__uint_as_float(v[4 * j + 0]) + bb[j].x, __uint_as_float(v[4 * j + 1]) + bb[j].y,
+                    __uint_as_float(v[4 * j + 2]) + bb[j].z, __uint_as_float(v[4 * j + 3]) + bb[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (relu) x[k] = fmaxf(x[k], 0.f);
+        if (part) x[k] -= __bfloat162float(__float2bfloat16_rn(x[k]));
+      }
+      p[c * 16 + 2 * j] = pack_bf16x2(x[0], x[1]);
+      p[c * 16 + 2 * j + 1] = pack_bf16x2(x[2], x[3]);
+    }
+  }
+}
+
 // Row `lane` of the warp's staging tile <- 64 bf16 (128 B), 16-byte chunks XOR-swizzled by (row & 7) as TMA expects.
 __device__ __forceinline__ void epi_stage_row(uint8_t* tile, int row, const uint32_t (&p)[32]) {
   const uint32_t base = smem_u32(tile + row * 128);

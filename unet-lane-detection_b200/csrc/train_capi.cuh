@@ -365,7 +365,7 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
     } else {
       const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
       const size_t smem = (size_t)(36 * c.Cout + c.Cout) * 4 + 18 * 18 * 16;
-      ub::stem_conv_kernel<<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0), reinterpret_cast<const float*>(c.wp),
+      ub::stem_conv_kernel<false><<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0), reinterpret_cast<const float*>(c.wp),
                                                       t->zero_bias, B, c.H, c.W, c.C0, c.Cout, 0,
                                                       reinterpret_cast<__nv_bfloat16*>(c.y));
       UB_CUDA(cudaGetLastError());

@@ -42,18 +42,15 @@ def pack_conv3x3(w, bn=None):
     return wp, bias
 
 
-def pack_stem(w, bn=None):
+def pack_stem(w, bn=None, fp32=False):
+    """fp32=False: weights rounded through bf16 (the bf16 path's stem); fp32=True: kept in fp32 (split-precision path)."""
     _req(w, torch.float32, "w")
     cout, cin = w.shape[:2]
     ws = torch.empty(9, 4, cout, dtype=torch.float32, device=w.device)
     bias = torch.empty(cout, dtype=torch.float32, device=w.device)
-    if bn is None:
-        check(lib.unet_b200_pack_stem(w.data_ptr(), None, None, None, None, 0.0, cout, cin, ws.data_ptr(),
-                                      bias.data_ptr(), _stream()))
-    else:
-        g, b, m, v, eps = bn
-        check(lib.unet_b200_pack_stem(w.data_ptr(), g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(), eps,
-                                      cout, cin, ws.data_ptr(), bias.data_ptr(), _stream()))
+    fn = lib.unet_b200_pack_stem_fp32 if fp32 else lib.unet_b200_pack_stem
+    g, b, m, v, eps = bn if bn is not None else (None, None, None, None, 0.0)
+    check(fn(w.data_ptr(), _p(g), _p(b), _p(m), _p(v), eps, cout, cin, ws.data_ptr(), bias.data_ptr(), _stream()))
     return ws, bias
 
 
@@ -347,3 +344,71 @@ def resize_gray_u8(masks, size):
     out = torch.empty(B, size[0], size[1], dtype=torch.uint8, device=masks.device)
     check(lib.unet_b200_resize_gray_u8(masks.data_ptr(), B, Hs, Ws, out.data_ptr(), size[0], size[1], _stream()))
     return out
+
+
+# ---------------------------------------------------------------- split-precision ("fp32-class") layers
+# Tensors are bf16 [B,H,W,2C] = [hi C | lo C] with value = hi + lo (16 mantissa bits); every product is evaluated as
+# hi*hi + lo*hi + hi*lo in the fp32 tensor-core accumulator (csrc/aux_kernels.cuh, csrc/conv_umma.cuh `split`).
+def pack_conv3x3_split(w, bn=None, c0=None):
+    """w fp32 [Cout,Cin,3,3] (+ eval BN); c0 = channels of the first input tensor (skip) when the conv reads a concat.
+    -> (wp bf16 [Cout, 9, 3*Cin], bias fp32 [Cout])."""
+    _req(w, torch.float32, "w")
+    cout, cin = w.shape[:2]
+    c0 = cin if c0 is None else c0
+    wp = torch.empty(cout, 9, 3 * cin, dtype=torch.bfloat16, device=w.device)
+    bias = torch.empty(cout, dtype=torch.float32, device=w.device)
+    g, b, m, v, eps = bn if bn is not None else (None, None, None, None, 0.0)
+    check(lib.unet_b200_pack_conv3x3_split(w.data_ptr(), _p(g), _p(b), _p(m), _p(v), eps, cout, c0, cin - c0, wp.data_ptr(),
+                                           bias.data_ptr(), _stream()))
+    return wp, bias
+
+
+def conv3x3_split(x0, wp, bias, x1=None, relu=True):
+    _req(x0, torch.bfloat16, "x0")
+    B, H, W, C0 = x0.shape
+    C1 = 0
+    if x1 is not None:
+        _req(x1, torch.bfloat16, "x1")
+        C1 = x1.shape[3]
+    cout = wp.shape[0]
+    y = torch.empty(B, H, W, 2 * cout, dtype=torch.bfloat16, device=x0.device)
+    check(lib.unet_b200_conv3x3_split(x0.data_ptr(), C0 // 2, _p(x1), C1 // 2, wp.data_ptr(), bias.data_ptr(), B, H, W, cout,
+                                      int(relu), y.data_ptr(), _stream()))
+    return y
+
+
+def pack_convT2x2_split(w):
+    """w fp32 [Cin,f,2,2] -> wp bf16 [4f, 3*Cin]."""
+    _req(w, torch.float32, "w")
+    cin, f = w.shape[:2]
+    wp = torch.empty(4 * f, 3 * cin, dtype=torch.bfloat16, device=w.device)
+    check(lib.unet_b200_pack_convT2x2_split(w.data_ptr(), cin, f, wp.data_ptr(), _stream()))
+    return wp
+
+
+def convT2x2_split(x, wp, bias):
+    _req(x, torch.bfloat16, "x")
+    B, H, W, c2 = x.shape
+    f = wp.shape[0] // 4
+    y = torch.empty(B, 2 * H, 2 * W, 2 * f, dtype=torch.bfloat16, device=x.device)
+    check(lib.unet_b200_convT2x2_split(x.data_ptr(), c2 // 2, wp.data_ptr(), bias.data_ptr(), B, H, W, f, y.data_ptr(), _stream()))
+    return y
+
+
+def stem_conv_split(x_nchw, ws, bias, relu=True):
+    """x fp32 NCHW [B,Cin<=4,H,W] (read as is, no bf16 rounding of the image), ws/bias from pack_stem -> [B,H,W,2*Cout]."""
+    _req(x_nchw, torch.float32, "x")
+    B, cin, H, W = x_nchw.shape
+    cout = ws.shape[2]
+    y = torch.empty(B, H, W, 2 * cout, dtype=torch.bfloat16, device=x_nchw.device)
+    check(lib.unet_b200_stem_conv_split(x_nchw.data_ptr(), ws.data_ptr(), bias.data_ptr(), B, H, W, cin, cout, int(relu),
+                                        y.data_ptr(), _stream()))
+    return y
+
+
+def maxpool2x2_split(x):
+    _req(x, torch.bfloat16, "x")
+    B, H, W, c2 = x.shape
+    y = torch.empty(B, H // 2, W // 2, c2, dtype=torch.bfloat16, device=x.device)
+    check(lib.unet_b200_maxpool2x2_split(x.data_ptr(), B, H, W, c2 // 2, y.data_ptr(), _stream()))
+    return y
