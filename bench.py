@@ -352,13 +352,25 @@ def main():
     halo64 = fam(lambda r: r.get("halo") and r["block_n"] == 64)
     halo128 = fam(lambda r: r.get("halo") and r["block_n"] == 128)
     allconv = fam(lambda r: r["kind"] in ("conv3x3", "convT2x2"))
+    # DRAM bytes of the dominant kernel family from the committed ncu capture (bench.py cannot run under ncu itself):
+    # sum over its launches of one pass, i.e. the same unit as flops_per_pass; only valid for the captured geometry
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    if os.path.exists(tpath) and (H, W) == (224, 224) and int(x4.shape[0]) == 128:
+        with open(tpath) as f:
+            tj = json.load(f)
+        fam_t = tj["families"].get("conv_umma_kernel<256>")
+        if fam_t and fam_t["launches"] == dom["launches"]:
+            traffic = fam_t["dram_read_bytes"] + fam_t["dram_write_bytes"]
+            traffic_src = "profiles/r1_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
     roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": dom["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                "frac": dom["tflops"] / peaks["bf16_sustained"], "traffic": traffic, "traffic_unit": "bytes per pass", "traffic_source": traffic_src,
                 "kernel": f"conv_umma_kernel<256> ({dom['launches']} launches per pass: 3x3 convs with Cout>=256 + 4 ConvT)",
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass": dom["ms"],
                 "timing": f"CUDA events around every kernel of one {int(x4.shape[0])}-frame pass on the launching stream, min of 3",
-                "traffic_note": "ncu --set full per-launch DRAM bytes are in profiles/r1_ncu_full_*.txt (no re-reads: dec3.conv0 reads 411 MB = its two inputs)",
+                "traffic_note": "reads equal the layers' input bytes exactly (no re-reads; e.g. enc0.conv1 reads 822.5 MB = 128x224x224x64 bf16); "
+                                "ncu --set full captures in profiles/r1_ncu_full_*.txt",
                 "other_kernels": {"conv_halo_kernel<64>": halo64, "conv_halo_kernel<128>": halo128, "all_tensor_core_convs": allconv},
                 "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
