@@ -198,3 +198,31 @@ def test_stem_conv_tensor_core(U, cin, B, H, W):
     ref = F.relu(F.conv2d(x, bf(w * s[:, None, None, None]), be - mu * s, padding=1))
     y = U.stem_conv_tc(U.nchw_to_nhwc4(x.cuda()), wp, bias)
     close(nchw(y), bf(ref), 1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,pool", [(2, 224, 224, 64, 0, 64, True), (1, 224, 224, 64, 64, 64, False),
+                                                   (2, 112, 112, 64, 0, 128, False), (2, 112, 112, 128, 0, 128, True),
+                                                   (1, 112, 112, 128, 128, 128, False), (3, 24, 40, 64, 0, 64, True),
+                                                   (1, 8, 24, 64, 0, 64, False), (5, 16, 8, 64, 0, 128, False),
+                                                   (1, 120, 160, 128, 0, 128, True), (2, 56, 56, 256, 0, 64, False)])
+def test_conv3x3_cta_pair_kernel_equals_single_cta(U, B, H, W, C0, C1, Cout, pool):
+    """conv_halo2_kernel (cta_group::2: M = 256 over two SMs, half of the weight tile per SM) issues the same MMAs in the same
+    order as conv_halo_kernel, so the outputs must be BIT-identical - on even and odd tile counts (the odd pair member is
+    loaded out of bounds), resident and streamed weights, two K sources and the fused pool; and both match the oracle."""
+    g = torch.Generator().manual_seed(11)
+    x0 = nhwc(bf(torch.randn(B, C0, H, W, generator=g)))
+    x1 = nhwc(bf(torch.randn(B, C1, H, W, generator=g))) if C1 else None
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) / (3.0 * (C0 + C1) ** 0.5)
+    wp, bias = U.pack_conv3x3(w.cuda(), None)
+    outs = []
+    for pair in (1, 0):
+        _set(U, "halo2", pair)
+        try:
+            o = U.conv3x3(x0, wp, bias, x1=x1, relu=True, pool=pool)
+        finally:
+            _set(U, "halo2", 1)
+        torch.cuda.synchronize()
+        outs.append(o if pool else (o,))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    conv_case(U, B, H, W, C0, C1, Cout, pool=pool, seed=5)

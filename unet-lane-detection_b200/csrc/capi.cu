@@ -9,6 +9,7 @@
 #include "../../include/unet_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_halo.cuh"
+#include "conv_halo2.cuh"
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
 
@@ -217,23 +218,60 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
   return UB_OK;
 }
 
-int g_hattr_done[2] = {0, 0};
+int g_hattr_done[4] = {0, 0, 0, 0};
+int g_opt_halo2 = 1;   // run halo layers on the CTA-pair kernel (conv_halo2.cuh) when at least two tiles exist
+
+// Shared-memory carve-up of the CTA-pair kernel (half-size weight tiles): resident weights first.
+bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
+  const int need = 3 * kc;
+  if (need <= ub::HaloCfg::MAX_B) {
+    for (int as = 4; as >= 2; --as) {
+      if (ub::halo2_smem_bytes(block_n, as, need, head) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 1; a->a_stages = as; a->b_stages = need;
+        return true;
+      }
+    }
+  }
+  for (int b = 6; b >= 2; --b) {
+    for (int as = 4; as >= 3; --as) {
+      if (ub::halo2_smem_bytes(block_n, as, b, head) <= ub::HaloCfg::SMEM_LIMIT) {
+        a->resident = 0; a->a_stages = as; a->b_stages = b;
+        return true;
+      }
+    }
+  }
+  return false;
+}
 
 template <int BN>
 int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
                   ub::HaloArgs args, int slot, cudaStream_t st) {
+  const int head = args.epi == ub::HEPI_HEAD;
+  if (head && BN != 64) return fail(UB_ERR_ARG, "the fused head epilogue needs Cout == 64");
+  const int total = args.tiles_w * args.tiles_h * args.B;
+  if (g_opt_halo2 && total >= 2 && halo2_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
+    if (!g_hattr_done[2 + slot]) {
+      UB_CUDA(cudaFuncSetAttribute(ub::conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   ub::HaloCfg::SMEM_LIMIT));
+      g_hattr_done[2 + slot] = 1;
+    }
+    const int smem = ub::halo2_smem_bytes(BN, args.a_stages, args.b_stages, head);
+    const int pairs = (total + 1) / 2;
+    const int max_pairs = g_num_sms / 2;
+    const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)
+    ub::conv_halo2_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, args);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
   if (!g_hattr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ub::HaloCfg::SMEM_LIMIT));
     g_hattr_done[slot] = 1;
   }
-  const int head = args.epi == ub::HEPI_HEAD;
-  if (head && BN != 64) return fail(UB_ERR_ARG, "the fused head epilogue needs Cout == 64");
   if (!halo_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
     return fail(UB_ERR_ARG, "no shared-memory plan for halo conv (N=%d, KC=%d)", BN, args.kc0 + args.kc1);
   }
   const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head);
-  const int total = args.tiles_w * args.tiles_h * args.B;
   const int grid = total < g_num_sms ? total : g_num_sms;
   ub::conv_halo_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, args);
   UB_CUDA(cudaGetLastError());
@@ -525,7 +563,7 @@ int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const voi
     } else {
       l.mA1 = l.mA0;
     }
-    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
+    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n / 2);   // half-tile boxes: see conv_halo2.cuh
     if (rc != UB_OK) return rc;
     return make_box_map(&l.mOut, y, B, H, W, Cout, 8, 4);
   }
@@ -723,7 +761,7 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
       if (rc != UB_OK) return rc;
     }
     if (l.kind == L_CONV) {
-      rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.block_n);
+      rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.halo ? l.block_n / 2 : l.block_n);
     } else {
       rc = make_w_map(&l.mW, p->wt + l.w_off, 4 * l.Cout, l.C0, l.block_n);
     }
@@ -796,6 +834,8 @@ int unet_b200_set_option(const char* name, int value) {
   if (name == nullptr) return fail(UB_ERR_ARG, "null option name");
   if (strcmp(name, "halo") == 0) {
     g_opt_halo = value;
+  } else if (strcmp(name, "halo2") == 0) {
+    g_opt_halo2 = value;
   } else if (strcmp(name, "fuse_head") == 0) {
     g_opt_fuse_head = value;
   } else if (strcmp(name, "stem_umma") == 0) {

@@ -151,7 +151,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               mbar_expect_tx(&b_full[bs], 3 * B_TILE);
 #pragma unroll
               for (int sx = 0; sx < 3; ++sx) {
+                // the weight map's box is half a tile (BLOCK_N/2 rows; shared with the CTA-pair kernel, conv_halo2.cuh)
                 tma_load_2d(smB + (bs * 3 + sx) * B_TILE, &tmW, &b_full[bs], ((r * 3 + sx) * KC + c) * 64, 0);
+                tma_load_2d(smB + (bs * 3 + sx) * B_TILE + B_TILE / 2, &tmW, &b_full[bs], ((r * 3 + sx) * KC + c) * 64, BLOCK_N / 2);
               }
               if (++bs == BS) {
                 bs = 0;
