@@ -85,9 +85,12 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// Arrive on the leader's copy of `bar` from either CTA of the pair.
+// Arrive on the leader's copy of `bar` from either CTA of the pair. No cluster-scope release: the only thing handed over is
+// "my tcgen05.ld of this accumulator stage has completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it);
+// a .release.cluster arrive compiles to ERRBAR + a membar that waits for every earlier global store of the warp (the pool
+// stores) - 12 % of all stall samples in profiles/r1_ncu_full_halo2.txt, on the path that frees the TMEM stage.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
 }
 
 // Shared memory of the pair kernel: a weight tile is BLOCK_N/2 rows here.
