@@ -191,6 +191,9 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
                "none: ONE kernel sums the owned gradient shard over the peers' buffers (NVLink loads), applies AdamW (ZeRO-1 "
                "sharded state) and stores the parameters to all replicas (NVLink stores); two device-side barriers per step"
                if step.exchange == "nvlink" else
+               "none: ONE kernel on NVSwitch multicast addresses - multimem.ld_reduce sums the owned gradient shard inside the "
+               "switch, AdamW (ZeRO-1 sharded state), multimem.st broadcasts the parameters; two device-side barriers per step"
+               if step.exchange == "nvlink_mc" else
                "none: NVLink P2P gradient atomics to the owner replica inside the backward kernels, sharded AdamW, parameter "
                "stores to all replicas; two device-side barriers per step"),
            "config": "BASELINE.json configs[3]: BCE+Dice (pos_weight 3), AdamW lr 1e-4 wd 1e-4, BatchNorm batch statistics per replica"}
@@ -216,7 +219,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE.json headline (configs[1]); train: the training step of configs[3] as the metric")
     ap.add_argument("--train-batch", type=int, default=64, help="samples per GPU per training step (configs[3])")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink", "nvlink_push"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "nvlink", "nvlink_pull", "nvlink_mc", "nvlink_push"],
                     help="training, N > 1: gradient exchange (auto = nvlink when the ranks can map each other's memory). nvlink: one kernel = reduce-scatter by NVLink loads + sharded AdamW + "
                          "all-gather by NVLink stores; nvlink_push: gradient atomics go to the owner GPU inside the backward kernels")
     ap.add_argument("--no-train", action="store_true", help="infer mode: skip the secondary training-step measurement")

@@ -218,6 +218,17 @@ int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_b
                              float* grads_local_dev, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev, long long n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale,
                              void* stream);
+/* NVSwitch (NVLS) form of adamw_step_p2p's pull mode: params_mc_dev / grads_mc_dev are MULTICAST addresses of the symmetric
+ * flat parameter / gradient buffers (cuMulticast* / torch symmetric memory multicast_ptr); the shard's gradient sum is formed
+ * by multimem.ld_reduce inside the switch and the new parameters reach every replica through multimem.st. params_local_dev is
+ * this rank's own (unicast) parameter buffer. Same barriers as adamw_step_p2p. */
+int unet_b200_adamw_step_multimem(float* params_mc_dev, const float* grads_mc_dev, const float* params_local_dev, int world,
+                                  int rank, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev, long long n, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale,
+                                  void* stream);
+/* out_dev[i] = sum over replicas of x[lo + i] through the multicast address x_mc_dev (multimem.ld_reduce); used to check the
+ * reduced gradient of the NVLS exchange. */
+int unet_b200_multimem_reduce(const float* x_mc_dev, long long lo, long long n, float* out_dev, void* stream);
 /* BCEDiceLoss (README.md:1855-1893): losses3_dev = {total, bce, dice}; dlogits_dev (optional) = d total / d logits.
  * target fp32, same shape as logits; scratch4_dev: 4 doubles. */
 int unet_b200_bce_dice_loss(const float* logits_dev, const float* target_dev, size_t n, float pos_weight, float bce_weight,

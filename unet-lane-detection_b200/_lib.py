@@ -75,6 +75,8 @@ _SIGS = {
     "unet_b200_train_backward": (i32, [vp, vp, vp, vp, vp]),
     "unet_b200_train_backward_p2p": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "unet_b200_adamw_step_p2p": (i32, [vp, vp, i32, i32, vp, vp, vp, C.c_longlong, f32, f32, f32, f32, f32, vp, f32, vp]),
+    "unet_b200_adamw_step_multimem": (i32, [vp, vp, vp, i32, i32, vp, vp, C.c_longlong, f32, f32, f32, f32, f32, vp, f32, vp]),
+    "unet_b200_multimem_reduce": (i32, [vp, C.c_longlong, C.c_longlong, vp, vp]),
     "unet_b200_bce_dice_loss": (i32, [vp, vp, sz, f32, f32, f32, f32, vp, vp, vp, vp]),
     "unet_b200_validation_metrics": (i32, [vp, vp, sz, f32, f32, f32, f32, f32, vp, vp, vp]),
     "unet_b200_adamw_step": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),

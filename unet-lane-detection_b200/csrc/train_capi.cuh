@@ -802,6 +802,36 @@ int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_b
   return UB_OK;
 }
 
+int unet_b200_adamw_step_multimem(float* params_mc, const float* grads_mc, const float* params_local, int world, int rank,
+                                  float* exp_avg_shard, float* exp_avg_sq_shard, long long n, float lr, float beta1, float beta2,
+                                  float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+  if (params_mc == nullptr || grads_mc == nullptr || params_local == nullptr || exp_avg_shard == nullptr ||
+      exp_avg_sq_shard == nullptr || step_dev == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  if (world < 1 || rank < 0 || rank >= world) return fail(UB_ERR_ARG, "bad rank / world");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  const long long shard = ((n + world - 1) / world + 3) / 4 * 4;
+  const long long lo = shard * rank;
+  long long hi = lo + shard;
+  if (hi > n) hi = n;
+  if (hi <= lo) return UB_OK;
+  ub::adamw_shard_multimem_kernel<<<grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params_mc, grads_mc, params_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale,
+      step_dev);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+int unet_b200_multimem_reduce(const float* x_mc, long long lo, long long n, float* out, void* stream) {
+  if (x_mc == nullptr || out == nullptr || n < 0) return fail(UB_ERR_ARG, "bad argument");
+  if (n == 0) return UB_OK;
+  ub::multimem_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_mc, lo, n, out);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
 int unet_b200_bce_dice_loss(const float* logits, const float* target, size_t n, float pos_weight, float bce_weight,
                             float dice_weight, float smooth, double* scratch4, float* losses3, float* dlogits, void* stream) {
   if (logits == nullptr || target == nullptr || scratch4 == nullptr || losses3 == nullptr) return fail(UB_ERR_ARG, "null argument");

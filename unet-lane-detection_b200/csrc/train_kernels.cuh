@@ -569,6 +569,73 @@ adamw_shard_allgather_kernel(float* const* __restrict__ param_bases, float* cons
   }
 }
 
+// NVSwitch (NVLS) form of the same step: grads_mc / params_mc are MULTICAST addresses of the symmetric gradient / parameter
+// buffers. multimem.ld_reduce makes the switch read the element from every replica and return the sum (the reduce-scatter
+// costs one 16-byte response per float4 instead of world-1 peer loads); multimem.st writes the new parameter values into
+// every replica with one store (the all-gather). Per GPU and step only 2 x 124/world MB cross its NVLink ports.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_v4(const float* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_v4(float* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float multimem_ld_reduce_add(const float* mc_addr) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(mc_addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc_addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+adamw_shard_multimem_kernel(float* __restrict__ params_mc, const float* __restrict__ grads_mc, const float* __restrict__ plocal,
+                            float* __restrict__ m, float* __restrict__ v, long long lo, long long hi, float lr, float beta1,
+                            float beta2, float eps, float wd, float grad_scale, const int* __restrict__ step_dev) {
+  const float st = static_cast<float>(*step_dev);
+  const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
+  const long long n4 = (hi - lo) / 4;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = lo + 4 * q;
+    const float4 g = multimem_ld_reduce_add_v4(grads_mc + i);
+    float4 p4 = *reinterpret_cast<const float4*>(plocal + i);
+    float4 m4 = *reinterpret_cast<const float4*>(m + 4 * q);
+    float4 v4 = *reinterpret_cast<const float4*>(v + 4 * q);
+    adamw_one(p4.x, g.x * grad_scale, m4.x, v4.x, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.y, g.y * grad_scale, m4.y, v4.y, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.z, g.z * grad_scale, m4.z, v4.z, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    adamw_one(p4.w, g.w * grad_scale, m4.w, v4.w, lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+    *reinterpret_cast<float4*>(m + 4 * q) = m4;
+    *reinterpret_cast<float4*>(v + 4 * q) = v4;
+    multimem_st_v4(params_mc + i, p4);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = lo + 4 * n4 + threadIdx.x; i < hi; i += blockDim.x) {
+      const float g = multimem_ld_reduce_add(grads_mc + i);
+      float pi = plocal[i];
+      adamw_one(pi, g * grad_scale, m[i - lo], v[i - lo], lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2);
+      multimem_st(params_mc + i, pi);
+    }
+  }
+}
+
+// out[i] = sum over replicas of x[lo + i], formed by the switch (multimem.ld_reduce) - the gradient check of the NVLS exchange
+__global__ void multimem_reduce_kernel(const float* __restrict__ x_mc, long long lo, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    out[i] = multimem_ld_reduce_add(x_mc + lo + i);
+  }
+}
+
 // dgrad weights: wd[ci][tap'][co] = w[co][ci][8 - tap'] (180-degree rotated, in/out swapped), bf16; w fp32 [Cout][Cin][3][3]
 __global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wd) {
   const int total = Cin * 9 * Cout;
