@@ -30,18 +30,17 @@ __device__ __forceinline__ void epi_load_unit(uint32_t taddr, const float* __res
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float x0 = __uint_as_float(v[4 * j + 0]) + bb[j].x;
-      float x1 = __uint_as_float(v[4 * j + 1]) + bb[j].y;
-      float x2 = __uint_as_float(v[4 * j + 2]) + bb[j].z;
-      float x3 = __uint_as_float(v[4 * j + 3]) + bb[j].w;
-      if (relu) {
-        x0 = fmaxf(x0, 0.f);
-        x1 = fmaxf(x1, 0.f);
-        x2 = fmaxf(x2, 0.f);
-        x3 = fmaxf(x3, 0.f);
+      const float x0 = __uint_as_float(v[4 * j + 0]) + bb[j].x;
+      const float x1 = __uint_as_float(v[4 * j + 1]) + bb[j].y;
+      const float x2 = __uint_as_float(v[4 * j + 2]) + bb[j].z;
+      const float x3 = __uint_as_float(v[4 * j + 3]) + bb[j].w;
+      if (relu) {   // warp-uniform
+        p[c * 16 + 2 * j] = pack_bf16x2_relu(x0, x1);
+        p[c * 16 + 2 * j + 1] = pack_bf16x2_relu(x2, x3);
+      } else {
+        p[c * 16 + 2 * j] = pack_bf16x2(x0, x1);
+        p[c * 16 + 2 * j + 1] = pack_bf16x2(x2, x3);
       }
-      p[c * 16 + 2 * j] = pack_bf16x2(x0, x1);
-      p[c * 16 + 2 * j + 1] = pack_bf16x2(x2, x3);
     }
   }
 }

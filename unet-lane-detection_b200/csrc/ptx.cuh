@@ -229,6 +229,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(v, 0) and the bf16 rounding in ONE instruction (F2FP.RELU): two fewer FMNMX per packed pair in every ReLU epilogue.
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
   __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);

@@ -2,7 +2,8 @@
 // (README.md:1452 with in_channels = 3), NHWC4 bf16 input -> NHWC bf16 output.
 //
 // K = 9 taps x 4 (padded) channels = 36, far below a 64-deep TMA K block, so the im2col tile is built
-// by producer warps instead of TMA: each thread assembles one 128-byte row (pixel) of the A operand -
+// by producer warps instead of TMA: a producer group stages the tile's halo'd [18][10] input patch in shared
+// memory with coalesced loads, then each thread assembles one 128-byte row (pixel) of the A operand from it -
 // taps 2j,2j+1 form 16-byte chunk j, chunks 0..5 cover K = 48 (columns 36..47 are zero) - and writes
 // it in the 128B-swizzled layout the UMMA descriptor expects. Three K=16 MMAs per 128-pixel tile.
 // The layer is bound by writing its 128 B/pixel output, so everything else is sized to stay out of
@@ -30,7 +31,8 @@ struct StemCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = N * 128;
   static constexpr int THREADS = 17 * 32;  // warp 0 MMA, warps 1..8 epilogue, warps 9..16 producers
-  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 8 * 4096 + 512 + 1024;
+  static constexpr int PATCH_BYTES = 1536;     // [18][10] input pixels x 8 B of one tile (1440 B), one buffer per producer group
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 8 * 4096 + 2 * PATCH_BYTES + 512 + 1024;
 };
 
 // Weights for the stem GEMM: wp[co][k] bf16, k = tap*4 + ci (zero for ci >= Cin and k >= 36), bias fp32.
@@ -65,7 +67,8 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint8_t* smA = smem;
   uint8_t* smB = smA + Cfg::A_STAGES * Cfg::A_BYTES;
   uint8_t* smS = smB + Cfg::B_BYTES;  // [8 warps][4 KB] private output staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + 8 * 4096);
+  uint8_t* smP = smS + 8 * 4096;      // [2 producer groups][18][10] uint2: the tile's halo'd input patch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + 2 * Cfg::PATCH_BYTES);
   uint64_t* a_full = bars;                       // [4] producers (128 arrivals) -> MMA
   uint64_t* a_empty = a_full + Cfg::A_STAGES;    // [4] MMA -> producers
   uint64_t* tfull = a_empty + Cfg::A_STAGES;     // [4] MMA -> epilogue
@@ -129,32 +132,58 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     __syncwarp();
   } else if (warp >= 9) {
     // ------------------------------------------------------------ im2col producers: group pg builds tiles it = pg, pg+2, ...
+    // The 128 threads of a group first stage the tile's [18][10] input patch in shared memory (180 pixels x 8 B: one or two
+    // coalesced loads per thread, ONE bounds test each) and then pick their 3x3 neighbourhood from it with nine LDS.64 -
+    // the first version did nine bounds-checked global loads per thread and the kernel was instruction-issue bound
+    // (profiles/r1_ncu_full_stem_umma_v2.txt: 128 M warp instructions, IPC 1.9). The global loads of the group's NEXT tile
+    // are issued before the current tile is assembled, so their latency is off the critical path.
     const int pg = (warp - 9) >> 2;
-    const int m = ((warp - 9) & 3) * 32 + lane;  // row of the A tile == pixel of the 16x8 tile
-    const int tw = m & 7, th = m >> 3;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      if ((it & 1) != pg) continue;
-      const int s = it & (Cfg::A_STAGES - 1);
+    const int pt = ((warp - 9) & 3) * 32 + lane;  // thread of the group == row of the A tile == pixel of the 16x8 tile
+    const int tw = pt & 7, th = pt >> 3;
+    uint2* patch = reinterpret_cast<uint2*>(smP + pg * Cfg::PATCH_BYTES);
+    const uint32_t bar_id = 1 + pg;
+    // patch entries of this thread: e0 = pt, e1 = pt + 128 (only the first 52 threads have one)
+    const int r0 = pt / 10, c0 = pt % 10;
+    const int r1 = (pt + 128) / 10, c1 = (pt + 128) % 10;
+    const bool has1 = pt + 128 < 180;
+    auto fetch = [&](int t, uint2& v0, uint2& v1) {
       const int b = t / tiles_per_img;
       const int ti = t - b * tiles_per_img;
-      const int w = (ti % a.tiles_w) * 8 + tw;
-      const int h = (ti / a.tiles_w) * 16 + th;
-      // gather the 3x3 neighbourhood (zero outside the image) before waiting for the slot
+      const int w0 = (ti % a.tiles_w) * 8 - 1;
+      const int h0 = (ti / a.tiles_w) * 16 - 1;
+      const uint2* img = a.x + static_cast<size_t>(b) * a.H * a.W;
+      v0 = make_uint2(0u, 0u);
+      v1 = make_uint2(0u, 0u);
+      int hh = h0 + r0, ww = w0 + c0;
+      if (static_cast<unsigned>(hh) < static_cast<unsigned>(a.H) && static_cast<unsigned>(ww) < static_cast<unsigned>(a.W)) {
+        v0 = __ldg(img + hh * a.W + ww);
+      }
+      hh = h0 + r1;
+      ww = w0 + c1;
+      if (has1 && static_cast<unsigned>(hh) < static_cast<unsigned>(a.H) && static_cast<unsigned>(ww) < static_cast<unsigned>(a.W)) {
+        v1 = __ldg(img + hh * a.W + ww);
+      }
+    };
+    const int t_step = 2 * static_cast<int>(gridDim.x);
+    int t = static_cast<int>(blockIdx.x) + pg * static_cast<int>(gridDim.x);
+    uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+    if (t < total_tiles) fetch(t, v0, v1);
+    for (int it = pg; t < total_tiles; t += t_step, it += 2) {
+      const int s = it & (Cfg::A_STAGES - 1);
+      patch[pt] = v0;
+      if (has1) patch[pt + 128] = v1;
+      named_bar_sync(bar_id, 128);                      // patch complete
+      if (t + t_step < total_tiles) fetch(t + t_step, v0, v1);   // next tile's loads in flight from here on
       uint2 tap[9];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int hh = h + r - 1, ww = w + c - 1;
-          uint2 v = make_uint2(0u, 0u);
-          if (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) v = __ldg(a.x + (static_cast<size_t>(b) * a.H + hh) * a.W + ww);
-          tap[r * 3 + c] = v;
-        }
+        for (int c = 0; c < 3; ++c) tap[r * 3 + c] = patch[(th + r) * 10 + tw + c];
       }
+      named_bar_sync(bar_id, 128);                      // everyone has read the patch: it may be overwritten
       mbar_wait_parked(&a_empty[s], ((it / Cfg::A_STAGES) & 1) ^ 1, 2000);
-      const uint32_t row = smem_u32(smA + s * Cfg::A_BYTES + m * 128);
-      const int sw = m & 7;
+      const uint32_t row = smem_u32(smA + s * Cfg::A_BYTES + pt * 128);
+      const int sw = pt & 7;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         st_shared_v4(row + ((j ^ sw) << 4), tap[2 * j].x, tap[2 * j].y, tap[2 * j + 1].x, tap[2 * j + 1].y);
