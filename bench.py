@@ -404,9 +404,9 @@ def main():
         torch.cuda.empty_cache()
         line["train"] = measure_train(dev, world, rank, args.train_batch, min(args.steps, 10), 3, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and (H, W) == (224, 224):
-        v, sps, threads = time_cpu_reference(8, 3, 1)
+        v, sps, threads = time_cpu_reference(32, 6, 1)      # about 10-15 s of CPU work on the box's host cores
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"8 frames/step x 3 steps ({sps * 3:.1f} s) of the oracle fp32 PyTorch CPU pipeline"}
+                                "sample": f"32 frames/step x 6 steps ({sps * 6:.1f} s) of the oracle fp32 PyTorch CPU pipeline"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:
