@@ -226,3 +226,50 @@ def test_conv3x3_cta_pair_kernel_equals_single_cta(U, B, H, W, C0, C1, Cout, poo
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
     conv_case(U, B, H, W, C0, C1, Cout, pool=pool, seed=5)
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,pool", [(2, 56, 56, 128, 0, 256, False), (2, 56, 56, 256, 0, 256, True),
+                                                   (8, 28, 28, 256, 0, 512, True), (8, 28, 28, 512, 512, 512, False),
+                                                   (32, 14, 14, 512, 0, 1024, False), (3, 14, 14, 64, 0, 256, False),
+                                                   (5, 28, 28, 64, 64, 256, False), (1, 60, 80, 64, 0, 256, False),
+                                                   (7, 8, 24, 128, 0, 512, False)])
+def test_conv3x3_umma_cta_pair_equals_single_cta(U, B, H, W, C0, C1, Cout, pool):
+    """conv_umma2_kernel (cta_group::2) against conv_umma_kernel on the per-tap implicit-GEMM layers: bit-identical outputs
+    (odd and even pixel-tile counts, several column blocks, two K sources, fused pool, ragged sizes)."""
+    g = torch.Generator().manual_seed(13)
+    x0 = nhwc(bf(torch.randn(B, C0, H, W, generator=g)))
+    x1 = nhwc(bf(torch.randn(B, C1, H, W, generator=g))) if C1 else None
+    w = torch.randn(Cout, C0 + C1, 3, 3, generator=g) / (3.0 * (C0 + C1) ** 0.5)
+    wp, bias = U.pack_conv3x3(w.cuda(), None)
+    outs = []
+    for pair in (1, 0):
+        _set(U, "umma2", pair)
+        _set(U, "halo", 0)
+        try:
+            o = U.conv3x3(x0, wp, bias, x1=x1, relu=True, pool=pool)
+        finally:
+            _set(U, "umma2", 1)
+            _set(U, "halo", 1)
+        torch.cuda.synchronize()
+        outs.append(o if pool else (o,))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    conv_case(U, B, H, W, C0, C1, Cout, pool=pool, seed=6)
+
+
+@pytest.mark.parametrize("B,H,Cin,f", [(32, 14, 1024, 512), (2, 56, 256, 128), (1, 112, 128, 64), (3, 14, 128, 64)])
+def test_convT2x2_cta_pair_equals_single_cta(U, B, H, Cin, f):
+    g = torch.Generator().manual_seed(17)
+    x = nhwc(bf(torch.randn(B, Cin, H, H, generator=g)))
+    w = torch.randn(Cin, f, 2, 2, generator=g) / (Cin ** 0.5)
+    b = torch.randn(f, generator=g).cuda()
+    wp = U.pack_convT2x2(w.cuda())
+    outs = []
+    for pair in (1, 0):
+        _set(U, "umma2", pair)
+        try:
+            outs.append(U.convT2x2(x, wp, b))
+        finally:
+            _set(U, "umma2", 1)
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])

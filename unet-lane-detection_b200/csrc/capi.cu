@@ -10,6 +10,7 @@
 #include "aux_kernels.cuh"
 #include "conv_halo.cuh"
 #include "conv_halo2.cuh"
+#include "conv_umma2.cuh"
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
 
@@ -69,8 +70,12 @@ int make_act_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C, 
   return UB_OK;
 }
 
-// bf16 weights [N][K] K-major -> 2-D map (K, N), box (64, block_n).
-int make_w_map(CUtensorMap* m, const void* base, int N, int K, int block_n) {
+// bf16 weights [N][K] K-major -> 2-D map (K, N), box (64, box_rows).
+int make_w_map_box(CUtensorMap* m, const void* base, int N, int K, int box_rows);
+// Weight map of the conv kernels: the box is HALF a BLOCK_N tile, so that the same map serves the 1-CTA kernels (two loads
+// per tile) and the CTA-pair kernels (each CTA of the pair loads its half: conv_halo2.cuh, conv_umma2.cuh).
+int make_w_map(CUtensorMap* m, const void* base, int N, int K, int block_n) { return make_w_map_box(m, base, N, K, block_n / 2); }
+int make_w_map_box(CUtensorMap* m, const void* base, int N, int K, int block_n) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return fail(UB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
@@ -199,9 +204,29 @@ int device_check() {
   return UB_OK;
 }
 
+int g_opt_umma2 = 1;   // run conv_umma layers on the CTA-pair kernel (conv_umma2.cuh) when at least two pixel tiles exist
+int g_attr2_done[3] = {0, 0, 0};
+
 template <int BN>
 int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args, int slot,
                   cudaStream_t st) {
+  const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_b;
+  if (g_opt_umma2 && m_tiles >= 2) {
+    using Cfg2 = ub::ConvCfg2<BN>;
+    if (!g_attr2_done[slot]) {
+      UB_CUDA(cudaFuncSetAttribute(ub::conv_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_LIMIT));
+      g_attr2_done[slot] = 1;
+    }
+    ub::ConvArgs args2 = args;
+    args2.stages = Cfg2::plan_stages();
+    const int smem = Cfg2::smem_bytes(args2.stages);
+    const int pair_tiles = ((m_tiles + 1) / 2) * args.n_tiles;
+    const int max_pairs = g_num_sms / 2;
+    const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // cluster size 2 (__cluster_dims__)
+    ub::conv_umma2_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
   using Cfg = ub::ConvCfg<BN>;
   if (!g_attr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -211,7 +236,7 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
   ub::ConvArgs args2 = args;
   args2.stages = Cfg::plan_stages();
   const int smem = Cfg::smem_bytes(args2.stages);
-  const int total = args.tiles_w * args.tiles_h * args.tiles_b * args.n_tiles;
+  const int total = m_tiles * args.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
   UB_CUDA(cudaGetLastError());
@@ -563,7 +588,7 @@ int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const voi
     } else {
       l.mA1 = l.mA0;
     }
-    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n / 2);   // half-tile boxes: see conv_halo2.cuh
+    rc = make_w_map(&l.mW, wp, Cout, 9 * (C0 + C1), l.block_n);
     if (rc != UB_OK) return rc;
     return make_box_map(&l.mOut, y, B, H, W, Cout, 8, 4);
   }
@@ -732,7 +757,7 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
   for (Layer& l : p->layers) {
     if (l.kind == L_STEM) {
       if (l.stem_tc) {
-        rc = make_w_map(&l.mW, p->wt + l.w_off, 64, 64, 64);
+        rc = make_w_map_box(&l.mW, p->wt + l.w_off, 64, 64, 64);
         if (rc != UB_OK) return rc;
         rc = make_box_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, 64, 8, 4);
         if (rc != UB_OK) return rc;
@@ -761,7 +786,7 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
       if (rc != UB_OK) return rc;
     }
     if (l.kind == L_CONV) {
-      rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.halo ? l.block_n / 2 : l.block_n);
+      rc = make_w_map(&l.mW, p->wt + l.w_off, l.Cout, 9 * (l.C0 + l.C1), l.block_n);
     } else {
       rc = make_w_map(&l.mW, p->wt + l.w_off, 4 * l.Cout, l.C0, l.block_n);
     }
@@ -836,6 +861,8 @@ int unet_b200_set_option(const char* name, int value) {
     g_opt_halo = value;
   } else if (strcmp(name, "halo2") == 0) {
     g_opt_halo2 = value;
+  } else if (strcmp(name, "umma2") == 0) {
+    g_opt_umma2 = value;
   } else if (strcmp(name, "fuse_head") == 0) {
     g_opt_fuse_head = value;
   } else if (strcmp(name, "stem_umma") == 0) {
@@ -1251,7 +1278,7 @@ int unet_b200_stem_conv_tc(const void* x, const void* wp, const float* bias, int
   int rc = device_check();
   if (rc != UB_OK) return rc;
   CUtensorMap mw, mo;
-  rc = make_w_map(&mw, wp, 64, 64, 64);
+  rc = make_w_map_box(&mw, wp, 64, 64, 64);
   if (rc != UB_OK) return rc;
   rc = make_box_map(&mo, y, B, H, W, 64, 8, 4);
   if (rc != UB_OK) return rc;

@@ -1,65 +1,27 @@
-// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16 activations.
-//
-// Replaces, for the U-Net of the reference (README.md:1421-1481):
-//   * Conv2d(3x3, pad 1, bias=False) + BatchNorm2d(eval, folded) + ReLU   (README.md:1451-1458)
-//   * the 2x2/2 MaxPool that follows an encoder block (README.md:1429,1467) - fused in the epilogue
-//   * torch.cat([skip, x], 1) (README.md:1478) - never materialised: the K loop walks two tensor maps
-//   * ConvTranspose2d(2f, f, 2, 2) (README.md:1441-1443,1476) as a 1-tap GEMM with N = 4f whose four
-//     (dy,dx) column groups are TMA-stored through four strided views of the 2x-upsampled output
-//
-// GEMM view: D[M = 128 output pixels][N = BLOCK_N out channels] += A[M][K] * Wt[N][K],
-// K = taps * Cin walked in 64-channel blocks (one 128-byte swizzled row per pixel / per out channel).
-// The 128 pixels of a tile are a TB x TH x TW box of the [B,H,W] grid, so a TMA 4-D box load at
-// (c0, w0+dx, h0+dy, b0) with zero OOB fill *is* the im2col tile for tap (dy,dx).
-//
-// Warp roles (320 threads): warp 0 = TMA producer (one elected thread), warp 1 = TMEM owner + MMA
-// issuer (one elected thread), warps 2..9 = epilogue: two warps per TMEM lane quarter. Persistent over
-// tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Epilogue work is cut into warp-private units of 32 rows x 64 columns (epilogue.cuh): registers ->
-// 4 KB swizzled staging tile -> TMA store of the quarter's sub-box (the tensor map clips partial tiles).
+// CTA-pair (cta_group::2) version of conv_umma.cuh: the two CTAs of a cluster take two adjacent 128-pixel tiles of the SAME
+// column block and run one tcgen05.mma of M = 256 per issue; each CTA loads its own A box and only HALF of the weight tile
+// (BLOCK_N/2 rows), so the B-operand shared-memory fill and reads per SM halve and the operand ring gets deeper
+// (32 KB instead of 48 KB per stage at BLOCK_N = 256). Barrier protocol as in conv_halo2.cuh: `full` lives in the leader
+// (both CTAs' TMA loads complete_tx on it), `empty` / `tfull` exist in both CTAs (multicast tcgen05.commit), `tempty` lives
+// in the leader (remote arrives from both epilogues). Everything else - K sources, epilogues (STORE / CONVT / split), fused
+// pool and statistics - is conv_umma.cuh's. A missing odd tile is loaded at an out-of-range image index (zero fill) and its
+// TMA stores are clipped away by the tensor map.
 #pragma once
-#include "epilogue.cuh"
-#include "ptx.cuh"
+#include "conv_halo2.cuh"
+#include "conv_umma.cuh"
 
 namespace ub {
 
-enum : int { EPI_STORE = 0, EPI_CONVT = 1 };
-
-struct ConvArgs {
-  int B, H, W;                    // spatial grid of the GEMM rows (conv: output == input size)
-  int TW, TH, TB;                 // pixel box of one tile, TW*TH*TB == 128
-  int tiles_w, tiles_h, tiles_b;  // number of boxes along each axis
-  int n_tiles;                    // N / BLOCK_N
-  int taps;                       // 9 (3x3, pad 1) or 1 (pointwise)
-  int kc0, kc1, kc2, kc3;         // 64-channel blocks taken from activation sources 0..3 (concat / ConvT-dgrad quads)
-  int epi;                        // EPI_*
-  int relu;
-  int stages;                     // operand ring depth (shared-memory split chosen by the host)
-  int sub_h, sub_b;               // rows / images of the 32-row sub-box one TMEM lane quarter covers (sub_w == TW)
-  __nv_bfloat16* pool_out;        // EPI_STORE, optional: [B,H/2,W/2,Cout] = maxpool2x2(out), written from registers
-  int a_bytes;                    // bytes one A box load delivers (128 rows x 128 B unless TB exceeds the batch dim)
-  int Cout;                       // EPI_STORE: channels of out; EPI_CONVT: f (out channels of the ConvT)
-  const float* bias;              // [Cout]
-  double* stat_sum;               // EPI_STORE, optional (training): per-channel sum / sum of squares of the bf16 output,
-  double* stat_sumsq;             //   accumulated atomically ([Cout] each, zeroed by the caller)
-  int split;                      // 1: fp32-class path - the output tensor has 2*Cout channels [hi | lo] (epilogue.cuh
-                                  //    epi_load_unit_part); inputs are such tensors too (the host lists hi|lo and hi again as
-                                  //    K sources against weights [w_hi | w_hi | w_lo]). No fused pool / statistics.
-};
-
-constexpr int CONV_THREADS = 320;
-
 template <int BLOCK_N>
-struct ConvCfg {
+struct ConvCfg2 {
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_HALF = (BLOCK_N / 2) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_HALF;
   static constexpr int MAX_STAGES = 8;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_LIMIT = 232448;
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
-  static constexpr int STG_BYTES = 8 * 4096;  // one private 4 KB staging tile per epilogue warp
+  static constexpr int STG_BYTES = 8 * 4096;
   __host__ __device__ static constexpr int smem_bytes(int stages) {
     return stages * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   }
@@ -70,13 +32,13 @@ struct ConvCfg {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
                  const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                  const __grid_constant__ CUtensorMap tmO3, const ConvArgs a) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg2<BLOCK_N>;
   constexpr int MAXS = Cfg::MAX_STAGES;
   constexpr int HALVES = BLOCK_N / 64;
   const int STAGES = a.stages;
@@ -105,33 +67,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], HALVES == 1 ? 128 : 256);
+      mbar_init(&tempty[s], 2 * (HALVES == 1 ? 128 : 256));   // the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kchunks = a.kc0 + a.kc1 + a.kc2 + a.kc3;
   const int num_kb = a.taps * kchunks;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
-  const int total_tiles = m_tiles * a.n_tiles;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * a.n_tiles;   // pair tiles: (n_tile, m_pair); this CTA's m_tile = 2*m_pair + rank
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: one elected thread runs the whole loop
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = pair0; t < total_tiles; t += pair_step) {
         const int n_tile = t % a.n_tiles;
-        const int m_tile = t / a.n_tiles;
-        const int w0 = (m_tile % a.tiles_w) * a.TW;
+        const int m_tile = 2 * (t / a.n_tiles) + static_cast<int>(rank);   // == m_tiles for the missing odd tile:
+        const int w0 = (m_tile % a.tiles_w) * a.TW;                        //    b0 lands past the batch, the box is zero-filled
         const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
         const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
         int kb = 0;
@@ -145,19 +112,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait_parked(&empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
-            mbar_expect_tx(&full[stage], a.a_bytes + Cfg::B_BYTES);
+            if (leader) mbar_expect_tx(&full[stage], 2 * (a.a_bytes + Cfg::B_HALF));   // the loads of both CTAs
             if (ch < a.kc0) {
-              tma_load_4d(sA, &tmA0, &full[stage], ch * 64, w0 + dx, h0 + dy, b0);
+              tma2_load_4d(sA, &tmA0, &full[stage], ch * 64, w0 + dx, h0 + dy, b0);
             } else if (ch < a.kc0 + a.kc1) {
-              tma_load_4d(sA, &tmA1, &full[stage], (ch - a.kc0) * 64, w0 + dx, h0 + dy, b0);
+              tma2_load_4d(sA, &tmA1, &full[stage], (ch - a.kc0) * 64, w0 + dx, h0 + dy, b0);
             } else if (ch < a.kc0 + a.kc1 + a.kc2) {
-              tma_load_4d(sA, &tmA2, &full[stage], (ch - a.kc0 - a.kc1) * 64, w0 + dx, h0 + dy, b0);
+              tma2_load_4d(sA, &tmA2, &full[stage], (ch - a.kc0 - a.kc1) * 64, w0 + dx, h0 + dy, b0);
             } else {
-              tma_load_4d(sA, &tmA3, &full[stage], (ch - a.kc0 - a.kc1 - a.kc2) * 64, w0 + dx, h0 + dy, b0);
+              tma2_load_4d(sA, &tmA3, &full[stage], (ch - a.kc0 - a.kc1 - a.kc2) * 64, w0 + dx, h0 + dy, b0);
             }
-            // the weight map's box is half a tile (shared with the CTA-pair kernel, conv_umma2.cuh)
-            tma_load_2d(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N);
-            tma_load_2d(sB + Cfg::B_BYTES / 2, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N + BLOCK_N / 2);
+            // this CTA's half of the weight tile (the map's box is BLOCK_N/2 rows)
+            tma2_load_2d(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -169,13 +135,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: one elected thread runs the whole loop
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(256, BLOCK_N);
       const uint64_t d_hi = make_sw128_kmajor_desc(0, 1024, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = pair0; t < total_tiles; t += pair_step, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -183,21 +149,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES) & 0x3FFFFu;
           const uint64_t da = d_hi + (sA >> 4);
           const uint64_t db = d_hi + ((sA + Cfg::A_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // +32 bytes (16 bf16) along K inside the 128-byte swizzled row == +2 in the >>4 address field
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma2_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          umma2_commit_both(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma2_commit_both(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -228,11 +194,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};
     int st_ntile = -1;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = pair0; t < total_tiles; t += pair_step, ++it) {
       const int acc = it & 1;
       if (HALVES == 1 && acc != cg) continue;
       const int n_tile = t % a.n_tiles;
-      const int m_tile = t / a.n_tiles;
+      const int m_tile = 2 * (t / a.n_tiles) + static_cast<int>(rank);
       const int w0 = (m_tile % a.tiles_w) * a.TW;
       const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
       const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
@@ -282,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (hf + 2 >= HALVES) {
           // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tempty[acc]);
+          mbar_arrive_leader(&tempty[acc]);
         }
         if (lane == 0) bulk_wait_group_read<0>();  // the previous unit's TMA store has finished reading the staging tile
         __syncwarp();
@@ -325,10 +291,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
   }
 }
+
 
 }  // namespace ub

@@ -319,7 +319,7 @@ int trainer_build_maps(unet_b200_trainer* t) {
     if (c.stem) {
       memset(&c.fwd, 0, sizeof(c.fwd));
       if (c.Cout == 64) {
-        rc = make_w_map(&c.fwd.mW, c.wp, 64, 64, 64);
+        rc = make_w_map_box(&c.fwd.mW, c.wp, 64, 64, 64);
         if (rc != UB_OK) return rc;
         rc = make_box_map(&c.fwd.mOut, c.y, B, c.H, c.W, 64, 8, 4);
         if (rc != UB_OK) return rc;
