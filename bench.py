@@ -350,7 +350,7 @@ def main():
         return {"launches": len(rs), "tflops": fl / (ms_ / 1e3) / 1e12 if ms_ > 0 else 0.0, "share_of_step": ms_ / all_ms,
                 "flops": fl, "ms": ms_}
 
-    # dominant kernel = conv_umma_kernel<256> (about half of the step, see profiles/r1_ncu_launches_bench.csv)
+    # dominant kernel = conv_umma2_kernel<256>, the CTA-pair implicit GEMM (over half of the step, see profiles/r1_ncu_launches_bench_v3.csv)
     dom = fam(lambda r: r["kind"] in ("conv3x3", "convT2x2") and r["block_n"] == 256 and not r.get("halo"))
     halo64 = fam(lambda r: r.get("halo") and r["block_n"] == 64)
     halo128 = fam(lambda r: r.get("halo") and r["block_n"] == 128)
@@ -362,19 +362,19 @@ def main():
     if os.path.exists(tpath) and (H, W) == (224, 224) and int(x4.shape[0]) == 128:
         with open(tpath) as f:
             tj = json.load(f)
-        fam_t = tj["families"].get("conv_umma_kernel<256>")
+        fam_t = tj["families"].get("conv_umma2_kernel<256>")
         if fam_t and fam_t["launches"] == dom["launches"]:
             traffic = fam_t["dram_read_bytes"] + fam_t["dram_write_bytes"]
             traffic_src = "profiles/r1_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
     roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": dom["tflops"] / peaks["bf16_sustained"], "traffic": traffic, "traffic_unit": "bytes per pass", "traffic_source": traffic_src,
-                "kernel": f"conv_umma_kernel<256> ({dom['launches']} launches per pass: 3x3 convs with Cout>=256 + 4 ConvT)",
+                "kernel": f"conv_umma2_kernel<256> (cta_group::2; {dom['launches']} launches per pass: 3x3 convs with Cout>=256 + 4 ConvT)",
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass": dom["ms"],
                 "timing": f"CUDA events around every kernel of one {int(x4.shape[0])}-frame pass on the launching stream, min of 3",
                 "traffic_note": "reads equal the layers' input bytes exactly (no re-reads; e.g. enc0.conv1 reads 822.5 MB = 128x224x224x64 bf16); "
                                 "ncu --set full captures in profiles/r1_ncu_full_*.txt",
-                "other_kernels": {"conv_halo_kernel<64>": halo64, "conv_halo_kernel<128>": halo128, "all_tensor_core_convs": allconv},
+                "other_kernels": {"conv_halo2_kernel<64>": halo64, "conv_halo2_kernel<128>": halo128, "all_tensor_core_convs": allconv},
                 "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
