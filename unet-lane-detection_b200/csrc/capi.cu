@@ -9,8 +9,6 @@
 #include "../../include/unet_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_halo.cuh"
-#include "conv_halo2.cuh"
-#include "conv_umma2.cuh"
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
 
@@ -73,7 +71,7 @@ int make_act_map(CUtensorMap* m, const void* base, int Bc, int H, int W, int C, 
 // bf16 weights [N][K] K-major -> 2-D map (K, N), box (64, box_rows).
 int make_w_map_box(CUtensorMap* m, const void* base, int N, int K, int box_rows);
 // Weight map of the conv kernels: the box is HALF a BLOCK_N tile, so that the same map serves the 1-CTA kernels (two loads
-// per tile) and the CTA-pair kernels (each CTA of the pair loads its half: conv_halo2.cuh, conv_umma2.cuh).
+// per tile) and the CTA-pair kernels (each CTA of the pair loads its half), see conv_umma.cuh / conv_halo.cuh.
 int make_w_map(CUtensorMap* m, const void* base, int N, int K, int block_n) { return make_w_map_box(m, base, N, K, block_n / 2); }
 int make_w_map_box(CUtensorMap* m, const void* base, int N, int K, int block_n) {
   EncodeTiledFn enc = get_encode();
@@ -204,7 +202,7 @@ int device_check() {
   return UB_OK;
 }
 
-int g_opt_umma2 = 1;   // run conv_umma layers on the CTA-pair kernel (conv_umma2.cuh) when at least two pixel tiles exist
+int g_opt_umma2 = 1;   // run conv_umma layers on the CTA-pair kernel (conv_umma2_kernel) when at least two pixel tiles exist
 int g_attr2_done[3] = {0, 0, 0};
 
 template <int BN>
@@ -212,7 +210,7 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
                   cudaStream_t st) {
   const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_b;
   if (g_opt_umma2 && m_tiles >= 2) {
-    using Cfg2 = ub::ConvCfg2<BN>;
+    using Cfg2 = ub::ConvCfg<BN, true>;
     if (!g_attr2_done[slot]) {
       UB_CUDA(cudaFuncSetAttribute(ub::conv_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_LIMIT));
       g_attr2_done[slot] = 1;
@@ -244,14 +242,14 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
 }
 
 int g_hattr_done[4] = {0, 0, 0, 0};
-int g_opt_halo2 = 1;   // run halo layers on the CTA-pair kernel (conv_halo2.cuh) when at least two tiles exist
+int g_opt_halo2 = 1;   // run halo layers on the CTA-pair kernel (conv_halo2_kernel) when at least two tiles exist
 
 // Shared-memory carve-up of the CTA-pair kernel (half-size weight tiles): resident weights first.
 bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
   const int need = 3 * kc;
   if (need <= ub::HaloCfg::MAX_B) {
     for (int as = 4; as >= 2; --as) {
-      if (ub::halo2_smem_bytes(block_n, as, need, head) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, need, head, 1) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 1; a->a_stages = as; a->b_stages = need;
         return true;
       }
@@ -259,7 +257,7 @@ bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
   }
   for (int b = 6; b >= 2; --b) {
     for (int as = 4; as >= 3; --as) {
-      if (ub::halo2_smem_bytes(block_n, as, b, head) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, b, head, 1) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 0; a->a_stages = as; a->b_stages = b;
         return true;
       }
@@ -280,7 +278,7 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
                                    ub::HaloCfg::SMEM_LIMIT));
       g_hattr_done[2 + slot] = 1;
     }
-    const int smem = ub::halo2_smem_bytes(BN, args.a_stages, args.b_stages, head);
+    const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head, 1);
     const int pairs = (total + 1) / 2;
     const int max_pairs = g_num_sms / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)

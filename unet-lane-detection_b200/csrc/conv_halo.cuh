@@ -14,6 +14,15 @@
 // Weights: one [BLOCK_N x 64] tile per (tap, 64-ch block), three taps (a kernel row) per barrier stage;
 // if all 3*KC stages fit the ring they are loaded once per CTA (resident mode), otherwise they stream.
 //
+// Two launch forms of the same body (PAIR template parameter, ptx.cuh "CTA pair"):
+//   conv_halo_kernel<N>   one CTA per 16x8 tile;
+//   conv_halo2_kernel<N>  a CTA pair (cta_group::2): M = 256 per MMA, each SM multiplies its own tile and holds HALF of every
+//                         weight tile. Why: the 1-CTA form is bound by the shared-memory operand reads of the tensor pipe (4 KB
+//                         of A + BLOCK_N*32 B of B per 128xBLOCK_Nx16 MMA against 128 B/cycle: 48 cycles for N = 64 against a
+//                         math floor of 32, 64 for N = 128 with no slack); with B split over the pair it is 40 / 48 cycles.
+//                         Pair p works on tiles 2*(p + i*pairs) + rank; a missing odd tile is loaded fully out of bounds (zeros)
+//                         and its epilogue stores nothing. Outputs are bit-identical to the 1-CTA form.
+//
 // Epilogues: STORE (+ fused 2x2 max-pool): warp-private units of 32 rows x 64 columns (epilogue.cuh):
 // TMEM -> registers -> bias/ReLU/bf16 -> 4 KB swizzled staging tile -> TMA store of the 4-row sub-box
 // (the tensor map clips partial tiles); or HEAD (Cout == 64): the 1x1 output conv +
@@ -55,20 +64,19 @@ struct HaloCfg {
   static constexpr int SMEM_LIMIT = 232448;
 };
 
-// Host + device: byte size of the dynamic shared memory for a given carve-up.
-__host__ __device__ constexpr int halo_smem_bytes(int block_n, int a_stages, int b_stages, int head) {
-  return a_stages * HaloCfg::A_STAGE_PITCH + b_stages * 3 * block_n * 128 + (head ? 0 : HaloCfg::STG_BYTES) +
-         HaloCfg::BAR_BYTES + 1024;
+// Host + device: byte size of the dynamic shared memory for a given carve-up (pair: a weight tile is BLOCK_N/2 rows per CTA).
+__host__ __device__ constexpr int halo_smem_bytes(int block_n, int a_stages, int b_stages, int head, int pair = 0) {
+  return a_stages * HaloCfg::A_STAGE_PITCH + b_stages * 3 * (pair ? block_n / 2 : block_n) * 128 +
+         (head ? 0 : HaloCfg::STG_BYTES) + HaloCfg::BAR_BYTES + 1024;
 }
 
 constexpr int HALO_THREADS = 320;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..9 epilogue (2 per TMEM lane quarter)
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(HALO_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
-                 const HaloArgs a) {
-  constexpr int B_TILE = BLOCK_N * 128;
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmWh,
+                                               const CUtensorMap& tmOut, const HaloArgs& a) {
+  constexpr int P = PAIR ? 2 : 1;                       // CTAs that share one MMA
+  constexpr int B_HALF = (BLOCK_N / P) * 128;           // bytes of one (tap, 64-channel block) weight tile held by ONE CTA
   constexpr int HALVES = BLOCK_N / 64;
   constexpr int TMEM_COLS = 2 * BLOCK_N;
   const int AS = a.a_stages, BS = a.b_stages;
@@ -77,7 +85,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smA + AS * HaloCfg::A_STAGE_PITCH;
-  uint8_t* smS = smB + BS * 3 * B_TILE;                            // [8 warps][4 KB] private output staging (HEPI_STORE)
+  uint8_t* smS = smB + BS * 3 * B_HALF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smS + (a.epi == HEPI_STORE ? HaloCfg::STG_BYTES : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + HaloCfg::MAX_A;
@@ -89,11 +97,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = pair_rank<PAIR>();
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmWh);
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < AS; ++s) {
       mbar_init(&a_full[s], 1);
@@ -105,55 +115,66 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], HALVES == 1 ? 128 : 256);
+      mbar_init(&tempty[s], P * (HALVES == 1 ? 128 : 256));   // the epilogue threads of every CTA of the group
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_p<PAIR>(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();   // (pair: the peer's barriers are initialised before anything signals them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int KC = a.kc0 + a.kc1;
   const int tiles_per_img = a.tiles_w * a.tiles_h;
   const int total_tiles = tiles_per_img * a.B;
+  const int pairs = gridDim.x / P;
+  const int pair = blockIdx.x / P;
+  // iteration i of this group covers tiles P*(pair + i*pairs) + rank; it runs while the first of them exists
+  const int t_first = P * pair + static_cast<int>(rank);
+  const int t_step = P * pairs;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: one elected thread runs the whole loop
+    // ------------------------------------------------------------ TMA producer (both CTAs; the leader also posts expect_tx)
     if (elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       bool first = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_img;
-        const int ti = t - b * tiles_per_img;
+      for (int t = t_first; t - static_cast<int>(rank) < total_tiles; t += t_step) {
+        // a tile index past the end (odd tile count): image index == B is fully out of bounds -> the box is zero-filled
+        const int b = t < total_tiles ? t / tiles_per_img : a.B;
+        const int ti = t < total_tiles ? t - b * tiles_per_img : 0;
         const int w0 = (ti % a.tiles_w) * 8;
         const int h0 = (ti / a.tiles_w) * 16;
         for (int c = 0; c < KC; ++c) {
           mbar_wait_parked(&a_empty[as], aph ^ 1);
-          mbar_expect_tx(&a_full[as], HaloCfg::A_STAGE_BYTES);
+          if (leader) mbar_expect_tx(&a_full[as], P * HaloCfg::A_STAGE_BYTES);
           if (c < a.kc0) {
-            tma_load_4d(smA + as * HaloCfg::A_STAGE_PITCH, &tmA0, &a_full[as], c * 64, w0 - 1, h0 - 1, b);
+            tma_load_4d_p<PAIR>(smA + as * HaloCfg::A_STAGE_PITCH, &tmA0, &a_full[as], c * 64, w0 - 1, h0 - 1, b);
           } else {
-            tma_load_4d(smA + as * HaloCfg::A_STAGE_PITCH, &tmA1, &a_full[as], (c - a.kc0) * 64, w0 - 1, h0 - 1, b);
+            tma_load_4d_p<PAIR>(smA + as * HaloCfg::A_STAGE_PITCH, &tmA1, &a_full[as], (c - a.kc0) * 64, w0 - 1, h0 - 1, b);
           }
           if (++as == AS) {
             as = 0;
             aph ^= 1;
           }
           if (!a.resident || first) {
-            for (int r = 0; r < 3; ++r) {  // one kernel row (3 taps) per weight stage
+            for (int r = 0; r < 3; ++r) {  // one kernel row (3 taps) per weight stage; this CTA's half of the rows
               mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_expect_tx(&b_full[bs], 3 * B_TILE);
+              if (leader) mbar_expect_tx(&b_full[bs], P * 3 * B_HALF);
 #pragma unroll
               for (int sx = 0; sx < 3; ++sx) {
-                // the weight map's box is half a tile (BLOCK_N/2 rows; shared with the CTA-pair kernel, conv_halo2.cuh)
-                tma_load_2d(smB + (bs * 3 + sx) * B_TILE, &tmW, &b_full[bs], ((r * 3 + sx) * KC + c) * 64, 0);
-                tma_load_2d(smB + (bs * 3 + sx) * B_TILE + B_TILE / 2, &tmW, &b_full[bs], ((r * 3 + sx) * KC + c) * 64, BLOCK_N / 2);
+                // the weight map's box is HALF a tile (BLOCK_N/2 rows): a pair CTA loads its half, a single CTA both
+                if constexpr (PAIR) {
+                  tma_load_2d_p<PAIR>(smB + (bs * 3 + sx) * B_HALF, &tmWh, &b_full[bs], ((r * 3 + sx) * KC + c) * 64,
+                                      static_cast<int>(rank) * (BLOCK_N / 2));
+                } else {
+                  tma_load_2d(smB + (bs * 3 + sx) * B_HALF, &tmWh, &b_full[bs], ((r * 3 + sx) * KC + c) * 64, 0);
+                  tma_load_2d(smB + (bs * 3 + sx) * B_HALF + B_HALF / 2, &tmWh, &b_full[bs], ((r * 3 + sx) * KC + c) * 64,
+                              BLOCK_N / 2);
+                }
               }
               if (++bs == BS) {
                 bs = 0;
@@ -167,16 +188,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: one elected thread, straight-line MMA blocks
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+    // ------------------------------------------------------------ MMA issuer: one elected thread of the LEADER CTA
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128 * P, BLOCK_N);
       const uint64_t da_hi = make_sw128_kmajor_desc(0, 1280, 0);  // SBO = one patch row (10 pixels)
       const uint64_t db_hi = make_sw128_kmajor_desc(0, 1024, 0);
-      const uint64_t db_base = db_hi + (smem_u32(smB) >> 4);
+      const uint64_t db_base = db_hi + ((smem_u32(smB) & 0x3FFFFu) >> 4);
       int as = 0, bs = 0, it = 0;
       uint32_t aph = 0, bph = 0;
       bool first = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = t_first; t < total_tiles; t += t_step, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -184,16 +205,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int c = 0; c < KC; ++c) {
           mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint64_t da0 = da_hi + (smem_u32(smA + as * HaloCfg::A_STAGE_PITCH) >> 4);
+          const uint64_t da0 = da_hi + ((smem_u32(smA + as * HaloCfg::A_STAGE_PITCH) & 0x3FFFFu) >> 4);
           if (a.resident && !first) {
-            // steady state of the resident mode: 36 MMAs back to back, no barrier traffic
-            const uint64_t dbc = db_base + static_cast<uint64_t>(c) * 9 * (B_TILE >> 4);
+            const uint64_t dbc = db_base + static_cast<uint64_t>(c) * 9 * (B_HALF >> 4);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_f16(d_tmem, da0 + (((tap / 3) * 10 + (tap % 3)) * 8 + k * 2), dbc + (tap * (B_TILE >> 4) + k * 2), idesc,
-                         (c | tap | k) != 0);
+                umma_f16_p<PAIR>(d_tmem, da0 + (((tap / 3) * 10 + (tap % 3)) * 8 + k * 2), dbc + (tap * (B_HALF >> 4) + k * 2), idesc,
+                          (c | tap | k) != 0);
               }
             }
           } else {
@@ -202,18 +222,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const int slot = a.resident ? (c * 3 + r) : bs;
               mbar_wait(&b_full[slot], a.resident ? 0u : bph);
               tc_fence_after();
-              const uint64_t db0 = db_base + static_cast<uint64_t>(slot) * 3 * (B_TILE >> 4);
+              const uint64_t db0 = db_base + static_cast<uint64_t>(slot) * 3 * (B_HALF >> 4);
 #pragma unroll
               for (int sx = 0; sx < 3; ++sx) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  // tap (r,sx): +(r*10+sx) patch rows of 128 B; k: +32 B inside the swizzled row (>>4 units)
-                  umma_f16(d_tmem, da0 + ((r * 10 + sx) * 8 + k * 2), db0 + (sx * (B_TILE >> 4) + k * 2), idesc,
-                           (c | r | sx | k) != 0);
+                  umma_f16_p<PAIR>(d_tmem, da0 + ((r * 10 + sx) * 8 + k * 2), db0 + (sx * (B_HALF >> 4) + k * 2), idesc,
+                            (c | r | sx | k) != 0);
                 }
               }
               if (!a.resident) {
-                umma_commit(&b_empty[bs]);
+                umma_commit_p<PAIR>(&b_empty[bs]);
                 if (++bs == BS) {
                   bs = 0;
                   bph ^= 1;
@@ -221,21 +240,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               }
             }
           }
-          umma_commit(&a_empty[as]);
+          umma_commit_p<PAIR>(&a_empty[as]);
           if (++as == AS) {
             as = 0;
             aph ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_p<PAIR>(&tfull[acc]);
         first = false;
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue: 8 warps, warp-private units (epilogue.cuh)
-    // warp (q, cg): rows 32q..32q+31 = image rows 4q..4q+3 of the tile; BLOCK_N == 128: cg picks the 64-column half,
-    // BLOCK_N == 64: the two warps of a quarter alternate tiles (warp group cg owns accumulator stage cg).
+    // ------------------------------------------------------------ epilogue (both CTAs): as conv_halo.cuh on this CTA's tile
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const int m = q * 32 + lane;
@@ -243,15 +260,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int th = m >> 3;
     uint8_t* stg = smS + (warp - 2) * 4096;
     const bool pool_writer = ((tw | th) & 1) == 0;
-    float st0[4] = {0.f, 0.f, 0.f, 0.f};  // fused batch statistics of this warp's 64-column group (epilogue.cuh)
+    float st0[4] = {0.f, 0.f, 0.f, 0.f};
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = t_first; t - static_cast<int>(rank) < total_tiles; t += t_step, ++it) {
       const int acc = it & 1;
       if (HALVES == 1 && acc != cg) continue;
       const int hf = (HALVES == 1) ? 0 : cg;
       const int n = hf * 64;
-      const int b = t / tiles_per_img;
-      const int ti = t - b * tiles_per_img;
+      const bool live = t < total_tiles;
+      const int b = live ? t / tiles_per_img : 0;
+      const int ti = live ? t - b * tiles_per_img : 0;
       const int w0 = (ti % a.tiles_w) * 8;
       const int h0 = (ti / a.tiles_w) * 16;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
@@ -259,21 +277,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t p[32];
       epi_load_unit(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + n, a.bias + n, a.relu, p);
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      mbar_arrive_p<PAIR>(&tempty[acc]);
+      if (!live) continue;   // warp-uniform
       const int w = w0 + tw, h = h0 + th;
       const bool valid = (w < a.W) && (h < a.H);
       if (a.epi == HEPI_STORE) {
-        if (lane == 0) bulk_wait_group_read<0>();  // the previous unit's TMA store has finished reading the staging tile
+        if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
         epi_stage_row(stg, lane, p);
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&tmOut, stg, n, w0, h0 + 4 * q, b);
           bulk_commit_group();
         }
         if (a.pool_out != nullptr) {
-          epi_pool2x2(p, 8);  // 2x2 partners: lane^1 (w) and lane^8 (h)
+          epi_pool2x2(p, 8);
           if (pool_writer && valid) {
             uint4* dst = reinterpret_cast<uint4*>(
                 a.pool_out + ((static_cast<size_t>(b) * (a.H >> 1) + (h >> 1)) * (a.W >> 1) + (w >> 1)) * a.Cout + n);
@@ -283,7 +302,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         if (a.stat_sum != nullptr) epi_stats_accumulate(stg, lane, __ballot_sync(0xffffffffu, valid), st0);
       } else {
-        // HEPI_HEAD (BLOCK_N == 64): 1x1 conv over the bf16-rounded activations (same rounding point as the unfused path)
         float z = a.head_b;
         const float4* hw4 = reinterpret_cast<const float4*>(a.head_w);
 #pragma unroll
@@ -314,11 +332,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();   // (pair: the leader's MMAs read the peer's shared memory - nobody leaves before both are done)
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_p<PAIR>(tmem_base, TMEM_COLS);
   }
+}
+
+
+#define UB_CONV_HALO_PARAMS                                                                                               \
+  const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,                                     \
+      const __grid_constant__ CUtensorMap tmW /* box = BLOCK_N/2 rows */, const __grid_constant__ CUtensorMap tmOut,      \
+      const HaloArgs a
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(UB_CONV_HALO_PARAMS) {
+  conv_halo_body<BLOCK_N, false>(tmA0, tmA1, tmW, tmOut, a);
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo2_kernel(UB_CONV_HALO_PARAMS) {
+  conv_halo_body<BLOCK_N, true>(tmA0, tmA1, tmW, tmOut, a);
 }
 
 }  // namespace ub

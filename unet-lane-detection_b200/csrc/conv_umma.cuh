@@ -12,6 +12,14 @@
 // The 128 pixels of a tile are a TB x TH x TW box of the [B,H,W] grid, so a TMA 4-D box load at
 // (c0, w0+dx, h0+dy, b0) with zero OOB fill *is* the im2col tile for tap (dy,dx).
 //
+// Two launch forms of the same body (PAIR template parameter, ptx.cuh "CTA pair"):
+//   conv_umma_kernel<N>   one CTA per tile;
+//   conv_umma2_kernel<N>  a CTA pair (cta_group::2) takes two adjacent pixel tiles of the SAME column block and issues one
+//                         M = 256 MMA per step; each CTA loads its own A box and only HALF of the weight tile, so the B-operand
+//                         shared-memory fill and reads per SM halve and the ring is deeper (32 KB instead of 48 KB per stage at
+//                         BLOCK_N = 256). A missing odd tile is loaded at an out-of-range image index (zero fill) and its stores
+//                         are clipped away by the tensor map. Outputs are bit-identical to the 1-CTA form.
+//
 // Warp roles (320 threads): warp 0 = TMA producer (one elected thread), warp 1 = TMEM owner + MMA
 // issuer (one elected thread), warps 2..9 = epilogue: two warps per TMEM lane quarter. Persistent over
 // tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -49,10 +57,10 @@ struct ConvArgs {
 
 constexpr int CONV_THREADS = 320;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // weight rows held by ONE CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int MAX_STAGES = 8;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -69,14 +77,13 @@ struct ConvCfg {
   }
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
-                 const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
-                 const __grid_constant__ CUtensorMap tmO3, const ConvArgs a) {
-  using Cfg = ConvCfg<BLOCK_N>;
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2,
+                                               const CUtensorMap& tmA3, const CUtensorMap& tmW, const CUtensorMap& tmO0,
+                                               const CUtensorMap& tmO1, const CUtensorMap& tmO2, const CUtensorMap& tmO3,
+                                               const ConvArgs& a) {
+  using Cfg = ConvCfg<BLOCK_N, PAIR>;
+  constexpr int P = PAIR ? 2 : 1;   // CTAs that share one MMA
   constexpr int MAXS = Cfg::MAX_STAGES;
   constexpr int HALVES = BLOCK_N / 64;
   const int STAGES = a.stages;
@@ -105,33 +112,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], HALVES == 1 ? 128 : 256);
+      mbar_init(&tempty[s], P * (HALVES == 1 ? 128 : 256));   // the epilogue threads of every CTA of the group
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_p<PAIR>(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();   // (pair: the peer's barriers are initialised before anything signals them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kchunks = a.kc0 + a.kc1 + a.kc2 + a.kc3;
   const int num_kb = a.taps * kchunks;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
-  const int total_tiles = m_tiles * a.n_tiles;
+  const int m_groups = (m_tiles + P - 1) / P;
+  const int total_tiles = m_groups * a.n_tiles;   // work items (n_tile, m_group); this CTA's m_tile = P*m_group + rank
+  const uint32_t rank = pair_rank<PAIR>();
+  const bool leader = rank == 0;
+  const int pair0 = blockIdx.x / P, pair_step = gridDim.x / P;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: one elected thread runs the whole loop
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = pair0; t < total_tiles; t += pair_step) {
         const int n_tile = t % a.n_tiles;
-        const int m_tile = t / a.n_tiles;
-        const int w0 = (m_tile % a.tiles_w) * a.TW;
+        const int m_tile = P * (t / a.n_tiles) + static_cast<int>(rank);   // == m_tiles for the missing odd tile:
+        const int w0 = (m_tile % a.tiles_w) * a.TW;                        //    b0 lands past the batch, the box is zero-filled
         const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
         const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
         int kb = 0;
@@ -145,19 +155,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait_parked(&empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
-            mbar_expect_tx(&full[stage], a.a_bytes + Cfg::B_BYTES);
+            if (leader) mbar_expect_tx(&full[stage], P * (a.a_bytes + Cfg::B_BYTES));   // the loads of every CTA of the group
             if (ch < a.kc0) {
-              tma_load_4d(sA, &tmA0, &full[stage], ch * 64, w0 + dx, h0 + dy, b0);
+              tma_load_4d_p<PAIR>(sA, &tmA0, &full[stage], ch * 64, w0 + dx, h0 + dy, b0);
             } else if (ch < a.kc0 + a.kc1) {
-              tma_load_4d(sA, &tmA1, &full[stage], (ch - a.kc0) * 64, w0 + dx, h0 + dy, b0);
+              tma_load_4d_p<PAIR>(sA, &tmA1, &full[stage], (ch - a.kc0) * 64, w0 + dx, h0 + dy, b0);
             } else if (ch < a.kc0 + a.kc1 + a.kc2) {
-              tma_load_4d(sA, &tmA2, &full[stage], (ch - a.kc0 - a.kc1) * 64, w0 + dx, h0 + dy, b0);
+              tma_load_4d_p<PAIR>(sA, &tmA2, &full[stage], (ch - a.kc0 - a.kc1) * 64, w0 + dx, h0 + dy, b0);
             } else {
-              tma_load_4d(sA, &tmA3, &full[stage], (ch - a.kc0 - a.kc1 - a.kc2) * 64, w0 + dx, h0 + dy, b0);
+              tma_load_4d_p<PAIR>(sA, &tmA3, &full[stage], (ch - a.kc0 - a.kc1 - a.kc2) * 64, w0 + dx, h0 + dy, b0);
             }
-            // the weight map's box is half a tile (shared with the CTA-pair kernel, conv_umma2.cuh)
-            tma_load_2d(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N);
-            tma_load_2d(sB + Cfg::B_BYTES / 2, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N + BLOCK_N / 2);
+            // the weight map's box is HALF a tile (BLOCK_N/2 rows): a pair CTA loads its half, a single CTA both
+            if constexpr (PAIR) {
+              tma_load_2d_p<PAIR>(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+            } else {
+              tma_load_2d(sB, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N);
+              tma_load_2d(sB + Cfg::B_BYTES / 2, &tmW, &full[stage], kb * 64, n_tile * BLOCK_N + BLOCK_N / 2);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -169,13 +183,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: one elected thread runs the whole loop
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128 * P, BLOCK_N);
       const uint64_t d_hi = make_sw128_kmajor_desc(0, 1024, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = pair0; t < total_tiles; t += pair_step, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -183,21 +197,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES) & 0x3FFFFu;
           const uint64_t da = d_hi + (sA >> 4);
           const uint64_t db = d_hi + ((sA + Cfg::A_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // +32 bytes (16 bf16) along K inside the 128-byte swizzled row == +2 in the >>4 address field
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_f16_p<PAIR>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          umma_commit_p<PAIR>(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_p<PAIR>(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -228,11 +242,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};
     int st_ntile = -1;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = pair0; t < total_tiles; t += pair_step, ++it) {
       const int acc = it & 1;
       if (HALVES == 1 && acc != cg) continue;
       const int n_tile = t % a.n_tiles;
-      const int m_tile = t / a.n_tiles;
+      const int m_tile = P * (t / a.n_tiles) + static_cast<int>(rank);
       const int w0 = (m_tile % a.tiles_w) * a.TW;
       const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
       const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
@@ -282,7 +296,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (hf + 2 >= HALVES) {
           // this warp's last TMEM read of the tile: hand the accumulator stage back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tempty[acc]);
+          mbar_arrive_p<PAIR>(&tempty[acc]);
         }
         if (lane == 0) bulk_wait_group_read<0>();  // the previous unit's TMA store has finished reading the staging tile
         __syncwarp();
@@ -324,11 +338,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();   // (pair: the leader's MMAs read the peer's shared memory - nobody leaves before both are done)
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_p<PAIR>(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+
+
+#define UB_CONV_UMMA_PARAMS                                                                                              \
+  const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,                                    \
+      const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,                                \
+      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,                                 \
+      const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,                                \
+      const __grid_constant__ CUtensorMap tmO3, const ConvArgs a
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(UB_CONV_UMMA_PARAMS) {
+  conv_umma_body<BLOCK_N, false>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv_umma2_kernel(UB_CONV_UMMA_PARAMS) {
+  conv_umma_body<BLOCK_N, true>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
 }
 
 }  // namespace ub

@@ -208,6 +208,136 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);   // M / 16
 }
 
+// ---------------------------------------------------------------- CTA pair (cta_group::2)
+// Two CTAs of a cluster (two SMs of a TPC) run ONE tcgen05.mma of M = 256 per issue: each SM multiplies its own 128 rows of A
+// and holds only half of the B tile. Barrier protocol of the kernels that use it (conv_umma.cuh, conv_halo.cuh, PAIR = true):
+//   "full" barriers live in the leader (cluster rank 0): both CTAs' TMA loads complete_tx on them
+//       (cp.async.bulk.tensor ... .cta_group::2, barrier address mapped to rank 0 with mapa), the leader expects both;
+//   "empty" / "tfull" barriers exist in both CTAs: the leader's tcgen05.commit multicasts the arrive to both;
+//   "tempty" lives in the leader: the epilogue threads of both CTAs arrive on it remotely.
+// shared::cluster address of the same shared-memory offset in cluster rank 0 (the leader CTA of the pair)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all earlier MMAs of this thread are done) on the barrier at this offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// TMA loads into this CTA's shared memory whose completion is signalled on the LEADER's barrier (same offset).
+__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_addr(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_addr(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Arrive on the leader's copy of `bar` from either CTA of the pair. No cluster-scope release: the only thing handed over is
+// "my tcgen05.ld of this accumulator stage has completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it);
+// a .release.cluster arrive compiles to ERRBAR + a membar that waits for every earlier global store of the warp (the pool
+// stores) - 12 % of all stall samples in profiles/r1_ncu_full_halo2.txt, on the path that frees the TMEM stage.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+
+// ---- one spelling for both forms: PAIR = false -> this CTA only, PAIR = true -> the CTA pair (cta_group::2) ----------------
+template <bool PAIR>
+__device__ __forceinline__ uint32_t pair_rank() {
+  if constexpr (PAIR) return cluster_ctarank();
+  return 0u;
+}
+template <bool PAIR>
+__device__ __forceinline__ void tmem_alloc_p(uint32_t* smem_dst, uint32_t ncols) {
+  if constexpr (PAIR) {
+    tmem_alloc2(smem_dst, ncols);
+    tmem_relinquish2();
+  } else {
+    tmem_alloc(smem_dst, ncols);
+    tmem_relinquish();
+  }
+}
+template <bool PAIR>
+__device__ __forceinline__ void tmem_dealloc_p(uint32_t taddr, uint32_t ncols) {
+  if constexpr (PAIR) tmem_dealloc2(taddr, ncols); else tmem_dealloc(taddr, ncols);
+}
+// CTA barrier; for a pair also a cluster barrier (the peer's mbarriers are initialised / the leader's MMAs no longer read the
+// peer's shared memory)
+template <bool PAIR>
+__device__ __forceinline__ void cta_sync_p() {
+  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_f16_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PAIR) umma2_f16(tmem_d, desc_a, desc_b, idesc, accumulate); else umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+// arrive on `bar` (in both CTAs of a pair) once every earlier MMA of this thread has completed
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar) {
+  if constexpr (PAIR) umma2_commit_both(bar); else umma_commit(bar);
+}
+// TMA load into this CTA's shared memory; completion is signalled on `bar` of this CTA, or of the pair's leader
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_4d_p(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  if constexpr (PAIR) tma2_load_4d(smem_dst, m, bar, c0, c1, c2, c3); else tma_load_4d(smem_dst, m, bar, c0, c1, c2, c3);
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_2d_p(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (PAIR) tma2_load_2d(smem_dst, m, bar, c0, c1); else tma_load_2d(smem_dst, m, bar, c0, c1);
+}
+// arrive on this CTA's `bar`, or on the pair leader's
+template <bool PAIR>
+__device__ __forceinline__ void mbar_arrive_p(uint64_t* bar) {
+  if constexpr (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar);
+}
+
 // ---------------------------------------------------------------- gradient routing (data-parallel training)
 // Every parameter-gradient contribution is added with an fp32 atomic at `flat index` of the flat gradient. Single GPU: the
 // local buffer. Data parallel over NVLink: the flat gradient is cut into `world` contiguous shards; the atomic goes
