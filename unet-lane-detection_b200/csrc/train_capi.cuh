@@ -66,6 +66,8 @@ struct unet_b200_trainer {
   size_t acc_bytes;
   float* zero_bias;
   uint8_t* x_in;      // copy of the network input (NHWC4 bf16)
+  ub::PackJob* jobs_dev;   // job table of pack_all_kernel (one launch builds every bf16 operand copy of a step)
+  int n_jobs, pack_blocks;
   bool fwd_done;
 };
 
@@ -88,6 +90,7 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
   Bump bp{base, 0};
   const size_t B = t->B;
   t->zero_bias = reinterpret_cast<float*>(bp.take(4096 * 4));
+  t->jobs_dev = reinterpret_cast<ub::PackJob*>(bp.take(64 * sizeof(ub::PackJob)));
   t->x_in = bp.take(B * t->H * t->W * 8);
   // accumulators (zeroed per step): per conv sum, sumsq (double) + s1, s2 (float)
   t->acc = reinterpret_cast<uint8_t*>(base + bp.off);
@@ -382,9 +385,22 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
                                                                            c.sumsq);
     UB_CUDA(cudaGetLastError());
   }
-  ub::bn_finalize_kernel<<<(c.Cout + 127) / 128, 128, 0, st>>>(
-      c.sum, c.sumsq, (float)npix, eps, momentum, params + c.gamma_off, params + c.beta_off, c.mean, c.invstd, c.scale, c.shift,
-      running_mean ? running_mean[bn_idx] : nullptr, running_var ? running_var[bn_idx] : nullptr, c.Cout);
+  ub::BnFin fin;
+  fin.sum = c.sum;
+  fin.sumsq = c.sumsq;
+  fin.count = (float)npix;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = params + c.gamma_off;
+  fin.beta = params + c.beta_off;
+  fin.mean = c.mean;
+  fin.invstd = c.invstd;
+  fin.scale = c.scale;
+  fin.shift = c.shift;
+  fin.running_mean = running_mean ? running_mean[bn_idx] : nullptr;
+  fin.running_var = running_var ? running_var[bn_idx] : nullptr;
+  fin.C = c.Cout;
+  ub::bn_finalize_kernel<<<(c.Cout + 127) / 128, 128, 0, st>>>(fin);
   UB_CUDA(cudaGetLastError());
   if (c.pooled) {
     const size_t n = npix / 4 * C8;
@@ -659,6 +675,34 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
   trainer_layout(t, reinterpret_cast<uintptr_t>(workspace_dev));
   UB_CUDA(cudaMemset(t->zero_bias, 0, 4096 * 4));
   t->fwd_done = false;
+  {
+    std::vector<ub::PackJob> jobs;
+    int blocks = 0;
+    auto add = [&](int kind, int Cout, int Cin, long long w_off, uint8_t* wp, uint8_t* wd, size_t elems) {
+      ub::PackJob j;
+      j.kind = kind;
+      j.Cout = Cout;
+      j.Cin = Cin;
+      j.block0 = blocks;
+      j.w_off = w_off;
+      j.wp = reinterpret_cast<__nv_bfloat16*>(wp);
+      j.wd = reinterpret_cast<__nv_bfloat16*>(wd);
+      jobs.push_back(j);
+      blocks += (int)((elems + ub::PACK_ELEMS_PER_BLOCK - 1) / ub::PACK_ELEMS_PER_BLOCK);
+    };
+    for (TConv& c : t->convs) {
+      if (c.stem && c.Cout == 64) {
+        add(2, c.Cout, c.C0, c.w_off, c.wp, nullptr, (size_t)c.Cout * 64);
+      } else if (!c.stem) {
+        add(0, c.Cout, c.C0 + c.C1, c.w_off, c.wp, c.wd, (size_t)c.Cout * 9 * (c.C0 + c.C1));
+      }
+    }
+    for (TConvT& u : t->ups) add(1, u.f, u.Cin, u.w_off, u.wp, u.wd, (size_t)4 * u.f * u.Cin);
+    if (jobs.size() > 64) return fail(UB_ERR_ARG, "too many weight tensors for the pack job table");
+    t->n_jobs = (int)jobs.size();
+    t->pack_blocks = blocks;
+    UB_CUDA(cudaMemcpy(t->jobs_dev, jobs.data(), jobs.size() * sizeof(ub::PackJob), cudaMemcpyHostToDevice));
+  }
   return trainer_build_maps(t);
 }
 
@@ -670,32 +714,17 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   const int B = t->B;
   UB_CUDA(cudaMemcpyAsync(t->x_in, x_nhwc4, (size_t)B * t->H * t->W * 8, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemsetAsync(t->acc, 0, t->acc_bytes, st));
-  // bf16 operand copies of the current fp32 parameters: forward layout and the rotated/transposed dgrad layout
+  // bf16 operand copies of the current fp32 parameters (forward layout + the rotated / transposed dgrad layout): ONE launch
+  ub::pack_all_kernel<<<t->pack_blocks, 256, 0, st>>>(params, t->jobs_dev, t->n_jobs);
+  UB_CUDA(cudaGetLastError());
   for (TConv& c : t->convs) {
-    const int cin = c.C0 + c.C1;
-    const float* w = params + c.w_off;
-    if (c.stem && c.Cout == 64) {
-      ub::pack_stem_umma_kernel<<<grid_for(64 * 64, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, c.C0,
-                                                                         reinterpret_cast<__nv_bfloat16*>(c.wp), c.s1 /*bias scratch*/);
-    } else if (c.stem) {
-      ub::pack_stem_kernel<<<grid_for(36 * c.Cout, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, c.C0,
-                                                                       reinterpret_cast<float*>(c.wp), c.s1);
-    } else {
-      const size_t n = (size_t)c.Cout * 9 * cin;
-      ub::pack_conv3x3_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, nullptr, nullptr, nullptr, nullptr, 0.f, c.Cout, cin,
-                                                                reinterpret_cast<__nv_bfloat16*>(c.wp), c.s1);
-      ub::pack_conv3x3_dgrad_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, c.Cout, cin, reinterpret_cast<__nv_bfloat16*>(c.wd));
+    if (c.stem && c.Cout != 64) {   // FP32-pipe stem (widths other than 64): fp32 weights, its own small kernel
+      ub::pack_stem_kernel<<<grid_for(36 * c.Cout, 256), 256, 0, st>>>(params + c.w_off, nullptr, nullptr, nullptr, nullptr, 0.f,
+                                                                       c.Cout, c.C0, reinterpret_cast<float*>(c.wp), c.s1);
+      UB_CUDA(cudaGetLastError());
     }
-    UB_CUDA(cudaGetLastError());
   }
-  for (TConvT& u : t->ups) {
-    const size_t n = (size_t)4 * u.f * u.Cin;
-    ub::pack_convT_kernel<<<grid_for(n, 256), 256, 0, st>>>(params + u.w_off, u.Cin, u.f, reinterpret_cast<__nv_bfloat16*>(u.wp));
-    ub::pack_convT_dgrad_kernel<<<grid_for(n, 256), 256, 0, st>>>(params + u.w_off, u.Cin, u.f,
-                                                                  reinterpret_cast<__nv_bfloat16*>(u.wd));
-    UB_CUDA(cudaGetLastError());
-  }
-  // (the pack kernels' bias output is all zeros without BN; it lands in s1, which stays zero for the backward)
+  // (no bias without BN: s1 / s2 stay zero - cleared with the accumulator region above - until the backward uses them)
   int rc;
   for (int id : t->fwd_order) {
     if (id >= 0) {
@@ -1017,8 +1046,22 @@ int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* 
   ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(y), npix, C8, scratch2,
                                                                          scratch2 + C);
   UB_CUDA(cudaGetLastError());
-  ub::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch2, scratch2 + C, (float)npix, eps, momentum, gamma, beta, stats4,
-                                                          stats4 + C, stats4 + 2 * C, stats4 + 3 * C, running_mean, running_var, C);
+  ub::BnFin fin;
+  fin.sum = scratch2;
+  fin.sumsq = scratch2 + C;
+  fin.count = (float)npix;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.mean = stats4;
+  fin.invstd = stats4 + C;
+  fin.scale = stats4 + 2 * C;
+  fin.shift = stats4 + 3 * C;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.C = C;
+  ub::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(fin);
   UB_CUDA(cudaGetLastError());
   if (pool != nullptr) {
     ub::bn_relu_apply_pool_kernel<<<grid_for(npix / 4 * C8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
