@@ -17,6 +17,7 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, const float* __
                                     const float* __restrict__ beta, const float* __restrict__ mean,
                                     const float* __restrict__ var, float eps, int Cout, int Cin,
                                     __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  pdl_enter();
   const int total = Cout * 9 * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % Cin;
@@ -41,6 +42,7 @@ __global__ void pack_conv3x3_pad_kernel(const float* __restrict__ w, const float
                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                         const float* __restrict__ var, float eps, int Cout_l, int C0_l, int C1_l, int Cout_p,
                                         int C0_p, int C1_p, __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  pdl_enter();
   const int Cin_p = C0_p + C1_p, Cin_l = C0_l + C1_l;
   const int total = Cout_p * 9 * Cin_p;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -70,6 +72,7 @@ __global__ void pack_conv3x3_pad_kernel(const float* __restrict__ w, const float
 // ConvT: logical w[Cin_l][f_l][2][2] -> wp[(quad*f_p + co)][Cin_p], bias_p[f_p] (bias may be null: not written).
 __global__ void pack_convT_pad_kernel(const float* __restrict__ w, const float* __restrict__ b, int Cin_l, int f_l, int Cin_p,
                                       int f_p, __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_p) {
+  pdl_enter();
   const int total = 4 * f_p * Cin_p;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % Cin_p;
@@ -89,7 +92,8 @@ __global__ void pack_convT_pad_kernel(const float* __restrict__ w, const float* 
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ mean,
                                  const float* __restrict__ var, float eps, int Cout, int Cin,
-                                 float* __restrict__ ws, float* __restrict__ bias, int keep_fp32 = 0) {
+                                 float* __restrict__ ws, float* __restrict__ bias, int keep_fp32) {
+  pdl_enter();
   const int total = 9 * 4 * Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % Cout;
@@ -114,6 +118,7 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
 
 // ConvTranspose2d(Cin, f, 2, 2): -> wp[(dy*2+dx)*f + co][Cin] bf16 (GEMM N = 4f, K = Cin).
 __global__ void pack_convT_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wp) {
+  pdl_enter();
   const int total = 4 * f * Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % Cin;
@@ -140,6 +145,7 @@ __global__ void pack_conv3x3_split_kernel(const float* __restrict__ w, const flo
                                           const float* __restrict__ beta, const float* __restrict__ mean,
                                           const float* __restrict__ var, float eps, int Cout, int C0, int C1,
                                           __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  pdl_enter();
   const int Cin = C0 + C1, K3 = 3 * Cin;
   const int total = Cout * 9 * K3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -167,6 +173,7 @@ __global__ void pack_conv3x3_split_kernel(const float* __restrict__ w, const flo
 
 // ConvT: w [Cin][f][2][2] -> wp[4f][3*Cin] (row n = quad*f + co; K = [w_hi | w_hi | w_lo]).
 __global__ void pack_convT_split_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wp) {
+  pdl_enter();
   const int K3 = 3 * Cin;
   const int total = 4 * f * K3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -180,6 +187,7 @@ __global__ void pack_convT_split_kernel(const float* __restrict__ w, int Cin, in
 
 // 2x2/2 max-pool of a split tensor [B,H,W,2C]: the maximum is taken on hi + lo (fp32) and the winner's pair is copied.
 __global__ void maxpool2x2_split_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ y) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -221,6 +229,7 @@ __global__ void maxpool2x2_split_kernel(const uint4* __restrict__ x, int B, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, int B, int C, int H, int W,
                                      uint2* __restrict__ y) {
+  pdl_enter();
   const size_t hw = static_cast<size_t>(H) * W;
   const size_t total = static_cast<size_t>(B) * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -274,6 +283,7 @@ __device__ __forceinline__ int resize_blend(int h0, int h1, int by0, int by1) {
 }
 
 __global__ void preprocess_u8_kernel(const PreArgs a) {
+  pdl_enter();
   extern __shared__ uint8_t rows[];  // 2 x Ws*3 bytes
   const int y = blockIdx.x % a.H;
   const int b = blockIdx.x / a.H;
@@ -379,6 +389,7 @@ __device__ __forceinline__ void warp_pixel_u8(const uint8_t* __restrict__ frame,
 
 __global__ void __launch_bounds__(256)
 warp_preprocess_u8_kernel(const WarpPreArgs a) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(a.B) * a.H * a.W;
   const bool area2 = (a.Hw == 2 * a.H) && (a.Ww == 2 * a.W);
   double m[9];
@@ -428,6 +439,7 @@ warp_preprocess_u8_kernel(const WarpPreArgs a) {
 // Stand-alone warp (the bird's-eye image itself, e.g. for display): dst [B,Hw,Ww,3] = cv2.warpPerspective(src, M).
 __global__ void __launch_bounds__(256)
 warp_perspective_u8_kernel(const WarpPreArgs a, uint8_t* __restrict__ dst) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(a.B) * a.Hw * a.Ww;
   double m[9];
 #pragma unroll
@@ -449,6 +461,7 @@ warp_perspective_u8_kernel(const WarpPreArgs a, uint8_t* __restrict__ dst) {
 // One thread per 4 consecutive output pixels (one 32-bit store); the 224x224 source stays in L1/L2.
 __global__ void __launch_bounds__(256)
 resize_gray_u8_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, uint8_t* __restrict__ dst, int Hd, int Wd) {
+  pdl_enter();
   const int wq = (Wd + 3) / 4;
   const size_t total = static_cast<size_t>(B) * Hd * wq;
   const bool area2 = (Hs == 2 * Hd) && (Ws == 2 * Wd);
@@ -502,6 +515,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const void* __restrict__ xin, const float* __restrict__ ws, const float* __restrict__ bias,
                  int B, int H, int W, int Cin, int Cout, int relu, __nv_bfloat16* __restrict__ y) {
+  pdl_enter();
   const uint2* x = reinterpret_cast<const uint2*>(xin);
   extern __shared__ float sm[];
   float* sw = sm;                       // [9][4][Cout]
@@ -624,6 +638,7 @@ stem_conv_kernel(const void* __restrict__ xin, const float* __restrict__ ws, con
 __global__ void __launch_bounds__(256)
 head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, float bias, size_t npix, int C,
             float* __restrict__ logits, float* __restrict__ probs, uint8_t* __restrict__ mask, float thr) {
+  pdl_enter();
   const int sub = threadIdx.x & 7;
   const size_t gstride = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
   const size_t g0 = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3;
@@ -666,6 +681,7 @@ head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, fl
 
 // Stand-alone 2x2/2 max-pool on NHWC bf16 (used when the pool is not fused into a conv epilogue).
 __global__ void maxpool2x2_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ y) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;

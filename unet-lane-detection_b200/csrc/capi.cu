@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/unet_b200.h"
@@ -35,6 +36,29 @@ int fail(int code, const char* fmt, ...) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Every kernel launch of the library. With g_opt_pdl (unet_b200_set_option("pdl", 1)) a kernel may be scheduled before its
+// stream predecessor has drained (programmatic dependent launch; every kernel starts with pdl_enter(), ptx.cuh, so the ordering
+// of the data is unchanged). OFF by default: measured on B200 (tools/ab_option.py pdl, same box, alternating) it is SLOWER -
+// inference 17.0 k -> 16.4 k frames/s, training 18.9 -> 19.3 ms/step - the persistent one-CTA-per-SM kernels leave no room for
+// an early dependent, and its parked CTAs only get in the way of the tail.
+int g_opt_pdl = 0;
+
+template <typename... KArgs, typename... Args>
+void ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_opt_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError() at the call site
+}
 
 EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
@@ -221,7 +245,7 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
     const int pair_tiles = ((m_tiles + 1) / 2) * args.n_tiles;
     const int max_pairs = g_num_sms / 2;
     const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // cluster size 2 (__cluster_dims__)
-    ub::conv_umma2_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
+    ub_launch(ub::conv_umma2_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
@@ -236,7 +260,7 @@ int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap
   const int smem = Cfg::smem_bytes(args2.stages);
   const int total = m_tiles * args.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_umma_kernel<BN><<<grid, ub::CONV_THREADS, smem, st>>>(ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
+  ub_launch(ub::conv_umma_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -282,7 +306,7 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     const int pairs = (total + 1) / 2;
     const int max_pairs = g_num_sms / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)
-    ub::conv_halo2_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, args);
+    ub_launch(ub::conv_halo2_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
@@ -296,7 +320,7 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   }
   const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head);
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::conv_halo_kernel<BN><<<grid, ub::HALO_THREADS, smem, st>>>(a0, a1, w, mo, args);
+  ub_launch(ub::conv_halo_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -336,7 +360,7 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
   a.stat_sumsq = stat_sumsq;
   const int total = a.tiles_w * a.tiles_h * B;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  ub::stem_umma_kernel<<<grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st>>>(mw, mo, a);
+  ub_launch(ub::stem_umma_kernel, grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st, mw, mo, a);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -805,15 +829,15 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
     // logical Cout rows are written; rows / bias entries of padded channels keep the zeros the buffer was created with
     UB_CUDA(cudaMemsetAsync(p->wt + l.w_off, 0, (size_t)64 * 64 * 2, st));
     UB_CUDA(cudaMemsetAsync(bias, 0, (size_t)l.Cout * 4, st));
-    ub::pack_stem_umma_kernel<<<grid_for(64 * l.lCout, 256), 256, 0, st>>>(
+    ub_launch(ub::pack_stem_umma_kernel, grid_for(64 * l.lCout, 256), 256, 0, st, 
         w, gamma, beta, mean, var, eps, l.lCout, l.C0, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
   } else if (l.kind == L_STEM) {
     if (l.lCout != l.Cout) return fail(UB_ERR_ARG, "stem width %d needs the tensor-core stem (option stem_umma)", l.lCout);
-    ub::pack_stem_kernel<<<grid_for(36 * l.Cout, 256), 256, 0, st>>>(w, gamma, beta, mean, var, eps, l.Cout, l.C0,
-                                                                     reinterpret_cast<float*>(p->wt + l.w_off), bias);
+    ub_launch(ub::pack_stem_kernel, grid_for(36 * l.Cout, 256), 256, 0, st, w, gamma, beta, mean, var, eps, l.Cout, l.C0,
+                                                                     reinterpret_cast<float*>(p->wt + l.w_off), bias, 0);
   } else {
     const int cin = l.C0 + l.C1;
-    ub::pack_conv3x3_pad_kernel<<<grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st>>>(
+    ub_launch(ub::pack_conv3x3_pad_kernel, grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st, 
         w, gamma, beta, mean, var, eps, l.lCout, l.lC0, l.lC1, l.Cout, l.C0, l.C1,
         reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
   }
@@ -828,7 +852,7 @@ int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w, const f
   if (idx < 0 || idx >= (int)p->convt_ids.size()) return fail(UB_ERR_ARG, "convT index %d out of range", idx);
   Layer& l = p->layers[p->convt_ids[idx]];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ub::pack_convT_pad_kernel<<<grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st>>>(
+  ub_launch(ub::pack_convT_pad_kernel, grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st, 
       w, bias, l.lC0, l.lCout, l.C0, l.Cout, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off),
       reinterpret_cast<float*>(p->wt + l.b_off));
   UB_CUDA(cudaGetLastError());
@@ -857,6 +881,8 @@ int unet_b200_set_option(const char* name, int value) {
   if (name == nullptr) return fail(UB_ERR_ARG, "null option name");
   if (strcmp(name, "halo") == 0) {
     g_opt_halo = value;
+  } else if (strcmp(name, "pdl") == 0) {
+    g_opt_pdl = value;
   } else if (strcmp(name, "halo2") == 0) {
     g_opt_halo2 = value;
   } else if (strcmp(name, "umma2") == 0) {
@@ -894,7 +920,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     } else if (l.kind == L_STEM) {
       const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
       const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
-      ub::stem_conv_kernel<false><<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(x),
+      ub_launch(ub::stem_conv_kernel<false>, tiles, 256, smem, st, reinterpret_cast<const uint2*>(x),
                                                       reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch, l.H,
                                                       l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
       UB_CUDA(cudaGetLastError());
@@ -922,7 +948,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
   if (!p->layers.back().fuse_head) {
     const Buf& fb = p->bufs[p->final_buf];
     const size_t npix = (size_t)batch * fb.H * fb.W;
-    ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(
+    ub_launch(ub::head_kernel, grid_for(npix * 8, 256), 256, 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
         p->head_bias, npix, fb.C, logits, probs, mask, threshold);
     UB_CUDA(cudaGetLastError());
@@ -978,7 +1004,7 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8) {
 int unet_b200_nchw_to_nhwc4(const float* x, int batch, int C, int H, int W, void* y, void* stream) {
   if (x == nullptr || y == nullptr || C < 1 || C > 4) return fail(UB_ERR_ARG, "bad argument");
   const size_t n = (size_t)batch * H * W;
-  ub::nchw_to_nhwc4_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::nchw_to_nhwc4_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       x, batch, C, H, W, reinterpret_cast<uint2*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1010,7 +1036,7 @@ int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_
   if (smem > 48 * 1024) {
     UB_CUDA(cudaFuncSetAttribute(ub::preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  ub::preprocess_u8_kernel<<<batch * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  ub_launch(ub::preprocess_u8_kernel, batch * H, 256, smem, static_cast<cudaStream_t>(stream), a);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -1044,11 +1070,11 @@ int unet_b200_preprocess_warp_u8(const uint8_t* src, int batch, int Hs, int Ws, 
   a.dst_u8 = resized;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (y != nullptr) {
-    ub::warp_preprocess_u8_kernel<<<grid_for((size_t)batch * H * W, 256), 256, 0, st>>>(a);
+    ub_launch(ub::warp_preprocess_u8_kernel, grid_for((size_t)batch * H * W, 256), 256, 0, st, a);
     UB_CUDA(cudaGetLastError());
   }
   if (warped != nullptr) {
-    ub::warp_perspective_u8_kernel<<<grid_for((size_t)batch * Hw * Ww, 256), 256, 0, st>>>(a, warped);
+    ub_launch(ub::warp_perspective_u8_kernel, grid_for((size_t)batch * Hw * Ww, 256), 256, 0, st, a, warped);
     UB_CUDA(cudaGetLastError());
   }
   return UB_OK;
@@ -1060,7 +1086,7 @@ int unet_b200_resize_gray_u8(const uint8_t* src, int batch, int Hs, int Ws, uint
   int rc = device_check();
   if (rc != UB_OK) return rc;
   const size_t work = (size_t)batch * Hd * ((Wd + 3) / 4);
-  ub::resize_gray_u8_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, batch, Hs, Ws, dst, Hd, Wd);
+  ub_launch(ub::resize_gray_u8_kernel, grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream), src, batch, Hs, Ws, dst, Hd, Wd);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -1224,7 +1250,7 @@ int unet_b200_convT2x2(const void* x, int Cin, const void* wp, const float* bias
 int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
                            float eps, int Cout, int Cin, void* wp, float* bias, void* stream) {
   if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
-  ub::pack_conv3x3_kernel<<<grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_conv3x3_kernel, grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, gamma, beta, mean, var, eps, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wp), bias);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1232,7 +1258,7 @@ int unet_b200_pack_conv3x3(const float* w, const float* gamma, const float* beta
 
 int unet_b200_pack_convT2x2(const float* w, int Cin, int f, void* wp, void* stream) {
   if (w == nullptr || wp == nullptr) return fail(UB_ERR_ARG, "null argument");
-  ub::pack_convT_kernel<<<grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_convT_kernel, grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wp));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1242,8 +1268,8 @@ int unet_b200_pack_stem(const float* w, const float* gamma, const float* beta, c
                         float eps, int Cout, int Cin, float* ws, float* bias, void* stream) {
   if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
-  ub::pack_stem_kernel<<<grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias);
+  ub_launch(ub::pack_stem_kernel, grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
+      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 0);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -1254,7 +1280,7 @@ int unet_b200_stem_conv(const void* x, const float* ws, const float* bias, int B
   if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
   const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
   const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
-  ub::stem_conv_kernel<false><<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::stem_conv_kernel<false>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint2*>(x), ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1264,7 +1290,7 @@ int unet_b200_pack_stem_tc(const float* w, const float* gamma, const float* beta
                            float eps, int Cout, int Cin, void* wp, float* bias, void* stream) {
   if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (Cin < 1 || Cin > 4 || Cout != 64) return fail(UB_ERR_ARG, "tensor-core stem needs Cin in [1,4] and Cout == 64");
-  ub::pack_stem_umma_kernel<<<grid_for((size_t)64 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_stem_umma_kernel, grid_for((size_t)64 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, gamma, beta, mean, var, eps, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wp), bias);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1287,7 +1313,7 @@ int unet_b200_head(const void* x, const float* w, float bias, size_t npix, int C
                    uint8_t* mask, float threshold, void* stream) {
   if (x == nullptr || w == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (C % 8 != 0) return fail(UB_ERR_ARG, "head C=%d must be a multiple of 8", C);
-  ub::head_kernel<<<grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::head_kernel, grid_for(npix * 8, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), w, bias, npix, C, logits, probs, mask, threshold);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1297,7 +1323,7 @@ int unet_b200_maxpool2x2(const void* x, int B, int H, int W, int C, void* y, voi
   if (x == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (C % 8 != 0 || ((H | W) & 1)) return fail(UB_ERR_ARG, "maxpool needs C %% 8 == 0 and even H, W");
   const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  ub::maxpool2x2_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::maxpool2x2_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), B, H, W, C / 8, reinterpret_cast<uint4*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1368,7 +1394,7 @@ int unet_b200_pack_conv3x3_split(const float* w, const float* gamma, const float
                                  float eps, int Cout, int C0, int C1, void* wp, float* bias, void* stream) {
   if (w == nullptr || wp == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (C0 <= 0 || C1 < 0) return fail(UB_ERR_ARG, "bad channel split");
-  ub::pack_conv3x3_split_kernel<<<grid_for((size_t)Cout * 27 * (C0 + C1), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_conv3x3_split_kernel, grid_for((size_t)Cout * 27 * (C0 + C1), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, gamma, beta, mean, var, eps, Cout, C0, C1, reinterpret_cast<__nv_bfloat16*>(wp), bias);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1376,7 +1402,7 @@ int unet_b200_pack_conv3x3_split(const float* w, const float* gamma, const float
 
 int unet_b200_pack_convT2x2_split(const float* w, int Cin, int f, void* wp, void* stream) {
   if (w == nullptr || wp == nullptr) return fail(UB_ERR_ARG, "null argument");
-  ub::pack_convT_split_kernel<<<grid_for((size_t)12 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_convT_split_kernel, grid_for((size_t)12 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wp));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1386,7 +1412,7 @@ int unet_b200_pack_stem_fp32(const float* w, const float* gamma, const float* be
                              float eps, int Cout, int Cin, float* ws, float* bias, void* stream) {
   if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
-  ub::pack_stem_kernel<<<grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_stem_kernel, grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 1);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1399,7 +1425,7 @@ int unet_b200_stem_conv_split(const float* x_nchw, const float* ws, const float*
   if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
   const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
   const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
-  ub::stem_conv_kernel<true><<<tiles, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::stem_conv_kernel<true>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
       x_nchw, ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1409,7 +1435,7 @@ int unet_b200_maxpool2x2_split(const void* x, int B, int H, int W, int C, void* 
   if (x == nullptr || y == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (C % 8 != 0 || ((H | W) & 1)) return fail(UB_ERR_ARG, "maxpool needs C %% 8 == 0 and even H, W");
   const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  ub::maxpool2x2_split_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::maxpool2x2_split_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(x), B, H, W, C / 8, reinterpret_cast<uint4*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;

@@ -347,11 +347,13 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(UB_CONV_HALO_PARAMS) {
+  pdl_enter();
   conv_halo_body<BLOCK_N, false>(tmA0, tmA1, tmW, tmOut, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo2_kernel(UB_CONV_HALO_PARAMS) {
+  pdl_enter();
   conv_halo_body<BLOCK_N, true>(tmA0, tmA1, tmW, tmOut, a);
 }
 

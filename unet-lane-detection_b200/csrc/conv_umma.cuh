@@ -356,11 +356,13 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(UB_CONV_UMMA_PARAMS) {
+  pdl_enter();
   conv_umma_body<BLOCK_N, false>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv_umma2_kernel(UB_CONV_UMMA_PARAMS) {
+  pdl_enter();
   conv_umma_body<BLOCK_N, true>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
 }
 

@@ -25,6 +25,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// First statement of EVERY kernel of this library. launch_dependents: the next kernel in the stream (when it was launched with
+// the programmatic-serialization attribute, capi.cu ub_launch) may be scheduled as soon as every CTA of this grid has started,
+// so its launch latency and the wait for free SMs overlap this grid's tail. wait: this kernel touches no global memory before
+// its stream predecessor has completed and its writes are visible - the dependency itself is unchanged. Both are no-ops for
+// a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -40,6 +40,7 @@ __global__ void pack_stem_umma_kernel(const float* __restrict__ w, const float* 
                                       const float* __restrict__ beta, const float* __restrict__ mean,
                                       const float* __restrict__ var, float eps, int Cout, int Cin,
                                       __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  pdl_enter();
   const int total = Cout * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % 64, co = i / 64;
@@ -61,6 +62,7 @@ __global__ void pack_stem_umma_kernel(const float* __restrict__ w, const float* 
 
 __global__ void __launch_bounds__(StemCfg::THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
+  pdl_enter();
   using Cfg = StemCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

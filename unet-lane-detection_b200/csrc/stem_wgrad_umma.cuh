@@ -31,6 +31,7 @@ struct StemWgradCfg {
 
 __global__ void __launch_bounds__(StemWgradCfg::THREADS, 1)
 stem_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const StemWgradArgs a) {
+  pdl_enter();
   using Cfg = StemWgradCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -177,7 +177,7 @@ int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorM
     UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[slot] = 1;
   }
-  ub::wgrad_umma_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(x0, x1, d[0], d[1], d[2], d[3], a);
+  ub_launch(ub::wgrad_umma_kernel<BN>, grid, 192, Cfg::SMEM_BYTES, st, x0, x1, d[0], d[1], d[2], d[3], a);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -368,7 +368,7 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
     } else {
       const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
       const size_t smem = (size_t)(36 * c.Cout + c.Cout) * 4 + 18 * 18 * 16;
-      ub::stem_conv_kernel<false><<<tiles, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0), reinterpret_cast<const float*>(c.wp),
+      ub_launch(ub::stem_conv_kernel<false>, tiles, 256, smem, st, reinterpret_cast<const uint2*>(c.x0), reinterpret_cast<const float*>(c.wp),
                                                       t->zero_bias, B, c.H, c.W, c.C0, c.Cout, 0,
                                                       reinterpret_cast<__nv_bfloat16*>(c.y));
       UB_CUDA(cudaGetLastError());
@@ -381,7 +381,7 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   const size_t npix = (size_t)B * c.H * c.W;
   const int C8 = c.Cout / 8;
   if (!stats_done) {
-    ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(c.y), npix, C8, c.sum,
+    ub_launch(ub::chan_stats_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st, reinterpret_cast<const uint4*>(c.y), npix, C8, c.sum,
                                                                            c.sumsq);
     UB_CUDA(cudaGetLastError());
   }
@@ -400,16 +400,16 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   fin.running_mean = running_mean ? running_mean[bn_idx] : nullptr;
   fin.running_var = running_var ? running_var[bn_idx] : nullptr;
   fin.C = c.Cout;
-  ub::bn_finalize_kernel<<<(c.Cout + 127) / 128, 128, 0, st>>>(fin);
+  ub_launch(ub::bn_finalize_kernel, (c.Cout + 127) / 128, 128, 0, st, fin);
   UB_CUDA(cudaGetLastError());
   if (c.pooled) {
     const size_t n = npix / 4 * C8;
-    ub::bn_relu_apply_pool_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, B, c.H,
+    ub_launch(ub::bn_relu_apply_pool_kernel, grid_for(n, 256), 256, 0, st, reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, B, c.H,
                                                                     c.W, C8, reinterpret_cast<uint4*>(c.a),
                                                                     reinterpret_cast<uint4*>(c.p));
   } else {
     const size_t n8 = npix * C8;
-    ub::bn_relu_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, n8, C8,
+    ub_launch(ub::bn_relu_apply_kernel, grid_for(n8, 256), 256, 0, st, reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, n8, C8,
                                                                 reinterpret_cast<uint4*>(c.a));
   }
   UB_CUDA(cudaGetLastError());
@@ -425,11 +425,11 @@ int conv_bn_backward(const TConv& c, int B, float* s1, float* s2, const ub::Grad
   const int C8 = c.Cout / 8;
   const uint4* g4 = reinterpret_cast<const uint4*>(c.g);
   const uint4* y4 = reinterpret_cast<const uint4*>(c.y);
-  ub::bn_relu_bwd_reduce_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
+  ub_launch(ub::bn_relu_bwd_reduce_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st, g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
                                                                                  C8, s1, s2);
   UB_CUDA(cudaGetLastError());
   const size_t n8 = npix * C8;
-  ub::bn_relu_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, st>>>(g4, y4, c.scale, c.shift, c.mean, c.invstd, s1, s2,
+  ub_launch(ub::bn_relu_bwd_apply_kernel, grid_for(n8, 256), 256, 0, st, g4, y4, c.scale, c.shift, c.mean, c.invstd, s1, s2,
                                                                   1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g), route,
                                                                   off_gamma, off_beta);
   UB_CUDA(cudaGetLastError());
@@ -457,7 +457,7 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
     sa.off = off;
     const int pairs = (sa.tiles_w * sa.tiles_h * B + 1) / 2;
     const int grid = pairs < g_num_sms ? pairs : g_num_sms;
-    ub::stem_wgrad_umma_kernel<<<grid, ub::StemWgradCfg::THREADS, ub::StemWgradCfg::SMEM_BYTES, st>>>(c.wD, sa);
+    ub_launch(ub::stem_wgrad_umma_kernel, grid, ub::StemWgradCfg::THREADS, ub::StemWgradCfg::SMEM_BYTES, st, c.wD, sa);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
@@ -471,7 +471,7 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
     }
     const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
     const int grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
-    ub::stem_wgrad_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const uint2*>(c.x0),
+    ub_launch(ub::stem_wgrad_kernel, grid, 256, smem, st, reinterpret_cast<const uint2*>(c.x0),
                                                     reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, route, off);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
@@ -502,7 +502,7 @@ int up_wgrad_launch(const TConvT& u, int B, int pitch8, const ub::GradRoute& rou
   const size_t npix_up = (size_t)B * 4 * u.H * u.W;
   const int C8 = u.f / 8;
   if (off_b >= 0) {
-    ub::chan_sum_kernel<<<chan_grid(npix_up, C8), 256, 2048 * 4, st>>>(reinterpret_cast<const uint4*>(u.dup), pitch8, npix_up, C8,
+    ub_launch(ub::chan_sum_kernel, chan_grid(npix_up, C8), 256, 2048 * 4, st, reinterpret_cast<const uint4*>(u.dup), pitch8, npix_up, C8,
                                                                        route, off_b);
     UB_CUDA(cudaGetLastError());
   }
@@ -715,12 +715,12 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   UB_CUDA(cudaMemcpyAsync(t->x_in, x_nhwc4, (size_t)B * t->H * t->W * 8, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemsetAsync(t->acc, 0, t->acc_bytes, st));
   // bf16 operand copies of the current fp32 parameters (forward layout + the rotated / transposed dgrad layout): ONE launch
-  ub::pack_all_kernel<<<t->pack_blocks, 256, 0, st>>>(params, t->jobs_dev, t->n_jobs);
+  ub_launch(ub::pack_all_kernel, t->pack_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs);
   UB_CUDA(cudaGetLastError());
   for (TConv& c : t->convs) {
     if (c.stem && c.Cout != 64) {   // FP32-pipe stem (widths other than 64): fp32 weights, its own small kernel
-      ub::pack_stem_kernel<<<grid_for(36 * c.Cout, 256), 256, 0, st>>>(params + c.w_off, nullptr, nullptr, nullptr, nullptr, 0.f,
-                                                                       c.Cout, c.C0, reinterpret_cast<float*>(c.wp), c.s1);
+      ub_launch(ub::pack_stem_kernel, grid_for(36 * c.Cout, 256), 256, 0, st, params + c.w_off, nullptr, nullptr, nullptr, nullptr, 0.f,
+                                                                       c.Cout, c.C0, reinterpret_cast<float*>(c.wp), c.s1, 0);
       UB_CUDA(cudaGetLastError());
     }
   }
@@ -737,7 +737,7 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   }
   const TConv& last = t->convs.back();
   const size_t npix = (size_t)B * last.H * last.W;
-  ub::head_fwd_train_kernel<<<grid_for(npix * 8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(last.a),
+  ub_launch(ub::head_fwd_train_kernel, grid_for(npix * 8, 256), 256, 0, st, reinterpret_cast<const uint4*>(last.a),
                                                                      params + t->head_w_off, params + t->head_b_off, npix,
                                                                      last.Cout / 8, logits);
   UB_CUDA(cudaGetLastError());
@@ -757,7 +757,7 @@ static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const
   {
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
-    ub::head_bwd_kernel<<<chan_grid(npix, C8), 256, (2048 + 256) * 4, st>>>(
+    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st, 
         reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g), route,
         t->head_w_off, t->head_b_off);
     UB_CUDA(cudaGetLastError());
@@ -781,7 +781,7 @@ static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const
     const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
     const int C8 = c1.Cout / 8;
     const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
-    ub::maxpool_bwd_add_kernel<<<grid_for(n, 256), 256, 0, st>>>(
+    ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, st, 
         reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
         2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
     UB_CUDA(cudaGetLastError());
@@ -824,7 +824,7 @@ int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_b
   long long hi = lo + shard;
   if (hi > n) hi = n;
   if (hi <= lo) return UB_OK;
-  ub::adamw_shard_allgather_kernel<<<grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::adamw_shard_allgather_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       param_bases_dev, grad_bases_dev, world, rank, grads_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay,
       grad_scale, step_dev);
   UB_CUDA(cudaGetLastError());
@@ -846,7 +846,7 @@ int unet_b200_adamw_step_multimem(float* params_mc, const float* grads_mc, const
   long long hi = lo + shard;
   if (hi > n) hi = n;
   if (hi <= lo) return UB_OK;
-  ub::adamw_shard_multimem_kernel<<<grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::adamw_shard_multimem_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       params_mc, grads_mc, params_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale,
       step_dev);
   UB_CUDA(cudaGetLastError());
@@ -856,7 +856,7 @@ int unet_b200_adamw_step_multimem(float* params_mc, const float* grads_mc, const
 int unet_b200_multimem_reduce(const float* x_mc, long long lo, long long n, float* out, void* stream) {
   if (x_mc == nullptr || out == nullptr || n < 0) return fail(UB_ERR_ARG, "bad argument");
   if (n == 0) return UB_OK;
-  ub::multimem_reduce_kernel<<<grid_for((size_t)n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_mc, lo, n, out);
+  ub_launch(ub::multimem_reduce_kernel, grid_for((size_t)n, 256), 256, 0, static_cast<cudaStream_t>(stream), x_mc, lo, n, out);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -868,9 +868,9 @@ int unet_b200_bce_dice_loss(const float* logits, const float* target, size_t n, 
   if (rc != UB_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   UB_CUDA(cudaMemsetAsync(scratch4, 0, 4 * sizeof(double), st));
-  ub::bce_dice_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, scratch4);
+  ub_launch(ub::bce_dice_reduce_kernel, grid_for(n, 256), 256, 0, st, logits, target, n, pos_weight, scratch4);
   UB_CUDA(cudaGetLastError());
-  ub::bce_dice_grad_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, bce_weight, dice_weight,
+  ub_launch(ub::bce_dice_grad_kernel, grid_for(n, 256), 256, 0, st, logits, target, n, pos_weight, bce_weight, dice_weight,
                                                              smooth, scratch4, dlogits, losses3);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -883,9 +883,9 @@ int unet_b200_validation_metrics(const float* logits, const float* target, size_
   if (rc != UB_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   UB_CUDA(cudaMemsetAsync(scratch6, 0, 6 * sizeof(double), st));
-  ub::val_metrics_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(logits, target, n, pos_weight, threshold, scratch6);
+  ub_launch(ub::val_metrics_reduce_kernel, grid_for(n, 256), 256, 0, st, logits, target, n, pos_weight, threshold, scratch6);
   UB_CUDA(cudaGetLastError());
-  ub::val_metrics_finalize_kernel<<<1, 1, 0, st>>>(scratch6, n, bce_weight, dice_weight, smooth, out4);
+  ub_launch(ub::val_metrics_finalize_kernel, 1, 1, 0, st, scratch6, n, bce_weight, dice_weight, smooth, out4);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -898,7 +898,7 @@ int unet_b200_adamw_step(float* params, const float* grads, float* exp_avg, floa
   if (rc != UB_OK) return rc;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  ub::adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+  ub_launch(ub::adamw_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                    beta2, eps, weight_decay, bc1, bc2, grad_scale,
                                                                                    nullptr);
   UB_CUDA(cudaGetLastError());
@@ -912,7 +912,7 @@ int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, 
   }
   int rc = device_check();
   if (rc != UB_OK) return rc;
-  ub::adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+  ub_launch(ub::adamw_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                    beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
                                                                                    step_dev);
   UB_CUDA(cudaGetLastError());
@@ -922,7 +922,7 @@ int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, 
 // ---- single training ops (parity tests; the trainer above runs the same code on prebuilt maps) --------------------
 int unet_b200_pack_conv3x3_dgrad(const float* w, int Cout, int Cin, void* wd, void* stream) {
   if (w == nullptr || wd == nullptr) return fail(UB_ERR_ARG, "null argument");
-  ub::pack_conv3x3_dgrad_kernel<<<grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_conv3x3_dgrad_kernel, grid_for((size_t)Cout * 9 * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(wd));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -930,7 +930,7 @@ int unet_b200_pack_conv3x3_dgrad(const float* w, int Cout, int Cin, void* wd, vo
 
 int unet_b200_pack_convT2x2_dgrad(const float* w, int Cin, int f, void* wd, void* stream) {
   if (w == nullptr || wd == nullptr) return fail(UB_ERR_ARG, "null argument");
-  ub::pack_convT_dgrad_kernel<<<grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::pack_convT_dgrad_kernel, grid_for((size_t)4 * f * Cin, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, Cin, f, reinterpret_cast<__nv_bfloat16*>(wd));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -999,7 +999,7 @@ int unet_b200_convT2x2_wgrad(const void* x, int Cin, const void* dup, int dup_pi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dbias != nullptr) {
     const size_t npix_up = (size_t)B * 4 * H * W;
-    ub::chan_sum_kernel<<<chan_grid(npix_up, f / 8), 256, 2048 * 4, st>>>(reinterpret_cast<const uint4*>(u.dup), dup_pitch / 8,
+    ub_launch(ub::chan_sum_kernel, chan_grid(npix_up, f / 8), 256, 2048 * 4, st, reinterpret_cast<const uint4*>(u.dup), dup_pitch / 8,
                                                                           npix_up, f / 8, ub::GradRoute{nullptr, dbias, 0u}, 0);
     UB_CUDA(cudaGetLastError());
   }
@@ -1043,7 +1043,7 @@ int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* 
   const size_t npix = (size_t)B * H * W;
   const int C8 = C / 8;
   UB_CUDA(cudaMemsetAsync(scratch2, 0, (size_t)2 * C * sizeof(double), st));
-  ub::chan_stats_kernel<<<chan_grid(npix, C8), 256, 2 * 2048 * 4, st>>>(reinterpret_cast<const uint4*>(y), npix, C8, scratch2,
+  ub_launch(ub::chan_stats_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st, reinterpret_cast<const uint4*>(y), npix, C8, scratch2,
                                                                          scratch2 + C);
   UB_CUDA(cudaGetLastError());
   ub::BnFin fin;
@@ -1061,15 +1061,15 @@ int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* 
   fin.running_mean = running_mean;
   fin.running_var = running_var;
   fin.C = C;
-  ub::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(fin);
+  ub_launch(ub::bn_finalize_kernel, (C + 127) / 128, 128, 0, st, fin);
   UB_CUDA(cudaGetLastError());
   if (pool != nullptr) {
-    ub::bn_relu_apply_pool_kernel<<<grid_for(npix / 4 * C8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
+    ub_launch(ub::bn_relu_apply_pool_kernel, grid_for(npix / 4 * C8, 256), 256, 0, st, reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
                                                                                 stats4 + 3 * C, B, H, W, C8,
                                                                                 reinterpret_cast<uint4*>(a),
                                                                                 reinterpret_cast<uint4*>(pool));
   } else {
-    ub::bn_relu_apply_kernel<<<grid_for(npix * C8, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
+    ub_launch(ub::bn_relu_apply_kernel, grid_for(npix * C8, 256), 256, 0, st, reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
                                                                        stats4 + 3 * C, npix * C8, C8, reinterpret_cast<uint4*>(a));
   }
   UB_CUDA(cudaGetLastError());
@@ -1109,7 +1109,7 @@ int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, i
   if (rc != UB_OK) return rc;
   const int C8 = C / 8;
   const size_t n = (size_t)B * (H / 2) * (W / 2) * C8;
-  ub::maxpool_bwd_add_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(dP), reinterpret_cast<const uint4*>(dskip),
       dskip ? skip_pitch / 8 : C8, B, H, W, C8, reinterpret_cast<uint4*>(dA));
   UB_CUDA(cudaGetLastError());

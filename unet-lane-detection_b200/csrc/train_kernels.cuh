@@ -26,6 +26,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // sum[c] += sum_p y[p][c], sumsq[c] += sum_p y[p][c]^2
 __global__ void __launch_bounds__(256)
 chan_stats_kernel(const uint4* __restrict__ y, size_t npix, int C8, double* __restrict__ sum, double* __restrict__ sumsq) {
+  pdl_enter();
   extern __shared__ float red[];  // [2][256][8]
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -72,6 +73,7 @@ struct BnFin {
   int C;
 };
 __global__ void bn_finalize_kernel(const BnFin f) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= f.C) return;
   const double md = f.sum[c] / static_cast<double>(f.count);
@@ -96,6 +98,7 @@ __global__ void bn_finalize_kernel(const BnFin f) {
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                      size_t n8, int C8, uint4* __restrict__ a) {
+  pdl_enter();
   const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const int c = static_cast<int>(i0 % C8) * 8;
   float sc[8], sh[8];
@@ -118,6 +121,7 @@ bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scal
 __global__ void __launch_bounds__(256)
 bn_relu_apply_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int B,
                           int H, int W, int C8, uint4* __restrict__ a, uint4* __restrict__ pl) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -162,6 +166,7 @@ bn_relu_bwd_reduce_kernel(const uint4* __restrict__ dA, const uint4* __restrict_
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, size_t npix, int C8, float* __restrict__ s1,
                           float* __restrict__ s2) {
+  pdl_enter();
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -234,6 +239,7 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
                          const float* __restrict__ invstd, const float* __restrict__ s1, const float* __restrict__ s2,
                          float inv_count, size_t n8, int C8, uint4* __restrict__ dY, GradRoute route, long long off_gamma,
                          long long off_beta) {
+  pdl_enter();
   // block 0 also publishes d gamma = sum g*xhat (s2) and d beta = sum g (s1) into the (possibly remote) flat gradient
   if (blockIdx.x == 0 && route.local != nullptr) {
     for (int ch = threadIdx.x; ch < C8 * 8; ch += blockDim.x) {
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip,
                        int skip_pitch8 /* uint4 per pixel of d_skip (>= C8: it may be the first half of a concat gradient) */,
                        int B, int H, int W, int C8, uint4* __restrict__ dA) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -322,6 +329,7 @@ maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP
 __global__ void __launch_bounds__(256)
 head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias, size_t npix,
                       int C8, float* __restrict__ logits) {
+  pdl_enter();
   const int sub = threadIdx.x & 7;
   const size_t stride = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
   // the loop bound is warp-uniform (p0 is the warp's first pixel) so the shuffles always see all 32 lanes
@@ -347,6 +355,7 @@ head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, 
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
                 uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b) {
+  pdl_enter();
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -387,6 +396,7 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
 __global__ void __launch_bounds__(256)
 bce_dice_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight,
                        double* __restrict__ sums) {
+  pdl_enter();
   __shared__ double red[4][256];
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -417,6 +427,7 @@ bce_dice_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t,
 __global__ void __launch_bounds__(256)
 val_metrics_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight, float thr,
                           double* __restrict__ sums) {
+  pdl_enter();
   __shared__ double red[6][256];
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -444,6 +455,7 @@ val_metrics_reduce_kernel(const float* __restrict__ z, const float* __restrict__
 // out[0..3] = {total loss, bce, dice loss, dice score of the thresholded prediction}
 __global__ void val_metrics_finalize_kernel(const double* __restrict__ sums, size_t n, float bce_w, float dice_w, float smooth,
                                             float* __restrict__ out) {
+  pdl_enter();
   const double bce = sums[0] / static_cast<double>(n);
   const double dice = 1.0 - (2.0 * sums[1] + smooth) / (sums[2] + sums[3] + smooth);
   out[0] = static_cast<float>(bce_w * bce + dice_w * dice);
@@ -457,6 +469,7 @@ __global__ void __launch_bounds__(256)
 bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, size_t n, float pos_weight, float bce_w,
                      float dice_w, float smooth, const double* __restrict__ sums, float* __restrict__ dz,
                      float* __restrict__ losses) {
+  pdl_enter();
   const double inter = sums[1], S = sums[2], T = sums[3];
   const double num = 2.0 * inter + smooth, den = S + T + smooth;
   const float inv_n = 1.f / static_cast<float>(n);
@@ -487,6 +500,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_scale,
              const int* __restrict__ step_dev) {
+  pdl_enter();
   if (step_dev != nullptr) {
     const float st = static_cast<float>(*step_dev);
     bc1 = 1.f - powf(beta1, st);
@@ -532,6 +546,7 @@ adamw_shard_allgather_kernel(float* const* __restrict__ param_bases, float* cons
                              float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v, long long lo, long long hi,
                              float lr, float beta1, float beta2, float eps, float wd, float grad_scale,
                              const int* __restrict__ step_dev) {
+  pdl_enter();
   const float st = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
   const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
@@ -608,6 +623,7 @@ __global__ void __launch_bounds__(256)
 adamw_shard_multimem_kernel(float* __restrict__ params_mc, const float* __restrict__ grads_mc, const float* __restrict__ plocal,
                             float* __restrict__ m, float* __restrict__ v, long long lo, long long hi, float lr, float beta1,
                             float beta2, float eps, float wd, float grad_scale, const int* __restrict__ step_dev) {
+  pdl_enter();
   const float st = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
   const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
@@ -639,6 +655,7 @@ adamw_shard_multimem_kernel(float* __restrict__ params_mc, const float* __restri
 
 // out[i] = sum over replicas of x[lo + i], formed by the switch (multimem.ld_reduce) - the gradient check of the NVLS exchange
 __global__ void multimem_reduce_kernel(const float* __restrict__ x_mc, long long lo, long long n, float* __restrict__ out) {
+  pdl_enter();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     out[i] = multimem_ld_reduce_add(x_mc + lo + i);
@@ -647,6 +664,7 @@ __global__ void multimem_reduce_kernel(const float* __restrict__ x_mc, long long
 
 // dgrad weights: wd[ci][tap'][co] = w[co][ci][8 - tap'] (180-degree rotated, in/out swapped), bf16; w fp32 [Cout][Cin][3][3]
 __global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, __nv_bfloat16* __restrict__ wd) {
+  pdl_enter();
   const int total = Cin * 9 * Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % Cout;
@@ -658,6 +676,7 @@ __global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int Cout,
 
 // ConvT dgrad weights: wd[ci][(quad, co)] = w[ci][co][quad] (GEMM N = Cin rows, K = 4f); w fp32 [Cin][f][2][2]
 __global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, int Cin, int f, __nv_bfloat16* __restrict__ wd) {
+  pdl_enter();
   const int total = Cin * 4 * f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % f;
@@ -681,6 +700,7 @@ constexpr int PACK_ELEMS_PER_BLOCK = 256 * 8;
 
 __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs) {
+  pdl_enter();
   int j = 0;
   while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].block0) ++j;   // <= 23 jobs
   const PackJob jb = jobs[j];
@@ -725,6 +745,7 @@ pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jo
 
 // packed fp32 gradients -> PyTorch layouts: conv gp[co][tap][ci] -> g[co][ci][tap]; convT gp[quad][co][ci] -> g[ci][co][quad]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ gp, int Cout, int Cin, float* __restrict__ g) {
+  pdl_enter();
   const int total = Cout * Cin * 9;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % 9;
@@ -734,6 +755,7 @@ __global__ void unpack_conv_grad_kernel(const float* __restrict__ gp, int Cout, 
   }
 }
 __global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, int f, float* __restrict__ g) {
+  pdl_enter();
   const int total = Cin * f * 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int quad = i % 4;
@@ -746,6 +768,7 @@ __global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, 
 // per-channel sum of a bf16 NHWC tensor (ConvT bias gradient): out[c] += sum_p x[p][c]
 __global__ void __launch_bounds__(256)
 chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, GradRoute route, long long off) {
+  pdl_enter();
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
@@ -773,6 +796,7 @@ chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, s
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const uint2* __restrict__ x4, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int Cin, int Cout,
                   GradRoute route, long long off /* dW fp32 [Cout][Cin][3][3] */) {
+  pdl_enter();
   extern __shared__ float sm[];
   float4* st = reinterpret_cast<float4*>(sm);                 // [18][18] input pixels (4 ch fp32)
   float* sd = sm + 18 * 18 * 4;                                // [256 px][Cout] dy tile (fp32)

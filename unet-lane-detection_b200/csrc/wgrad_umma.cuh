@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                   const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
                   const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const WgradArgs a) {
+  pdl_enter();
   using Cfg = WgradCfg<BLOCK_N>;
   constexpr int NB = Cfg::NB;
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
