@@ -94,7 +94,11 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "halo" (default 1)      3x3 convs with Cout 64/128 and W % 8 == 0 run on the halo-patch kernel
  *   "fuse_head" (default 1) the 1x1 head + sigmoid + mask run in the last conv's epilogue when it is a halo layer
  *   "stem_umma" (default 1) the Cin<=4 -> 64 stem runs on tensor cores (in-kernel im2col) instead of the FP32 pipes
- * Both paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
+ *   "halo2" / "umma2" (default 1) the conv kernels run as CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, half of the weight
+ *                           tile per SM) whenever a layer has at least two pixel tiles; 0 = one CTA per tile. Bit-identical results.
+ *   "wgrad_rows64" (default 1) 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
+ *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
+ * All paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
 int unet_b200_set_option(const char* name, int value);
 
 /* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary). */

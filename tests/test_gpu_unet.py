@@ -313,3 +313,16 @@ def test_fp32_path_logits_within_1e4(U, gain):
     with torch.no_grad():
         yb = net(x.cuda()).cpu()
     assert (yb - y32).abs().max().item() > err   # the bf16 path is the coarser one (sanity: the switch does something)
+
+
+@pytest.mark.parametrize("feats,B,H,W", [([64, 128], 3, 64, 96), ([64, 128, 256], 1, 40, 56)])
+def test_fp32_path_other_topologies(U, feats, B, H, W):
+    """fp32-class path on shallower networks, non-square inputs and odd batches (partial tiles, odd pixel-tile counts)."""
+    ref, net = make_pair(U, feats, gain=20.0)
+    net.b200_precision = "fp32"
+    x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(77))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert y.shape == y32.shape
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_FP32 * max(1.0, y32.abs().max().item())
