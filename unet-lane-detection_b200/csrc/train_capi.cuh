@@ -68,6 +68,12 @@ struct unet_b200_trainer {
   uint8_t* x_in;      // copy of the network input (NHWC4 bf16)
   ub::PackJob* jobs_dev;   // job table of pack_all_kernel (one launch builds every bf16 operand copy of a step)
   int n_jobs, pack_blocks;
+  // weight-gradient side stream (backward): the wgrad GEMM of layer L is forked off after the layer's dgrad and runs next to
+  // the HBM-bound BatchNorm / pool backward passes of layer L-1; joined before the backward returns
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_fork;
+  int ev_next = 0;
   bool fwd_done;
 };
 
@@ -167,6 +173,7 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
 }
 
 int g_opt_wgrad_rows64 = 1;  // A/B switch: 64-pixel reduction tiles for BLOCK_N == 256
+int g_opt_wgrad_stream = 1;  // A/B switch: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
 
 template <int BN>
 int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
@@ -483,17 +490,33 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
   return launch_wgrad(c.w_bn, c.wX0, c.wX1, d, wa, c.w_grid, st);
 }
 
+// Stream the next weight-gradient launch goes to: the side stream, made to wait for everything enqueued on `st` so far
+// (fork), or `st` itself when the overlap is switched off. Works the same eagerly and under stream capture.
+int wgrad_stream(unet_b200_trainer* t, cudaStream_t st, cudaStream_t* out) {
+  *out = st;
+  if (!g_opt_wgrad_stream || t->s2 == nullptr) return UB_OK;
+  if (t->ev_next >= (int)t->ev_fork.size()) return fail(UB_ERR_STATE, "out of fork events");
+  cudaEvent_t ev = t->ev_fork[t->ev_next++];
+  UB_CUDA(cudaEventRecord(ev, st));
+  UB_CUDA(cudaStreamWaitEvent(t->s2, ev, 0));
+  *out = t->s2;
+  return UB_OK;
+}
+
 int trainer_conv_backward(unet_b200_trainer* t, TConv& c, const ub::GradRoute& route, cudaStream_t st) {
   const int B = t->B;
   int rc = conv_bn_backward(c, B, c.s1, c.s2, route, c.gamma_off, c.beta_off, st);
   if (rc != UB_OK) return rc;
-  rc = conv_wgrad_launch(c, B, route, c.w_off, st);
-  if (rc != UB_OK) return rc;
+  // dgrad first (the next layer's backward waits for it), then the wgrad is forked: it only feeds the gradient buffer, so it
+  // runs concurrently with the bandwidth-bound BN / pool backward kernels that follow on `st`
   if (c.dx != nullptr) {
     rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st);
     if (rc != UB_OK) return rc;
   }
-  return UB_OK;
+  cudaStream_t sw;
+  rc = wgrad_stream(t, st, &sw);
+  if (rc != UB_OK) return rc;
+  return conv_wgrad_launch(c, B, route, c.w_off, sw);
 }
 
 // ConvT backward pieces on prepared maps: bias gradient + weight gradient, and the input gradient.
@@ -521,9 +544,12 @@ int up_dgrad_launch(const TConvT& u, int B, const float* zero_bias, cudaStream_t
 }
 
 int trainer_up_backward(unet_b200_trainer* t, TConvT& u, const ub::GradRoute& route, cudaStream_t st) {
-  int rc = up_wgrad_launch(u, t->B, 2 * (u.f / 8), route, u.w_off, u.b_off, st);
+  int rc = up_dgrad_launch(u, t->B, t->zero_bias, st);
   if (rc != UB_OK) return rc;
-  return up_dgrad_launch(u, t->B, t->zero_bias, st);
+  cudaStream_t sw;
+  rc = wgrad_stream(t, st, &sw);
+  if (rc != UB_OK) return rc;
+  return up_wgrad_launch(u, t->B, 2 * (u.f / 8), route, u.w_off, u.b_off, sw);
 }
 
 float* g_zero_bias = nullptr;  // 4096 zero floats for the single-op entry points (allocated once per process)
@@ -657,7 +683,15 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   return UB_OK;
 }
 
-void unet_b200_trainer_destroy(unet_b200_trainer* t) { delete t; }
+void unet_b200_trainer_destroy(unet_b200_trainer* t) {
+  if (t == nullptr) return;
+  for (cudaEvent_t e : t->ev_fork) {
+    if (e != nullptr) cudaEventDestroy(e);
+  }
+  if (t->ev_join != nullptr) cudaEventDestroy(t->ev_join);
+  if (t->s2 != nullptr) cudaStreamDestroy(t->s2);
+  delete t;
+}
 size_t unet_b200_trainer_workspace_bytes(const unet_b200_trainer* t) { return t ? t->ws_bytes : 0; }
 long long unet_b200_trainer_num_params(const unet_b200_trainer* t) { return t ? t->n_params : 0; }
 int unet_b200_trainer_num_tensors(const unet_b200_trainer* t) { return t ? (int)t->tensor_off.size() - 1 : 0; }
@@ -675,6 +709,12 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
   trainer_layout(t, reinterpret_cast<uintptr_t>(workspace_dev));
   UB_CUDA(cudaMemset(t->zero_bias, 0, 4096 * 4));
   t->fwd_done = false;
+  if (t->s2 == nullptr) {
+    UB_CUDA(cudaStreamCreateWithFlags(&t->s2, cudaStreamNonBlocking));
+    UB_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    t->ev_fork.resize(t->convs.size() + t->ups.size() + 2);
+    for (cudaEvent_t& e : t->ev_fork) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   {
     std::vector<ub::PackJob> jobs;
     int blocks = 0;
@@ -750,6 +790,7 @@ static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const
   if (t == nullptr || dlogits == nullptr || params == nullptr || route.local == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (!t->fwd_done) return fail(UB_ERR_STATE, "train_backward needs a preceding train_forward");
   const int B = t->B, L = t->levels;
+  t->ev_next = 0;
   if (zero_local) UB_CUDA(cudaMemsetAsync(route.local, 0, (size_t)t->n_params * 4, st));
   // s1 received the pack kernels' (all-zero) bias in the forward and s2 was cleared with the accumulator region: both are
   // zero here, once per forward/backward pair
@@ -789,6 +830,10 @@ static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const
     if (rc != UB_OK) return rc;
     rc = trainer_conv_backward(t, t->convs[2 * i], route, st);
     if (rc != UB_OK) return rc;
+  }
+  if (t->ev_next > 0) {   // join: the gradient is complete on `st` when every forked wgrad has finished
+    UB_CUDA(cudaEventRecord(t->ev_join, t->s2));
+    UB_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
   }
   t->fwd_done = false;
   return UB_OK;
