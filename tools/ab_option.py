@@ -1,5 +1,6 @@
 """Same-box A/B of a library option (unet_b200_set_option): inference frames/s and training ms/step with the option at 0 and 1.
-   python tools/ab_option.py pdl"""
+   python tools/ab_option.py pdl            # values 0 1 0 1
+   python tools/ab_option.py <name> A B      # explicit pair of values"""
 import os
 import sys
 
@@ -10,7 +11,8 @@ import unet_lane_detection_b200 as U  # noqa: E402
 from unet_lane_detection_b200._lib import check, lib  # noqa: E402
 
 name = sys.argv[1].encode()
-for val in (0, 1, 0, 1):
+vals = [int(v) for v in sys.argv[2:4]] if len(sys.argv) >= 4 else [0, 1]
+for val in vals * 2:
     check(lib.unet_b200_set_option(name, val))
     torch.manual_seed(0)
     net = U.UNet(3, 1, [64, 128, 256, 512]).cuda().eval()
