@@ -97,6 +97,7 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "halo2" / "umma2" (default 1) the conv kernels run as CTA pairs (tcgen05 cta_group::2, M = 256 per MMA, half of the weight
  *                           tile per SM) whenever a layer has at least two pixel tiles; 0 = one CTA per tile. Bit-identical results.
  *   "wgrad_rows64" (default 1) 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
+ *   "wgrad2" (default 1)    CTA-pair weight-gradient kernel for Cout >= 128 (read when a trainer / wgrad call is set up)
  *   "wgrad_stream" (default 1) backward: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
  *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
  * All paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */

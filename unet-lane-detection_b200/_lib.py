@@ -109,5 +109,12 @@ def check(rc: int) -> None:
         raise UnetB200Error(f"libunet_b200 error {rc}: {lib.unet_b200_last_error().decode()}")
 
 
+# UB_OPTIONS="halo2=0,wgrad2=0": kernel-selection switches (include/unet_b200.h unet_b200_set_option) for A/B runs of
+# unmodified scripts. Unknown names fail loudly.
+for _kv in filter(None, os.environ.get("UB_OPTIONS", "").split(",")):
+    _k, _, _v = _kv.partition("=")
+    check(lib.unet_b200_set_option(_k.strip().encode(), int(_v)))
+
+
 def f3(vals):
     return (f32 * 3)(*[float(v) for v in vals])

@@ -188,6 +188,7 @@ int g_opt_halo = 1;       // use conv_halo_kernel where eligible
 int g_opt_fuse_head = 1;  // fold the 1x1 head into the last conv's epilogue where eligible
 extern int g_opt_wgrad_rows64;
 extern int g_opt_wgrad_stream;
+extern int g_opt_wgrad2;
 int g_opt_stem_umma = 1;  // run the Cout == 64 stem on tensor cores (stem_umma.cuh) instead of the FP32-pipe kernel
 
 bool halo_eligible(int H, int W, int C0, int C1, int Cout) {
@@ -894,6 +895,8 @@ int unet_b200_set_option(const char* name, int value) {
     g_opt_stem_umma = value;
   } else if (strcmp(name, "wgrad_rows64") == 0) {
     g_opt_wgrad_rows64 = value;
+  } else if (strcmp(name, "wgrad2") == 0) {
+    g_opt_wgrad2 = value;
   } else if (strcmp(name, "wgrad_stream") == 0) {
     g_opt_wgrad_stream = value;
   } else {

@@ -33,6 +33,7 @@ struct TConv {
   CUtensorMap wX0, wX1, wD;
   ub::WgradArgs wa;
   int w_bn, w_grid;
+  bool w_pair;
 };
 
 struct TConvT {
@@ -47,6 +48,7 @@ struct TConvT {
   CUtensorMap wX, wDq[4];
   ub::WgradArgs wa;
   int w_bn, w_grid;
+  bool w_pair;
 };
 
 }  // namespace
@@ -173,13 +175,25 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
 }
 
 int g_opt_wgrad_rows64 = 1;  // A/B switch: 64-pixel reduction tiles for BLOCK_N == 256
+int g_opt_wgrad2 = 1;        // A/B switch: CTA-pair weight-gradient kernel (wgrad_umma2_kernel) for BLOCK_N >= 128
 int g_opt_wgrad_stream = 1;  // A/B switch: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
 
 template <int BN>
 int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
-                   int slot, cudaStream_t st) {
-  static int attr_done[3] = {0, 0, 0};
+                   int slot, bool pair, cudaStream_t st) {
+  static int attr_done[6] = {0, 0, 0, 0, 0, 0};
   using Cfg = ub::WgradCfg<BN>;
+  if constexpr (BN >= 128) {
+    if (pair) {
+      if (!attr_done[3 + slot]) {
+        UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done[3 + slot] = 1;
+      }
+      ub_launch(ub::wgrad_umma2_kernel<BN>, grid, 192, Cfg::SMEM_BYTES, st, x0, x1, d[0], d[1], d[2], d[3], a);
+      UB_CUDA(cudaGetLastError());
+      return UB_OK;
+    }
+  }
   if (!attr_done[slot]) {
     UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[slot] = 1;
@@ -189,18 +203,19 @@ int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorM
   return UB_OK;
 }
 
+// `pair`: the geometry in `a` (ksplit, stages, grid) was planned for the CTA-pair kernel (wgrad_geometry)
 int launch_wgrad(int bn, const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
-                 cudaStream_t st) {
+                 bool pair, cudaStream_t st) {
   switch (bn) {
-    case 64: return launch_wgrad_t<64>(x0, x1, d, a, grid, 0, st);
-    case 128: return launch_wgrad_t<128>(x0, x1, d, a, grid, 1, st);
-    case 256: return launch_wgrad_t<256>(x0, x1, d, a, grid, 2, st);
+    case 64: return launch_wgrad_t<64>(x0, x1, d, a, grid, 0, false, st);
+    case 128: return launch_wgrad_t<128>(x0, x1, d, a, grid, 1, pair, st);
+    case 256: return launch_wgrad_t<256>(x0, x1, d, a, grid, 2, pair, st);
   }
   return fail(UB_ERR_ARG, "unsupported wgrad BLOCK_N %d", bn);
 }
 
 // Common part of the weight-gradient launch geometry: pixel tiles, split-K, grid.
-int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int taps, int* bn, int* grid) {
+int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int taps, int* bn, int* grid, bool* pair) {
   memset(&a, 0, sizeof(a));
   a.B = B;
   a.H = H;
@@ -228,8 +243,6 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   a.Cin = Cin;
   a.Cout = Cout;
   a.n_tiles = Cout / *bn;
-  a.stages = ub::WGRAD_RING_BYTES / ((2 + *bn / 64) * a.blk_bytes);
-  if (a.stages > ub::WGRAD_MAX_STAGES) a.stages = ub::WGRAD_MAX_STAGES;
   if (taps == 9 && Cin == 64) {
     a.pair_taps = 1;
     a.m_tiles = 5;
@@ -238,20 +251,27 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
     a.pair_taps = 0;
     a.m_tiles = Cin / 128;
   }
-  const int tiles = (a.pair_taps ? 1 : taps) * a.m_tiles * a.n_tiles;
+  a.rt_total = (a.pair_taps ? 1 : taps) * a.m_tiles;
+  // CTA pair: two consecutive row tiles share the dy operand. For a 3x3 conv any two row tiles do (the taps shift only x);
+  // the ConvT quads read dy through different views, so there both tiles must belong to the same quad (m_tiles even).
+  *pair = g_opt_wgrad2 && *bn >= 128 && a.rt_total >= 2 && (taps != 4 || a.m_tiles % 2 == 0);
+  const int P = *pair ? 2 : 1;
+  a.stages = ub::WGRAD_RING_BYTES / ((2 + *bn / 64 / P) * a.blk_bytes);
+  if (a.stages > ub::WGRAD_MAX_STAGES) a.stages = ub::WGRAD_MAX_STAGES;
+  const int tiles = ((a.rt_total + P - 1) / P) * a.n_tiles;   // work items per K slice (each runs on P CTAs)
   const int ptiles = a.tiles_w * a.tiles_h * a.tiles_b;
-  int ks = g_num_sms / tiles;
+  int ks = (g_num_sms / P) / tiles;
   if (ks < 1) ks = 1;
   if (ks > ptiles) ks = ptiles;
   a.ksplit = ks;
-  *grid = tiles * ks;
+  *grid = P * tiles * ks;
   return UB_OK;
 }
 
 // weight gradient of a 3x3 conv: dW[co][ci][tap] += sum_p dY[p][co] * x[p + shift(tap)][ci]   (x = cat(x0, x1), dY = c.g)
 int setup_conv_wgrad(TConv& c, int B) {
   const int cin = c.C0 + c.C1;
-  int rc = wgrad_geometry(c.wa, B, c.H, c.W, cin, c.Cout, 9, &c.w_bn, &c.w_grid);
+  int rc = wgrad_geometry(c.wa, B, c.H, c.W, cin, c.Cout, 9, &c.w_bn, &c.w_grid, &c.w_pair);
   if (rc != UB_OK) return rc;
   c.wa.shift = 1;
   c.wa.c_split = c.C0;
@@ -301,7 +321,7 @@ int setup_up_backward(TConvT& u, int B, size_t pitch = 0) {
   }
   // weight gradient: dW[ci][co][quad] += sum_p x[p][ci] * dUp_quad[p][co]
   if (u.x != nullptr) {
-    rc = wgrad_geometry(u.wa, B, u.H, u.W, u.Cin, u.f, 4, &u.w_bn, &u.w_grid);
+    rc = wgrad_geometry(u.wa, B, u.H, u.W, u.Cin, u.f, 4, &u.w_bn, &u.w_grid, &u.w_pair);
     if (rc != UB_OK) return rc;
     u.wa.shift = 0;
     u.wa.c_split = u.Cin;
@@ -487,7 +507,7 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
   wa.route = route;
   wa.off = off;
   const CUtensorMap d[4] = {c.wD, c.wD, c.wD, c.wD};
-  return launch_wgrad(c.w_bn, c.wX0, c.wX1, d, wa, c.w_grid, st);
+  return launch_wgrad(c.w_bn, c.wX0, c.wX1, d, wa, c.w_grid, c.w_pair, st);
 }
 
 // Stream the next weight-gradient launch goes to: the side stream, made to wait for everything enqueued on `st` so far
@@ -532,7 +552,7 @@ int up_wgrad_launch(const TConvT& u, int B, int pitch8, const ub::GradRoute& rou
   ub::WgradArgs wa = u.wa;
   wa.route = route;
   wa.off = off_w;
-  return launch_wgrad(u.w_bn, u.wX, u.wX, u.wDq, wa, u.w_grid, st);
+  return launch_wgrad(u.w_bn, u.wX, u.wX, u.wDq, wa, u.w_grid, u.w_pair, st);
 }
 
 // dX[b,h,w,ci] = sum_quad sum_co dUp[b,2h+dy,2w+dx,co] * w[ci][co][quad]: 1-tap GEMM, K walks the four quad views

@@ -11,6 +11,10 @@
 // (split-K), then adds it to the fp32 gradient with red.global.add. The 128 rows are either 2 x 64 input channels
 // (Cin >= 128, possibly from two source tensors for the decoder concat) or, for Cin == 64, the SAME 64 channels at
 // two different taps (two shifted boxes), so M = 128 is always full.
+// Two launch forms of the same body (PAIR, ptx.cuh "CTA pair"): wgrad_umma_kernel<N> = one CTA per output tile;
+// wgrad_umma2_kernel<N> (N >= 128) = a CTA pair takes two consecutive row tiles (two ci blocks, or two taps when Cin <= 128)
+// of the SAME column block and K slice: M = 256 per MMA, each CTA loads its own x boxes and only HALF of the dy blocks, so a
+// third / a quarter less operand traffic is pulled through L2 (the 1-CTA form is L2-bound: profiles/r1_ncu_full_train_wgrad256.txt).
 // Also used for ConvTranspose2d weight gradients: "taps" are the four (dy,dx) quads and the dy operand is read
 // through the strided quad views of the upsampled gradient.
 #pragma once
@@ -35,6 +39,7 @@ struct WgradArgs {
   int a_bytes;                    // bytes one x / dy box load delivers (box rows * 128; fewer rows when TB exceeds the batch)
   int blk_bytes;                  // shared-memory pitch of one 64-channel box (full box rows * 128) = LBO of the descriptors
   int stages;                     // operand ring depth chosen by the host (<= WGRAD_MAX_STAGES)
+  int rt_total;                   // row tiles = m_tiles * (pair_taps ? 1 : taps); a CTA pair takes two consecutive ones
   GradRoute route;                // where gradient atomics go (local buffer, or the owner rank's buffer over NVLink)
   long long off;                  // flat index of this tensor's first element
 };
@@ -64,14 +69,14 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
   return d;
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
-wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
-                  const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
-                  const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const WgradArgs a) {
-  pdl_enter();
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void wgrad_umma_body(const CUtensorMap& tmX0, const CUtensorMap& tmX1, const CUtensorMap& tmD0,
+                                                const CUtensorMap& tmD1, const CUtensorMap& tmD2, const CUtensorMap& tmD3,
+                                                const WgradArgs& a) {
+  constexpr int P = PAIR ? 2 : 1;       // CTAs that share one MMA
   using Cfg = WgradCfg<BLOCK_N>;
-  constexpr int NB = Cfg::NB;
+  constexpr int NB = Cfg::NB / P;       // 64-channel dy blocks loaded by ONE CTA
+  static_assert(!PAIR || Cfg::NB >= 2, "the CTA-pair form needs BLOCK_N >= 128");
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   const int STAGES = a.stages;
   const int BLK = a.blk_bytes;
@@ -99,22 +104,26 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_p<PAIR>(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item: (output tile, K slice)
-  int wi = blockIdx.x;
+  // work item: (row-tile group, column block, K slice); row tile rt = m_tile + m_tiles * tap
+  const uint32_t rank = pair_rank<PAIR>();
+  const bool leader = rank == 0;
+  int wi = blockIdx.x / P;
   const int ks = wi % a.ksplit;
   wi /= a.ksplit;
   const int n_tile = wi % a.n_tiles;
   wi /= a.n_tiles;
-  const int m_tile = wi % a.m_tiles;
-  const int tap_o = a.pair_taps ? 0 : wi / a.m_tiles;  // tap of this tile (pair mode: taps come from m_tile)
+  const int rt = P * wi + static_cast<int>(rank);
+  const bool dummy = rt >= a.rt_total;               // odd row-tile count: the pair's second CTA repeats the last tile,
+  const int rtc = dummy ? a.rt_total - 1 : rt;       //   its result is dropped
+  const int m_tile = rtc % a.m_tiles;
+  const int tap_o = a.pair_taps ? 0 : rtc / a.m_tiles;  // tap of this tile (pair_taps mode: taps come from m_tile)
   const int ptiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int k_lo = static_cast<int>(static_cast<long long>(ptiles) * ks / a.ksplit);
   const int k_hi = static_cast<int>(static_cast<long long>(ptiles) * (ks + 1) / a.ksplit);
@@ -130,7 +139,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         mbar_wait_parked(&empty[stage], phase ^ 1);
         uint8_t* sA = smem + stage * STAGE_BYTES;
         uint8_t* sB = sA + 2 * BLK;
-        mbar_expect_tx(&full[stage], (2 + NB) * a.a_bytes);
+        if (leader) mbar_expect_tx(&full[stage], P * (2 + NB) * a.a_bytes);   // the loads of every CTA of the group
         // x operand: two 64-row blocks
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
@@ -146,9 +155,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             dx = tap % 3 - 1;
           }
           if (c < a.c_split) {
-            tma_load_4d(sA + hb * BLK, &tmX0, &full[stage], c, w0 + dx, h0 + dy, b0);
+            tma_load_4d_p<PAIR>(sA + hb * BLK, &tmX0, &full[stage], c, w0 + dx, h0 + dy, b0);
           } else {
-            tma_load_4d(sA + hb * BLK, &tmX1, &full[stage], c - a.c_split, w0 + dx, h0 + dy, b0);
+            tma_load_4d_p<PAIR>(sA + hb * BLK, &tmX1, &full[stage], c - a.c_split, w0 + dx, h0 + dy, b0);
           }
         }
         // dy operand: NB 64-channel blocks (ConvT: through the quad view of this tile's tap)
@@ -156,7 +165,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         if (a.taps == 4) md = tap_o == 0 ? &tmD0 : tap_o == 1 ? &tmD1 : tap_o == 2 ? &tmD2 : &tmD3;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          tma_load_4d(sB + nb * BLK, md, &full[stage], n_tile * BLOCK_N + nb * 64, w0, h0, b0);
+          tma_load_4d_p<PAIR>(sB + nb * BLK, md, &full[stage], n_tile * BLOCK_N + (static_cast<int>(rank) * NB + nb) * 64, w0, h0, b0);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -166,30 +175,30 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
       // both operands MN-major: bits 15 / 16 of the instruction descriptor
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N) | (1u << 15) | (1u << 16);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128 * P, BLOCK_N) | (1u << 15) | (1u << 16);
       const uint64_t d_hi = make_sw128_mnmajor_desc(0, BLK, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = k_lo; kt < k_hi; ++kt) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES) & 0x3FFFFu;
         const uint64_t da = d_hi + (sA >> 4);
         const uint64_t db = d_hi + ((sA + 2 * BLK) >> 4);
 #pragma unroll
         for (int j = 0; j < a.k_mmas; ++j) {
           // 16 pixel rows per MMA = two 8-row groups = 2048 B
-          umma_f16(tmem_base, da + j * 128, db + j * 128, idesc, (kt > k_lo || j > 0) ? 1u : 0u);
+          umma_f16_p<PAIR>(tmem_base, da + j * 128, db + j * 128, idesc, (kt > k_lo || j > 0) ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);
+        umma_commit_p<PAIR>(&empty[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(done);
+      umma_commit_p<PAIR>(done);
     }
     __syncwarp();
   } else {
@@ -199,7 +208,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     mbar_wait(done, 0);
     tc_fence_after();
     int tap = tap_o, ci = m_tile * 128 + m;
-    bool live = k_hi > k_lo;
+    bool live = k_hi > k_lo && !dummy;
     if (a.pair_taps) {
       tap = m_tile * 2 + (m >> 6);
       ci = m & 63;
@@ -222,11 +231,29 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  cta_sync_p<PAIR>();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_p<PAIR>(tmem_base, TMEM_COLS);
   }
+}
+
+
+#define UB_WGRAD_PARAMS                                                                                                   \
+  const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,                                    \
+      const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,                                \
+      const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3, const WgradArgs a
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) wgrad_umma_kernel(UB_WGRAD_PARAMS) {
+  pdl_enter();
+  wgrad_umma_body<BLOCK_N, false>(tmX0, tmX1, tmD0, tmD1, tmD2, tmD3, a);
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad_umma2_kernel(UB_WGRAD_PARAMS) {
+  pdl_enter();
+  wgrad_umma_body<BLOCK_N, true>(tmX0, tmX1, tmD0, tmD1, tmD2, tmD3, a);
 }
 
 }  // namespace ub
