@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=128, help="frames per pass through the plan")
+    ap.add_argument("--chunk", type=int, default=256, help="frames per pass through the plan (256 = the whole batch in one pass)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: BASELINE.json headline (configs[1]); train: the training step of configs[3] as the metric")
@@ -359,11 +359,11 @@ def main():
     # sum over its launches of one pass, i.e. the same unit as flops_per_pass; only valid for the captured geometry
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if os.path.exists(tpath) and (H, W) == (224, 224) and int(x4.shape[0]) == 128:
+    if os.path.exists(tpath) and (H, W) == (224, 224):
         with open(tpath) as f:
             tj = json.load(f)
         fam_t = tj["families"].get("conv_umma2_kernel<256>")
-        if fam_t and fam_t["launches"] == dom["launches"]:
+        if fam_t and fam_t["launches"] == dom["launches"] and tj.get("chunk") == int(x4.shape[0]):
             traffic = fam_t["dram_read_bytes"] + fam_t["dram_write_bytes"]
             traffic_src = "profiles/r1_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
     roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
