@@ -66,16 +66,61 @@ def build_model_cpu(seed=0):
     return m.eval()
 
 
+def physical_gpu_index():
+    """Index nvidia-smi / NVML know this process's first visible GPU by (CUDA_VISIBLE_DEVICES may hold indices or UUIDs)."""
+    first = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0].strip()
+    try:
+        return int(first)
+    except ValueError:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=index,uuid", "--format=csv,noheader"], capture_output=True, text=True,
+                                 timeout=10).stdout
+            for line in out.splitlines():
+                idx, uuid = [c.strip() for c in line.split(",")]
+                if uuid.startswith(first) or first.startswith(uuid):
+                    return int(idx)
+        except Exception:  # noqa: BLE001
+            pass
+        return 0
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / throttle reasons sampled WHILE the timed region runs: NVML in-process every 20 ms (the GPU index is the
+    physical one, NVML ignores CUDA_VISIBLE_DEVICES); `nvidia-smi` polling as the fallback when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.sm_max, self.power = None, []
+        self.source = "nvidia-smi"
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self._halt.is_set():
+            mask = int(reasons_fn(h))
+            self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(self.sm_max), "",
+                              *["Active" if mask & self.BITS[n] else "Not Active" for n in self.NAMES]])
+            try:
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.02)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:  # noqa: BLE001  (no pynvml / NVML error: poll nvidia-smi instead)
+            pass
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -91,13 +136,15 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+               "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 def cpu_reference_pipeline(model_cpu, frames_u8_nhwc, threshold=0.5):
@@ -281,7 +328,7 @@ def main():
 
     if args.mode == "train":
         peaks = load_peaks()
-        sampler = ClockSampler(index=int(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]) if rank == 0 else 0)
+        sampler = ClockSampler(index=physical_gpu_index() if rank == 0 else 0)
         if rank == 0:
             sampler.start()
         tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True,
@@ -316,7 +363,7 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(index=int(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]) if rank == 0 else 0)
+    sampler = ClockSampler(index=physical_gpu_index() if rank == 0 else 0)
     if rank == 0:
         sampler.start()
     l0 = model.gpu_launches
