@@ -89,8 +89,12 @@ class UNet(nn.Module):
     def _weights_key(self):
         return (self._b200_epoch,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
-    def _engine(self, device, H, W, batch):
+    def _engine(self, device, H, W, batch, pipelined=False):
         cap = min(max(1, int(self.b200_chunk)), batch) if batch < self.b200_chunk else int(self.b200_chunk)
+        if pipelined and batch >= 64 and cap >= batch:
+            # host-buffer entry: a batch that fits one pass is still cut in two, so that the H2D copy of the second half and
+            # the D2H copy of the first overlap the kernels (a single chunk would serialise copy -> compute -> copy)
+            cap = (batch + 1) // 2
         key = (str(device), cap, H, W)
         eng = self._engines.get(key)
         if eng is None:
@@ -248,7 +252,7 @@ class UNet(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("UNet (B200): model parameters are not on a CUDA device (no CPU fallback)")
-        eng = self._engine(dev, size[0], size[1], B)
+        eng = self._engine(dev, size[0], size[1], B, pipelined=True)
         skey = (Hs, Ws)
         if getattr(eng, "staging_key", None) != skey:
             eng.staging = torch.empty(lib.unet_b200_infer_stream_staging_bytes(eng.handle, Hs, Ws), dtype=torch.uint8, device=dev)
