@@ -203,10 +203,24 @@ int pow2_divisor(int v, int cap) {
 }
 
 // 128-pixel box: TW | W (<= 16 so the fused pool's partners stay inside a warp), TH | H, rest from batch.
-void pick_tile(int H, int W, int* TW, int* TH, int* TB) {
+// Small batches (the per-frame path of the ROS node): when the batch cannot fill the box's image dimension, the box is made
+// as large as the image allows instead - TW / TH = the largest powers of two not exceeding W / H (and 16, 128/TW), whether or
+// not they divide the image: TMA zero-fills the overhang on loads (which is also the conv's padding) and clips it on stores.
+// A 14x14 level at batch 1 is then 4 tiles per column block instead of 49 tiles with 4 live rows each.
+void pick_tile(int H, int W, int* TW, int* TH, int* TB, int batch = 1 << 30) {
   *TW = pow2_divisor(W, 16);
   *TH = pow2_divisor(H, 128 / *TW);
   *TB = 128 / (*TW * *TH);
+  if (*TB > batch && *TB > 1) {
+    int tw = 1, th = 1;
+    while (tw * 2 <= W && tw * 2 <= 16) tw *= 2;
+    while (th * 2 <= H && th * 2 <= 128 / tw) th *= 2;
+    if (tw * th > *TW * *TH) {   // only when it actually puts more pixels of one image into the box
+      *TW = tw;
+      *TH = th;
+      *TB = 128 / (tw * th);
+    }
+  }
 }
 
 int pick_block_n(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64; }
@@ -503,7 +517,7 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   p->wt_bytes += align_up((size_t)Cout * 4, 256);
   if (kind == L_STEM) l.stem_tc = g_opt_stem_umma && Cout == 64;
   if (kind != L_STEM) {
-    pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+    pick_tile(H, W, &l.TW, &l.TH, &l.TB, p->Bc);
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
     l.halo = (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);
     if (l.halo) l.block_n = Cout;
@@ -589,7 +603,7 @@ int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const voi
   l.Cout = Cout;
   l.relu = relu;
   l.set = true;
-  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB, B);
   int rc;
   if (kind == L_CONVT) {
     l.block_n = pick_block_n(4 * Cout);
@@ -1348,7 +1362,7 @@ int split_layer_launch(LayerKind kind, const void* x0, int C0, const void* x1, i
   l.C1 = C1;
   l.Cout = Cout;
   l.relu = relu;
-  pick_tile(H, W, &l.TW, &l.TH, &l.TB);
+  pick_tile(H, W, &l.TW, &l.TH, &l.TB, B);
   const int N = (kind == L_CONV) ? Cout : 4 * Cout;
   l.block_n = pick_block_n(N);
   CUtensorMap m0, m1;
