@@ -326,3 +326,15 @@ def test_fp32_path_other_topologies(U, feats, B, H, W):
         y = net(x.cuda()).cpu()
     assert y.shape == y32.shape
     assert (y - y32).abs().max().item() <= LOGIT_TOL_FP32 * max(1.0, y32.abs().max().item())
+
+
+def test_camera_resolution_parity(U):
+    """configs[4] geometry (480x640, no resize) at batch 1: the small-batch image-sized tiles (pick_tile) on every level,
+    including the 30x40 bottleneck whose tiles do not divide the image."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    x = torch.randn(1, 3, 480, 640, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        y32 = ref(x)
+        y = net(x.cuda()).cpu()
+    assert (y - y32).abs().max().item() <= LOGIT_TOL_BF16 * max(1.0, y32.abs().max().item())
+    assert O.mask_agreement(y, y32) >= 0.999
