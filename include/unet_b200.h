@@ -13,7 +13,9 @@
  * available from unet_b200_last_error() (thread-local). Nothing here throws or calls exit().
  * All `*_dev` pointers are caller-owned CUDA device memory; `stream` is a cudaStream_t passed as
  * void* (NULL = default stream); work is enqueued, not synchronised, unless stated otherwise.
- * A plan is not thread-safe; distinct plans are independent. The library targets sm_100a only:
+ * A plan is not thread-safe; distinct plans are independent (each carries the switches it was created with, and everything
+ * the library remembers about a GPU is kept per device ordinal, so one process may drive plans on several devices).
+ * Every call works on the CUDA device that is current for the calling thread. The library targets sm_100a only:
  * on any other device the calls fail with UB_ERR_DEVICE - there is no CPU or library fallback.
  */
 #ifndef UNET_B200_H
@@ -41,16 +43,19 @@ int unet_b200_version(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), UB_ERR_DEVICE otherwise. */
 int unet_b200_device_ok(void);
 
-/* ---- plan: UNet(in_channels, out_channels=1, features) at a fixed HxW and batch capacity ------- *
+/* ---- plan: UNet(in_channels, out_channels, features) at a fixed HxW and batch capacity ---------- *
  * Mirrors UNet.__init__ (README.md:1424-1447). H and W must be divisible by 2^levels, features
  * multiples of 32 (widths that are not multiples of 64 - the deployed topology [32,64,128] - are stored zero-extended to
- * the next multiple of 64; results are unchanged), in_channels <= 4,
- * out_channels == 1. */
+ * the next multiple of 64; results are unchanged), in_channels <= 4, out_channels in [1,64] (the reference trains and
+ * deploys out_channels = 1, README.md:2165; with more the 1x1 head runs as its own kernel instead of inside the last conv). */
 int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
                           const int* features, int levels);
 void unet_b200_plan_destroy(unet_b200_plan* p);
-/* Bytes of device memory the plan needs for activations (workspace) and packed weights. */
+/* Bytes of device memory the plan needs for activations (workspace) and packed weights. Layer outputs share the workspace
+ * by liveness (an output's space is reused after its last reader): the default network needs 19.3 MB per frame of batch
+ * capacity; plan_workspace_unshared_bytes reports what one private buffer per layer output would take (64.1 MB). */
 size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p);
+size_t unet_b200_plan_workspace_unshared_bytes(const unet_b200_plan* p);
 size_t unet_b200_plan_weight_bytes(const unet_b200_plan* p);
 /* Hand the plan its two caller-owned device buffers (256-byte aligned); builds the TMA tensor maps. */
 int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_dev);
@@ -66,15 +71,15 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w_dev, cons
                             void* stream);
 /* ConvTranspose2d(2f, f, 2, 2) of decoder level idx (0 = deepest): w fp32 [2f][f][2][2], bias fp32 [f]. */
 int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w_dev, const float* bias_dev, void* stream);
-/* Output Conv2d(f0, 1, 1): w fp32 [f0], bias fp32 [1] (read synchronously on `stream`). */
+/* Output Conv2d(f0, out_channels, 1): w fp32 [out_channels][f0], bias fp32 [out_channels] (read synchronously on `stream`). */
 int unet_b200_plan_set_head(unet_b200_plan* p, const float* w_dev, const float* bias_dev, void* stream);
 
 /* ---- forward (UNet.forward, README.md:1460-1481, eval mode) -------------------------------------- *
  * x_nhwc4_dev: bf16 [batch][H][W][4] (channels >= in_channels are ignored/zero).
- * Any of the three outputs may be NULL:
- *   logits_dev fp32 [batch][H][W]   (== NCHW [batch,1,H,W])
- *   probs_dev  fp32 [batch][H][W]   sigmoid(logits)
- *   mask_dev   u8   [batch][H][W]   (sigmoid(logit) > threshold) ? 255 : 0   (src/unet.py:63-67) */
+ * Any of the three outputs may be NULL (OC = out_channels):
+ *   logits_dev fp32 [batch][OC][H][W]   (NCHW, as the reference module returns them)
+ *   probs_dev  fp32 [batch][OC][H][W]   sigmoid(logits)
+ *   mask_dev   u8   [batch][OC][H][W]   (sigmoid(logit) > threshold) ? 255 : 0   (src/unet.py:63-67) */
 int unet_b200_forward(unet_b200_plan* p, const void* x_nhwc4_dev, int batch, float* logits_dev, float* probs_dev,
                       uint8_t* mask_dev, float threshold, void* stream);
 /* Number of kernels one unet_b200_forward call launches (for launch accounting). */
@@ -90,7 +95,9 @@ int unet_b200_plan_num_layers(const unet_b200_plan* p);
  * H, W are the GEMM-row grid (input resolution). */
 int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
 
-/* Process-wide kernel-selection switches, read when a plan is created / a single-layer call is made:
+/* Kernel-selection switches. unet_b200_set_option changes the PROCESS DEFAULTS; a plan / trainer copies the defaults when it is
+ * created and keeps its copy for life (changing a default later does not touch existing plans), the single-layer entry points
+ * read the defaults when they are called:
  *   "halo" (default 1)      3x3 convs with Cout 64/128 and W % 8 == 0 run on the halo-patch kernel
  *   "fuse_head" (default 1) the 1x1 head + sigmoid + mask run in the last conv's epilogue when it is a halo layer
  *   "stem_umma" (default 1) the Cin<=4 -> 64 stem runs on tensor cores (in-kernel im2col) instead of the FP32 pipes
@@ -100,6 +107,8 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad2" (default 1)    CTA-pair weight-gradient kernel for Cout >= 128 (read when a trainer / wgrad call is set up)
  *   "wgrad_stream" (default 1) backward: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
  *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
+ *   "bwd_fuse" (default 1)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
+ *                           incoming gradient where that pass is an elementwise kernel (head / max-pool backward)
  * All paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
 int unet_b200_set_option(const char* name, int value);
 
@@ -205,6 +214,18 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4_dev, const
  * as params_dev) with the gradient of every parameter. Needs the activations of the preceding train_forward. */
 int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits_dev, const float* params_dev, float* grads_dev,
                              void* stream);
+/* The same backward in stages, cut where a contiguous range of the flat gradient becomes final, so that a data-parallel
+ * caller can exchange that range while the rest of the backward runs ("bucketed, launched on a side stream
+ * as each level's wgrad finishes"). trainer_num_stages = 2*levels + 2: stage 0 = head (also clears grads_dev), then the
+ * decoder levels shallowest first, the bottleneck, the encoder levels deepest first; stages must be called in order.
+ * trainer_stage_range gives the flat range [lo, hi) that is final once the stage's work has completed. A stage only enqueues
+ * work on `stream` and on the trainer's internal weight-gradient stream; trainer_join makes `waiter_stream` (which may be
+ * `stream` itself) wait for everything enqueued so far. */
+int unet_b200_trainer_num_stages(const unet_b200_trainer* t);
+int unet_b200_trainer_stage_range(const unet_b200_trainer* t, int stage, long long* lo, long long* hi);
+int unet_b200_train_backward_stage(unet_b200_trainer* t, int stage, const float* dlogits_dev, const float* params_dev,
+                                   float* grads_dev, void* stream);
+int unet_b200_trainer_join(unet_b200_trainer* t, void* stream, void* waiter_stream);
 /* Data-parallel training over NVLink without a separate collective (replaces loss.backward() + DDP all-reduce +
  * optimizer.step() of README.md:2076-2079 when world > 1). The flat gradient is cut into `world` contiguous shards of
  * S = roundup4(ceil(n/world)) elements, rank r owning [r*S, min(n,(r+1)*S)). Buffers are peer-mapped (torch symmetric
@@ -224,6 +245,17 @@ int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_b
                              float* grads_local_dev, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev, long long n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale,
                              void* stream);
+/* The same kernel on an explicit flat range [lo, hi) (lo a multiple of 4; m_dev / v_dev hold hi - lo elements: the caller's
+ * optimizer state for exactly this range) - what a bucketed exchange calls once per bucket with this rank's part of the
+ * bucket. lr_dev as in adamw_step_dev. */
+int unet_b200_adamw_range_p2p(float* const* param_bases_dev, float* const* grad_bases_dev, int world, int rank,
+                              float* grads_local_dev, long long lo, long long hi, float* m_dev, float* v_dev, float lr,
+                              const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, const int* step_dev,
+                              float grad_scale, void* stream);
+int unet_b200_adamw_range_multimem(float* params_mc_dev, const float* grads_mc_dev, const float* params_local_dev, long long lo,
+                                   long long hi, float* m_dev, float* v_dev, float lr, const float* lr_dev, float beta1,
+                                   float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale,
+                                   void* stream);
 /* NVSwitch (NVLS) form of adamw_step_p2p's pull mode: params_mc_dev / grads_mc_dev are MULTICAST addresses of the symmetric
  * flat parameter / gradient buffers (cuMulticast* / torch symmetric memory multicast_ptr); the shard's gradient sum is formed
  * by multimem.ld_reduce inside the switch and the new parameters reach every replica through multimem.st. params_local_dev is
@@ -251,10 +283,11 @@ int unet_b200_adamw_step(float* params_dev, const float* grads_dev, float* exp_a
                          float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                          void* stream);
 
-/* Same, with the step count read from device memory (int32, >= 1) so the call can be captured in a CUDA graph. */
+/* Same, with the step count read from device memory (int32, >= 1) so the call can be captured in a CUDA graph; lr_dev
+ * (optional, fp32 scalar in device memory) overrides lr, so a learning-rate schedule does not need a new graph either. */
 int unet_b200_adamw_step_dev(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev, size_t n,
-                             float lr, float beta1, float beta2, float eps, float weight_decay, const int* step_dev,
-                             float grad_scale, void* stream);
+                             float lr, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                             const int* step_dev, float grad_scale, void* stream);
 
 /* ---- single training ops (same kernels the trainer runs; exposed for parity tests and reuse) ------------------------ *
  * All activations bf16 NHWC, gradients of activations bf16 NHWC, weight gradients fp32 in the PyTorch layout and

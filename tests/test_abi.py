@@ -48,7 +48,9 @@ def test_argument_validation_without_gpu():
     assert b"multiple of 32" in lib.unet_b200_last_error()
     assert lib.unet_b200_plan_create(C.byref(h), 8, 100, 224, 3, 1, feats, 4) == -1   # H not divisible by 16
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 5, 1, feats, 4) == -1   # in_channels > 4
-    assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 2, feats, 4) == -1   # out_channels != 1
+    assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 0, feats, 4) == -1   # out_channels < 1
+    assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 3, feats, 4) == 0    # any out_channels (README.md:1447)
+    lib.unet_b200_plan_destroy(h)
     assert lib.unet_b200_conv3x3(None, 64, None, 0, None, None, 1, 8, 8, 64, 1, None, None, None) == -1
 
 
@@ -67,3 +69,75 @@ def test_layer_table_matches_survey_appendix_b():
         flops += 2.0 * H * W * cout * (4 if kind == 2 else 1) * taps * cin
     lib.unet_b200_plan_destroy(h)
     assert abs(flops / 1e9 - 73.756) < 0.01
+
+
+def test_workspace_is_shared_by_liveness():
+    """layer outputs share the workspace by liveness. Default network: 19.3 MB per frame of capacity (the
+    live set at dec3.conv0: skip + up-sampled tensor + output) instead of 64.1 MB; <= 5.5 GB at batch 256."""
+    from unet_lane_detection_b200._lib import lib
+    h = C.c_void_p()
+    feats = (C.c_int * 4)(64, 128, 256, 512)
+    assert lib.unet_b200_plan_create(C.byref(h), 256, 224, 224, 3, 1, feats, 4) == 0
+    ws, un = lib.unet_b200_plan_workspace_bytes(h), lib.unet_b200_plan_workspace_unshared_bytes(h)
+    lib.unet_b200_plan_destroy(h)
+    assert ws <= 5.5e9, ws
+    assert ws / 256 <= 20.0e6 and un / 256 >= 57e6, (ws / 256, un / 256)   # (unshared: 64.1 MB minus the never-written last output)
+    # the unfused head also writes the last activation; it fits the space the skip / up-sampled tensors just left
+    assert lib.unet_b200_set_option(b"fuse_head", 0) == 0
+    try:
+        assert lib.unet_b200_plan_create(C.byref(h), 256, 224, 224, 3, 1, feats, 4) == 0
+        ws2 = lib.unet_b200_plan_workspace_bytes(h)
+        lib.unet_b200_plan_destroy(h)
+    finally:
+        lib.unet_b200_set_option(b"fuse_head", 1)
+    assert ws <= ws2 <= 26.5e6 * 256
+
+
+def test_backward_stages_cover_the_flat_gradient_once():
+    """Stage ranges of the staged backward (trainer_stage_range) tile [0, n_params) exactly; the bucket plan built from them
+    keeps that property and ends every bucket on a 4-element boundary (16-byte accesses of the exchange kernels)."""
+    from unet_lane_detection_b200._lib import lib
+    from unet_lane_detection_b200.training import plan_buckets, shard_of
+    for feats_l, hw in (([64, 128, 256, 512], 224), ([64, 128], 32), ([128, 256, 512], 64)):
+        h = C.c_void_p()
+        feats = (C.c_int * len(feats_l))(*feats_l)
+        assert lib.unet_b200_trainer_create(C.byref(h), 64, hw, hw, 3, 1, feats, len(feats_l)) == 0
+        n = lib.unet_b200_trainer_num_params(h)
+        S = lib.unet_b200_trainer_num_stages(h)
+        assert S == 2 * len(feats_l) + 2
+        rs = []
+        for s in range(S):
+            lo, hi = C.c_longlong(), C.c_longlong()
+            assert lib.unet_b200_trainer_stage_range(h, s, C.byref(lo), C.byref(hi)) == 0
+            rs.append((lo.value, hi.value))
+        lib.unet_b200_trainer_destroy(h)
+        cover = sorted(rs)
+        assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+        for mb in (1, 20000, 2 << 20, 1 << 40):
+            bk = plan_buckets(rs, mb, min(1 << 16, mb))
+            iv = sorted((lo, hi) for _, lo, hi in bk)
+            assert iv[0][0] == 0 and iv[-1][1] == n and all(a[1] == b[0] for a, b in zip(iv, iv[1:])), (feats_l, mb, bk)
+            assert [s for s, _, _ in bk] == sorted(s for s, _, _ in bk)
+            for stage, lo, hi in bk:       # a bucket is sent only after every stage that contributes to it
+                assert all(s <= stage for s, (a, b) in enumerate(rs) if a < hi and b > lo)
+                assert lo % 4 == 0
+                for world in (2, 8):
+                    parts = [shard_of(lo, hi, r, world) for r in range(world)]
+                    assert parts[0][0] == lo and parts[-1][1] == hi and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+                    assert all(a % 4 == 0 for a, b in parts if b > a)      # (empty parts are never launched)
+    # default network: five buckets, the big decoder / bottleneck ones leave mid-backward
+    assert len(plan_buckets(rs_default())) == 5
+
+
+def rs_default():
+    from unet_lane_detection_b200._lib import lib
+    h = C.c_void_p()
+    feats = (C.c_int * 4)(64, 128, 256, 512)
+    assert lib.unet_b200_trainer_create(C.byref(h), 64, 224, 224, 3, 1, feats, 4) == 0
+    rs = []
+    for s in range(lib.unet_b200_trainer_num_stages(h)):
+        lo, hi = C.c_longlong(), C.c_longlong()
+        lib.unet_b200_trainer_stage_range(h, s, C.byref(lo), C.byref(hi))
+        rs.append((lo.value, hi.value))
+    lib.unet_b200_trainer_destroy(h)
+    return rs

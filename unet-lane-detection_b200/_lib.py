@@ -26,6 +26,7 @@ _SIGS = {
     "unet_b200_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
     "unet_b200_plan_destroy": (None, [vp]),
     "unet_b200_plan_workspace_bytes": (sz, [vp]),
+    "unet_b200_plan_workspace_unshared_bytes": (sz, [vp]),
     "unet_b200_plan_weight_bytes": (sz, [vp]),
     "unet_b200_plan_bind": (i32, [vp, vp, vp]),
     "unet_b200_plan_num_convs": (i32, [vp]),
@@ -80,7 +81,13 @@ _SIGS = {
     "unet_b200_bce_dice_loss": (i32, [vp, vp, sz, f32, f32, f32, f32, vp, vp, vp, vp]),
     "unet_b200_validation_metrics": (i32, [vp, vp, sz, f32, f32, f32, f32, f32, vp, vp, vp]),
     "unet_b200_adamw_step": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, i32, f32, vp]),
-    "unet_b200_adamw_step_dev": (i32, [vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]),
+    "unet_b200_adamw_step_dev": (i32, [vp, vp, vp, vp, sz, f32, vp, f32, f32, f32, f32, vp, f32, vp]),
+    "unet_b200_trainer_num_stages": (i32, [vp]),
+    "unet_b200_trainer_stage_range": (i32, [vp, i32, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "unet_b200_train_backward_stage": (i32, [vp, i32, vp, vp, vp, vp]),
+    "unet_b200_trainer_join": (i32, [vp, vp, vp]),
+    "unet_b200_adamw_range_p2p": (i32, [vp, vp, i32, i32, vp, C.c_longlong, C.c_longlong, vp, vp, f32, vp, f32, f32, f32, f32, vp, f32, vp]),
+    "unet_b200_adamw_range_multimem": (i32, [vp, vp, vp, C.c_longlong, C.c_longlong, vp, vp, f32, vp, f32, f32, f32, f32, vp, f32, vp]),
     "unet_b200_pack_conv3x3_dgrad": (i32, [vp, i32, i32, vp, vp]),
     "unet_b200_pack_convT2x2_dgrad": (i32, [vp, i32, i32, vp, vp]),
     "unet_b200_conv3x3_wgrad": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, vp]),

@@ -245,8 +245,8 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, int B, int C, 
 // Preprocess (north_star (d)): uint8 HWC frames -> bilinear resize to HxW exactly as cv2.resize
 // INTER_LINEAR does on uint8 (11-bit fixed-point taps; src/unet.py:33) -> optional R<->B swap
 // (BGR->RGB, src/unet_ros_node.py:310) -> (x - mean)/std (README.md:3110-3111) -> NHWC4 bf16.
-// One block per output row; the two source rows it needs are staged in shared memory so global
-// reads are fully coalesced regardless of the horizontal scale.
+// Source rows are staged in shared memory so global reads are fully coalesced 16-byte loads regardless of the
+// horizontal scale.
 // ------------------------------------------------------------------------------------------------
 struct PreArgs {
   const uint8_t* src;  // [B, Hs, Ws, 3], row pitch in bytes
@@ -282,45 +282,127 @@ __device__ __forceinline__ int resize_blend(int h0, int h1, int by0, int by1) {
   return min(max(v, 0), 255);
 }
 
-__global__ void preprocess_u8_kernel(const PreArgs a) {
+// Tile kernel: one CTA produces PRE_ROWS consecutive output rows of one frame.
+//   1. per-CTA tables in shared memory: the horizontal taps of every output column (computed once per CTA instead of once
+//      per pixel: resize_coef costs a double division) and, per output row, the two source-row slots + vertical weights;
+//   2. the source rows the tile needs are staged with 16-byte loads: the contiguous span [first, last] when it is short
+//      (identity, up-scaling, down-scaling by <= 2: every row is read once), else exactly the two rows per output row;
+//   3. every thread blends one output pixel per trip from shared memory and writes its 8-byte NHWC4 pixel; a warp's
+//      stores cover 256 contiguous bytes.
+// profiles/r1: the first version (one CTA per output row, byte-wide staging loads) reached 1.04 TB/s = 16 % of the copy peak.
+constexpr int PRE_ROWS = 8;
+constexpr int PRE_THREADS = 256;
+__host__ __device__ constexpr int pre_row_pitch(int Ws) { return ((Ws * 3 + 15) / 16) * 16 + 16; }   // + head misalignment
+// dynamic shared memory: row slots + [W] x-tap table (int4)
+__host__ __device__ constexpr size_t pre_smem_bytes(int Ws, int W, int rows) {
+  return static_cast<size_t>(2 * rows) * pre_row_pitch(Ws) + static_cast<size_t>(W) * 16;
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArgs a, int rows_per_cta) {
   pdl_enter();
-  extern __shared__ uint8_t rows[];  // 2 x Ws*3 bytes
-  const int y = blockIdx.x % a.H;
-  const int b = blockIdx.x / a.H;
-  int sy0, sy1, by0, by1;
-  resize_coef(y, a.H, a.Hs, false, sy0, sy1, by0, by1);
+  extern __shared__ __align__(16) uint8_t pre_smem[];
+  __shared__ int s_slot[2 * PRE_ROWS], s_by[2 * PRE_ROWS], s_src[2 * PRE_ROWS], s_off[2 * PRE_ROWS];
+  __shared__ int s_nslots;
+  const int R = rows_per_cta;
+  const int tiles_h = (a.H + R - 1) / R;
+  const int b = blockIdx.x / tiles_h;
+  const int y0 = (blockIdx.x % tiles_h) * R;
+  const int nrows = min(R, a.H - y0);
+  const int pitch_s = pre_row_pitch(a.Ws);
+  int4* xtab = reinterpret_cast<int4*>(pre_smem + static_cast<size_t>(2 * R) * pitch_s);
   // cv::resize special cases: equal sizes copy (the taps below reduce to that), and an exact 2x2 decimation is computed
   // as INTER_AREA = (a + b + c + d + 2) >> 2
   const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
-  if (area2) {
-    sy0 = 2 * y;
-    sy1 = 2 * y + 1;
+  const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
+
+  if (threadIdx.x == 0) {
+    int lo = 1 << 30, hi = -1;
+    int sy0[PRE_ROWS], sy1[PRE_ROWS];
+    for (int r = 0; r < nrows; ++r) {
+      int b0, b1;
+      resize_coef(y0 + r, a.H, a.Hs, false, sy0[r], sy1[r], b0, b1);
+      if (area2) {
+        sy0[r] = 2 * (y0 + r);
+        sy1[r] = 2 * (y0 + r) + 1;
+      }
+      s_by[2 * r] = b0;
+      s_by[2 * r + 1] = b1;
+      lo = min(lo, min(sy0[r], sy1[r]));
+      hi = max(hi, max(sy0[r], sy1[r]));
+    }
+    int n;
+    if (hi - lo + 1 <= 2 * R) {       // span mode: slot i holds source row lo + i
+      n = hi - lo + 1;
+      for (int i = 0; i < n; ++i) s_src[i] = lo + i;
+      for (int r = 0; r < nrows; ++r) {
+        s_slot[2 * r] = sy0[r] - lo;
+        s_slot[2 * r + 1] = sy1[r] - lo;
+      }
+    } else {                          // sparse mode: two private slots per output row
+      n = 2 * nrows;
+      for (int r = 0; r < nrows; ++r) {
+        s_src[2 * r] = sy0[r];
+        s_src[2 * r + 1] = sy1[r];
+        s_slot[2 * r] = 2 * r;
+        s_slot[2 * r + 1] = 2 * r + 1;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      const uintptr_t p = reinterpret_cast<uintptr_t>(frame + static_cast<size_t>(s_src[i]) * a.pitch);
+      s_off[i] = static_cast<int>(p & 15);   // the row is staged from its 16-byte aligned address; this is where it starts
+    }
+    s_nslots = n;
   }
-  const int row_bytes = a.Ws * 3;
-  const uint8_t* r0 = a.src + b * a.frame_stride + sy0 * a.pitch;
-  const uint8_t* r1 = a.src + b * a.frame_stride + sy1 * a.pitch;
-  for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) {
-    rows[i] = __ldg(r0 + i);
-    rows[row_bytes + i] = __ldg(r1 + i);
-  }
-  __syncthreads();
-  for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
+  // horizontal taps: {3*sx0, 3*sx1, ax0, ax1} per output column
+  for (int x = threadIdx.x; x < a.W; x += PRE_THREADS) {
     int sx0, sx1, ax0, ax1;
     resize_coef(x, a.W, a.Ws, true, sx0, sx1, ax0, ax1);
+    if (area2) {
+      sx0 = 2 * x;
+      sx1 = 2 * x + 1;
+    }
+    xtab[x] = make_int4(3 * sx0, 3 * sx1, ax0, ax1);
+  }
+  __syncthreads();
+  // stage the rows: 16-byte chunks from the aligned-down row address (never below the allocation: it is at least 16-byte
+  // aligned); a chunk that would reach past the last byte of the last frame is read byte by byte instead
+  const int nslots = s_nslots;
+  const int row_bytes = a.Ws * 3;
+  const uint8_t* src_end = a.src + static_cast<size_t>(a.B - 1) * a.frame_stride + static_cast<size_t>(a.Hs - 1) * a.pitch + row_bytes;
+  for (int i = 0; i < nslots; ++i) {
+    const uint8_t* rp = frame + static_cast<size_t>(s_src[i]) * a.pitch - s_off[i];
+    const int chunks = (s_off[i] + row_bytes + 15) >> 4;
+    uint8_t* dst = pre_smem + static_cast<size_t>(i) * pitch_s;
+    for (int c = threadIdx.x; c < chunks; c += PRE_THREADS) {
+      const uint8_t* g = rp + 16 * c;
+      if (g + 16 <= src_end) {
+        *reinterpret_cast<uint4*>(dst + 16 * c) = __ldg(reinterpret_cast<const uint4*>(g));
+      } else {
+        for (int k = 0; k < 16; ++k) dst[16 * c + k] = (g + k < src_end) ? __ldg(g + k) : 0;
+      }
+    }
+  }
+  __syncthreads();
+  const int total = nrows * a.W;
+  for (int i = threadIdx.x; i < total; i += PRE_THREADS) {
+    const int r = i / a.W, x = i - r * a.W;
+    const int4 t = xtab[x];
+    const int sl0 = s_slot[2 * r], sl1 = s_slot[2 * r + 1];
+    const uint8_t* r0 = pre_smem + static_cast<size_t>(sl0) * pitch_s + s_off[sl0];
+    const uint8_t* r1 = pre_smem + static_cast<size_t>(sl1) * pitch_s + s_off[sl1];
     int px[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (area2) {
-        px[c] = (rows[(2 * x) * 3 + c] + rows[(2 * x + 1) * 3 + c] + rows[row_bytes + (2 * x) * 3 + c] +
-                 rows[row_bytes + (2 * x + 1) * 3 + c] + 2) >> 2;
+        px[c] = (r0[t.x + c] + r0[t.y + c] + r1[t.x + c] + r1[t.y + c] + 2) >> 2;
       } else {
-        const int h0 = rows[sx0 * 3 + c] * ax0 + rows[sx1 * 3 + c] * ax1;
-        const int h1 = rows[row_bytes + sx0 * 3 + c] * ax0 + rows[row_bytes + sx1 * 3 + c] * ax1;
-        px[c] = resize_blend(h0, h1, by0, by1);
+        const int h0 = r0[t.x + c] * t.z + r0[t.y + c] * t.w;
+        const int h1 = r1[t.x + c] * t.z + r1[t.y + c] * t.w;
+        px[c] = resize_blend(h0, h1, s_by[2 * r], s_by[2 * r + 1]);
       }
     }
-    if (a.swap_rb) { const int t = px[0]; px[0] = px[2]; px[2] = t; }
-    const size_t o = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+    if (a.swap_rb) { const int tt = px[0]; px[0] = px[2]; px[2] = tt; }
+    const size_t o = (static_cast<size_t>(b) * a.H + y0 + r) * a.W + x;
     if (a.dst_u8 != nullptr) {
       a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
       a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
@@ -674,6 +756,62 @@ head_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, fl
         const float s = 1.f / (1.f + expf(-z));
         if (probs != nullptr) probs[p] = s;
         if (mask != nullptr) mask[p] = (s > thr) ? 255 : 0;
+      }
+    }
+  }
+}
+
+// Head for out_channels > 1 (README.md:1447 builds nn.Conv2d(features[0], out_channels, 1) for any out_channels):
+// x bf16 [B*hw][C], w fp32 [OC][C] (staged in shared memory), bias fp32 [OC]; outputs NCHW [B][OC][hw].
+// One thread per pixel, eight output channels per sweep over the pixel's row.
+__global__ void __launch_bounds__(256)
+head_multi_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B,
+                  size_t hw, int C, int OC, float* __restrict__ logits, float* __restrict__ probs, uint8_t* __restrict__ mask,
+                  float thr) {
+  pdl_enter();
+  extern __shared__ float hsm[];   // [OC][C] weights, [OC] bias
+  for (int i = threadIdx.x; i < OC * C; i += blockDim.x) hsm[i] = w[i];
+  for (int i = threadIdx.x; i < OC; i += blockDim.x) hsm[OC * C + i] = bias[i];
+  __syncthreads();
+  const size_t npix = static_cast<size_t>(B) * hw;
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < npix;
+       p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4* row = reinterpret_cast<const uint4*>(x + p * C);
+    const size_t bi = p / hw, q = p - bi * hw;
+    for (int oc0 = 0; oc0 < OC; oc0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int c8 = 0; c8 < C / 8; ++c8) {
+        const uint4 r = __ldg(row + c8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          f[2 * k] = __low2float(h[k]);
+          f[2 * k + 1] = __high2float(h[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (oc0 + j < OC) {
+            const float* wr = hsm + (oc0 + j) * C + c8 * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j] = fmaf(f[k], wr[k], acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (oc0 + j < OC) {
+          const float z = acc[j] + hsm[OC * C + oc0 + j];
+          const size_t o = (bi * OC + oc0 + j) * hw + q;
+          if (logits != nullptr) logits[o] = z;
+          if (probs != nullptr || mask != nullptr) {
+            const float sg = 1.f / (1.f + expf(-z));
+            if (probs != nullptr) probs[o] = sg;
+            if (mask != nullptr) mask[o] = (sg > thr) ? 255 : 0;
+          }
+        }
       }
     }
   }

@@ -1,5 +1,7 @@
 // C ABI of libunet_b200.so (see include/unet_b200.h). Host-side plan: layer table, workspace layout,
 // TMA tensor maps, launches. No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -37,13 +39,83 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// Every kernel launch of the library. With g_opt_pdl (unet_b200_set_option("pdl", 1)) a kernel may be scheduled before its
+// ---- kernel-selection switches (unet_b200_set_option) ------------------------------------------------------------------
+// g_opts holds the PROCESS DEFAULTS. A plan / trainer copies them when it is created and runs with its own copy from then on
+// (its entry points install the copy as this thread's current options, OptScope), so changing a default never changes the
+// behaviour of an existing plan, and two plans with different options can run side by side. The single-layer entry points
+// have no plan and read the defaults at call time.
+struct Opts {
+  int halo = 1;          // 3x3 convs with Cout 64/128 on the halo-patch kernel
+  int fuse_head = 1;     // 1x1 head + sigmoid + mask inside the last conv's epilogue
+  int stem_umma = 1;     // Cout == 64 stem on tensor cores (stem_umma.cuh) instead of the FP32-pipe kernel
+  int halo2 = 1;         // halo layers on the CTA-pair kernel when at least two tiles exist
+  int umma2 = 1;         // per-tap layers on the CTA-pair kernel when at least two pixel tiles exist
+  int pdl = 0;           // programmatic dependent launch (measured slower, see below)
+  int wgrad_rows64 = 1;  // 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
+  int wgrad2 = 1;        // CTA-pair weight-gradient kernel for BLOCK_N >= 128
+  int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
+  int bwd_fuse = 1;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient
+};
+Opts g_opts;
+thread_local const Opts* tl_opts = &g_opts;
+struct OptScope {
+  const Opts* prev;
+  explicit OptScope(const Opts* o) : prev(tl_opts) { tl_opts = o; }
+  ~OptScope() { tl_opts = prev; }
+};
+
+// ---- per-device state -----------------------------------------------------------------------------------------------
+// Everything the library remembers about a device lives here, indexed by the CUDA device ordinal that is current when an
+// entry point runs: SM count, which kernels already had their dynamic-shared-memory limit raised (cudaFuncSetAttribute is
+// per device), and a small all-zero bias vector for the single-op entry points. One process may drive several devices.
+constexpr int UB_MAX_DEVICES = 64;
+enum AttrSlot : int {
+  AT_UMMA = 0,        // + {0,1,2} for BLOCK_N 64/128/256
+  AT_UMMA2 = 3,
+  AT_HALO = 6,        // + {0,1} for BLOCK_N 64/128
+  AT_HALO2 = 8,
+  AT_STEM = 10,
+  AT_PRE = 11,
+  AT_WGRAD = 12,      // + {0,1,2}
+  AT_WGRAD2 = 15,     // + {1,2}
+  AT_STEM_WGRAD_TC = 18,
+  AT_STEM_WGRAD = 19,
+  AT_PRE_ROWS = 20,
+  AT_BNFUSE = 21,
+};
+struct DevState {
+  std::atomic<int> num_sms{0};
+  std::atomic<unsigned long long> attrs{0};
+  std::atomic<float*> zero_bias{nullptr};
+};
+DevState g_dev[UB_MAX_DEVICES];
+
+DevState* cur_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= UB_MAX_DEVICES) dev = 0;
+  return &g_dev[dev];
+}
+// SM count of the current device (device_check() has run for it: every entry point that launches calls it first)
+int cur_sms() {
+  const int n = cur_dev()->num_sms.load(std::memory_order_relaxed);
+  return n > 0 ? n : 148;
+}
+// Raise a kernel's dynamic shared-memory limit once per device.
+template <typename K>
+cudaError_t ensure_smem(K kernel, int slot, int bytes) {
+  DevState* d = cur_dev();
+  const unsigned long long bit = 1ull << slot;
+  if (d->attrs.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) d->attrs.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
+// Every kernel launch of the library. With the "pdl" option a kernel may be scheduled before its
 // stream predecessor has drained (programmatic dependent launch; every kernel starts with pdl_enter(), ptx.cuh, so the ordering
 // of the data is unchanged). OFF by default: measured on B200 (tools/ab_option.py pdl, same box, alternating) it is SLOWER -
 // inference 17.0 k -> 16.4 k frames/s, training 18.9 -> 19.3 ms/step - the persistent one-CTA-per-SM kernels leave no room for
 // an early dependent, and its parked CTAs only get in the way of the tail.
-int g_opt_pdl = 0;
-
 template <typename... KArgs, typename... Args>
 void ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -54,7 +126,7 @@ void ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_opt_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tl_opts->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError() at the call site
@@ -184,16 +256,9 @@ bool halo_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
   return false;
 }
 
-int g_opt_halo = 1;       // use conv_halo_kernel where eligible
-int g_opt_fuse_head = 1;  // fold the 1x1 head into the last conv's epilogue where eligible
-extern int g_opt_wgrad_rows64;
-extern int g_opt_wgrad_stream;
-extern int g_opt_wgrad2;
-int g_opt_stem_umma = 1;  // run the Cout == 64 stem on tensor cores (stem_umma.cuh) instead of the FP32-pipe kernel
-
 bool halo_eligible(int H, int W, int C0, int C1, int Cout) {
   (void)H;
-  return g_opt_halo && (W % 8 == 0) && (Cout == 64 || Cout == 128) && (C0 % 64 == 0) && (C1 % 64 == 0);
+  return tl_opts->halo && (W % 8 == 0) && (Cout == 64 || Cout == 128) && (C0 % 64 == 0) && (C1 % 64 == 0);
 }
 
 int pow2_divisor(int v, int cap) {
@@ -225,64 +290,52 @@ void pick_tile(int H, int W, int* TW, int* TH, int* TB, int batch = 1 << 30) {
 
 int pick_block_n(int N) { return (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64; }
 
-int g_num_sms = 0;
-int g_attr_done[3] = {0, 0, 0};
-
 int device_check() {
-  if (g_num_sms > 0) return UB_OK;  // cudaGetDeviceProperties is slow; the process is pinned to one device
   int dev = 0;
   UB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= UB_MAX_DEVICES) return fail(UB_ERR_DEVICE, "device ordinal %d outside [0,%d)", dev, UB_MAX_DEVICES);
+  DevState* d = &g_dev[dev];
+  if (d->num_sms.load(std::memory_order_acquire) > 0) return UB_OK;  // cudaGetDeviceProperties is slow: once per device
   cudaDeviceProp prop;
   UB_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) {
-    return fail(UB_ERR_DEVICE, "device '%s' is sm_%d%d; libunet_b200 runs on sm_100 only (no fallback)", prop.name,
+    return fail(UB_ERR_DEVICE, "device %d '%s' is sm_%d%d; libunet_b200 runs on sm_100 only (no fallback)", dev, prop.name,
                 prop.major, prop.minor);
   }
-  g_num_sms = prop.multiProcessorCount;
+  d->num_sms.store(prop.multiProcessorCount, std::memory_order_release);
   return UB_OK;
 }
 
-int g_opt_umma2 = 1;   // run conv_umma layers on the CTA-pair kernel (conv_umma2_kernel) when at least two pixel tiles exist
-int g_attr2_done[3] = {0, 0, 0};
 
 template <int BN>
 int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args, int slot,
                   cudaStream_t st) {
   const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_b;
-  if (g_opt_umma2 && m_tiles >= 2) {
+  const int sms = cur_sms();
+  if (tl_opts->umma2 && m_tiles >= 2) {
     using Cfg2 = ub::ConvCfg<BN, true>;
-    if (!g_attr2_done[slot]) {
-      UB_CUDA(cudaFuncSetAttribute(ub::conv_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_LIMIT));
-      g_attr2_done[slot] = 1;
-    }
+    UB_CUDA(ensure_smem(ub::conv_umma2_kernel<BN>, AT_UMMA2 + slot, Cfg2::SMEM_LIMIT));
     ub::ConvArgs args2 = args;
     args2.stages = Cfg2::plan_stages();
     const int smem = Cfg2::smem_bytes(args2.stages);
     const int pair_tiles = ((m_tiles + 1) / 2) * args.n_tiles;
-    const int max_pairs = g_num_sms / 2;
+    const int max_pairs = sms / 2;
     const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // cluster size 2 (__cluster_dims__)
     ub_launch(ub::conv_umma2_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
   using Cfg = ub::ConvCfg<BN>;
-  if (!g_attr_done[slot]) {
-    UB_CUDA(cudaFuncSetAttribute(ub::conv_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_LIMIT));
-    g_attr_done[slot] = 1;
-  }
+  UB_CUDA(ensure_smem(ub::conv_umma_kernel<BN>, AT_UMMA + slot, Cfg::SMEM_LIMIT));
   ub::ConvArgs args2 = args;
   args2.stages = Cfg::plan_stages();
   const int smem = Cfg::smem_bytes(args2.stages);
   const int total = m_tiles * args.n_tiles;
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  const int grid = total < sms ? total : sms;
   ub_launch(ub::conv_umma_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
-
-int g_hattr_done[4] = {0, 0, 0, 0};
-int g_opt_halo2 = 1;   // run halo layers on the CTA-pair kernel (conv_halo2_kernel) when at least two tiles exist
 
 // Shared-memory carve-up of the CTA-pair kernel (half-size weight tiles): resident weights first.
 bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
@@ -312,30 +365,23 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   const int head = args.epi == ub::HEPI_HEAD;
   if (head && BN != 64) return fail(UB_ERR_ARG, "the fused head epilogue needs Cout == 64");
   const int total = args.tiles_w * args.tiles_h * args.B;
-  if (g_opt_halo2 && total >= 2 && halo2_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
-    if (!g_hattr_done[2 + slot]) {
-      UB_CUDA(cudaFuncSetAttribute(ub::conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ub::HaloCfg::SMEM_LIMIT));
-      g_hattr_done[2 + slot] = 1;
-    }
+  const int sms = cur_sms();
+  if (tl_opts->halo2 && total >= 2 && halo2_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
+    UB_CUDA(ensure_smem(ub::conv_halo2_kernel<BN>, AT_HALO2 + slot, ub::HaloCfg::SMEM_LIMIT));
     const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head, 1);
     const int pairs = (total + 1) / 2;
-    const int max_pairs = g_num_sms / 2;
+    const int max_pairs = sms / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)
     ub_launch(ub::conv_halo2_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
-  if (!g_hattr_done[slot]) {
-    UB_CUDA(cudaFuncSetAttribute(ub::conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ub::HaloCfg::SMEM_LIMIT));
-    g_hattr_done[slot] = 1;
-  }
+  UB_CUDA(ensure_smem(ub::conv_halo_kernel<BN>, AT_HALO + slot, ub::HaloCfg::SMEM_LIMIT));
   if (!halo_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
     return fail(UB_ERR_ARG, "no shared-memory plan for halo conv (N=%d, KC=%d)", BN, args.kc0 + args.kc1);
   }
   const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head);
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  const int grid = total < sms ? total : sms;
   ub_launch(ub::conv_halo_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -343,26 +389,18 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
 
 int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
                 const ub::HaloArgs& args, cudaStream_t st) {
-  if (g_num_sms == 0) {
-    int rc = device_check();
-    if (rc != UB_OK) return rc;
-  }
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
   if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, args, 0, st);
   if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, args, 1, st);
   return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
 }
 
-int g_sattr_done = 0;
-
 int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x, const float* bias, int B, int H, int W,
                      int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
-  if (!g_sattr_done) {
-    UB_CUDA(cudaFuncSetAttribute(ub::stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ub::StemCfg::SMEM_BYTES));
-    g_sattr_done = 1;
-  }
+  UB_CUDA(ensure_smem(ub::stem_umma_kernel, AT_STEM, ub::StemCfg::SMEM_BYTES));
   ub::StemArgs a;
   a.B = B;
   a.H = H;
@@ -375,7 +413,8 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
   a.stat_sum = stat_sum;
   a.stat_sumsq = stat_sumsq;
   const int total = a.tiles_w * a.tiles_h * B;
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  const int sms = cur_sms();
+  const int grid = total < sms ? total : sms;
   ub_launch(ub::stem_umma_kernel, grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st, mw, mo, a);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -383,10 +422,8 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
 
 int launch_conv(int block_n, const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args,
                 cudaStream_t st) {
-  if (g_num_sms == 0) {
-    int rc = device_check();
-    if (rc != UB_OK) return rc;
-  }
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
   switch (block_n) {
     case 64: return launch_conv_t<64>(ma, w, mo, args, 0, st);
     case 128: return launch_conv_t<128>(ma, w, mo, args, 1, st);
@@ -420,7 +457,8 @@ struct Layer {
 
 struct Buf {
   int H, W, C;
-  size_t off;
+  size_t off, bytes;
+  int first, last;   // layer index that writes it / last layer index that reads it (-1: never read; n_layers: the head kernel)
 };
 
 // Store views for a conv_umma_kernel layer. Conv: out (+ pooled out). ConvT: quad (dy,dx) of the [B,2H,2W,f] output is
@@ -454,16 +492,18 @@ int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc, int cm) {
 }  // namespace
 
 struct unet_b200_plan {
-  int Bc, H, W, in_ch, levels;
+  int Bc, H, W, in_ch, out_ch, levels;
   int feat[UB_MAX_LEVELS];
+  Opts opt;                    // the switches this plan was created with (unet_b200_set_option changes later plans only)
+  size_t ws_unshared_bytes;    // what the workspace would be with one private buffer per layer output (reporting)
   std::vector<Layer> layers;
   std::vector<int> conv_ids;   // layer index of 3x3 conv #i (stem included as conv 0)
   std::vector<int> convt_ids;  // layer index of ConvT #i
   std::vector<Buf> bufs;
   int final_buf;
   size_t ws_bytes, wt_bytes;
-  size_t head_w_off;
-  float head_bias;
+  size_t head_w_off, head_b_off;   // fp32 [out_ch][f0 physical], fp32 [out_ch]
+  float head_bias;                 // host copy of bias[0] for the fused head epilogue (out_ch == 1)
   bool head_set;
   uint8_t* ws;
   uint8_t* wt;
@@ -480,8 +520,10 @@ int add_buf(unet_b200_plan* p, int H, int W, int C) {
   b.H = H;
   b.W = W;
   b.C = C;
-  b.off = p->ws_bytes;
-  p->ws_bytes += align_up((size_t)p->Bc * H * W * C * 2, 1024);
+  b.off = 0;
+  b.bytes = align_up((size_t)p->Bc * H * W * C * 2, 1024);
+  b.first = -1;
+  b.last = -1;
   p->bufs.push_back(b);
   return (int)p->bufs.size() - 1;
 }
@@ -515,7 +557,7 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   }
   l.b_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)Cout * 4, 256);
-  if (kind == L_STEM) l.stem_tc = g_opt_stem_umma && Cout == 64;
+  if (kind == L_STEM) l.stem_tc = tl_opts->stem_umma && Cout == 64;
   if (kind != L_STEM) {
     pick_tile(H, W, &l.TW, &l.TH, &l.TB, p->Bc);
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
@@ -660,9 +702,86 @@ int conv_layer_launch(const Layer& l, int batch, int Bc, const float* bias, void
   return launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
 }
 
+// Workspace layout by liveness: a layer output gets its address when the layer runs and gives it back after its last
+// reader, so the workspace holds the live set (the skips + the tensors of the layer in flight: <= 19.3 MB per frame for the
+// default network instead of 64.1 MB with one private buffer per output). Kernels run in stream order, so reuse needs no
+// extra synchronisation; a layer's outputs are placed BEFORE its inputs are released (a conv reads neighbouring pixels of
+// its input while it writes). Best fit over a coalescing free list, growing the top when nothing fits.
+void plan_assign_workspace(unet_b200_plan* p) {
+  const int n = (int)p->layers.size();
+  for (Buf& b : p->bufs) b.first = b.last = -1;
+  for (int li = 0; li < n; ++li) {
+    const Layer& l = p->layers[li];
+    if (l.out >= 0 && !l.fuse_head) p->bufs[l.out].first = li;
+    if (l.pool >= 0) p->bufs[l.pool].first = li;
+    if (l.in0 >= 0) p->bufs[l.in0].last = li;
+    if (l.in1 >= 0) p->bufs[l.in1].last = li;
+  }
+  if (!p->layers.back().fuse_head) p->bufs[p->final_buf].last = n;   // read by the head kernel
+  struct Blk { size_t off, size; };
+  std::vector<Blk> fl;
+  size_t top = 0;
+  p->ws_unshared_bytes = 0;
+  auto take = [&](size_t bytes) -> size_t {
+    int best = -1;
+    for (int i = 0; i < (int)fl.size(); ++i) {
+      if (fl[i].size >= bytes && (best < 0 || fl[i].size < fl[best].size)) best = i;
+    }
+    if (best >= 0) {
+      const size_t off = fl[best].off;
+      fl[best].off += bytes;
+      fl[best].size -= bytes;
+      if (fl[best].size == 0) fl.erase(fl.begin() + best);
+      return off;
+    }
+    // grow: a free block that touches the top is extended instead of left behind
+    for (int i = 0; i < (int)fl.size(); ++i) {
+      if (fl[i].off + fl[i].size == top) {
+        const size_t off = fl[i].off;
+        top = off + bytes;
+        fl.erase(fl.begin() + i);
+        return off;
+      }
+    }
+    const size_t off = top;
+    top += bytes;
+    return off;
+  };
+  auto give = [&](size_t off, size_t bytes) {
+    fl.push_back({off, bytes});
+    std::sort(fl.begin(), fl.end(), [](const Blk& a, const Blk& b) { return a.off < b.off; });
+    for (int i = 0; i + 1 < (int)fl.size();) {
+      if (fl[i].off + fl[i].size == fl[i + 1].off) {
+        fl[i].size += fl[i + 1].size;
+        fl.erase(fl.begin() + i + 1);
+      } else {
+        ++i;
+      }
+    }
+  };
+  for (int li = 0; li < n; ++li) {
+    const Layer& l = p->layers[li];
+    const int outs[2] = {l.fuse_head ? -1 : l.out, l.pool};
+    for (int o : outs) {
+      if (o < 0) continue;
+      Buf& b = p->bufs[o];
+      b.off = take(b.bytes);
+      p->ws_unshared_bytes += b.bytes;
+    }
+    for (int o : outs) {   // written but never read: free again once the layer's other output has its own space
+      if (o >= 0 && p->bufs[o].last < 0) give(p->bufs[o].off, p->bufs[o].bytes);
+    }
+    const int ins[2] = {l.in0, l.in1};
+    for (int i : ins) {
+      if (i >= 0 && p->bufs[i].last == li) give(p->bufs[i].off, p->bufs[i].bytes);
+    }
+  }
+  p->ws_bytes = top > 0 ? top : 1024;
+}
+
 int grid_for(size_t work_items, int threads) {
   size_t g = (work_items + threads - 1) / threads;
-  const size_t cap = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * 16;
+  const size_t cap = (size_t)cur_sms() * 16;
   if (g > cap) g = cap;
   if (g == 0) g = 1;
   return (int)g;
@@ -682,7 +801,7 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   if (levels < 1 || levels > UB_MAX_LEVELS) return fail(UB_ERR_ARG, "levels must be in [1,%d]", UB_MAX_LEVELS);
   if (max_batch < 1) return fail(UB_ERR_ARG, "max_batch must be >= 1");
   if (in_channels < 1 || in_channels > 4) return fail(UB_ERR_ARG, "in_channels must be in [1,4] (got %d)", in_channels);
-  if (out_channels != 1) return fail(UB_ERR_ARG, "out_channels must be 1 (got %d)", out_channels);
+  if (out_channels < 1 || out_channels > 64) return fail(UB_ERR_ARG, "out_channels must be in [1,64] (got %d)", out_channels);
   if (H % (1 << levels) != 0 || W % (1 << levels) != 0) {
     return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
   }
@@ -701,7 +820,10 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   p->H = H;
   p->W = W;
   p->in_ch = in_channels;
+  p->out_ch = out_channels;
   p->levels = levels;
+  p->opt = g_opts;                // this plan's switches from here on
+  OptScope opt_scope(&p->opt);
   p->ws_bytes = 0;
   p->wt_bytes = 0;
   p->ws = nullptr;
@@ -758,10 +880,13 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   p->final_buf = cur;
   {
     Layer& last = p->layers.back();
-    last.fuse_head = g_opt_fuse_head && last.kind == L_CONV && last.halo && last.Cout == 64;
+    last.fuse_head = tl_opts->fuse_head && out_channels == 1 && last.kind == L_CONV && last.halo && last.Cout == 64;
   }
   p->head_w_off = p->wt_bytes;
-  p->wt_bytes += align_up((size_t)fp[0] * 4, 256);
+  p->wt_bytes += align_up((size_t)out_channels * fp[0] * 4, 256);
+  p->head_b_off = p->wt_bytes;
+  p->wt_bytes += align_up((size_t)out_channels * 4, 256);
+  plan_assign_workspace(p);
   *out = p;
   return UB_OK;
 }
@@ -780,6 +905,7 @@ void unet_b200_plan_destroy(unet_b200_plan* p) {
   delete p;
 }
 size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p) { return p ? p->ws_bytes : 0; }
+size_t unet_b200_plan_workspace_unshared_bytes(const unet_b200_plan* p) { return p ? p->ws_unshared_bytes : 0; }
 size_t unet_b200_plan_weight_bytes(const unet_b200_plan* p) { return p ? p->wt_bytes : 0; }
 int unet_b200_plan_num_convs(const unet_b200_plan* p) { return p ? (int)p->conv_ids.size() : 0; }
 
@@ -790,6 +916,7 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
   }
   int rc = device_check();
   if (rc != UB_OK) return rc;
+  OptScope opt_scope(&p->opt);
   p->ws = static_cast<uint8_t*>(workspace_dev);
   p->wt = static_cast<uint8_t*>(weights_dev);
   for (Layer& l : p->layers) {
@@ -880,8 +1007,11 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
   if (p == nullptr || w == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (p->wt == nullptr) return fail(UB_ERR_STATE, "plan_bind must be called before set_head");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UB_CUDA(cudaMemsetAsync(p->wt + p->head_w_off, 0, (size_t)((p->feat[0] + 63) / 64 * 64) * 4, st));
-  UB_CUDA(cudaMemcpyAsync(p->wt + p->head_w_off, w, (size_t)p->feat[0] * 4, cudaMemcpyDeviceToDevice, st));
+  const size_t f0 = (size_t)p->feat[0], f0p = (f0 + 63) / 64 * 64;
+  // rows of the logical width copied into zero-extended rows of the physical width
+  UB_CUDA(cudaMemsetAsync(p->wt + p->head_w_off, 0, (size_t)p->out_ch * f0p * 4, st));
+  UB_CUDA(cudaMemcpy2DAsync(p->wt + p->head_w_off, f0p * 4, w, f0 * 4, f0 * 4, (size_t)p->out_ch, cudaMemcpyDeviceToDevice, st));
+  UB_CUDA(cudaMemcpyAsync(p->wt + p->head_b_off, bias, (size_t)p->out_ch * 4, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemcpyAsync(&p->head_bias, bias, 4, cudaMemcpyDeviceToHost, st));
   UB_CUDA(cudaStreamSynchronize(st));
   p->head_set = true;
@@ -895,28 +1025,17 @@ int unet_b200_forward_launches(const unet_b200_plan* p) {
 
 int unet_b200_set_option(const char* name, int value) {
   if (name == nullptr) return fail(UB_ERR_ARG, "null option name");
-  if (strcmp(name, "halo") == 0) {
-    g_opt_halo = value;
-  } else if (strcmp(name, "pdl") == 0) {
-    g_opt_pdl = value;
-  } else if (strcmp(name, "halo2") == 0) {
-    g_opt_halo2 = value;
-  } else if (strcmp(name, "umma2") == 0) {
-    g_opt_umma2 = value;
-  } else if (strcmp(name, "fuse_head") == 0) {
-    g_opt_fuse_head = value;
-  } else if (strcmp(name, "stem_umma") == 0) {
-    g_opt_stem_umma = value;
-  } else if (strcmp(name, "wgrad_rows64") == 0) {
-    g_opt_wgrad_rows64 = value;
-  } else if (strcmp(name, "wgrad2") == 0) {
-    g_opt_wgrad2 = value;
-  } else if (strcmp(name, "wgrad_stream") == 0) {
-    g_opt_wgrad_stream = value;
-  } else {
-    return fail(UB_ERR_ARG, "unknown option '%s'", name);
+  struct { const char* n; int* v; } tab[] = {
+      {"halo", &g_opts.halo}, {"pdl", &g_opts.pdl}, {"halo2", &g_opts.halo2}, {"umma2", &g_opts.umma2},
+      {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
+      {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse}};
+  for (auto& e : tab) {
+    if (strcmp(name, e.n) == 0) {
+      *e.v = value;
+      return UB_OK;
+    }
   }
-  return UB_OK;
+  return fail(UB_ERR_ARG, "unknown option '%s'", name);
 }
 
 static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
@@ -928,6 +1047,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
   for (const Layer& l : p->layers) {
     if (!l.set) return fail(UB_ERR_STATE, "layer weights not set");
   }
+  OptScope opt_scope(&p->opt);
   size_t ei = 0;
   if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
   for (Layer& l : p->layers) {
@@ -968,9 +1088,18 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
   if (!p->layers.back().fuse_head) {
     const Buf& fb = p->bufs[p->final_buf];
     const size_t npix = (size_t)batch * fb.H * fb.W;
-    ub_launch(ub::head_kernel, grid_for(npix * 8, 256), 256, 0, st, 
-        reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
-        p->head_bias, npix, fb.C, logits, probs, mask, threshold);
+    if (p->out_ch == 1) {
+      ub_launch(ub::head_kernel, grid_for(npix * 8, 256), 256, 0, st,
+          reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
+          p->head_bias, npix, fb.C, logits, probs, mask, threshold);
+    } else {
+      // out_channels > 1 (README.md:1447 builds any): outputs are NCHW [batch][out_ch][H][W]
+      const size_t smem = ((size_t)p->out_ch * fb.C + p->out_ch) * 4;
+      ub_launch(ub::head_multi_kernel, grid_for(npix, 256), 256, smem, st,
+          reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
+          reinterpret_cast<const float*>(p->wt + p->head_b_off), batch, (size_t)fb.H * fb.W, fb.C, p->out_ch, logits, probs, mask,
+          threshold);
+    }
     UB_CUDA(cudaGetLastError());
   }
   if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
@@ -1035,7 +1164,13 @@ int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_
                             void* stream) {
   if (src == nullptr || y == nullptr || mean3 == nullptr || std3 == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (batch < 1 || Hs < 1 || Ws < 1 || H < 1 || W < 1) return fail(UB_ERR_ARG, "bad size");
-  if ((size_t)Ws * 3 * 2 > 200 * 1024) return fail(UB_ERR_ARG, "source row too wide for shared-memory staging");
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  // output rows per CTA: as many as keep the staged source rows within 64 KB (several CTAs per SM), at least one
+  int rows = ub::PRE_ROWS;
+  while (rows > 1 && ub::pre_smem_bytes(Ws, W, rows) > 64 * 1024) rows >>= 1;
+  const size_t smem = ub::pre_smem_bytes(Ws, W, rows);
+  if (smem > 200 * 1024) return fail(UB_ERR_ARG, "source row too wide for shared-memory staging (%d pixels)", Ws);
   ub::PreArgs a;
   a.src = src;
   a.pitch = pitch;
@@ -1052,11 +1187,9 @@ int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_
   }
   a.dst = reinterpret_cast<uint2*>(y);
   a.dst_u8 = resized;
-  const size_t smem = (size_t)Ws * 3 * 2;
-  if (smem > 48 * 1024) {
-    UB_CUDA(cudaFuncSetAttribute(ub::preprocess_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  ub_launch(ub::preprocess_u8_kernel, batch * H, 256, smem, static_cast<cudaStream_t>(stream), a);
+  if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
+  const int tiles_h = (H + rows - 1) / rows;
+  ub_launch(ub::preprocess_u8_kernel, batch * tiles_h, ub::PRE_THREADS, smem, static_cast<cudaStream_t>(stream), a, rows);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -1113,11 +1246,11 @@ int unet_b200_resize_gray_u8(const uint8_t* src, int batch, int Hs, int Ws, uint
 
 size_t unet_b200_infer_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
   if (p == nullptr) return 0;
-  const size_t npix = (size_t)p->Bc * p->H * p->W;
+  const size_t npix = (size_t)p->Bc * p->H * p->W, nout = npix * p->out_ch;
   size_t n = align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // frames
   n += align_up(npix * 8, 256);                           // NHWC4 bf16
-  n += 2 * align_up(npix * 4, 256);                       // logits, probs
-  n += align_up(npix, 256);                               // mask
+  n += 2 * align_up(nout * 4, 256);                       // logits, probs
+  n += align_up(nout, 256);                               // mask
   return n;
 }
 
@@ -1127,17 +1260,17 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* fra
   if (p == nullptr || staging == nullptr || frames == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (batch < 1 || batch > p->Bc) return fail(UB_ERR_ARG, "batch %d outside [1,%d]", batch, p->Bc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t npix_c = (size_t)p->Bc * p->H * p->W;
-  const size_t npix = (size_t)batch * p->H * p->W;
+  const size_t npix_c = (size_t)p->Bc * p->H * p->W, nout_c = npix_c * p->out_ch;
+  const size_t npix = (size_t)batch * p->H * p->W * p->out_ch;   // output elements of this call
   uint8_t* s = static_cast<uint8_t*>(staging);
   uint8_t* d_frames = s;
   s += align_up((size_t)p->Bc * Hs * Ws * 3, 256);
   void* d_x = s;
   s += align_up(npix_c * 8, 256);
   float* d_logits = reinterpret_cast<float*>(s);
-  s += align_up(npix_c * 4, 256);
+  s += align_up(nout_c * 4, 256);
   float* d_probs = reinterpret_cast<float*>(s);
-  s += align_up(npix_c * 4, 256);
+  s += align_up(nout_c * 4, 256);
   uint8_t* d_mask = s;
   const size_t frame_bytes = (size_t)Hs * Ws * 3;
   UB_CUDA(cudaMemcpyAsync(d_frames, frames, frame_bytes * batch, cudaMemcpyHostToDevice, st));
@@ -1157,10 +1290,10 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* fra
 // ---- host-buffer entry point with copy/compute overlap over chunks ----------------------------------------------------
 size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
   if (p == nullptr) return 0;
-  const size_t npix = (size_t)p->Bc * p->H * p->W;
+  const size_t npix = (size_t)p->Bc * p->H * p->W, nout = npix * p->out_ch;
   size_t n = 2 * align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // two frame slots
   n += align_up(npix * 8, 256);                               // NHWC4 bf16 (consumed by the stem before the next chunk's preprocess)
-  n += 2 * (2 * align_up(npix * 4, 256) + align_up(npix, 256));  // two output slots: logits, probs, mask
+  n += 2 * (2 * align_up(nout * 4, 256) + align_up(nout, 256));  // two output slots: logits, probs, mask
   return n;
 }
 
@@ -1193,19 +1326,20 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
   s += align_up(npix_c * 8, 256);
   float *d_logits[2], *d_probs[2];
   uint8_t* d_mask[2];
+  const size_t nout_c = npix_c * p->out_ch;
   for (int i = 0; i < 2; ++i) {
     d_logits[i] = reinterpret_cast<float*>(s);
-    s += align_up(npix_c * 4, 256);
+    s += align_up(nout_c * 4, 256);
     d_probs[i] = reinterpret_cast<float*>(s);
-    s += align_up(npix_c * 4, 256);
+    s += align_up(nout_c * 4, 256);
     d_mask[i] = s;
-    s += align_up(npix_c, 256);
+    s += align_up(nout_c, 256);
   }
   // the side streams start after whatever the caller already queued on `stream`
   UB_CUDA(cudaEventRecord(p->ev_start, st));
   UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
   UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
-  const int hw = p->H * p->W;
+  const size_t hw = (size_t)p->H * p->W * p->out_ch;   // output elements per frame
   int it = 0;
   for (int b0 = 0; b0 < total; b0 += p->Bc, ++it) {
     const int n = total - b0 < p->Bc ? total - b0 : p->Bc;

@@ -55,6 +55,7 @@ struct TConvT {
 
 struct unet_b200_trainer {
   int B, H, W, in_ch, levels;
+  Opts opt;                    // the switches this trainer was created with
   int feat[UB_MAX_LEVELS];
   std::vector<TConv> convs;    // plan order: enc0.0, enc0.3, ..., bott.0, bott.3, dec0.0, dec0.3, ...
   std::vector<TConvT> ups;     // decoder order (deepest first)
@@ -73,9 +74,10 @@ struct unet_b200_trainer {
   // weight-gradient side stream (backward): the wgrad GEMM of layer L is forked off after the layer's dgrad and runs next to
   // the HBM-bound BatchNorm / pool backward passes of layer L-1; joined before the backward returns
   cudaStream_t s2 = nullptr;
-  cudaEvent_t ev_join = nullptr;
   std::vector<cudaEvent_t> ev_fork;
   int ev_next = 0;
+  int n_forks = 0;        // weight-gradient launches forked to s2 since stage 0
+  int bwd_stage = -1;     // last backward stage enqueued
   bool fwd_done;
 };
 
@@ -174,30 +176,19 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
   t->ws_bytes = bp.off;
 }
 
-int g_opt_wgrad_rows64 = 1;  // A/B switch: 64-pixel reduction tiles for BLOCK_N == 256
-int g_opt_wgrad2 = 1;        // A/B switch: CTA-pair weight-gradient kernel (wgrad_umma2_kernel) for BLOCK_N >= 128
-int g_opt_wgrad_stream = 1;  // A/B switch: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
-
 template <int BN>
 int launch_wgrad_t(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap* d, const ub::WgradArgs& a, int grid,
                    int slot, bool pair, cudaStream_t st) {
-  static int attr_done[6] = {0, 0, 0, 0, 0, 0};
   using Cfg = ub::WgradCfg<BN>;
   if constexpr (BN >= 128) {
     if (pair) {
-      if (!attr_done[3 + slot]) {
-        UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done[3 + slot] = 1;
-      }
+      UB_CUDA(ensure_smem(ub::wgrad_umma2_kernel<BN>, AT_WGRAD2 + slot, Cfg::SMEM_BYTES));
       ub_launch(ub::wgrad_umma2_kernel<BN>, grid, 192, Cfg::SMEM_BYTES, st, x0, x1, d[0], d[1], d[2], d[3], a);
       UB_CUDA(cudaGetLastError());
       return UB_OK;
     }
   }
-  if (!attr_done[slot]) {
-    UB_CUDA(cudaFuncSetAttribute(ub::wgrad_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done[slot] = 1;
-  }
+  UB_CUDA(ensure_smem(ub::wgrad_umma_kernel<BN>, AT_WGRAD + slot, Cfg::SMEM_BYTES));
   ub_launch(ub::wgrad_umma_kernel<BN>, grid, 192, Cfg::SMEM_BYTES, st, x0, x1, d[0], d[1], d[2], d[3], a);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -223,7 +214,7 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   *bn = pick_block_n(Cout);
   // reduction tile = a box of 128 pixels, or 64 for the wide tiles: (2 + BLOCK_N/64) boxes per stage must leave room for a
   // ring deep enough to hide the L2 latency (BLOCK_N 256: 4 stages of 48 KB instead of 2 of 96 KB)
-  const int rows_full = (*bn == 256 && g_opt_wgrad_rows64) ? 64 : 128;
+  const int rows_full = (*bn == 256 && tl_opts->wgrad_rows64) ? 64 : 128;
   a.TW = pow2_divisor(W, 16);
   a.TH = pow2_divisor(H, rows_full / a.TW);
   a.TB = rows_full / (a.TW * a.TH);
@@ -254,13 +245,13 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   a.rt_total = (a.pair_taps ? 1 : taps) * a.m_tiles;
   // CTA pair: two consecutive row tiles share the dy operand. For a 3x3 conv any two row tiles do (the taps shift only x);
   // the ConvT quads read dy through different views, so there both tiles must belong to the same quad (m_tiles even).
-  *pair = g_opt_wgrad2 && *bn >= 128 && a.rt_total >= 2 && (taps != 4 || a.m_tiles % 2 == 0);
+  *pair = tl_opts->wgrad2 && *bn >= 128 && a.rt_total >= 2 && (taps != 4 || a.m_tiles % 2 == 0);
   const int P = *pair ? 2 : 1;
   a.stages = ub::WGRAD_RING_BYTES / ((2 + *bn / 64 / P) * a.blk_bytes);
   if (a.stages > ub::WGRAD_MAX_STAGES) a.stages = ub::WGRAD_MAX_STAGES;
   const int tiles = ((a.rt_total + P - 1) / P) * a.n_tiles;   // work items per K slice (each runs on P CTAs)
   const int ptiles = a.tiles_w * a.tiles_h * a.tiles_b;
-  int ks = (g_num_sms / P) / tiles;
+  int ks = (cur_sms() / P) / tiles;
   if (ks < 1) ks = 1;
   if (ks > ptiles) ks = ptiles;
   a.ksplit = ks;
@@ -377,7 +368,7 @@ int trainer_build_maps(unet_b200_trainer* t) {
 int chan_grid(size_t npix, int C8) {
   const int ppb = 256 / C8;
   size_t g = (npix + ppb - 1) / ppb;
-  const size_t cap = (size_t)(g_num_sms > 0 ? g_num_sms : 148) * 8;
+  const size_t cap = (size_t)cur_sms() * 8;
   if (g > cap) g = cap;
   return g < 1 ? 1 : (int)g;
 }
@@ -466,12 +457,7 @@ int conv_bn_backward(const TConv& c, int B, float* s1, float* s2, const ub::Grad
 // Weight gradient of one conv (3x3 on tensor cores, stem on tensor cores for Cout == 64), accumulated into dw (PyTorch layout).
 int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long long off, cudaStream_t st) {
   if (c.stem && c.Cout == 64) {
-    static int attr_done_tc = 0;
-    if (!attr_done_tc) {
-      UB_CUDA(cudaFuncSetAttribute(ub::stem_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ub::StemWgradCfg::SMEM_BYTES));
-      attr_done_tc = 1;
-    }
+    UB_CUDA(ensure_smem(ub::stem_wgrad_umma_kernel, AT_STEM_WGRAD_TC, ub::StemWgradCfg::SMEM_BYTES));
     ub::StemWgradArgs sa;
     sa.B = B;
     sa.H = c.H;
@@ -483,7 +469,7 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
     sa.route = route;
     sa.off = off;
     const int pairs = (sa.tiles_w * sa.tiles_h * B + 1) / 2;
-    const int grid = pairs < g_num_sms ? pairs : g_num_sms;
+    const int grid = pairs < cur_sms() ? pairs : cur_sms();
     ub_launch(ub::stem_wgrad_umma_kernel, grid, ub::StemWgradCfg::THREADS, ub::StemWgradCfg::SMEM_BYTES, st, c.wD, sa);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
@@ -491,13 +477,9 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
   if (c.stem) {
     if (c.Cout > 128) return fail(UB_ERR_ARG, "stem weight gradient supports Cout <= 128");
     const size_t smem = (size_t)(18 * 18 * 4 + 256 * c.Cout) * 4;
-    static int attr_done = 0;
-    if (!attr_done) {
-      UB_CUDA(cudaFuncSetAttribute(ub::stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (18 * 18 * 4 + 256 * 128) * 4));
-      attr_done = 1;
-    }
+    UB_CUDA(ensure_smem(ub::stem_wgrad_kernel, AT_STEM_WGRAD, (18 * 18 * 4 + 256 * 128) * 4));
     const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;
-    const int grid = tiles < 2 * g_num_sms ? tiles : 2 * g_num_sms;
+    const int grid = tiles < 2 * cur_sms() ? tiles : 2 * cur_sms();
     ub_launch(ub::stem_wgrad_kernel, grid, 256, smem, st, reinterpret_cast<const uint2*>(c.x0),
                                                     reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, route, off);
     UB_CUDA(cudaGetLastError());
@@ -514,11 +496,12 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
 // (fork), or `st` itself when the overlap is switched off. Works the same eagerly and under stream capture.
 int wgrad_stream(unet_b200_trainer* t, cudaStream_t st, cudaStream_t* out) {
   *out = st;
-  if (!g_opt_wgrad_stream || t->s2 == nullptr) return UB_OK;
+  if (!tl_opts->wgrad_stream || t->s2 == nullptr) return UB_OK;
   if (t->ev_next >= (int)t->ev_fork.size()) return fail(UB_ERR_STATE, "out of fork events");
   cudaEvent_t ev = t->ev_fork[t->ev_next++];
   UB_CUDA(cudaEventRecord(ev, st));
   UB_CUDA(cudaStreamWaitEvent(t->s2, ev, 0));
+  ++t->n_forks;
   *out = t->s2;
   return UB_OK;
 }
@@ -572,13 +555,20 @@ int trainer_up_backward(unet_b200_trainer* t, TConvT& u, const ub::GradRoute& ro
   return up_wgrad_launch(u, t->B, 2 * (u.f / 8), route, u.w_off, u.b_off, sw);
 }
 
-float* g_zero_bias = nullptr;  // 4096 zero floats for the single-op entry points (allocated once per process)
+// 4096 zero floats for the single-op entry points (allocated once per device)
 int get_zero_bias(float** out) {
-  if (g_zero_bias == nullptr) {
-    UB_CUDA(cudaMalloc(&g_zero_bias, 4096 * 4));
-    UB_CUDA(cudaMemset(g_zero_bias, 0, 4096 * 4));
+  DevState* d = cur_dev();
+  float* zb = d->zero_bias.load(std::memory_order_acquire);
+  if (zb == nullptr) {
+    UB_CUDA(cudaMalloc(&zb, 4096 * 4));
+    UB_CUDA(cudaMemset(zb, 0, 4096 * 4));
+    float* expected = nullptr;
+    if (!d->zero_bias.compare_exchange_strong(expected, zb)) {   // another thread got there first
+      cudaFree(zb);
+      zb = expected;
+    }
   }
-  *out = g_zero_bias;
+  *out = zb;
   return UB_OK;
 }
 
@@ -611,6 +601,7 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   t->levels = levels;
   t->ws = nullptr;
   t->fwd_done = false;
+  t->opt = g_opts;
   for (int i = 0; i < levels; ++i) t->feat[i] = features[i];
 
   auto mk = [&](int h, int w, int c0, int c1, int cout, bool stem, bool pooled) {
@@ -708,7 +699,6 @@ void unet_b200_trainer_destroy(unet_b200_trainer* t) {
   for (cudaEvent_t e : t->ev_fork) {
     if (e != nullptr) cudaEventDestroy(e);
   }
-  if (t->ev_join != nullptr) cudaEventDestroy(t->ev_join);
   if (t->s2 != nullptr) cudaStreamDestroy(t->s2);
   delete t;
 }
@@ -725,14 +715,14 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
   if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(UB_ERR_ARG, "workspace must be 1024-byte aligned");
   int rc = device_check();
   if (rc != UB_OK) return rc;
+  OptScope opt_scope(&t->opt);
   t->ws = static_cast<uint8_t*>(workspace_dev);
   trainer_layout(t, reinterpret_cast<uintptr_t>(workspace_dev));
   UB_CUDA(cudaMemset(t->zero_bias, 0, 4096 * 4));
   t->fwd_done = false;
   if (t->s2 == nullptr) {
     UB_CUDA(cudaStreamCreateWithFlags(&t->s2, cudaStreamNonBlocking));
-    UB_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
-    t->ev_fork.resize(t->convs.size() + t->ups.size() + 2);
+    t->ev_fork.resize(t->convs.size() + t->ups.size() + 2 + 2 * (2 * t->levels + 3));
     for (cudaEvent_t& e : t->ev_fork) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   {
@@ -770,6 +760,7 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
                             float* const* running_var, float momentum, float eps, float* logits, void* stream) {
   if (t == nullptr || x_nhwc4 == nullptr || params == nullptr || logits == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (t->ws == nullptr) return fail(UB_ERR_STATE, "trainer is not bound");
+  OptScope opt_scope(&t->opt);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = t->B;
   UB_CUDA(cudaMemcpyAsync(t->x_in, x_nhwc4, (size_t)B * t->H * t->W * 8, cudaMemcpyDeviceToDevice, st));
@@ -805,63 +796,145 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   return UB_OK;
 }
 
-static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const float* params, const ub::GradRoute& route,
-                               bool zero_local, cudaStream_t st) {
-  if (t == nullptr || dlogits == nullptr || params == nullptr || route.local == nullptr) return fail(UB_ERR_ARG, "null argument");
-  if (!t->fwd_done) return fail(UB_ERR_STATE, "train_backward needs a preceding train_forward");
+// ---- backward in stages ------------------------------------------------------------------------------------------------
+// The backward pass is cut where a contiguous range of the flat gradient becomes final, so that a data-parallel caller can
+// start exchanging that range while the rest of the backward still runs (decoder gradients are final first):
+//   stage 0            head (output.weight / output.bias); also clears the gradient buffer
+//   stage 1 .. L       decoder level j = L - stage  (shallowest level first: ConvT j + its double conv)
+//   stage L + 1        bottleneck
+//   stage L + 2 .. 2L+1  encoder level i = 2L + 1 - stage
+// A stage only ENQUEUES work (on `st` and on the trainer's weight-gradient side stream); unet_b200_trainer_join makes a
+// stream wait for all of it.
+static int trainer_num_stages(const unet_b200_trainer* t) { return 2 * t->levels + 2; }
+
+static void stage_range(const unet_b200_trainer* t, int stage, long long* lo, long long* hi) {
+  const int L = t->levels;
+  if (stage == 0) {
+    *lo = t->head_w_off;
+    *hi = t->n_params;
+  } else if (stage <= L) {
+    const int j = L - stage;
+    *lo = t->ups[j].w_off;
+    *hi = (j + 1 < L) ? t->ups[j + 1].w_off : t->convs[2 * L].w_off;   // next decoder level, or the bottleneck
+  } else if (stage == L + 1) {
+    *lo = t->convs[2 * L].w_off;
+    *hi = t->head_w_off;
+  } else {
+    const int i = 2 * L + 1 - stage;
+    *lo = t->convs[2 * i].w_off;
+    *hi = (i + 1 < L) ? t->convs[2 * i + 2].w_off : t->ups[0].w_off;
+  }
+}
+
+static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const float* dlogits, const float* params,
+                                     const ub::GradRoute& route, bool zero_local, cudaStream_t st) {
+  if (t == nullptr || params == nullptr || route.local == nullptr) return fail(UB_ERR_ARG, "null argument");
   const int B = t->B, L = t->levels;
-  t->ev_next = 0;
-  if (zero_local) UB_CUDA(cudaMemsetAsync(route.local, 0, (size_t)t->n_params * 4, st));
-  // s1 received the pack kernels' (all-zero) bias in the forward and s2 was cleared with the accumulator region: both are
-  // zero here, once per forward/backward pair
-  TConv& last = t->convs.back();
-  {
+  if (stage < 0 || stage >= trainer_num_stages(t)) return fail(UB_ERR_ARG, "stage %d outside [0,%d)", stage, trainer_num_stages(t));
+  OptScope opt_scope(&t->opt);
+  int rc;
+  if (stage == 0) {
+    if (dlogits == nullptr) return fail(UB_ERR_ARG, "null argument");
+    if (!t->fwd_done) return fail(UB_ERR_STATE, "train_backward needs a preceding train_forward");
+    t->ev_next = 0;
+    t->n_forks = 0;
+    t->bwd_stage = 0;
+    if (zero_local) UB_CUDA(cudaMemsetAsync(route.local, 0, (size_t)t->n_params * 4, st));
+    // s1 received the pack kernels' (all-zero) bias in the forward and s2 was cleared with the accumulator region: both are
+    // zero here, once per forward/backward pair
+    TConv& last = t->convs.back();
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
-    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st, 
+    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st,
         reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g), route,
         t->head_w_off, t->head_b_off);
     UB_CUDA(cudaGetLastError());
+  } else {
+    if (t->bwd_stage != stage - 1) return fail(UB_ERR_STATE, "backward stages must run in order (got %d after %d)", stage, t->bwd_stage);
+    if (stage <= L) {
+      const int j = L - stage;
+      rc = trainer_conv_backward(t, t->convs[2 * L + 3 + 2 * j], route, st);
+      if (rc != UB_OK) return rc;
+      rc = trainer_conv_backward(t, t->convs[2 * L + 2 + 2 * j], route, st);
+      if (rc != UB_OK) return rc;
+      rc = trainer_up_backward(t, t->ups[j], route, st);
+      if (rc != UB_OK) return rc;
+    } else if (stage == L + 1) {
+      rc = trainer_conv_backward(t, t->convs[2 * L + 1], route, st);
+      if (rc != UB_OK) return rc;
+      rc = trainer_conv_backward(t, t->convs[2 * L], route, st);
+      if (rc != UB_OK) return rc;
+    } else {
+      const int i = 2 * L + 1 - stage;
+      TConv& c1 = t->convs[2 * i + 1];
+      const TConv& next0 = t->convs[2 * i + 2];                 // consumer of the pooled tensor (next encoder level / bottleneck)
+      const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
+      const int C8 = c1.Cout / 8;
+      const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
+      ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, st,
+          reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
+          2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
+      UB_CUDA(cudaGetLastError());
+      rc = trainer_conv_backward(t, c1, route, st);
+      if (rc != UB_OK) return rc;
+      rc = trainer_conv_backward(t, t->convs[2 * i], route, st);
+      if (rc != UB_OK) return rc;
+    }
   }
-  int rc;
-  for (int j = L - 1; j >= 0; --j) {
-    rc = trainer_conv_backward(t, t->convs[2 * L + 3 + 2 * j], route, st);
-    if (rc != UB_OK) return rc;
-    rc = trainer_conv_backward(t, t->convs[2 * L + 2 + 2 * j], route, st);
-    if (rc != UB_OK) return rc;
-    rc = trainer_up_backward(t, t->ups[j], route, st);
-    if (rc != UB_OK) return rc;
-  }
-  rc = trainer_conv_backward(t, t->convs[2 * L + 1], route, st);
-  if (rc != UB_OK) return rc;
-  rc = trainer_conv_backward(t, t->convs[2 * L], route, st);
-  if (rc != UB_OK) return rc;
-  for (int i = L - 1; i >= 0; --i) {
-    TConv& c1 = t->convs[2 * i + 1];
-    const TConv& next0 = t->convs[2 * i + 2];                 // consumer of the pooled tensor (next encoder level / bottleneck)
-    const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
-    const int C8 = c1.Cout / 8;
-    const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
-    ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, st, 
-        reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
-        2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
-    UB_CUDA(cudaGetLastError());
-    rc = trainer_conv_backward(t, c1, route, st);
-    if (rc != UB_OK) return rc;
-    rc = trainer_conv_backward(t, t->convs[2 * i], route, st);
-    if (rc != UB_OK) return rc;
-  }
-  if (t->ev_next > 0) {   // join: the gradient is complete on `st` when every forked wgrad has finished
-    UB_CUDA(cudaEventRecord(t->ev_join, t->s2));
-    UB_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
-  }
-  t->fwd_done = false;
+  t->bwd_stage = stage;
+  if (stage == trainer_num_stages(t) - 1) t->fwd_done = false;
   return UB_OK;
+}
+
+// `waiter` waits for everything the backward stages have enqueued so far: the work on `st` and the forked weight-gradient GEMMs.
+static int trainer_join_impl(unet_b200_trainer* t, cudaStream_t st, cudaStream_t waiter) {
+  if (t->ev_next + 2 > (int)t->ev_fork.size()) return fail(UB_ERR_STATE, "out of join events");
+  if (t->s2 != nullptr && t->n_forks > 0) {
+    cudaEvent_t e2 = t->ev_fork[t->ev_next++];
+    UB_CUDA(cudaEventRecord(e2, t->s2));
+    UB_CUDA(cudaStreamWaitEvent(waiter, e2, 0));
+  }
+  if (waiter != st) {
+    cudaEvent_t e1 = t->ev_fork[t->ev_next++];
+    UB_CUDA(cudaEventRecord(e1, st));
+    UB_CUDA(cudaStreamWaitEvent(waiter, e1, 0));
+  }
+  return UB_OK;
+}
+
+static int train_backward_impl(unet_b200_trainer* t, const float* dlogits, const float* params, const ub::GradRoute& route,
+                               bool zero_local, cudaStream_t st) {
+  if (t == nullptr) return fail(UB_ERR_ARG, "null argument");
+  for (int s = 0; s < trainer_num_stages(t); ++s) {
+    int rc = train_backward_stage_impl(t, s, dlogits, params, route, zero_local, st);
+    if (rc != UB_OK) return rc;
+  }
+  return trainer_join_impl(t, st, st);   // the gradient is complete on `st` when every forked wgrad has finished
 }
 
 int unet_b200_train_backward(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads, void* stream) {
   ub::GradRoute route{nullptr, grads, 0u};
   return train_backward_impl(t, dlogits, params, route, true, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_trainer_num_stages(const unet_b200_trainer* t) { return t ? trainer_num_stages(t) : 0; }
+
+int unet_b200_trainer_stage_range(const unet_b200_trainer* t, int stage, long long* lo, long long* hi) {
+  if (t == nullptr || lo == nullptr || hi == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (stage < 0 || stage >= trainer_num_stages(t)) return fail(UB_ERR_ARG, "stage %d outside [0,%d)", stage, trainer_num_stages(t));
+  stage_range(t, stage, lo, hi);
+  return UB_OK;
+}
+
+int unet_b200_train_backward_stage(unet_b200_trainer* t, int stage, const float* dlogits, const float* params, float* grads,
+                                   void* stream) {
+  ub::GradRoute route{nullptr, grads, 0u};
+  return train_backward_stage_impl(t, stage, dlogits, params, route, true, static_cast<cudaStream_t>(stream));
+}
+
+int unet_b200_trainer_join(unet_b200_trainer* t, void* stream, void* waiter_stream) {
+  if (t == nullptr) return fail(UB_ERR_ARG, "null argument");
+  return trainer_join_impl(t, static_cast<cudaStream_t>(stream), static_cast<cudaStream_t>(waiter_stream));
 }
 
 int unet_b200_train_backward_p2p(unet_b200_trainer* t, const float* dlogits, const float* params, float* grads_local,
@@ -873,25 +946,53 @@ int unet_b200_train_backward_p2p(unet_b200_trainer* t, const float* dlogits, con
   return train_backward_impl(t, dlogits, params, route, false, static_cast<cudaStream_t>(stream));
 }
 
+// AdamW over NVLink on the flat range [lo, hi) (lo a multiple of 4): sum of the range over every rank's gradient buffer
+// (peer loads; grad_bases == NULL: the local buffer already holds the sum and is cleared), update, store to every rank's
+// parameters. m / v hold hi - lo elements: the caller's optimizer state for exactly this range.
+int unet_b200_adamw_range_p2p(float* const* param_bases_dev, float* const* grad_bases_dev, int world, int rank, float* grads_local,
+                              long long lo, long long hi, float* m, float* v, float lr, const float* lr_dev, float beta1,
+                              float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+  if (param_bases_dev == nullptr || grads_local == nullptr || m == nullptr || v == nullptr || step_dev == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  if (world < 1 || rank < 0 || rank >= world) return fail(UB_ERR_ARG, "bad rank / world");
+  if (lo < 0 || (lo & 3)) return fail(UB_ERR_ARG, "range start %lld must be a non-negative multiple of 4", lo);
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
+  if (hi <= lo) return UB_OK;
+  ub_launch(ub::adamw_shard_allgather_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream),
+      param_bases_dev, grad_bases_dev, world, rank, grads_local, m, v, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale,
+      step_dev, lr_dev);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
 int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_bases_dev, int world, int rank,
                              float* grads_local, float* exp_avg_shard,
                              float* exp_avg_sq_shard, long long n, float lr, float beta1, float beta2, float eps,
                              float weight_decay, const int* step_dev, float grad_scale, void* stream) {
-  if (param_bases_dev == nullptr || grads_local == nullptr || exp_avg_shard == nullptr || exp_avg_sq_shard == nullptr ||
-      step_dev == nullptr) {
-    return fail(UB_ERR_ARG, "null argument");
-  }
   if (world < 1 || rank < 0 || rank >= world) return fail(UB_ERR_ARG, "bad rank / world");
-  int rc = device_check();
-  if (rc != UB_OK) return rc;
   const long long shard = ((n + world - 1) / world + 3) / 4 * 4;   // multiple of 4: 16-byte accesses stay aligned
   const long long lo = shard * rank;
   long long hi = lo + shard;
   if (hi > n) hi = n;
+  return unet_b200_adamw_range_p2p(param_bases_dev, grad_bases_dev, world, rank, grads_local, lo, hi, exp_avg_shard,
+                                   exp_avg_sq_shard, lr, nullptr, beta1, beta2, eps, weight_decay, step_dev, grad_scale, stream);
+}
+
+// NVSwitch form on the flat range [lo, hi): multimem.ld_reduce of the gradients, multimem.st of the new parameters.
+int unet_b200_adamw_range_multimem(float* params_mc, const float* grads_mc, const float* params_local, long long lo, long long hi,
+                                   float* m, float* v, float lr, const float* lr_dev, float beta1, float beta2, float eps,
+                                   float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+  if (params_mc == nullptr || grads_mc == nullptr || params_local == nullptr || m == nullptr || v == nullptr || step_dev == nullptr) {
+    return fail(UB_ERR_ARG, "null argument");
+  }
+  if (lo < 0 || (lo & 3)) return fail(UB_ERR_ARG, "range start %lld must be a non-negative multiple of 4", lo);
+  int rc = device_check();
+  if (rc != UB_OK) return rc;
   if (hi <= lo) return UB_OK;
-  ub_launch(ub::adamw_shard_allgather_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), 
-      param_bases_dev, grad_bases_dev, world, rank, grads_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay,
-      grad_scale, step_dev);
+  ub_launch(ub::adamw_shard_multimem_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream),
+      params_mc, grads_mc, params_local, m, v, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev, lr_dev);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -899,23 +1000,13 @@ int unet_b200_adamw_step_p2p(float* const* param_bases_dev, float* const* grad_b
 int unet_b200_adamw_step_multimem(float* params_mc, const float* grads_mc, const float* params_local, int world, int rank,
                                   float* exp_avg_shard, float* exp_avg_sq_shard, long long n, float lr, float beta1, float beta2,
                                   float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
-  if (params_mc == nullptr || grads_mc == nullptr || params_local == nullptr || exp_avg_shard == nullptr ||
-      exp_avg_sq_shard == nullptr || step_dev == nullptr) {
-    return fail(UB_ERR_ARG, "null argument");
-  }
   if (world < 1 || rank < 0 || rank >= world) return fail(UB_ERR_ARG, "bad rank / world");
-  int rc = device_check();
-  if (rc != UB_OK) return rc;
   const long long shard = ((n + world - 1) / world + 3) / 4 * 4;
   const long long lo = shard * rank;
   long long hi = lo + shard;
   if (hi > n) hi = n;
-  if (hi <= lo) return UB_OK;
-  ub_launch(ub::adamw_shard_multimem_kernel, grid_for((size_t)(hi - lo + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), 
-      params_mc, grads_mc, params_local, exp_avg_shard, exp_avg_sq_shard, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale,
-      step_dev);
-  UB_CUDA(cudaGetLastError());
-  return UB_OK;
+  return unet_b200_adamw_range_multimem(params_mc, grads_mc, params_local, lo, hi, exp_avg_shard, exp_avg_sq_shard, lr, nullptr,
+                                        beta1, beta2, eps, weight_decay, step_dev, grad_scale, stream);
 }
 
 int unet_b200_multimem_reduce(const float* x_mc, long long lo, long long n, float* out, void* stream) {
@@ -965,13 +1056,14 @@ int unet_b200_adamw_step(float* params, const float* grads, float* exp_avg, floa
   const float bc2 = 1.f - powf(beta2, (float)step);
   ub_launch(ub::adamw_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                    beta2, eps, weight_decay, bc1, bc2, grad_scale,
-                                                                                   nullptr);
+                                                                                   nullptr, nullptr);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
-int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                             const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, const int* step_dev,
+                             float grad_scale, void* stream) {
   if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || step_dev == nullptr) {
     return fail(UB_ERR_ARG, "null argument");
   }
@@ -979,7 +1071,7 @@ int unet_b200_adamw_step_dev(float* params, const float* grads, float* exp_avg, 
   if (rc != UB_OK) return rc;
   ub_launch(ub::adamw_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                    beta2, eps, weight_decay, 1.f, 1.f, grad_scale,
-                                                                                   step_dev);
+                                                                                   step_dev, lr_dev);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }

@@ -499,8 +499,9 @@ bce_dice_grad_kernel(const float* __restrict__ z, const float* __restrict__ t, s
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, float grad_scale,
-             const int* __restrict__ step_dev) {
+             const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
   pdl_enter();
+  if (lr_dev != nullptr) lr = *lr_dev;   // learning rate in device memory: a scheduler changes it without re-capturing the graph
   if (step_dev != nullptr) {
     const float st = static_cast<float>(*step_dev);
     bc1 = 1.f - powf(beta1, st);
@@ -545,8 +546,9 @@ __global__ void __launch_bounds__(256)
 adamw_shard_allgather_kernel(float* const* __restrict__ param_bases, float* const* __restrict__ grad_bases, int world, int rank,
                              float* __restrict__ grads, float* __restrict__ m, float* __restrict__ v, long long lo, long long hi,
                              float lr, float beta1, float beta2, float eps, float wd, float grad_scale,
-                             const int* __restrict__ step_dev) {
+                             const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
   pdl_enter();
+  if (lr_dev != nullptr) lr = *lr_dev;
   const float st = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
   const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);
@@ -622,8 +624,10 @@ __device__ __forceinline__ void multimem_st(float* mc_addr, float v) {
 __global__ void __launch_bounds__(256)
 adamw_shard_multimem_kernel(float* __restrict__ params_mc, const float* __restrict__ grads_mc, const float* __restrict__ plocal,
                             float* __restrict__ m, float* __restrict__ v, long long lo, long long hi, float lr, float beta1,
-                            float beta2, float eps, float wd, float grad_scale, const int* __restrict__ step_dev) {
+                            float beta2, float eps, float wd, float grad_scale, const int* __restrict__ step_dev,
+                            const float* __restrict__ lr_dev) {
   pdl_enter();
+  if (lr_dev != nullptr) lr = *lr_dev;
   const float st = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(beta1, st), bc2 = 1.f - powf(beta2, st);
   const float step_size = lr / bc1, inv_sqrt_bc2 = 1.f / sqrtf(bc2);

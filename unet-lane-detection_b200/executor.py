@@ -83,7 +83,15 @@ class B200_model_container:
             sd = remap_milesial_state_dict(sd)
             feats, cin, cout = _features_from_state_dict(sd)
             model = UNet(cin, cout, feats)
-            model.load_state_dict(sd, strict=all(k in sd for k in model.state_dict()))
+            # only the BatchNorm step counters may be absent (exports that drop integer buffers); a checkpoint that lacks real
+            # tensors would otherwise load silently and serve the random initialisation of the missing layers
+            res = model.load_state_dict(sd, strict=False)
+            missing = [k for k in res.missing_keys if not k.endswith("num_batches_tracked")]
+            if missing or res.unexpected_keys:
+                raise ValueError(f"checkpoint does not match UNet(in={cin}, out={cout}, features={feats}): "
+                                 f"missing {missing[:6]}{'...' if len(missing) > 6 else ''}, "
+                                 f"unexpected {list(res.unexpected_keys)[:6]}")
+            model.b200_frozen = True      # private copy, weights fixed from here on
         self.model = model.to(dev).eval()
         self.device = dev
         self.output = output  # "probs" (deployed graph has the sigmoid inside) or "logits"
@@ -110,7 +118,7 @@ class B200_model_container:
                 return [out.reshape(B, 1, *size).cpu().numpy()]
             # the per-frame path of the ROS node (one small batch per call, same shape every time): the ~24 launches of a pass
             # are captured once per (shape, weights) and replayed - launch overhead is most of a batch-1 pass
-            key = (B, size, self.output, self.model._weights_key())
+            key = (B, size, self.output) if self.model.b200_frozen else (B, size, self.output, self.model._weights_key())
             entry = self._graphs.get(key)
             if entry is None:
                 self._graphs.clear()     # one live shape at a time (a new key also means new weights)
@@ -122,9 +130,9 @@ class B200_model_container:
                 with torch.cuda.graph(graph):
                     logits, probs, _ = self.model.predict_mask(static_in, size=size, want=(self.output,))
                 out = probs if self.output == "probs" else logits
-                entry = (graph, static_in, out)
+                entry = (graph, static_in, out, self.model._last_engine)   # the graph replays into this plan's buffers
                 self._graphs[key] = entry
-            graph, static_in, out = entry
+            graph, static_in, out, _ = entry
             static_in.copy_(torch.from_numpy(frames), non_blocking=True)
             graph.replay()
             return [out.reshape(B, 1, *size).cpu().numpy()]

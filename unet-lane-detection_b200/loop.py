@@ -63,19 +63,24 @@ def train_one_epoch(step: FusedTrainStep, dataloader, device="cuda"):
 
 
 @torch.no_grad()
-def validate(model, dataloader, device="cuda", pos_weight=3.0, bce_weight=0.5, dice_weight=0.5, smooth=1e-6):
-    """README.md:2086-2112: eval-mode forward (folded BatchNorm), criterion and thresholded Dice per batch, batch means."""
+def validate(model, dataloader, device="cuda", pos_weight=3.0, bce_weight=0.5, dice_weight=0.5, smooth=1e-6, process_group=None):
+    """README.md:2086-2112: eval-mode forward (folded BatchNorm), criterion and thresholded Dice per batch, batch means.
+    Data-parallel (torch.distributed initialised): every rank validates ITS loader and the sums are all-reduced, so all
+    ranks return the same two numbers (the mean over all batches of all ranks) and take the same best-model / early-stop
+    decisions."""
     model.eval()
-    acc = torch.zeros(4, dtype=torch.float32, device=device)
-    n = 0
+    acc = torch.zeros(5, dtype=torch.float32, device=device)   # 4 metric sums + the batch count
     for images, masks in dataloader:
         images = images.to(device, non_blocking=True)
         masks = masks.to(device, non_blocking=True)
         outputs = model(images)
-        acc += validation_metrics(outputs, masks, pos_weight, bce_weight, dice_weight, smooth)
-        n += 1
-    acc = (acc / max(n, 1)).tolist()
-    return acc[0], acc[3]
+        acc[:4] += validation_metrics(outputs, masks, pos_weight, bce_weight, dice_weight, smooth)
+        acc[4] += 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(process_group) > 1:
+        torch.distributed.all_reduce(acc, op=torch.distributed.ReduceOp.SUM, group=process_group)
+    acc = acc.tolist()
+    n = max(acc[4], 1.0)
+    return acc[0] / n, acc[3] / n
 
 
 class EarlyStopping:
@@ -108,20 +113,33 @@ def fit(model, train_loader, val_loader, config, process_group=None, logger=None
     base_lr = config["learning_rate"]
     step = FusedTrainStep(model, lr=base_lr, weight_decay=config["weight_decay"], process_group=process_group)
     stopper = EarlyStopping(config["patience"])
-    rank0 = (not torch.distributed.is_initialized()) or torch.distributed.get_rank(process_group) == 0
+    distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+        torch.distributed.get_world_size(process_group) > 1
+    rank0 = (not distributed) or torch.distributed.get_rank(process_group) == 0
     os.makedirs(config["save_dir"], exist_ok=True)
     history = []
     for epoch in range(1, config["epochs"] + 1):
         step.lr = cosine_warm_restarts_lr(base_lr, epoch - 1)          # scheduler.step() ran epoch-1 times so far
         logger.info("Epoch %d/%d  Learning Rate: %.6f", epoch, config["epochs"], step.lr)
         train_loss = train_one_epoch(step, train_loader, device)
-        val_loss, val_dice = validate(model, val_loader, device, **{k: step.loss_cfg[k] for k in step.loss_cfg})
+        if distributed:
+            # BatchNorm running statistics are per replica (batch statistics of the replica's own samples, as a
+            # single-device reference run would see them): evaluate and checkpoint rank 0's, on every rank
+            src = torch.distributed.get_global_rank(process_group, 0) if process_group is not None else 0
+            for buf in model.buffers():
+                torch.distributed.broadcast(buf, src=src, group=process_group)
+            model._b200_epoch += 1
+        val_loss, val_dice = validate(model, val_loader, device, process_group=process_group,
+                                      **{k: step.loss_cfg[k] for k in step.loss_cfg})
         history.append({"epoch": epoch, "lr": step.lr, "train_loss": train_loss, "val_loss": val_loss, "val_dice": val_dice})
         logger.info("Train Loss: %.4f  Val Loss: %.4f, Val Dice: %.4f", train_loss, val_loss, val_dice)
+        # val_dice is identical on every rank (validate all-reduces), so is_best / stop are too: all ranks leave the loop together
         is_best, stop = stopper.update(val_dice)
-        if is_best and rank0:
-            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": step.state_dict(),
-                        "best_dice": stopper.best}, os.path.join(config["save_dir"], "best_model.pth"))
+        if is_best:
+            opt_sd = step.state_dict()       # collective when the optimizer state is sharded over the replicas: every rank calls it
+            if rank0:
+                torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": opt_sd,
+                            "best_dice": stopper.best}, os.path.join(config["save_dir"], "best_model.pth"))
         if stop:
             logger.info("Early stopping at epoch %d", epoch)
             break

@@ -9,12 +9,15 @@ packs them for the tensor-core kernels and runs the hand-written CUDA path. CPU 
 missing/unsupported device, raise - there is no PyTorch/cuDNN fallback.
 """
 import ctypes as C
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
 
 from ._lib import check, f3, lib
 from .ops import MEAN_255, STD_255
+
+MAX_ENGINES = 4   # bound plans kept per model (each owns a workspace + packed weights): least recently used goes first
 
 
 class _Engine:
@@ -64,8 +67,12 @@ class UNet(nn.Module):
         # same tensor-core kernel, logits within 1e-4; about 3x the tensor work) - BASELINE.json north_star parity gates
         self.b200_precision = "bf16"
         self._split_weights = None
-        self._engines = {}
+        self._engines = OrderedDict()   # LRU, at most MAX_ENGINES entries (shared with the trainers of training.py)
         self._b200_epoch = 0  # bumped whenever a kernel updates parameters / BN buffers in place
+        # True: the weights will not change any more (a deployed model, e.g. inside B200_model_container) - the per-call
+        # check that walks all 118 tensors for in-place updates is skipped once a plan has packed them
+        self.b200_frozen = False
+        self._last_engine = None
         self.gpu_launches = 0
 
     def _conv_block(self, in_channels, out_channels):
@@ -98,8 +105,14 @@ class UNet(nn.Module):
         key = (str(device), cap, H, W)
         eng = self._engines.get(key)
         if eng is None:
+            while len(self._engines) >= MAX_ENGINES:
+                self._engines.popitem(last=False)
             eng = _Engine(self, device, cap, H, W)
             self._engines[key] = eng
+        else:
+            self._engines.move_to_end(key)
+        if self.b200_frozen and eng.weights_key is not None:
+            return eng
         wkey = self._weights_key()
         if eng.weights_key != wkey:
             self._pack(eng)
@@ -121,7 +134,8 @@ class UNet(nn.Module):
         for j in range(len(self.features)):
             up = self.decoder_blocks[2 * j]
             check(lib.unet_b200_plan_set_convT(eng.handle, j, dev32(up.weight), dev32(up.bias), st))
-        check(lib.unet_b200_plan_set_head(eng.handle, dev32(self.output.weight.reshape(-1)), dev32(self.output.bias), st))
+        check(lib.unet_b200_plan_set_head(eng.handle, dev32(self.output.weight.reshape(self.out_channels, -1)),
+                                          dev32(self.output.bias), st))
         torch.cuda.current_stream().synchronize()
 
     def _check_input(self, t, what):
@@ -151,7 +165,7 @@ class UNet(nn.Module):
         check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, self.in_channels, H, W, x4.data_ptr(), st))
         self.gpu_launches += 1
         logits = self.forward_nhwc4(x4, want=("logits",))[0]
-        return logits.reshape(B, 1, H, W).to(x.dtype)
+        return logits.reshape(B, self.out_channels, H, W).to(x.dtype)
 
     def _forward_split(self, xin):
         """fp32-class eval forward (b200_precision == "fp32"): fp32 NCHW in -> fp32 logits [B,H,W]. Layer by layer through the
@@ -207,14 +221,17 @@ class UNet(nn.Module):
         return logits
 
     def forward_nhwc4(self, x4, threshold=0.5, want=("logits",)):
-        """x4: bf16 [B,H,W,4] normalised input. Returns (logits, probs, mask) with None for outputs not in `want`."""
+        """x4: bf16 [B,H,W,4] normalised input. Returns (logits, probs, mask) with None for outputs not in `want`;
+        shapes [B,H,W] for out_channels == 1 (the reference's case), [B,out_channels,H,W] otherwise."""
         self._check_input(x4, "input")
         B, H, W, _ = x4.shape
         dev = x4.device
         eng = self._engine(dev, H, W, B)
-        logits = torch.empty(B, H, W, dtype=torch.float32, device=dev) if "logits" in want else None
-        probs = torch.empty(B, H, W, dtype=torch.float32, device=dev) if "probs" in want else None
-        mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if "mask" in want else None
+        self._last_engine = eng   # (a caller that captures this call in a CUDA graph keeps the reference: the graph replays into eng's buffers)
+        shp = (B, H, W) if self.out_channels == 1 else (B, self.out_channels, H, W)
+        logits = torch.empty(shp, dtype=torch.float32, device=dev) if "logits" in want else None
+        probs = torch.empty(shp, dtype=torch.float32, device=dev) if "probs" in want else None
+        mask = torch.empty(shp, dtype=torch.uint8, device=dev) if "mask" in want else None
         st = torch.cuda.current_stream().cuda_stream
         for b0 in range(0, B, eng.cap):
             n = min(eng.cap, B - b0)
