@@ -19,10 +19,10 @@ import sys
 import threading
 import time
 
-# one process per GPU: pin the visible device before CUDA initialises (the C-ABI library carries its own runtime)
-# (the NVLink gradient exchange maps the peers' buffers, so every GPU has to stay visible: no pinning there)
-PINNED = ("LOCAL_RANK" in os.environ and os.environ.get("UB_BENCH_PIN", "1") == "1"
-          and ("train" not in sys.argv or "nccl" in sys.argv))
+# One process per GPU, every GPU visible to every rank: the library keeps its state per device and the NVLink / NVSwitch
+# gradient exchange of the training step maps the peers' buffers, so nothing is pinned by default. UB_BENCH_PIN=1 restricts
+# each rank to its own device before CUDA initialises (the training step then falls back to NCCL).
+PINNED = "LOCAL_RANK" in os.environ and os.environ.get("UB_BENCH_PIN", "0") == "1"
 if PINNED:
     _vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     _ids = _vis.split(",") if _vis else None
@@ -66,9 +66,10 @@ def build_model_cpu(seed=0):
     return m.eval()
 
 
-def physical_gpu_index():
-    """Index nvidia-smi / NVML know this process's first visible GPU by (CUDA_VISIBLE_DEVICES may hold indices or UUIDs)."""
-    first = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0].strip()
+def physical_gpu_index(ordinal=0):
+    """Index nvidia-smi / NVML know this process's GPU `ordinal` by (CUDA_VISIBLE_DEVICES may hold indices or UUIDs)."""
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    first = vis[ordinal] if ordinal < len(vis) else str(ordinal)
     try:
         return int(first)
     except ValueError:
@@ -151,7 +152,7 @@ def cpu_reference_pipeline(model_cpu, frames_u8_nhwc, threshold=0.5):
     """The reference's CPU path (src/unet.py:24-72 around README.md:1460-1481), restated in oracle/."""
     import torch
     from oracle import unet_oracle as O
-    pre = [O.preprocess_oracle(f, (224, 224))[0] for f in frames_u8_nhwc]   # resize (identity at 224) + batch dim
+    pre = [O.preprocess_oracle(f, (224, 224), swap_rb=True)[0] for f in frames_u8_nhwc]   # BGR->RGB + resize (identity at 224) + batch dim
     import numpy as np
     x = torch.from_numpy(O.normalize_oracle(np.concatenate(pre, 0)))
     with torch.no_grad():
@@ -215,6 +216,34 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
     x, y = x_host.to(dev), y_host.to(dev)
     step = U.FusedTrainStep(net, exchange=exchange)                     # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
     box = {}
+    check = None
+    if world > 1:
+        # proof that the exchange ran and is right, taken on the first (eager) step: the gradient sum exactly as the exchange
+        # kernel forms it (NVLink peer loads / NVSwitch multimem.ld_reduce / the bucketed NCCL all-reduce) against one plain
+        # all-reduce of copies of the local gradients, and the parameters of all replicas against each other afterwards
+        import torch.distributed as dist
+        step.step(x, y)
+        torch.cuda.synchronize()
+        if step.nvlink is not None and step.nvlink.mode != "push":
+            ref = step.grads.clone()
+            dist.all_reduce(ref)
+            num = torch.zeros(1, device=dev)
+            for a, b, t in step.nvlink.reduced_parts():
+                num = torch.maximum(num, (t - ref[a:b]).abs().max().reshape(1))
+            dist.all_reduce(num, op=dist.ReduceOp.MAX)
+            check = float(num.item()) / float(ref.abs().max().item())
+        elif step.nvlink is None:
+            # NCCL buckets reduce in place: compare the bucketed result with an all-reduce of a second, un-bucketed backward
+            # is not possible without re-running; report the spread of the reduced buffer across ranks instead (must be 0)
+            lo, hi = step.grads.clone(), step.grads.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            check = float((hi - lo).abs().max().item()) / float(hi.abs().max().item())
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        pl, ph = flat.clone(), flat.clone()
+        dist.all_reduce(pl, op=dist.ReduceOp.MIN)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        box["params_spread"] = float((ph - pl).abs().max().item())
 
     def run_dev():
         box["loss"] = step.step(x, y)
@@ -233,13 +262,20 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
            "batch_per_gpu": batch, "tflops_per_gpu": value / world * TRAIN_FLOPS_PER_SAMPLE / 1e12,
            "flops_per_sample": TRAIN_FLOPS_PER_SAMPLE, "loss_after": loss,
            "exchange": step.exchange,
+           "exchange_check": check,
+           "exchange_check_note": None if world == 1 else (
+               "step 1: max |sum formed by the exchange kernel - all_reduce(local gradients)| / max |gradient|, max over ranks"
+               if step.nvlink is not None else "step 1: spread of the bucket-wise all-reduced gradient across ranks / max |gradient|"),
+           "params_spread_after_step1": box.get("params_spread"),
+           "buckets": None if world == 1 else [[int(s_), int(a), int(b)] for s_, a, b in (step.buckets or [])],
+           "overlap": "each bucket's exchange + AdamW runs on a side stream as soon as its backward stages have finished" if world > 1 else None,
            "collective": "none" if world == 1 else (
-               f"NCCL all-reduce(sum) of the flat fp32 gradient ({31037633 * 4 / 1e6:.0f} MB) per step" if step.exchange == "nccl" else
-               "none: ONE kernel sums the owned gradient shard over the peers' buffers (NVLink loads), applies AdamW (ZeRO-1 "
-               "sharded state) and stores the parameters to all replicas (NVLink stores); two device-side barriers per step"
+               f"NCCL all-reduce(sum) per gradient bucket ({31037633 * 4 / 1e6:.0f} MB per step in total) + AdamW on the bucket" if step.exchange == "nccl" else
+               "none: per gradient bucket ONE kernel sums its part over the peers' buffers (NVLink loads), applies AdamW (ZeRO-1 "
+               "sharded state) and stores the parameters to all replicas (NVLink stores); device-side barriers"
                if step.exchange == "nvlink" else
-               "none: ONE kernel on NVSwitch multicast addresses - multimem.ld_reduce sums the owned gradient shard inside the "
-               "switch, AdamW (ZeRO-1 sharded state), multimem.st broadcasts the parameters; two device-side barriers per step"
+               "none: per gradient bucket ONE kernel on NVSwitch multicast addresses - multimem.ld_reduce sums the gradients inside the "
+               "switch, AdamW (ZeRO-1 sharded state), multimem.st broadcasts the parameters; device-side barriers"
                if step.exchange == "nvlink_mc" else
                "none: NVLink P2P gradient atomics to the owner replica inside the backward kernels, sharded AdamW, parameter "
                "stores to all replicas; two device-side barriers per step"),
@@ -258,9 +294,15 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=150, help="timed steps (default: a timed region of about 2 s at N = 1)")
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="frames per GPU per step. Default: 256 at N = 1 (BASELINE.json configs[1]); 4096 / N at N > 1 "
+                         "(configs[2]: batch 4096 sharded across the GPUs, strong scaling)")
+    ap.add_argument("--src-hw", nargs=2, type=int, default=None, metavar=("HS", "WS"),
+                    help="source frame size when it differs from the network input (480 640 = camera frames, a real resize in "
+                         "the fused preprocess); by default the headline uses frames of the network size and the 480x640 case "
+                         "is reported as the extra key e2e_src480x640")
     ap.add_argument("--chunk", type=int, default=256, help="frames per pass through the plan (256 = the whole batch in one pass)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -300,11 +342,13 @@ def main():
 
     model = build_model_cpu().to(dev)
     model.b200_chunk = args.chunk
-    B = args.batch
+    strong = args.batch is None and world > 1 and args.mode == "infer"
+    B = args.batch if args.batch is not None else (4096 // world if world > 1 else 256)
     H, W = args.hw
+    Hs, Ws = args.src_hw if args.src_hw else (H, W)
     flops_per_frame = FLOPS_PER_FRAME * (H * W) / (224 * 224)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    frames_host = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory()
+    frames_host = torch.randint(0, 256, (B, Hs, Ws, 3), dtype=torch.uint8, generator=g).pin_memory()
     frames_dev = frames_host.to(dev)
     mask_host = torch.empty(B, H, W, dtype=torch.uint8).pin_memory()
 
@@ -328,7 +372,7 @@ def main():
 
     if args.mode == "train":
         peaks = load_peaks()
-        sampler = ClockSampler(index=physical_gpu_index() if rank == 0 else 0)
+        sampler = ClockSampler(index=physical_gpu_index(0 if PINNED else torch.cuda.current_device()) if rank == 0 else 0)
         if rank == 0:
             sampler.start()
         tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True,
@@ -356,14 +400,14 @@ def main():
         return
 
     def step_device():
-        model.predict_mask(frames_dev, threshold=0.5, size=(H, W), want=("mask",))
+        model.predict_mask(frames_dev, threshold=0.5, swap_rb=True, size=(H, W), want=("mask",))
 
     def step_host():
-        model.infer_host(frames_host, threshold=0.5, size=(H, W), mask_out=mask_host)
+        model.infer_host(frames_host, threshold=0.5, swap_rb=True, size=(H, W), mask_out=mask_host)
 
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(index=physical_gpu_index() if rank == 0 else 0)
+    sampler = ClockSampler(index=physical_gpu_index(0 if PINNED else torch.cuda.current_device()) if rank == 0 else 0)
     if rank == 0:
         sampler.start()
     l0 = model.gpu_launches
@@ -377,9 +421,33 @@ def main():
     ms_host = timed(step_host, args.steps)
     e2e_value = world * B * args.steps / (ms_host / 1e3)
 
-    # roofline of the dominant kernel family (tcgen05 implicit-GEMM convs), from per-kernel CUDA events
+    # second end-to-end figure: 480x640 camera frames (src/unet_ros_node.py publishes 640x480 bgr8, README.md:3763-3765), i.e.
+    # a REAL bilinear resize in the fused preprocess and 6.1x the bytes over PCIe; the headline's source frames already have
+    # the network size (configs[1] names 224x224 frames), so its resize is the identity
+    e2e_cam = None
+    if (Hs, Ws) == (H, W) == (224, 224):
+        cam_host = torch.randint(0, 256, (B, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory()
+
+        def step_cam():
+            model.infer_host(cam_host, threshold=0.5, swap_rb=True, size=(H, W), mask_out=mask_host)
+
+        for _ in range(2):
+            step_cam()
+        ms_cam = timed(step_cam, args.steps)
+        e2e_cam = {"value": world * B * args.steps / (ms_cam / 1e3), "unit": UNIT, "ms_per_step": ms_cam / args.steps,
+                   "h2d_bytes_per_step": B * 480 * 640 * 3, "d2h_bytes_per_step": B * H * W,
+                   "source": "uint8 BGR 480x640 frames in pinned host memory -> cv2-exact bilinear resize to 224x224 + BGR->RGB + "
+                             "normalise fused in the preprocess kernel"}
+        del cam_host
+
+    # ---- roofline ---------------------------------------------------------------------------------------------------------
+    # Per-kernel CUDA events over one chunk-sized pass give every kernel's SHARE of the pass; the dominant family's in-step
+    # time is that share x the driver-style timed ms_per_step (same clocks, same power state as `value`), and its fraction is
+    # taken against the SUSTAINED bf16 peak. The per-kernel event times themselves come from short passes at boost clocks:
+    # they are reported separately against the BURST peak (a kernel timed alone).
     peaks = load_peaks()
-    x4 = torch.empty(min(args.chunk, B), H, W, 4, dtype=torch.bfloat16, device=dev).normal_()
+    nb = min(args.chunk, B)
+    x4 = torch.empty(nb, H, W, 4, dtype=torch.bfloat16, device=dev).normal_()
     model.profile_layers(x4)
     rows = None
     for _ in range(3):
@@ -387,17 +455,37 @@ def main():
         if rows is None:
             rows = r
         else:
-            for a, b in zip(rows, r):
-                a["ms"] = min(a["ms"], b["ms"])
-    all_ms = sum(r["ms"] for r in rows)
+            for a_, b_ in zip(rows, r):
+                a_["ms"] = min(a_["ms"], b_["ms"])
+
+    def time_kernel(fn, reps=5):
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    import unet_lane_detection_b200 as U
+    pre_ms = time_kernel(lambda: U.preprocess_u8(frames_dev[:nb], size=(H, W)))
+    pre_bytes = nb * (3 * Hs * Ws + H * W * 8)
+    all_ms = sum(r["ms"] for r in rows) + pre_ms
+    passes_per_step = B / nb
 
     def fam(sel):
         rs = [r for r in rows if sel(r)]
         fl, ms_ = sum(r["flops"] for r in rs), sum(r["ms"] for r in rs)
-        return {"launches": len(rs), "tflops": fl / (ms_ / 1e3) / 1e12 if ms_ > 0 else 0.0, "share_of_step": ms_ / all_ms,
-                "flops": fl, "ms": ms_}
+        share = ms_ / all_ms
+        in_step_ms = share * (ms / args.steps) / passes_per_step     # this family's time inside one pass of the timed region
+        return {"launches": len(rs), "share_of_step": share, "flops": fl, "ms_burst": ms_,
+                "tflops_burst": fl / (ms_ / 1e3) / 1e12 if ms_ > 0 else 0.0, "frac_of_burst_peak": fl / (ms_ / 1e3) / 1e12 / peaks["bf16_burst"] if ms_ > 0 else 0.0,
+                "ms_in_step": in_step_ms, "tflops_in_step": fl / (in_step_ms / 1e3) / 1e12 if in_step_ms > 0 else 0.0,
+                "frac_of_sustained_peak": fl / (in_step_ms / 1e3) / 1e12 / peaks["bf16_sustained"] if in_step_ms > 0 else 0.0}
 
-    # dominant kernel = conv_umma2_kernel<256>, the CTA-pair implicit GEMM (over half of the step, see profiles/r1_ncu_launches_bench_v3.csv)
+    # dominant kernel = conv_umma2_kernel<256>, the CTA-pair implicit GEMM (over half of the step, see profiles/)
     dom = fam(lambda r: r["kind"] in ("conv3x3", "convT2x2") and r["block_n"] == 256 and not r.get("halo"))
     halo64 = fam(lambda r: r.get("halo") and r["block_n"] == 64)
     halo128 = fam(lambda r: r.get("halo") and r["block_n"] == 128)
@@ -405,43 +493,69 @@ def main():
     # DRAM bytes of the dominant kernel family from the committed ncu capture (bench.py cannot run under ncu itself):
     # sum over its launches of one pass, i.e. the same unit as flops_per_pass; only valid for the captured geometry
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if os.path.exists(tpath) and (H, W) == (224, 224):
-        with open(tpath) as f:
-            tj = json.load(f)
-        fam_t = tj["families"].get("conv_umma2_kernel<256>")
-        if fam_t and fam_t["launches"] == dom["launches"] and tj.get("chunk") == int(x4.shape[0]):
-            traffic = fam_t["dram_read_bytes"] + fam_t["dram_write_bytes"]
-            traffic_src = "profiles/r1_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
-    roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": dom["tflops"] / peaks["bf16_sustained"], "traffic": traffic, "traffic_unit": "bytes per pass", "traffic_source": traffic_src,
+    for tname in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and (H, W) == (224, 224):
+            with open(tpath) as f:
+                tj = json.load(f)
+            fam_t = tj["families"].get("conv_umma2_kernel<256>")
+            if fam_t and fam_t["launches"] == dom["launches"] and tj.get("chunk") == nb:
+                traffic = fam_t["dram_read_bytes"] + fam_t["dram_write_bytes"]
+                traffic_src = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
+                break
+
+    # bandwidth-bound kernels: algorithmic bytes / CUDA-event time against the measured copy bandwidth
+    def hbm_row(name, bytes_, ms_, note):
+        gbs = bytes_ / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": name, "bytes": bytes_, "ms": ms_, "gbs": gbs, "frac": gbs / peaks["hbm_gbs"], "note": note}
+
+    hbm = [hbm_row("preprocess_u8_kernel", pre_bytes, pre_ms,
+                   f"{nb} frames: reads 3*{Hs}*{Ws} B uint8, writes {H}*{W}*8 B NHWC4 bf16 per frame "
+                   f"(algorithmic 3-channel output would be {H * W * 6} B)")]
+    for r in rows:
+        if r["kind"] == "stem":
+            hbm.append(hbm_row("stem_umma_kernel", nb * r["H"] * r["W"] * (8 + r["Cout"] * 2), r["ms"], "reads NHWC4 input, writes 64-channel bf16 output"))
+        if r["kind"] == "convT2x2" and r["H"] >= H // 4:
+            hbm.append(hbm_row(f"conv_umma2_kernel<256> ConvT {r['H']}x{r['W']} {r['Cin']}->{r['Cout']}",
+                               nb * r["H"] * r["W"] * (r["Cin"] * 2 + 4 * r["Cout"] * 2), r["ms"],
+                               "reads the low-resolution tensor, writes the 2x up-sampled one (4 strided quad views)"))
+    roofline = {"bound": "tensor", "achieved": dom["tflops_in_step"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": dom["frac_of_sustained_peak"], "traffic": traffic, "traffic_unit": "bytes per pass", "traffic_source": traffic_src,
                 "kernel": f"conv_umma2_kernel<256> (cta_group::2; {dom['launches']} launches per pass: 3x3 convs with Cout>=256 + 4 ConvT)",
-                "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass": dom["ms"],
-                "timing": f"CUDA events around every kernel of one {int(x4.shape[0])}-frame pass on the launching stream, min of 3",
-                "traffic_note": "reads equal the layers' input bytes exactly (no re-reads; e.g. enc0.conv1 reads 822.5 MB = 128x224x224x64 bf16); "
-                                "ncu --set full captures in profiles/r1_ncu_full_*.txt",
+                "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                "method": "achieved = the family's algorithmic FLOPs per pass / (its share of a pass x the timed ms_per_step / passes per step); "
+                          "share from CUDA events around every kernel of one pass on the launching stream (min of 3)",
+                "burst": {"achieved": dom["tflops_burst"], "peak": peaks["bf16_burst"], "frac": dom["frac_of_burst_peak"],
+                          "method": "the same FLOPs / the summed per-kernel CUDA-event times of a short pass (boost clocks) against bf16_tflops (burst)"},
+                "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass_in_step": dom["ms_in_step"],
+                "ms_per_pass_burst": dom["ms_burst"], "frames_per_pass": nb,
                 "other_kernels": {"conv_halo2_kernel<64>": halo64, "conv_halo2_kernel<128>": halo128, "all_tensor_core_convs": allconv},
+                "hbm": hbm, "hbm_peak_gbs": peaks["hbm_gbs"],
                 "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
         with open(args.layers_out, "w") as f:
-            json.dump({"chunk": int(x4.shape[0]), "rows": rows, "peaks": peaks}, f, indent=1)
+            json.dump({"chunk": int(x4.shape[0]), "rows": rows, "peaks": peaks, "preprocess_ms": pre_ms}, f, indent=1)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": f"U-Net {H}x{W} bf16 inference, features {FEATURES}, batch {B}/GPU, fused preprocess + mask threshold "
-                               + ("(BASELINE.json configs[1])" if (H, W) == (224, 224) else "(BASELINE.json configs[4] geometry)"),
-                   "batch_per_gpu": B, "chunk": args.chunk,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"U-Net {H}x{W} bf16 inference, features {FEATURES}, "
+                               + (f"batch {B * world} sharded across {world} GPUs ({B}/GPU), " if strong else f"batch {B}/GPU, ")
+                               + f"uint8 {Hs}x{Ws} source frames, fused preprocess + mask threshold "
+                               + (("(BASELINE.json configs[2])" if strong else "(BASELINE.json configs[1])") if (H, W) == (224, 224)
+                                  else "(BASELINE.json configs[4] geometry)"),
+                   "batch_per_gpu": B, "global_batch": B * world, "chunk": args.chunk, "source_hw": [Hs, Ws],
                    "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2_policy": f"inputs+activations >> L2: {B * H * W * 3 / 1e6:.0f} MB frames and "
+                   "l2_policy": f"inputs+activations >> L2: {B * Hs * Ws * 3 / 1e6:.0f} MB frames and "
                                 f"{min(args.chunk, B) * 64.1 * H * W / (224 * 224):.0f} MB activations per chunk vs 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 3, "d2h_bytes_per_step": B * H * W,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Hs * Ws * 3, "d2h_bytes_per_step": B * H * W,
                 "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host_stream (pinned host buffers, copies overlapped with compute)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    if e2e_cam is not None:
+        line["e2e_src480x640"] = e2e_cam
     if (H, W) != (224, 224):
         line["metric"] = f"unet{H}x{W}_inference_frames_per_sec"
         args.no_train = True

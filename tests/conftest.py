@@ -27,3 +27,22 @@ def _built_library():
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def record_parity(name, payload, fname="r2_parity.json"):
+    """Parity figures the tests measure (noise floors, per-tensor gradient errors) are written next to the other GPU-run
+    artefacts (gpurun_out/, merged back by gpurun) so they can be committed under profiles/."""
+    import json
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, fname)
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[name] = payload
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

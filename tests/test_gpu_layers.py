@@ -152,6 +152,18 @@ def test_preprocess_is_cv2_exact(U, hs, ws):
     assert y[..., 3].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("hs,ws,h,w,b", [(37, 53, 64, 96, 3), (480, 640, 100, 60, 2), (1080, 1920, 224, 224, 1), (224, 224, 448, 448, 1),
+                                         (200, 4001, 16, 16, 1), (17, 23, 8, 8, 5)])
+def test_preprocess_tile_kernel_ragged_shapes(U, hs, ws, h, w, b):
+    """The tile kernel's row staging (span / sparse modes, rows narrower than a 16-byte chunk, unaligned pitches, tiles that
+    overhang the image, very wide rows that force fewer rows per CTA) stays bit-equal to cv2's resize."""
+    rng = np.random.default_rng(hs * 7 + ws)
+    img = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    _, r = U.preprocess_u8(torch.from_numpy(img).cuda(), size=(h, w), swap_rb=False, return_resized=True)
+    want = np.stack([O.preprocess_oracle(im, (h, w))[0][0] for im in img])
+    assert np.array_equal(r.cpu().numpy(), want)
+
+
 def test_preprocess_golden_images(U, golden_dir):
     import os
     g = np.load(os.path.join(golden_dir, "preprocess.npz"))
