@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--hw", nargs=2, type=int, default=[224, 224], metavar=("H", "W"),
                     help="network input size; 480 640 = BASELINE.json configs[4] (camera resolution, use --batch 16 --chunk 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="infer mode: skip the fp32-class plan's throughput line")
     ap.add_argument("--layers-out", default=None, help="write the per-kernel profile table to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -471,7 +472,6 @@ def main():
 
     import unet_lane_detection_b200 as U
     pre_ms = time_kernel(lambda: U.preprocess_u8(frames_dev[:nb], size=(H, W)))
-    pre_bytes = nb * (3 * Hs * Ws + H * W * 8)
     all_ms = sum(r["ms"] for r in rows) + pre_ms
     passes_per_step = B / nb
 
@@ -504,20 +504,37 @@ def main():
                 traffic_src = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the family's launches of one pass)"
                 break
 
-    # bandwidth-bound kernels: algorithmic bytes / CUDA-event time against the measured copy bandwidth
-    def hbm_row(name, bytes_, ms_, note):
-        gbs = bytes_ / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
-        return {"kernel": name, "bytes": bytes_, "ms": ms_, "gbs": gbs, "frac": gbs / peaks["hbm_gbs"], "note": note}
+    # bandwidth-bound kernels: algorithmic bytes / CUDA-event time against the measured copy bandwidth (MEASURED_PEAKS hbm_gbs:
+    # a copy, half reads half writes) and, for the write-dominated ones, their write rate against this GPU's pure-write
+    # ceiling measured here (a 2 GiB cudaMemset, best of 3: ~3.9 TB/s on B200 - a kernel that only writes cannot reach the copy figure)
+    fill_buf = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+    fill_ms = time_kernel(lambda: fill_buf.zero_(), reps=3)
+    write_peak = fill_buf.numel() * 2 / (fill_ms / 1e3) / 1e9
+    del fill_buf
 
-    hbm = [hbm_row("preprocess_u8_kernel", pre_bytes, pre_ms,
+    def hbm_row(name, rd, wr, ms_, note):
+        gbs = (rd + wr) / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
+        wgbs = wr / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": name, "bytes": rd + wr, "read_bytes": rd, "write_bytes": wr, "ms": ms_, "gbs": gbs, "frac": gbs / peaks["hbm_gbs"],
+                "write_gbs": wgbs, "frac_of_write_ceiling": wgbs / write_peak, "note": note}
+
+    hbm = [hbm_row("preprocess_copy_u8_kernel" if (Hs, Ws) == (H, W) else "preprocess_u8_kernel", nb * 3 * Hs * Ws, nb * H * W * 8, pre_ms,
                    f"{nb} frames: reads 3*{Hs}*{Ws} B uint8, writes {H}*{W}*8 B NHWC4 bf16 per frame "
                    f"(algorithmic 3-channel output would be {H * W * 6} B)")]
+    if (Hs, Ws) == (H, W) == (224, 224):
+        ncam = min(64, nb)
+        cam_dev = torch.randint(0, 256, (ncam, 480, 640, 3), dtype=torch.uint8, device=dev)
+        cam_ms = time_kernel(lambda: U.preprocess_u8(cam_dev, size=(H, W), swap_rb=True))
+        hbm.append(hbm_row("preprocess_u8_kernel (480x640 -> 224x224, cv2-exact bilinear)", ncam * 3 * 480 * 640, ncam * H * W * 8, cam_ms,
+                           f"{ncam} camera frames: the real-resize case of e2e_src480x640"))
+        del cam_dev
     for r in rows:
         if r["kind"] == "stem":
-            hbm.append(hbm_row("stem_umma_kernel", nb * r["H"] * r["W"] * (8 + r["Cout"] * 2), r["ms"], "reads NHWC4 input, writes 64-channel bf16 output"))
+            hbm.append(hbm_row("stem_umma_kernel", nb * r["H"] * r["W"] * 8, nb * r["H"] * r["W"] * r["Cout"] * 2, r["ms"],
+                               "reads NHWC4 input, writes 64-channel bf16 output"))
         if r["kind"] == "convT2x2" and r["H"] >= H // 4:
             hbm.append(hbm_row(f"conv_umma2_kernel<256> ConvT {r['H']}x{r['W']} {r['Cin']}->{r['Cout']}",
-                               nb * r["H"] * r["W"] * (r["Cin"] * 2 + 4 * r["Cout"] * 2), r["ms"],
+                               nb * r["H"] * r["W"] * r["Cin"] * 2, nb * r["H"] * r["W"] * 4 * r["Cout"] * 2, r["ms"],
                                "reads the low-resolution tensor, writes the 2x up-sampled one (4 strided quad views)"))
     roofline = {"bound": "tensor", "achieved": dom["tflops_in_step"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": dom["frac_of_sustained_peak"], "traffic": traffic, "traffic_unit": "bytes per pass", "traffic_source": traffic_src,
@@ -530,7 +547,8 @@ def main():
                 "share_of_step": dom["share_of_step"], "flops_per_pass": dom["flops"], "ms_per_pass_in_step": dom["ms_in_step"],
                 "ms_per_pass_burst": dom["ms_burst"], "frames_per_pass": nb,
                 "other_kernels": {"conv_halo2_kernel<64>": halo64, "conv_halo2_kernel<128>": halo128, "all_tensor_core_convs": allconv},
-                "hbm": hbm, "hbm_peak_gbs": peaks["hbm_gbs"],
+                "hbm": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_write_ceiling_gbs": write_peak,
+                "hbm_write_ceiling_how": "2 GiB cudaMemset on this GPU inside this run, best of 3, CUDA events",
                 "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
@@ -559,6 +577,28 @@ def main():
     if (H, W) != (224, 224):
         line["metric"] = f"unet{H}x{W}_inference_frames_per_sec"
         args.no_train = True
+    elif not args.no_fp32:
+        # the fp32-class plan (north_star's second parity gate, logits within 1e-4): same pipeline entry, UB_PRECISION_FP32 plan
+        nf = min(64, B)
+        model.b200_precision, model.b200_chunk = "fp32", nf
+        f32_frames = frames_dev[:nf].contiguous()
+
+        def step_fp32():
+            model.predict_mask(f32_frames, threshold=0.5, swap_rb=True, size=(H, W), want=("mask",))
+
+        for _ in range(3):
+            step_fp32()
+        n32 = max(5, args.steps // 2)
+        ms32 = timed(step_fp32, n32)
+        fps32 = world * nf * n32 / (ms32 / 1e3)
+        tensor_flops = 3.0 * (flops_per_frame - 2.0 * H * W * 64 * 27)       # three bf16 passes per product; the stem runs on the FP32 pipes
+        line["fp32_path"] = {"value": fps32, "unit": UNIT, "ms_per_step": ms32 / n32, "batch_per_gpu": nf,
+                             "parity_gate": "logits within 1e-4 of the fp32 reference (tests/test_gpu_unet.py)",
+                             "tensor_work_tflops_per_gpu": fps32 / world * tensor_flops / 1e12,
+                             "frac_of_sustained_bf16_peak": fps32 / world * tensor_flops / 1e12 / peaks["bf16_sustained"],
+                             "how": "UB_PRECISION_FP32 plan: split-bf16 (hi + lo) activations and weights, three tcgen05 K passes per product"}
+        model.b200_precision, model.b200_chunk = "bf16", args.chunk
+        del f32_frames
     if not args.no_train:
         del frames_dev
         model._engines.clear()

@@ -50,6 +50,18 @@ int unet_b200_device_ok(void);
  * deploys out_channels = 1, README.md:2165; with more the 1x1 head runs as its own kernel instead of inside the last conv). */
 int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
                           const int* features, int levels);
+/* The same with an explicit arithmetic class (plan_create = UB_PRECISION_BF16):
+ *   UB_PRECISION_BF16  bf16 operands, fp32 accumulation: logits within 2e-2 of the fp32 reference (BASELINE.json north_star);
+ *   UB_PRECISION_FP32  "fp32-class": every activation and BN-folded weight is carried as two bf16 numbers hi + lo (16 mantissa
+ *                      bits) and a product is hi*hi + lo*hi + hi*lo on the same tcgen05 kernel - logits within 1e-4 (north_star's
+ *                      second gate), about 3x the tensor work. Needs features % 64 == 0 and out_channels == 1. The network
+ *                      input of such a plan is FP32 NHWC4 (unet_b200_nchw_to_nhwc4_f32 / unet_b200_preprocess_u8_f32), and
+ *                      the host-buffer entry points (infer_u8_host*) pick the fp32 preprocess themselves. */
+#define UB_PRECISION_BF16 0
+#define UB_PRECISION_FP32 1
+int unet_b200_plan_create_ex(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
+                             const int* features, int levels, int precision);
+int unet_b200_plan_precision(const unet_b200_plan* p);
 void unet_b200_plan_destroy(unet_b200_plan* p);
 /* Bytes of device memory the plan needs for activations (workspace) and packed weights. Layer outputs share the workspace
  * by liveness (an output's space is reused after its last reader): the default network needs 19.3 MB per frame of batch
@@ -75,7 +87,8 @@ int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w_dev, con
 int unet_b200_plan_set_head(unet_b200_plan* p, const float* w_dev, const float* bias_dev, void* stream);
 
 /* ---- forward (UNet.forward, README.md:1460-1481, eval mode) -------------------------------------- *
- * x_nhwc4_dev: bf16 [batch][H][W][4] (channels >= in_channels are ignored/zero).
+ * x_nhwc4_dev: bf16 [batch][H][W][4] (channels >= in_channels are ignored/zero); fp32 [batch][H][W][4] for a
+ * UB_PRECISION_FP32 plan.
  * Any of the three outputs may be NULL (OC = out_channels):
  *   logits_dev fp32 [batch][OC][H][W]   (NCHW, as the reference module returns them)
  *   probs_dev  fp32 [batch][OC][H][W]   sigmoid(logits)
@@ -112,8 +125,9 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  * All paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
 int unet_b200_set_option(const char* name, int value);
 
-/* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary). */
+/* NCHW fp32 [batch][C<=4][H][W] -> NHWC4 bf16 (the nn.Module boundary); _f32: -> NHWC4 fp32 (fp32-class plans). */
 int unet_b200_nchw_to_nhwc4(const float* x_dev, int batch, int C, int H, int W, void* y_nhwc4_dev, void* stream);
+int unet_b200_nchw_to_nhwc4_f32(const float* x_dev, int batch, int C, int H, int W, float* y_nhwc4_dev, void* stream);
 
 /* ---- preprocess (src/unet.py:24-42 + in-graph normalisation README.md:3110-3111) ---------------- *
  * src_dev: uint8 [batch][Hs][Ws][3] with the given row pitch / frame stride in bytes.
@@ -123,6 +137,10 @@ int unet_b200_nchw_to_nhwc4(const float* x_dev, int batch, int C, int H, int W, 
 int unet_b200_preprocess_u8(const uint8_t* src_dev, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride,
                             int H, int W, int swap_rb, const float* mean3, const float* std3, void* y_nhwc4_dev,
                             uint8_t* resized_u8_dev, void* stream);
+/* Same, written as NHWC4 fp32 (no bf16 rounding of the normalised image): the input of a UB_PRECISION_FP32 plan. */
+int unet_b200_preprocess_u8_f32(const uint8_t* src_dev, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride,
+                                int H, int W, int swap_rb, const float* mean3, const float* std3, float* y_nhwc4_dev,
+                                uint8_t* resized_u8_dev, void* stream);
 
 /* ---- IPM front end of the ROS node fused into the preprocess (src/unet_ros_node.py:297-313) --------------------- *
  * cv2.warpPerspective(bgr, M, (Ww, Hw)) -> BGR2RGB (swap_rb) -> cv2.resize to HxW -> normalise -> NHWC4 bf16, bit-exact

@@ -153,7 +153,7 @@ def test_preprocess_is_cv2_exact(U, hs, ws):
 
 
 @pytest.mark.parametrize("hs,ws,h,w,b", [(37, 53, 64, 96, 3), (480, 640, 100, 60, 2), (1080, 1920, 224, 224, 1), (224, 224, 448, 448, 1),
-                                         (200, 4001, 16, 16, 1), (17, 23, 8, 8, 5)])
+                                         (200, 4001, 16, 16, 1), (17, 23, 8, 8, 5), (30, 42, 30, 42, 2), (32, 48, 32, 48, 3)])
 def test_preprocess_tile_kernel_ragged_shapes(U, hs, ws, h, w, b):
     """The tile kernel's row staging (span / sparse modes, rows narrower than a 16-byte chunk, unaligned pitches, tiles that
     overhang the image, very wide rows that force fewer rows per CTA) stays bit-equal to cv2's resize."""
@@ -197,9 +197,33 @@ def test_conv3x3_halo_and_per_tap_kernels(U, halo, B, H, W, C0, C1, Cout, pool):
         _set(U, "halo", 1)
 
 
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("cin,B,H,W", [(3, 2, 224, 224), (3, 1, 32, 48), (1, 3, 16, 16), (4, 1, 24, 40), (3, 1, 480, 640), (3, 5, 28, 36)])
-def test_stem_conv_tensor_core(U, cin, B, H, W):
-    """Tensor-core stem (in-kernel im2col, K = 36 padded to 48) vs the oracle; partial tiles when H % 16 or W % 8 != 0."""
+def test_stem_conv_tensor_core(U, cin, B, H, W, wide):
+    """Tensor-core stem (in-kernel im2col, K = 36 padded to 48) vs the oracle; partial tiles when H % 16 or W % 8 != 0.
+    wide: the 4 x 32 tile form (one contiguous 4 KB row segment per TMA store) - same MMAs, bit-identical to the 16 x 8 form."""
+    _set(U, "stem_wide", wide)
+    try:
+        _stem_case(U, cin, B, H, W)
+    finally:
+        _set(U, "stem_wide", 0)
+
+
+def test_stem_tile_forms_are_bit_identical(U):
+    x = U.nchw_to_nhwc4(bf(torch.randn(3, 3, 52, 72, generator=torch.Generator().manual_seed(8))).cuda())
+    w = torch.randn(64, 3, 3, 3, generator=torch.Generator().manual_seed(9)) / 5
+    wp, bias = U.pack_stem_tc(w.cuda(), None)
+    outs = []
+    for wide in (0, 1):
+        _set(U, "stem_wide", wide)
+        try:
+            outs.append(U.stem_conv_tc(x, wp, bias))
+        finally:
+            _set(U, "stem_wide", 0)
+    assert torch.equal(outs[0], outs[1])
+
+
+def _stem_case(U, cin, B, H, W):
     g = torch.Generator().manual_seed(5)
     x = bf(torch.randn(B, cin, H, W, generator=g))
     w = torch.randn(64, cin, 3, 3, generator=g) / 5

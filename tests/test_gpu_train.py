@@ -293,13 +293,14 @@ def test_train_step_config4_geometry_224_batch4(U):
     record_parity("config4_224x224_batch4_default_widths", {
         "loss": loss.item(), "loss_oracle_fp32": losses_ref[0].item(), "max_abs_logit_err": logit_err, "logit_abs_max": out_ref.abs().max().item(),
         "worst_err_over_floor": {"tensor": worst[0], "ratio": worst[1], "err": worst[2], "floor": worst[3]},
-        "gate": "per tensor: rel L2 err <= 1.15 * floor + 0.01, cosine >= emulated cosine - 0.03, "
-                "rel L2 vs the emulated oracle <= 0.75 * floor + 0.02; output.* <= 5e-3",
+        "gate": "per tensor: rel L2 err <= 1.1 * floor + 0.01, cosine >= emulated cosine - 0.01, "
+                "rel L2 vs the emulated oracle <= 0.7 * floor + 0.01; output.* <= 5e-3",
         "tensors": table}, fname="r2_train_parity.json")
     for n, row in table.items():
-        assert row["rel_l2_err"] <= 1.15 * row["rel_l2_floor_bf16_emulated"] + 0.01, (n, row)
-        assert row["cosine"] >= row["cosine_bf16_emulated"] - 0.03, (n, row)
-        assert row["rel_l2_vs_emulated"] <= 0.75 * row["rel_l2_floor_bf16_emulated"] + 0.02, (n, row)
+        # measured (profiles/r2_train_parity.json): err / floor between 0.97 and 1.09 on every tensor, vs-emulated 0.53-0.62 x floor
+        assert row["rel_l2_err"] <= 1.1 * row["rel_l2_floor_bf16_emulated"] + 0.01, (n, row)
+        assert row["cosine"] >= row["cosine_bf16_emulated"] - 0.01, (n, row)
+        assert row["rel_l2_vs_emulated"] <= 0.7 * row["rel_l2_floor_bf16_emulated"] + 0.01, (n, row)
     assert table["output.weight"]["rel_l2_err"] <= 5e-3 and table["output.bias"]["rel_l2_err"] <= 5e-3
     # the fused step (loss + backward kernels) produces the same gradients as the autograd path just checked
     _, net2 = make_train_pair(U, [64, 128, 256, 512])

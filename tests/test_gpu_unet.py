@@ -389,6 +389,88 @@ def test_fp32_path_logits_within_1e4(U, gain):
     assert (yb - y32).abs().max().item() > err   # the bf16 path is the coarser one (sanity: the switch does something)
 
 
+def _torch_model_container_run(path, input_datas):
+    """The reference's Torch_model_container (src/py_utils/pytorch_executor.py:14-61), its load and run() steps in order:
+    torch.jit.load -> eval -> torch.tensor(ndarray) (CPU tensors) -> model(*inputs) -> dequantize -> .cpu().detach().numpy()."""
+    pt_model = torch.jit.load(path)
+    pt_model.eval()
+    ins = [torch.tensor(d) for d in input_datas]
+    ins = [v.float() if v.dtype == torch.float64 else v for v in ins]
+    result = pt_model(*ins)
+    result = list(result) if isinstance(result, tuple) else result
+    result = result if isinstance(result, list) else [result]
+    return [torch.dequantize(r).cpu().detach().numpy() for r in result]
+
+
+def test_torchscript_trace_and_torch_model_container(U, tmp_path):
+    """SURVEY.md 8(f) rank 3: torch.jit.trace(model) serialises (the graph holds one unet_b200::infer operator and the model
+    state as a constant) and the reference's Torch_model_container flow runs the file - float NCHW module and the uint8 NHWC
+    lane graph (normalisation + sigmoid inside, like the deployed RKNN blob)."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(31))
+    with torch.no_grad():
+        eager = net(x.cuda()).cpu()
+    traced = torch.jit.trace(net, x.cuda(), check_trace=False)
+    assert "unet_b200::infer" in str(traced.graph)
+    assert torch.equal(traced(x.cuda()).cpu(), eager)
+    p1 = str(tmp_path / "unet_float.pt")
+    torch.jit.save(traced, p1)
+    out = _torch_model_container_run(p1, [x.numpy()])                  # CPU ndarray in, as the container feeds it
+    assert len(out) == 1 and out[0].shape == (2, 1, 224, 224)
+    assert np.array_equal(out[0], eager.numpy())
+    other = _torch_model_container_run(p1, [x[:1, :, :64, :96].numpy().copy()])   # a trace is not tied to the example's shape
+    with torch.no_grad():
+        assert np.array_equal(other[0], net(x[:1, :, :64, :96].contiguous().cuda()).cpu().numpy())
+    # the lane node's contract: uint8 NHWC RGB (1,224,224,3) -> probabilities (1,1,224,224)  (src/unet.py:24-72)
+    p2 = str(tmp_path / "lane_unet_b200.pt")
+    U.export_torchscript(net, p2, input_kind="uint8_nhwc", sigmoid=True)
+    frame = np.random.default_rng(2).integers(0, 256, (1, 224, 224, 3), dtype=np.uint8)
+    probs = _torch_model_container_run(p2, [frame])[0]
+    with torch.no_grad():
+        want = torch.sigmoid(ref(torch.from_numpy(O.normalize_oracle(frame)))).numpy()
+    assert probs.shape == (1, 1, 224, 224) and probs.dtype == np.float32
+    assert np.abs(probs - want).max() <= 2e-2
+    mask = O.postprocess_oracle([probs], (224, 224), 0.5)               # the reference post-process on the container's output
+    assert (mask == O.postprocess_oracle([want], (224, 224), 0.5)).mean() >= 0.999
+
+
+def test_fp32_plan_from_uint8_frames_and_executor(U, tmp_path):
+    """The fp32-class path is a plan of its own (UB_PRECISION_FP32): reachable from predict_mask / infer_host (fp32 preprocess,
+    the image is never rounded to bf16) and from the executor, where the per-frame call replays a captured CUDA graph."""
+    ref, net = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    net.b200_precision = "fp32"
+    rng = np.random.default_rng(17)
+    frames = rng.integers(0, 256, (3, 480, 640, 3), dtype=np.uint8)
+    logits, probs, mask = net.predict_mask(torch.from_numpy(frames).cuda(), swap_rb=True, want=("logits", "probs", "mask"))
+    pre = np.concatenate([O.preprocess_oracle(f, (224, 224), swap_rb=True)[0] for f in frames])
+    with torch.no_grad():
+        z = ref(torch.from_numpy(O.normalize_oracle(pre)))
+    err = (logits.cpu() - z[:, 0]).abs().max().item()
+    assert err <= LOGIT_TOL_FP32 * max(1.0, z.abs().max().item()), err
+    want = np.stack([O.postprocess_oracle([z[i:i + 1].numpy()], (224, 224), 0.5) for i in range(3)])
+    assert (mask.cpu().numpy() == want).mean() >= 0.9999
+    # host-buffer entry point picks the fp32 preprocess from the plan's precision
+    m_host = torch.empty(3, 224, 224, dtype=torch.uint8).pin_memory()
+    l_host = torch.empty(3, 224, 224, dtype=torch.float32).pin_memory()
+    net.infer_host(torch.from_numpy(frames).pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)
+    assert torch.equal(m_host, mask.cpu()) and torch.equal(l_host, logits.cpu())
+    record_parity("fp32_plan_480x640_sources_gain40", {"max_abs_logit_err": err, "logit_abs_max": z.abs().max().item(),
+                                                       "gate": "<= 1e-4 * max(1, |z|max)"})
+    # executor: graph replay of the fp32 plan (same frame twice -> identical output), probabilities within 1e-4
+    path = tmp_path / "m.pth"
+    torch.save(ref.state_dict(), path)
+    box = U.B200_model_container(str(path), precision="fp32")
+    rgb = np.ascontiguousarray(pre[:1])
+    a = box.run([rgb])[0]
+    b = box.run([rgb])[0]
+    assert np.array_equal(a, b)
+    with torch.no_grad():
+        want_p = torch.sigmoid(ref(torch.from_numpy(O.normalize_oracle(rgb)))).numpy()
+    assert np.abs(a - want_p).max() <= 1e-4
+    box.release()
+    net.b200_precision = "bf16"
+
+
 @pytest.mark.parametrize("feats,B,H,W", [([64, 128], 3, 64, 96), ([64, 128, 256], 1, 40, 56)])
 def test_fp32_path_other_topologies(U, feats, B, H, W):
     """fp32-class path on shallower networks, non-square inputs and odd batches (partial tiles, odd pixel-tile counts)."""

@@ -15,6 +15,7 @@ from .unet import UNet  # noqa: F401
 from .executor import B200_model_container, B200LaneInference, B200LanePipeline  # noqa: F401
 from .training import FusedTrainStep, bce_dice_loss  # noqa: F401
 from .loop import cosine_warm_restarts_lr, fit, train_one_epoch, validate, validation_metrics  # noqa: F401
+from .torchscript import LaneGraph, export_torchscript  # noqa: F401  (importing it registers the unet_b200::infer operator)
 
 __all__ = ["UNet", "B200_model_container", "B200LaneInference", "B200LanePipeline", "FusedTrainStep", "bce_dice_loss", "fit", "train_one_epoch",
-           "validate", "validation_metrics", "cosine_warm_restarts_lr"]
+           "validate", "validation_metrics", "cosine_warm_restarts_lr", "export_torchscript", "LaneGraph"]

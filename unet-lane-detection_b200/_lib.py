@@ -24,6 +24,8 @@ _SIGS = {
     "unet_b200_version": (i32, []),
     "unet_b200_device_ok": (i32, []),
     "unet_b200_plan_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
+    "unet_b200_plan_create_ex": (i32, [C.POINTER(vp), i32, i32, i32, i32, i32, C.POINTER(i32), i32, i32]),
+    "unet_b200_plan_precision": (i32, [vp]),
     "unet_b200_plan_destroy": (None, [vp]),
     "unet_b200_plan_workspace_bytes": (sz, [vp]),
     "unet_b200_plan_workspace_unshared_bytes": (sz, [vp]),
@@ -40,6 +42,8 @@ _SIGS = {
     "unet_b200_plan_layer_info": (i32, [vp, i32, C.POINTER(i32)]),
     "unet_b200_set_option": (i32, [C.c_char_p, i32]),
     "unet_b200_nchw_to_nhwc4": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_nchw_to_nhwc4_f32": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "unet_b200_preprocess_u8_f32": (i32, [vp, i32, i32, i32, sz, sz, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, vp]),
     "unet_b200_preprocess_u8": (i32, [vp, i32, i32, i32, sz, sz, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, vp]),
     "unet_b200_preprocess_warp_u8": (i32, [vp, i32, i32, i32, sz, sz, C.POINTER(C.c_double), i32, i32, i32, i32, i32,
                                            C.POINTER(f32), C.POINTER(f32), vp, vp, vp, vp]),

@@ -241,6 +241,20 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, int B, int C, 
   }
 }
 
+// fp32-class path: the same transform without the bf16 rounding (NCHW fp32 -> NHWC4 fp32).
+__global__ void nchw_to_nhwc4_f32_kernel(const float* __restrict__ x, int B, int C, int H, int W, float4* __restrict__ y) {
+  pdl_enter();
+  const size_t hw = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / hw, p = i - b * hw;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < C; ++k) c[k] = __ldg(x + (b * C + k) * hw + p);
+    y[i] = make_float4(c[0], c[1], c[2], c[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Preprocess (north_star (d)): uint8 HWC frames -> bilinear resize to HxW exactly as cv2.resize
 // INTER_LINEAR does on uint8 (11-bit fixed-point taps; src/unet.py:33) -> optional R<->B swap
@@ -255,9 +269,17 @@ struct PreArgs {
   int B, Hs, Ws, H, W;
   int swap_rb;
   float mean[3], inv_std[3];  // in output channel order
-  uint2* dst;          // [B,H,W] x (4 bf16)
+  uint2* dst;          // [B,H,W] x (4 bf16); null when dst_f32 is given
+  float4* dst_f32;     // fp32-class path: [B,H,W] x (4 fp32) instead - the normalised image without bf16 rounding
   uint8_t* dst_u8;     // optional [B,H,W,3] resized uint8 (pre-normalisation), for parity tests
 };
+__device__ __forceinline__ void pre_store(const PreArgs& a, size_t o, float f0, float f1, float f2) {
+  if (a.dst_f32 != nullptr) {
+    a.dst_f32[o] = make_float4(f0, f1, f2, 0.f);
+  } else {
+    a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+  }
+}
 
 // cv2 INTER_LINEAR (uint8) taps of one axis. Horizontal axis (clamp_weights): a tap outside the row is folded into its
 // neighbour (fx = 0). Vertical axis: cv2 keeps the weights and only clips the ROW INDICES (resize.cpp), so border rows
@@ -315,43 +337,19 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArg
   const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
   const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
 
-  if (threadIdx.x == 0) {
-    int lo = 1 << 30, hi = -1;
-    int sy0[PRE_ROWS], sy1[PRE_ROWS];
-    for (int r = 0; r < nrows; ++r) {
-      int b0, b1;
-      resize_coef(y0 + r, a.H, a.Hs, false, sy0[r], sy1[r], b0, b1);
-      if (area2) {
-        sy0[r] = 2 * (y0 + r);
-        sy1[r] = 2 * (y0 + r) + 1;
-      }
-      s_by[2 * r] = b0;
-      s_by[2 * r + 1] = b1;
-      lo = min(lo, min(sy0[r], sy1[r]));
-      hi = max(hi, max(sy0[r], sy1[r]));
+  __shared__ int s_sy[2 * PRE_ROWS];
+  if (threadIdx.x < nrows) {           // vertical taps of the tile's rows, one thread per row
+    const int r = threadIdx.x;
+    int y_0, y_1, b0, b1;
+    resize_coef(y0 + r, a.H, a.Hs, false, y_0, y_1, b0, b1);
+    if (area2) {
+      y_0 = 2 * (y0 + r);
+      y_1 = 2 * (y0 + r) + 1;
     }
-    int n;
-    if (hi - lo + 1 <= 2 * R) {       // span mode: slot i holds source row lo + i
-      n = hi - lo + 1;
-      for (int i = 0; i < n; ++i) s_src[i] = lo + i;
-      for (int r = 0; r < nrows; ++r) {
-        s_slot[2 * r] = sy0[r] - lo;
-        s_slot[2 * r + 1] = sy1[r] - lo;
-      }
-    } else {                          // sparse mode: two private slots per output row
-      n = 2 * nrows;
-      for (int r = 0; r < nrows; ++r) {
-        s_src[2 * r] = sy0[r];
-        s_src[2 * r + 1] = sy1[r];
-        s_slot[2 * r] = 2 * r;
-        s_slot[2 * r + 1] = 2 * r + 1;
-      }
-    }
-    for (int i = 0; i < n; ++i) {
-      const uintptr_t p = reinterpret_cast<uintptr_t>(frame + static_cast<size_t>(s_src[i]) * a.pitch);
-      s_off[i] = static_cast<int>(p & 15);   // the row is staged from its 16-byte aligned address; this is where it starts
-    }
-    s_nslots = n;
+    s_sy[2 * r] = y_0;
+    s_sy[2 * r + 1] = y_1;
+    s_by[2 * r] = b0;
+    s_by[2 * r + 1] = b1;
   }
   // horizontal taps: {3*sx0, 3*sx1, ax0, ax1} per output column
   for (int x = threadIdx.x; x < a.W; x += PRE_THREADS) {
@@ -362,6 +360,25 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArg
       sx1 = 2 * x + 1;
     }
     xtab[x] = make_int4(3 * sx0, 3 * sx1, ax0, ax1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * PRE_ROWS) {    // slot tables: every one of these threads derives the (tiny) min / max itself
+    int lo = 1 << 30, hi = -1;
+    for (int k = 0; k < 2 * nrows; ++k) {
+      lo = min(lo, s_sy[k]);
+      hi = max(hi, s_sy[k]);
+    }
+    const bool span = hi - lo + 1 <= 2 * R;   // span mode: slot i holds source row lo + i; sparse: two private slots per row
+    const int n = span ? hi - lo + 1 : 2 * nrows;
+    const int i = threadIdx.x;
+    if (i < 2 * nrows) s_slot[i] = span ? s_sy[i] - lo : i;
+    if (i < n) {
+      const int row = span ? lo + i : s_sy[i];
+      s_src[i] = row;
+      const uintptr_t p = reinterpret_cast<uintptr_t>(frame + static_cast<size_t>(row) * a.pitch);
+      s_off[i] = static_cast<int>(p & 15);   // the row is staged from its 16-byte aligned address; this is where it starts
+    }
+    if (i == 0) s_nslots = n;
   }
   __syncthreads();
   // stage the rows: 16-byte chunks from the aligned-down row address (never below the allocation: it is at least 16-byte
@@ -411,7 +428,71 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArg
     const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
     const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
     const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
-    a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
+    pre_store(a, o, f0, f1, f2);
+  }
+}
+
+// Same-size frames (Hs == H, Ws == W): cv2.resize returns a copy, so the preprocess is channel swap + normalise only.
+// One thread per 4 pixels: three 32-bit loads (12 source bytes), two 16-byte stores (four NHWC4 bf16 pixels); a warp reads
+// 384 and writes 1024 contiguous bytes; two groups per trip so that six loads are in flight per thread.
+// Needs rows / frames that start on 4-byte boundaries and W % 4 == 0 (host checks).
+__device__ __forceinline__ void pre_copy_group(const PreArgs& a, size_t o, uint32_t w0, uint32_t w1, uint32_t w2) {
+  uint32_t px[4][3];   // 12 bytes = 4 pixels x 3 channels
+  px[0][0] = w0 & 255u; px[0][1] = (w0 >> 8) & 255u; px[0][2] = (w0 >> 16) & 255u;
+  px[1][0] = w0 >> 24;  px[1][1] = w1 & 255u;        px[1][2] = (w1 >> 8) & 255u;
+  px[2][0] = (w1 >> 16) & 255u; px[2][1] = w1 >> 24; px[2][2] = w2 & 255u;
+  px[3][0] = (w2 >> 8) & 255u;  px[3][1] = (w2 >> 16) & 255u; px[3][2] = w2 >> 24;
+  uint32_t out[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (a.swap_rb) { const uint32_t t = px[k][0]; px[k][0] = px[k][2]; px[k][2] = t; }
+    if (a.dst_u8 != nullptr) {
+      a.dst_u8[(o + k) * 3 + 0] = static_cast<uint8_t>(px[k][0]);
+      a.dst_u8[(o + k) * 3 + 1] = static_cast<uint8_t>(px[k][1]);
+      a.dst_u8[(o + k) * 3 + 2] = static_cast<uint8_t>(px[k][2]);
+    }
+    const float f0 = (static_cast<int>(px[k][0]) - a.mean[0]) * a.inv_std[0];
+    const float f1 = (static_cast<int>(px[k][1]) - a.mean[1]) * a.inv_std[1];
+    const float f2 = (static_cast<int>(px[k][2]) - a.mean[2]) * a.inv_std[2];
+    if (a.dst_f32 != nullptr) a.dst_f32[o + k] = make_float4(f0, f1, f2, 0.f);
+    out[2 * k] = pack_bf16x2(f0, f1);
+    out[2 * k + 1] = pack_bf16x2(f2, 0.f);
+  }
+  if (a.dst_f32 != nullptr) return;
+  uint4* dp = reinterpret_cast<uint4*>(a.dst + o);
+  dp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+__global__ void __launch_bounds__(256) preprocess_copy_u8_kernel(const PreArgs a) {
+  pdl_enter();
+  const int wq = a.W >> 2;
+  const size_t total = static_cast<size_t>(a.B) * a.H * wq;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  auto locate = [&](size_t i, const uint32_t*& sp, size_t& o) {
+    const int xq = static_cast<int>(i % wq);
+    const size_t r = i / wq;
+    const int y = static_cast<int>(r % a.H);
+    const size_t b = r / a.H;
+    sp = reinterpret_cast<const uint32_t*>(a.src + b * a.frame_stride + static_cast<size_t>(y) * a.pitch) + 3 * xq;
+    o = (b * a.H + y) * a.W + 4 * xq;
+  };
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (; i + stride < total; i += 2 * stride) {
+    const uint32_t *s0, *s1;
+    size_t o0, o1;
+    locate(i, s0, o0);
+    locate(i + stride, s1, o1);
+    const uint32_t a0 = __ldg(s0), a1 = __ldg(s0 + 1), a2 = __ldg(s0 + 2);
+    const uint32_t b0 = __ldg(s1), b1 = __ldg(s1 + 1), b2 = __ldg(s1 + 2);
+    pre_copy_group(a, o0, a0, a1, a2);
+    pre_copy_group(a, o1, b0, b1, b2);
+  }
+  if (i < total) {
+    const uint32_t* s0;
+    size_t o0;
+    locate(i, s0, o0);
+    pre_copy_group(a, o0, __ldg(s0), __ldg(s0 + 1), __ldg(s0 + 2));
   }
 }
 
@@ -592,12 +673,14 @@ resize_gray_u8_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, ui
 // (reads 8 B/pixel, writes 128 B/pixel), so it runs on the FP32 pipes: 16x16 pixel tile per block,
 // each thread owns 2 horizontally adjacent pixels x 32 output channels, weights broadcast from smem.
 // ------------------------------------------------------------------------------------------------
-// SPLIT (fp32-class path): x is the module's own fp32 NCHW input (no bf16 rounding of the image) and y is [B,H,W,2*Cout] = [hi | lo].
-template <bool SPLIT>
+// MODE 0: bf16 path, x = NHWC4 bf16. MODE 1 / 2 (fp32-class path): x is fp32 - the module's own NCHW input (1) or the NHWC4
+// fp32 tensor of the fp32 preprocess (2), i.e. no bf16 rounding of the image - and y is [B,H,W,2*Cout] = [hi | lo].
+template <int MODE>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const void* __restrict__ xin, const float* __restrict__ ws, const float* __restrict__ bias,
                  int B, int H, int W, int Cin, int Cout, int relu, __nv_bfloat16* __restrict__ y) {
   pdl_enter();
+  constexpr bool SPLIT = MODE != 0;
   const uint2* x = reinterpret_cast<const uint2*>(xin);
   extern __shared__ float sm[];
   float* sw = sm;                       // [9][4][Cout]
@@ -614,7 +697,9 @@ stem_conv_kernel(const void* __restrict__ xin, const float* __restrict__ ws, con
     const int hh = h0 + i / 18 - 1, ww = w0 + i % 18 - 1;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-      if (SPLIT) {
+      if (MODE == 2) {
+        v = __ldg(reinterpret_cast<const float4*>(xin) + (static_cast<size_t>(b) * H + hh) * W + ww);
+      } else if (MODE == 1) {
         const float* xf = reinterpret_cast<const float*>(xin);
         float c4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < Cin; ++k) c4[k] = __ldg(xf + ((static_cast<size_t>(b) * Cin + k) * H + hh) * W + ww);

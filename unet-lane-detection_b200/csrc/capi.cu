@@ -54,6 +54,7 @@ struct Opts {
   int wgrad_rows64 = 1;  // 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
   int wgrad2 = 1;        // CTA-pair weight-gradient kernel for BLOCK_N >= 128
   int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
+  int stem_wide = 0;     // tensor-core stem on 4 x 32 tiles (4 KB contiguous output rows per store) instead of 16 x 8
   int bwd_fuse = 1;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient
 };
 Opts g_opts;
@@ -82,6 +83,7 @@ enum AttrSlot : int {
   AT_STEM_WGRAD = 19,
   AT_PRE_ROWS = 20,
   AT_BNFUSE = 21,
+  AT_STEM_WIDE = 22,
 };
 struct DevState {
   std::atomic<int> num_sms{0};
@@ -396,28 +398,41 @@ int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const
   return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
 }
 
+// Tile width of the tensor-core stem (stem_umma.cuh): 8 (16 x 8 tiles) or 32 (4 x 32 tiles, option "stem_wide").
+int stem_tile_w() { return tl_opts->stem_wide ? 32 : 8; }
+// TMA-store target of the stem: one TMEM lane quarter = (tw pixels) x (32 / tw rows)
+int make_stem_out_map(CUtensorMap* m, void* out, int Bc, int H, int W, int tw) { return make_box_map(m, out, Bc, H, W, 64, tw, 32 / tw); }
+
+template <int TW>
+int launch_stem_umma_t(const CUtensorMap& mw, const CUtensorMap& mo, ub::StemArgs a, int slot, cudaStream_t st) {
+  UB_CUDA(ensure_smem(ub::stem_umma_kernel<TW>, slot, ub::StemCfg::SMEM_BYTES));
+  a.tiles_w = (a.W + TW - 1) / TW;
+  a.tiles_h = (a.H + 128 / TW - 1) / (128 / TW);
+  const int total = a.tiles_w * a.tiles_h * a.B;
+  const int sms = cur_sms();
+  const int grid = total < sms ? total : sms;
+  ub_launch(ub::stem_umma_kernel<TW>, grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st, mw, mo, a);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+// tw must be the tile width the output map `mo` was built for (make_stem_out_map)
 int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x, const float* bias, int B, int H, int W,
-                     int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
+                     int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr, int tw = 8) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
-  UB_CUDA(ensure_smem(ub::stem_umma_kernel, AT_STEM, ub::StemCfg::SMEM_BYTES));
   ub::StemArgs a;
   a.B = B;
   a.H = H;
   a.W = W;
-  a.tiles_w = (W + 7) / 8;
-  a.tiles_h = (H + 15) / 16;
+  a.tiles_w = a.tiles_h = 0;
   a.relu = relu;
   a.x = reinterpret_cast<const uint2*>(x);
   a.bias = bias;
   a.stat_sum = stat_sum;
   a.stat_sumsq = stat_sumsq;
-  const int total = a.tiles_w * a.tiles_h * B;
-  const int sms = cur_sms();
-  const int grid = total < sms ? total : sms;
-  ub_launch(ub::stem_umma_kernel, grid, ub::StemCfg::THREADS, ub::StemCfg::SMEM_BYTES, st, mw, mo, a);
-  UB_CUDA(cudaGetLastError());
-  return UB_OK;
+  if (tw == 32) return launch_stem_umma_t<32>(mw, mo, a, AT_STEM_WIDE, st);
+  return launch_stem_umma_t<8>(mw, mo, a, AT_STEM, st);
 }
 
 int launch_conv(int block_n, const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args,
@@ -450,6 +465,7 @@ struct Layer {
   bool halo;       // runs on conv_halo_kernel
   bool fuse_head;  // last conv: 1x1 head + sigmoid + mask evaluated in its epilogue
   bool stem_tc;    // stem on tensor cores (Cout == 64)
+  int stem_tw;     // its tile width (8 or 32), fixed when the layer is created
   CUtensorMap mA0, mA1, mW;
   CUtensorMap mOut, mPool;  // TMA-store targets (halo layers)
   CUtensorMap mO[4];        // TMA-store targets of conv_umma_kernel: {out, pool, -, -} or the four ConvT quads
@@ -493,6 +509,7 @@ int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc, int cm) {
 
 struct unet_b200_plan {
   int Bc, H, W, in_ch, out_ch, levels;
+  int split;                   // 1: fp32-class plan (every tensor [hi | lo] bf16, three K passes per product, fp32 network input)
   int feat[UB_MAX_LEVELS];
   Opts opt;                    // the switches this plan was created with (unet_b200_set_option changes later plans only)
   size_t ws_unshared_bytes;    // what the workspace would be with one private buffer per layer output (reporting)
@@ -521,7 +538,7 @@ int add_buf(unet_b200_plan* p, int H, int W, int C) {
   b.W = W;
   b.C = C;
   b.off = 0;
-  b.bytes = align_up((size_t)p->Bc * H * W * C * 2, 1024);
+  b.bytes = align_up((size_t)p->Bc * H * W * C * 2 * (p->split ? 2 : 1), 1024);   // split tensors carry [hi C | lo C]
   b.first = -1;
   b.last = -1;
   p->bufs.push_back(b);
@@ -548,20 +565,24 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
   l.pool = pool;
   l.set = false;
   l.w_off = p->wt_bytes;
+  const size_t kmul = p->split ? 3 : 1;   // split weights: [w_hi | w_hi | w_lo] per K source
   if (kind == L_STEM) {
     p->wt_bytes += align_up((size_t)36 * Cout * 4, 256);
   } else if (kind == L_CONV) {
-    p->wt_bytes += align_up((size_t)Cout * 9 * (C0 + C1) * 2, 256);
+    p->wt_bytes += align_up((size_t)Cout * 9 * (C0 + C1) * 2 * kmul, 256);
   } else {
-    p->wt_bytes += align_up((size_t)4 * Cout * C0 * 2, 256);
+    p->wt_bytes += align_up((size_t)4 * Cout * C0 * 2 * kmul, 256);
   }
   l.b_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)Cout * 4, 256);
-  if (kind == L_STEM) l.stem_tc = tl_opts->stem_umma && Cout == 64;
+  if (kind == L_STEM) {
+    l.stem_tc = !p->split && tl_opts->stem_umma && Cout == 64;   // split plan: FP32-pipe stem on the fp32 image
+    l.stem_tw = stem_tile_w();
+  }
   if (kind != L_STEM) {
     pick_tile(H, W, &l.TW, &l.TH, &l.TB, p->Bc);
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
-    l.halo = (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);
+    l.halo = !p->split && (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);   // split plan: per-tap kernel only (4 K sources)
     if (l.halo) l.block_n = Cout;
   }
   p->layers.push_back(l);
@@ -797,7 +818,15 @@ int unet_b200_device_ok(void) { return device_check(); }
 
 int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
                           const int* features, int levels) {
+  return unet_b200_plan_create_ex(out, max_batch, H, W, in_channels, out_channels, features, levels, UB_PRECISION_BF16);
+}
+
+int unet_b200_plan_precision(const unet_b200_plan* p) { return p ? (p->split ? UB_PRECISION_FP32 : UB_PRECISION_BF16) : -1; }
+
+int unet_b200_plan_create_ex(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
+                             const int* features, int levels, int precision) {
   if (out == nullptr || features == nullptr) return fail(UB_ERR_ARG, "null argument");
+  if (precision != UB_PRECISION_BF16 && precision != UB_PRECISION_FP32) return fail(UB_ERR_ARG, "unknown precision %d", precision);
   if (levels < 1 || levels > UB_MAX_LEVELS) return fail(UB_ERR_ARG, "levels must be in [1,%d]", UB_MAX_LEVELS);
   if (max_batch < 1) return fail(UB_ERR_ARG, "max_batch must be >= 1");
   if (in_channels < 1 || in_channels > 4) return fail(UB_ERR_ARG, "in_channels must be in [1,4] (got %d)", in_channels);
@@ -809,7 +838,11 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
     if (features[i] % 32 != 0 || features[i] <= 0) {
       return fail(UB_ERR_ARG, "features[%d]=%d must be a positive multiple of 32", i, features[i]);
     }
+    if (precision == UB_PRECISION_FP32 && features[i] % 64 != 0) {
+      return fail(UB_ERR_ARG, "the fp32-class plan needs features that are multiples of 64 (features[%d]=%d)", i, features[i]);
+    }
   }
+  if (precision == UB_PRECISION_FP32 && out_channels != 1) return fail(UB_ERR_ARG, "the fp32-class plan needs out_channels == 1");
   // physical channel counts: 64-aligned (one 128-byte swizzled row per pixel and channel block); a logical width such as
   // the deployed topology's 32 is stored zero-extended, see pack_conv3x3_pad_kernel
   int fp[UB_MAX_LEVELS];
@@ -822,6 +855,7 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
   p->in_ch = in_channels;
   p->out_ch = out_channels;
   p->levels = levels;
+  p->split = precision == UB_PRECISION_FP32 ? 1 : 0;
   p->opt = g_opts;                // this plan's switches from here on
   OptScope opt_scope(&p->opt);
   p->ws_bytes = 0;
@@ -883,7 +917,7 @@ int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int
     last.fuse_head = tl_opts->fuse_head && out_channels == 1 && last.kind == L_CONV && last.halo && last.Cout == 64;
   }
   p->head_w_off = p->wt_bytes;
-  p->wt_bytes += align_up((size_t)out_channels * fp[0] * 4, 256);
+  p->wt_bytes += align_up((size_t)out_channels * fp[0] * 4 * (p->split ? 2 : 1), 256);   // split: the weight vector twice (hi + lo)
   p->head_b_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)out_channels * 4, 256);
   plan_assign_workspace(p);
@@ -924,12 +958,28 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
       if (l.stem_tc) {
         rc = make_w_map_box(&l.mW, p->wt + l.w_off, 64, 64, 64);
         if (rc != UB_OK) return rc;
-        rc = make_box_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, 64, 8, 4);
+        rc = make_stem_out_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, l.stem_tw);
         if (rc != UB_OK) return rc;
       }
       continue;
     }
     const Buf& b0 = p->bufs[l.in0];
+    if (p->split) {
+      // fp32-class plan: tensors are [hi C | lo C]; one map per input over its 2C channels serves both K sources (hi|lo, hi)
+      rc = make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, 2 * l.C0, l.TW, l.TH, l.TB);
+      if (rc != UB_OK) return rc;
+      l.mA1 = l.mA0;
+      if (l.C1 > 0) {
+        rc = make_act_map(&l.mA1, p->ws + p->bufs[l.in1].off, p->Bc, l.H, l.W, 2 * l.C1, l.TW, l.TH, l.TB);
+        if (rc != UB_OK) return rc;
+      }
+      rc = make_umma_store_maps(l, p->ws + p->bufs[l.out].off, nullptr, p->Bc, 2);
+      if (rc != UB_OK) return rc;
+      rc = make_w_map(&l.mW, p->wt + l.w_off, l.kind == L_CONV ? l.Cout : 4 * l.Cout, (l.kind == L_CONV ? 9 : 1) * 3 * (l.C0 + l.C1),
+                      l.block_n);
+      if (rc != UB_OK) return rc;
+      continue;
+    }
     rc = l.halo ? make_halo_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0)
                 : make_act_map(&l.mA0, p->ws + b0.off, p->Bc, l.H, l.W, l.C0, l.TW, l.TH, l.TB);
     if (rc != UB_OK) return rc;
@@ -968,6 +1018,18 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
   Layer& l = p->layers[p->conv_ids[idx]];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* bias = reinterpret_cast<float*>(p->wt + l.b_off);
+  if (p->split) {
+    if (l.kind == L_STEM) {   // fp32 weights, no bf16 rounding
+      ub_launch(ub::pack_stem_kernel, grid_for(36 * l.Cout, 256), 256, 0, st, w, gamma, beta, mean, var, eps, l.Cout, l.C0,
+                reinterpret_cast<float*>(p->wt + l.w_off), bias, 1);
+    } else {
+      ub_launch(ub::pack_conv3x3_split_kernel, grid_for((size_t)l.Cout * 27 * (l.C0 + l.C1), 256), 256, 0, st, w, gamma, beta, mean,
+                var, eps, l.Cout, l.C0, l.C1, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
+    }
+    UB_CUDA(cudaGetLastError());
+    l.set = true;
+    return UB_OK;
+  }
   if (l.kind == L_STEM && l.stem_tc) {
     // logical Cout rows are written; rows / bias entries of padded channels keep the zeros the buffer was created with
     UB_CUDA(cudaMemsetAsync(p->wt + l.w_off, 0, (size_t)64 * 64 * 2, st));
@@ -995,6 +1057,14 @@ int unet_b200_plan_set_convT(unet_b200_plan* p, int idx, const float* w, const f
   if (idx < 0 || idx >= (int)p->convt_ids.size()) return fail(UB_ERR_ARG, "convT index %d out of range", idx);
   Layer& l = p->layers[p->convt_ids[idx]];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->split) {
+    ub_launch(ub::pack_convT_split_kernel, grid_for((size_t)12 * l.Cout * l.C0, 256), 256, 0, st, w, l.C0, l.Cout,
+              reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off));
+    UB_CUDA(cudaGetLastError());
+    UB_CUDA(cudaMemcpyAsync(p->wt + l.b_off, bias, (size_t)l.Cout * 4, cudaMemcpyDeviceToDevice, st));
+    l.set = true;
+    return UB_OK;
+  }
   ub_launch(ub::pack_convT_pad_kernel, grid_for((size_t)4 * l.Cout * l.C0, 256), 256, 0, st, 
       w, bias, l.lC0, l.lCout, l.C0, l.Cout, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off),
       reinterpret_cast<float*>(p->wt + l.b_off));
@@ -1011,6 +1081,9 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
   // rows of the logical width copied into zero-extended rows of the physical width
   UB_CUDA(cudaMemsetAsync(p->wt + p->head_w_off, 0, (size_t)p->out_ch * f0p * 4, st));
   UB_CUDA(cudaMemcpy2DAsync(p->wt + p->head_w_off, f0p * 4, w, f0 * 4, f0 * 4, (size_t)p->out_ch, cudaMemcpyDeviceToDevice, st));
+  if (p->split) {   // the head runs over [hi | lo]: the same weights for both halves
+    UB_CUDA(cudaMemcpyAsync(p->wt + p->head_w_off + f0p * 4, w, f0 * 4, cudaMemcpyDeviceToDevice, st));
+  }
   UB_CUDA(cudaMemcpyAsync(p->wt + p->head_b_off, bias, (size_t)p->out_ch * 4, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemcpyAsync(&p->head_bias, bias, 4, cudaMemcpyDeviceToHost, st));
   UB_CUDA(cudaStreamSynchronize(st));
@@ -1020,7 +1093,11 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
 
 int unet_b200_forward_launches(const unet_b200_plan* p) {
   if (p == nullptr) return 0;
-  return (int)p->layers.size() + (p->layers.back().fuse_head ? 0 : 1);
+  int n = (int)p->layers.size() + (p->layers.back().fuse_head ? 0 : 1);
+  if (p->split) {
+    for (const Layer& l : p->layers) n += l.pool >= 0 ? 1 : 0;   // the 2x2 pools are their own kernels there
+  }
+  return n;
 }
 
 int unet_b200_set_option(const char* name, int value) {
@@ -1028,7 +1105,8 @@ int unet_b200_set_option(const char* name, int value) {
   struct { const char* n; int* v; } tab[] = {
       {"halo", &g_opts.halo}, {"pdl", &g_opts.pdl}, {"halo2", &g_opts.halo2}, {"umma2", &g_opts.umma2},
       {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
-      {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse}};
+      {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
+      {"stem_wide", &g_opts.stem_wide}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
@@ -1054,13 +1132,40 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     const float* bias = reinterpret_cast<const float*>(p->wt + l.b_off);
     void* out = p->ws + p->bufs[l.out].off;
     void* pool = l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr;
-    if (l.kind == L_STEM && l.stem_tc) {
-      int rc = launch_stem_umma(l.mW, l.mOut, x, bias, batch, l.H, l.W, l.relu, st);
+    if (p->split) {
+      // fp32-class plan: stem on the FP32 pipes from the fp32 NHWC4 image, every other layer = the per-tap
+      // tcgen05 kernel over K sources (x[hi|lo] : 2C), (x[hi] : C) against weights [w_hi | w_hi | w_lo]; pools on hi + lo
+      if (l.kind == L_STEM) {
+        const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
+        const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
+        ub_launch(ub::stem_conv_kernel<2>, tiles, 256, smem, st, x, reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch,
+                  l.H, l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
+        UB_CUDA(cudaGetLastError());
+      } else {
+        ub::ConvArgs a = conv_args(l, batch, p->Bc, bias, out, nullptr);
+        a.kc0 = 2 * l.C0 / 64;
+        a.kc1 = l.C0 / 64;
+        a.kc2 = 2 * l.C1 / 64;
+        a.kc3 = l.C1 / 64;
+        a.split = 1;
+        a.pool_out = nullptr;
+        const CUtensorMap ma[4] = {l.mA0, l.mA0, l.mA1, l.mA1};
+        int rc = launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
+        if (rc != UB_OK) return rc;
+      }
+      if (l.pool >= 0) {
+        const size_t n = (size_t)batch * (l.H / 2) * (l.W / 2) * (l.Cout / 8);
+        ub_launch(ub::maxpool2x2_split_kernel, grid_for(n, 256), 256, 0, st, reinterpret_cast<const uint4*>(out), batch, l.H, l.W,
+                  l.Cout / 8, reinterpret_cast<uint4*>(pool));
+        UB_CUDA(cudaGetLastError());
+      }
+    } else if (l.kind == L_STEM && l.stem_tc) {
+      int rc = launch_stem_umma(l.mW, l.mOut, x, bias, batch, l.H, l.W, l.relu, st, nullptr, nullptr, l.stem_tw);
       if (rc != UB_OK) return rc;
     } else if (l.kind == L_STEM) {
       const int tiles = ((l.W + 15) / 16) * ((l.H + 15) / 16) * batch;
       const size_t smem = (size_t)(36 * l.Cout + l.Cout) * 4 + 18 * 18 * 16;
-      ub_launch(ub::stem_conv_kernel<false>, tiles, 256, smem, st, reinterpret_cast<const uint2*>(x),
+      ub_launch(ub::stem_conv_kernel<0>, tiles, 256, smem, st, reinterpret_cast<const uint2*>(x),
                                                       reinterpret_cast<const float*>(p->wt + l.w_off), bias, batch, l.H,
                                                       l.W, l.C0, l.Cout, l.relu, reinterpret_cast<__nv_bfloat16*>(out));
       UB_CUDA(cudaGetLastError());
@@ -1091,7 +1196,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     if (p->out_ch == 1) {
       ub_launch(ub::head_kernel, grid_for(npix * 8, 256), 256, 0, st,
           reinterpret_cast<const __nv_bfloat16*>(p->ws + fb.off), reinterpret_cast<const float*>(p->wt + p->head_w_off),
-          p->head_bias, npix, fb.C, logits, probs, mask, threshold);
+          p->head_bias, npix, fb.C * (p->split ? 2 : 1), logits, probs, mask, threshold);
     } else {
       // out_channels > 1 (README.md:1447 builds any): outputs are NCHW [batch][out_ch][H][W]
       const size_t smem = ((size_t)p->out_ch * fb.C + p->out_ch) * 4;
@@ -1159,9 +1264,32 @@ int unet_b200_nchw_to_nhwc4(const float* x, int batch, int C, int H, int W, void
   return UB_OK;
 }
 
+int unet_b200_nchw_to_nhwc4_f32(const float* x, int batch, int C, int H, int W, float* y, void* stream) {
+  if (x == nullptr || y == nullptr || C < 1 || C > 4) return fail(UB_ERR_ARG, "bad argument");
+  const size_t n = (size_t)batch * H * W;
+  ub_launch(ub::nchw_to_nhwc4_f32_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), x, batch, C, H, W,
+            reinterpret_cast<float4*>(y));
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
+}
+
+static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride, int H, int W,
+                           int swap_rb, const float* mean3, const float* std3, void* y, bool y_f32, uint8_t* resized, void* stream);
+
 int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride, int H,
                             int W, int swap_rb, const float* mean3, const float* std3, void* y, uint8_t* resized,
                             void* stream) {
+  return preprocess_impl(src, batch, Hs, Ws, pitch, frame_stride, H, W, swap_rb, mean3, std3, y, false, resized, stream);
+}
+
+int unet_b200_preprocess_u8_f32(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride, int H,
+                                int W, int swap_rb, const float* mean3, const float* std3, float* y, uint8_t* resized,
+                                void* stream) {
+  return preprocess_impl(src, batch, Hs, Ws, pitch, frame_stride, H, W, swap_rb, mean3, std3, y, true, resized, stream);
+}
+
+static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t pitch, size_t frame_stride, int H, int W,
+                           int swap_rb, const float* mean3, const float* std3, void* y, bool y_f32, uint8_t* resized, void* stream) {
   if (src == nullptr || y == nullptr || mean3 == nullptr || std3 == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (batch < 1 || Hs < 1 || Ws < 1 || H < 1 || W < 1) return fail(UB_ERR_ARG, "bad size");
   int rc = device_check();
@@ -1185,8 +1313,16 @@ int unet_b200_preprocess_u8(const uint8_t* src, int batch, int Hs, int Ws, size_
     a.mean[c] = mean3[c];
     a.inv_std[c] = 1.f / std3[c];
   }
-  a.dst = reinterpret_cast<uint2*>(y);
+  a.dst = y_f32 ? nullptr : reinterpret_cast<uint2*>(y);
+  a.dst_f32 = y_f32 ? reinterpret_cast<float4*>(y) : nullptr;
   a.dst_u8 = resized;
+  // same-size frames: cv2.resize is a copy - swap + normalise straight from global memory, four pixels per thread
+  if (Hs == H && Ws == W && (W & 3) == 0 && (pitch & 3) == 0 && (frame_stride & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    ub_launch(ub::preprocess_copy_u8_kernel, grid_for((size_t)batch * H * (W / 4), 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
   if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
   const int tiles_h = (H + rows - 1) / rows;
   ub_launch(ub::preprocess_u8_kernel, batch * tiles_h, ub::PRE_THREADS, smem, static_cast<cudaStream_t>(stream), a, rows);
@@ -1248,7 +1384,7 @@ size_t unet_b200_infer_staging_bytes(const unet_b200_plan* p, int Hs, int Ws) {
   if (p == nullptr) return 0;
   const size_t npix = (size_t)p->Bc * p->H * p->W, nout = npix * p->out_ch;
   size_t n = align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // frames
-  n += align_up(npix * 8, 256);                           // NHWC4 bf16
+  n += align_up(npix * (p->split ? 16 : 8), 256);         // network input: NHWC4 bf16 (fp32-class plan: NHWC4 fp32)
   n += 2 * align_up(nout * 4, 256);                       // logits, probs
   n += align_up(nout, 256);                               // mask
   return n;
@@ -1266,7 +1402,7 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* fra
   uint8_t* d_frames = s;
   s += align_up((size_t)p->Bc * Hs * Ws * 3, 256);
   void* d_x = s;
-  s += align_up(npix_c * 8, 256);
+  s += align_up(npix_c * (p->split ? 16 : 8), 256);
   float* d_logits = reinterpret_cast<float*>(s);
   s += align_up(nout_c * 4, 256);
   float* d_probs = reinterpret_cast<float*>(s);
@@ -1274,8 +1410,8 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging, const uint8_t* fra
   uint8_t* d_mask = s;
   const size_t frame_bytes = (size_t)Hs * Ws * 3;
   UB_CUDA(cudaMemcpyAsync(d_frames, frames, frame_bytes * batch, cudaMemcpyHostToDevice, st));
-  int rc = unet_b200_preprocess_u8(d_frames, batch, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3,
-                                   std3, d_x, nullptr, st);
+  int rc = preprocess_impl(d_frames, batch, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3, std3, d_x,
+                           p->split != 0, nullptr, st);
   if (rc != UB_OK) return rc;
   rc = unet_b200_forward(p, d_x, batch, logits_h ? d_logits : nullptr, probs_h ? d_probs : nullptr,
                          mask_h ? d_mask : nullptr, threshold, st);
@@ -1292,7 +1428,7 @@ size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int
   if (p == nullptr) return 0;
   const size_t npix = (size_t)p->Bc * p->H * p->W, nout = npix * p->out_ch;
   size_t n = 2 * align_up((size_t)p->Bc * Hs * Ws * 3, 256);  // two frame slots
-  n += align_up(npix * 8, 256);                               // NHWC4 bf16 (consumed by the stem before the next chunk's preprocess)
+  n += align_up(npix * (p->split ? 16 : 8), 256);             // NHWC4 input (consumed by the stem before the next chunk's preprocess)
   n += 2 * (2 * align_up(nout * 4, 256) + align_up(nout, 256));  // two output slots: logits, probs, mask
   return n;
 }
@@ -1323,7 +1459,7 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
     s += align_up((size_t)p->Bc * frame_bytes, 256);
   }
   void* d_x = s;
-  s += align_up(npix_c * 8, 256);
+  s += align_up(npix_c * (p->split ? 16 : 8), 256);
   float *d_logits[2], *d_probs[2];
   uint8_t* d_mask[2];
   const size_t nout_c = npix_c * p->out_ch;
@@ -1351,8 +1487,8 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
     UB_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
     // compute
     UB_CUDA(cudaStreamWaitEvent(st, p->ev_in[slot], 0));
-    int rc = unet_b200_preprocess_u8(d_frames[slot], n, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3, std3, d_x,
-                                     nullptr, st);
+    int rc = preprocess_impl(d_frames[slot], n, Hs, Ws, (size_t)Ws * 3, frame_bytes, p->H, p->W, swap_rb, mean3, std3, d_x,
+                             p->split != 0, nullptr, st);
     if (rc != UB_OK) return rc;
     UB_CUDA(cudaEventRecord(p->ev_in_free[slot], st));
     if (it >= 2) UB_CUDA(cudaStreamWaitEvent(st, p->ev_out_free[slot], 0));  // chunk it-2's results have left the slot
@@ -1434,7 +1570,7 @@ int unet_b200_stem_conv(const void* x, const float* ws, const float* bias, int B
   if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
   const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
   const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
-  ub_launch(ub::stem_conv_kernel<false>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
+  ub_launch(ub::stem_conv_kernel<0>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint2*>(x), ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -1458,9 +1594,10 @@ int unet_b200_stem_conv_tc(const void* x, const void* wp, const float* bias, int
   CUtensorMap mw, mo;
   rc = make_w_map_box(&mw, wp, 64, 64, 64);
   if (rc != UB_OK) return rc;
-  rc = make_box_map(&mo, y, B, H, W, 64, 8, 4);
+  const int tw = stem_tile_w();
+  rc = make_stem_out_map(&mo, y, B, H, W, tw);
   if (rc != UB_OK) return rc;
-  return launch_stem_umma(mw, mo, x, bias, B, H, W, relu, static_cast<cudaStream_t>(stream));
+  return launch_stem_umma(mw, mo, x, bias, B, H, W, relu, static_cast<cudaStream_t>(stream), nullptr, nullptr, tw);
 }
 
 int unet_b200_head(const void* x, const float* w, float bias, size_t npix, int C, float* logits, float* probs,
@@ -1579,7 +1716,7 @@ int unet_b200_stem_conv_split(const float* x_nchw, const float* ws, const float*
   if (Cout % 32 != 0 || Cout <= 0 || Cout > 256) return fail(UB_ERR_ARG, "stem Cout=%d must be a multiple of 32, <= 256", Cout);
   const int tiles = ((W + 15) / 16) * ((H + 15) / 16) * B;
   const size_t smem = (size_t)(36 * Cout + Cout) * 4 + 18 * 18 * 16;
-  ub_launch(ub::stem_conv_kernel<true>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
+  ub_launch(ub::stem_conv_kernel<1>, tiles, 256, smem, static_cast<cudaStream_t>(stream), 
       x_nchw, ws, bias, B, H, W, Cin, Cout, relu, reinterpret_cast<__nv_bfloat16*>(y));
   UB_CUDA(cudaGetLastError());
   return UB_OK;

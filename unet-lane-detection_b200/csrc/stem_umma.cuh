@@ -17,7 +17,7 @@ namespace ub {
 
 struct StemArgs {
   int B, H, W;
-  int tiles_w, tiles_h;   // 8-pixel x 16-row tiles per image
+  int tiles_w, tiles_h;   // TW-pixel x (128/TW)-row tiles per image
   int relu;
   const uint2* x;         // [B,H,W] x 4 bf16
   const float* bias;      // [64]
@@ -31,7 +31,7 @@ struct StemCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = N * 128;
   static constexpr int THREADS = 17 * 32;  // warp 0 MMA, warps 1..8 epilogue, warps 9..16 producers
-  static constexpr int PATCH_BYTES = 1536;     // [18][10] input pixels x 8 B of one tile (1440 B), one buffer per producer group
+  static constexpr int PATCH_BYTES = 2048;     // halo'd input patch of one tile x 8 B ([18][10] = 1440 B or [6][34] = 1632 B), one per producer group
   static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_BYTES + 8 * 4096 + 2 * PATCH_BYTES + 512 + 1024;
 };
 
@@ -60,10 +60,21 @@ __global__ void pack_stem_umma_kernel(const float* __restrict__ w, const float* 
   }
 }
 
+// TW = tile width in pixels (tile = 128/TW rows x TW pixels):
+//   8  -> 16 x 8 tiles, the smallest halo ([18][10] patch); a TMEM lane quarter stores a 4-row x 8-pixel box = four 1 KB pieces;
+//   32 -> 4 x 32 tiles ([6][34] patch, 13 % more input reads); a lane quarter is ONE image-row segment of 32 pixels = 4 KB
+//         contiguous in HBM. The layer is bound by its output writes, so the store pattern is what matters.
+template <int TW>
 __global__ void __launch_bounds__(StemCfg::THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
   pdl_enter();
   using Cfg = StemCfg;
+  constexpr int TH = 128 / TW;             // tile rows
+  constexpr int PW = TW + 2;               // patch pitch in pixels
+  constexpr int PATCH = (TH + 2) * PW;     // patch entries (<= 256: at most two per producer thread)
+  constexpr int QROWS = 32 / TW;           // tile rows covered by one TMEM lane quarter (TW <= 32)
+  static_assert(TW == 8 || TW == 16 || TW == 32, "tile width");
+  static_assert(PATCH <= 256 && PATCH * 8 <= Cfg::PATCH_BYTES, "patch size");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -140,19 +151,19 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     // (profiles/r1_ncu_full_stem_umma_v2.txt: 128 M warp instructions, IPC 1.9). The global loads of the group's NEXT tile
     // are issued before the current tile is assembled, so their latency is off the critical path.
     const int pg = (warp - 9) >> 2;
-    const int pt = ((warp - 9) & 3) * 32 + lane;  // thread of the group == row of the A tile == pixel of the 16x8 tile
-    const int tw = pt & 7, th = pt >> 3;
+    const int pt = ((warp - 9) & 3) * 32 + lane;  // thread of the group == row of the A tile == pixel of the tile
+    const int tw = pt % TW, th = pt / TW;
     uint2* patch = reinterpret_cast<uint2*>(smP + pg * Cfg::PATCH_BYTES);
     const uint32_t bar_id = 1 + pg;
-    // patch entries of this thread: e0 = pt, e1 = pt + 128 (only the first 52 threads have one)
-    const int r0 = pt / 10, c0 = pt % 10;
-    const int r1 = (pt + 128) / 10, c1 = (pt + 128) % 10;
-    const bool has1 = pt + 128 < 180;
+    // patch entries of this thread: e0 = pt, e1 = pt + 128 (only the first PATCH - 128 threads have one)
+    const int r0 = pt / PW, c0 = pt % PW;
+    const int r1 = (pt + 128) / PW, c1 = (pt + 128) % PW;
+    const bool has1 = pt + 128 < PATCH;
     auto fetch = [&](int t, uint2& v0, uint2& v1) {
       const int b = t / tiles_per_img;
       const int ti = t - b * tiles_per_img;
-      const int w0 = (ti % a.tiles_w) * 8 - 1;
-      const int h0 = (ti / a.tiles_w) * 16 - 1;
+      const int w0 = (ti % a.tiles_w) * TW - 1;
+      const int h0 = (ti / a.tiles_w) * TH - 1;
       const uint2* img = a.x + static_cast<size_t>(b) * a.H * a.W;
       v0 = make_uint2(0u, 0u);
       v1 = make_uint2(0u, 0u);
@@ -180,7 +191,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tap[r * 3 + c] = patch[(th + r) * 10 + tw + c];
+        for (int c = 0; c < 3; ++c) tap[r * 3 + c] = patch[(th + r) * PW + tw + c];
       }
       named_bar_sync(bar_id, 128);                      // everyone has read the patch: it may be overwritten
       mbar_wait_parked(&a_empty[s], ((it / Cfg::A_STAGES) & 1) ^ 1, 2000);
@@ -208,8 +219,8 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       const int acc = it & (Cfg::ACC_STAGES - 1);
       const int b = t / tiles_per_img;
       const int ti = t - b * tiles_per_img;
-      const int w0 = (ti % a.tiles_w) * 8;
-      const int h0 = (ti / a.tiles_w) * 16;
+      const int w0 = (ti % a.tiles_w) * TW;
+      const int h0 = (ti / a.tiles_w) * TH;
       mbar_wait(&tfull[acc], (it / Cfg::ACC_STAGES) & 1);
       tc_fence_after();
       uint32_t p[32];
@@ -222,11 +233,11 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&tmOut, stg, 0, w0, h0 + 4 * q, b);
+        tma_store_4d(&tmOut, stg, 0, w0, h0 + QROWS * q, b);   // box (64 ch, TW pixels, QROWS rows, 1 image)
         bulk_commit_group();
       }
       if (a.stat_sum != nullptr) {
-        const bool valid = (w0 + (lane & 7) < a.W) && (h0 + 4 * q + (lane >> 3) < a.H);
+        const bool valid = (w0 + (lane % TW) < a.W) && (h0 + QROWS * q + (lane / TW) < a.H);
         epi_stats_accumulate(stg, lane, __ballot_sync(0xffffffffu, valid), st0);
       }
     }

@@ -342,7 +342,8 @@ int trainer_build_maps(unet_b200_trainer* t) {
       if (c.Cout == 64) {
         rc = make_w_map_box(&c.fwd.mW, c.wp, 64, 64, 64);
         if (rc != UB_OK) return rc;
-        rc = make_box_map(&c.fwd.mOut, c.y, B, c.H, c.W, 64, 8, 4);
+        c.fwd.stem_tw = stem_tile_w();
+        rc = make_stem_out_map(&c.fwd.mOut, c.y, B, c.H, c.W, c.fwd.stem_tw);
         if (rc != UB_OK) return rc;
         rc = make_box_map(&c.wD, c.g, B, c.H, c.W, 64, 8, 16);  // dY tiles of the tensor-core stem weight gradient
         if (rc != UB_OK) return rc;
@@ -381,7 +382,7 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   bool stats_done = true;
   if (c.stem) {
     if (c.Cout == 64) {
-      rc = launch_stem_umma(c.fwd.mW, c.fwd.mOut, c.x0, t->zero_bias, B, c.H, c.W, 0, st, c.sum, c.sumsq);
+      rc = launch_stem_umma(c.fwd.mW, c.fwd.mOut, c.x0, t->zero_bias, B, c.H, c.W, 0, st, c.sum, c.sumsq, c.fwd.stem_tw);
       if (rc != UB_OK) return rc;
     } else {
       const int tiles = ((c.W + 15) / 16) * ((c.H + 15) / 16) * B;

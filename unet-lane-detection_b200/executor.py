@@ -71,7 +71,7 @@ def remap_milesial_state_dict(sd):
 
 
 class B200_model_container:
-    def __init__(self, model_path, target=None, device_id=None, output="probs"):
+    def __init__(self, model_path, target=None, device_id=None, output="probs", precision="bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("B200_model_container needs a CUDA sm_100 device (no CPU fallback)")
         dev = torch.device("cuda", int(device_id) if device_id not in (None, "") else torch.cuda.current_device())
@@ -93,6 +93,7 @@ class B200_model_container:
                                  f"unexpected {list(res.unexpected_keys)[:6]}")
             model.b200_frozen = True      # private copy, weights fixed from here on
         self.model = model.to(dev).eval()
+        self.model.b200_precision = precision   # "bf16" (default) or "fp32" (the fp32-class plan, logits within 1e-4)
         self.device = dev
         self.output = output  # "probs" (deployed graph has the sigmoid inside) or "logits"
         self.graph_max_batch = 8   # calls with at most this many frames replay a captured CUDA graph

@@ -17,19 +17,20 @@ import torch.nn as nn
 from ._lib import check, f3, lib
 from .ops import MEAN_255, STD_255
 
+PRECISIONS = {"bf16": 0, "fp32": 1}   # UB_PRECISION_* of include/unet_b200.h
 MAX_ENGINES = 4   # bound plans kept per model (each owns a workspace + packed weights): least recently used goes first
 
 
 class _Engine:
-    """One bound plan: (device, batch capacity, H, W) + workspace + packed weights."""
+    """One bound plan: (device, batch capacity, H, W, precision) + workspace + packed weights."""
 
-    def __init__(self, model: "UNet", device: torch.device, cap: int, H: int, W: int):
+    def __init__(self, model: "UNet", device: torch.device, cap: int, H: int, W: int, precision: str = "bf16"):
         feats = (C.c_int * len(model.features))(*model.features)
         handle = C.c_void_p()
-        check(lib.unet_b200_plan_create(C.byref(handle), cap, H, W, model.in_channels, model.out_channels, feats,
-                                        len(model.features)))
+        check(lib.unet_b200_plan_create_ex(C.byref(handle), cap, H, W, model.in_channels, model.out_channels, feats,
+                                           len(model.features), PRECISIONS[precision]))
         self.handle = handle
-        self.cap, self.H, self.W, self.device = cap, H, W, device
+        self.cap, self.H, self.W, self.device, self.precision = cap, H, W, device, precision
         self.workspace = torch.empty(lib.unet_b200_plan_workspace_bytes(handle), dtype=torch.uint8, device=device)
         self.weights = torch.zeros(lib.unet_b200_plan_weight_bytes(handle), dtype=torch.uint8, device=device)
         check(lib.unet_b200_plan_bind(handle, self.workspace.data_ptr(), self.weights.data_ptr()))
@@ -63,10 +64,10 @@ class UNet(nn.Module):
         self.output = nn.Conv2d(self.features[0], out_channels, kernel_size=1)
         # B200 runtime state (not part of the state_dict)
         self.b200_chunk = 128  # frames per pass through the plan (bounds the workspace; tune for L2 reuse)
-        # eval forward precision: "bf16" (fast path, logits within 2e-2 of the fp32 reference) or "fp32" (split-bf16 x3 on the
-        # same tensor-core kernel, logits within 1e-4; about 3x the tensor work) - BASELINE.json north_star parity gates
+        # eval precision of forward / predict_mask / infer_host: "bf16" (fast path, logits within 2e-2 of the fp32 reference) or
+        # "fp32" (a UB_PRECISION_FP32 plan: split-bf16 x3 on the same tensor-core kernel, logits within 1e-4; about 3x the
+        # tensor work) - BASELINE.json north_star parity gates
         self.b200_precision = "bf16"
-        self._split_weights = None
         self._engines = OrderedDict()   # LRU, at most MAX_ENGINES entries (shared with the trainers of training.py)
         self._b200_epoch = 0  # bumped whenever a kernel updates parameters / BN buffers in place
         # True: the weights will not change any more (a deployed model, e.g. inside B200_model_container) - the per-call
@@ -97,17 +98,20 @@ class UNet(nn.Module):
         return (self._b200_epoch,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _engine(self, device, H, W, batch, pipelined=False):
+        prec = self.b200_precision
+        if prec not in PRECISIONS:
+            raise ValueError("b200_precision must be 'bf16' or 'fp32'")
         cap = min(max(1, int(self.b200_chunk)), batch) if batch < self.b200_chunk else int(self.b200_chunk)
         if pipelined and batch >= 64 and cap >= batch:
             # host-buffer entry: a batch that fits one pass is still cut in two, so that the H2D copy of the second half and
             # the D2H copy of the first overlap the kernels (a single chunk would serialise copy -> compute -> copy)
             cap = (batch + 1) // 2
-        key = (str(device), cap, H, W)
+        key = (str(device), cap, H, W, prec)
         eng = self._engines.get(key)
         if eng is None:
             while len(self._engines) >= MAX_ENGINES:
                 self._engines.popitem(last=False)
-            eng = _Engine(self, device, cap, H, W)
+            eng = _Engine(self, device, cap, H, W, prec)
             self._engines[key] = eng
         else:
             self._engines.move_to_end(key)
@@ -148,85 +152,41 @@ class UNet(nn.Module):
         """Forward on the B200 kernels: float NCHW -> logits NCHW (README.md:1460-1481).
         eval(): BatchNorm folded into the weights. train(): batch-statistics BatchNorm, activations kept, and the
         result carries a grad_fn whose backward runs the B200 backward kernels (training.py)."""
-        self._check_input(x, "input")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise ValueError(f"expected [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        if torch.jit.is_tracing():
+            # torch.jit.trace cannot see a C-ABI call: the traced graph holds ONE operator, unet_b200::infer (torchscript.py)
+            if self.training:
+                raise RuntimeError("UNet (B200): trace the model in eval() mode")
+            from .torchscript import traced_forward
+            return traced_forward(self, x)
+        self._check_input(x, "input")
         if self.training:
             from .training import forward_train_autograd
             return forward_train_autograd(self, x)
         B, _, H, W = x.shape
         xin = x.detach().to(torch.float32).contiguous()
-        if self.b200_precision == "fp32":
-            return self._forward_split(xin).reshape(B, 1, H, W).to(x.dtype)
-        if self.b200_precision != "bf16":
-            raise ValueError("b200_precision must be 'bf16' or 'fp32'")
-        x4 = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=x.device)
         st = torch.cuda.current_stream().cuda_stream
-        check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, self.in_channels, H, W, x4.data_ptr(), st))
+        if self.b200_precision == "fp32":     # fp32-class plan: the image stays fp32
+            x4 = torch.empty(B, H, W, 4, dtype=torch.float32, device=x.device)
+            check(lib.unet_b200_nchw_to_nhwc4_f32(xin.data_ptr(), B, self.in_channels, H, W, x4.data_ptr(), st))
+        else:
+            x4 = torch.empty(B, H, W, 4, dtype=torch.bfloat16, device=x.device)
+            check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, self.in_channels, H, W, x4.data_ptr(), st))
         self.gpu_launches += 1
         logits = self.forward_nhwc4(x4, want=("logits",))[0]
         return logits.reshape(B, self.out_channels, H, W).to(x.dtype)
 
-    def _forward_split(self, xin):
-        """fp32-class eval forward (b200_precision == "fp32"): fp32 NCHW in -> fp32 logits [B,H,W]. Layer by layer through the
-        split-precision C-ABI entry points (ops.*_split): stem on the fp32 pipes, every other conv / ConvT as a three-pass
-        tcgen05 GEMM over (hi, lo) bf16 pairs, concat never materialised (two K sources), head over hi + lo."""
-        from . import ops
-        if any(f % 64 for f in self.features) or self.out_channels != 1:
-            raise ValueError("the fp32 path needs features that are multiples of 64 and out_channels == 1")
-        B, _, H, W = xin.shape
-        if H % (1 << len(self.features)) or W % (1 << len(self.features)):
-            raise ValueError(f"H and W must be divisible by {1 << len(self.features)}")
-        dev = xin.device
-        wkey = (str(dev),) + self._weights_key()
-        if self._split_weights is None or self._split_weights[0] != wkey:
-            def f32(t):
-                return t.detach().to(device=dev, dtype=torch.float32).contiguous()
-
-            def bn_of(bn):
-                return (f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var), float(bn.eps))
-
-            packed = []
-            L = len(self.features)
-            for i, (conv, bn) in enumerate(self._double_convs()):
-                if i == 0:
-                    packed.append(ops.pack_stem(f32(conv.weight), bn_of(bn), fp32=True))
-                else:
-                    dec = i >= 2 * L + 2 and (i - 2 * L - 2) % 2 == 0     # decoder conv0 reads cat([skip, up])
-                    packed.append(ops.pack_conv3x3_split(f32(conv.weight), bn_of(bn), c0=conv.in_channels // 2 if dec else None))
-            ups = [(ops.pack_convT2x2_split(f32(self.decoder_blocks[2 * j].weight)), f32(self.decoder_blocks[2 * j].bias))
-                   for j in range(L)]
-            hw = f32(self.output.weight.reshape(-1))
-            self._split_weights = (wkey, packed, ups, torch.cat([hw, hw]).contiguous(), float(self.output.bias.item()))
-        _, packed, ups, head_w, head_b = self._split_weights
-        L = len(self.features)
-        skips = []
-        cur = None
-        for i in range(L):
-            if i == 0:
-                cur = ops.stem_conv_split(xin, packed[0][0], packed[0][1])
-            else:
-                cur = ops.conv3x3_split(cur, *packed[2 * i])
-            cur = ops.conv3x3_split(cur, *packed[2 * i + 1])
-            skips.append(cur)
-            cur = ops.maxpool2x2_split(cur)
-        cur = ops.conv3x3_split(cur, *packed[2 * L])
-        cur = ops.conv3x3_split(cur, *packed[2 * L + 1])
-        for j in range(L):
-            up = ops.convT2x2_split(cur, *ups[j])
-            cur = ops.conv3x3_split(skips[L - 1 - j], *packed[2 * L + 2 + 2 * j], x1=up)
-            cur = ops.conv3x3_split(cur, *packed[2 * L + 3 + 2 * j])
-        logits, _, _ = ops.head(cur, head_w, head_b, want=("logits",))
-        self.gpu_launches += 4 * L + 2 + 2 * L + L + 1
-        return logits
-
     def forward_nhwc4(self, x4, threshold=0.5, want=("logits",)):
-        """x4: bf16 [B,H,W,4] normalised input. Returns (logits, probs, mask) with None for outputs not in `want`;
-        shapes [B,H,W] for out_channels == 1 (the reference's case), [B,out_channels,H,W] otherwise."""
+        """x4: normalised input [B,H,W,4], bf16 (fp32 when b200_precision == "fp32"). Returns (logits, probs, mask) with None
+        for outputs not in `want`; shapes [B,H,W] for out_channels == 1 (the reference's case), [B,out_channels,H,W] otherwise."""
         self._check_input(x4, "input")
         B, H, W, _ = x4.shape
         dev = x4.device
         eng = self._engine(dev, H, W, B)
+        want_dtype = torch.float32 if eng.precision == "fp32" else torch.bfloat16
+        if x4.dtype != want_dtype or not x4.is_contiguous():
+            raise ValueError(f"forward_nhwc4 with b200_precision={eng.precision!r} takes a contiguous {want_dtype} [B,H,W,4] tensor, got {x4.dtype}")
         self._last_engine = eng   # (a caller that captures this call in a CUDA graph keeps the reference: the graph replays into eng's buffers)
         shp = (B, H, W) if self.out_channels == 1 else (B, self.out_channels, H, W)
         logits = torch.empty(shp, dtype=torch.float32, device=dev) if "logits" in want else None
@@ -250,10 +210,12 @@ class UNet(nn.Module):
         (p > threshold)*255 (src/unet.py:63-67). Returns (logits, probs, mask) like forward_nhwc4."""
         self._check_input(frames_u8, "frames")
         B, Hs, Ws, _ = frames_u8.shape
-        x4 = torch.empty(B, size[0], size[1], 4, dtype=torch.bfloat16, device=frames_u8.device)
+        fp32 = self.b200_precision == "fp32"
+        x4 = torch.empty(B, size[0], size[1], 4, dtype=torch.float32 if fp32 else torch.bfloat16, device=frames_u8.device)
         st = torch.cuda.current_stream().cuda_stream
-        check(lib.unet_b200_preprocess_u8(frames_u8.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, size[0], size[1],
-                                          int(swap_rb), f3(MEAN_255), f3(STD_255), x4.data_ptr(), None, st))
+        pre = lib.unet_b200_preprocess_u8_f32 if fp32 else lib.unet_b200_preprocess_u8
+        check(pre(frames_u8.data_ptr(), B, Hs, Ws, Ws * 3, Hs * Ws * 3, size[0], size[1], int(swap_rb), f3(MEAN_255), f3(STD_255),
+                  x4.data_ptr(), None, st))
         self.gpu_launches += 1
         return self.forward_nhwc4(x4, threshold=threshold, want=want)
 
@@ -290,6 +252,8 @@ class UNet(nn.Module):
         eng = self._engine(x4.device, H, W, B)
         if B > eng.cap:
             raise ValueError(f"profile_layers takes at most one chunk ({eng.cap} frames)")
+        if eng.precision == "fp32":
+            raise ValueError("profile_layers reports the bf16 plan's kernels; set b200_precision = 'bf16'")
         n = lib.unet_b200_plan_num_layers(eng.handle)
         ms = (C.c_float * n)()
         mask = torch.empty(B, H, W, dtype=torch.uint8, device=x4.device)
