@@ -304,55 +304,36 @@ __device__ __forceinline__ int resize_blend(int h0, int h1, int by0, int by1) {
   return min(max(v, 0), 255);
 }
 
-// Tile kernel: one CTA produces PRE_ROWS consecutive output rows of one frame.
-//   1. per-CTA tables in shared memory: the horizontal taps of every output column (computed once per CTA instead of once
-//      per pixel: resize_coef costs a double division) and, per output row, the two source-row slots + vertical weights;
-//   2. the source rows the tile needs are staged with 16-byte loads: the contiguous span [first, last] when it is short
-//      (identity, up-scaling, down-scaling by <= 2: every row is read once), else exactly the two rows per output row;
-//   3. every thread blends one output pixel per trip from shared memory and writes its 8-byte NHWC4 pixel; a warp's
-//      stores cover 256 contiguous bytes.
-// profiles/r1: the first version (one CTA per output row, byte-wide staging loads) reached 1.04 TB/s = 16 % of the copy peak.
+// Persistent tile kernel: a CTA walks tiles of `rows_per_cta` consecutive output rows of one frame.
+//   once per CTA: the horizontal taps of every output column and the vertical taps of every output row go to shared memory
+//      (resize_coef costs a double division; the first version recomputed it per pixel, the second per tile);
+//   per tile: 1. the source rows the tile needs are staged with 16-byte loads: the contiguous span [first, last] when it is
+//                short (identity, up-scaling, down-scaling by <= 2: every row is read once), else the two rows per output row;
+//             2. a thread owns output COLUMNS (its taps stay in registers) and walks the tile's rows, four at a time so that
+//                48 shared-memory byte loads are in flight; a warp's stores of one row cover 256 contiguous bytes.
+// profiles/: one CTA per output row with byte-wide staging reached 1.04 TB/s (r1); one CTA per 8-row tile with per-tile tables
+// 0.84-1.45 TB/s; this form is the one measured in profiles/r2_*.
 constexpr int PRE_ROWS = 8;
 constexpr int PRE_THREADS = 256;
 __host__ __device__ constexpr int pre_row_pitch(int Ws) { return ((Ws * 3 + 15) / 16) * 16 + 16; }   // + head misalignment
-// dynamic shared memory: row slots + [W] x-tap table (int4)
-__host__ __device__ constexpr size_t pre_smem_bytes(int Ws, int W, int rows) {
-  return static_cast<size_t>(2 * rows) * pre_row_pitch(Ws) + static_cast<size_t>(W) * 16;
+// dynamic shared memory: row slots + [W] x-tap table + [H] y-tap table (int4 each)
+__host__ __device__ constexpr size_t pre_smem_bytes(int Ws, int W, int H, int rows) {
+  return static_cast<size_t>(2 * rows) * pre_row_pitch(Ws) + static_cast<size_t>(W + H) * 16;
 }
 
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArgs a, int rows_per_cta) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t pre_smem[];
-  __shared__ int s_slot[2 * PRE_ROWS], s_by[2 * PRE_ROWS], s_src[2 * PRE_ROWS], s_off[2 * PRE_ROWS];
+  __shared__ int s_slot[2 * PRE_ROWS], s_src[2 * PRE_ROWS], s_off[2 * PRE_ROWS];
   __shared__ int s_nslots;
   const int R = rows_per_cta;
-  const int tiles_h = (a.H + R - 1) / R;
-  const int b = blockIdx.x / tiles_h;
-  const int y0 = (blockIdx.x % tiles_h) * R;
-  const int nrows = min(R, a.H - y0);
   const int pitch_s = pre_row_pitch(a.Ws);
   int4* xtab = reinterpret_cast<int4*>(pre_smem + static_cast<size_t>(2 * R) * pitch_s);
+  int4* ytab = xtab + a.W;
   // cv::resize special cases: equal sizes copy (the taps below reduce to that), and an exact 2x2 decimation is computed
   // as INTER_AREA = (a + b + c + d + 2) >> 2
   const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
-  const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
-
-  __shared__ int s_sy[2 * PRE_ROWS];
-  if (threadIdx.x < nrows) {           // vertical taps of the tile's rows, one thread per row
-    const int r = threadIdx.x;
-    int y_0, y_1, b0, b1;
-    resize_coef(y0 + r, a.H, a.Hs, false, y_0, y_1, b0, b1);
-    if (area2) {
-      y_0 = 2 * (y0 + r);
-      y_1 = 2 * (y0 + r) + 1;
-    }
-    s_sy[2 * r] = y_0;
-    s_sy[2 * r + 1] = y_1;
-    s_by[2 * r] = b0;
-    s_by[2 * r + 1] = b1;
-  }
-  // horizontal taps: {3*sx0, 3*sx1, ax0, ax1} per output column
-  for (int x = threadIdx.x; x < a.W; x += PRE_THREADS) {
+  for (int x = threadIdx.x; x < a.W; x += PRE_THREADS) {     // {3*sx0, 3*sx1, ax0, ax1}
     int sx0, sx1, ax0, ax1;
     resize_coef(x, a.W, a.Ws, true, sx0, sx1, ax0, ax1);
     if (area2) {
@@ -361,74 +342,98 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArg
     }
     xtab[x] = make_int4(3 * sx0, 3 * sx1, ax0, ax1);
   }
-  __syncthreads();
-  if (threadIdx.x < 2 * PRE_ROWS) {    // slot tables: every one of these threads derives the (tiny) min / max itself
-    int lo = 1 << 30, hi = -1;
-    for (int k = 0; k < 2 * nrows; ++k) {
-      lo = min(lo, s_sy[k]);
-      hi = max(hi, s_sy[k]);
+  for (int y = threadIdx.x; y < a.H; y += PRE_THREADS) {     // {sy0, sy1, by0, by1}
+    int sy0, sy1, by0, by1;
+    resize_coef(y, a.H, a.Hs, false, sy0, sy1, by0, by1);
+    if (area2) {
+      sy0 = 2 * y;
+      sy1 = 2 * y + 1;
     }
-    const bool span = hi - lo + 1 <= 2 * R;   // span mode: slot i holds source row lo + i; sparse: two private slots per row
-    const int n = span ? hi - lo + 1 : 2 * nrows;
-    const int i = threadIdx.x;
-    if (i < 2 * nrows) s_slot[i] = span ? s_sy[i] - lo : i;
-    if (i < n) {
-      const int row = span ? lo + i : s_sy[i];
-      s_src[i] = row;
-      const uintptr_t p = reinterpret_cast<uintptr_t>(frame + static_cast<size_t>(row) * a.pitch);
-      s_off[i] = static_cast<int>(p & 15);   // the row is staged from its 16-byte aligned address; this is where it starts
-    }
-    if (i == 0) s_nslots = n;
+    ytab[y] = make_int4(sy0, sy1, by0, by1);
   }
   __syncthreads();
-  // stage the rows: 16-byte chunks from the aligned-down row address (never below the allocation: it is at least 16-byte
-  // aligned); a chunk that would reach past the last byte of the last frame is read byte by byte instead
-  const int nslots = s_nslots;
+  const int tiles_h = (a.H + R - 1) / R;
+  const int total = a.B * tiles_h;
   const int row_bytes = a.Ws * 3;
   const uint8_t* src_end = a.src + static_cast<size_t>(a.B - 1) * a.frame_stride + static_cast<size_t>(a.Hs - 1) * a.pitch + row_bytes;
-  for (int i = 0; i < nslots; ++i) {
-    const uint8_t* rp = frame + static_cast<size_t>(s_src[i]) * a.pitch - s_off[i];
-    const int chunks = (s_off[i] + row_bytes + 15) >> 4;
-    uint8_t* dst = pre_smem + static_cast<size_t>(i) * pitch_s;
-    for (int c = threadIdx.x; c < chunks; c += PRE_THREADS) {
-      const uint8_t* g = rp + 16 * c;
-      if (g + 16 <= src_end) {
-        *reinterpret_cast<uint4*>(dst + 16 * c) = __ldg(reinterpret_cast<const uint4*>(g));
-      } else {
-        for (int k = 0; k < 16; ++k) dst[16 * c + k] = (g + k < src_end) ? __ldg(g + k) : 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int b = t / tiles_h;
+    const int y0 = (t - b * tiles_h) * R;
+    const int nrows = min(R, a.H - y0);
+    const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
+    if (threadIdx.x < 2 * PRE_ROWS) {    // slot tables: every one of these threads derives the (tiny) min / max itself
+      int lo = 1 << 30, hi = -1;
+      for (int r = 0; r < nrows; ++r) {
+        const int4 yt = ytab[y0 + r];
+        lo = min(lo, min(yt.x, yt.y));
+        hi = max(hi, max(yt.x, yt.y));
+      }
+      const bool span = hi - lo + 1 <= 2 * R;   // span mode: slot i holds source row lo + i; sparse: two private slots per row
+      const int n = span ? hi - lo + 1 : 2 * nrows;
+      const int i = threadIdx.x;
+      if (i < 2 * nrows) {
+        const int4 yt = ytab[y0 + (i >> 1)];
+        const int row = (i & 1) ? yt.y : yt.x;
+        s_slot[i] = span ? row - lo : i;
+        if (!span) s_src[i] = row;
+      }
+      if (span && i < n) s_src[i] = lo + i;
+      if (i == 0) s_nslots = n;
+    }
+    __syncthreads();
+    // stage the rows: 16-byte chunks from the aligned-down row address (never below the allocation: it is at least 16-byte
+    // aligned); a chunk that would reach past the last byte of the last frame is read byte by byte instead
+    const int nslots = s_nslots;
+    for (int i = 0; i < nslots; ++i) {
+      const uint8_t* rowp = frame + static_cast<size_t>(s_src[i]) * a.pitch;
+      const int off = static_cast<int>(reinterpret_cast<uintptr_t>(rowp) & 15);
+      if (threadIdx.x == 0) s_off[i] = off;      // where the row starts inside its slot
+      const uint8_t* rp = rowp - off;
+      const int chunks = (off + row_bytes + 15) >> 4;
+      uint8_t* dst = pre_smem + static_cast<size_t>(i) * pitch_s;
+      for (int c = threadIdx.x; c < chunks; c += PRE_THREADS) {
+        const uint8_t* g = rp + 16 * c;
+        if (g + 16 <= src_end) {
+          *reinterpret_cast<uint4*>(dst + 16 * c) = __ldg(reinterpret_cast<const uint4*>(g));
+        } else {
+          for (int k = 0; k < 16; ++k) dst[16 * c + k] = (g + k < src_end) ? __ldg(g + k) : 0;
+        }
       }
     }
-  }
-  __syncthreads();
-  const int total = nrows * a.W;
-  for (int i = threadIdx.x; i < total; i += PRE_THREADS) {
-    const int r = i / a.W, x = i - r * a.W;
-    const int4 t = xtab[x];
-    const int sl0 = s_slot[2 * r], sl1 = s_slot[2 * r + 1];
-    const uint8_t* r0 = pre_smem + static_cast<size_t>(sl0) * pitch_s + s_off[sl0];
-    const uint8_t* r1 = pre_smem + static_cast<size_t>(sl1) * pitch_s + s_off[sl1];
-    int px[3];
+    __syncthreads();
+    for (int x = threadIdx.x; x < a.W; x += PRE_THREADS) {
+      const int4 xt = xtab[x];
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const int4 yt = ytab[y0 + r];
+        const int sl0 = s_slot[2 * r], sl1 = s_slot[2 * r + 1];
+        const uint8_t* r0 = pre_smem + static_cast<size_t>(sl0) * pitch_s + s_off[sl0];
+        const uint8_t* r1 = pre_smem + static_cast<size_t>(sl1) * pitch_s + s_off[sl1];
+        int px[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (area2) {
-        px[c] = (r0[t.x + c] + r0[t.y + c] + r1[t.x + c] + r1[t.y + c] + 2) >> 2;
-      } else {
-        const int h0 = r0[t.x + c] * t.z + r0[t.y + c] * t.w;
-        const int h1 = r1[t.x + c] * t.z + r1[t.y + c] * t.w;
-        px[c] = resize_blend(h0, h1, s_by[2 * r], s_by[2 * r + 1]);
+        for (int c = 0; c < 3; ++c) {
+          if (area2) {
+            px[c] = (r0[xt.x + c] + r0[xt.y + c] + r1[xt.x + c] + r1[xt.y + c] + 2) >> 2;
+          } else {
+            const int h0 = r0[xt.x + c] * xt.z + r0[xt.y + c] * xt.w;
+            const int h1 = r1[xt.x + c] * xt.z + r1[xt.y + c] * xt.w;
+            px[c] = resize_blend(h0, h1, yt.z, yt.w);
+          }
+        }
+        if (a.swap_rb) { const int tt = px[0]; px[0] = px[2]; px[2] = tt; }
+        const size_t o = (static_cast<size_t>(b) * a.H + y0 + r) * a.W + x;
+        if (a.dst_u8 != nullptr) {
+          a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
+          a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
+          a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+        }
+        const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
+        const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
+        const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
+        pre_store(a, o, f0, f1, f2);
       }
     }
-    if (a.swap_rb) { const int tt = px[0]; px[0] = px[2]; px[2] = tt; }
-    const size_t o = (static_cast<size_t>(b) * a.H + y0 + r) * a.W + x;
-    if (a.dst_u8 != nullptr) {
-      a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
-      a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
-      a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
-    }
-    const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
-    const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
-    const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
-    pre_store(a, o, f0, f1, f2);
+    __syncthreads();   // the slot tables and the staged rows are free for the next tile
   }
 }
 

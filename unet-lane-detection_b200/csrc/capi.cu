@@ -1294,11 +1294,11 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
   if (batch < 1 || Hs < 1 || Ws < 1 || H < 1 || W < 1) return fail(UB_ERR_ARG, "bad size");
   int rc = device_check();
   if (rc != UB_OK) return rc;
-  // output rows per CTA: as many as keep the staged source rows within 64 KB (several CTAs per SM), at least one
+  // output rows per tile: as many as keep the staged source rows within 64 KB (several CTAs per SM), at least one
   int rows = ub::PRE_ROWS;
-  while (rows > 1 && ub::pre_smem_bytes(Ws, W, rows) > 64 * 1024) rows >>= 1;
-  const size_t smem = ub::pre_smem_bytes(Ws, W, rows);
-  if (smem > 200 * 1024) return fail(UB_ERR_ARG, "source row too wide for shared-memory staging (%d pixels)", Ws);
+  while (rows > 1 && ub::pre_smem_bytes(Ws, W, H, rows) > 64 * 1024) rows >>= 1;
+  const size_t smem = ub::pre_smem_bytes(Ws, W, H, rows);
+  if (smem > 200 * 1024) return fail(UB_ERR_ARG, "frames too large for shared-memory staging (%d pixels wide, %d x %d output)", Ws, H, W);
   ub::PreArgs a;
   a.src = src;
   a.pitch = pitch;
@@ -1324,8 +1324,12 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
     return UB_OK;
   }
   if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
-  const int tiles_h = (H + rows - 1) / rows;
-  ub_launch(ub::preprocess_u8_kernel, batch * tiles_h, ub::PRE_THREADS, smem, static_cast<cudaStream_t>(stream), a, rows);
+  // persistent CTAs: as many as are resident at once (shared memory bound), each walks tiles of `rows` output rows
+  const int tiles = batch * ((H + rows - 1) / rows);
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int resident = cur_sms() * per_sm;
+  ub_launch(ub::preprocess_u8_kernel, tiles < resident ? tiles : resident, ub::PRE_THREADS, smem, static_cast<cudaStream_t>(stream), a, rows);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -1476,9 +1480,15 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
   UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
   UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
   const size_t hw = (size_t)p->H * p->W * p->out_ch;   // output elements per frame
+  // Chunk schedule: the H2D copy of the FIRST chunk is the one copy no kernel can hide, so the first chunk is a quarter of
+  // the plan's capacity; every later chunk is plan-sized and its copy runs under the previous chunk's kernels.
+  int first = (p->Bc / 4) & ~7;
+  if (first < 8) first = 8;
+  if (first * 2 >= total) first = total < p->Bc ? total : p->Bc;
   int it = 0;
-  for (int b0 = 0; b0 < total; b0 += p->Bc, ++it) {
-    const int n = total - b0 < p->Bc ? total - b0 : p->Bc;
+  for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
+    n = (it == 0) ? first : p->Bc;
+    if (n > total - b0) n = total - b0;
     const int slot = it & 1;
     const size_t npix = (size_t)n * hw;
     // H2D of chunk `it` (runs while chunk it-1 computes); the slot is free once chunk it-2's preprocess has read it

@@ -128,7 +128,9 @@ class B200_model_container:
                 self.model.predict_mask(static_in, size=size, want=(self.output,))   # eager once: builds the plan, packs weights
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                # (an explicit capture stream on THIS device: torch's default capture stream is created once per process, on
+                # whichever device was current then - a second container on another GPU would capture on the wrong device)
+                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.device)):
                     logits, probs, _ = self.model.predict_mask(static_in, size=size, want=(self.output,))
                 out = probs if self.output == "probs" else logits
                 entry = (graph, static_in, out, self.model._last_engine)   # the graph replays into this plan's buffers

@@ -329,8 +329,8 @@ class NvlinkExchange:
             for _, lo, hi in self.buckets:
                 a, b = shard_of(lo, hi, self.rank, self.world)
                 self.parts.append((a, b, off))
-                off += b - a
-        n_local = max(1, sum(b - a for a, b, _ in self.parts))
+                off += (b - a + 3) // 4 * 4      # every part's moments start 16-byte aligned (the kernel moves float4)
+        n_local = max(4, max((off_ + (b - a + 3) // 4 * 4) for a, b, off_ in self.parts))
         self.exp_avg = torch.zeros(n_local, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n_local, dtype=torch.float32, device=dev)
         torch.cuda.synchronize()
@@ -595,7 +595,7 @@ class FusedTrainStep:
                 sx, sy = torch.empty_like(images), torch.empty_like(masks)
                 graph = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=images.device)):   # capture stream on THIS device
                     out = self._run(sx, sy)
                 # the graph replays into the trainer's workspace: the entry keeps the engine alive even if the model's engine
                 # cache lets go of it

@@ -242,7 +242,9 @@ class UNet(nn.Module):
             eng.handle, eng.staging.data_ptr(), frames_host.data_ptr(), B, Hs, Ws, int(swap_rb), f3(MEAN_255), f3(STD_255),
             float(threshold), None if logits_out is None else logits_out.data_ptr(),
             None if probs_out is None else probs_out.data_ptr(), None if mask_out is None else mask_out.data_ptr(), st))
-        self.gpu_launches += ((B + eng.cap - 1) // eng.cap) * (eng.launches + 1)
+        first = max(8, (eng.cap // 4) & ~7)           # chunk schedule of unet_b200_infer_u8_host_stream: short first chunk
+        first = min(B, eng.cap) if first * 2 >= B else first
+        self.gpu_launches += (1 + (B - first + eng.cap - 1) // eng.cap) * (eng.launches + 1)
         return mask_out, probs_out, logits_out
 
     def profile_layers(self, x4):
