@@ -312,6 +312,28 @@ def test_train_step_config4_geometry_224_batch4(U):
         assert abs(got - want) <= 2e-3 * max(1.0, abs(want))
 
 
+def test_bn_backward_reduction_fused_into_producers(U):
+    """Option bwd_fuse: the BatchNorm-backward sums of the encoder conv1 layers / the last conv come out of the max-pool /
+    head backward kernels instead of a separate reduction pass. Same sums (fp32 atomics in a different order)."""
+    from unet_lane_detection_b200._lib import check, lib
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(8, 3, 64, 64, generator=g).cuda()
+    y = (torch.rand(8, 1, 64, 64, generator=g) < 0.1).float().cuda()
+    grads, losses = [], []
+    try:
+        for fuse in (1, 0, 1):
+            check(lib.unet_b200_set_option(b"bwd_fuse", fuse))
+            _, net = make_train_pair(U, [64, 128, 256, 512])
+            step = U.FusedTrainStep(net, lr=0.0, weight_decay=0.0, cuda_graph=False)
+            losses.append(step.step(x, y).cpu())
+            grads.append(step.last_grads.clone())
+    finally:
+        check(lib.unet_b200_set_option(b"bwd_fuse", 1))
+    noise = rel_l2(grads[2], grads[0])           # run-to-run spread of the same configuration
+    assert rel_l2(grads[1], grads[0]) <= max(3 * noise, 2e-3), (rel_l2(grads[1], grads[0]), noise)
+    assert torch.equal(losses[0], losses[1])
+
+
 def test_fused_step_trains_and_eval_sees_new_weights(U):
     """FusedTrainStep (loss + backward + AdamW kernels): loss goes down on a fixed batch; eval() afterwards uses the
     updated parameters and running statistics (packed inference weights are refreshed)."""

@@ -34,6 +34,7 @@ struct TConv {
   ub::WgradArgs wa;
   int w_bn, w_grid;
   bool w_pair;
+  bool reduce_fused;  // the BatchNorm-backward sums of this layer come out of the kernel that produces its incoming gradient
 };
 
 struct TConvT {
@@ -94,6 +95,19 @@ struct Bump {
 };
 
 bool pow2_times_64(int c) { return c >= 64 && c <= 2048 && (c & (c - 1)) == 0; }
+
+ub::BnBwdStats bn_stats_of(const TConv& c) {
+  ub::BnBwdStats b;
+  b.y = c.reduce_fused ? reinterpret_cast<const uint4*>(c.y) : nullptr;
+  b.scale = c.scale;
+  b.shift = c.shift;
+  b.mean = c.mean;
+  b.invstd = c.invstd;
+  b.s1 = c.s1;
+  b.s2 = c.s2;
+  return b;
+}
+const ub::BnBwdStats kNoBnStats = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
 // One pass over the network assigning workspace addresses (base == 0: size computation only).
 void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
@@ -444,9 +458,11 @@ int conv_bn_backward(const TConv& c, int B, float* s1, float* s2, const ub::Grad
   const int C8 = c.Cout / 8;
   const uint4* g4 = reinterpret_cast<const uint4*>(c.g);
   const uint4* y4 = reinterpret_cast<const uint4*>(c.y);
-  ub_launch(ub::bn_relu_bwd_reduce_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st, g4, y4, c.scale, c.shift, c.mean, c.invstd, npix,
-                                                                                 C8, s1, s2);
-  UB_CUDA(cudaGetLastError());
+  if (!c.reduce_fused) {   // (fused: s1 / s2 were accumulated by the kernel that wrote c.g - max-pool or head backward)
+    ub_launch(ub::bn_relu_bwd_reduce_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st, g4, y4, c.scale, c.shift, c.mean, c.invstd,
+              npix, C8, s1, s2);
+    UB_CUDA(cudaGetLastError());
+  }
   const size_t n8 = npix * C8;
   ub_launch(ub::bn_relu_bwd_apply_kernel, grid_for(n8, 256), 256, 0, st, g4, y4, c.scale, c.shift, c.mean, c.invstd, s1, s2,
                                                                   1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g), route,
@@ -648,6 +664,12 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
     mk(h, w, f, 0, f, false, false);
     cin = f;
   }
+  // BatchNorm-backward sums fused into the producer of the incoming gradient where that producer is an elementwise kernel:
+  // the encoder conv1 layers (max-pool backward) and the last conv (head backward)
+  if (t->opt.bwd_fuse) {
+    for (int i = 0; i < levels; ++i) t->convs[2 * i + 1].reduce_fused = true;
+    t->convs.back().reduce_fused = true;
+  }
   // forward order and parameters() order (encoder, decoder, bottleneck, output: README.md:1427-1447)
   for (int i = 0; i < 2 * levels + 2; ++i) t->fwd_order.push_back(i);
   for (int j = 0; j < levels; ++j) {
@@ -846,9 +868,9 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
     TConv& last = t->convs.back();
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
-    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st,
+    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
         reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g), route,
-        t->head_w_off, t->head_b_off);
+        t->head_w_off, t->head_b_off, bn_stats_of(last));
     UB_CUDA(cudaGetLastError());
   } else {
     if (t->bwd_stage != stage - 1) return fail(UB_ERR_STATE, "backward stages must run in order (got %d after %d)", stage, t->bwd_stage);
@@ -872,9 +894,9 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
       const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
       const int C8 = c1.Cout / 8;
       const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
-      ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, st,
+      ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, c1.reduce_fused ? 2 * 2048 * 4 : 0, st,
           reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
-          2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g));
+          2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g), bn_stats_of(c1));
       UB_CUDA(cudaGetLastError());
       rc = trainer_conv_backward(t, c1, route, st);
       if (rc != UB_OK) return rc;
@@ -1267,9 +1289,9 @@ int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, i
   if (rc != UB_OK) return rc;
   const int C8 = C / 8;
   const size_t n = (size_t)B * (H / 2) * (W / 2) * C8;
-  ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
+  ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream),
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(dP), reinterpret_cast<const uint4*>(dskip),
-      dskip ? skip_pitch / 8 : C8, B, H, W, C8, reinterpret_cast<uint4*>(dA));
+      dskip ? skip_pitch / 8 : C8, B, H, W, C8, reinterpret_cast<uint4*>(dA), kNoBnStats);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }

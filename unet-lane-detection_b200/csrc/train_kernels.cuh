@@ -270,15 +270,76 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
   }
 }
 
+// BatchNorm-backward statistics fused into the pass that PRODUCES the incoming gradient dA of a conv layer (max-pool backward,
+// head backward): that pass has dA in registers, so reading the layer's raw conv output y beside it yields
+// s1 = sum dA*[relu on] and s2 = sum dA*[relu on]*xhat without bn_relu_bwd_reduce_kernel's extra read of dA (and its launch).
+struct BnBwdStats {
+  const uint4* y;       // raw conv output of the layer whose dA is being produced (null: no fusion)
+  const float* scale;   // per channel: gamma * invstd
+  const float* shift;   // beta - mean * scale
+  const float* mean;
+  const float* invstd;
+  float* s1;            // [C] += sum g        (g = dA where relu(bn(y)) > 0)
+  float* s2;            // [C] += sum g * xhat
+};
+struct BnBwdRegs {       // a thread's eight channels
+  float sc[8], sh[8], mu[8], is[8], a1[8], a2[8];
+};
+__device__ __forceinline__ void bnbwd_init(const BnBwdStats& b, int c8, BnBwdRegs& r) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.sc[i] = __ldg(b.scale + c8 * 8 + i);
+    r.sh[i] = __ldg(b.shift + c8 * 8 + i);
+    r.mu[i] = __ldg(b.mean + c8 * 8 + i);
+    r.is[i] = __ldg(b.invstd + c8 * 8 + i);
+    r.a1[i] = 0.f;
+    r.a2[i] = 0.f;
+  }
+}
+// dA8: the eight gradient values AS STORED (bf16-rounded), so the sums match what the apply pass will read back
+__device__ __forceinline__ void bnbwd_accumulate(BnBwdRegs& r, const uint4& y8, const uint4& dA8) {
+  float fy[8], fd[8];
+  unpack8(y8, fy);
+  unpack8(dA8, fd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = fmaf(fy[i], r.sc[i], r.sh[i]) > 0.f ? fd[i] : 0.f;
+    r.a1[i] += g;
+    r.a2[i] = fmaf(g, (fy[i] - r.mu[i]) * r.is[i], r.a2[i]);
+  }
+}
+// block reduction (thread t holds channel group t % C8) + one atomicAdd per channel; red: 2 * 2048 floats of shared memory
+__device__ __forceinline__ void bnbwd_flush(const BnBwdStats& b, const BnBwdRegs& r, int C8, float* red) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 8 + i] = r.a1[i];
+    red[2048 + threadIdx.x * 8 + i] = r.a2[i];
+  }
+  __syncthreads();
+  const int ppb = 256 / C8;
+  for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+    float x = 0.f, z = 0.f;
+    for (int j = 0; j < ppb; ++j) {
+      x += red[(j * C8 + c / 8) * 8 + (c & 7)];
+      z += red[2048 + (j * C8 + c / 8) * 8 + (c & 7)];
+    }
+    atomicAdd(b.s1 + c, x);
+    atomicAdd(b.s2 + c, z);
+  }
+}
+
 // Max-pool backward merged with the skip connection's other gradient:
 // dA[b,h,w,c] = (d_skip ? d_skip[b,h,w,c] : 0) + (pixel is the FIRST maximum of its 2x2 window ? dP[b,h/2,w/2,c] : 0)
 __global__ void __launch_bounds__(256)
 maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip,
                        int skip_pitch8 /* uint4 per pixel of d_skip (>= C8: it may be the first half of a concat gradient) */,
-                       int B, int H, int W, int C8, uint4* __restrict__ dA) {
+                       int B, int H, int W, int C8, uint4* __restrict__ dA, const BnBwdStats bn) {
   pdl_enter();
+  extern __shared__ float red[];   // 2 * 2048 floats when bn.y != null (C8 must then divide 256)
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
+  BnBwdRegs br;
+  if (bn.y != nullptr) bnbwd_init(bn, threadIdx.x % C8, br);   // the grid stride is a multiple of C8: the channel group is fixed
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = i % C8;
@@ -321,8 +382,13 @@ maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dA[base + off[k]] = pack8(o[k]);
+    for (int k = 0; k < 4; ++k) {
+      const uint4 pk = pack8(o[k]);
+      dA[base + off[k]] = pk;
+      if (bn.y != nullptr) bnbwd_accumulate(br, __ldg(bn.y + base + off[k]), pk);
+    }
   }
+  if (bn.y != nullptr) bnbwd_flush(bn, br, C8, red);
 }
 
 // Head forward in training (README.md:1481): logits[p] = bias + sum_c a[p][c] * w[c]; 8 lanes share one pixel.
@@ -354,9 +420,9 @@ head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, 
 // Head backward: dA[p][c] = dz[p] * w[c] (bf16);  dw[c] += sum_p dz[p] * a[p][c];  db += sum_p dz[p]
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
-                uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b) {
+                uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b, const BnBwdStats bn) {
   pdl_enter();
-  extern __shared__ float red[];
+  extern __shared__ float red[];   // (2048 + 256) floats; 2 * 2048 when bn.y != null
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
   const int ppb = 256 / C8;
@@ -364,6 +430,8 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
 #pragma unroll
   for (int i = 0; i < 8; ++i) wv[i] = w[cl * 8 + i];
   float bsum = 0.f;
+  BnBwdRegs br;
+  if (bn.y != nullptr) bnbwd_init(bn, cl, br);
   for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
     const float g = __ldg(dz + p);
     float fa[8], o[8];
@@ -373,7 +441,9 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
       acc[i] = fmaf(g, fa[i], acc[i]);
       o[i] = g * wv[i];
     }
-    dA[p * C8 + cl] = pack8(o);
+    const uint4 pk = pack8(o);
+    dA[p * C8 + cl] = pk;
+    if (bn.y != nullptr) bnbwd_accumulate(br, __ldg(bn.y + p * C8 + cl), pk);
     if (cl == 0) bsum += g;
   }
 #pragma unroll
@@ -389,6 +459,10 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
     float s = 0.f;
     for (int j = 0; j < 256; ++j) s += red[2048 + j];
     grad_add(route, off_b, s);
+  }
+  if (bn.y != nullptr) {
+    __syncthreads();   // red is reused
+    bnbwd_flush(bn, br, C8, red);
   }
 }
 
