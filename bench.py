@@ -316,6 +316,7 @@ def main():
                     help="network input size; 480 640 = BASELINE.json configs[4] (camera resolution, use --batch 16 --chunk 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="infer mode: skip the fp32-class plan's throughput line")
+    ap.add_argument("--no-cfg5", action="store_true", help="infer mode: skip the 480x640 (BASELINE.json configs[4]) secondary measurement")
     ap.add_argument("--layers-out", default=None, help="write the per-kernel profile table to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -405,6 +406,22 @@ def main():
 
     def step_host():
         model.infer_host(frames_host, threshold=0.5, swap_rb=True, size=(H, W), mask_out=mask_host)
+
+    # pure-write ceiling of this GPU (a kernel that only writes cannot reach the copy bandwidth of MEASURED_PEAKS): a 2 GiB
+    # cudaMemset, best of 5 after a warm-up, taken BEFORE the long loops (boost clocks, like the per-kernel event timings)
+    fill_buf = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+    fill_buf.zero_()
+    torch.cuda.synchronize()
+    fill_ms = 1e30
+    for _ in range(5):
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe0.record()
+        fill_buf.zero_()
+        fe1.record()
+        torch.cuda.synchronize()
+        fill_ms = min(fill_ms, fe0.elapsed_time(fe1))
+    write_peak = fill_buf.numel() * 2 / (fill_ms / 1e3) / 1e9
+    del fill_buf
 
     for _ in range(args.warmup):
         step_device()
@@ -507,11 +524,6 @@ def main():
     # bandwidth-bound kernels: algorithmic bytes / CUDA-event time against the measured copy bandwidth (MEASURED_PEAKS hbm_gbs:
     # a copy, half reads half writes) and, for the write-dominated ones, their write rate against this GPU's pure-write
     # ceiling measured here (a 2 GiB cudaMemset, best of 3: ~3.9 TB/s on B200 - a kernel that only writes cannot reach the copy figure)
-    fill_buf = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
-    fill_ms = time_kernel(lambda: fill_buf.zero_(), reps=3)
-    write_peak = fill_buf.numel() * 2 / (fill_ms / 1e3) / 1e9
-    del fill_buf
-
     def hbm_row(name, rd, wr, ms_, note):
         gbs = (rd + wr) / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
         wgbs = wr / (ms_ / 1e3) / 1e9 if ms_ > 0 else 0.0
@@ -522,7 +534,7 @@ def main():
                    f"{nb} frames: reads 3*{Hs}*{Ws} B uint8, writes {H}*{W}*8 B NHWC4 bf16 per frame "
                    f"(algorithmic 3-channel output would be {H * W * 6} B)")]
     if (Hs, Ws) == (H, W) == (224, 224):
-        ncam = min(64, nb)
+        ncam = nb
         cam_dev = torch.randint(0, 256, (ncam, 480, 640, 3), dtype=torch.uint8, device=dev)
         cam_ms = time_kernel(lambda: U.preprocess_u8(cam_dev, size=(H, W), swap_rb=True))
         hbm.append(hbm_row("preprocess_u8_kernel (480x640 -> 224x224, cv2-exact bilinear)", ncam * 3 * 480 * 640, ncam * H * W * 8, cam_ms,
@@ -548,7 +560,7 @@ def main():
                 "ms_per_pass_burst": dom["ms_burst"], "frames_per_pass": nb,
                 "other_kernels": {"conv_halo2_kernel<64>": halo64, "conv_halo2_kernel<128>": halo128, "all_tensor_core_convs": allconv},
                 "hbm": hbm, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_write_ceiling_gbs": write_peak,
-                "hbm_write_ceiling_how": "2 GiB cudaMemset on this GPU inside this run, best of 3, CUDA events",
+                "hbm_write_ceiling_how": "2 GiB cudaMemset on this GPU at the start of this run, best of 5, CUDA events",
                 "whole_net_frac_of_peak": (value / world) * flops_per_frame / 1e12 / peaks["bf16_sustained"]}
     if args.layers_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
@@ -599,6 +611,33 @@ def main():
                              "how": "UB_PRECISION_FP32 plan: split-bf16 (hi + lo) activations and weights, three tcgen05 K passes per product"}
         model.b200_precision, model.b200_chunk = "bf16", args.chunk
         del f32_frames
+    if (H, W) == (224, 224) and not args.no_cfg5:
+        # BASELINE.json configs[4]: the default-width U-Net at camera resolution (480x640 network input), batch 128 over 8 GPUs =
+        # 16 frames per GPU; sources 960x1280 (the 2x down-scale of SURVEY.md 8(d) config 5: cv2 computes an exact 2x2
+        # decimation as INTER_AREA) and 480x640 (resize = identity). Same kernels, different tensor maps.
+        model._engines.clear()
+        torch.cuda.empty_cache()
+        model.b200_chunk = 16
+        cfg5 = {}
+        for tag, (hs5, ws5) in (("src960x1280", (960, 1280)), ("src480x640", (480, 640))):
+            f5 = torch.randint(0, 256, (16, hs5, ws5, 3), dtype=torch.uint8, device=dev)
+
+            def step5():
+                model.predict_mask(f5, threshold=0.5, swap_rb=True, size=(480, 640), want=("mask",))
+
+            for _ in range(3):
+                step5()
+            n5 = max(5, args.steps // 2)
+            ms5 = timed(step5, n5)
+            fps5 = world * 16 * n5 / (ms5 / 1e3)
+            cfg5[tag] = {"value": fps5, "unit": UNIT, "ms_per_step": ms5 / n5,
+                         "frac_of_sustained_bf16_peak": fps5 / world * FLOPS_PER_FRAME * (480 * 640) / (224 * 224) / 1e12 / peaks["bf16_sustained"]}
+            del f5
+        cfg5["config"] = (f"U-Net 480x640 bf16 inference, features {FEATURES}, 16 frames/GPU x {world} GPUs "
+                          "(BASELINE.json configs[4]: batch 128 on 8 GPUs), fused resize/normalise preprocess + mask threshold")
+        cfg5["flops_per_frame"] = FLOPS_PER_FRAME * (480 * 640) / (224 * 224)
+        line["config5_480x640"] = cfg5
+        model.b200_chunk = args.chunk
     if not args.no_train:
         del frames_dev
         model._engines.clear()

@@ -120,8 +120,13 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad2" (default 1)    CTA-pair weight-gradient kernel for Cout >= 128 (read when a trainer / wgrad call is set up)
  *   "wgrad_stream" (default 1) backward: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
  *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
- *   "bwd_fuse" (default 1)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
- *                           incoming gradient where that pass is an elementwise kernel (head / max-pool backward)
+ *   "bwd_fuse" (default 0)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
+ *                           incoming gradient where that pass is an elementwise kernel (head / max-pool backward);
+ *                           measured on B200: 19.15 vs 19.07 ms/step, i.e. no gain (the producers slow down by what the
+ *                           five saved reduction launches cost), so it is off
+ *   "stem_wide" (default 0) tensor-core stem on 4 x 32 pixel tiles (one contiguous 4 KB output row per TMA store) instead
+ *                           of 16 x 8; bit-identical, measured +0.3 % (noise): the stem is bound by the write rate, not by
+ *                           the store pattern
  * All paths are hand-written sm_100a kernels; the switches exist for A/B measurement and tests. */
 int unet_b200_set_option(const char* name, int value);
 
@@ -210,8 +215,10 @@ int unet_b200_maxpool2x2(const void* x_dev, int B, int H, int W, int C, void* y_
  * Parameters and gradients are FLAT fp32 device arrays in model.parameters() order (registration order of
  * README.md:1427-1447: encoder_blocks.i.{0.weight,1.weight,1.bias,3.weight,4.weight,4.bias}, decoder_blocks.2j.{weight,
  * bias}, decoder_blocks.2j+1.{...}, bottleneck.{...}, output.{weight,bias}); tensor i starts at
- * trainer_tensor_offset(i) and the array holds trainer_num_params() floats. Features must be powers of two in
- * [64,1024], features[0] <= 128; batch must give every level's 128-pixel box a multiple of 16 rows. */
+ * trainer_tensor_offset(i) and the array holds trainer_num_params() floats. Features must be multiples of 32 whose 64-aligned
+ * width is a power of two in [64,1024] (32 -> stored zero-extended to 64, as in the inference plan: the deployed topology
+ * [32,64,128] trains; parameters and gradients keep the reference's shapes), features[0] in {32,64,128}; out_channels == 1;
+ * batch must give every level's 128-pixel box a multiple of 16 rows. */
 typedef struct unet_b200_trainer unet_b200_trainer;
 int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, int in_channels, int out_channels,
                              const int* features, int levels);

@@ -211,7 +211,8 @@ def make_train_pair(U, feats, seed=0, gain=10.0):
     return ref, net.cuda().train()
 
 
-@pytest.mark.parametrize("feats,H,W,B", [([64, 128], 32, 48, 4), ([64, 128, 256, 512], 64, 64, 8)])
+@pytest.mark.parametrize("feats,H,W,B", [([64, 128], 32, 48, 4), ([64, 128, 256, 512], 64, 64, 8), ([32, 64, 128], 64, 96, 4),
+                                         ([32, 64], 32, 32, 8)])
 def test_train_step_against_oracle(U, feats, H, W, B):
     """model.train(); loss = criterion(model(x), y); loss.backward() - README.md:2071-2078 - through the drop-in module
     with the oracle's own criterion, against the fp32 oracle and against the oracle with the B200 rounding points."""
@@ -312,6 +313,33 @@ def test_train_step_config4_geometry_224_batch4(U):
         assert abs(got - want) <= 2e-3 * max(1.0, abs(want))
 
 
+def test_deployed_topology_trains(U):
+    """the deployed 3-level base-32 topology UNet(features=[32,64,128]) (1,927,009 parameters)
+    trains on the B200 step: widths that are not multiples of 64 are stored zero-extended, parameters / gradients / optimizer
+    state keep the reference's (logical) shapes."""
+    ref, net = make_train_pair(U, [32, 64, 128], gain=1.0)
+    assert sum(p.numel() for p in net.parameters()) == 1927009
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 3, 64, 64, generator=g).cuda()
+    y = torch.zeros(8, 1, 64, 64)
+    y[:, :, 16:48, 24:40] = 1.0
+    y = y.cuda()
+    step = U.FusedTrainStep(net, lr=1e-3)
+    first = step.step(x, y).cpu()
+    assert step.last_grads.numel() == 1927009 and torch.isfinite(step.last_grads).all()
+    for _ in range(30):
+        last = step.step(x, y)
+    last = last.cpu()
+    assert torch.isfinite(last).all() and last[0].item() < 0.8 * first[0].item(), (first, last)
+    # eval with the trained weights matches the oracle loaded from the module's state_dict (padded channels stayed zero)
+    net.eval()
+    ref.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    ref.eval()
+    with torch.no_grad():
+        got, want = net(x).cpu(), ref(x.cpu())
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
 def test_bn_backward_reduction_fused_into_producers(U):
     """Option bwd_fuse: the BatchNorm-backward sums of the encoder conv1 layers / the last conv come out of the max-pool /
     head backward kernels instead of a separate reduction pass. Same sums (fp32 atomics in a different order)."""
@@ -328,7 +356,7 @@ def test_bn_backward_reduction_fused_into_producers(U):
             losses.append(step.step(x, y).cpu())
             grads.append(step.last_grads.clone())
     finally:
-        check(lib.unet_b200_set_option(b"bwd_fuse", 1))
+        check(lib.unet_b200_set_option(b"bwd_fuse", 0))
     noise = rel_l2(grads[2], grads[0])           # run-to-run spread of the same configuration
     assert rel_l2(grads[1], grads[0]) <= max(3 * noise, 2e-3), (rel_l2(grads[1], grads[0]), noise)
     assert torch.equal(losses[0], losses[1])

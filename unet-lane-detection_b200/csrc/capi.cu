@@ -55,7 +55,7 @@ struct Opts {
   int wgrad2 = 1;        // CTA-pair weight-gradient kernel for BLOCK_N >= 128
   int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
   int stem_wide = 0;     // tensor-core stem on 4 x 32 tiles (4 KB contiguous output rows per store) instead of 16 x 8
-  int bwd_fuse = 1;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient
+  int bwd_fuse = 0;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient (measured: no gain)
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;

@@ -16,6 +16,7 @@ namespace ub {
 
 struct StemWgradArgs {
   int B, H, W, Cin;
+  int lCout;             // logical output channels (<= 64): gradients of zero-extended channels are not written
   int tiles_w, tiles_h;  // 8-pixel x 16-row tiles per image
   const uint2* x;        // [B,H,W] x 4 bf16
   GradRoute route;       // gradient destination (ptx.cuh)
@@ -154,7 +155,7 @@ stem_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const StemWgradA
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
       tmem_ld_wait();
-      if (pairs > static_cast<int>(blockIdx.x)) {
+      if (pairs > static_cast<int>(blockIdx.x) && co < a.lCout) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int tp = k >> 2, ci = k & 3;
@@ -163,7 +164,7 @@ stem_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const StemWgradA
       }
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col0 + 32, v);
       tmem_ld_wait();
-      if (pairs > static_cast<int>(blockIdx.x)) {
+      if (pairs > static_cast<int>(blockIdx.x) && co < a.lCout) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // tap 8
           if (k < a.Cin) grad_add(a.route, a.off + (static_cast<long long>(co) * a.Cin + k) * 9 + 8, __uint_as_float(v[k]));

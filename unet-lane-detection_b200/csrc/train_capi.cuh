@@ -19,7 +19,8 @@
 namespace {
 
 struct TConv {
-  int H, W, C0, C1, Cout;
+  int H, W, C0, C1, Cout;       // PHYSICAL channel counts (multiples of 64; a logical width such as 32 is stored zero-extended)
+  int lC0, lC1, lCout;          // LOGICAL counts = shapes of the PyTorch parameters (0 in a memset TConv: same as physical)
   bool stem, pooled;
   uint8_t *x0, *x1;   // inputs (bf16 NHWC); stem: the trainer's copy of the network input (NHWC4)
   uint8_t *y, *a, *p; // raw conv output, relu(bn(y)), maxpool(a) (or null)
@@ -38,7 +39,9 @@ struct TConv {
 };
 
 struct TConvT {
-  int H, W, Cin, f;   // input grid
+  int H, W, Cin, f;   // input grid; PHYSICAL channels
+  int lCin, lf;       // LOGICAL channels (weight [lCin][lf][2][2], bias [lf])
+  float* bias_pad;    // fp32 [f]: the bias zero-extended to the physical width (pack job, every step)
   uint8_t *x, *y;     // input activation [B,H,W,Cin]; output up [B,2H,2W,f]
   uint8_t *dup;       // gradient w.r.t. up: channels [f,2f) of the concat gradient (pixel pitch 2f elements)
   uint8_t *dx;        // gradient w.r.t. x (= g of the producing conv)
@@ -64,6 +67,7 @@ struct unet_b200_trainer {
   long long n_params;
   std::vector<long long> tensor_off;  // parameters() order, one entry per tensor (+ total at the end)
   long long head_w_off, head_b_off;
+  float* head_w_pad;  // fp32 [physical f0]: output.weight zero-extended (pack job, every step)
   size_t ws_bytes;
   uint8_t* ws;
   uint8_t* acc;       // accumulator region zeroed every step
@@ -115,6 +119,8 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
   const size_t B = t->B;
   t->zero_bias = reinterpret_cast<float*>(bp.take(4096 * 4));
   t->jobs_dev = reinterpret_cast<ub::PackJob*>(bp.take(64 * sizeof(ub::PackJob)));
+  t->head_w_pad = reinterpret_cast<float*>(bp.take((size_t)t->convs.back().Cout * 4));
+  for (TConvT& u : t->ups) u.bias_pad = reinterpret_cast<float*>(bp.take((size_t)u.f * 4));
   t->x_in = bp.take(B * t->H * t->W * 8);
   // accumulators (zeroed per step): per conv sum, sumsq (double) + s1, s2 (float)
   t->acc = reinterpret_cast<uint8_t*>(base + bp.off);
@@ -251,11 +257,20 @@ int wgrad_geometry(ub::WgradArgs& a, int B, int H, int W, int Cin, int Cout, int
   if (taps == 9 && Cin == 64) {
     a.pair_taps = 1;
     a.m_tiles = 5;
+  } else if (Cin == 64) {
+    // no taps to pair (ConvT quads read different dy views): the 128-row tile holds the 64 channels twice, the second copy
+    // is dropped in the epilogue - half the tensor work is wasted on what is a tiny layer (the deployed topology's last ConvT)
+    a.pair_taps = 0;
+    a.dup_rows = 1;
+    a.m_tiles = 1;
   } else {
     if (Cin % 128 != 0) return fail(UB_ERR_ARG, "wgrad: Cin=%d must be 64 or a multiple of 128", Cin);
     a.pair_taps = 0;
     a.m_tiles = Cin / 128;
   }
+  a.lc0 = Cin;        // callers with zero-extended tensors overwrite these
+  a.lc1 = 0;
+  a.lcout = Cout;
   a.rt_total = (a.pair_taps ? 1 : taps) * a.m_tiles;
   // CTA pair: two consecutive row tiles share the dy operand. For a 3x3 conv any two row tiles do (the taps shift only x);
   // the ConvT quads read dy through different views, so there both tiles must belong to the same quad (m_tiles even).
@@ -278,9 +293,13 @@ int setup_conv_wgrad(TConv& c, int B) {
   const int cin = c.C0 + c.C1;
   int rc = wgrad_geometry(c.wa, B, c.H, c.W, cin, c.Cout, 9, &c.w_bn, &c.w_grid, &c.w_pair);
   if (rc != UB_OK) return rc;
+  const int lc0 = c.lC0 > 0 ? c.lC0 : c.C0, lc1 = c.C1 > 0 ? (c.lC1 > 0 ? c.lC1 : c.C1) : 0, lcout = c.lCout > 0 ? c.lCout : c.Cout;
   c.wa.shift = 1;
   c.wa.c_split = c.C0;
-  c.wa.s_co = (long long)cin * 9;
+  c.wa.lc0 = lc0;
+  c.wa.lc1 = lc1;
+  c.wa.lcout = lcout;
+  c.wa.s_co = (long long)(lc0 + lc1) * 9;     // dW is the PyTorch tensor [lCout][lCin][3][3]
   c.wa.s_ci = 9;
   c.wa.s_tap = 1;
   rc = make_act_map(&c.wX0, c.x0, B, c.H, c.W, c.C0, c.wa.TW, c.wa.TH, c.wa.TB);
@@ -328,9 +347,13 @@ int setup_up_backward(TConvT& u, int B, size_t pitch = 0) {
   if (u.x != nullptr) {
     rc = wgrad_geometry(u.wa, B, u.H, u.W, u.Cin, u.f, 4, &u.w_bn, &u.w_grid, &u.w_pair);
     if (rc != UB_OK) return rc;
+    const int lcin = u.lCin > 0 ? u.lCin : u.Cin, lf = u.lf > 0 ? u.lf : u.f;
     u.wa.shift = 0;
     u.wa.c_split = u.Cin;
-    u.wa.s_ci = 4 * (long long)u.f;
+    u.wa.lc0 = lcin;
+    u.wa.lc1 = 0;
+    u.wa.lcout = lf;
+    u.wa.s_ci = 4 * (long long)lf;              // dW is the PyTorch tensor [lCin][lf][2][2]
     u.wa.s_co = 4;
     u.wa.s_tap = 1;
     rc = make_act_map(&u.wX, u.x, B, u.H, u.W, u.Cin, u.wa.TW, u.wa.TH, u.wa.TB);
@@ -433,6 +456,7 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   fin.running_mean = running_mean ? running_mean[bn_idx] : nullptr;
   fin.running_var = running_var ? running_var[bn_idx] : nullptr;
   fin.C = c.Cout;
+  fin.lC = c.lCout > 0 ? c.lCout : c.Cout;
   ub_launch(ub::bn_finalize_kernel, (c.Cout + 127) / 128, 128, 0, st, fin);
   UB_CUDA(cudaGetLastError());
   if (c.pooled) {
@@ -466,7 +490,7 @@ int conv_bn_backward(const TConv& c, int B, float* s1, float* s2, const ub::Grad
   const size_t n8 = npix * C8;
   ub_launch(ub::bn_relu_bwd_apply_kernel, grid_for(n8, 256), 256, 0, st, g4, y4, c.scale, c.shift, c.mean, c.invstd, s1, s2,
                                                                   1.f / (float)npix, n8, C8, reinterpret_cast<uint4*>(c.g), route,
-                                                                  off_gamma, off_beta);
+                                                                  off_gamma, off_beta, c.lCout > 0 ? c.lCout : c.Cout);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -480,6 +504,7 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
     sa.H = c.H;
     sa.W = c.W;
     sa.Cin = c.C0;
+    sa.lCout = c.lCout > 0 ? c.lCout : c.Cout;
     sa.tiles_w = (c.W + 7) / 8;
     sa.tiles_h = (c.H + 15) / 16;
     sa.x = reinterpret_cast<const uint2*>(c.x0);
@@ -546,7 +571,7 @@ int up_wgrad_launch(const TConvT& u, int B, int pitch8, const ub::GradRoute& rou
   const int C8 = u.f / 8;
   if (off_b >= 0) {
     ub_launch(ub::chan_sum_kernel, chan_grid(npix_up, C8), 256, 2048 * 4, st, reinterpret_cast<const uint4*>(u.dup), pitch8, npix_up, C8,
-                                                                       route, off_b);
+                                                                       route, off_b, u.lf > 0 ? u.lf : u.f);
     UB_CUDA(cudaGetLastError());
   }
   ub::WgradArgs wa = u.wa;
@@ -603,12 +628,21 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   if (H % (1 << levels) != 0 || W % (1 << levels) != 0) {
     return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
   }
+  // Logical widths (the PyTorch parameter shapes) are multiples of 32; tensors are stored with 64-aligned PHYSICAL channel counts
+  // whose extra channels are exact zeros (zero weights; BatchNorm scale = shift = 0 there), as in the inference plan. The
+  // per-channel kernels need the physical widths to be powers of two.
+  int fp[UB_MAX_LEVELS];
   for (int i = 0; i < levels; ++i) {
-    if (!pow2_times_64(features[i]) || features[i] > 1024) {
-      return fail(UB_ERR_ARG, "training needs features[%d]=%d in {64,128,256,512,1024}", i, features[i]);
+    fp[i] = (features[i] + 63) / 64 * 64;
+    if (features[i] <= 0 || features[i] % 32 != 0 || !pow2_times_64(fp[i]) || fp[i] > 1024) {
+      return fail(UB_ERR_ARG, "training needs features[%d]=%d to be a multiple of 32 whose 64-aligned width is in {64,128,256,512,1024}",
+                  i, features[i]);
     }
   }
-  if (features[0] > 128) return fail(UB_ERR_ARG, "training needs features[0] <= 128 (stem weight gradient)");
+  if (fp[0] > 128) return fail(UB_ERR_ARG, "training needs features[0] <= 128 (stem weight gradient)");
+  if (fp[0] == 128 && features[0] != 128) return fail(UB_ERR_ARG, "training needs features[0] in {32, 64, 128}");
+  const int lbott = 2 * features[levels - 1], pbott = (lbott + 63) / 64 * 64;
+  if (!pow2_times_64(pbott)) return fail(UB_ERR_ARG, "bottleneck width %d not supported", lbott);
   unet_b200_trainer* t = new (std::nothrow) unet_b200_trainer();
   if (t == nullptr) return fail(UB_ERR_ARG, "out of host memory");
   t->B = batch;
@@ -621,7 +655,7 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   t->opt = g_opts;
   for (int i = 0; i < levels; ++i) t->feat[i] = features[i];
 
-  auto mk = [&](int h, int w, int c0, int c1, int cout, bool stem, bool pooled) {
+  auto mk = [&](int h, int w, int c0, int c1, int cout, int lc0, int lc1, int lcout, bool stem, bool pooled) {
     TConv c;
     memset(&c, 0, sizeof(c));
     c.H = h;
@@ -629,40 +663,48 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
     c.C0 = c0;
     c.C1 = c1;
     c.Cout = cout;
+    c.lC0 = lc0;
+    c.lC1 = lc1;
+    c.lCout = lcout;
     c.stem = stem;
     c.pooled = pooled;
     t->convs.push_back(c);
   };
-  int cin = in_channels;
+  int cin = in_channels, lcin = in_channels;
   for (int i = 0; i < levels; ++i) {
-    const int h = H >> i, w = W >> i, f = features[i];
-    mk(h, w, cin, 0, f, i == 0, false);
-    mk(h, w, f, 0, f, false, true);
+    const int h = H >> i, w = W >> i, f = fp[i], lf = features[i];
+    mk(h, w, cin, 0, f, lcin, 0, lf, i == 0, false);
+    mk(h, w, f, 0, f, lf, 0, lf, false, true);
     cin = f;
+    lcin = lf;
   }
   {
-    const int h = H >> levels, w = W >> levels, f = 2 * features[levels - 1];
-    mk(h, w, cin, 0, f, false, false);
-    mk(h, w, f, 0, f, false, false);
-    cin = f;
+    const int h = H >> levels, w = W >> levels;
+    mk(h, w, cin, 0, pbott, lcin, 0, lbott, false, false);
+    mk(h, w, pbott, 0, pbott, lbott, 0, lbott, false, false);
+    cin = pbott;
+    lcin = lbott;
   }
   for (int j = 0; j < levels; ++j) {
     const int i = levels - 1 - j;
-    const int h = H >> i, w = W >> i, f = features[i];
+    const int h = H >> i, w = W >> i, f = fp[i], lf = features[i];
     TConvT u;
     memset(&u, 0, sizeof(u));
     u.H = h / 2;
     u.W = w / 2;
     u.Cin = cin;
     u.f = f;
-    if (cin != 2 * f) {
+    u.lCin = lcin;
+    u.lf = lf;
+    if (lcin != 2 * lf) {
       delete t;
-      return fail(UB_ERR_ARG, "decoder level %d: ConvT input channels %d != 2*%d", j, cin, f);
+      return fail(UB_ERR_ARG, "decoder level %d: ConvT input channels %d != 2*%d", j, lcin, lf);
     }
     t->ups.push_back(u);
-    mk(h, w, f, f, f, false, false);
-    mk(h, w, f, 0, f, false, false);
+    mk(h, w, f, f, f, lf, lf, lf, false, false);
+    mk(h, w, f, 0, f, lf, 0, lf, false, false);
     cin = f;
+    lcin = lf;
   }
   // BatchNorm-backward sums fused into the producer of the incoming gradient where that producer is an elementwise kernel:
   // the encoder conv1 layers (max-pool backward) and the last conv (head backward)
@@ -679,26 +721,26 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   }
   long long off = 0;
   auto conv_params = [&](TConv& c) {
-    const long long cn = c.C0 + c.C1;
+    const long long cn = c.lC0 + c.lC1;     // parameter shapes are the LOGICAL ones
     c.w_off = off;
     t->tensor_off.push_back(off);
-    off += (long long)c.Cout * cn * 9;
+    off += (long long)c.lCout * cn * 9;
     c.gamma_off = off;
     t->tensor_off.push_back(off);
-    off += c.Cout;
+    off += c.lCout;
     c.beta_off = off;
     t->tensor_off.push_back(off);
-    off += c.Cout;
+    off += c.lCout;
   };
   for (int i = 0; i < 2 * levels; ++i) conv_params(t->convs[i]);
   for (int j = 0; j < levels; ++j) {
     TConvT& u = t->ups[j];
     u.w_off = off;
     t->tensor_off.push_back(off);
-    off += (long long)u.Cin * u.f * 4;
+    off += (long long)u.lCin * u.lf * 4;
     u.b_off = off;
     t->tensor_off.push_back(off);
-    off += u.f;
+    off += u.lf;
     conv_params(t->convs[2 * levels + 2 + 2 * j]);
     conv_params(t->convs[2 * levels + 3 + 2 * j]);
   }
@@ -751,11 +793,16 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
   {
     std::vector<ub::PackJob> jobs;
     int blocks = 0;
-    auto add = [&](int kind, int Cout, int Cin, long long w_off, uint8_t* wp, uint8_t* wd, size_t elems) {
+    auto add = [&](int kind, int Cout, int C0, int C1, int lCout, int lC0, int lC1, long long w_off, void* wp, void* wd,
+                   size_t elems) {
       ub::PackJob j;
       j.kind = kind;
       j.Cout = Cout;
-      j.Cin = Cin;
+      j.C0 = C0;
+      j.C1 = C1;
+      j.lCout = lCout;
+      j.lC0 = lC0;
+      j.lC1 = lC1;
       j.block0 = blocks;
       j.w_off = w_off;
       j.wp = reinterpret_cast<__nv_bfloat16*>(wp);
@@ -765,12 +812,16 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
     };
     for (TConv& c : t->convs) {
       if (c.stem && c.Cout == 64) {
-        add(2, c.Cout, c.C0, c.w_off, c.wp, nullptr, (size_t)c.Cout * 64);
+        add(2, c.Cout, c.C0, 0, c.lCout, c.C0, 0, c.w_off, c.wp, nullptr, (size_t)c.Cout * 64);
       } else if (!c.stem) {
-        add(0, c.Cout, c.C0 + c.C1, c.w_off, c.wp, c.wd, (size_t)c.Cout * 9 * (c.C0 + c.C1));
+        add(0, c.Cout, c.C0, c.C1, c.lCout, c.lC0, c.lC1, c.w_off, c.wp, c.wd, (size_t)c.Cout * 9 * (c.C0 + c.C1));
       }
     }
-    for (TConvT& u : t->ups) add(1, u.f, u.Cin, u.w_off, u.wp, u.wd, (size_t)4 * u.f * u.Cin);
+    for (TConvT& u : t->ups) {
+      add(1, u.f, u.Cin, 0, u.lf, u.lCin, 0, u.w_off, u.wp, u.wd, (size_t)4 * u.f * u.Cin);
+      add(3, u.f, 0, 0, u.lf, 0, 0, u.b_off, u.bias_pad, nullptr, (size_t)u.f);                 // bias, zero-extended
+    }
+    add(3, t->convs.back().Cout, 0, 0, t->feat[0], 0, 0, t->head_w_off, t->head_w_pad, nullptr, (size_t)t->convs.back().Cout);
     if (jobs.size() > 64) return fail(UB_ERR_ARG, "too many weight tensors for the pack job table");
     t->n_jobs = (int)jobs.size();
     t->pack_blocks = blocks;
@@ -805,14 +856,14 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
       rc = trainer_conv_forward(t, t->convs[id], id, params, running_mean, running_var, momentum, eps, st);
     } else {
       TConvT& u = t->ups[-id - 1];
-      rc = conv_layer_launch(u.fwd, B, B, params + u.b_off, u.y, nullptr, st);
+      rc = conv_layer_launch(u.fwd, B, B, u.bias_pad, u.y, nullptr, st);
     }
     if (rc != UB_OK) return rc;
   }
   const TConv& last = t->convs.back();
   const size_t npix = (size_t)B * last.H * last.W;
   ub_launch(ub::head_fwd_train_kernel, grid_for(npix * 8, 256), 256, 0, st, reinterpret_cast<const uint4*>(last.a),
-                                                                     params + t->head_w_off, params + t->head_b_off, npix,
+                                                                     t->head_w_pad, params + t->head_b_off, npix,
                                                                      last.Cout / 8, logits);
   UB_CUDA(cudaGetLastError());
   t->fwd_done = true;
@@ -869,8 +920,8 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
     ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
-        reinterpret_cast<const uint4*>(last.a), dlogits, params + t->head_w_off, npix, C8, reinterpret_cast<uint4*>(last.g), route,
-        t->head_w_off, t->head_b_off, bn_stats_of(last));
+        reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
+        t->head_w_off, t->head_b_off, bn_stats_of(last), t->feat[0]);
     UB_CUDA(cudaGetLastError());
   } else {
     if (t->bwd_stage != stage - 1) return fail(UB_ERR_STATE, "backward stages must run in order (got %d after %d)", stage, t->bwd_stage);
@@ -1180,7 +1231,7 @@ int unet_b200_convT2x2_wgrad(const void* x, int Cin, const void* dup, int dup_pi
   if (dbias != nullptr) {
     const size_t npix_up = (size_t)B * 4 * H * W;
     ub_launch(ub::chan_sum_kernel, chan_grid(npix_up, f / 8), 256, 2048 * 4, st, reinterpret_cast<const uint4*>(u.dup), dup_pitch / 8,
-                                                                          npix_up, f / 8, ub::GradRoute{nullptr, dbias, 0u}, 0);
+                                                                          npix_up, f / 8, ub::GradRoute{nullptr, dbias, 0u}, 0, f);
     UB_CUDA(cudaGetLastError());
   }
   return up_wgrad_launch(u, B, dup_pitch / 8, ub::GradRoute{nullptr, dw, 0u}, 0, -1, st);
@@ -1241,6 +1292,7 @@ int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* 
   fin.running_mean = running_mean;
   fin.running_var = running_var;
   fin.C = C;
+  fin.lC = C;
   ub_launch(ub::bn_finalize_kernel, (C + 127) / 128, 128, 0, st, fin);
   UB_CUDA(cudaGetLastError());
   if (pool != nullptr) {

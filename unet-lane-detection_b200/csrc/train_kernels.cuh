@@ -70,12 +70,21 @@ struct BnFin {
   const float* beta;
   float *mean, *invstd, *scale, *shift;
   float *running_mean, *running_var;   // may be null
-  int C;
+  int C;     // physical channels of the tensor
+  int lC;    // logical channels (<= C): gamma / beta / running statistics have lC entries; the zero-extended channels beyond
+             // them get scale = shift = 0, so they stay exactly zero through BatchNorm + ReLU and its backward
 };
 __global__ void bn_finalize_kernel(const BnFin f) {
   pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= f.C) return;
+  if (c >= f.lC) {
+    f.mean[c] = 0.f;
+    f.invstd[c] = 0.f;
+    f.scale[c] = 0.f;
+    f.shift[c] = 0.f;
+    return;
+  }
   const double md = f.sum[c] / static_cast<double>(f.count);
   const double vd = f.sumsq[c] / static_cast<double>(f.count) - md * md;
   const float m = static_cast<float>(md);
@@ -238,11 +247,12 @@ bn_relu_bwd_apply_kernel(const uint4* __restrict__ dA, const uint4* __restrict__
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, const float* __restrict__ s1, const float* __restrict__ s2,
                          float inv_count, size_t n8, int C8, uint4* __restrict__ dY, GradRoute route, long long off_gamma,
-                         long long off_beta) {
+                         long long off_beta, int lC) {
   pdl_enter();
   // block 0 also publishes d gamma = sum g*xhat (s2) and d beta = sum g (s1) into the (possibly remote) flat gradient
+  // (logical channels only: gamma / beta have lC entries)
   if (blockIdx.x == 0 && route.local != nullptr) {
-    for (int ch = threadIdx.x; ch < C8 * 8; ch += blockDim.x) {
+    for (int ch = threadIdx.x; ch < lC; ch += blockDim.x) {
       grad_add(route, off_gamma + ch, s2[ch]);
       grad_add(route, off_beta + ch, s1[ch]);
     }
@@ -420,7 +430,7 @@ head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, 
 // Head backward: dA[p][c] = dz[p] * w[c] (bf16);  dw[c] += sum_p dz[p] * a[p][c];  db += sum_p dz[p]
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
-                uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b, const BnBwdStats bn) {
+                uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b, const BnBwdStats bn, int lC) {
   pdl_enter();
   extern __shared__ float red[];   // (2048 + 256) floats; 2 * 2048 when bn.y != null
   const int cl = threadIdx.x % C8;
@@ -453,7 +463,7 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
   for (int c = threadIdx.x; c < C8 * 8; c += 256) {
     float s = 0.f;
     for (int j = 0; j < ppb; ++j) s += red[(j * C8 + c / 8) * 8 + (c & 7)];
-    grad_add(route, off_w + c, s);
+    if (c < lC) grad_add(route, off_w + c, s);      // output.weight has lC (logical) entries
   }
   if (threadIdx.x == 0) {
     float s = 0.f;
@@ -769,34 +779,48 @@ __global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, int Cin, in
 // transposed dgrad layout wd[ci][8-tap][co] from ONE read of w; kind 1: ConvT -> wp[(quad,co)][ci] and wd[ci][(quad,co)];
 // kind 2: tensor-core stem -> wp[co][k = tap*4+ci] (zero padded to 64).
 struct PackJob {
-  int kind, Cout, Cin, block0;     // block0: first block of this job (jobs are sorted by it)
+  int kind, block0;                // block0: first block of this job (jobs are sorted by it)
+  int Cout, C0, C1;                // PHYSICAL channel counts of the operand copies (conv: Cin = C0 + C1 from two sources)
+  int lCout, lC0, lC1;             // LOGICAL counts of the fp32 master tensor; physical channels beyond them are zero-filled
   long long w_off;                 // offset of the fp32 master tensor in the flat parameter buffer
-  __nv_bfloat16* wp;
+  __nv_bfloat16* wp;               // forward layout (kind 3: a float* - the zero-extended fp32 copy)
   __nv_bfloat16* wd;               // null: no dgrad copy (first layer)
 };
 constexpr int PACK_ELEMS_PER_BLOCK = 256 * 8;
 
+// kind 0: conv 3x3 -> forward layout wp[co][tap][c] AND the rotated / transposed dgrad layout wd[c][8-tap][co] from ONE read
+// of w; kind 1: ConvT -> wp[(quad,co)][ci] and wd[ci][(quad,co)]; kind 2: tensor-core stem -> wp[co][k = tap*4+ci] (zero padded
+// to 64); kind 3: fp32 vector (ConvT bias, head weights) zero-extended from lCout to Cout entries.
 __global__ void __launch_bounds__(256)
 pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs) {
   pdl_enter();
   int j = 0;
-  while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].block0) ++j;   // <= 23 jobs
+  while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].block0) ++j;   // <= 32 jobs
   const PackJob jb = jobs[j];
   const float* w = params + jb.w_off;
   const int i0 = (static_cast<int>(blockIdx.x) - jb.block0) * PACK_ELEMS_PER_BLOCK + threadIdx.x;
   if (jb.kind == 0) {
-    const int total = jb.Cout * 9 * jb.Cin;
+    const int Cin = jb.C0 + jb.C1, lCin = jb.lC0 + jb.lC1;
+    const int total = jb.Cout * 9 * Cin;
 #pragma unroll 1
     for (int i = i0; i < total && i < i0 + PACK_ELEMS_PER_BLOCK; i += 256) {
-      const int ci = i % jb.Cin;
-      const int tap = (i / jb.Cin) % 9;
-      const int co = i / (9 * jb.Cin);
-      const __nv_bfloat16 v = __float2bfloat16_rn(w[(static_cast<size_t>(co) * jb.Cin + ci) * 9 + tap]);
+      const int cp = i % Cin;
+      const int tap = (i / Cin) % 9;
+      const int co = i / (9 * Cin);
+      int ci = -1;                      // physical channel of cat(x0, x1) -> logical input channel (or none)
+      if (cp < jb.C0) {
+        if (cp < jb.lC0) ci = cp;
+      } else if (cp - jb.C0 < jb.lC1) {
+        ci = jb.lC0 + (cp - jb.C0);
+      }
+      float f = 0.f;
+      if (co < jb.lCout && ci >= 0) f = w[(static_cast<size_t>(co) * lCin + ci) * 9 + tap];
+      const __nv_bfloat16 v = __float2bfloat16_rn(f);
       jb.wp[i] = v;
-      if (jb.wd != nullptr) jb.wd[(static_cast<size_t>(ci) * 9 + (8 - tap)) * jb.Cout + co] = v;
+      if (jb.wd != nullptr) jb.wd[(static_cast<size_t>(cp) * 9 + (8 - tap)) * jb.Cout + co] = v;
     }
   } else if (jb.kind == 1) {
-    const int f = jb.Cout, Cin = jb.Cin;
+    const int f = jb.Cout, Cin = jb.C0, lf = jb.lCout, lCin = jb.lC0;
     const int total = 4 * f * Cin;
 #pragma unroll 1
     for (int i = i0; i < total && i < i0 + PACK_ELEMS_PER_BLOCK; i += 256) {
@@ -804,20 +828,26 @@ pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jo
       const int n = i / Cin;          // quad*f + co
       const int co = n % f;
       const int quad = n / f;
-      const __nv_bfloat16 v = __float2bfloat16_rn(w[(static_cast<size_t>(ci) * f + co) * 4 + quad]);
+      float x = 0.f;
+      if (ci < lCin && co < lf) x = w[(static_cast<size_t>(ci) * lf + co) * 4 + quad];
+      const __nv_bfloat16 v = __float2bfloat16_rn(x);
       jb.wp[i] = v;
       jb.wd[(static_cast<size_t>(ci) * 4 + quad) * f + co] = v;
     }
-  } else {
+  } else if (jb.kind == 2) {
     const int total = jb.Cout * 64;
 #pragma unroll 1
     for (int i = i0; i < total && i < i0 + PACK_ELEMS_PER_BLOCK; i += 256) {
       const int k = i % 64, co = i / 64;
       const int tap = k / 4, ci = k % 4;
       float v = 0.f;
-      if (tap < 9 && ci < jb.Cin) v = w[(static_cast<size_t>(co) * jb.Cin + ci) * 9 + tap];
+      if (tap < 9 && ci < jb.C0 && co < jb.lCout) v = w[(static_cast<size_t>(co) * jb.C0 + ci) * 9 + tap];
       jb.wp[i] = __float2bfloat16_rn(v);
     }
+  } else {
+    float* dst = reinterpret_cast<float*>(jb.wp);
+#pragma unroll 1
+    for (int i = i0; i < jb.Cout && i < i0 + PACK_ELEMS_PER_BLOCK; i += 256) dst[i] = i < jb.lCout ? w[i] : 0.f;
   }
 }
 
@@ -845,7 +875,8 @@ __global__ void unpack_convT_grad_kernel(const float* __restrict__ gp, int Cin, 
 
 // per-channel sum of a bf16 NHWC tensor (ConvT bias gradient): out[c] += sum_p x[p][c]
 __global__ void __launch_bounds__(256)
-chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, GradRoute route, long long off) {
+chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, size_t npix, int C8, GradRoute route, long long off,
+                int lC /* logical channels: the destination has lC entries */) {
   pdl_enter();
   extern __shared__ float red[];
   const int cl = threadIdx.x % C8;
@@ -864,7 +895,7 @@ chan_sum_kernel(const uint4* __restrict__ x, int pitch8 /* uint4 per pixel */, s
   for (int c = threadIdx.x; c < C8 * 8; c += 256) {
     float a = 0.f;
     for (int j = 0; j < ppb; ++j) a += red[(j * C8 + c / 8) * 8 + (c & 7)];
-    grad_add(route, off + c, a);
+    if (c < lC) grad_add(route, off + c, a);
   }
 }
 

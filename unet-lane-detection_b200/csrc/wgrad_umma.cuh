@@ -33,7 +33,11 @@ struct WgradArgs {
   int n_tiles;                    // Cout / BLOCK_N
   int ksplit;                     // CTAs sharing one output tile
   int c_split;                    // channels of x source 0 (the rest come from source 1)
-  int Cin, Cout;
+  int Cin, Cout;                  // PHYSICAL channel counts (multiples of 64)
+  int lc0, lc1, lcout;            // LOGICAL channels of x source 0 / 1 and of dy: physical channels beyond them are the exact
+                                  //    zeros of a zero-extended tensor and have no gradient slot (dW is indexed logically)
+  int dup_rows;                   // 1: Cin == 64 without tap pairing (ConvT): both 64-row blocks hold the same channels,
+                                  //    rows 64..127 are dropped
   long long s_co, s_ci, s_tap;    // dW index = co*s_co + ci*s_ci + tap*s_tap (PyTorch layouts are written directly)
   int k_mmas;                     // 16-pixel MMAs per box = box rows / 16 (8 unless TB exceeds the batch)
   int a_bytes;                    // bytes one x / dy box load delivers (box rows * 128; fewer rows when TB exceeds the batch)
@@ -144,6 +148,7 @@ __device__ __forceinline__ void wgrad_umma_body(const CUtensorMap& tmX0, const C
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
           int tap = tap_o, c = m_tile * 128 + hb * 64;
+          if (a.dup_rows) c = 0;
           if (a.pair_taps) {
             tap = m_tile * 2 + hb;
             if (tap >= a.taps) tap = a.taps - 1;  // odd tap count: the last block is a duplicate whose rows are dropped
@@ -214,6 +219,14 @@ __device__ __forceinline__ void wgrad_umma_body(const CUtensorMap& tmX0, const C
       ci = m & 63;
       live = live && tap < a.taps;
     }
+    if (a.dup_rows) live = live && m < 64;
+    // physical channel of cat(x0, x1) -> logical input channel of the weight tensor (or none: a zero-extended channel)
+    if (ci < a.c_split) {
+      live = live && ci < a.lc0;
+    } else {
+      live = live && (ci - a.c_split) < a.lc1;
+      ci = a.lc0 + (ci - a.c_split);
+    }
     const long long base = a.off + static_cast<long long>(tap) * a.s_tap + static_cast<long long>(ci) * a.s_ci;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -224,7 +237,7 @@ __device__ __forceinline__ void wgrad_umma_body(const CUtensorMap& tmX0, const C
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int co = n_tile * BLOCK_N + c * 32 + j;
-          grad_add(a.route, base + static_cast<long long>(co) * a.s_co, __uint_as_float(v[j]));
+          if (co < a.lcout) grad_add(a.route, base + static_cast<long long>(co) * a.s_co, __uint_as_float(v[j]));
         }
       }
     }
