@@ -476,15 +476,20 @@ def main():
             for a_, b_ in zip(rows, r):
                 a_["ms"] = min(a_["ms"], b_["ms"])
 
-    def time_kernel(fn, reps=5):
+    def time_kernel(fn, reps=3, inner=20):
+        """ms per call: `inner` back-to-back calls between two events (a single short kernel would mostly measure the Python
+        launch path: the GPU idles between the first event and the arrival of the launch), best of `reps`."""
+        fn()
         best = 1e30
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
             e0.record()
-            fn()
+            for _ in range(inner):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+            best = min(best, e0.elapsed_time(e1) / inner)
         return best
 
     import unet_lane_detection_b200 as U
