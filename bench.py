@@ -203,7 +203,7 @@ def run_reference(args):
 TRAIN_FLOPS_PER_SAMPLE = 3 * FLOPS_PER_FRAME  # forward + dgrad + wgrad
 
 
-def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=False, exchange="auto"):
+def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=False, exchange="auto", overlap=True):
     """BASELINE.json configs[3]: U-Net training step (BCE+Dice, AdamW), bf16 tensor-core convs, `batch` samples per GPU,
     NCCL all-reduce of the flat fp32 gradient when world > 1. Returns a dict for the JSON line."""
     import torch
@@ -214,7 +214,7 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
     x_host = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
     y_host = (torch.rand(batch, 1, 224, 224, generator=g) < 0.085).float().pin_memory()   # 8.5 % positives (README.md:2534)
     x, y = x_host.to(dev), y_host.to(dev)
-    step = U.FusedTrainStep(net, exchange=exchange)                     # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
+    step = U.FusedTrainStep(net, exchange=exchange, overlap=overlap)    # lr 1e-4, wd 1e-4, pos_weight 3 (README.md:2169-2174)
     box = {}
     check = None
     if world > 1:
@@ -268,7 +268,8 @@ def measure_train(dev, world, rank, batch, steps, warmup, timed, host_inputs=Fal
                if step.nvlink is not None else "step 1: spread of the bucket-wise all-reduced gradient across ranks / max |gradient|"),
            "params_spread_after_step1": box.get("params_spread"),
            "buckets": None if world == 1 else [[int(s_), int(a), int(b)] for s_, a, b in (step.buckets or [])],
-           "overlap": "each bucket's exchange + AdamW runs on a side stream as soon as its backward stages have finished" if world > 1 else None,
+           "overlap": None if world == 1 else ("each bucket's exchange + AdamW runs on a side stream as soon as its backward stages have finished"
+                                              if overlap else "off: one exchange after the whole backward (A/B run)"),
            "collective": "none" if world == 1 else (
                f"NCCL all-reduce(sum) per gradient bucket ({31037633 * 4 / 1e6:.0f} MB per step in total) + AdamW on the bucket" if step.exchange == "nccl" else
                "none: per gradient bucket ONE kernel sums its part over the peers' buffers (NVLink loads), applies AdamW (ZeRO-1 "
@@ -312,6 +313,7 @@ def main():
                     help="training, N > 1: gradient exchange (auto = nvlink when the ranks can map each other's memory). nvlink: one kernel = reduce-scatter by NVLink loads + sharded AdamW + "
                          "all-gather by NVLink stores; nvlink_push: gradient atomics go to the owner GPU inside the backward kernels")
     ap.add_argument("--no-train", action="store_true", help="infer mode: skip the secondary training-step measurement")
+    ap.add_argument("--no-overlap", action="store_true", help="train mode, N > 1: one gradient exchange after the whole backward (A/B)")
     ap.add_argument("--hw", nargs=2, type=int, default=[224, 224], metavar=("H", "W"),
                     help="network input size; 480 640 = BASELINE.json configs[4] (camera resolution, use --batch 16 --chunk 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -378,7 +380,7 @@ def main():
         if rank == 0:
             sampler.start()
         tr = measure_train(dev, world, rank, args.train_batch, args.steps, args.warmup, timed, host_inputs=True,
-                           exchange=args.exchange)
+                           exchange=args.exchange, overlap=not args.no_overlap)
         clocks = sampler.summary() if rank == 0 else None
         line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
