@@ -1,0 +1,39 @@
+"""Preprocess kernels alone: GB/s of the same-size copy path and of the cv2-exact tile kernel on camera frames.
+    python tools/pre_bench.py [frames]      (also the target of the ncu capture in profiles/r2_ncu_full_preprocess.txt)"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import unet_lane_detection_b200 as U  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+out = {}
+for tag, hs, ws in (("same_224x224", 224, 224), ("camera_480x640", 480, 640), ("bev_685x1055", 685, 1055), ("hd_960x1280", 960, 1280)):
+    f = torch.randint(0, 256, (n, hs, ws, 3), dtype=torch.uint8, device="cuda")
+    y = torch.empty(n, 224, 224, 4, dtype=torch.bfloat16, device="cuda")
+    from unet_lane_detection_b200._lib import check, f3, lib
+    from unet_lane_detection_b200.ops import MEAN_255, STD_255
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        check(lib.unet_b200_preprocess_u8(f.data_ptr(), n, hs, ws, ws * 3, hs * ws * 3, 224, 224, 1, f3(MEAN_255), f3(STD_255),
+                                          y.data_ptr(), None, st))
+
+    run()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 20)
+    rd, wr = n * hs * ws * 3, n * 224 * 224 * 8
+    out[tag] = {"frames": n, "us": best * 1e3, "read_mb": rd / 1e6, "write_mb": wr / 1e6, "gbs": (rd + wr) / (best / 1e3) / 1e9}
+    del f, y
+print(json.dumps(out))
