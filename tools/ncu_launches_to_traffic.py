@@ -36,7 +36,12 @@ ids = list(launches)
 starts = [i for i in ids if "preprocess" in launches[i]["name"]]
 passes = []
 for a, b in zip(starts, starts[1:] + [ids[-1] + 1]):
-    p = [launches[i] for i in ids if a <= i < b]
+    p = []
+    for i in ids:
+        if a <= i < b:
+            if "pack_" in launches[i]["name"] or "at::native" in launches[i]["name"]:
+                break            # the next plan's weight packing / a torch fill: not part of the pass
+            p.append(launches[i])
     if len(p) >= 20:
         passes.append(p)
 if not passes:

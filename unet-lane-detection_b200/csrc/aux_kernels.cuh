@@ -382,22 +382,41 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const PreArg
     }
     __syncthreads();
     // stage the rows: 16-byte chunks from the aligned-down row address (never below the allocation: it is at least 16-byte
-    // aligned); a chunk that would reach past the last byte of the last frame is read byte by byte instead
+    // aligned); a chunk that would reach past the last byte of the last frame is read byte by byte instead. The (slot, chunk)
+    // items are flattened and every thread issues EIGHT loads before it stores any of them: one load per row and thread,
+    // each followed by its dependent shared-memory store, left too few bytes in flight to cover the HBM latency
+    // (2.2 TB/s on camera frames; profiles/r2_pre_bench.json)
     const int nslots = s_nslots;
-    for (int i = 0; i < nslots; ++i) {
-      const uint8_t* rowp = frame + static_cast<size_t>(s_src[i]) * a.pitch;
-      const int off = static_cast<int>(reinterpret_cast<uintptr_t>(rowp) & 15);
-      if (threadIdx.x == 0) s_off[i] = off;      // where the row starts inside its slot
-      const uint8_t* rp = rowp - off;
-      const int chunks = (off + row_bytes + 15) >> 4;
-      uint8_t* dst = pre_smem + static_cast<size_t>(i) * pitch_s;
-      for (int c = threadIdx.x; c < chunks; c += PRE_THREADS) {
-        const uint8_t* g = rp + 16 * c;
-        if (g + 16 <= src_end) {
-          *reinterpret_cast<uint4*>(dst + 16 * c) = __ldg(reinterpret_cast<const uint4*>(g));
-        } else {
-          for (int k = 0; k < 16; ++k) dst[16 * c + k] = (g + k < src_end) ? __ldg(g + k) : 0;
+    const int chunks = (row_bytes + 30) >> 4;          // enough for any alignment of the row start; <= pitch_s / 16
+    const int items = nslots * chunks;
+    for (int base = 0; base < items; base += 8 * PRE_THREADS) {
+      uint4 v[8];
+      int dsto[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int it = base + k * PRE_THREADS + threadIdx.x;
+        dsto[k] = -1;
+        if (it < items) {
+          const int i = it / chunks, c = it - i * chunks;
+          const uint8_t* rowp = frame + static_cast<size_t>(s_src[i]) * a.pitch;
+          const int off = static_cast<int>(reinterpret_cast<uintptr_t>(rowp) & 15);
+          if (c == 0) s_off[i] = off;                  // where the row starts inside its slot
+          const uint8_t* g = rowp - off + 16 * c;
+          dsto[k] = i * pitch_s + 16 * c;
+          if (g + 16 <= src_end) {
+            v[k] = __ldg(reinterpret_cast<const uint4*>(g));
+          } else {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int q = 0; q < 16; ++q) {
+              if (g + q < src_end) w[q >> 2] |= static_cast<uint32_t>(__ldg(g + q)) << (8 * (q & 3));
+            }
+            v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (dsto[k] >= 0) *reinterpret_cast<uint4*>(pre_smem + dsto[k]) = v[k];
       }
     }
     __syncthreads();
