@@ -1326,8 +1326,10 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
   if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
   // persistent CTAs: as many as are resident at once (shared memory bound), each walks tiles of `rows` output rows
   const int tiles = batch * ((H + rows - 1) / rows);
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  int per_sm = 0;   // what the hardware really keeps resident (registers AND shared memory): a second wave of persistent CTAs
+                    // would start when the first has finished all its tiles
+  UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ub::preprocess_u8_kernel, ub::PRE_THREADS, smem));
+  per_sm = per_sm < 1 ? 1 : per_sm;
   const int resident = cur_sms() * per_sm;
   ub_launch(ub::preprocess_u8_kernel, tiles < resident ? tiles : resident, ub::PRE_THREADS, smem, static_cast<cudaStream_t>(stream), a, rows);
   UB_CUDA(cudaGetLastError());
