@@ -312,7 +312,9 @@ __device__ __forceinline__ int resize_blend(int h0, int h1, int by0, int by1) {
 //             2. a thread owns output COLUMNS (its taps stay in registers) and walks the tile's rows, four at a time so that
 //                48 shared-memory byte loads are in flight; a warp's stores of one row cover 256 contiguous bytes.
 // profiles/: one CTA per output row with byte-wide staging reached 1.04 TB/s (r1); one CTA per 8-row tile with per-tile tables
-// 0.84-1.45 TB/s; this form is the one measured in profiles/r2_*.
+// 0.84-1.45 TB/s; this form is the one measured in profiles/r2_pre_bench.json. Tried on top and dropped: three aligned 32-bit
+// shared loads + two funnel shifts per row instead of six byte loads (fewer shared-memory wavefronts, but 137 instead of
+// 119 us on 256 camera frames: the kernel is bound by instruction issue and dependent-latency chains, not by the LSU).
 constexpr int PRE_ROWS = 8;
 constexpr int PRE_THREADS = 256;
 __host__ __device__ constexpr int pre_row_pitch(int Ws) { return ((Ws * 3 + 15) / 16) * 16 + 16; }   // + head misalignment
