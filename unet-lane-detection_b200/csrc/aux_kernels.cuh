@@ -428,31 +428,16 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_u8_kernel(const Pre
       for (int r = 0; r < nrows; ++r) {
         const int4 yt = ytab[y0 + r];
         const int sl0 = s_slot[2 * r], sl1 = s_slot[2 * r + 1];
-        // The right tap is the pixel after the left one (or has weight 0 where cv2 clamps at a border), so a pixel needs the
-        // SIX contiguous bytes at 3*sx0 of each of its two rows: three aligned 32-bit loads + two funnel shifts per row
-        // instead of six byte loads (the kernel was bound by shared-memory wavefronts: 1.4 per output pixel)
-        const uint32_t a0 = static_cast<uint32_t>(sl0 * pitch_s + s_off[sl0] + xt.x);   // byte offsets into pre_smem (16-byte aligned base)
-        const uint32_t a1 = static_cast<uint32_t>(sl1 * pitch_s + s_off[sl1] + xt.x);
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(pre_smem + (a0 & ~3u));
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(pre_smem + (a1 & ~3u));
-        const uint32_t u0 = q0[0], u1 = q0[1], u2 = q0[2], v0 = q1[0], v1 = q1[1], v2 = q1[2];
-        const uint32_t lo0 = __funnelshift_r(u0, u1, (a0 & 3u) * 8);   // bytes 0..3 from the left tap's first channel
-        const uint32_t hi0 = __funnelshift_r(u1, u2, (a0 & 3u) * 8);   // bytes 4..7
-        const uint32_t lo1 = __funnelshift_r(v0, v1, (a1 & 3u) * 8);
-        const uint32_t hi1 = __funnelshift_r(v1, v2, (a1 & 3u) * 8);
-        // left tap channels: bytes 0,1,2; right tap channels: bytes 3,4,5
-        const int l0[3] = {static_cast<int>(lo0 & 255u), static_cast<int>((lo0 >> 8) & 255u), static_cast<int>((lo0 >> 16) & 255u)};
-        const int r0v[3] = {static_cast<int>(lo0 >> 24), static_cast<int>(hi0 & 255u), static_cast<int>((hi0 >> 8) & 255u)};
-        const int l1[3] = {static_cast<int>(lo1 & 255u), static_cast<int>((lo1 >> 8) & 255u), static_cast<int>((lo1 >> 16) & 255u)};
-        const int r1v[3] = {static_cast<int>(lo1 >> 24), static_cast<int>(hi1 & 255u), static_cast<int>((hi1 >> 8) & 255u)};
+        const uint8_t* r0 = pre_smem + static_cast<size_t>(sl0) * pitch_s + s_off[sl0];
+        const uint8_t* r1 = pre_smem + static_cast<size_t>(sl1) * pitch_s + s_off[sl1];
         int px[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           if (area2) {
-            px[c] = (l0[c] + r0v[c] + l1[c] + r1v[c] + 2) >> 2;
+            px[c] = (r0[xt.x + c] + r0[xt.y + c] + r1[xt.x + c] + r1[xt.y + c] + 2) >> 2;
           } else {
-            const int h0 = l0[c] * xt.z + r0v[c] * xt.w;
-            const int h1 = l1[c] * xt.z + r1v[c] * xt.w;
+            const int h0 = r0[xt.x + c] * xt.z + r0[xt.y + c] * xt.w;
+            const int h1 = r1[xt.x + c] * xt.z + r1[xt.y + c] * xt.w;
             px[c] = resize_blend(h0, h1, yt.z, yt.w);
           }
         }
