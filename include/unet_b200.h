@@ -124,6 +124,10 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *                           incoming gradient where that pass is an elementwise kernel (head / max-pool backward);
  *                           measured on B200: 19.15 vs 19.07 ms/step, i.e. no gain (the producers slow down by what the
  *                           five saved reduction launches cost), so it is off
+ *   "dgrad_fuse" (default 1) training: where a layer's incoming gradient is written by a tcgen05 dgrad kernel (13 of the 18
+ *                           BatchNorm layers of the default network), that kernel's epilogue also takes the layer's
+ *                           BatchNorm-backward sums (the y sub-box is TMA-loaded beside the staged output tile), so the
+ *                           separate reduction pass over g and y does not run
  *   "stem_wide" (default 0) tensor-core stem on 4 x 32 pixel tiles (one contiguous 4 KB output row per TMA store) instead
  *                           of 16 x 8; bit-identical, measured +0.3 % (noise): the stem is bound by the write rate, not by
  *                           the store pattern
@@ -217,7 +221,8 @@ int unet_b200_maxpool2x2(const void* x_dev, int B, int H, int W, int C, void* y_
  * bias}, decoder_blocks.2j+1.{...}, bottleneck.{...}, output.{weight,bias}); tensor i starts at
  * trainer_tensor_offset(i) and the array holds trainer_num_params() floats. Features must be multiples of 32 whose 64-aligned
  * width is a power of two in [64,1024] (32 -> stored zero-extended to 64, as in the inference plan: the deployed topology
- * [32,64,128] trains; parameters and gradients keep the reference's shapes), features[0] in {32,64,128}; out_channels == 1;
+ * [32,64,128] trains; parameters and gradients keep the reference's shapes), features[0] in {32,64,128}; out_channels in [1,8]
+ * (the reference trains 1; with more, logits / dlogits are NCHW [batch][out_channels][H][W]);
  * batch must give every level's 128-pixel box a multiple of 16 rows. */
 typedef struct unet_b200_trainer unet_b200_trainer;
 int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, int in_channels, int out_channels,
@@ -230,7 +235,7 @@ long long unet_b200_trainer_tensor_offset(const unet_b200_trainer* t, int idx); 
 /* workspace_dev: caller-owned, 1024-byte aligned, trainer_workspace_bytes() bytes. */
 int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev);
 /* UNet.forward in train mode (README.md:1460-1481 under model.train()): x bf16 NHWC4 [batch][H][W][4] -> logits fp32
- * [batch][H][W]. running_mean / running_var: HOST arrays of plan_num_convs device pointers (fp32 [C] each, plan conv
+ * [batch][H][W] (out_channels > 1: NCHW [batch][out_channels][H][W]). running_mean / running_var: HOST arrays of plan_num_convs device pointers (fp32 [C] each, plan conv
  * order) updated with `momentum` and the unbiased batch variance as nn.BatchNorm2d does; either may be NULL. */
 int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4_dev, const float* params_dev,
                             float* const* running_mean, float* const* running_var, float momentum, float eps,

@@ -313,6 +313,54 @@ def test_train_step_config4_geometry_224_batch4(U):
         assert abs(got - want) <= 2e-3 * max(1.0, abs(want))
 
 
+def test_train_step_multi_class_head(U):
+    """README.md:1447 builds Conv2d(features[0], out_channels, 1) for any out_channels (the reference trains 1): a 3-channel
+    head trains too - logits NCHW [B,3,H,W], output.weight [3,f0,1,1] / output.bias [3] gradients against the fp32 oracle,
+    through the autograd path and through the fused step (whose loss kernel sees B*3*H*W elements)."""
+    torch.manual_seed(0)
+    feats, B, H, W, OC = [64, 128], 4, 32, 48, 3
+    ref = O.UNetOracle(3, OC, feats).train()
+    O.randomize_bn_(ref, seed=1)
+    O.scale_head_(ref, 10.0)
+    emu = copy.deepcopy(ref)
+    net = U.UNet(3, OC, feats)
+    net.load_state_dict(ref.state_dict())
+    net = net.cuda().train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, H, W, generator=g)
+    y = (torch.rand(B, OC, H, W, generator=g) < 0.15).float()
+    crit = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]), smooth=1e-6)
+    out_ref = ref(x)
+    losses_ref = crit(out_ref, y)
+    losses_ref[0].backward()
+    crit(O.forward_train_bf16_emulated(emu, x), y)[0].backward()
+    out = net(x.cuda())
+    assert out.shape == (B, OC, H, W) and out.requires_grad
+    crit_gpu = O.BCEDiceLossOracle(0.5, 0.5, pos_weight=torch.tensor([3.0]).cuda(), smooth=1e-6)
+    crit_gpu(out, y.cuda())[0].backward()
+    rng = max(1.0, out_ref.abs().max().item())
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() <= 2e-2 * rng * 1.5
+    for (n, p), (_, q), (_, e) in zip(ref.named_parameters(), net.named_parameters(), emu.named_parameters()):
+        assert q.grad is not None and q.grad.shape == p.grad.shape, n
+        err, floor = rel_l2(q.grad.detach().cpu(), p.grad), rel_l2(e.grad, p.grad)
+        assert err <= 1.3 * floor + 0.02, (n, err, floor)
+    assert net.output.weight.grad.shape == (OC, feats[0], 1, 1)
+    assert rel_l2(net.output.weight.grad.cpu(), ref.output.weight.grad) <= 5e-3
+    assert rel_l2(net.output.bias.grad.cpu(), ref.output.bias.grad) <= 5e-3
+    # fused step: same gradients, the reference's three loss figures
+    net2 = U.UNet(3, OC, feats)
+    net2.load_state_dict(ref.state_dict())
+    net2 = net2.cuda().train()
+    step = U.FusedTrainStep(net2, lr=0.0, weight_decay=0.0, cuda_graph=False)
+    losses = step.step(x.cuda(), y.cuda()).cpu()
+    ga = torch.cat([q.grad.reshape(-1) for q in net.parameters()])
+    assert rel_l2(step.last_grads, ga) <= 1e-2
+    for got, want in zip(losses.tolist(), [t.item() for t in losses_ref]):
+        assert abs(got - want) <= 2e-3 * max(1.0, abs(want))
+    with pytest.raises(Exception):
+        U.UNet(3, 9, feats).cuda().train()(x.cuda())          # trainer supports up to 8 output channels
+
+
 def test_deployed_topology_trains(U):
     """the deployed 3-level base-32 topology UNet(features=[32,64,128]) (1,927,009 parameters)
     trains on the B200 step: widths that are not multiples of 64 are stored zero-extended, parameters / gradients / optimizer
@@ -337,7 +385,12 @@ def test_deployed_topology_trains(U):
     ref.eval()
     with torch.no_grad():
         got, want = net(x).cpu(), ref(x.cpu())
-    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+        emu = O.forward_bf16_emulated(ref, x.cpu())
+    # the weights of a 31-step trajectory differ from run to run (fp32 atomics), and so does the bf16 rounding noise of their
+    # eval logits: measured 0.023-0.038 at |z|max 1.6-1.8 over six runs, always within 10 % of the bf16-emulated oracle's own
+    # error (tools/deployed_err.py) - so the gate is the emulated error, not a fixed fraction of the range
+    err, floor = (got - want).abs().max().item(), (emu - want).abs().max().item()
+    assert err <= max(2e-2 * max(1.0, want.abs().max().item()), 1.25 * floor + 5e-3), (err, floor)
 
 
 def test_bn_backward_reduction_fused_into_producers(U):
@@ -357,6 +410,32 @@ def test_bn_backward_reduction_fused_into_producers(U):
             grads.append(step.last_grads.clone())
     finally:
         check(lib.unet_b200_set_option(b"bwd_fuse", 0))
+    noise = rel_l2(grads[2], grads[0])           # run-to-run spread of the same configuration
+    assert rel_l2(grads[1], grads[0]) <= max(3 * noise, 2e-3), (rel_l2(grads[1], grads[0]), noise)
+    assert torch.equal(losses[0], losses[1])
+
+
+@pytest.mark.parametrize("feats,B,H,W", [([64, 128, 256, 512], 8, 64, 64), ([64, 128], 2, 224, 224), ([32, 64, 128], 4, 64, 96)])
+def test_bn_backward_sums_in_dgrad_epilogue(U, feats, B, H, W):
+    """Option dgrad_fuse (default on): where a layer's incoming gradient is written by a tcgen05 dgrad kernel (the conv0 of every
+    block, and the conv1 below every ConvT), that kernel's epilogue takes the layer's BatchNorm-backward sums from the staged
+    output tile and a TMA-loaded y tile; without the option the separate reduction pass runs. Same sums up to the fp32
+    summation order: gradients agree within the run-to-run spread. Covers the halo<64>/<128> and per-tap kernels (pair and,
+    at batch 2 x 224^2, image-sized tiles) and zero-extended widths."""
+    from unet_lane_detection_b200._lib import check, lib
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, 3, H, W, generator=g).cuda()
+    y = (torch.rand(B, 1, H, W, generator=g) < 0.1).float().cuda()
+    grads, losses = [], []
+    try:
+        for fuse in (1, 0, 1):
+            check(lib.unet_b200_set_option(b"dgrad_fuse", fuse))
+            _, net = make_train_pair(U, feats)
+            step = U.FusedTrainStep(net, lr=0.0, weight_decay=0.0, cuda_graph=False)
+            losses.append(step.step(x, y).cpu())
+            grads.append(step.last_grads.clone())
+    finally:
+        check(lib.unet_b200_set_option(b"dgrad_fuse", 1))
     noise = rel_l2(grads[2], grads[0])           # run-to-run spread of the same configuration
     assert rel_l2(grads[1], grads[0]) <= max(3 * noise, 2e-3), (rel_l2(grads[1], grads[0]), noise)
     assert torch.equal(losses[0], losses[1])

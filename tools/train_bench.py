@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--per-launch", default=None, help="substring: list every launch of matching kernels in order")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph")
+    ap.add_argument("--timeline", default=None, help="write every kernel of the profiled step (start, duration, stream) to this JSON")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=value (unet_b200_set_option)")
     args = ap.parse_args()
     from unet_lane_detection_b200._lib import check, lib
@@ -58,6 +59,19 @@ def main():
                 k = ev.name[:90]
                 t, n = agg.get(k, (0.0, 0))
                 agg[k] = (t + ev.device_time_total if hasattr(ev, "device_time_total") else t + ev.cuda_time_total, n + 1)
+        if args.timeline:
+            import json
+            rows = []
+            for ev in prof.profiler.kineto_results.events():
+                if ev.device_type() == torch.autograd.DeviceType.CUDA:
+                    rows.append({"name": ev.name()[:60], "start_us": ev.start_ns() / 1e3, "dur_us": ev.duration_ns() / 1e3,
+                                 "stream": ev.device_resource_id()})
+            rows.sort(key=lambda r: r["start_us"])
+            t0 = rows[0]["start_us"] if rows else 0.0
+            for r in rows:
+                r["start_us"] -= t0
+            with open(args.timeline, "w") as f:
+                json.dump(rows, f)
         if args.per_launch:
             evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and args.per_launch in ev.name]
             evs.sort(key=lambda e: e.time_range.start)

@@ -56,6 +56,7 @@ struct Opts {
   int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
   int stem_wide = 0;     // tensor-core stem on 4 x 32 tiles (4 KB contiguous output rows per store) instead of 16 x 8
   int bwd_fuse = 0;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient (measured: no gain)
+  int dgrad_fuse = 1;    // training: BatchNorm-backward reduction inside the tcgen05 dgrad epilogues that write the gradient
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -237,10 +238,11 @@ int make_umma_store_maps(Layer& l, void* out, void* pool, int Bc, int cm = 1);
 
 // Shared-memory carve-up of conv_halo_kernel: prefer resident weights, then the deepest patch ring that fits.
 bool halo_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
+  const int ystg = a->bn.y != nullptr;   // fused BatchNorm-backward sums: a second set of warp-private tiles
   const int need = 3 * kc;  // weight stages (3 taps each)
   if (need <= ub::HaloCfg::MAX_B) {
     for (int as = 4; as >= 2; --as) {
-      if (ub::halo_smem_bytes(block_n, as, need, head) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, need, head, 0, ystg) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 1; a->a_stages = as; a->b_stages = need;
         return true;
       }
@@ -249,7 +251,7 @@ bool halo_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
   // streamed weights: a full kernel (3 stages) in flight first, then as many patch stages as fit
   for (int b = 3; b >= 2; --b) {
     for (int as = 3; as >= 2; --as) {
-      if (ub::halo_smem_bytes(block_n, as, b, head) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, b, head, 0, ystg) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 0; a->a_stages = as; a->b_stages = b;
         return true;
       }
@@ -311,40 +313,44 @@ int device_check() {
 
 template <int BN>
 int launch_conv_t(const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args, int slot,
-                  cudaStream_t st) {
+                  cudaStream_t st, const CUtensorMap* my) {
   const int m_tiles = args.tiles_w * args.tiles_h * args.tiles_b;
   const int sms = cur_sms();
+  const bool ystg = args.bn.y != nullptr;     // fused BatchNorm-backward sums need the y map and a second set of staging tiles
+  if (ystg && (my == nullptr || args.epi != ub::EPI_STORE || args.split)) return fail(UB_ERR_ARG, "fused BN-backward sums: bad layer");
+  const CUtensorMap& tmy = my != nullptr ? *my : mo[0];
   if (tl_opts->umma2 && m_tiles >= 2) {
     using Cfg2 = ub::ConvCfg<BN, true>;
     UB_CUDA(ensure_smem(ub::conv_umma2_kernel<BN>, AT_UMMA2 + slot, Cfg2::SMEM_LIMIT));
     ub::ConvArgs args2 = args;
-    args2.stages = Cfg2::plan_stages();
-    const int smem = Cfg2::smem_bytes(args2.stages);
+    args2.stages = Cfg2::plan_stages(ystg);
+    const int smem = Cfg2::smem_bytes(args2.stages, ystg);
     const int pair_tiles = ((m_tiles + 1) / 2) * args.n_tiles;
     const int max_pairs = sms / 2;
     const int grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);   // cluster size 2 (__cluster_dims__)
-    ub_launch(ub::conv_umma2_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
+    ub_launch(ub::conv_umma2_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], tmy, args2);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
   using Cfg = ub::ConvCfg<BN>;
   UB_CUDA(ensure_smem(ub::conv_umma_kernel<BN>, AT_UMMA + slot, Cfg::SMEM_LIMIT));
   ub::ConvArgs args2 = args;
-  args2.stages = Cfg::plan_stages();
-  const int smem = Cfg::smem_bytes(args2.stages);
+  args2.stages = Cfg::plan_stages(ystg);
+  const int smem = Cfg::smem_bytes(args2.stages, ystg);
   const int total = m_tiles * args.n_tiles;
   const int grid = total < sms ? total : sms;
-  ub_launch(ub::conv_umma_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], args2);
+  ub_launch(ub::conv_umma_kernel<BN>, grid, ub::CONV_THREADS, smem, st, ma[0], ma[1], ma[2], ma[3], w, mo[0], mo[1], mo[2], mo[3], tmy, args2);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
 // Shared-memory carve-up of the CTA-pair kernel (half-size weight tiles): resident weights first.
 bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
+  const int ystg = a->bn.y != nullptr;
   const int need = 3 * kc;
   if (need <= ub::HaloCfg::MAX_B) {
     for (int as = 4; as >= 2; --as) {
-      if (ub::halo_smem_bytes(block_n, as, need, head, 1) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, need, head, 1, ystg) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 1; a->a_stages = as; a->b_stages = need;
         return true;
       }
@@ -352,7 +358,7 @@ bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
   }
   for (int b = 6; b >= 2; --b) {
     for (int as = 4; as >= 3; --as) {
-      if (ub::halo_smem_bytes(block_n, as, b, head, 1) <= ub::HaloCfg::SMEM_LIMIT) {
+      if (ub::halo_smem_bytes(block_n, as, b, head, 1, ystg) <= ub::HaloCfg::SMEM_LIMIT) {
         a->resident = 0; a->a_stages = as; a->b_stages = b;
         return true;
       }
@@ -363,18 +369,21 @@ bool halo2_smem_plan(int block_n, int kc, int head, ub::HaloArgs* a) {
 
 template <int BN>
 int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
-                  ub::HaloArgs args, int slot, cudaStream_t st) {
+                  ub::HaloArgs args, int slot, cudaStream_t st, const CUtensorMap* my) {
   const int head = args.epi == ub::HEPI_HEAD;
+  const int ystg = args.bn.y != nullptr;
+  if (ystg && (my == nullptr || head)) return fail(UB_ERR_ARG, "fused BN-backward sums: bad layer");
+  const CUtensorMap& tmy = my != nullptr ? *my : mo;
   if (head && BN != 64) return fail(UB_ERR_ARG, "the fused head epilogue needs Cout == 64");
   const int total = args.tiles_w * args.tiles_h * args.B;
   const int sms = cur_sms();
   if (tl_opts->halo2 && total >= 2 && halo2_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
     UB_CUDA(ensure_smem(ub::conv_halo2_kernel<BN>, AT_HALO2 + slot, ub::HaloCfg::SMEM_LIMIT));
-    const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head, 1);
+    const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head, 1, ystg);
     const int pairs = (total + 1) / 2;
     const int max_pairs = sms / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)
-    ub_launch(ub::conv_halo2_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
+    ub_launch(ub::conv_halo2_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, tmy, args);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
@@ -382,19 +391,19 @@ int launch_halo_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   if (!halo_smem_plan(BN, args.kc0 + args.kc1, head, &args)) {
     return fail(UB_ERR_ARG, "no shared-memory plan for halo conv (N=%d, KC=%d)", BN, args.kc0 + args.kc1);
   }
-  const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head);
+  const int smem = ub::halo_smem_bytes(BN, args.a_stages, args.b_stages, head, 0, ystg);
   const int grid = total < sms ? total : sms;
-  ub_launch(ub::conv_halo_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, args);
+  ub_launch(ub::conv_halo_kernel<BN>, grid, ub::HALO_THREADS, smem, st, a0, a1, w, mo, tmy, args);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
 
 int launch_halo(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const CUtensorMap& mo,
-                const ub::HaloArgs& args, cudaStream_t st) {
+                const ub::HaloArgs& args, cudaStream_t st, const CUtensorMap* my = nullptr) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
-  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, args, 0, st);
-  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, args, 1, st);
+  if (block_n == 64) return launch_halo_t<64>(a0, a1, w, mo, args, 0, st, my);
+  if (block_n == 128) return launch_halo_t<128>(a0, a1, w, mo, args, 1, st, my);
   return fail(UB_ERR_ARG, "halo kernel supports Cout 64/128, got %d", block_n);
 }
 
@@ -436,13 +445,13 @@ int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x
 }
 
 int launch_conv(int block_n, const CUtensorMap* ma, const CUtensorMap& w, const CUtensorMap* mo, const ub::ConvArgs& args,
-                cudaStream_t st) {
+                cudaStream_t st, const CUtensorMap* my = nullptr) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
   switch (block_n) {
-    case 64: return launch_conv_t<64>(ma, w, mo, args, 0, st);
-    case 128: return launch_conv_t<128>(ma, w, mo, args, 1, st);
-    case 256: return launch_conv_t<256>(ma, w, mo, args, 2, st);
+    case 64: return launch_conv_t<64>(ma, w, mo, args, 0, st, my);
+    case 128: return launch_conv_t<128>(ma, w, mo, args, 1, st, my);
+    case 256: return launch_conv_t<256>(ma, w, mo, args, 2, st, my);
   }
   return fail(UB_ERR_ARG, "unsupported BLOCK_N %d", block_n);
 }
@@ -469,6 +478,8 @@ struct Layer {
   CUtensorMap mA0, mA1, mW;
   CUtensorMap mOut, mPool;  // TMA-store targets (halo layers)
   CUtensorMap mO[4];        // TMA-store targets of conv_umma_kernel: {out, pool, -, -} or the four ConvT quads
+  CUtensorMap mY;           // training backward (dgrad layers): load view of the y tensor that has the output's geometry, same box
+  int y_bytes;              //   as the output store view; bytes one such box delivers (0: no view built)
 };
 
 struct Buf {
@@ -639,6 +650,7 @@ ub::ConvArgs conv_args(const Layer& l, int batch, int batch_cap, const float* bi
   a.stat_sum = nullptr;
   a.stat_sumsq = nullptr;
   a.split = 0;
+  memset(&a.bn, 0, sizeof(a.bn));
   if (l.TB >= 4) {
     a.sub_b = l.TB / 4;
     a.sub_h = l.TH;
@@ -708,19 +720,44 @@ int conv_layer_setup(Layer& l, LayerKind kind, const void* x0, int C0, const voi
 }
 
 // Launch a layer prepared by conv_layer_setup (maps were built for batch capacity Bc).
+// bn != null (training backward): the epilogue also takes the BatchNorm-backward sums of the layer whose gradient it writes;
+// needs the y view of make_epi_y_map.
 int conv_layer_launch(const Layer& l, int batch, int Bc, const float* bias, void* y, void* pool, cudaStream_t st,
-                      double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
+                      double* stat_sum = nullptr, double* stat_sumsq = nullptr, const ub::EpiBnBwd* bn = nullptr) {
+  if (bn != nullptr && l.y_bytes == 0) return fail(UB_ERR_STATE, "fused BN-backward sums without a y view");
   if (l.halo) {
     ub::HaloArgs ha = halo_args(l, batch, bias, y, pool);
     ha.stat_sum = stat_sum;
     ha.stat_sumsq = stat_sumsq;
-    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, st);
+    if (bn != nullptr) {
+      ha.bn = *bn;
+      ha.bn.bytes = l.y_bytes;
+    }
+    return launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, ha, st, bn != nullptr ? &l.mY : nullptr);
   }
   ub::ConvArgs a = conv_args(l, batch, Bc, bias, y, pool);
   a.stat_sum = stat_sum;
   a.stat_sumsq = stat_sumsq;
+  if (bn != nullptr) {
+    a.bn = *bn;
+    a.bn.bytes = l.y_bytes;
+  }
   const CUtensorMap ma[4] = {l.mA0, l.mA1, l.mA0, l.mA0};
-  return launch_conv(l.block_n, ma, l.mW, l.mO, a, st);
+  return launch_conv(l.block_n, ma, l.mW, l.mO, a, st, bn != nullptr ? &l.mY : nullptr);
+}
+
+// Load view of `ysrc` ([Bc][H][W][Cout] bf16, the geometry of the layer's output) with the box of the output store view, for
+// the fused BatchNorm-backward sums of a dgrad layer (L_CONV, prepared by conv_layer_setup or setup_up_backward).
+int make_epi_y_map(Layer& l, const void* ysrc, int Bc) {
+  const size_t C = (size_t)l.Cout;
+  if (l.halo) {
+    l.y_bytes = 4096;
+    return make_box_map(&l.mY, ysrc, Bc, l.H, l.W, l.Cout, 8, 4);
+  }
+  const int sb = l.TB >= 4 ? l.TB / 4 : 1;
+  const int sh = l.TB >= 4 ? l.TH : (l.TB == 2 ? l.TH / 2 : l.TH / 4);
+  l.y_bytes = 128 * l.TW * sh * (sb < Bc ? sb : Bc);
+  return make_tile_store_map(&l.mY, ysrc, Bc, l.H, l.W, l.Cout, C, (size_t)l.W * C, (size_t)l.H * l.W * C, l.TW, sh, sb);
 }
 
 // Workspace layout by liveness: a layer output gets its address when the layer runs and gives it back after its last
@@ -1106,7 +1143,7 @@ int unet_b200_set_option(const char* name, int value) {
       {"halo", &g_opts.halo}, {"pdl", &g_opts.pdl}, {"halo2", &g_opts.halo2}, {"umma2", &g_opts.umma2},
       {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
-      {"stem_wide", &g_opts.stem_wide}};
+      {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;

@@ -53,6 +53,7 @@ struct HaloArgs {
   uint8_t* mask;            // [B,H,W] or null
   double* stat_sum;         // HEPI_STORE, optional (training): per-channel sum / sum of squares of the bf16 output
   double* stat_sumsq;
+  EpiBnBwd bn;              // HEPI_STORE, optional (training backward): fused BatchNorm-backward sums (epilogue.cuh); bn.y null: off
 };
 
 struct HaloCfg {
@@ -65,16 +66,17 @@ struct HaloCfg {
 };
 
 // Host + device: byte size of the dynamic shared memory for a given carve-up (pair: a weight tile is BLOCK_N/2 rows per CTA).
-__host__ __device__ constexpr int halo_smem_bytes(int block_n, int a_stages, int b_stages, int head, int pair = 0) {
+// ystg: a second set of warp-private 4 KB tiles (the y sub-boxes of the fused BatchNorm-backward sums)
+__host__ __device__ constexpr int halo_smem_bytes(int block_n, int a_stages, int b_stages, int head, int pair = 0, int ystg = 0) {
   return a_stages * HaloCfg::A_STAGE_PITCH + b_stages * 3 * (pair ? block_n / 2 : block_n) * 128 +
-         (head ? 0 : HaloCfg::STG_BYTES) + HaloCfg::BAR_BYTES + 1024;
+         (head ? 0 : HaloCfg::STG_BYTES) + (ystg ? HaloCfg::STG_BYTES : 0) + HaloCfg::BAR_BYTES + 1024;
 }
 
 constexpr int HALO_THREADS = 320;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..9 epilogue (2 per TMEM lane quarter)
 
 template <int BLOCK_N, bool PAIR>
 __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmWh,
-                                               const CUtensorMap& tmOut, const HaloArgs& a) {
+                                               const CUtensorMap& tmOut, const CUtensorMap& tmY, const HaloArgs& a) {
   constexpr int P = PAIR ? 2 : 1;                       // CTAs that share one MMA
   constexpr int B_HALF = (BLOCK_N / P) * 128;           // bytes of one (tap, 64-channel block) weight tile held by ONE CTA
   constexpr int HALVES = BLOCK_N / 64;
@@ -86,7 +88,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   uint8_t* smA = smem;
   uint8_t* smB = smA + AS * HaloCfg::A_STAGE_PITCH;
   uint8_t* smS = smB + BS * 3 * B_HALF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + (a.epi == HEPI_STORE ? HaloCfg::STG_BYTES : 0));
+  const bool bnb = a.bn.y != nullptr && a.epi == HEPI_STORE;   // fused BatchNorm-backward sums: [8 warps][4 KB] y tiles
+  uint8_t* smY = smS + (a.epi == HEPI_STORE ? HaloCfg::STG_BYTES : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smY + (bnb ? HaloCfg::STG_BYTES : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + HaloCfg::MAX_A;
   uint64_t* b_full = a_empty + HaloCfg::MAX_A;
@@ -94,6 +98,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   uint64_t* tfull = b_empty + HaloCfg::MAX_B;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* ybars = tempty + 3;   // [8] y tile of epilogue warp w has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,6 +121,10 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], P * (HALVES == 1 ? 128 : 256));   // the epilogue threads of every CTA of the group
+    }
+    if (bnb) {
+      tma_prefetch_desc(&tmY);
+      for (int s = 0; s < 8; ++s) mbar_init(&ybars[s], 1);
     }
     fence_mbar_init();
   }
@@ -261,12 +270,31 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     uint8_t* stg = smS + (warp - 2) * 4096;
     const bool pool_writer = ((tw | th) & 1) == 0;
     float st0[4] = {0.f, 0.f, 0.f, 0.f};
+    // fused BatchNorm-backward sums: this warp's y tile + barrier, a cursor one unit ahead of the main loop, the constants of
+    // the warp's 64 channels (fixed: one column group per warp) and its accumulators
+    const int n = ((HALVES == 1) ? 0 : cg) * 64;
+    uint8_t* ystg = smY + (warp - 2) * 4096;
+    uint64_t* ybar = &ybars[warp - 2];
+    uint32_t yph = 0;
+    float bk[8], ba[4] = {0.f, 0.f, 0.f, 0.f};
+    int yt = t_first + (HALVES == 1 ? cg * t_step : 0);
+    const int y_step = (HALVES == 1 ? 2 : 1) * t_step;     // BLOCK_N == 64: the two warps of a quarter alternate tiles
+    auto y_issue = [&]() {   // lane 0: request the y sub-box of tile yt (live tiles only), then advance the cursor
+      if (yt >= total_tiles) return;
+      const int yb = yt / tiles_per_img;
+      const int yti = yt - yb * tiles_per_img;
+      mbar_expect_tx(ybar, 4096);
+      tma_load_4d(ystg, &tmY, ybar, n, (yti % a.tiles_w) * 8, (yti / a.tiles_w) * 16 + 4 * q, yb);
+      yt += y_step;
+    };
+    if (bnb) {
+      epi_bnbwd_consts(a.bn, n, lane, bk);
+      if (lane == 0) y_issue();
+    }
     int it = 0;
     for (int t = t_first; t - static_cast<int>(rank) < total_tiles; t += t_step, ++it) {
       const int acc = it & 1;
       if (HALVES == 1 && acc != cg) continue;
-      const int hf = (HALVES == 1) ? 0 : cg;
-      const int n = hf * 64;
       const bool live = t < total_tiles;
       const int b = live ? t / tiles_per_img : 0;
       const int ti = live ? t - b * tiles_per_img : 0;
@@ -300,7 +328,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             for (int j = 0; j < 8; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
           }
         }
-        if (a.stat_sum != nullptr) epi_stats_accumulate(stg, lane, __ballot_sync(0xffffffffu, valid), st0);
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        if (a.stat_sum != nullptr) epi_stats_accumulate(stg, lane, vmask, st0);
+        if (bnb) {
+          mbar_wait(ybar, yph);
+          yph ^= 1;
+          epi_bnbwd_accumulate(stg, ystg, lane, vmask, bk, ba);
+          __syncwarp();             // every lane has finished reading the y tile: the next box may land in it
+          if (lane == 0) y_issue();
+        }
       } else {
         float z = a.head_b;
         const float4* hw4 = reinterpret_cast<const float4*>(a.head_w);
@@ -325,9 +361,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         }
       }
     }
-    if (a.stat_sum != nullptr && a.epi == HEPI_STORE) {
-      epi_stats_flush(a.stat_sum, a.stat_sumsq, (HALVES == 1 ? 0 : cg) * 64, lane, st0);
-    }
+    if (a.stat_sum != nullptr && a.epi == HEPI_STORE) epi_stats_flush(a.stat_sum, a.stat_sumsq, n, lane, st0);
+    if (bnb) epi_bnbwd_flush(a.bn, n, lane, ba);
     if (lane == 0) bulk_wait_group_read<0>();
   }
 
@@ -343,18 +378,18 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
 #define UB_CONV_HALO_PARAMS                                                                                               \
   const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,                                     \
       const __grid_constant__ CUtensorMap tmW /* box = BLOCK_N/2 rows */, const __grid_constant__ CUtensorMap tmOut,      \
-      const HaloArgs a
+      const __grid_constant__ CUtensorMap tmY /* EpiBnBwd y boxes */, const HaloArgs a
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(UB_CONV_HALO_PARAMS) {
   pdl_enter();
-  conv_halo_body<BLOCK_N, false>(tmA0, tmA1, tmW, tmOut, a);
+  conv_halo_body<BLOCK_N, false>(tmA0, tmA1, tmW, tmOut, tmY, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo2_kernel(UB_CONV_HALO_PARAMS) {
   pdl_enter();
-  conv_halo_body<BLOCK_N, true>(tmA0, tmA1, tmW, tmOut, a);
+  conv_halo_body<BLOCK_N, true>(tmA0, tmA1, tmW, tmOut, tmY, a);
 }
 
 }  // namespace ub

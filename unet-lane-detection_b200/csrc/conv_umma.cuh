@@ -53,6 +53,8 @@ struct ConvArgs {
   int split;                      // 1: fp32-class path - the output tensor has 2*Cout channels [hi | lo] (epilogue.cuh
                                   //    epi_load_unit_part); inputs are such tensors too (the host lists hi|lo and hi again as
                                   //    K sources against weights [w_hi | w_hi | w_lo]). No fused pool / statistics.
+  EpiBnBwd bn;                    // EPI_STORE, optional (training backward): BatchNorm-backward sums of the layer whose incoming
+                                  //    gradient this conv writes, taken in the epilogue (epilogue.cuh); bn.y == null: off
 };
 
 constexpr int CONV_THREADS = 320;
@@ -68,11 +70,12 @@ struct ConvCfg {
   static constexpr int SMEM_LIMIT = 232448;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
   static constexpr int STG_BYTES = 8 * 4096;  // one private 4 KB staging tile per epilogue warp
-  __host__ __device__ static constexpr int smem_bytes(int stages) {
-    return stages * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  // ystg: a second set of warp-private 4 KB tiles (the y sub-boxes of the fused BatchNorm-backward sums)
+  __host__ __device__ static constexpr int smem_bytes(int stages, bool ystg = false) {
+    return stages * STAGE_BYTES + (ystg ? 2 : 1) * STG_BYTES + BAR_BYTES + 1024;
   }
-  static int plan_stages() {
-    int s = (SMEM_LIMIT - BAR_BYTES - 1024 - STG_BYTES) / STAGE_BYTES;
+  static int plan_stages(bool ystg = false) {
+    int s = (SMEM_LIMIT - BAR_BYTES - 1024 - (ystg ? 2 : 1) * STG_BYTES) / STAGE_BYTES;
     return s > MAX_STAGES ? MAX_STAGES : s;
   }
 };
@@ -81,7 +84,7 @@ template <int BLOCK_N, bool PAIR>
 __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmA2,
                                                const CUtensorMap& tmA3, const CUtensorMap& tmW, const CUtensorMap& tmO0,
                                                const CUtensorMap& tmO1, const CUtensorMap& tmO2, const CUtensorMap& tmO3,
-                                               const ConvArgs& a) {
+                                               const CUtensorMap& tmY, const ConvArgs& a) {
   using Cfg = ConvCfg<BLOCK_N, PAIR>;
   constexpr int P = PAIR ? 2 : 1;   // CTAs that share one MMA
   constexpr int MAXS = Cfg::MAX_STAGES;
@@ -91,12 +94,15 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smS = smem + STAGES * Cfg::STAGE_BYTES;  // [8 warps][4 KB] private output staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smS + Cfg::STG_BYTES);
+  const bool bnb = a.bn.y != nullptr;   // fused BatchNorm-backward sums: [8 warps][4 KB] y tiles follow the staging tiles
+  uint8_t* smY = smS + Cfg::STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smY + (bnb ? Cfg::STG_BYTES : 0));
   uint64_t* full = bars;                // [MAXS] TMA -> MMA
   uint64_t* empty = bars + MAXS;        // [MAXS] MMA -> TMA
   uint64_t* tfull = bars + 2 * MAXS;    // [2] MMA -> epilogue
   uint64_t* tempty = bars + 2 * MAXS + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXS + 4);
+  uint64_t* ybars = bars + 2 * MAXS + 5;   // [8] y tile of epilogue warp w has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +119,10 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], P * (HALVES == 1 ? 128 : 256));   // the epilogue threads of every CTA of the group
+    }
+    if (bnb) {
+      tma_prefetch_desc(&tmY);
+      for (int s = 0; s < 8; ++s) mbar_init(&ybars[s], 1);
     }
     fence_mbar_init();
   }
@@ -241,6 +251,44 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
     // when the tile's column block changes (never, when gridDim.x is a multiple of n_tiles) and at the end
     float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};
     int st_ntile = -1;
+    // fused BatchNorm-backward sums: this warp's y tile + barrier, a cursor (yt, yit, yhf) one unit ahead of the main loop
+    // (the next unit's y box is requested as soon as the walk over the current one has finished), per-channel constants and
+    // accumulators for the (at most two) 64-column groups the warp serves
+    uint8_t* ystg = smY + (warp - 2) * 4096;
+    uint64_t* ybar = &ybars[warp - 2];
+    uint32_t yph = 0;
+    float bk0[8], bk1[8], ba0[4] = {0.f, 0.f, 0.f, 0.f}, ba1[4] = {0.f, 0.f, 0.f, 0.f};
+    const int hf_first = HALVES == 1 ? 0 : cg;
+    int yt = pair0, yit = 0, yhf = hf_first;
+    auto y_skip = [&]() {   // BLOCK_N == 64: the two warps of a quarter alternate tiles
+      if (HALVES == 1) {
+        while (yt < total_tiles && (yit & 1) != cg) {
+          yt += pair_step;
+          ++yit;
+        }
+      }
+    };
+    auto y_issue = [&]() {  // lane 0: request the y sub-box of unit (yt, yhf), then advance the cursor
+      if (yt >= total_tiles) return;
+      const int m_tile = P * (yt / a.n_tiles) + static_cast<int>(rank);
+      const int yw0 = (m_tile % a.tiles_w) * a.TW;
+      const int yh0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
+      const int yb0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
+      mbar_expect_tx(ybar, a.bn.bytes);
+      tma_load_4d(ystg, &tmY, ybar, (yt % a.n_tiles) * BLOCK_N + yhf * 64, yw0, yh0 + off_h, yb0 + off_b);
+      if (yhf + 2 < HALVES) {
+        yhf += 2;
+      } else {
+        yhf = hf_first;
+        yt += pair_step;
+        ++yit;
+        y_skip();
+      }
+    };
+    if (bnb && lane == 0) {
+      y_skip();
+      y_issue();
+    }
     int it = 0;
     for (int t = pair0; t < total_tiles; t += pair_step, ++it) {
       const int acc = it & 1;
@@ -251,13 +299,21 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
       const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.TH;
       const int b0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.TB;
       uint32_t vmask = 0;
-      if (a.stat_sum != nullptr) {
+      if (a.stat_sum != nullptr || bnb) {
         vmask = __ballot_sync(0xffffffffu, (w0 + tw < a.W) && (h0 + th < a.H) && (b0 + tb < a.B));
         if (n_tile != st_ntile) {
-          if (st_ntile >= 0) {
-            const int c0 = st_ntile * BLOCK_N + (HALVES == 1 ? 0 : cg) * 64;
-            epi_stats_flush(a.stat_sum, a.stat_sumsq, c0, lane, st0);
-            if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c0 + 128, lane, st1);
+          const int c_old = st_ntile * BLOCK_N + hf_first * 64, c_new = n_tile * BLOCK_N + hf_first * 64;
+          if (st_ntile >= 0 && a.stat_sum != nullptr) {
+            epi_stats_flush(a.stat_sum, a.stat_sumsq, c_old, lane, st0);
+            if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c_old + 128, lane, st1);
+          }
+          if (bnb) {
+            if (st_ntile >= 0) {
+              epi_bnbwd_flush(a.bn, c_old, lane, ba0);
+              if (HALVES == 4) epi_bnbwd_flush(a.bn, c_old + 128, lane, ba1);
+            }
+            epi_bnbwd_consts(a.bn, c_new, lane, bk0);
+            if (HALVES == 4) epi_bnbwd_consts(a.bn, c_new + 128, lane, bk1);
           }
           st_ntile = n_tile;
         }
@@ -321,18 +377,35 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
         }
         // (after the pool: the accumulator registers p[] are dead here, the staging tile still holds the unit)
         if (a.stat_sum != nullptr) {
-          if (hf == (HALVES == 1 ? 0 : cg)) {
+          if (hf == hf_first) {
             epi_stats_accumulate(stg, lane, vmask, st0);
           } else {
             epi_stats_accumulate(stg, lane, vmask, st1);
           }
         }
+        if (bnb) {
+          mbar_wait(ybar, yph);
+          yph ^= 1;
+          if (hf == hf_first) {
+            epi_bnbwd_accumulate(stg, ystg, lane, vmask, bk0, ba0);
+          } else {
+            epi_bnbwd_accumulate(stg, ystg, lane, vmask, bk1, ba1);
+          }
+          __syncwarp();             // every lane has finished reading the y tile: the next box may land in it
+          if (lane == 0) y_issue();
+        }
       }
     }
-    if (a.stat_sum != nullptr && st_ntile >= 0) {
-      const int c0 = st_ntile * BLOCK_N + (HALVES == 1 ? 0 : cg) * 64;
-      epi_stats_flush(a.stat_sum, a.stat_sumsq, c0, lane, st0);
-      if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c0 + 128, lane, st1);
+    if (st_ntile >= 0) {
+      const int c0 = st_ntile * BLOCK_N + hf_first * 64;
+      if (a.stat_sum != nullptr) {
+        epi_stats_flush(a.stat_sum, a.stat_sumsq, c0, lane, st0);
+        if (HALVES == 4) epi_stats_flush(a.stat_sum, a.stat_sumsq, c0 + 128, lane, st1);
+      }
+      if (bnb) {
+        epi_bnbwd_flush(a.bn, c0, lane, ba0);
+        if (HALVES == 4) epi_bnbwd_flush(a.bn, c0 + 128, lane, ba1);
+      }
     }
     if (lane == 0) bulk_wait_group_read<0>();
   }
@@ -352,18 +425,19 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
       const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,                                \
       const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,                                 \
       const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,                                \
-      const __grid_constant__ CUtensorMap tmO3, const ConvArgs a
+      const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmY /* EpiBnBwd y boxes */,        \
+      const ConvArgs a
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(UB_CONV_UMMA_PARAMS) {
   pdl_enter();
-  conv_umma_body<BLOCK_N, false>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
+  conv_umma_body<BLOCK_N, false>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, tmY, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv_umma2_kernel(UB_CONV_UMMA_PARAMS) {
   pdl_enter();
-  conv_umma_body<BLOCK_N, true>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, a);
+  conv_umma_body<BLOCK_N, true>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, tmY, a);
 }
 
 }  // namespace ub

@@ -116,6 +116,66 @@ __device__ __forceinline__ void epi_stats_flush(double* __restrict__ sum, double
   acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
 }
 
+// ---- fused BatchNorm-backward sums (training backward, dgrad epilogues) ------------------------------------------------
+// The dgrad conv of layer L+1 writes g = dL/da of layer L, a = relu(bn(y)). BatchNorm's backward needs, per channel,
+// s1 = sum g*[a > 0] and s2 = sum g*[a > 0]*xhat before it can turn g into dL/dy (train_kernels.cuh bn_relu_bwd_apply_kernel).
+// Instead of a separate pass over g and y (bn_relu_bwd_reduce_kernel) the epilogue that PRODUCES g takes the sums: the unit's
+// y sub-box is TMA-loaded into a second warp-private 4 KB tile (same box and swizzle as the output staging tile) and the
+// column walk of epi_stats_accumulate reads both. g is read back from the staging tile, i.e. bf16-rounded as stored.
+struct EpiBnBwd {
+  const void* y;        // raw conv output of layer L (null: no fusion); only tested for null here, the data comes through tmY
+  const float* scale;   // per channel: gamma * invstd
+  const float* shift;   // beta - mean * scale
+  const float* mean;
+  const float* invstd;
+  float* s1;            // [C] += sum g       (fp32 atomics, one per lane and channel at the end of the kernel)
+  float* s2;            // [C] += sum g * xhat
+  int bytes;            // bytes one y box load delivers (4096 unless the box is clipped along the batch axis)
+};
+// k = {scale, shift, mean, invstd} of channel col + 2*lane, then of col + 2*lane + 1
+__device__ __forceinline__ void epi_bnbwd_consts(const EpiBnBwd& b, int col, int lane, float (&k)[8]) {
+  const int c = col + 2 * lane;
+  const float2 sc = __ldg(reinterpret_cast<const float2*>(b.scale + c));
+  const float2 sh = __ldg(reinterpret_cast<const float2*>(b.shift + c));
+  const float2 mu = __ldg(reinterpret_cast<const float2*>(b.mean + c));
+  const float2 is = __ldg(reinterpret_cast<const float2*>(b.invstd + c));
+  k[0] = sc.x; k[1] = sh.x; k[2] = mu.x; k[3] = is.x;
+  k[4] = sc.y; k[5] = sh.y; k[6] = mu.y; k[7] = is.y;
+}
+// acc = {s1, s2} of channel 2*lane, then of channel 2*lane + 1
+__device__ __forceinline__ void epi_bnbwd_accumulate(const uint8_t* gtile, const uint8_t* ytile, int lane, uint32_t valid_mask,
+                                                     const float (&k)[8], float (&acc)[4]) {
+  const uint32_t off = (lane & 3) * 4;
+  const uint32_t gbase = smem_u32(gtile) + off, ybase = smem_u32(ytile) + off;
+  const int chunk = lane >> 2;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    if ((valid_mask >> r) & 1u) {
+      const uint32_t o = r * 128 + ((chunk ^ (r & 7)) << 4);
+      uint32_t wg, wy;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wg) : "r"(gbase + o));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wy) : "r"(ybase + o));
+      const __nv_bfloat162 hg = *reinterpret_cast<const __nv_bfloat162*>(&wg);
+      const __nv_bfloat162 hy = *reinterpret_cast<const __nv_bfloat162*>(&wy);
+      const float y0 = __low2float(hy), y1 = __high2float(hy);
+      const float g0 = fmaf(y0, k[0], k[1]) > 0.f ? __low2float(hg) : 0.f;
+      const float g1 = fmaf(y1, k[4], k[5]) > 0.f ? __high2float(hg) : 0.f;
+      acc[0] += g0;
+      acc[1] = fmaf(g0, (y0 - k[2]) * k[3], acc[1]);
+      acc[2] += g1;
+      acc[3] = fmaf(g1, (y1 - k[6]) * k[7], acc[3]);
+    }
+  }
+}
+__device__ __forceinline__ void epi_bnbwd_flush(const EpiBnBwd& b, int col, int lane, float (&acc)[4]) {
+  const int c = col + 2 * lane;
+  atomicAdd(b.s1 + c, acc[0]);
+  atomicAdd(b.s2 + c, acc[1]);
+  atomicAdd(b.s1 + c + 1, acc[2]);
+  atomicAdd(b.s2 + c + 1, acc[3]);
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+}
+
 // 2x2 max over the window partners lane^1 (w) and lane^xor_h (h); afterwards every lane of a window holds the max.
 __device__ __forceinline__ void epi_pool2x2(uint32_t (&p)[32], int xor_h) {
 #pragma unroll

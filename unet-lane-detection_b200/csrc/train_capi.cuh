@@ -36,6 +36,8 @@ struct TConv {
   int w_bn, w_grid;
   bool w_pair;
   bool reduce_fused;  // the BatchNorm-backward sums of this layer come out of the kernel that produces its incoming gradient
+  int dg_bn;          // >= 0: this layer's dgrad kernel writes the COMPLETE incoming gradient of conv #dg_bn and takes that
+                      // layer's BatchNorm-backward sums in its epilogue (option dgrad_fuse); -1: no
 };
 
 struct TConvT {
@@ -53,12 +55,13 @@ struct TConvT {
   ub::WgradArgs wa;
   int w_bn, w_grid;
   bool w_pair;
+  int dg_bn;          // as TConv::dg_bn: the conv whose incoming gradient the ConvT dgrad writes (u.dx == that conv's g)
 };
 
 }  // namespace
 
 struct unet_b200_trainer {
-  int B, H, W, in_ch, levels;
+  int B, H, W, in_ch, out_ch, levels;
   Opts opt;                    // the switches this trainer was created with
   int feat[UB_MAX_LEVELS];
   std::vector<TConv> convs;    // plan order: enc0.0, enc0.3, ..., bott.0, bott.3, dec0.0, dec0.3, ...
@@ -67,7 +70,7 @@ struct unet_b200_trainer {
   long long n_params;
   std::vector<long long> tensor_off;  // parameters() order, one entry per tensor (+ total at the end)
   long long head_w_off, head_b_off;
-  float* head_w_pad;  // fp32 [physical f0]: output.weight zero-extended (pack job, every step)
+  float* head_w_pad;  // fp32 [out_ch][physical f0]: output.weight zero-extended (pack jobs, every step)
   size_t ws_bytes;
   uint8_t* ws;
   uint8_t* acc;       // accumulator region zeroed every step
@@ -112,6 +115,19 @@ ub::BnBwdStats bn_stats_of(const TConv& c) {
   return b;
 }
 const ub::BnBwdStats kNoBnStats = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+// the same for a tcgen05 dgrad epilogue (epilogue.cuh EpiBnBwd); `bytes` is filled in by conv_layer_launch
+ub::EpiBnBwd epi_bn_of(const TConv& c) {
+  ub::EpiBnBwd b;
+  b.y = c.y;
+  b.scale = c.scale;
+  b.shift = c.shift;
+  b.mean = c.mean;
+  b.invstd = c.invstd;
+  b.s1 = c.s1;
+  b.s2 = c.s2;
+  b.bytes = 0;
+  return b;
+}
 
 // One pass over the network assigning workspace addresses (base == 0: size computation only).
 void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
@@ -119,7 +135,7 @@ void trainer_layout(unet_b200_trainer* t, uintptr_t base) {
   const size_t B = t->B;
   t->zero_bias = reinterpret_cast<float*>(bp.take(4096 * 4));
   t->jobs_dev = reinterpret_cast<ub::PackJob*>(bp.take(64 * sizeof(ub::PackJob)));
-  t->head_w_pad = reinterpret_cast<float*>(bp.take((size_t)t->convs.back().Cout * 4));
+  t->head_w_pad = reinterpret_cast<float*>(bp.take((size_t)t->out_ch * t->convs.back().Cout * 4));
   for (TConvT& u : t->ups) u.bias_pad = reinterpret_cast<float*>(bp.take((size_t)u.f * 4));
   t->x_in = bp.take(B * t->H * t->W * 8);
   // accumulators (zeroed per step): per conv sum, sumsq (double) + s1, s2 (float)
@@ -391,6 +407,10 @@ int trainer_build_maps(unet_b200_trainer* t) {
     if (rc != UB_OK) return rc;
     rc = conv_layer_setup(c.dg, L_CONV, c.g, c.Cout, nullptr, 0, c.wd, c.dx, nullptr, B, c.H, c.W, cin, 0, true);
     if (rc != UB_OK) return rc;
+    if (c.dg_bn >= 0) {
+      rc = make_epi_y_map(c.dg, t->convs[c.dg_bn].y, B);
+      if (rc != UB_OK) return rc;
+    }
     rc = setup_conv_wgrad(c, B);
     if (rc != UB_OK) return rc;
   }
@@ -399,6 +419,10 @@ int trainer_build_maps(unet_b200_trainer* t) {
     if (rc != UB_OK) return rc;
     rc = setup_up_backward(u, B);
     if (rc != UB_OK) return rc;
+    if (u.dg_bn >= 0) {
+      rc = make_epi_y_map(u.dg, t->convs[u.dg_bn].y, B);
+      if (rc != UB_OK) return rc;
+    }
   }
   return UB_OK;
 }
@@ -457,17 +481,17 @@ int trainer_conv_forward(unet_b200_trainer* t, TConv& c, int bn_idx, const float
   fin.running_var = running_var ? running_var[bn_idx] : nullptr;
   fin.C = c.Cout;
   fin.lC = c.lCout > 0 ? c.lCout : c.Cout;
-  ub_launch(ub::bn_finalize_kernel, (c.Cout + 127) / 128, 128, 0, st, fin);
-  UB_CUDA(cudaGetLastError());
+  // (no bn_finalize launch: the apply kernel finalises the statistics itself, train_kernels.cuh bn_fin_channels; the grid
+  // always has at least C8 threads - one block is 256 >= C8 threads - so every channel gets published)
   if (c.pooled) {
     const size_t n = npix / 4 * C8;
     ub_launch(ub::bn_relu_apply_pool_kernel, grid_for(n, 256), 256, 0, st, reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, B, c.H,
                                                                     c.W, C8, reinterpret_cast<uint4*>(c.a),
-                                                                    reinterpret_cast<uint4*>(c.p));
+                                                                    reinterpret_cast<uint4*>(c.p), fin);
   } else {
     const size_t n8 = npix * C8;
     ub_launch(ub::bn_relu_apply_kernel, grid_for(n8, 256), 256, 0, st, reinterpret_cast<const uint4*>(c.y), c.scale, c.shift, n8, C8,
-                                                                reinterpret_cast<uint4*>(c.a));
+                                                                reinterpret_cast<uint4*>(c.a), fin);
   }
   UB_CUDA(cudaGetLastError());
   return UB_OK;
@@ -555,7 +579,12 @@ int trainer_conv_backward(unet_b200_trainer* t, TConv& c, const ub::GradRoute& r
   // dgrad first (the next layer's backward waits for it), then the wgrad is forked: it only feeds the gradient buffer, so it
   // runs concurrently with the bandwidth-bound BN / pool backward kernels that follow on `st`
   if (c.dx != nullptr) {
-    rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st);
+    if (c.dg_bn >= 0) {   // the epilogue also takes the BatchNorm-backward sums of the layer whose gradient it writes
+      const ub::EpiBnBwd bn = epi_bn_of(t->convs[c.dg_bn]);
+      rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st, nullptr, nullptr, &bn);
+    } else {
+      rc = conv_layer_launch(c.dg, B, B, t->zero_bias, c.dx, nullptr, st);
+    }
     if (rc != UB_OK) return rc;
   }
   cudaStream_t sw;
@@ -581,15 +610,26 @@ int up_wgrad_launch(const TConvT& u, int B, int pitch8, const ub::GradRoute& rou
 }
 
 // dX[b,h,w,ci] = sum_quad sum_co dUp[b,2h+dy,2w+dx,co] * w[ci][co][quad]: 1-tap GEMM, K walks the four quad views
-int up_dgrad_launch(const TConvT& u, int B, const float* zero_bias, cudaStream_t st) {
+int up_dgrad_launch(const TConvT& u, int B, const float* zero_bias, cudaStream_t st, const ub::EpiBnBwd* bn = nullptr) {
   ub::ConvArgs a = conv_args(u.dg, B, B, zero_bias, u.dx, nullptr);
   a.taps = 1;
   a.kc0 = a.kc1 = a.kc2 = a.kc3 = u.f / 64;
-  return launch_conv(u.dg.block_n, u.dgA, u.dg.mW, u.dg.mO, a, st);
+  if (bn != nullptr) {
+    if (u.dg.y_bytes == 0) return fail(UB_ERR_STATE, "fused BN-backward sums without a y view");
+    a.bn = *bn;
+    a.bn.bytes = u.dg.y_bytes;
+  }
+  return launch_conv(u.dg.block_n, u.dgA, u.dg.mW, u.dg.mO, a, st, bn != nullptr ? &u.dg.mY : nullptr);
 }
 
 int trainer_up_backward(unet_b200_trainer* t, TConvT& u, const ub::GradRoute& route, cudaStream_t st) {
-  int rc = up_dgrad_launch(u, t->B, t->zero_bias, st);
+  int rc;
+  if (u.dg_bn >= 0) {
+    const ub::EpiBnBwd bn = epi_bn_of(t->convs[u.dg_bn]);
+    rc = up_dgrad_launch(u, t->B, t->zero_bias, st, &bn);
+  } else {
+    rc = up_dgrad_launch(u, t->B, t->zero_bias, st);
+  }
   if (rc != UB_OK) return rc;
   cudaStream_t sw;
   rc = wgrad_stream(t, st, &sw);
@@ -624,7 +664,9 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   if (levels < 1 || levels > UB_MAX_LEVELS) return fail(UB_ERR_ARG, "levels must be in [1,%d]", UB_MAX_LEVELS);
   if (batch < 1) return fail(UB_ERR_ARG, "batch must be >= 1");
   if (in_channels < 1 || in_channels > 4) return fail(UB_ERR_ARG, "in_channels must be in [1,4] (got %d)", in_channels);
-  if (out_channels != 1) return fail(UB_ERR_ARG, "out_channels must be 1 (got %d)", out_channels);
+  if (out_channels < 1 || out_channels > ub::HEAD_MAX_OC) {
+    return fail(UB_ERR_ARG, "training needs out_channels in [1,%d] (got %d)", ub::HEAD_MAX_OC, out_channels);
+  }
   if (H % (1 << levels) != 0 || W % (1 << levels) != 0) {
     return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
   }
@@ -649,6 +691,7 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   t->H = H;
   t->W = W;
   t->in_ch = in_channels;
+  t->out_ch = out_channels;
   t->levels = levels;
   t->ws = nullptr;
   t->fwd_done = false;
@@ -710,7 +753,24 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   // the encoder conv1 layers (max-pool backward) and the last conv (head backward)
   if (t->opt.bwd_fuse) {
     for (int i = 0; i < levels; ++i) t->convs[2 * i + 1].reduce_fused = true;
-    t->convs.back().reduce_fused = true;
+    t->convs.back().reduce_fused = out_channels == 1;
+  }
+  // ... and into the tcgen05 dgrad epilogue where the producer is a dgrad GEMM that writes the complete gradient: the conv1 of
+  // every block (its dgrad writes the block's conv0 gradient) and the ConvTs (their dgrad writes the gradient of the conv1
+  // below them: the bottleneck's or the previous decoder level's). The stem's gradient comes from enc0.conv1's dgrad too.
+  for (TConv& c : t->convs) c.dg_bn = -1;
+  for (TConvT& u : t->ups) u.dg_bn = -1;
+  if (t->opt.dgrad_fuse) {
+    const int nblocks = 2 * levels + 1;
+    for (int b = 0; b < nblocks; ++b) {
+      t->convs[2 * b + 1].dg_bn = 2 * b;
+      t->convs[2 * b].reduce_fused = true;
+    }
+    for (int j = 0; j < levels; ++j) {
+      const int below = (j == 0) ? 2 * levels + 1 : 2 * levels + 3 + 2 * (j - 1);
+      t->ups[j].dg_bn = below;
+      t->convs[below].reduce_fused = true;
+    }
   }
   // forward order and parameters() order (encoder, decoder, bottleneck, output: README.md:1427-1447)
   for (int i = 0; i < 2 * levels + 2; ++i) t->fwd_order.push_back(i);
@@ -748,10 +808,10 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   conv_params(t->convs[2 * levels + 1]);
   t->head_w_off = off;
   t->tensor_off.push_back(off);
-  off += features[0];
+  off += (long long)out_channels * features[0];
   t->head_b_off = off;
   t->tensor_off.push_back(off);
-  off += 1;
+  off += out_channels;
   t->tensor_off.push_back(off);
   t->n_params = off;
   trainer_layout(t, 0);
@@ -821,7 +881,10 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
       add(1, u.f, u.Cin, 0, u.lf, u.lCin, 0, u.w_off, u.wp, u.wd, (size_t)4 * u.f * u.Cin);
       add(3, u.f, 0, 0, u.lf, 0, 0, u.b_off, u.bias_pad, nullptr, (size_t)u.f);                 // bias, zero-extended
     }
-    add(3, t->convs.back().Cout, 0, 0, t->feat[0], 0, 0, t->head_w_off, t->head_w_pad, nullptr, (size_t)t->convs.back().Cout);
+    for (int oc = 0; oc < t->out_ch; ++oc) {      // one zero-extended row per output channel
+      add(3, t->convs.back().Cout, 0, 0, t->feat[0], 0, 0, t->head_w_off + (long long)oc * t->feat[0],
+          t->head_w_pad + (size_t)oc * t->convs.back().Cout, nullptr, (size_t)t->convs.back().Cout);
+    }
     if (jobs.size() > 64) return fail(UB_ERR_ARG, "too many weight tensors for the pack job table");
     t->n_jobs = (int)jobs.size();
     t->pack_blocks = blocks;
@@ -862,9 +925,14 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   }
   const TConv& last = t->convs.back();
   const size_t npix = (size_t)B * last.H * last.W;
-  ub_launch(ub::head_fwd_train_kernel, grid_for(npix * 8, 256), 256, 0, st, reinterpret_cast<const uint4*>(last.a),
-                                                                     t->head_w_pad, params + t->head_b_off, npix,
-                                                                     last.Cout / 8, logits);
+  if (t->out_ch == 1) {
+    ub_launch(ub::head_fwd_train_kernel, grid_for(npix * 8, 256), 256, 0, st, reinterpret_cast<const uint4*>(last.a),
+                                                                       t->head_w_pad, params + t->head_b_off, npix,
+                                                                       last.Cout / 8, logits);
+  } else {
+    ub_launch(ub::head_fwd_train_multi_kernel, grid_for(npix, 256), 256, 0, st, reinterpret_cast<const uint4*>(last.a), t->head_w_pad,
+              params + t->head_b_off, npix, (size_t)last.H * last.W, last.Cout / 8, t->out_ch, logits);
+  }
   UB_CUDA(cudaGetLastError());
   t->fwd_done = true;
   return UB_OK;
@@ -919,9 +987,15 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
     TConv& last = t->convs.back();
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
-    ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
-        reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
-        t->head_w_off, t->head_b_off, bn_stats_of(last), t->feat[0]);
+    if (t->out_ch == 1) {
+      ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
+          reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
+          t->head_w_off, t->head_b_off, bn_stats_of(last), t->feat[0]);
+    } else {
+      ub_launch(ub::head_bwd_multi_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st,
+          reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, (size_t)last.H * last.W, C8, t->out_ch,
+          reinterpret_cast<uint4*>(last.g), route, t->head_w_off, t->head_b_off, t->feat[0]);
+    }
     UB_CUDA(cudaGetLastError());
   } else {
     if (t->bwd_stage != stage - 1) return fail(UB_ERR_STATE, "backward stages must run in order (got %d after %d)", stage, t->bwd_stage);
@@ -1295,14 +1369,16 @@ int unet_b200_bn_relu_train_fwd(const void* y, const float* gamma, const float* 
   fin.lC = C;
   ub_launch(ub::bn_finalize_kernel, (C + 127) / 128, 128, 0, st, fin);
   UB_CUDA(cudaGetLastError());
+  ub::BnFin no_fin;   // this entry point keeps the two-kernel form (finalise, then apply from the published scale / shift)
+  memset(&no_fin, 0, sizeof(no_fin));
   if (pool != nullptr) {
     ub_launch(ub::bn_relu_apply_pool_kernel, grid_for(npix / 4 * C8, 256), 256, 0, st, reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
                                                                                 stats4 + 3 * C, B, H, W, C8,
                                                                                 reinterpret_cast<uint4*>(a),
-                                                                                reinterpret_cast<uint4*>(pool));
+                                                                                reinterpret_cast<uint4*>(pool), no_fin);
   } else {
     ub_launch(ub::bn_relu_apply_kernel, grid_for(npix * C8, 256), 256, 0, st, reinterpret_cast<const uint4*>(y), stats4 + 2 * C,
-                                                                       stats4 + 3 * C, npix * C8, C8, reinterpret_cast<uint4*>(a));
+                                                                       stats4 + 3 * C, npix * C8, C8, reinterpret_cast<uint4*>(a), no_fin);
   }
   UB_CUDA(cudaGetLastError());
   return UB_OK;

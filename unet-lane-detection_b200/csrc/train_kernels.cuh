@@ -102,19 +102,58 @@ __global__ void bn_finalize_kernel(const BnFin f) {
   }
 }
 
+// The same finalisation inside the kernel that applies it (bn_relu_apply*_kernel with fin.sum != null): every thread works
+// out scale / shift of its own eight channels from the batch sums - multiplications by 1/count in double, no division, a few
+// dozen instructions per thread - and the first C/8 threads of the grid also publish mean / invstd / scale / shift (the
+// backward reads them) and update the running statistics. Saves one launch per BatchNorm layer and step.
+__device__ __forceinline__ void bn_fin_channels(const BnFin& f, int c0, bool publish, float (&sc)[8], float (&sh)[8]) {
+  const double inv_n = 1.0 / static_cast<double>(f.count);   // one division per thread, of loop-invariant values
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    float m = 0.f, is = 0.f, var = 0.f;
+    sc[k] = 0.f;
+    sh[k] = 0.f;
+    if (c < f.lC) {
+      const double md = f.sum[c] * inv_n;
+      const double vd = f.sumsq[c] * inv_n - md * md;
+      m = static_cast<float>(md);
+      var = fmaxf(static_cast<float>(vd), 0.f);
+      is = rsqrtf(var + f.eps);
+      sc[k] = __ldg(f.gamma + c) * is;
+      sh[k] = __ldg(f.beta + c) - m * sc[k];
+    }
+    if (publish) {
+      f.mean[c] = m;
+      f.invstd[c] = is;
+      f.scale[c] = sc[k];
+      f.shift[c] = sh[k];
+      if (c < f.lC && f.running_mean != nullptr) {
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * m;
+        const float unbiased = f.count > 1.f ? var * f.count / (f.count - 1.f) : var;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
+      }
+    }
+  }
+}
+
 // a = relu(y*scale + shift). The grid stride is a multiple of C8 (C8 | 256), so a thread's channel group never changes
-// and its eight scale/shift pairs live in registers.
+// and its eight scale/shift pairs live in registers. fin.sum != null: scale / shift come from the batch sums (above).
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                     size_t n8, int C8, uint4* __restrict__ a) {
+                     size_t n8, int C8, uint4* __restrict__ a, const BnFin fin) {
   pdl_enter();
   const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const int c = static_cast<int>(i0 % C8) * 8;
   float sc[8], sh[8];
+  if (fin.sum != nullptr) {
+    bn_fin_channels(fin, c, i0 < static_cast<size_t>(C8), sc, sh);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    sc[k] = __ldg(scale + c + k);
-    sh[k] = __ldg(shift + c + k);
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = __ldg(scale + c + k);
+      sh[k] = __ldg(shift + c + k);
+    }
   }
   for (size_t i = i0; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float f[8];
@@ -129,17 +168,21 @@ bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scal
 // One thread = one 2x2 window x 8 channels.
 __global__ void __launch_bounds__(256)
 bn_relu_apply_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, int B,
-                          int H, int W, int C8, uint4* __restrict__ a, uint4* __restrict__ pl) {
+                          int H, int W, int C8, uint4* __restrict__ a, uint4* __restrict__ pl, const BnFin fin) {
   pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const int c8 = static_cast<int>(i0 % C8);  // loop-invariant: the grid stride is a multiple of C8
   float sc[8], sh[8];
+  if (fin.sum != nullptr) {
+    bn_fin_channels(fin, c8 * 8, i0 < static_cast<size_t>(C8), sc, sh);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    sc[k] = __ldg(scale + c8 * 8 + k);
-    sh[k] = __ldg(shift + c8 * 8 + k);
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = __ldg(scale + c8 * 8 + k);
+      sh[k] = __ldg(shift + c8 * 8 + k);
+    }
   }
   for (size_t i = i0; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = i / C8;
@@ -473,6 +516,87 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
   if (bn.y != nullptr) {
     __syncthreads();   // red is reused
     bnbwd_flush(bn, br, C8, red);
+  }
+}
+
+// out_channels > 1 (README.md:1447 builds any; the reference itself trains out_channels = 1): plain versions of the two head
+// kernels. logits / dz are NCHW [B][OC][hw], w is the zero-extended weight [OC][C8*8], OC <= HEAD_MAX_OC.
+constexpr int HEAD_MAX_OC = 8;
+__global__ void __launch_bounds__(256)
+head_fwd_train_multi_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias, size_t npix,
+                            size_t hw, int C8, int OC, float* __restrict__ logits) {
+  pdl_enter();
+  for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < npix;
+       p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc[HEAD_MAX_OC];
+#pragma unroll
+    for (int oc = 0; oc < HEAD_MAX_OC; ++oc) acc[oc] = 0.f;
+    for (int c = 0; c < C8; ++c) {
+      float f[8];
+      unpack8(__ldg(a + p * C8 + c), f);
+#pragma unroll
+      for (int oc = 0; oc < HEAD_MAX_OC; ++oc) {
+        if (oc < OC) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[oc] = fmaf(f[k], __ldg(w + (static_cast<size_t>(oc) * C8 + c) * 8 + k), acc[oc]);
+        }
+      }
+    }
+    const size_t b = p / hw, q = p - b * hw;
+#pragma unroll
+    for (int oc = 0; oc < HEAD_MAX_OC; ++oc) {
+      if (oc < OC) logits[(b * OC + oc) * hw + q] = acc[oc] + __ldg(bias + oc);
+    }
+  }
+}
+
+// dA[p][c] = sum_oc dz[b][oc][q] * w[oc][c];  dw[oc][c] += sum_p dz * a[p][c] (c < lC);  db[oc] += sum_p dz
+__global__ void __launch_bounds__(256)
+head_bwd_multi_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, size_t hw,
+                      int C8, int OC, uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b, int lC) {
+  pdl_enter();
+  extern __shared__ float red[];   // [256][8] + [256]
+  const int cl = threadIdx.x % C8;
+  const int pl = threadIdx.x / C8;
+  const int ppb = 256 / C8;
+  for (int oc = 0; oc < OC; ++oc) {          // one sweep per output channel for the parameter gradients (OC is small)
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float bsum = 0.f;
+    for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+      const size_t b = p / hw, q = p - b * hw;
+      const float g = __ldg(dz + (b * OC + oc) * hw + q);
+      float fa[8];
+      unpack8(__ldg(a + p * C8 + cl), fa);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(g, fa[i], acc[i]);
+      if (cl == 0) bsum += g;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    red[2048 + threadIdx.x] = bsum;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C8 * 8; c += 256) {
+      float s_ = 0.f;
+      for (int j = 0; j < ppb; ++j) s_ += red[(j * C8 + c / 8) * 8 + (c & 7)];
+      if (c < lC) grad_add(route, off_w + static_cast<long long>(oc) * lC + c, s_);
+    }
+    if (threadIdx.x == 0) {
+      float s_ = 0.f;
+      for (int j = 0; j < 256; ++j) s_ += red[2048 + j];
+      grad_add(route, off_b + oc, s_);
+    }
+    __syncthreads();
+  }
+  // activation gradient
+  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
+    const size_t b = p / hw, q = p - b * hw;
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int oc = 0; oc < OC; ++oc) {
+      const float g = __ldg(dz + (b * OC + oc) * hw + q);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(g, __ldg(w + (static_cast<size_t>(oc) * C8 + cl) * 8 + i), o[i]);
+    }
+    dA[p * C8 + cl] = pack8(o);
   }
 }
 

@@ -121,12 +121,14 @@ def _bn_tables(model):
 
 
 def train_forward(model, x4):
-    """x4: bf16 NHWC4 [B,H,W,4] -> logits fp32 [B,H,W]; updates BN running statistics like nn.BatchNorm2d."""
+    """x4: bf16 NHWC4 [B,H,W,4] -> logits fp32 [B,H,W] (out_channels == 1, the reference's case) or NCHW [B,out_channels,H,W];
+    updates BN running statistics like nn.BatchNorm2d."""
     B, H, W, _ = x4.shape
     eng = _engine(model, x4.device, B, H, W)
     flat = flatten_parameters_(model)
     bns, means, vars_ = _bn_tables(model)
-    logits = torch.empty(B, H, W, dtype=torch.float32, device=x4.device)
+    shape = (B, H, W) if model.out_channels == 1 else (B, model.out_channels, H, W)
+    logits = torch.empty(shape, dtype=torch.float32, device=x4.device)
     st = torch.cuda.current_stream().cuda_stream
     check(lib.unet_b200_train_forward(eng.handle, x4.data_ptr(), flat.data_ptr(), means, vars_, float(bns[0].momentum),
                                       float(bns[0].eps), logits.data_ptr(), st))
@@ -137,7 +139,7 @@ def train_forward(model, x4):
 
 
 def train_backward(model, eng, dlogits, grads=None):
-    """dlogits fp32 [B,H,W] -> flat fp32 gradient (parameters() order)."""
+    """dlogits fp32, same shape as the logits of train_forward -> flat fp32 gradient (parameters() order)."""
     flat = flatten_parameters_(model)
     if grads is None:
         grads = torch.empty_like(flat)
@@ -179,7 +181,7 @@ def forward_train_autograd(model, x):
     check(lib.unet_b200_nchw_to_nhwc4(xin.data_ptr(), B, model.in_channels, H, W, x4.data_ptr(), st))
     flatten_parameters_(model)
     logits = _UNetTrainFn.apply(model, x4, *model.parameters())
-    return logits.reshape(B, 1, H, W).to(x.dtype)
+    return logits.reshape(B, model.out_channels, H, W).to(x.dtype)
 
 
 def bce_dice_loss(logits, target, pos_weight=3.0, bce_weight=0.5, dice_weight=0.5, smooth=1e-6, want_grad=True):
