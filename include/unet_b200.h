@@ -128,6 +128,8 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *                           BatchNorm layers of the default network), that kernel's epilogue also takes the layer's
  *                           BatchNorm-backward sums (the y sub-box is TMA-loaded beside the staged output tile), so the
  *                           separate reduction pass over g and y does not run
+ *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
+ *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
  *   "stem_wide" (default 0) tensor-core stem on 4 x 32 pixel tiles (one contiguous 4 KB output row per TMA store) instead
  *                           of 16 x 8; bit-identical, measured +0.3 % (noise): the stem is bound by the write rate, not by
  *                           the store pattern

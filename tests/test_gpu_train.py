@@ -61,6 +61,9 @@ def rnd(*shape, seed=0, scale=1.0):
     (2, 8, 8, 256, 0, 256),      # BLOCK_N 256, batch folded into the pixel tile
     (4, 4, 4, 256, 256, 256),    # deepest levels: 4x4 maps, 8 images per tile
     (1, 32, 16, 128, 0, 64),
+    (3, 24, 40, 64, 0, 64),      # Cout == 64 (halo-patch kernel): ragged rows (24 = 16 + 8), several tiles per image
+    (2, 40, 56, 64, 64, 64),     #   two sources, more tiles than CTAs per channel block get strided K slices
+    (1, 224, 224, 64, 0, 64),    #   the level it is built for
 ])
 def test_conv3x3_wgrad(U, B, H, W, C0, C1, Cout):
     x = rnd(B, C0 + C1, H, W, seed=1)

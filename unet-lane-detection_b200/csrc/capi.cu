@@ -57,6 +57,7 @@ struct Opts {
   int stem_wide = 0;     // tensor-core stem on 4 x 32 tiles (4 KB contiguous output rows per store) instead of 16 x 8
   int bwd_fuse = 0;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient (measured: no gain)
   int dgrad_fuse = 1;    // training: BatchNorm-backward reduction inside the tcgen05 dgrad epilogues that write the gradient
+  int wgrad_halo = 1;    // training: Cout == 64 weight gradients on the halo-patch kernel (all nine taps per CTA)
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -85,6 +86,7 @@ enum AttrSlot : int {
   AT_PRE_ROWS = 20,
   AT_BNFUSE = 21,
   AT_STEM_WIDE = 22,
+  AT_WGRAD_HALO = 23,
 };
 struct DevState {
   std::atomic<int> num_sms{0};
@@ -1143,7 +1145,8 @@ int unet_b200_set_option(const char* name, int value) {
       {"halo", &g_opts.halo}, {"pdl", &g_opts.pdl}, {"halo2", &g_opts.halo2}, {"umma2", &g_opts.umma2},
       {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
-      {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse}};
+      {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
+      {"wgrad_halo", &g_opts.wgrad_halo}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;

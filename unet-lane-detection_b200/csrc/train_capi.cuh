@@ -14,6 +14,7 @@
 #pragma once
 #include "train_kernels.cuh"
 #include "wgrad_umma.cuh"
+#include "wgrad_halo.cuh"
 #include "stem_wgrad_umma.cuh"
 
 namespace {
@@ -35,6 +36,9 @@ struct TConv {
   ub::WgradArgs wa;
   int w_bn, w_grid;
   bool w_pair;
+  bool w_halo;        // Cout == 64: all nine taps from one halo'd patch (wgrad_halo.cuh) instead of one CTA per tap pair
+  CUtensorMap wXh0, wXh1, wDh;
+  ub::WgradHaloArgs wha;
   bool reduce_fused;  // the BatchNorm-backward sums of this layer come out of the kernel that produces its incoming gradient
   int dg_bn;          // >= 0: this layer's dgrad kernel writes the COMPLETE incoming gradient of conv #dg_bn and takes that
                       // layer's BatchNorm-backward sums in its epilogue (option dgrad_fuse); -1: no
@@ -79,6 +83,9 @@ struct unet_b200_trainer {
   uint8_t* x_in;      // copy of the network input (NHWC4 bf16)
   ub::PackJob* jobs_dev;   // job table of pack_all_kernel (one launch builds every bf16 operand copy of a step)
   int n_jobs, pack_blocks;
+  int pack_early_blocks;   // blocks of the jobs the first layers need (stem .. level 1): the rest is packed on the side stream
+  int pack_join_conv;      // forward conv index that is the first reader of a late-packed operand
+  cudaEvent_t ev_pack[2] = {nullptr, nullptr};
   // weight-gradient side stream (backward): the wgrad GEMM of layer L is forked off after the layer's dgrad and runs next to
   // the HBM-bound BatchNorm / pool backward passes of layer L-1; joined before the backward returns
   cudaStream_t s2 = nullptr;
@@ -326,7 +333,44 @@ int setup_conv_wgrad(TConv& c, int B) {
   } else {
     c.wX1 = c.wX0;
   }
-  return make_act_map(&c.wD, c.g, B, c.H, c.W, c.Cout, c.wa.TW, c.wa.TH, c.wa.TB);
+  rc = make_act_map(&c.wD, c.g, B, c.H, c.W, c.Cout, c.wa.TW, c.wa.TH, c.wa.TB);
+  if (rc != UB_OK) return rc;
+  // Cout == 64 on a map with W % 8 == 0 (the 224^2 level): the halo-patch kernel
+  c.w_halo = tl_opts->wgrad_halo && c.Cout == 64 && c.W % 8 == 0 && c.C0 % 64 == 0 && c.C1 % 64 == 0;
+  if (c.w_halo) {
+    ub::WgradHaloArgs& h = c.wha;
+    memset(&h, 0, sizeof(h));
+    h.B = B;
+    h.H = c.H;
+    h.W = c.W;
+    h.tiles_w = c.W / 8;
+    h.tiles_h = (c.H + 15) / 16;
+    h.ncb = cin / 64;
+    h.cb_split = c.C0 / 64;
+    const int total = h.tiles_w * h.tiles_h * B;
+    int ksl = cur_sms() / h.ncb;
+    if (ksl < 1) ksl = 1;
+    if (ksl > total) ksl = total;
+    h.kslices = ksl;
+    h.stages = ub::WgradHaloCfg::STAGES;
+    h.lc0 = lc0;
+    h.lc1 = lc1;
+    h.lcout = lcout;
+    h.s_co = c.wa.s_co;
+    h.s_ci = c.wa.s_ci;
+    h.s_tap = c.wa.s_tap;
+    rc = make_halo_map(&c.wXh0, c.x0, B, c.H, c.W, c.C0);
+    if (rc != UB_OK) return rc;
+    if (c.C1 > 0) {
+      rc = make_halo_map(&c.wXh1, c.x1, B, c.H, c.W, c.C1);
+      if (rc != UB_OK) return rc;
+    } else {
+      c.wXh1 = c.wXh0;
+    }
+    rc = make_box_map(&c.wDh, c.g, B, c.H, c.W, c.Cout, 8, 16);
+    if (rc != UB_OK) return rc;
+  }
+  return UB_OK;
 }
 
 // Backward of ConvTranspose2d(2x2, stride 2): maps for the 4-source dgrad GEMM and the 4-quad weight gradient.
@@ -548,6 +592,16 @@ int conv_wgrad_launch(const TConv& c, int B, const ub::GradRoute& route, long lo
     const int grid = tiles < 2 * cur_sms() ? tiles : 2 * cur_sms();
     ub_launch(ub::stem_wgrad_kernel, grid, 256, smem, st, reinterpret_cast<const uint2*>(c.x0),
                                                     reinterpret_cast<const __nv_bfloat16*>(c.g), B, c.H, c.W, c.C0, c.Cout, route, off);
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+  }
+  if (c.w_halo) {
+    UB_CUDA(ensure_smem(ub::wgrad_halo_kernel, AT_WGRAD_HALO, ub::WgradHaloCfg::SMEM_BYTES));
+    ub::WgradHaloArgs ha = c.wha;
+    ha.route = route;
+    ha.off = off;
+    ub_launch(ub::wgrad_halo_kernel, ha.ncb * ha.kslices, ub::WgradHaloCfg::THREADS, ub::WgradHaloCfg::SMEM_BYTES, st, c.wXh0, c.wXh1,
+              c.wDh, ha);
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
@@ -824,6 +878,9 @@ void unet_b200_trainer_destroy(unet_b200_trainer* t) {
   for (cudaEvent_t e : t->ev_fork) {
     if (e != nullptr) cudaEventDestroy(e);
   }
+  for (cudaEvent_t e : t->ev_pack) {
+    if (e != nullptr) cudaEventDestroy(e);
+  }
   if (t->s2 != nullptr) cudaStreamDestroy(t->s2);
   delete t;
 }
@@ -849,6 +906,7 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
     UB_CUDA(cudaStreamCreateWithFlags(&t->s2, cudaStreamNonBlocking));
     t->ev_fork.resize(t->convs.size() + t->ups.size() + 2 + 2 * (2 * t->levels + 3));
     for (cudaEvent_t& e : t->ev_fork) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t& e : t->ev_pack) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   {
     std::vector<ub::PackJob> jobs;
@@ -870,12 +928,19 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
       jobs.push_back(j);
       blocks += (int)((elems + ub::PACK_ELEMS_PER_BLOCK - 1) / ub::PACK_ELEMS_PER_BLOCK);
     };
+    // the jobs are in first-use order; the operands of the first EARLY convs (stem, enc0.conv1, level 1) are packed on the
+    // caller's stream, everything else on the side stream while those layers run (train_forward)
+    const int EARLY = t->levels >= 2 ? 4 : 0;
+    t->pack_early_blocks = 0;
+    t->pack_join_conv = EARLY;
+    int ci_idx = 0;
     for (TConv& c : t->convs) {
       if (c.stem && c.Cout == 64) {
         add(2, c.Cout, c.C0, 0, c.lCout, c.C0, 0, c.w_off, c.wp, nullptr, (size_t)c.Cout * 64);
       } else if (!c.stem) {
         add(0, c.Cout, c.C0, c.C1, c.lCout, c.lC0, c.lC1, c.w_off, c.wp, c.wd, (size_t)c.Cout * 9 * (c.C0 + c.C1));
       }
+      if (++ci_idx == EARLY) t->pack_early_blocks = blocks;
     }
     for (TConvT& u : t->ups) {
       add(1, u.f, u.Cin, 0, u.lf, u.lCin, 0, u.w_off, u.wp, u.wd, (size_t)4 * u.f * u.Cin);
@@ -903,7 +968,20 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   UB_CUDA(cudaMemcpyAsync(t->x_in, x_nhwc4, (size_t)B * t->H * t->W * 8, cudaMemcpyDeviceToDevice, st));
   UB_CUDA(cudaMemsetAsync(t->acc, 0, t->acc_bytes, st));
   // bf16 operand copies of the current fp32 parameters (forward layout + the rotated / transposed dgrad layout): ONE launch
-  ub_launch(ub::pack_all_kernel, t->pack_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs);
+  // (the operands of the first layers on `st`; the bulk - 124 MB of fp32 masters - on the side stream under those layers)
+  const bool pack_split = tl_opts->wgrad_stream && t->s2 != nullptr && t->pack_early_blocks > 0 &&
+                          t->pack_early_blocks < t->pack_blocks;
+  if (pack_split) {
+    UB_CUDA(cudaEventRecord(t->ev_pack[0], st));
+    UB_CUDA(cudaStreamWaitEvent(t->s2, t->ev_pack[0], 0));
+    ub_launch(ub::pack_all_kernel, t->pack_blocks - t->pack_early_blocks, 256, 0, t->s2, params, t->jobs_dev, t->n_jobs,
+              t->pack_early_blocks);
+    UB_CUDA(cudaGetLastError());
+    UB_CUDA(cudaEventRecord(t->ev_pack[1], t->s2));
+    ub_launch(ub::pack_all_kernel, t->pack_early_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0);
+  } else {
+    ub_launch(ub::pack_all_kernel, t->pack_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0);
+  }
   UB_CUDA(cudaGetLastError());
   for (TConv& c : t->convs) {
     if (c.stem && c.Cout != 64) {   // FP32-pipe stem (widths other than 64): fp32 weights, its own small kernel
@@ -914,7 +992,12 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   }
   // (no bias without BN: s1 / s2 stay zero - cleared with the accumulator region above - until the backward uses them)
   int rc;
+  bool pack_joined = !pack_split;
   for (int id : t->fwd_order) {
+    if (!pack_joined && (id < 0 || id >= t->pack_join_conv)) {   // first layer whose operands were packed on the side stream
+      UB_CUDA(cudaStreamWaitEvent(st, t->ev_pack[1], 0));
+      pack_joined = true;
+    }
     if (id >= 0) {
       rc = trainer_conv_forward(t, t->convs[id], id, params, running_mean, running_var, momentum, eps, st);
     } else {

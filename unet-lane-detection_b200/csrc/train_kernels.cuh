@@ -916,13 +916,14 @@ constexpr int PACK_ELEMS_PER_BLOCK = 256 * 8;
 // of w; kind 1: ConvT -> wp[(quad,co)][ci] and wd[ci][(quad,co)]; kind 2: tensor-core stem -> wp[co][k = tap*4+ci] (zero padded
 // to 64); kind 3: fp32 vector (ConvT bias, head weights) zero-extended from lCout to Cout entries.
 __global__ void __launch_bounds__(256)
-pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs) {
+pack_all_kernel(const float* __restrict__ params, const PackJob* __restrict__ jobs, int njobs, int block_lo) {
   pdl_enter();
+  const int blk = static_cast<int>(blockIdx.x) + block_lo;   // (the table may be worked off in several launches)
   int j = 0;
-  while (j + 1 < njobs && static_cast<int>(blockIdx.x) >= jobs[j + 1].block0) ++j;   // <= 32 jobs
+  while (j + 1 < njobs && blk >= jobs[j + 1].block0) ++j;   // <= 64 jobs
   const PackJob jb = jobs[j];
   const float* w = params + jb.w_off;
-  const int i0 = (static_cast<int>(blockIdx.x) - jb.block0) * PACK_ELEMS_PER_BLOCK + threadIdx.x;
+  const int i0 = (blk - jb.block0) * PACK_ELEMS_PER_BLOCK + threadIdx.x;
   if (jb.kind == 0) {
     const int Cin = jb.C0 + jb.C1, lCin = jb.lC0 + jb.lC1;
     const int total = jb.Cout * 9 * Cin;
