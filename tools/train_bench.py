@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--per-launch", default=None, help="substring: list every launch of matching kernels in order")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="one AdamW launch after the whole backward")
     ap.add_argument("--timeline", default=None, help="write every kernel of the profiled step (start, duration, stream) to this JSON")
     ap.add_argument("--opt", action="append", default=[], help="library switch name=value (unet_b200_set_option)")
     args = ap.parse_args()
@@ -34,7 +35,7 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(42)
     x = torch.randn(B, 3, H, W, device="cuda", generator=g)
     y = (torch.rand(B, 1, H, W, device="cuda", generator=g) < 0.085).float()
-    step = U.FusedTrainStep(net, cuda_graph=not args.eager)
+    step = U.FusedTrainStep(net, cuda_graph=not args.eager, overlap=not args.no_overlap)
     for _ in range(3):
         losses = step.step(x, y)
     torch.cuda.synchronize()

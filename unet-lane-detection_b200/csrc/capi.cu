@@ -58,6 +58,7 @@ struct Opts {
   int bwd_fuse = 0;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient (measured: no gain)
   int dgrad_fuse = 1;    // training: BatchNorm-backward reduction inside the tcgen05 dgrad epilogues that write the gradient
   int wgrad_halo = 1;    // training: Cout == 64 weight gradients on the halo-patch kernel (all nine taps per CTA)
+  int pack_split = 0;    // training: bulk of the operand pack on the side stream (measured: the block scheduler runs it first anyway)
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -1146,7 +1147,7 @@ int unet_b200_set_option(const char* name, int value) {
       {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
-      {"wgrad_halo", &g_opts.wgrad_halo}};
+      {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;

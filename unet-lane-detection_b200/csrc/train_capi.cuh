@@ -926,7 +926,8 @@ int unet_b200_trainer_bind(unet_b200_trainer* t, void* workspace_dev) {
       j.wp = reinterpret_cast<__nv_bfloat16*>(wp);
       j.wd = reinterpret_cast<__nv_bfloat16*>(wd);
       jobs.push_back(j);
-      blocks += (int)((elems + ub::PACK_ELEMS_PER_BLOCK - 1) / ub::PACK_ELEMS_PER_BLOCK);
+      // kind 0: one block per 32 x 32-channel tile (pack_one_block); the others: flat ranges of PACK_ELEMS_PER_BLOCK elements
+      blocks += kind == 0 ? (Cout / 32) * ((C0 + C1) / 32) : (int)((elems + ub::PACK_ELEMS_PER_BLOCK - 1) / ub::PACK_ELEMS_PER_BLOCK);
     };
     // the jobs are in first-use order; the operands of the first EARLY convs (stem, enc0.conv1, level 1) are packed on the
     // caller's stream, everything else on the side stream while those layers run (train_forward)
@@ -969,18 +970,23 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   UB_CUDA(cudaMemsetAsync(t->acc, 0, t->acc_bytes, st));
   // bf16 operand copies of the current fp32 parameters (forward layout + the rotated / transposed dgrad layout): ONE launch
   // (the operands of the first layers on `st`; the bulk - 124 MB of fp32 masters - on the side stream under those layers)
-  const bool pack_split = tl_opts->wgrad_stream && t->s2 != nullptr && t->pack_early_blocks > 0 &&
+  const bool pack_split = tl_opts->pack_split && tl_opts->wgrad_stream && t->s2 != nullptr && t->pack_early_blocks > 0 &&
                           t->pack_early_blocks < t->pack_blocks;
   if (pack_split) {
+    // first the small launch the stem is waiting for, then the bulk as a SMALL persistent grid on the side stream: launched
+    // with one CTA per work block it would sit in front of the stem in the block scheduler (measured: no overlap at all)
+    ub_launch(ub::pack_all_kernel, t->pack_early_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0, t->pack_early_blocks);
+    UB_CUDA(cudaGetLastError());
     UB_CUDA(cudaEventRecord(t->ev_pack[0], st));
     UB_CUDA(cudaStreamWaitEvent(t->s2, t->ev_pack[0], 0));
-    ub_launch(ub::pack_all_kernel, t->pack_blocks - t->pack_early_blocks, 256, 0, t->s2, params, t->jobs_dev, t->n_jobs,
-              t->pack_early_blocks);
+    int late = t->pack_blocks - t->pack_early_blocks;
+    const int cap = 4 * cur_sms();
+    ub_launch(ub::pack_all_kernel, late < cap ? late : cap, 256, 0, t->s2, params, t->jobs_dev, t->n_jobs, t->pack_early_blocks,
+              t->pack_blocks);
     UB_CUDA(cudaGetLastError());
     UB_CUDA(cudaEventRecord(t->ev_pack[1], t->s2));
-    ub_launch(ub::pack_all_kernel, t->pack_early_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0);
   } else {
-    ub_launch(ub::pack_all_kernel, t->pack_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0);
+    ub_launch(ub::pack_all_kernel, t->pack_blocks, 256, 0, st, params, t->jobs_dev, t->n_jobs, 0, t->pack_blocks);
   }
   UB_CUDA(cudaGetLastError());
   for (TConv& c : t->convs) {

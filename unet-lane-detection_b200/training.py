@@ -428,7 +428,8 @@ class FusedTrainStep:
         "auto"        nvlink when every rank of the group sits on its own visible GPU of one host (peer mapping possible),
                       else nccl (e.g. processes pinned with CUDA_VISIBLE_DEVICES to one device each).
         overlap: exchange every bucket on a side stream as soon as its backward stage has finished (default); False = one
-        bucket after the whole backward (the round-1 behaviour, kept for A/B measurement).
+        bucket after the whole backward (the round-1 behaviour, kept for A/B measurement). On ONE GPU there is nothing to
+        exchange, but the AdamW update of a bucket still runs on the side stream beside the rest of the backward.
         bucket_elems: gradient elements that must be final before a bucket is sent (plan_buckets)."""
         if exchange not in ("auto", "nccl", "nvlink", "nvlink_pull", "nvlink_mc", "nvlink_push"):
             raise ValueError("exchange must be 'auto', 'nccl', 'nvlink', 'nvlink_pull', 'nvlink_mc' or 'nvlink_push'")
@@ -475,7 +476,8 @@ class FusedTrainStep:
         world = self._world()
         if self.exchange == "auto":
             self.exchange = "nccl" if world == 1 else _pick_exchange(self.group)
-        if world > 1 and self.buckets is None:
+        staged = world > 1 or self.overlap     # one GPU: the optimizer of a bucket still runs beside the rest of the backward
+        if staged and self.buckets is None and (world > 1 or images_shape is not None):
             B, H, W = images_shape
             eng = _engine(self.model, device, B, H, W)
             self.buckets = (plan_buckets(eng.stage_ranges, self.bucket_elems, min(MIN_INTERVAL, self.bucket_elems))
@@ -501,9 +503,9 @@ class FusedTrainStep:
             if self.exp_avg is None or self.exp_avg.numel() != flat.numel() or self.exp_avg.device != flat.device:
                 self.exp_avg = torch.zeros_like(flat)
                 self.exp_avg_sq = torch.zeros_like(flat)
-            if world > 1 and (self.grads is None or self.grads.numel() != flat.numel()):
+            if staged and (self.grads is None or self.grads.numel() != flat.numel()):
                 self.grads = torch.empty_like(flat)
-        if world > 1 and self._side is None:
+        if staged and self._side is None:
             self._side = torch.cuda.Stream(device=device)
         if self._lr_on_dev != float(self.lr):
             self.lr_dev.fill_(float(self.lr))
@@ -533,7 +535,7 @@ class FusedTrainStep:
         losses, dz = bce_dice_loss(logits, masks.reshape(logits.shape), **self.loss_cfg)
         self.step_dev.add_(1)
         world = self._world()
-        if world == 1:
+        if world == 1 and not self.overlap:
             grads = train_backward(model, eng, dz)
             self._adamw_range(flat, grads, 0, flat.numel(), 1.0)
             return losses, grads
@@ -555,7 +557,8 @@ class FusedTrainStep:
                     if self.nvlink is not None:
                         self.nvlink.exchange_bucket(nb, self.step_dev, self.lr, self.lr_dev, self.betas, self.eps, self.weight_decay)
                     else:
-                        dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                        if world > 1:
+                            dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
                         self._adamw_range(flat, grads, lo, hi, 1.0 / world)
                 nb += 1
         with torch.cuda.stream(side):
