@@ -130,6 +130,7 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *                           separate reduction pass over g and y does not run
  *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
  *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
+ *   "host_pieces" (default 8) unet_b200_infer_u8_host_stream: pieces per pass (see there); 0 or 1 = pass-granular pipeline
  *   "stem_wide" (default 0) tensor-core stem on 4 x 32 pixel tiles (one contiguous 4 KB output row per TMA store) instead
  *                           of 16 x 8; bit-identical, measured +0.3 % (noise): the stem is bound by the write rate, not by
  *                           the store pattern
@@ -176,10 +177,20 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging_dev, const uint8_t*
                             int Ws, int swap_rb, const float* mean3, const float* std3, float threshold,
                             float* logits_host, float* probs_host, uint8_t* mask_host, void* stream);
 
-/* Same contract for ANY number of frames: the batch is cut into chunks of the plan's capacity and the H2D copy of chunk
- * i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i (two staging slots, two internal copy streams created
- * on first use). Host buffers should be pinned. staging_dev: unet_b200_infer_stream_staging_bytes(...) bytes. */
+/* Same contract for ANY number of frames: the batch is cut into passes of the plan's capacity; the H2D copies of pass
+ * i+1 and the D2H copies of pass i-1 overlap the kernels of pass i (two staging slots, two internal copy streams created
+ * on first use). Inside a pass the input copy, the preprocess and the two full-resolution layers at the start of the
+ * network, and the fused-head conv and the output copies at its end, run per PIECE of the pass (option "host_pieces",
+ * default 8 pieces; bf16 plans whose stem / first conv / last conv run on the tensor-core stem and halo kernels), so only
+ * the first piece's input copy and the last piece's output copy are not hidden behind kernels; other plans, and source
+ * frames more than 1.5x the size of the network input (whose copies take longer than those two layers), use a
+ * pass-granular pipeline with a short first pass. Host buffers should be pinned.
+ * staging_dev: unet_b200_infer_stream_staging_bytes(...) bytes.
+ * plan_host_pieces: pieces a full pass is cut into (0: pass-granular fallback); infer_stream_launches: kernels one call
+ * for `total` frames launches. */
 size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int Ws);
+int unet_b200_plan_host_pieces(const unet_b200_plan* p);
+int unet_b200_infer_stream_launches(const unet_b200_plan* p, int total, int Hs, int Ws);
 int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging_dev, const uint8_t* frames_host, int total, int Hs,
                                    int Ws, int swap_rb, const float* mean3, const float* std3, float threshold,
                                    float* logits_host, float* probs_host, uint8_t* mask_host, void* stream);

@@ -235,6 +235,35 @@ def test_infer_host_equals_device_path(U):
     assert torch.equal(m_host, m_dev.cpu())
 
 
+def test_infer_host_pieces_and_passes(U):
+    """unet_b200_infer_u8_host_stream: a pass is cut into pieces whose copies / preprocess / first and last layers are
+    pipelined (include/unet_b200.h). 77 camera frames through a plan of 32 (passes 32 / 32 / 13, two pieces each, ragged last
+    piece): logits and masks are bit-equal to the device-resident path, for the piece-wise and the pass-granular schedule."""
+    from unet_lane_detection_b200._lib import check, lib
+    ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    frames = torch.randint(0, 256, (77, 120, 160, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
+    outs = {}
+    try:
+        for pieces in (8, 0):
+            check(lib.unet_b200_set_option(b"host_pieces", pieces))
+            net = U.UNet(3, 1, [64, 128, 256, 512])
+            net.load_state_dict(ref.state_dict())
+            net = net.cuda().eval()
+            net.b200_chunk = 32
+            m_host = torch.zeros(77, 224, 224, dtype=torch.uint8).pin_memory()
+            l_host = torch.zeros(77, 224, 224, dtype=torch.float32).pin_memory()
+            net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)
+            net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)   # events / slots are reused
+            outs[pieces] = (m_host.clone(), l_host.clone(), net.gpu_launches)
+            if pieces:
+                l_dev, _, m_dev = net.predict_mask(frames.cuda(), swap_rb=True, want=("logits", "mask"))
+    finally:
+        check(lib.unet_b200_set_option(b"host_pieces", 8))
+    for pieces in (8, 0):
+        assert torch.equal(outs[pieces][0], m_dev.cpu()), pieces
+        assert torch.equal(outs[pieces][1], l_dev.cpu()), pieces
+
+
 def test_fused_head_and_halo_switches_agree(U):
     """The fused (1x1 head in the last conv's epilogue) and unfused paths, and the two 3x3 kernels, give the same net."""
     from unet_lane_detection_b200._lib import check, lib

@@ -51,6 +51,8 @@ _SIGS = {
     "unet_b200_infer_staging_bytes": (sz, [vp, i32, i32]),
     "unet_b200_infer_u8_host": (i32, [vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), f32, vp, vp, vp, vp]),
     "unet_b200_infer_stream_staging_bytes": (sz, [vp, i32, i32]),
+    "unet_b200_plan_host_pieces": (i32, [vp]),
+    "unet_b200_infer_stream_launches": (i32, [vp, i32, i32, i32]),
     "unet_b200_infer_u8_host_stream": (i32, [vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), f32, vp, vp, vp, vp]),
     "unet_b200_conv3x3": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "unet_b200_convT2x2": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, vp]),

@@ -59,6 +59,7 @@ struct Opts {
   int dgrad_fuse = 1;    // training: BatchNorm-backward reduction inside the tcgen05 dgrad epilogues that write the gradient
   int wgrad_halo = 1;    // training: Cout == 64 weight gradients on the halo-patch kernel (all nine taps per CTA)
   int pack_split = 0;    // training: bulk of the operand pack on the side stream (measured: the block scheduler runs it first anyway)
+  int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -429,12 +430,14 @@ int launch_stem_umma_t(const CUtensorMap& mw, const CUtensorMap& mo, ub::StemArg
 }
 
 // tw must be the tile width the output map `mo` was built for (make_stem_out_map)
+// b0: first image (x and the output map address the whole tensors; images [b0, b0 + B) are processed)
 int launch_stem_umma(const CUtensorMap& mw, const CUtensorMap& mo, const void* x, const float* bias, int B, int H, int W,
-                     int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr, int tw = 8) {
+                     int relu, cudaStream_t st, double* stat_sum = nullptr, double* stat_sumsq = nullptr, int tw = 8, int b0 = 0) {
   int rc = device_check();
   if (rc != UB_OK) return rc;
   ub::StemArgs a;
   a.B = B;
+  a.b0 = b0;
   a.H = H;
   a.W = W;
   a.tiles_w = a.tiles_h = 0;
@@ -542,6 +545,8 @@ struct unet_b200_plan {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr},
               ev_out_free[2] = {nullptr, nullptr}, ev_start = nullptr;
+  static constexpr int MAX_PIECES = 16;     // pieces of one pass (PieceHooks)
+  cudaEvent_t ev_piece_in[MAX_PIECES] = {}, ev_piece_cmp[MAX_PIECES] = {};
 };
 
 namespace {
@@ -976,6 +981,10 @@ void unet_b200_plan_destroy(unet_b200_plan* p) {
     if (p->ev_out_free[i]) cudaEventDestroy(p->ev_out_free[i]);
   }
   if (p->ev_start) cudaEventDestroy(p->ev_start);
+  for (int i = 0; i < unet_b200_plan::MAX_PIECES; ++i) {
+    if (p->ev_piece_in[i]) cudaEventDestroy(p->ev_piece_in[i]);
+    if (p->ev_piece_cmp[i]) cudaEventDestroy(p->ev_piece_cmp[i]);
+  }
   delete p;
 }
 size_t unet_b200_plan_workspace_bytes(const unet_b200_plan* p) { return p ? p->ws_bytes : 0; }
@@ -1147,7 +1156,8 @@ int unet_b200_set_option(const char* name, int value) {
       {"fuse_head", &g_opts.fuse_head}, {"stem_umma", &g_opts.stem_umma}, {"wgrad_rows64", &g_opts.wgrad_rows64},
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
-      {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split}};
+      {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
+      {"host_pieces", &g_opts.host_pieces}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
@@ -1157,8 +1167,27 @@ int unet_b200_set_option(const char* name, int value) {
   return fail(UB_ERR_ARG, "unknown option '%s'", name);
 }
 
+// Pieces (host-buffer entry point): the two layers of the full-resolution level at the START of the network (stem, enc0.conv1)
+// and the LAST layer (dec3.conv1 with the fused head) run once per piece of `piece` images instead of once per batch, with a
+// callback before the first / after the last: the caller hangs the piece's H2D copy + preprocess in front and its D2H copy
+// behind, so that only the first piece's input copy and the last piece's output copy are not hidden by kernels. Those three
+// layers have >= 392 tiles per image, so a piece of 32 images still fills the GPU; every other layer runs on the whole batch.
+struct PieceHooks {
+  int piece;                                            // images per piece
+  void* ctx;
+  int (*before)(void* ctx, int b0, int n);              // before the first layer works on images [b0, b0 + n)
+  int (*after)(void* ctx, int b0, int n);               // after the last layer has been enqueued for images [b0, b0 + n)
+};
+static bool plan_supports_pieces(const unet_b200_plan* p) {
+  if (p->split || p->layers.size() < 4) return false;
+  const Layer& l0 = p->layers[0];
+  const Layer& l1 = p->layers[1];
+  const Layer& ll = p->layers.back();
+  return l0.kind == L_STEM && l0.stem_tc && l1.kind == L_CONV && l1.halo && ll.kind == L_CONV && ll.halo && ll.fuse_head;
+}
+
 static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logits, float* probs, uint8_t* mask,
-                        float threshold, cudaStream_t st, std::vector<cudaEvent_t>* ev) {
+                        float threshold, cudaStream_t st, std::vector<cudaEvent_t>* ev, const PieceHooks* ph = nullptr) {
   if (p == nullptr || x == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (p->ws == nullptr) return fail(UB_ERR_STATE, "plan is not bound");
   if (batch < 1 || batch > p->Bc) return fail(UB_ERR_ARG, "batch %d outside [1,%d]", batch, p->Bc);
@@ -1169,10 +1198,48 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
   OptScope opt_scope(&p->opt);
   size_t ei = 0;
   if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
-  for (Layer& l : p->layers) {
+  if (ph != nullptr && (ph->piece < 1 || !plan_supports_pieces(p))) return fail(UB_ERR_STATE, "plan cannot run in pieces");
+  const int n_layers = (int)p->layers.size();
+  for (int li = 0; li < n_layers; ++li) {
+    Layer& l = p->layers[li];
     const float* bias = reinterpret_cast<const float*>(p->wt + l.b_off);
     void* out = p->ws + p->bufs[l.out].off;
     void* pool = l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr;
+    if (ph != nullptr && (li == 0 || li == n_layers - 1)) {
+      // piece-wise: (stem + enc0.conv1) per piece up front, the fused-head conv per piece at the end
+      for (int b0 = 0; b0 < batch; b0 += ph->piece) {
+        const int n = batch - b0 < ph->piece ? batch - b0 : ph->piece;
+        int rc;
+        if (li == 0) {
+          rc = ph->before(ph->ctx, b0, n);
+          if (rc != UB_OK) return rc;
+          rc = launch_stem_umma(l.mW, l.mOut, x, bias, n, l.H, l.W, l.relu, st, nullptr, nullptr, l.stem_tw, b0);
+          if (rc != UB_OK) return rc;
+          Layer& l1 = p->layers[1];
+          ub::HaloArgs a = halo_args(l1, n, reinterpret_cast<const float*>(p->wt + l1.b_off), p->ws + p->bufs[l1.out].off,
+                                     l1.pool >= 0 ? p->ws + p->bufs[l1.pool].off : nullptr);
+          a.b0 = b0;
+          rc = launch_halo(l1.block_n, l1.mA0, l1.mA1, l1.mW, l1.mOut, a, st);
+          if (rc != UB_OK) return rc;
+        } else {
+          ub::HaloArgs a = halo_args(l, n, bias, out, pool);
+          a.b0 = b0;
+          a.epi = ub::HEPI_HEAD;
+          a.head_w = reinterpret_cast<const float*>(p->wt + p->head_w_off);
+          a.head_b = p->head_bias;
+          a.thr = threshold;
+          a.logits = logits;
+          a.probs = probs;
+          a.mask = mask;
+          rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, a, st);
+          if (rc != UB_OK) return rc;
+          rc = ph->after(ph->ctx, b0, n);
+          if (rc != UB_OK) return rc;
+        }
+      }
+      if (li == 0) ++li;   // enc0.conv1 ran with the stem
+      continue;
+    }
     if (p->split) {
       // fp32-class plan: stem on the FP32 pipes from the fp32 NHWC4 image, every other layer = the per-tap
       // tcgen05 kernel over K sources (x[hi|lo] : 2C), (x[hi] : C) against weights [w_hi | w_hi | w_lo]; pools on hi + lo
@@ -1480,6 +1547,58 @@ size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int
   return n;
 }
 
+// pieces of a pass of n frames (0: the plan / the options do not run in pieces), and frames per piece
+static int host_piece_size(const unet_b200_plan* p, int n, int* np) {
+  *np = 0;
+  if (p->opt.host_pieces <= 1 || !plan_supports_pieces(p)) return 0;
+  const int pieces = p->opt.host_pieces < unet_b200_plan::MAX_PIECES ? p->opt.host_pieces : unet_b200_plan::MAX_PIECES;
+  int piece = ((n + pieces - 1) / pieces + 7) & ~7;      // multiples of 8 frames, at least 16
+  if (piece < 16) piece = 16;
+  *np = (n + piece - 1) / piece;
+  return piece;
+}
+
+int unet_b200_plan_host_pieces(const unet_b200_plan* p) {
+  if (p == nullptr) return 0;
+  int np = 0;
+  host_piece_size(p, p->Bc, &np);
+  return np;
+}
+
+// Pass schedule of unet_b200_infer_u8_host_stream: frames of pass `it` when `left` of `total` frames remain. With pieces a
+// pass takes the plan's capacity; without, the FIRST pass is a quarter of the capacity, so that the bulk of the copies runs
+// under the first pass's kernels. Pieces are used unless the source frames are much larger than the network input
+// (copy-bound: the H2D copy of a pass takes longer than the two layers its pieces could hide it behind - 480x640 camera
+// frames measured 15.9 k frames/s piece-wise, 16.0 k pass-granular; 224x224 frames 16.7 k against 16.2 k).
+static bool host_copy_bound(const unet_b200_plan* p, size_t frame_bytes) { return 2 * frame_bytes > 3 * (size_t)p->H * p->W * 3; }
+static int host_pass_size(const unet_b200_plan* p, int it, int left, int total, bool pieces, size_t frame_bytes) {
+  int n = p->Bc;
+  if (it == 0 && !pieces) {
+    int first = (p->Bc / 4) & ~7;
+    if (first < 8) first = 8;
+    if (first * 2 >= total) first = total < p->Bc ? total : p->Bc;
+    n = first;
+  }
+  return n < left ? n : left;
+}
+
+// kernels unet_b200_infer_u8_host_stream launches for `total` frames of Hs x Ws pixels (preprocess included)
+int unet_b200_infer_stream_launches(const unet_b200_plan* p, int total, int Hs, int Ws) {
+  if (p == nullptr || total < 1) return 0;
+  const int per_pass = unet_b200_forward_launches(p) + 1;
+  int launches = 0;
+  int np = 0;
+  const bool pieces = host_piece_size(p, p->Bc, &np) > 0 && !host_copy_bound(p, (size_t)Hs * Ws * 3);
+  int it = 0;
+  for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
+    n = host_pass_size(p, it, total - b0, total, pieces, (size_t)Hs * Ws * 3);
+    np = 1;
+    if (pieces) host_piece_size(p, n, &np);
+    launches += per_pass + 4 * (np - 1);   // preprocess, stem, enc0.conv1 and the fused-head conv once per piece
+  }
+  return launches;
+}
+
 int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8_t* frames, int total, int Hs, int Ws,
                                    int swap_rb, const float* mean3, const float* std3, float threshold, float* logits_h,
                                    float* probs_h, uint8_t* mask_h, void* stream) {
@@ -1523,15 +1642,110 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
   UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
   UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
   const size_t hw = (size_t)p->H * p->W * p->out_ch;   // output elements per frame
-  // Chunk schedule: the H2D copy of the FIRST chunk is the one copy no kernel can hide, so the first chunk is a quarter of
-  // the plan's capacity; every later chunk is plan-sized and its copy runs under the previous chunk's kernels.
-  int first = (p->Bc / 4) & ~7;
-  if (first < 8) first = 8;
-  if (first * 2 >= total) first = total < p->Bc ? total : p->Bc;
+  OptScope opt_scope(&p->opt);
+  // ---- piece-wise passes (default): every pass takes up to Bc frames; inside a pass the input copy, the preprocess and the
+  // two full-resolution layers at the start run per PIECE, and so do the fused-head conv and the output copies at the end
+  // (forward_impl, PieceHooks). Not hidden: the first piece's H2D copy and the last piece's D2H copy - 1/8 of what a
+  // pass-granular pipeline leaves exposed - and no pass has to be cut short to get the pipeline going.
+  int np_cap = 0;
+  if (host_piece_size(p, p->Bc, &np_cap) > 0 && !host_copy_bound(p, frame_bytes)) {
+    struct Ctx {
+      unet_b200_plan* p;
+      cudaStream_t st;
+      const uint8_t* frames_h;      // this pass's frames on the host
+      uint8_t* d_frames;            // this pass's frame slot
+      void* d_x;
+      float *d_logits, *d_probs;
+      uint8_t* d_mask;
+      float *logits_h, *probs_h;    // this pass's rows of the caller's outputs (or null)
+      uint8_t* mask_h;
+      size_t frame_bytes, hw;
+      int Hs, Ws, swap_rb, piece, n, slot;
+      const float *mean3, *std3;
+    } c;
+    c.p = p;
+    c.st = st;
+    c.d_x = d_x;
+    c.frame_bytes = frame_bytes;
+    c.hw = hw;
+    c.Hs = Hs;
+    c.Ws = Ws;
+    c.swap_rb = swap_rb;
+    c.mean3 = mean3;
+    c.std3 = std3;
+    PieceHooks ph;
+    ph.ctx = &c;
+    ph.before = [](void* v, int b0, int n) -> int {
+      Ctx* c = static_cast<Ctx*>(v);
+      unet_b200_plan* p = c->p;
+      const int i = b0 / c->piece;
+      UB_CUDA(cudaStreamWaitEvent(c->st, p->ev_piece_in[i], 0));
+      int rc = preprocess_impl(c->d_frames + (size_t)b0 * c->frame_bytes, n, c->Hs, c->Ws, (size_t)c->Ws * 3, c->frame_bytes, p->H,
+                               p->W, c->swap_rb, c->mean3, c->std3, static_cast<uint8_t*>(c->d_x) + (size_t)b0 * p->H * p->W * 8,
+                               false, nullptr, c->st);
+      if (rc != UB_OK) return rc;
+      if (b0 + n >= c->n) UB_CUDA(cudaEventRecord(p->ev_in_free[c->slot], c->st));   // the frame slot has been read
+      return UB_OK;
+    };
+    ph.after = [](void* v, int b0, int n) -> int {
+      Ctx* c = static_cast<Ctx*>(v);
+      unet_b200_plan* p = c->p;
+      const int i = b0 / c->piece;
+      const size_t o = (size_t)b0 * c->hw, cnt = (size_t)n * c->hw;
+      UB_CUDA(cudaEventRecord(p->ev_piece_cmp[i], c->st));
+      UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_piece_cmp[i], 0));
+      if (c->logits_h) UB_CUDA(cudaMemcpyAsync(c->logits_h + o, c->d_logits + o, cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+      if (c->probs_h) UB_CUDA(cudaMemcpyAsync(c->probs_h + o, c->d_probs + o, cnt * 4, cudaMemcpyDeviceToHost, p->s_out));
+      if (c->mask_h) UB_CUDA(cudaMemcpyAsync(c->mask_h + o, c->d_mask + o, cnt, cudaMemcpyDeviceToHost, p->s_out));
+      if (b0 + n >= c->n) UB_CUDA(cudaEventRecord(p->ev_out_free[c->slot], p->s_out));
+      return UB_OK;
+    };
+    int it = 0;
+    for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
+      n = host_pass_size(p, it, total - b0, total, true, frame_bytes);
+      const int slot = it & 1;
+      int np = 0;
+      const int piece = host_piece_size(p, n, &np);
+      for (int i = 0; i < np; ++i) {
+        if (p->ev_piece_in[i] == nullptr) {
+          UB_CUDA(cudaEventCreateWithFlags(&p->ev_piece_in[i], cudaEventDisableTiming));
+          UB_CUDA(cudaEventCreateWithFlags(&p->ev_piece_cmp[i], cudaEventDisableTiming));
+        }
+      }
+      // H2D of every piece of this pass (the slot is free once pass it-2's last preprocess has read it)
+      if (it >= 2) UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_in_free[slot], 0));
+      for (int i = 0; i < np; ++i) {
+        const int pb = i * piece, pn = n - pb < piece ? n - pb : piece;
+        UB_CUDA(cudaMemcpyAsync(d_frames[slot] + (size_t)pb * frame_bytes, frames + (size_t)(b0 + pb) * frame_bytes,
+                                frame_bytes * pn, cudaMemcpyHostToDevice, p->s_in));
+        UB_CUDA(cudaEventRecord(p->ev_piece_in[i], p->s_in));
+      }
+      if (it >= 2) UB_CUDA(cudaStreamWaitEvent(st, p->ev_out_free[slot], 0));  // pass it-2's results have left the output slot
+      c.frames_h = frames + (size_t)b0 * frame_bytes;
+      c.d_frames = d_frames[slot];
+      c.d_logits = d_logits[slot];
+      c.d_probs = d_probs[slot];
+      c.d_mask = d_mask[slot];
+      c.logits_h = logits_h ? logits_h + (size_t)b0 * hw : nullptr;
+      c.probs_h = probs_h ? probs_h + (size_t)b0 * hw : nullptr;
+      c.mask_h = mask_h ? mask_h + (size_t)b0 * hw : nullptr;
+      c.piece = piece;
+      c.n = n;
+      c.slot = slot;
+      ph.piece = piece;
+      int rc = forward_impl(p, d_x, n, logits_h ? d_logits[slot] : nullptr, probs_h ? d_probs[slot] : nullptr,
+                            mask_h ? d_mask[slot] : nullptr, threshold, st, nullptr, &ph);
+      if (rc != UB_OK) return rc;
+    }
+    UB_CUDA(cudaStreamSynchronize(p->s_out));
+    UB_CUDA(cudaStreamSynchronize(st));
+    return UB_OK;
+  }
+  // Pass-granular fallback: the H2D copy of the FIRST pass is the one copy no kernel can hide, so the first pass is a quarter
+  // of the plan's capacity (host_pass_size); every later pass is plan-sized and its copy runs under the previous pass's kernels.
   int it = 0;
   for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
-    n = (it == 0) ? first : p->Bc;
-    if (n > total - b0) n = total - b0;
+    n = host_pass_size(p, it, total - b0, total, false, frame_bytes);
     const int slot = it & 1;
     const size_t npix = (size_t)n * hw;
     // H2D of chunk `it` (runs while chunk it-1 computes); the slot is free once chunk it-2's preprocess has read it

@@ -37,7 +37,8 @@ namespace ub {
 enum : int { HEPI_STORE = 0, HEPI_HEAD = 1 };
 
 struct HaloArgs {
-  int B, H, W;
+  int B, H, W;           // images [b0, b0 + B) of the tensors behind the maps / output pointers
+  int b0;
   int tiles_w, tiles_h;  // 8-pixel / 16-row tiles per image
   int kc0, kc1;          // 64-channel blocks from source 0 / source 1
   int resident;          // 1: all weight tiles fit the ring and are loaded once
@@ -153,8 +154,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       bool first = true;
       for (int t = t_first; t - static_cast<int>(rank) < total_tiles; t += t_step) {
         // a tile index past the end (odd tile count): image index == B is fully out of bounds -> the box is zero-filled
-        const int b = t < total_tiles ? t / tiles_per_img : a.B;
-        const int ti = t < total_tiles ? t - b * tiles_per_img : 0;
+        const int br = t < total_tiles ? t / tiles_per_img : a.B;
+        const int ti = t < total_tiles ? t - br * tiles_per_img : 0;
+        const int b = a.b0 + br;
         const int w0 = (ti % a.tiles_w) * 8;
         const int h0 = (ti / a.tiles_w) * 16;
         for (int c = 0; c < KC; ++c) {
@@ -284,7 +286,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       const int yb = yt / tiles_per_img;
       const int yti = yt - yb * tiles_per_img;
       mbar_expect_tx(ybar, 4096);
-      tma_load_4d(ystg, &tmY, ybar, n, (yti % a.tiles_w) * 8, (yti / a.tiles_w) * 16 + 4 * q, yb);
+      tma_load_4d(ystg, &tmY, ybar, n, (yti % a.tiles_w) * 8, (yti / a.tiles_w) * 16 + 4 * q, a.b0 + yb);
       yt += y_step;
     };
     if (bnb) {
@@ -296,8 +298,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       const int acc = it & 1;
       if (HALVES == 1 && acc != cg) continue;
       const bool live = t < total_tiles;
-      const int b = live ? t / tiles_per_img : 0;
-      const int ti = live ? t - b * tiles_per_img : 0;
+      const int br = live ? t / tiles_per_img : 0;
+      const int ti = live ? t - br * tiles_per_img : 0;
+      const int b = a.b0 + br;
       const int w0 = (ti % a.tiles_w) * 8;
       const int h0 = (ti / a.tiles_w) * 16;
       mbar_wait(&tfull[acc], (it >> 1) & 1);

@@ -16,7 +16,8 @@
 namespace ub {
 
 struct StemArgs {
-  int B, H, W;
+  int B, H, W;            // images [b0, b0 + B) of the tensors behind x / the output map
+  int b0;
   int tiles_w, tiles_h;   // TW-pixel x (128/TW)-row tiles per image
   int relu;
   const uint2* x;         // [B,H,W] x 4 bf16
@@ -160,8 +161,9 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const int r1 = (pt + 128) / PW, c1 = (pt + 128) % PW;
     const bool has1 = pt + 128 < PATCH;
     auto fetch = [&](int t, uint2& v0, uint2& v1) {
-      const int b = t / tiles_per_img;
-      const int ti = t - b * tiles_per_img;
+      const int br = t / tiles_per_img;
+      const int ti = t - br * tiles_per_img;
+      const int b = a.b0 + br;
       const int w0 = (ti % a.tiles_w) * TW - 1;
       const int h0 = (ti / a.tiles_w) * TH - 1;
       const uint2* img = a.x + static_cast<size_t>(b) * a.H * a.W;
@@ -217,8 +219,9 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       if ((it & 1) != cg) continue;
       const int acc = it & (Cfg::ACC_STAGES - 1);
-      const int b = t / tiles_per_img;
-      const int ti = t - b * tiles_per_img;
+      const int br = t / tiles_per_img;
+      const int ti = t - br * tiles_per_img;
+      const int b = a.b0 + br;
       const int w0 = (ti % a.tiles_w) * TW;
       const int h0 = (ti / a.tiles_w) * TH;
       mbar_wait(&tfull[acc], (it / Cfg::ACC_STAGES) & 1);

@@ -102,9 +102,9 @@ class UNet(nn.Module):
         if prec not in PRECISIONS:
             raise ValueError("b200_precision must be 'bf16' or 'fp32'")
         cap = min(max(1, int(self.b200_chunk)), batch) if batch < self.b200_chunk else int(self.b200_chunk)
-        if pipelined and batch >= 64 and cap >= batch:
-            # host-buffer entry: a batch that fits one pass is still cut in two, so that the H2D copy of the second half and
-            # the D2H copy of the first overlap the kernels (a single chunk would serialise copy -> compute -> copy)
+        if pipelined == "halved" and batch >= 64 and cap >= batch:
+            # host-buffer entry of a plan that cannot run in pieces: a batch that fits one pass is still cut in two, so that
+            # the H2D copy of the second half and the D2H copy of the first overlap the kernels
             cap = (batch + 1) // 2
         key = (str(device), cap, H, W, prec)
         eng = self._engines.get(key)
@@ -231,20 +231,20 @@ class UNet(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("UNet (B200): model parameters are not on a CUDA device (no CPU fallback)")
-        eng = self._engine(dev, size[0], size[1], B, pipelined=True)
+        eng = self._engine(dev, size[0], size[1], B)
+        if lib.unet_b200_plan_host_pieces(eng.handle) == 0:
+            eng = self._engine(dev, size[0], size[1], B, pipelined="halved")    # (pass-granular pipeline: two passes at least)
         skey = (Hs, Ws)
         if getattr(eng, "staging_key", None) != skey:
             eng.staging = torch.empty(lib.unet_b200_infer_stream_staging_bytes(eng.handle, Hs, Ws), dtype=torch.uint8, device=dev)
             eng.staging_key = skey
         st = torch.cuda.current_stream().cuda_stream
-        # one call for the whole batch: chunks of eng.cap frames, copies of neighbouring chunks overlap the kernels
+        # one call for the whole batch: passes of eng.cap frames; the copies are pipelined with the kernels piece by piece
         check(lib.unet_b200_infer_u8_host_stream(
             eng.handle, eng.staging.data_ptr(), frames_host.data_ptr(), B, Hs, Ws, int(swap_rb), f3(MEAN_255), f3(STD_255),
             float(threshold), None if logits_out is None else logits_out.data_ptr(),
             None if probs_out is None else probs_out.data_ptr(), None if mask_out is None else mask_out.data_ptr(), st))
-        first = max(8, (eng.cap // 4) & ~7)           # chunk schedule of unet_b200_infer_u8_host_stream: short first chunk
-        first = min(B, eng.cap) if first * 2 >= B else first
-        self.gpu_launches += (1 + (B - first + eng.cap - 1) // eng.cap) * (eng.launches + 1)
+        self.gpu_launches += lib.unet_b200_infer_stream_launches(eng.handle, B, Hs, Ws)
         return mask_out, probs_out, logits_out
 
     def profile_layers(self, x4):
