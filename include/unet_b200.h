@@ -131,6 +131,11 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
  *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
  *   "host_pieces" (default 8) unet_b200_infer_u8_host_stream: pieces per pass (see there); 0 or 1 = pass-granular pipeline
+ *   "stem_fuse" (default 0) inference plans: the stem is computed inside the patch producer of the first block's second
+ *                           conv (stem_halo2_kernel: a small tensor-core GEMM per tile fills the halo'd shared-memory patch), so
+ *                           the stem's 64-channel output is never written to or read from HBM; bit-identical results.
+ *                           Measured on B200: 1.46-1.58 ms against 0.61 + 0.82 ms for the two kernels (256 frames) - the fused
+ *                           kernel is bound by shared-memory bandwidth - so it is off
  *   "stem_wide" (default 0) tensor-core stem on 4 x 32 pixel tiles (one contiguous 4 KB output row per TMA store) instead
  *                           of 16 x 8; bit-identical, measured +0.3 % (noise): the stem is bound by the write rate, not by
  *                           the store pattern

@@ -264,6 +264,34 @@ def test_infer_host_pieces_and_passes(U):
         assert torch.equal(outs[pieces][1], l_dev.cpu()), pieces
 
 
+@pytest.mark.parametrize("feats,B,H,W", [([64, 128, 256, 512], 3, 224, 224), ([64, 128], 5, 40, 56), ([32, 64], 1, 16, 8),
+                                         ([64, 128], 2, 72, 200)])
+def test_stem_fused_into_second_conv_is_bit_identical(U, feats, B, H, W):
+    """Option stem_fuse (off by default - same speed): the stem conv runs inside the patch producer of enc0.conv1 (stem_halo2_kernel) and its
+    output never goes to HBM. Same MMAs and rounding points as the two-kernel path: logits are bit-equal, including ragged
+    tiles (rows 40 = 2 x 16 + 8), an odd tile count (the CTA pair's missing tile), a single pair and zero-extended widths."""
+    from unet_lane_detection_b200._lib import check, lib
+    ref, _ = make_pair(U, feats, gain=40.0)
+    x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(8)).cuda()
+    outs, launches = [], []
+    try:
+        for fuse in (1, 0):
+            check(lib.unet_b200_set_option(b"stem_fuse", fuse))
+            net = U.UNet(3, 1, feats)
+            net.load_state_dict(ref.state_dict())
+            net = net.cuda().eval()
+            with torch.no_grad():
+                outs.append(net(x).clone())
+            launches.append(net.gpu_launches)
+    finally:
+        check(lib.unet_b200_set_option(b"stem_fuse", 0))
+    assert torch.equal(outs[0], outs[1])
+    assert launches[0] == launches[1] - 1          # one kernel fewer
+    with torch.no_grad():
+        want = ref(x.cpu())
+    assert (outs[0].cpu() - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
 def test_fused_head_and_halo_switches_agree(U):
     """The fused (1x1 head in the last conv's epilogue) and unfused paths, and the two 3x3 kernels, give the same net."""
     from unet_lane_detection_b200._lib import check, lib

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libunet_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "conv_umma.cuh", "conv_halo.cuh", "stem_umma.cuh", "epilogue.cuh", "aux_kernels.cuh", "train_kernels.cuh",
+HEADERS = ["ptx.cuh", "conv_umma.cuh", "conv_halo.cuh", "stem_umma.cuh", "stem_halo.cuh", "epilogue.cuh", "aux_kernels.cuh", "train_kernels.cuh",
            "wgrad_umma.cuh", "wgrad_halo.cuh", "stem_wgrad_umma.cuh", "train_capi.cuh", os.path.join("..", "..", "include", "unet_b200.h")]
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",

@@ -14,6 +14,7 @@
 #include "conv_halo.cuh"
 #include "conv_umma.cuh"
 #include "stem_umma.cuh"
+#include "stem_halo.cuh"
 
 namespace {
 
@@ -60,6 +61,8 @@ struct Opts {
   int wgrad_halo = 1;    // training: Cout == 64 weight gradients on the halo-patch kernel (all nine taps per CTA)
   int pack_split = 0;    // training: bulk of the operand pack on the side stream (measured: the block scheduler runs it first anyway)
   int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
+  int stem_fuse = 0;     // inference: the stem runs inside enc0.conv1's patch producer (stem_halo2_kernel), its output never stored
+                         // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -89,6 +92,7 @@ enum AttrSlot : int {
   AT_BNFUSE = 21,
   AT_STEM_WIDE = 22,
   AT_WGRAD_HALO = 23,
+  AT_STEM_HALO = 24,
 };
 struct DevState {
   std::atomic<int> num_sms{0};
@@ -480,6 +484,8 @@ struct Layer {
   bool halo;       // runs on conv_halo_kernel
   bool fuse_head;  // last conv: 1x1 head + sigmoid + mask evaluated in its epilogue
   bool stem_tc;    // stem on tensor cores (Cout == 64)
+  bool fuse_stem;  // enc0.conv1 only: the stem is computed inside this layer's patch producer (stem_halo.cuh), no stem launch
+  CUtensorMap mWs; //   its weight map (the stem's packed [64][64] weights, box of 32 rows)
   int stem_tw;     // its tile width (8 or 32), fixed when the layer is created
   CUtensorMap mA0, mA1, mW;
   CUtensorMap mOut, mPool;  // TMA-store targets (halo layers)
@@ -961,6 +967,13 @@ int unet_b200_plan_create_ex(unet_b200_plan** out, int max_batch, int H, int W, 
     Layer& last = p->layers.back();
     last.fuse_head = tl_opts->fuse_head && out_channels == 1 && last.kind == L_CONV && last.halo && last.Cout == 64;
   }
+  if (p->layers.size() >= 2) {
+    // the stem inside enc0.conv1 (stem_halo.cuh): tensor-core stem, second conv 64 -> 64 on the CTA-pair halo kernel
+    const Layer& l0 = p->layers[0];
+    Layer& l1 = p->layers[1];
+    l1.fuse_stem = tl_opts->stem_fuse && tl_opts->halo2 && !p->split && l0.kind == L_STEM && l0.stem_tc && l1.kind == L_CONV &&
+                   l1.halo && l1.C0 == 64 && l1.C1 == 0 && l1.Cout == 64;
+  }
   p->head_w_off = p->wt_bytes;
   p->wt_bytes += align_up((size_t)out_channels * fp[0] * 4 * (p->split ? 2 : 1), 256);   // split: the weight vector twice (hi + lo)
   p->head_b_off = p->wt_bytes;
@@ -1009,6 +1022,11 @@ int unet_b200_plan_bind(unet_b200_plan* p, void* workspace_dev, void* weights_de
         if (rc != UB_OK) return rc;
         rc = make_stem_out_map(&l.mOut, p->ws + p->bufs[l.out].off, p->Bc, l.H, l.W, l.stem_tw);
         if (rc != UB_OK) return rc;
+        Layer& l1 = p->layers[1];
+        if (l1.fuse_stem) {
+          rc = make_w_map_box(&l1.mWs, p->wt + l.w_off, 64, 64, 32);
+          if (rc != UB_OK) return rc;
+        }
       }
       continue;
     }
@@ -1143,6 +1161,7 @@ int unet_b200_plan_set_head(unet_b200_plan* p, const float* w, const float* bias
 int unet_b200_forward_launches(const unet_b200_plan* p) {
   if (p == nullptr) return 0;
   int n = (int)p->layers.size() + (p->layers.back().fuse_head ? 0 : 1);
+  if (p->layers.size() > 1 && p->layers[1].fuse_stem) --n;   // the stem runs inside enc0.conv1
   if (p->split) {
     for (const Layer& l : p->layers) n += l.pool >= 0 ? 1 : 0;   // the 2x2 pools are their own kernels there
   }
@@ -1157,7 +1176,7 @@ int unet_b200_set_option(const char* name, int value) {
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
       {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
-      {"host_pieces", &g_opts.host_pieces}};
+      {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
@@ -1165,6 +1184,37 @@ int unet_b200_set_option(const char* name, int value) {
     }
   }
   return fail(UB_ERR_ARG, "unknown option '%s'", name);
+}
+
+// Stem + enc0.conv1 as one kernel (stem_halo.cuh) on images [b0, b0 + batch); needs at least two tiles (a CTA pair).
+static bool stem_fused(const unet_b200_plan* p, int batch) {
+  if (p->layers.size() < 2 || !p->layers[1].fuse_stem) return false;
+  const Layer& l1 = p->layers[1];
+  return ((l1.W + 7) / 8) * ((l1.H + 15) / 16) * batch >= 2;
+}
+static int launch_stem_halo(unet_b200_plan* p, const void* x, int batch, int b0, cudaStream_t st) {
+  const Layer& l0 = p->layers[0];
+  const Layer& l1 = p->layers[1];
+  UB_CUDA(ensure_smem(ub::stem_halo2_kernel, AT_STEM_HALO, ub::StemHaloCfg::SMEM_BYTES));
+  ub::StemHaloArgs a;
+  a.B = batch;
+  a.H = l1.H;
+  a.W = l1.W;
+  a.b0 = b0;
+  a.tiles_w = (l1.W + 7) / 8;
+  a.tiles_h = (l1.H + 15) / 16;
+  a.x = reinterpret_cast<const uint2*>(x);
+  a.stem_bias = reinterpret_cast<const float*>(p->wt + l0.b_off);
+  a.bias = reinterpret_cast<const float*>(p->wt + l1.b_off);
+  a.relu = l1.relu;
+  a.pool_out = l1.pool >= 0 ? reinterpret_cast<__nv_bfloat16*>(p->ws + p->bufs[l1.pool].off) : nullptr;
+  const int total = a.tiles_w * a.tiles_h * batch;
+  const int pairs = (total + 1) / 2;
+  const int max_pairs = cur_sms() / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);   // cluster size 2 (__cluster_dims__)
+  ub_launch(ub::stem_halo2_kernel, grid, ub::StemHaloCfg::THREADS, ub::StemHaloCfg::SMEM_BYTES, st, l1.mW, l1.mWs, l1.mOut, a);
+  UB_CUDA(cudaGetLastError());
+  return UB_OK;
 }
 
 // Pieces (host-buffer entry point): the two layers of the full-resolution level at the START of the network (stem, enc0.conv1)
@@ -1213,14 +1263,19 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
         if (li == 0) {
           rc = ph->before(ph->ctx, b0, n);
           if (rc != UB_OK) return rc;
-          rc = launch_stem_umma(l.mW, l.mOut, x, bias, n, l.H, l.W, l.relu, st, nullptr, nullptr, l.stem_tw, b0);
-          if (rc != UB_OK) return rc;
-          Layer& l1 = p->layers[1];
-          ub::HaloArgs a = halo_args(l1, n, reinterpret_cast<const float*>(p->wt + l1.b_off), p->ws + p->bufs[l1.out].off,
-                                     l1.pool >= 0 ? p->ws + p->bufs[l1.pool].off : nullptr);
-          a.b0 = b0;
-          rc = launch_halo(l1.block_n, l1.mA0, l1.mA1, l1.mW, l1.mOut, a, st);
-          if (rc != UB_OK) return rc;
+          if (stem_fused(p, n)) {
+            rc = launch_stem_halo(p, x, n, b0, st);
+            if (rc != UB_OK) return rc;
+          } else {
+            rc = launch_stem_umma(l.mW, l.mOut, x, bias, n, l.H, l.W, l.relu, st, nullptr, nullptr, l.stem_tw, b0);
+            if (rc != UB_OK) return rc;
+            Layer& l1 = p->layers[1];
+            ub::HaloArgs a = halo_args(l1, n, reinterpret_cast<const float*>(p->wt + l1.b_off), p->ws + p->bufs[l1.out].off,
+                                       l1.pool >= 0 ? p->ws + p->bufs[l1.pool].off : nullptr);
+            a.b0 = b0;
+            rc = launch_halo(l1.block_n, l1.mA0, l1.mA1, l1.mW, l1.mOut, a, st);
+            if (rc != UB_OK) return rc;
+          }
         } else {
           ub::HaloArgs a = halo_args(l, n, bias, out, pool);
           a.b0 = b0;
@@ -1267,6 +1322,11 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
                   l.Cout / 8, reinterpret_cast<uint4*>(pool));
         UB_CUDA(cudaGetLastError());
       }
+    } else if (l.kind == L_STEM && l.stem_tc && stem_fused(p, batch)) {
+      // (computed inside the next layer)
+    } else if (li == 1 && l.fuse_stem && stem_fused(p, batch)) {
+      int rc = launch_stem_halo(p, x, batch, 0, st);
+      if (rc != UB_OK) return rc;
     } else if (l.kind == L_STEM && l.stem_tc) {
       int rc = launch_stem_umma(l.mW, l.mOut, x, bias, batch, l.H, l.W, l.relu, st, nullptr, nullptr, l.stem_tw);
       if (rc != UB_OK) return rc;
