@@ -91,13 +91,21 @@ __device__ __forceinline__ void epi_stage_row(uint8_t* tile, int row, const uint
 __device__ __forceinline__ void epi_stats_accumulate(const uint8_t* tile, int lane, uint32_t valid_mask, float (&acc)[4]) {
   const uint32_t base = smem_u32(tile) + (lane & 3) * 4;
   const int chunk = lane >> 2;
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    if ((valid_mask >> r) & 1u) {
-      uint32_t w;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((chunk ^ (r & 7)) << 4)));
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
-      const float lo = __low2float(h), hi = __high2float(h);
+  // eight rows per trip: the eight loads go out back to back and the arithmetic follows (one load per row behind a per-row
+  // branch left every load's full shared-memory latency exposed: the walk cost ~2 k cycles per unit, ncu short-scoreboard
+  // stalls on the unpack instructions); rows outside the tensor are masked AFTER the load (their staged values are finite)
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(base + (r0 + i) * 128 + ((chunk ^ i) << 4)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool valid = (valid_mask >> (r0 + i)) & 1u;
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      const float lo = valid ? __low2float(h) : 0.f, hi = valid ? __high2float(h) : 0.f;
       acc[0] += lo;
       acc[1] = fmaf(lo, lo, acc[1]);
       acc[2] += hi;
@@ -148,18 +156,25 @@ __device__ __forceinline__ void epi_bnbwd_accumulate(const uint8_t* gtile, const
   const uint32_t off = (lane & 3) * 4;
   const uint32_t gbase = smem_u32(gtile) + off, ybase = smem_u32(ytile) + off;
   const int chunk = lane >> 2;
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    if ((valid_mask >> r) & 1u) {
-      const uint32_t o = r * 128 + ((chunk ^ (r & 7)) << 4);
-      uint32_t wg, wy;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wg) : "r"(gbase + o));
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wy) : "r"(ybase + o));
-      const __nv_bfloat162 hg = *reinterpret_cast<const __nv_bfloat162*>(&wg);
-      const __nv_bfloat162 hy = *reinterpret_cast<const __nv_bfloat162*>(&wy);
-      const float y0 = __low2float(hy), y1 = __high2float(hy);
-      const float g0 = fmaf(y0, k[0], k[1]) > 0.f ? __low2float(hg) : 0.f;
-      const float g1 = fmaf(y1, k[4], k[5]) > 0.f ? __high2float(hg) : 0.f;
+  // eight rows per trip, all sixteen loads first (see epi_stats_accumulate); invalid rows are masked after the load
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    uint32_t wg[8], wy[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t o = (r0 + i) * 128 + ((chunk ^ i) << 4);
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wg[i]) : "r"(gbase + o));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wy[i]) : "r"(ybase + o));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool valid = (valid_mask >> (r0 + i)) & 1u;
+      const __nv_bfloat162 hg = *reinterpret_cast<const __nv_bfloat162*>(&wg[i]);
+      const __nv_bfloat162 hy = *reinterpret_cast<const __nv_bfloat162*>(&wy[i]);
+      // (an invalid row's y is whatever the box load left there: keep it out of the arithmetic altogether - 0 * NaN is NaN)
+      const float y0 = valid ? __low2float(hy) : 0.f, y1 = valid ? __high2float(hy) : 0.f;
+      const float g0 = (valid && fmaf(y0, k[0], k[1]) > 0.f) ? __low2float(hg) : 0.f;
+      const float g1 = (valid && fmaf(y1, k[4], k[5]) > 0.f) ? __high2float(hg) : 0.f;
       acc[0] += g0;
       acc[1] = fmaf(g0, (y0 - k[2]) * k[3], acc[1]);
       acc[2] += g1;
