@@ -597,7 +597,7 @@ def main():
                    "l2_policy": f"inputs+activations >> L2: {B * Hs * Ws * 3 / 1e6:.0f} MB frames and "
                                 f"{min(args.chunk, B) * 64.1 * H * W / (224 * 224):.0f} MB activations per chunk vs 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * Hs * Ws * 3, "d2h_bytes_per_step": B * H * W,
-                "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host_stream (pinned host buffers, copies overlapped with compute)"},
+                "ms_per_step": ms_host / args.steps, "api": "UNet.infer_host -> unet_b200_infer_u8_host_stream (pinned host buffers; input copies, preprocess and the first two layers pipelined piece by piece at the front of a pass, the fused-head conv and the mask copies piece by piece at its end)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
     if e2e_cam is not None:
