@@ -805,8 +805,10 @@ int unet_b200_trainer_create(unet_b200_trainer** out, int batch, int H, int W, i
   }
   // BatchNorm-backward sums fused into the producer of the incoming gradient where that producer is an elementwise kernel:
   // the encoder conv1 layers (max-pool backward) and the last conv (head backward)
-  if (t->opt.bwd_fuse) {
-    for (int i = 0; i < levels; ++i) t->convs[2 * i + 1].reduce_fused = true;
+  if (t->opt.bwd_fuse) {   // 1: all five layers, 2: the head's only
+    if (t->opt.bwd_fuse == 1) {
+      for (int i = 0; i < levels; ++i) t->convs[2 * i + 1].reduce_fused = true;
+    }
     t->convs.back().reduce_fused = out_channels == 1;
   }
   // ... and into the tcgen05 dgrad epilogue where the producer is a dgrad GEMM that writes the complete gradient: the conv1 of
@@ -1077,9 +1079,15 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
     const size_t npix = (size_t)B * last.H * last.W;
     const int C8 = last.Cout / 8;
     if (t->out_ch == 1) {
-      ub_launch(ub::head_bwd_kernel, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
-          reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
-          t->head_w_off, t->head_b_off, bn_stats_of(last), t->feat[0]);
+      if (last.reduce_fused) {
+        ub_launch(ub::head_bwd_kernel<true>, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
+            reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
+            t->head_w_off, t->head_b_off, bn_stats_of(last), t->feat[0]);
+      } else {
+        ub_launch(ub::head_bwd_kernel<false>, chan_grid(npix, C8), 256, 2 * 2048 * 4, st,
+            reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, C8, reinterpret_cast<uint4*>(last.g), route,
+            t->head_w_off, t->head_b_off, kNoBnStats, t->feat[0]);
+      }
     } else {
       ub_launch(ub::head_bwd_multi_kernel, chan_grid(npix, C8), 256, (2048 + 256) * 4, st,
           reinterpret_cast<const uint4*>(last.a), dlogits, t->head_w_pad, npix, (size_t)last.H * last.W, C8, t->out_ch,
@@ -1108,9 +1116,15 @@ static int train_backward_stage_impl(unet_b200_trainer* t, int stage, const floa
       const TConv& d0 = t->convs[2 * L + 2 + 2 * (L - 1 - i)];  // decoder conv that consumed the skip
       const int C8 = c1.Cout / 8;
       const size_t n = (size_t)B * (c1.H / 2) * (c1.W / 2) * C8;
-      ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, c1.reduce_fused ? 2 * 2048 * 4 : 0, st,
-          reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
-          2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g), bn_stats_of(c1));
+      if (c1.reduce_fused) {
+        ub_launch(ub::maxpool_bwd_add_kernel<true>, grid_for(n, 256), 256, 2 * 2048 * 4, st,
+            reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
+            2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g), bn_stats_of(c1));
+      } else {
+        ub_launch(ub::maxpool_bwd_add_kernel<false>, grid_for(n, 256), 256, 0, st,
+            reinterpret_cast<const uint4*>(c1.a), reinterpret_cast<const uint4*>(next0.dx), reinterpret_cast<const uint4*>(d0.dx),
+            2 * C8, B, c1.H, c1.W, C8, reinterpret_cast<uint4*>(c1.g), kNoBnStats);
+      }
       UB_CUDA(cudaGetLastError());
       rc = trainer_conv_backward(t, c1, route, st);
       if (rc != UB_OK) return rc;
@@ -1506,7 +1520,7 @@ int unet_b200_maxpool2x2_bwd(const void* a, const void* dP, const void* dskip, i
   if (rc != UB_OK) return rc;
   const int C8 = C / 8;
   const size_t n = (size_t)B * (H / 2) * (W / 2) * C8;
-  ub_launch(ub::maxpool_bwd_add_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream),
+  ub_launch(ub::maxpool_bwd_add_kernel<false>, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream),
       reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(dP), reinterpret_cast<const uint4*>(dskip),
       dskip ? skip_pitch / 8 : C8, B, H, W, C8, reinterpret_cast<uint4*>(dA), kNoBnStats);
   UB_CUDA(cudaGetLastError());

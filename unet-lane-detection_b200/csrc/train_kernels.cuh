@@ -155,7 +155,23 @@ bn_relu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scal
       sh[k] = __ldg(shift + c + k);
     }
   }
-  for (size_t i = i0; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  // four 16-byte loads in flight per thread (one per trip left the pass latency-bound: 5.0 TB/s at 224^2)
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = i0;
+  for (; i + 3 * stride < n8; i += 4 * stride) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = __ldg(y + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(r[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      a[i + u * stride] = pack8(f);
+    }
+  }
+  for (; i < n8; i += stride) {
     float f[8];
     unpack8(__ldg(y + i), f);
 #pragma unroll
@@ -383,16 +399,19 @@ __device__ __forceinline__ void bnbwd_flush(const BnBwdStats& b, const BnBwdRegs
 
 // Max-pool backward merged with the skip connection's other gradient:
 // dA[b,h,w,c] = (d_skip ? d_skip[b,h,w,c] : 0) + (pixel is the FIRST maximum of its 2x2 window ? dP[b,h/2,w/2,c] : 0)
+// BN = false keeps the BatchNorm registers (48 floats) out of the kernel: the first version carried them always and ran at one
+// 256-thread CTA per SM (145 registers, 3.7 TB/s). The window's values stay PACKED (two bf16 per register) until they are used.
+template <bool BN>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP, const uint4* __restrict__ d_skip,
                        int skip_pitch8 /* uint4 per pixel of d_skip (>= C8: it may be the first half of a concat gradient) */,
                        int B, int H, int W, int C8, uint4* __restrict__ dA, const BnBwdStats bn) {
   pdl_enter();
-  extern __shared__ float red[];   // 2 * 2048 floats when bn.y != null (C8 must then divide 256)
+  extern __shared__ float red[];   // 2 * 2048 floats when BN (C8 must then divide 256)
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C8;
   BnBwdRegs br;
-  if (bn.y != nullptr) bnbwd_init(bn, threadIdx.x % C8, br);   // the grid stride is a multiple of C8: the channel group is fixed
+  if constexpr (BN) bnbwd_init(bn, threadIdx.x % C8, br);   // the grid stride is a multiple of C8: the channel group is fixed
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = i % C8;
@@ -401,47 +420,52 @@ maxpool_bwd_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ dP
     r /= Wo;
     const int ho = r % Ho;
     const size_t b = r / Ho;
-    const size_t base = ((b * H + 2 * ho) * W + 2 * wo) * C8 + c;
-    const size_t off[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
-    float v[4][8], g[8], o[4][8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) unpack8(__ldg(a + base + off[k]), v[k]);
-    unpack8(__ldg(dP + i), g);
     const size_t pix0 = (b * H + 2 * ho) * W + 2 * wo;
+    const size_t base = pix0 * C8 + c;
+    const size_t off[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
     const size_t poff[4] = {0, 1, (size_t)W, (size_t)W + 1};
+    uint4 va[4], vs[4], out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) va[k] = __ldg(a + base + off[k]);
+    const uint4 vg = __ldg(dP + i);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (d_skip != nullptr) {
-        unpack8(__ldg(d_skip + (pix0 + poff[k]) * skip_pitch8 + c), o[k]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[k][e] = 0.f;
-      }
+      vs[k] = d_skip != nullptr ? __ldg(d_skip + (pix0 + poff[k]) * skip_pitch8 + c) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int best = 0;
-      float m = v[0][e];
+    for (int j = 0; j < 4; ++j) {          // 32-bit word j = channels 2j, 2j+1
+      float2 fa[4], fs[4];
 #pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        if (v[k][e] > m) {  // strict '>' keeps the first maximum in (row, col) scan order, as ATen does
-          m = v[k][e];
-          best = k;
+      for (int k = 0; k < 4; ++k) {
+        fa[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&(&va[k].x)[j]));
+        fs[k] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&(&vs[k].x)[j]));
+      }
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&(&vg.x)[j]));
+      int bx = 0, by = 0;
+      float mx = fa[0].x, my = fa[0].y;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {       // strict '>' keeps the first maximum in (row, col) scan order, as ATen does
+        if (fa[k].x > mx) {
+          mx = fa[k].x;
+          bx = k;
+        }
+        if (fa[k].y > my) {
+          my = fa[k].y;
+          by = k;
         }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k == best) o[k][e] += g[e];
+        (&out[k].x)[j] = pack_bf16x2(fs[k].x + (k == bx ? g.x : 0.f), fs[k].y + (k == by ? g.y : 0.f));
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint4 pk = pack8(o[k]);
-      dA[base + off[k]] = pk;
-      if (bn.y != nullptr) bnbwd_accumulate(br, __ldg(bn.y + base + off[k]), pk);
+      dA[base + off[k]] = out[k];
+      if constexpr (BN) bnbwd_accumulate(br, __ldg(bn.y + base + off[k]), out[k]);
     }
   }
-  if (bn.y != nullptr) bnbwd_flush(bn, br, C8, red);
+  if constexpr (BN) bnbwd_flush(bn, br, C8, red);
 }
 
 // Head forward in training (README.md:1481): logits[p] = bias + sum_c a[p][c] * w[c]; 8 lanes share one pixel.
@@ -471,11 +495,14 @@ head_fwd_train_kernel(const uint4* __restrict__ a, const float* __restrict__ w, 
 }
 
 // Head backward: dA[p][c] = dz[p] * w[c] (bf16);  dw[c] += sum_p dz[p] * a[p][c];  db += sum_p dz[p]
+// Four pixels per trip (four independent 16-byte loads in flight per thread; one left the pass latency-bound at 3.3 TB/s);
+// BN = false keeps the BatchNorm registers out of the kernel.
+template <bool BN>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const float* __restrict__ w, size_t npix, int C8,
                 uint4* __restrict__ dA, GradRoute route, long long off_w, long long off_b, const BnBwdStats bn, int lC) {
   pdl_enter();
-  extern __shared__ float red[];   // (2048 + 256) floats; 2 * 2048 when bn.y != null
+  extern __shared__ float red[];   // (2048 + 256) floats; 2 * 2048 when BN
   const int cl = threadIdx.x % C8;
   const int pl = threadIdx.x / C8;
   const int ppb = 256 / C8;
@@ -484,11 +511,10 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
   for (int i = 0; i < 8; ++i) wv[i] = w[cl * 8 + i];
   float bsum = 0.f;
   BnBwdRegs br;
-  if (bn.y != nullptr) bnbwd_init(bn, cl, br);
-  for (size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<size_t>(gridDim.x) * ppb) {
-    const float g = __ldg(dz + p);
+  if constexpr (BN) bnbwd_init(bn, cl, br);
+  auto one = [&](size_t p, const uint4& ra, float g) {
     float fa[8], o[8];
-    unpack8(__ldg(a + p * C8 + cl), fa);
+    unpack8(ra, fa);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i] = fmaf(g, fa[i], acc[i]);
@@ -496,9 +522,23 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
     }
     const uint4 pk = pack8(o);
     dA[p * C8 + cl] = pk;
-    if (bn.y != nullptr) bnbwd_accumulate(br, __ldg(bn.y + p * C8 + cl), pk);
+    if constexpr (BN) bnbwd_accumulate(br, __ldg(bn.y + p * C8 + cl), pk);
     if (cl == 0) bsum += g;
+  };
+  const size_t stride = static_cast<size_t>(gridDim.x) * ppb;
+  size_t p = static_cast<size_t>(blockIdx.x) * ppb + pl;
+  for (; p + 3 * stride < npix; p += 4 * stride) {
+    uint4 ra[4];
+    float g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ra[u] = __ldg(a + (p + u * stride) * C8 + cl);
+      g[u] = __ldg(dz + p + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(p + u * stride, ra[u], g[u]);
   }
+  for (; p < npix; p += stride) one(p, __ldg(a + p * C8 + cl), __ldg(dz + p));
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
   red[2048 + threadIdx.x] = bsum;
@@ -513,7 +553,7 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ dz, const
     for (int j = 0; j < 256; ++j) s += red[2048 + j];
     grad_add(route, off_b, s);
   }
-  if (bn.y != nullptr) {
+  if constexpr (BN) {
     __syncthreads();   // red is reused
     bnbwd_flush(bn, br, C8, red);
   }
@@ -943,11 +983,21 @@ __device__ __forceinline__ void pack_one_block(const float* __restrict__ params,
     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
     __syncthreads();   // (a block may work several tiles: the previous one has been read out)
 #pragma unroll 1
-    for (int e = threadIdx.x; e < 32 * 288; e += 256) {
-      const int co_l = e / 288, k = e - co_l * 288;   // k = ci_l * 9 + tap
-      float f = 0.f;
-      if (co0 + co_l < jb.lCout && k < nvalid * 9) f = __ldg(w + (static_cast<size_t>(co0 + co_l) * lCin + ci0) * 9 + k);
-      tile[co_l][k] = f;
+    for (int e0 = threadIdx.x; e0 < 32 * 288; e0 += 256 * 6) {   // 36 elements per thread, six loads in flight
+      float f[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int e = e0 + u * 256;
+        const int co_l = e / 288, k = e - co_l * 288;   // k = ci_l * 9 + tap
+        f[u] = 0.f;
+        if (co0 + co_l < jb.lCout && k < nvalid * 9) f[u] = __ldg(w + (static_cast<size_t>(co0 + co_l) * lCin + ci0) * 9 + k);
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int e = e0 + u * 256;
+        const int co_l = e / 288, k = e - co_l * 288;
+        tile[co_l][k] = f[u];
+      }
     }
     __syncthreads();
 #pragma unroll 1
