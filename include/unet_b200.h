@@ -120,10 +120,10 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad2" (default 1)    CTA-pair weight-gradient kernel for Cout >= 128 (read when a trainer / wgrad call is set up)
  *   "wgrad_stream" (default 1) backward: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
  *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
- *   "bwd_fuse" (default 0)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
- *                           incoming gradient where that pass is an elementwise kernel (head / max-pool backward);
- *                           measured on B200: 19.15 vs 19.07 ms/step, i.e. no gain (the producers slow down by what the
- *                           five saved reduction launches cost), so it is off
+ *   "bwd_fuse" (default 2)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
+ *                           incoming gradient where that pass is an elementwise kernel: 2 = the head backward only
+ *                           (measured 16.81-16.99 against 17.00-17.24 ms/step), 1 = also the four max-pool backward passes
+ *                           (measured slower: those kernels then need 140 registers), 0 = off
  *   "dgrad_fuse" (default 1) training: where a layer's incoming gradient is written by a tcgen05 dgrad kernel (13 of the 18
  *                           BatchNorm layers of the default network), that kernel's epilogue also takes the layer's
  *                           BatchNorm-backward sums (the y sub-box is TMA-loaded beside the staged output tile), so the

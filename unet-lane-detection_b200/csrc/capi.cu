@@ -56,7 +56,9 @@ struct Opts {
   int wgrad2 = 1;        // CTA-pair weight-gradient kernel for BLOCK_N >= 128
   int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
   int stem_wide = 0;     // tensor-core stem on 4 x 32 tiles (4 KB contiguous output rows per store) instead of 16 x 8
-  int bwd_fuse = 0;      // training: BatchNorm-backward reduction fused into the pass that produces the gradient (measured: no gain)
+  int bwd_fuse = 2;      // training: BatchNorm-backward reduction fused into the elementwise pass that produces the gradient:
+                         // 2 = the head backward only (16.9 vs 17.0-17.2 ms/step), 1 = also the four max-pool backward passes
+                         // (slower: 140 registers), 0 = off
   int dgrad_fuse = 1;    // training: BatchNorm-backward reduction inside the tcgen05 dgrad epilogues that write the gradient
   int wgrad_halo = 1;    // training: Cout == 64 weight gradients on the halo-patch kernel (all nine taps per CTA)
   int pack_split = 0;    // training: bulk of the operand pack on the side stream (measured: the block scheduler runs it first anyway)
