@@ -131,6 +131,12 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
  *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
  *   "host_pieces" (default 8) unet_b200_infer_u8_host_stream: pieces per pass (see there); 0 or 1 = pass-granular pipeline
+ *   "host_hybrid" (default 1) unet_b200_infer_u8_host_stream with source frames more than 1.5x the network input (their
+ *                           copies take longer than the layers a piece hides them behind): short first pass AND pieces
+ *                           inside every pass; 0 = pass-granular pipeline without pieces for such frames
+ *   "pre_bulk" (default 1)  resizing preprocess: the source rows of a tile are staged by the copy engine (cp.async.bulk
+ *                           into two shared-memory stages, preprocess_bulk_u8_kernel) when base, pitch, frame stride and
+ *                           3*Ws are multiples of 16 bytes; 0 = always the thread-staged tile kernel. Bit-identical results.
  *   "stem_fuse" (default 0) inference plans: the stem is computed inside the patch producer of the first block's second
  *                           conv (stem_halo2_kernel: a small tensor-core GEMM per tile fills the halo'd shared-memory patch), so
  *                           the stem's 64-channel output is never written to or read from HBM; bit-identical results.
@@ -187,9 +193,10 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging_dev, const uint8_t*
  * on first use). Inside a pass the input copy, the preprocess and the two full-resolution layers at the start of the
  * network, and the fused-head conv and the output copies at its end, run per PIECE of the pass (option "host_pieces",
  * default 8 pieces; bf16 plans whose stem / first conv / last conv run on the tensor-core stem and halo kernels), so only
- * the first piece's input copy and the last piece's output copy are not hidden behind kernels; other plans, and source
- * frames more than 1.5x the size of the network input (whose copies take longer than those two layers), use a
- * pass-granular pipeline with a short first pass. Host buffers should be pinned.
+ * the first piece's input copy and the last piece's output copy are not hidden behind kernels. Source frames more than
+ * 1.5x the size of the network input (whose copies take longer than those two layers) additionally get a SHORT first
+ * pass (a quarter of the capacity) whose kernels cover the copies of the rest (option "host_hybrid"); plans without
+ * pieces use a pass-granular pipeline with a short first pass. Host buffers should be pinned.
  * staging_dev: unet_b200_infer_stream_staging_bytes(...) bytes.
  * plan_host_pieces: pieces a full pass is cut into (0: pass-granular fallback); infer_stream_launches: kernels one call
  * for `total` frames launches. */

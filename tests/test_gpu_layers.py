@@ -182,6 +182,40 @@ def _set(U, name, v):
     check(lib.unet_b200_set_option(name.encode(), v))
 
 
+@pytest.mark.parametrize("hs,ws,pad,h,w,b", [(480, 640, 0, 224, 224, 3), (480, 640, 64, 224, 224, 2), (960, 1280, 0, 224, 224, 2),
+                                             (1080, 1920, 16, 224, 224, 1), (100, 64, 0, 224, 224, 2), (131, 176, 32, 60, 300, 2),
+                                             (300, 400, 0, 299, 400, 1), (9, 16, 0, 3, 5, 4), (480, 640, 0, 480, 640, 1)])
+def test_preprocess_bulk_kernel_equals_cv2_and_thread_staged(U, hs, ws, pad, h, w, b):
+    """preprocess_bulk_u8_kernel (rows staged by cp.async.bulk, two stages; 16-byte aligned frames take it by default):
+    bit-equal to cv2 and to the thread-staged tile kernel, the normalised bf16 output included. Covers the span mode with
+    ONE request per tile (contiguous rows), per-row requests (padded pitch), the sparse mode (down-scaling > 2x), the exact
+    2x2 decimation, up-scaling, tiles that overhang the image, more output columns than threads."""
+    from unet_lane_detection_b200._lib import check, f3, lib
+    from unet_lane_detection_b200.ops import MEAN_255, STD_255
+    rng = np.random.default_rng(hs * 11 + ws + pad)
+    img = rng.integers(0, 256, (b, hs, ws, 3), dtype=np.uint8)
+    pitch = ws * 3 + pad
+    buf = torch.zeros(b, hs, pitch, dtype=torch.uint8)
+    buf[:, :, :ws * 3] = torch.from_numpy(img.reshape(b, hs, ws * 3))
+    buf = buf.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for bulk in (1, 0):
+        _set(U, "pre_bulk", bulk)
+        try:
+            y = torch.full((b, h, w, 4), 7.0, dtype=torch.bfloat16, device="cuda")
+            r = torch.zeros(b, h, w, 3, dtype=torch.uint8, device="cuda")
+            check(lib.unet_b200_preprocess_u8(buf.data_ptr(), b, hs, ws, pitch, hs * pitch, h, w, 0, f3(MEAN_255), f3(STD_255),
+                                              y.data_ptr(), r.data_ptr(), st))
+            torch.cuda.synchronize()
+            outs.append((y.cpu(), r.cpu()))
+        finally:
+            _set(U, "pre_bulk", 1)
+    want = np.stack([O.preprocess_oracle(im, (h, w))[0][0] for im in img])
+    assert np.array_equal(outs[0][1].numpy(), want)
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+
+
 @pytest.mark.parametrize("halo", [0, 1])
 @pytest.mark.parametrize("B,H,W,C0,C1,Cout,pool", [(2, 224, 224, 64, 0, 64, True), (1, 224, 224, 64, 64, 64, False),
                                                    (2, 112, 112, 64, 0, 128, False), (2, 112, 112, 128, 0, 128, True),

@@ -235,17 +235,21 @@ def test_infer_host_equals_device_path(U):
     assert torch.equal(m_host, m_dev.cpu())
 
 
-def test_infer_host_pieces_and_passes(U):
+@pytest.mark.parametrize("hs,ws", [(120, 160), (480, 640)])
+def test_infer_host_pieces_and_passes(U, hs, ws):
     """unet_b200_infer_u8_host_stream: a pass is cut into pieces whose copies / preprocess / first and last layers are
     pipelined (include/unet_b200.h). 77 camera frames through a plan of 32 (passes 32 / 32 / 13, two pieces each, ragged last
-    piece): logits and masks are bit-equal to the device-resident path, for the piece-wise and the pass-granular schedule."""
+    piece): logits and masks are bit-equal to the device-resident path, for the piece-wise and the pass-granular schedule.
+    480x640 frames are "copy-bound" (more than 1.5x the network input): they take the hybrid schedule (short first pass of 8,
+    then 32 / 32 / 5, pieces inside) or, with host_hybrid = 0, the pass-granular one."""
     from unet_lane_detection_b200._lib import check, lib
     ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
-    frames = torch.randint(0, 256, (77, 120, 160, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
+    frames = torch.randint(0, 256, (77, hs, ws, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
     outs = {}
     try:
-        for pieces in (8, 0):
+        for pieces, hybrid in ((8, 1), (0, 1), (8, 0)):
             check(lib.unet_b200_set_option(b"host_pieces", pieces))
+            check(lib.unet_b200_set_option(b"host_hybrid", hybrid))
             net = U.UNet(3, 1, [64, 128, 256, 512])
             net.load_state_dict(ref.state_dict())
             net = net.cuda().eval()
@@ -254,14 +258,15 @@ def test_infer_host_pieces_and_passes(U):
             l_host = torch.zeros(77, 224, 224, dtype=torch.float32).pin_memory()
             net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)
             net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)   # events / slots are reused
-            outs[pieces] = (m_host.clone(), l_host.clone(), net.gpu_launches)
-            if pieces:
+            outs[(pieces, hybrid)] = (m_host.clone(), l_host.clone(), net.gpu_launches)
+            if pieces and hybrid:
                 l_dev, _, m_dev = net.predict_mask(frames.cuda(), swap_rb=True, want=("logits", "mask"))
     finally:
         check(lib.unet_b200_set_option(b"host_pieces", 8))
-    for pieces in (8, 0):
-        assert torch.equal(outs[pieces][0], m_dev.cpu()), pieces
-        assert torch.equal(outs[pieces][1], l_dev.cpu()), pieces
+        check(lib.unet_b200_set_option(b"host_hybrid", 1))
+    for key, (m, l, _) in outs.items():
+        assert torch.equal(m, m_dev.cpu()), key
+        assert torch.equal(l, l_dev.cpu()), key
 
 
 @pytest.mark.parametrize("feats,B,H,W", [([64, 128, 256, 512], 3, 224, 224), ([64, 128], 5, 40, 56), ([32, 64], 1, 16, 8),

@@ -458,6 +458,134 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_u8_kernel(const Pre
   }
 }
 
+// Bulk-copy form of the tile kernel (option pre_bulk, the default when the frames allow it): the staging loop above costs about
+// as many instructions as the blend (one 16-byte load, an index division and a dependent shared-memory store per chunk) and
+// three CTA barriers per tile. Here ONE thread asks the copy engine for the tile's source rows (cp.async.bulk global ->
+// shared, completion on an mbarrier; one request for the whole span when the rows are contiguous in memory) and the rows of
+// tile i+1 arrive while tile i is blended: two stages, one barrier per tile, no staging instructions at all.
+// Needs 16-byte aligned rows: base, pitch, frame stride and 3*Ws all multiples of 16 (camera sizes 640 / 1280 / 1920 are).
+// Same arithmetic as preprocess_u8_kernel (bit-equal to cv2, test_preprocess_bulk_kernel_*).
+constexpr int PREB_THREADS = 256;
+__host__ __device__ constexpr size_t preb_smem_bytes(int Ws, int W, int H, int rows) {
+  return static_cast<size_t>(2) * (2 * rows) * (Ws * 3) + static_cast<size_t>(W + H) * 16;
+}
+__device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(const PreArgs a, int rows_per_cta) {
+  pdl_enter();
+  extern __shared__ __align__(128) uint8_t preb_smem[];
+  __shared__ __align__(8) uint64_t full[2];
+  const int R = rows_per_cta;
+  const int row_bytes = a.Ws * 3;
+  const int stage_bytes = 2 * R * row_bytes;
+  int4* xtab = reinterpret_cast<int4*>(preb_smem + static_cast<size_t>(2) * stage_bytes);
+  int4* ytab = xtab + a.W;
+  const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
+  for (int x = threadIdx.x; x < a.W; x += blockDim.x) {     // {3*sx0, 3*sx1, ax0, ax1}
+    int sx0, sx1, ax0, ax1;
+    resize_coef(x, a.W, a.Ws, true, sx0, sx1, ax0, ax1);
+    if (area2) {
+      sx0 = 2 * x;
+      sx1 = 2 * x + 1;
+    }
+    xtab[x] = make_int4(3 * sx0, 3 * sx1, ax0, ax1);
+  }
+  for (int y = threadIdx.x; y < a.H; y += blockDim.x) {     // {sy0, sy1, by0, by1}
+    int sy0, sy1, by0, by1;
+    resize_coef(y, a.H, a.Hs, false, sy0, sy1, by0, by1);
+    if (area2) {
+      sy0 = 2 * y;
+      sy1 = 2 * y + 1;
+    }
+    ytab[y] = make_int4(sy0, sy1, by0, by1);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int tiles_h = (a.H + R - 1) / R;
+  const int total = a.B * tiles_h;
+  // thread 0: request the source rows of tile t into `stage`. The row taps are non-decreasing in y, so the tile needs the
+  // rows [sy0(first row), sy1(last row)]: slot i = row lo + i when that span fits the stage, else two private slots per row.
+  auto request = [&](int t, int stage) {
+    const int b = t / tiles_h;
+    const int y0 = (t - b * tiles_h) * R;
+    const int nrows = min(R, a.H - y0);
+    const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
+    uint8_t* dst = preb_smem + static_cast<size_t>(stage) * stage_bytes;
+    const int lo = ytab[y0].x, n = ytab[y0 + nrows - 1].y - lo + 1;
+    if (n <= 2 * R) {
+      mbar_expect_tx(&full[stage], static_cast<uint32_t>(n * row_bytes));
+      if (a.pitch == static_cast<size_t>(row_bytes)) {
+        bulk_load_g2s(dst, frame + static_cast<size_t>(lo) * a.pitch, static_cast<uint32_t>(n * row_bytes), &full[stage]);
+      } else {
+        for (int i = 0; i < n; ++i) {
+          bulk_load_g2s(dst + i * row_bytes, frame + static_cast<size_t>(lo + i) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
+        }
+      }
+    } else {
+      mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * nrows * row_bytes));
+      for (int r = 0; r < nrows; ++r) {
+        const int4 yt = ytab[y0 + r];
+        bulk_load_g2s(dst + (2 * r) * row_bytes, frame + static_cast<size_t>(yt.x) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
+        bulk_load_g2s(dst + (2 * r + 1) * row_bytes, frame + static_cast<size_t>(yt.y) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
+      }
+    }
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < total) request(blockIdx.x, 0);
+  uint32_t phase = 0;   // bit s: parity of the next completion of stage s
+  int stage = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, stage ^= 1) {
+    // the other stage was last read before the barrier that ended the previous iteration
+    if (threadIdx.x == 0 && t + static_cast<int>(gridDim.x) < total) request(t + gridDim.x, stage ^ 1);
+    const int b = t / tiles_h;
+    const int y0 = (t - b * tiles_h) * R;
+    const int nrows = min(R, a.H - y0);
+    const int lo = ytab[y0].x;
+    const bool span = ytab[y0 + nrows - 1].y - lo + 1 <= 2 * R;
+    const uint8_t* base = preb_smem + static_cast<size_t>(stage) * stage_bytes;
+    mbar_wait(&full[stage], (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+    for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
+      const int4 xt = xtab[x];
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        const int4 yt = ytab[y0 + r];
+        const uint8_t* r0 = base + (span ? yt.x - lo : 2 * r) * row_bytes;
+        const uint8_t* r1 = base + (span ? yt.y - lo : 2 * r + 1) * row_bytes;
+        int px[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (area2) {
+            px[c] = (r0[xt.x + c] + r0[xt.y + c] + r1[xt.x + c] + r1[xt.y + c] + 2) >> 2;
+          } else {
+            const int h0 = r0[xt.x + c] * xt.z + r0[xt.y + c] * xt.w;
+            const int h1 = r1[xt.x + c] * xt.z + r1[xt.y + c] * xt.w;
+            px[c] = resize_blend(h0, h1, yt.z, yt.w);
+          }
+        }
+        if (a.swap_rb) { const int tt = px[0]; px[0] = px[2]; px[2] = tt; }
+        const size_t o = (static_cast<size_t>(b) * a.H + y0 + r) * a.W + x;
+        if (a.dst_u8 != nullptr) {
+          a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
+          a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
+          a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+        }
+        const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
+        const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
+        const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
+        pre_store(a, o, f0, f1, f2);
+      }
+    }
+    __syncthreads();   // every thread has read this stage: the next iteration may refill it
+  }
+}
+
 // Same-size frames (Hs == H, Ws == W): cv2.resize returns a copy, so the preprocess is channel swap + normalise only.
 // One thread per 4 pixels: three 32-bit loads (12 source bytes), two 16-byte stores (four NHWC4 bf16 pixels); a warp reads
 // 384 and writes 1024 contiguous bytes; two groups per trip so that six loads are in flight per thread.

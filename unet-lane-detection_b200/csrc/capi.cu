@@ -65,6 +65,10 @@ struct Opts {
   int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
   int stem_fuse = 0;     // inference: the stem runs inside enc0.conv1's patch producer (stem_halo2_kernel), its output never stored
                          // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
+  int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
+                         // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
+  int pre_bulk = 1;      // resizing preprocess: source rows staged by the copy engine (cp.async.bulk, two stages) when the frames
+                         // are 16-byte aligned, instead of by the threads
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -95,6 +99,7 @@ enum AttrSlot : int {
   AT_STEM_WIDE = 22,
   AT_WGRAD_HALO = 23,
   AT_STEM_HALO = 24,
+  AT_PRE_BULK = 25,
 };
 struct DevState {
   std::atomic<int> num_sms{0};
@@ -1178,7 +1183,8 @@ int unet_b200_set_option(const char* name, int value) {
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
       {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
-      {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}};
+      {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}, {"pre_bulk", &g_opts.pre_bulk},
+      {"host_hybrid", &g_opts.host_hybrid}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
@@ -1493,6 +1499,27 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
+  // 16-byte aligned frames: the copy engine stages the rows (two stages in flight), see preprocess_bulk_u8_kernel
+  if (tl_opts->pre_bulk && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (frame_stride & 15) == 0 &&
+      ((size_t)Ws * 3 & 15) == 0) {
+    int rb = ub::PRE_ROWS;
+    while (rb > 1 && ub::preb_smem_bytes(Ws, W, H, rb) > 72 * 1024) rb >>= 1;
+    const size_t smem_b = ub::preb_smem_bytes(Ws, W, H, rb);
+    if (smem_b <= 200 * 1024) {
+      if (smem_b > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_bulk_u8_kernel, AT_PRE_BULK, 200 * 1024));
+      int threads = ((W + 31) / 32) * 32;       // a thread owns output columns: no idle warps for W < 256
+      if (threads > ub::PREB_THREADS) threads = ub::PREB_THREADS;
+      const int tiles_b = batch * ((H + rb - 1) / rb);
+      int per_sm_b = 0;
+      UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, ub::preprocess_bulk_u8_kernel, threads, smem_b));
+      per_sm_b = per_sm_b < 1 ? 1 : per_sm_b;
+      const int resident_b = cur_sms() * per_sm_b;
+      ub_launch(ub::preprocess_bulk_u8_kernel, tiles_b < resident_b ? tiles_b : resident_b, threads, smem_b,
+                static_cast<cudaStream_t>(stream), a, rb);
+      UB_CUDA(cudaGetLastError());
+      return UB_OK;
+    }
+  }
   if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
   // persistent CTAs: as many as are resident at once (shared memory bound), each walks tiles of `rows` output rows
   const int tiles = batch * ((H + rows - 1) / rows);
@@ -1633,9 +1660,16 @@ int unet_b200_plan_host_pieces(const unet_b200_plan* p) {
 // (copy-bound: the H2D copy of a pass takes longer than the two layers its pieces could hide it behind - 480x640 camera
 // frames measured 15.9 k frames/s piece-wise, 16.0 k pass-granular; 224x224 frames 16.7 k against 16.2 k).
 static bool host_copy_bound(const unet_b200_plan* p, size_t frame_bytes) { return 2 * frame_bytes > 3 * (size_t)p->H * p->W * 3; }
+// pieces for frames of this size? Copy-bound sources take them only in the hybrid schedule (option host_hybrid): a SHORT first
+// pass whose kernels cover the copies of the rest, and inside every pass the pieces, so that only one piece's copy is exposed.
+static bool host_use_pieces(const unet_b200_plan* p, size_t frame_bytes) {
+  int np = 0;
+  if (host_piece_size(p, p->Bc, &np) <= 0) return false;
+  return p->opt.host_hybrid != 0 || !host_copy_bound(p, frame_bytes);
+}
 static int host_pass_size(const unet_b200_plan* p, int it, int left, int total, bool pieces, size_t frame_bytes) {
   int n = p->Bc;
-  if (it == 0 && !pieces) {
+  if (it == 0 && (!pieces || host_copy_bound(p, frame_bytes))) {
     int first = (p->Bc / 4) & ~7;
     if (first < 8) first = 8;
     if (first * 2 >= total) first = total < p->Bc ? total : p->Bc;
@@ -1650,7 +1684,7 @@ int unet_b200_infer_stream_launches(const unet_b200_plan* p, int total, int Hs, 
   const int per_pass = unet_b200_forward_launches(p) + 1;
   int launches = 0;
   int np = 0;
-  const bool pieces = host_piece_size(p, p->Bc, &np) > 0 && !host_copy_bound(p, (size_t)Hs * Ws * 3);
+  const bool pieces = host_use_pieces(p, (size_t)Hs * Ws * 3);
   int it = 0;
   for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
     n = host_pass_size(p, it, total - b0, total, pieces, (size_t)Hs * Ws * 3);
@@ -1709,8 +1743,7 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
   // two full-resolution layers at the start run per PIECE, and so do the fused-head conv and the output copies at the end
   // (forward_impl, PieceHooks). Not hidden: the first piece's H2D copy and the last piece's D2H copy - 1/8 of what a
   // pass-granular pipeline leaves exposed - and no pass has to be cut short to get the pipeline going.
-  int np_cap = 0;
-  if (host_piece_size(p, p->Bc, &np_cap) > 0 && !host_copy_bound(p, frame_bytes)) {
+  if (host_use_pieces(p, frame_bytes)) {
     struct Ctx {
       unet_b200_plan* p;
       cudaStream_t st;
