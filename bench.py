@@ -18,6 +18,7 @@ import subprocess
 import sys
 import threading
 import time
+import numpy as np
 
 # One process per GPU, every GPU visible to every rank: the library keeps its state per device and the NVLink / NVSwitch
 # gradient exchange of the training step maps the peers' buffers, so nothing is pinned by default. UB_BENCH_PIN=1 restricts
@@ -553,8 +554,13 @@ def main():
         ncam = nb
         cam_dev = torch.randint(0, 256, (ncam, 480, 640, 3), dtype=torch.uint8, device=dev)
         cam_ms = time_kernel(lambda: run_pre(cam_dev, 480, 640))
-        hbm.append(hbm_row("preprocess_u8_kernel (480x640 -> 224x224, cv2-exact bilinear)", ncam * 3 * 480 * 640, ncam * H * W * 8, cam_ms,
-                           f"{ncam} camera frames: the real-resize case of e2e_src480x640"))
+        # down-scaling by more than 2 skips source rows: 448 of a camera frame's 480 rows hold a tap of the 224 output rows
+        f_ = ((np.arange(H) + 0.5) * (480 / H) - 0.5).astype(np.float32)
+        s0_ = np.floor(f_).astype(np.int64)
+        rows_t = len(set(np.clip(s0_, 0, 479)) | set(np.clip(s0_ + 1, 0, 479)))
+        hbm.append(hbm_row("preprocess_bulk_u8_kernel (480x640 -> 224x224, cv2-exact bilinear)", ncam * 3 * rows_t * 640, ncam * H * W * 8, cam_ms,
+                           f"{ncam} camera frames: the real-resize case of e2e_src480x640; read bytes = the {rows_t} of 480 source rows "
+                           f"per frame that hold a tap (whole frames would be {ncam * 3 * 480 * 640} B)"))
         del cam_dev
     for r in rows:
         if r["kind"] == "stem":

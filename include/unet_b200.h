@@ -135,8 +135,8 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *                           copies take longer than the layers a piece hides them behind): short first pass AND pieces
  *                           inside every pass; 0 = pass-granular pipeline without pieces for such frames
  *   "pre_bulk" (default 1)  resizing preprocess: the source rows of a tile are staged by the copy engine (cp.async.bulk
- *                           into two shared-memory stages, preprocess_bulk_u8_kernel) when base, pitch, frame stride and
- *                           3*Ws are multiples of 16 bytes; 0 = always the thread-staged tile kernel. Bit-identical results.
+ *                           into two shared-memory stages, preprocess_bulk_u8_kernel); 0 = the thread-staged tile kernel.
+ *                           Bit-identical results.
  *   "stem_fuse" (default 0) inference plans: the stem is computed inside the patch producer of the first block's second
  *                           conv (stem_halo2_kernel: a small tensor-core GEMM per tile fills the halo'd shared-memory patch), so
  *                           the stem's 64-channel output is never written to or read from HBM; bit-identical results.

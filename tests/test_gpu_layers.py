@@ -184,12 +184,16 @@ def _set(U, name, v):
 
 @pytest.mark.parametrize("hs,ws,pad,h,w,b", [(480, 640, 0, 224, 224, 3), (480, 640, 64, 224, 224, 2), (960, 1280, 0, 224, 224, 2),
                                              (1080, 1920, 16, 224, 224, 1), (100, 64, 0, 224, 224, 2), (131, 176, 32, 60, 300, 2),
-                                             (300, 400, 0, 299, 400, 1), (9, 16, 0, 3, 5, 4), (480, 640, 0, 480, 640, 1)])
+                                             (300, 400, 0, 299, 400, 1), (9, 16, 0, 3, 5, 4), (480, 640, 0, 480, 640, 1),
+                                             (685, 1055, 0, 224, 224, 2), (37, 53, 5, 64, 96, 3), (17, 23, 0, 8, 8, 5),
+                                             (200, 4001, 3, 16, 16, 1)])
 def test_preprocess_bulk_kernel_equals_cv2_and_thread_staged(U, hs, ws, pad, h, w, b):
     """preprocess_bulk_u8_kernel (rows staged by cp.async.bulk, two stages; 16-byte aligned frames take it by default):
     bit-equal to cv2 and to the thread-staged tile kernel, the normalised bf16 output included. Covers the span mode with
     ONE request per tile (contiguous rows), per-row requests (padded pitch), the sparse mode (down-scaling > 2x), the exact
-    2x2 decimation, up-scaling, tiles that overhang the image, more output columns than threads."""
+    2x2 decimation, up-scaling, tiles that overhang the image, more output columns than threads, and rows that do not start
+    on 16-byte boundaries (odd widths / pitches: aligned-down requests + per-slot offsets, tail bytes of the last frame copied
+    by the requesting thread - the source tensor ends exactly at the last pixel)."""
     from unet_lane_detection_b200._lib import check, f3, lib
     from unet_lane_detection_b200.ops import MEAN_255, STD_255
     rng = np.random.default_rng(hs * 11 + ws + pad)

@@ -458,29 +458,37 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_u8_kernel(const Pre
   }
 }
 
-// Bulk-copy form of the tile kernel (option pre_bulk, the default when the frames allow it): the staging loop above costs about
-// as many instructions as the blend (one 16-byte load, an index division and a dependent shared-memory store per chunk) and
-// three CTA barriers per tile. Here ONE thread asks the copy engine for the tile's source rows (cp.async.bulk global ->
-// shared, completion on an mbarrier; one request for the whole span when the rows are contiguous in memory) and the rows of
-// tile i+1 arrive while tile i is blended: two stages, one barrier per tile, no staging instructions at all.
-// Needs 16-byte aligned rows: base, pitch, frame stride and 3*Ws all multiples of 16 (camera sizes 640 / 1280 / 1920 are).
+// Bulk-copy form of the tile kernel (option pre_bulk, the default): the staging loop above costs about as many instructions
+// as the blend (one 16-byte load, an index division and a dependent shared-memory store per chunk) and three CTA barriers
+// per tile. Here one warp asks the copy engine for the tile's source rows (cp.async.bulk global -> shared, completion on
+// an mbarrier; the lanes of warp 0 take one row each, or one request serves the whole span when the rows are contiguous
+// in memory) and the rows of tile i+1 arrive while tile i is blended: two stages, one barrier per tile, no staging instructions at all.
+// The copy engine moves 16-byte aligned chunks: a request starts at the aligned-down address of the row (never below the
+// allocation, which is at least 16-byte aligned) and the row's offset inside its slot is kept in a small table; where the
+// rounded-up end would pass the last byte of the last frame the requesting thread copies the (< 16) tail bytes itself.
 // Same arithmetic as preprocess_u8_kernel (bit-equal to cv2, test_preprocess_bulk_kernel_*).
 constexpr int PREB_THREADS = 256;
+__host__ __device__ constexpr int preb_slot_pitch(int Ws) { return ((Ws * 3 + 15 + 15) >> 4) << 4; }
 __host__ __device__ constexpr size_t preb_smem_bytes(int Ws, int W, int H, int rows) {
-  return static_cast<size_t>(2) * (2 * rows) * (Ws * 3) + static_cast<size_t>(W + H) * 16;
+  return static_cast<size_t>(2) * (2 * rows) * preb_slot_pitch(Ws) + static_cast<size_t>(W + H) * 16;
 }
 __device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_add_tx(uint64_t* bar, uint32_t bytes) {   // expect-tx without an arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(const PreArgs a, int rows_per_cta) {
   pdl_enter();
   extern __shared__ __align__(128) uint8_t preb_smem[];
   __shared__ __align__(8) uint64_t full[2];
+  __shared__ int s_off[2][2 * PRE_ROWS];     // where slot i's row starts inside its stage
   const int R = rows_per_cta;
   const int row_bytes = a.Ws * 3;
-  const int stage_bytes = 2 * R * row_bytes;
+  const int P = preb_slot_pitch(a.Ws);
+  const int stage_bytes = 2 * R * P;
   int4* xtab = reinterpret_cast<int4*>(preb_smem + static_cast<size_t>(2) * stage_bytes);
   int4* ytab = xtab + a.W;
   const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
@@ -503,46 +511,65 @@ __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(con
     ytab[y] = make_int4(sy0, sy1, by0, by1);
   }
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(&full[0], 32);
+    mbar_init(&full[1], 32);
     fence_mbar_init();
   }
   __syncthreads();
   const int tiles_h = (a.H + R - 1) / R;
   const int total = a.B * tiles_h;
-  // thread 0: request the source rows of tile t into `stage`. The row taps are non-decreasing in y, so the tile needs the
-  // rows [sy0(first row), sy1(last row)]: slot i = row lo + i when that span fits the stage, else two private slots per row.
+  const uint8_t* src_end = a.src + static_cast<size_t>(a.B - 1) * a.frame_stride + static_cast<size_t>(a.Hs - 1) * a.pitch + row_bytes;
+  // warp 0: request the source rows of tile t into `stage`, one slot per lane (2R <= 16 slots). The row taps are
+  // non-decreasing in y, so the tile needs the rows [sy0(first row), sy1(last row)]: slot i = row lo + i when that span fits
+  // the stage, else two private slots per output row. Every lane arrives once on the stage's barrier (count 32) AFTER it
+  // has announced its bytes, written its table entry and copied its tail bytes, so the phase ends when all of that is visible
+  // and the copies have landed.
   auto request = [&](int t, int stage) {
+    const int lane = threadIdx.x;
     const int b = t / tiles_h;
     const int y0 = (t - b * tiles_h) * R;
     const int nrows = min(R, a.H - y0);
     const uint8_t* frame = a.src + static_cast<size_t>(b) * a.frame_stride;
-    uint8_t* dst = preb_smem + static_cast<size_t>(stage) * stage_bytes;
+    uint8_t* sbase = preb_smem + static_cast<size_t>(stage) * stage_bytes;
+    uint64_t* bar = &full[stage];
+    // `nbytes` from global address g -> dst + (g & 15), dst 16-byte aligned
+    auto span_in = [&](uint8_t* dst, const uint8_t* g, int nbytes) {
+      const int off = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
+      const uint8_t* g0 = g - off;
+      const int want = (off + nbytes + 15) & ~15;
+      int bulk = want;
+      if (g0 + want > src_end) bulk = static_cast<int>((src_end - g0) & ~static_cast<ptrdiff_t>(15));
+      if (bulk > 0) {
+        mbar_add_tx(bar, static_cast<uint32_t>(bulk));
+        bulk_load_g2s(dst, g0, static_cast<uint32_t>(bulk), bar);
+      }
+      for (int q = bulk; q < off + nbytes; ++q) dst[q] = __ldg(g0 + q);
+    };
     const int lo = ytab[y0].x, n = ytab[y0 + nrows - 1].y - lo + 1;
     if (n <= 2 * R) {
-      mbar_expect_tx(&full[stage], static_cast<uint32_t>(n * row_bytes));
-      if (a.pitch == static_cast<size_t>(row_bytes)) {
-        bulk_load_g2s(dst, frame + static_cast<size_t>(lo) * a.pitch, static_cast<uint32_t>(n * row_bytes), &full[stage]);
-      } else {
-        for (int i = 0; i < n; ++i) {
-          bulk_load_g2s(dst + i * row_bytes, frame + static_cast<size_t>(lo + i) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
-        }
+      if (a.pitch == static_cast<size_t>(row_bytes)) {       // the rows follow each other in memory: one request
+        const uint8_t* g = frame + static_cast<size_t>(lo) * a.pitch;
+        if (lane == 0) span_in(sbase, g, n * row_bytes);
+        if (lane < n) s_off[stage][lane] = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15) + lane * row_bytes;
+      } else if (lane < n) {
+        const uint8_t* g = frame + static_cast<size_t>(lo + lane) * a.pitch;
+        span_in(sbase + lane * P, g, row_bytes);
+        s_off[stage][lane] = lane * P + static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
       }
-    } else {
-      mbar_expect_tx(&full[stage], static_cast<uint32_t>(2 * nrows * row_bytes));
-      for (int r = 0; r < nrows; ++r) {
-        const int4 yt = ytab[y0 + r];
-        bulk_load_g2s(dst + (2 * r) * row_bytes, frame + static_cast<size_t>(yt.x) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
-        bulk_load_g2s(dst + (2 * r + 1) * row_bytes, frame + static_cast<size_t>(yt.y) * a.pitch, static_cast<uint32_t>(row_bytes), &full[stage]);
-      }
+    } else if (lane < 2 * nrows) {
+      const int4 yt = ytab[y0 + (lane >> 1)];
+      const uint8_t* g = frame + static_cast<size_t>((lane & 1) ? yt.y : yt.x) * a.pitch;
+      span_in(sbase + lane * P, g, row_bytes);
+      s_off[stage][lane] = lane * P + static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
     }
+    mbar_arrive(bar);
   };
-  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < total) request(blockIdx.x, 0);
+  if (threadIdx.x < 32 && static_cast<int>(blockIdx.x) < total) request(blockIdx.x, 0);
   uint32_t phase = 0;   // bit s: parity of the next completion of stage s
   int stage = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x, stage ^= 1) {
     // the other stage was last read before the barrier that ended the previous iteration
-    if (threadIdx.x == 0 && t + static_cast<int>(gridDim.x) < total) request(t + gridDim.x, stage ^ 1);
+    if (threadIdx.x < 32 && t + static_cast<int>(gridDim.x) < total) request(t + gridDim.x, stage ^ 1);
     const int b = t / tiles_h;
     const int y0 = (t - b * tiles_h) * R;
     const int nrows = min(R, a.H - y0);
@@ -556,8 +583,8 @@ __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(con
 #pragma unroll 4
       for (int r = 0; r < nrows; ++r) {
         const int4 yt = ytab[y0 + r];
-        const uint8_t* r0 = base + (span ? yt.x - lo : 2 * r) * row_bytes;
-        const uint8_t* r1 = base + (span ? yt.y - lo : 2 * r + 1) * row_bytes;
+        const uint8_t* r0 = base + s_off[stage][span ? yt.x - lo : 2 * r];
+        const uint8_t* r1 = base + s_off[stage][span ? yt.y - lo : 2 * r + 1];
         int px[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -582,7 +609,7 @@ __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(con
         pre_store(a, o, f0, f1, f2);
       }
     }
-    __syncthreads();   // every thread has read this stage: the next iteration may refill it
+    __syncthreads();   // every thread has read this stage (and its offset table): the next iteration may refill it
   }
 }
 

@@ -67,8 +67,7 @@ struct Opts {
                          // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
   int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
                          // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
-  int pre_bulk = 1;      // resizing preprocess: source rows staged by the copy engine (cp.async.bulk, two stages) when the frames
-                         // are 16-byte aligned, instead of by the threads
+  int pre_bulk = 1;      // resizing preprocess: source rows staged by the copy engine (cp.async.bulk, two stages) instead of by the threads
 };
 Opts g_opts;
 thread_local const Opts* tl_opts = &g_opts;
@@ -1499,9 +1498,8 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
     UB_CUDA(cudaGetLastError());
     return UB_OK;
   }
-  // 16-byte aligned frames: the copy engine stages the rows (two stages in flight), see preprocess_bulk_u8_kernel
-  if (tl_opts->pre_bulk && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (pitch & 15) == 0 && (frame_stride & 15) == 0 &&
-      ((size_t)Ws * 3 & 15) == 0) {
+  // the copy engine stages the rows (two stages in flight), see preprocess_bulk_u8_kernel
+  if (tl_opts->pre_bulk) {
     int rb = ub::PRE_ROWS;
     while (rb > 1 && ub::preb_smem_bytes(Ws, W, H, rb) > 72 * 1024) rb >>= 1;
     const size_t smem_b = ub::preb_smem_bytes(Ws, W, H, rb);
