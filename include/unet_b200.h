@@ -131,6 +131,10 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
  *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
  *   "host_pieces" (default 8) unet_b200_infer_u8_host_stream: pieces per pass (see there); 0 or 1 = pass-granular pipeline
+ *   "host_geometric" (default 1) unet_b200_infer_u8_host_stream: the pieces of a pass are 16, 32, 64, ... frames (the copy of a
+ *                           piece hides behind the front layers of the piece half its size before it) and the last layer
+ *                           runs them largest first: 16 frames of input / output copy exposed and 4 instead of 8 launches per
+ *                           piece-wise layer; 0 = "host_pieces" equal pieces. Measured e2e 16.64-16.70 k -> 16.79-16.83 k frames/s
  *   "host_hybrid" (default 1) unet_b200_infer_u8_host_stream with source frames more than 1.5x the network input (their
  *                           copies take longer than the layers a piece hides them behind): short first pass AND pieces
  *                           inside every pass; 0 = pass-granular pipeline without pieces for such frames

@@ -241,29 +241,33 @@ def test_infer_host_pieces_and_passes(U, hs, ws):
     pipelined (include/unet_b200.h). 77 camera frames through a plan of 32 (passes 32 / 32 / 13, two pieces each, ragged last
     piece): logits and masks are bit-equal to the device-resident path, for the piece-wise and the pass-granular schedule.
     480x640 frames are "copy-bound" (more than 1.5x the network input): they take the hybrid schedule (short first pass of 8,
-    then 32 / 32 / 5, pieces inside) or, with host_hybrid = 0, the pass-granular one."""
+    then 32 / 32 / 5, pieces inside) or, with host_hybrid = 0, the pass-granular one. Pieces are geometric by default (16, 16
+    for a pass of 32; 16, 32, 29 for the 77-frame pass of a plan of 80, the last layer running them largest first) or, with
+    host_geometric = 0, equal."""
     from unet_lane_detection_b200._lib import check, lib
     ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
     frames = torch.randint(0, 256, (77, hs, ws, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(6))
     outs = {}
     try:
-        for pieces, hybrid in ((8, 1), (0, 1), (8, 0)):
+        for pieces, hybrid, geometric, chunk in ((8, 1, 1, 32), (8, 1, 1, 80), (0, 1, 1, 32), (8, 0, 1, 32), (8, 1, 0, 32)):
             check(lib.unet_b200_set_option(b"host_pieces", pieces))
             check(lib.unet_b200_set_option(b"host_hybrid", hybrid))
+            check(lib.unet_b200_set_option(b"host_geometric", geometric))
             net = U.UNet(3, 1, [64, 128, 256, 512])
             net.load_state_dict(ref.state_dict())
             net = net.cuda().eval()
-            net.b200_chunk = 32
+            net.b200_chunk = chunk
             m_host = torch.zeros(77, 224, 224, dtype=torch.uint8).pin_memory()
             l_host = torch.zeros(77, 224, 224, dtype=torch.float32).pin_memory()
             net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)
             net.infer_host(frames.pin_memory(), swap_rb=True, mask_out=m_host, logits_out=l_host)   # events / slots are reused
-            outs[(pieces, hybrid)] = (m_host.clone(), l_host.clone(), net.gpu_launches)
-            if pieces and hybrid:
+            outs[(pieces, hybrid, geometric, chunk)] = (m_host.clone(), l_host.clone(), net.gpu_launches)
+            if pieces and hybrid and geometric and chunk == 32:
                 l_dev, _, m_dev = net.predict_mask(frames.cuda(), swap_rb=True, want=("logits", "mask"))
     finally:
         check(lib.unet_b200_set_option(b"host_pieces", 8))
         check(lib.unet_b200_set_option(b"host_hybrid", 1))
+        check(lib.unet_b200_set_option(b"host_geometric", 1))
     for key, (m, l, _) in outs.items():
         assert torch.equal(m, m_dev.cpu()), key
         assert torch.equal(l, l_dev.cpu()), key

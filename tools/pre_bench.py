@@ -50,4 +50,21 @@ for tag, hs, ws in (("same_224x224", 224, 224), ("camera_480x640", 480, 640), ("
     out[tag] = {"frames": n, "us": best * 1e3, "read_mb": rd / 1e6, "frame_mb": n * hs * ws * 3 / 1e6, "write_mb": wr / 1e6,
                 "gbs": (rd + wr) / (best / 1e3) / 1e9}
     del f, y
+# IPM front end (warp_preprocess_u8_kernel): camera frames -> bird's-eye 1055x685 (never stored) -> 224x224 network input
+import numpy as np  # noqa: E402
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ipm.npz"))
+f = torch.randint(0, 256, (n, 480, 640, 3), dtype=torch.uint8, device="cuda")
+U.ops.preprocess_warp_u8(f, g["M"], (1055, 685), (224, 224))
+torch.cuda.synchronize()
+best = 1e30
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        U.ops.preprocess_warp_u8(f, g["M"], (1055, 685), (224, 224))
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 10)
+out["ipm_480x640_to_1055x685_to_224"] = {"frames": n, "us": best * 1e3, "frame_mb": n * 480 * 640 * 3 / 1e6, "write_mb": n * 224 * 224 * 8 / 1e6,
+                                         "gbs_whole_frames": (n * 480 * 640 * 3 + n * 224 * 224 * 8) / (best / 1e3) / 1e9}
 print(json.dumps(out))

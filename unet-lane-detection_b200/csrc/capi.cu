@@ -65,6 +65,7 @@ struct Opts {
   int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
   int stem_fuse = 0;     // inference: the stem runs inside enc0.conv1's patch producer (stem_halo2_kernel), its output never stored
                          // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
+  int host_geometric = 1; // host-buffer entry point: pieces of 16, 32, 64, ... frames (largest first at the output end) instead of equal ones
   int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
                          // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
   int pre_bulk = 1;      // resizing preprocess: source rows staged by the copy engine (cp.async.bulk, two stages) instead of by the threads
@@ -1183,7 +1184,7 @@ int unet_b200_set_option(const char* name, int value) {
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
       {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
       {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}, {"pre_bulk", &g_opts.pre_bulk},
-      {"host_hybrid", &g_opts.host_hybrid}};
+      {"host_hybrid", &g_opts.host_hybrid}, {"host_geometric", &g_opts.host_geometric}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
@@ -1230,10 +1231,12 @@ static int launch_stem_halo(unet_b200_plan* p, const void* x, int batch, int b0,
 // behind, so that only the first piece's input copy and the last piece's output copy are not hidden by kernels. Those three
 // layers have >= 392 tiles per image, so a piece of 32 images still fills the GPU; every other layer runs on the whole batch.
 struct PieceHooks {
-  int piece;                                            // images per piece
+  int np;                                               // pieces of this pass (<= unet_b200_plan::MAX_PIECES)
+  int front_b0[unet_b200_plan::MAX_PIECES], front_n[unet_b200_plan::MAX_PIECES];   // pieces of the first two layers, in run order
+  int tail_b0[unet_b200_plan::MAX_PIECES], tail_n[unet_b200_plan::MAX_PIECES];     // pieces of the last layer, in run order
   void* ctx;
-  int (*before)(void* ctx, int b0, int n);              // before the first layer works on images [b0, b0 + n)
-  int (*after)(void* ctx, int b0, int n);               // after the last layer has been enqueued for images [b0, b0 + n)
+  int (*before)(void* ctx, int i, int b0, int n);       // before the first layer works on front piece i = images [b0, b0 + n)
+  int (*after)(void* ctx, int i, int b0, int n);        // after the last layer has been enqueued for tail piece i
 };
 static bool plan_supports_pieces(const unet_b200_plan* p) {
   if (p->split || p->layers.size() < 4) return false;
@@ -1255,7 +1258,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
   OptScope opt_scope(&p->opt);
   size_t ei = 0;
   if (ev) UB_CUDA(cudaEventRecord((*ev)[ei++], st));
-  if (ph != nullptr && (ph->piece < 1 || !plan_supports_pieces(p))) return fail(UB_ERR_STATE, "plan cannot run in pieces");
+  if (ph != nullptr && (ph->np < 1 || !plan_supports_pieces(p))) return fail(UB_ERR_STATE, "plan cannot run in pieces");
   const int n_layers = (int)p->layers.size();
   for (int li = 0; li < n_layers; ++li) {
     Layer& l = p->layers[li];
@@ -1264,11 +1267,12 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
     void* pool = l.pool >= 0 ? p->ws + p->bufs[l.pool].off : nullptr;
     if (ph != nullptr && (li == 0 || li == n_layers - 1)) {
       // piece-wise: (stem + enc0.conv1) per piece up front, the fused-head conv per piece at the end
-      for (int b0 = 0; b0 < batch; b0 += ph->piece) {
-        const int n = batch - b0 < ph->piece ? batch - b0 : ph->piece;
+      for (int i = 0; i < ph->np; ++i) {
+        const int b0 = li == 0 ? ph->front_b0[i] : ph->tail_b0[i];
+        const int n = li == 0 ? ph->front_n[i] : ph->tail_n[i];
         int rc;
         if (li == 0) {
-          rc = ph->before(ph->ctx, b0, n);
+          rc = ph->before(ph->ctx, i, b0, n);
           if (rc != UB_OK) return rc;
           if (stem_fused(p, n)) {
             rc = launch_stem_halo(p, x, n, b0, st);
@@ -1295,7 +1299,7 @@ static int forward_impl(unet_b200_plan* p, const void* x, int batch, float* logi
           a.mask = mask;
           rc = launch_halo(l.block_n, l.mA0, l.mA1, l.mW, l.mOut, a, st);
           if (rc != UB_OK) return rc;
-          rc = ph->after(ph->ctx, b0, n);
+          rc = ph->after(ph->ctx, i, b0, n);
           if (rc != UB_OK) return rc;
         }
       }
@@ -1634,22 +1638,50 @@ size_t unet_b200_infer_stream_staging_bytes(const unet_b200_plan* p, int Hs, int
   return n;
 }
 
-// pieces of a pass of n frames (0: the plan / the options do not run in pieces), and frames per piece
-static int host_piece_size(const unet_b200_plan* p, int n, int* np) {
-  *np = 0;
-  if (p->opt.host_pieces <= 1 || !plan_supports_pieces(p)) return 0;
-  const int pieces = p->opt.host_pieces < unet_b200_plan::MAX_PIECES ? p->opt.host_pieces : unet_b200_plan::MAX_PIECES;
-  int piece = ((n + pieces - 1) / pieces + 7) & ~7;      // multiples of 8 frames, at least 16
+// Pieces of a pass of n frames: sizes[] in FRONT order, returns their number (0: the plan / the options do not run in pieces).
+// host_geometric (default): 16, 32, 64, ... - a piece's input copy takes about half as long as the two front layers on the
+// same frames, so the copy of a piece twice the size still hides behind the piece before it: the exposed first copy is 16
+// frames, and a pass is four or five pieces instead of eight (every per-piece launch has a tail). The last layer runs the
+// same sizes in reverse order (largest first), so the exposed last output copy is 16 frames as well.
+// Otherwise: `host_pieces` equal pieces (multiples of 8 frames, at least 16).
+static int host_piece_table(const unet_b200_plan* p, int n, int* sizes) {
+  if (p->opt.host_pieces <= 1 || !plan_supports_pieces(p) || n < 1) return 0;
+  const int max_np = p->opt.host_pieces < unet_b200_plan::MAX_PIECES ? p->opt.host_pieces : unet_b200_plan::MAX_PIECES;
+  int np = 0;
+  if (p->opt.host_geometric) {
+    int left = n, sz = 16;
+    while (left > 0) {
+      int take = sz < left ? sz : left;
+      if (np == max_np - 1 || left - take < take) take = left;  // the last piece takes a remainder smaller than itself
+      sizes[np++] = take;
+      left -= take;
+      sz *= 2;
+    }
+    return np;
+  }
+  int piece = ((n + max_np - 1) / max_np + 7) & ~7;
   if (piece < 16) piece = 16;
-  *np = (n + piece - 1) / piece;
-  return piece;
+  for (int b0 = 0; b0 < n; b0 += piece) sizes[np++] = n - b0 < piece ? n - b0 : piece;
+  return np;
+}
+static void host_fill_hooks(PieceHooks* ph, const int* sizes, int np) {
+  ph->np = np;
+  for (int i = 0, b0 = 0; i < np; ++i) {
+    ph->front_b0[i] = b0;
+    ph->front_n[i] = sizes[i];
+    b0 += sizes[i];
+  }
+  for (int i = 0, b0 = 0; i < np; ++i) {      // largest first
+    ph->tail_b0[i] = b0;
+    ph->tail_n[i] = sizes[np - 1 - i];
+    b0 += sizes[np - 1 - i];
+  }
 }
 
 int unet_b200_plan_host_pieces(const unet_b200_plan* p) {
   if (p == nullptr) return 0;
-  int np = 0;
-  host_piece_size(p, p->Bc, &np);
-  return np;
+  int sizes[unet_b200_plan::MAX_PIECES];
+  return host_piece_table(p, p->Bc, sizes);
 }
 
 // Pass schedule of unet_b200_infer_u8_host_stream: frames of pass `it` when `left` of `total` frames remain. With pieces a
@@ -1661,8 +1693,8 @@ static bool host_copy_bound(const unet_b200_plan* p, size_t frame_bytes) { retur
 // pieces for frames of this size? Copy-bound sources take them only in the hybrid schedule (option host_hybrid): a SHORT first
 // pass whose kernels cover the copies of the rest, and inside every pass the pieces, so that only one piece's copy is exposed.
 static bool host_use_pieces(const unet_b200_plan* p, size_t frame_bytes) {
-  int np = 0;
-  if (host_piece_size(p, p->Bc, &np) <= 0) return false;
+  int sizes[unet_b200_plan::MAX_PIECES];
+  if (host_piece_table(p, p->Bc, sizes) <= 0) return false;
   return p->opt.host_hybrid != 0 || !host_copy_bound(p, frame_bytes);
 }
 static int host_pass_size(const unet_b200_plan* p, int it, int left, int total, bool pieces, size_t frame_bytes) {
@@ -1681,13 +1713,12 @@ int unet_b200_infer_stream_launches(const unet_b200_plan* p, int total, int Hs, 
   if (p == nullptr || total < 1) return 0;
   const int per_pass = unet_b200_forward_launches(p) + 1;
   int launches = 0;
-  int np = 0;
   const bool pieces = host_use_pieces(p, (size_t)Hs * Ws * 3);
   int it = 0;
   for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
     n = host_pass_size(p, it, total - b0, total, pieces, (size_t)Hs * Ws * 3);
-    np = 1;
-    if (pieces) host_piece_size(p, n, &np);
+    int sizes[unet_b200_plan::MAX_PIECES];
+    const int np = pieces ? host_piece_table(p, n, sizes) : 1;
     launches += per_pass + 4 * (np - 1);   // preprocess, stem, enc0.conv1 and the fused-head conv once per piece
   }
   return launches;
@@ -1753,7 +1784,7 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
       float *logits_h, *probs_h;    // this pass's rows of the caller's outputs (or null)
       uint8_t* mask_h;
       size_t frame_bytes, hw;
-      int Hs, Ws, swap_rb, piece, n, slot;
+      int Hs, Ws, swap_rb, n, slot;
       const float *mean3, *std3;
     } c;
     c.p = p;
@@ -1768,10 +1799,9 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
     c.std3 = std3;
     PieceHooks ph;
     ph.ctx = &c;
-    ph.before = [](void* v, int b0, int n) -> int {
+    ph.before = [](void* v, int i, int b0, int n) -> int {
       Ctx* c = static_cast<Ctx*>(v);
       unet_b200_plan* p = c->p;
-      const int i = b0 / c->piece;
       UB_CUDA(cudaStreamWaitEvent(c->st, p->ev_piece_in[i], 0));
       int rc = preprocess_impl(c->d_frames + (size_t)b0 * c->frame_bytes, n, c->Hs, c->Ws, (size_t)c->Ws * 3, c->frame_bytes, p->H,
                                p->W, c->swap_rb, c->mean3, c->std3, static_cast<uint8_t*>(c->d_x) + (size_t)b0 * p->H * p->W * 8,
@@ -1780,10 +1810,9 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
       if (b0 + n >= c->n) UB_CUDA(cudaEventRecord(p->ev_in_free[c->slot], c->st));   // the frame slot has been read
       return UB_OK;
     };
-    ph.after = [](void* v, int b0, int n) -> int {
+    ph.after = [](void* v, int i, int b0, int n) -> int {
       Ctx* c = static_cast<Ctx*>(v);
       unet_b200_plan* p = c->p;
-      const int i = b0 / c->piece;
       const size_t o = (size_t)b0 * c->hw, cnt = (size_t)n * c->hw;
       UB_CUDA(cudaEventRecord(p->ev_piece_cmp[i], c->st));
       UB_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_piece_cmp[i], 0));
@@ -1797,8 +1826,9 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
     for (int b0 = 0, n = 0; b0 < total; b0 += n, ++it) {
       n = host_pass_size(p, it, total - b0, total, true, frame_bytes);
       const int slot = it & 1;
-      int np = 0;
-      const int piece = host_piece_size(p, n, &np);
+      int sizes[unet_b200_plan::MAX_PIECES];
+      const int np = host_piece_table(p, n, sizes);
+      host_fill_hooks(&ph, sizes, np);
       for (int i = 0; i < np; ++i) {
         if (p->ev_piece_in[i] == nullptr) {
           UB_CUDA(cudaEventCreateWithFlags(&p->ev_piece_in[i], cudaEventDisableTiming));
@@ -1808,7 +1838,7 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
       // H2D of every piece of this pass (the slot is free once pass it-2's last preprocess has read it)
       if (it >= 2) UB_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_in_free[slot], 0));
       for (int i = 0; i < np; ++i) {
-        const int pb = i * piece, pn = n - pb < piece ? n - pb : piece;
+        const int pb = ph.front_b0[i], pn = ph.front_n[i];
         UB_CUDA(cudaMemcpyAsync(d_frames[slot] + (size_t)pb * frame_bytes, frames + (size_t)(b0 + pb) * frame_bytes,
                                 frame_bytes * pn, cudaMemcpyHostToDevice, p->s_in));
         UB_CUDA(cudaEventRecord(p->ev_piece_in[i], p->s_in));
@@ -1822,10 +1852,8 @@ int unet_b200_infer_u8_host_stream(unet_b200_plan* p, void* staging, const uint8
       c.logits_h = logits_h ? logits_h + (size_t)b0 * hw : nullptr;
       c.probs_h = probs_h ? probs_h + (size_t)b0 * hw : nullptr;
       c.mask_h = mask_h ? mask_h + (size_t)b0 * hw : nullptr;
-      c.piece = piece;
       c.n = n;
       c.slot = slot;
-      ph.piece = piece;
       int rc = forward_impl(p, d_x, n, logits_h ? d_logits[slot] : nullptr, probs_h ? d_probs[slot] : nullptr,
                             mask_h ? d_mask[slot] : nullptr, threshold, st, nullptr, &ph);
       if (rc != UB_OK) return rc;
