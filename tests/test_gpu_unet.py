@@ -329,6 +329,34 @@ def test_fused_head_and_halo_switches_agree(U):
     assert torch.equal(ma, own)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_small_plan_column_blocks_are_bit_identical(U, precision):
+    """Option small_n (default on): a plan too small to give every SM a 128 x 256 tile - the per-frame executor path - runs
+    its per-tap layers with BLOCK_N 128 / 64 (more CTAs). Every output element still accumulates the same products in the
+    same order, so the logits are bit-equal to the BLOCK_N = 256 plan (which the small-batch tests no longer exercise
+    end to end otherwise), for the bf16 and the fp32-class plan."""
+    from unet_lane_detection_b200._lib import check, lib
+    ref, _ = make_pair(U, [64, 128, 256, 512], gain=40.0)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(11)).cuda()
+    outs = []
+    try:
+        for small in (1, 0):
+            check(lib.unet_b200_set_option(b"small_n", small))
+            net = U.UNet(3, 1, [64, 128, 256, 512])
+            net.load_state_dict(ref.state_dict())
+            net = net.cuda().eval()
+            net.b200_precision = precision
+            with torch.no_grad():
+                outs.append(net(x).clone())
+    finally:
+        check(lib.unet_b200_set_option(b"small_n", 1))
+    assert torch.equal(outs[0], outs[1])
+    with torch.no_grad():
+        want = ref(x.cpu())
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    assert (outs[0].cpu() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
+
+
 def test_deployed_topology_32_64_128(U, golden_dir, tmp_path):
     """the topology of model/lane_unet*.rknn = UNet(features=[32,64,128]), 1,927,009
     parameters. Widths that are not multiples of 64 are stored zero-extended; logits must match the oracle as for the

@@ -23,3 +23,21 @@ for _ in range(200):
 ts.sort()
 print(f"run() latency, batch 1 @224x224 (host in -> host out): median {ts[100]:.3f} ms, p10 {ts[20]:.3f}, p90 {ts[180]:.3f}; "
       f"output {out[0].shape} {out[0].dtype}")
+# where the time goes: the captured pass alone (GPU time between two events, replays back to back) and replay + synchronize
+graph = next(iter(box._graphs.values()))[0]
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(200):
+    graph.replay()
+e1.record()
+torch.cuda.synchronize()
+gpu_ms = e0.elapsed_time(e1) / 200
+ts = []
+for _ in range(200):
+    t0 = time.perf_counter()
+    graph.replay()
+    torch.cuda.synchronize()
+    ts.append((time.perf_counter() - t0) * 1e3)
+ts.sort()
+print(f"captured pass alone: {gpu_ms:.3f} ms of GPU time per replay (back to back); replay + synchronize from the host: median {ts[100]:.3f} ms")

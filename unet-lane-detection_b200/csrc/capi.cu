@@ -65,6 +65,7 @@ struct Opts {
   int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
   int stem_fuse = 0;     // inference: the stem runs inside enc0.conv1's patch producer (stem_halo2_kernel), its output never stored
                          // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
+  int small_n = 1;       // plans too small to give every SM a 128 x 256 tile (per-frame executor): narrower column blocks (BLOCK_N 128 / 64)
   int host_geometric = 1; // host-buffer entry point: pieces of 16, 32, 64, ... frames (largest first at the output end) instead of equal ones
   int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
                          // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
@@ -616,6 +617,14 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
     l.block_n = pick_block_n(kind == L_CONV ? Cout : 4 * Cout);
     l.halo = !p->split && (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);   // split plan: per-tap kernel only (4 K sources)
     if (l.halo) l.block_n = Cout;
+    // Small plans (the per-frame executor path): a 14 x 14 level at batch 1 is 4 pixel tiles x 4 column blocks of 256 = 16
+    // CTAs on 148 SMs. Narrower column blocks multiply the CTAs (the pixel tile is re-read from L2, which costs nothing at
+    // this size): halve BLOCK_N while the layer cannot give every SM a tile. Large plans keep 256 (one wave >= 148 tiles).
+    if (!l.halo && tl_opts->small_n) {
+      const int m_tiles = ((W + l.TW - 1) / l.TW) * ((H + l.TH - 1) / l.TH) * ((p->Bc + l.TB - 1) / l.TB);
+      const int N = kind == L_CONV ? Cout : 4 * Cout;
+      while (l.block_n > 64 && m_tiles * (N / l.block_n) < cur_sms()) l.block_n /= 2;
+    }
   }
   p->layers.push_back(l);
   if (kind == L_CONVT) {
@@ -1184,7 +1193,8 @@ int unet_b200_set_option(const char* name, int value) {
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
       {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
       {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}, {"pre_bulk", &g_opts.pre_bulk},
-      {"host_hybrid", &g_opts.host_hybrid}, {"host_geometric", &g_opts.host_geometric}};
+      {"host_hybrid", &g_opts.host_hybrid}, {"host_geometric", &g_opts.host_geometric},
+      {"small_n", &g_opts.small_n}};
   for (auto& e : tab) {
     if (strcmp(name, e.n) == 0) {
       *e.v = value;
