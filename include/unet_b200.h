@@ -44,9 +44,10 @@ int unet_b200_version(void);
 int unet_b200_device_ok(void);
 
 /* ---- plan: UNet(in_channels, out_channels, features) at a fixed HxW and batch capacity ---------- *
- * Mirrors UNet.__init__ (README.md:1424-1447). H and W must be divisible by 2^levels, features
- * multiples of 32 (widths that are not multiples of 64 - the deployed topology [32,64,128] - are stored zero-extended to
- * the next multiple of 64; results are unchanged), in_channels <= 4, out_channels in [1,64] (the reference trains and
+ * Mirrors UNet.__init__ (README.md:1424-1447). H and W must be divisible by 2^levels; features are any positive widths
+ * (widths that are not multiples of 64 - the deployed topology [32,64,128], or 48 / 100 / 264 - are stored zero-extended to
+ * the next multiple of 64; results are unchanged; features[0] <= 256; the fp32-class plan and the trainer keep their own
+ * limits, see there), in_channels <= 4, out_channels in [1,64] (the reference trains and
  * deploys out_channels = 1, README.md:2165; with more the 1x1 head runs as its own kernel instead of inside the last conv). */
 int unet_b200_plan_create(unet_b200_plan** out, int max_batch, int H, int W, int in_channels, int out_channels,
                           const int* features, int levels);

@@ -43,9 +43,14 @@ def test_argument_validation_without_gpu():
     # forward before bind -> state error, never a crash
     assert lib.unet_b200_forward(h, C.c_void_p(8), 1, None, None, None, 0.5, None) == -4
     lib.unet_b200_plan_destroy(h)
-    bad = (C.c_int * 2)(64, 100)
+    odd = (C.c_int * 2)(64, 100)                      # any positive widths (stored zero-extended to multiples of 64)
+    assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 1, odd, 2) == 0
+    lib.unet_b200_plan_destroy(h)
+    bad = (C.c_int * 2)(64, 0)
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 1, bad, 2) == -1
-    assert b"multiple of 32" in lib.unet_b200_last_error()
+    assert b"features[1]" in lib.unet_b200_last_error()
+    wide = (C.c_int * 2)(320, 640)                    # the first block's width is bounded by the stem kernel
+    assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 1, wide, 2) == -1
     assert lib.unet_b200_plan_create(C.byref(h), 8, 100, 224, 3, 1, feats, 4) == -1   # H not divisible by 16
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 5, 1, feats, 4) == -1   # in_channels > 4
     assert lib.unet_b200_plan_create(C.byref(h), 8, 224, 224, 3, 0, feats, 4) == -1   # out_channels < 1

@@ -357,6 +357,28 @@ def test_small_plan_column_blocks_are_bit_identical(U, precision):
     assert (outs[0].cpu() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("feats,H,W", [([48, 96], 64, 96), ([24, 48, 96], 64, 64), ([96, 192], 32, 64), ([20], 16, 24),
+                                       ([72, 144, 288], 32, 32)])
+def test_arbitrary_feature_widths(U, feats, H, W):
+    """UNet(features=...) takes any list of widths the reference's own module accepts (README.md:1424; its decoder needs every
+    width to be twice the one before): channel counts that are not multiples of 64 are stored
+    zero-extended (zero weights, zero bias, relu(0) = 0), so the logits are those of the logical network. Covers widths
+    below and above 64 in the first block (tensor-core stem / FP32-pipe stem), odd multiples of 8 and a width above 256."""
+    ref, net = make_pair(U, feats, gain=40.0)
+    x = torch.randn(3, 3, H, W, generator=torch.Generator().manual_seed(sum(feats)))
+    with torch.no_grad():
+        got = net(x.cuda()).cpu()
+        want = ref(x)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    frames = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    _, _, mask = net.predict_mask(frames.cuda(), size=(H, W), want=("mask",))
+    with torch.no_grad():
+        z = ref(torch.from_numpy(O.normalize_oracle(frames.numpy())))
+    agree = ((z[:, 0] > 0).numpy() == (mask.cpu().numpy() > 0)).mean()
+    assert agree >= 0.995, agree
+
+
 def test_deployed_topology_32_64_128(U, golden_dir, tmp_path):
     """the topology of model/lane_unet*.rknn = UNet(features=[32,64,128]), 1,927,009
     parameters. Widths that are not multiples of 64 are stored zero-extended; logits must match the oracle as for the

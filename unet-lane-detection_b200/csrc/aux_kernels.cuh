@@ -92,7 +92,8 @@ __global__ void pack_convT_pad_kernel(const float* __restrict__ w, const float* 
 __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* __restrict__ mean,
                                  const float* __restrict__ var, float eps, int Cout, int Cin,
-                                 float* __restrict__ ws, float* __restrict__ bias, int keep_fp32) {
+                                 float* __restrict__ ws, float* __restrict__ bias, int keep_fp32, int Cout_l) {
+  // Cout_l <= Cout: logical width of the reference tensors; the channels above it are stored as exact zeros
   pdl_enter();
   const int total = 9 * 4 * Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -100,9 +101,9 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
     const int ci = (i / Cout) % 4;
     const int tap = i / (4 * Cout);
     float s = 1.f;
-    if (gamma != nullptr) s = gamma[co] / sqrtf(var[co] + eps);
+    if (gamma != nullptr && co < Cout_l) s = gamma[co] / sqrtf(var[co] + eps);
     float v = 0.f;
-    if (ci < Cin) {
+    if (ci < Cin && co < Cout_l) {
       // round through bf16 so the stem uses the same weight precision as the tensor-core layers (keep_fp32: split path)
       v = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] * s;
       if (!keep_fp32) v = __bfloat162float(__float2bfloat16_rn(v));
@@ -111,7 +112,7 @@ __global__ void pack_stem_kernel(const float* __restrict__ w, const float* __res
   }
   for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < Cout; co += gridDim.x * blockDim.x) {
     float bv = 0.f;
-    if (gamma != nullptr) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
+    if (gamma != nullptr && co < Cout_l) bv = beta[co] - mean[co] * (gamma[co] / sqrtf(var[co] + eps));
     bias[co] = bv;
   }
 }

@@ -902,14 +902,13 @@ int unet_b200_plan_create_ex(unet_b200_plan** out, int max_batch, int H, int W, 
     return fail(UB_ERR_ARG, "H=%d and W=%d must be divisible by 2^levels=%d", H, W, 1 << levels);
   }
   for (int i = 0; i < levels; ++i) {
-    if (features[i] % 32 != 0 || features[i] <= 0) {
-      return fail(UB_ERR_ARG, "features[%d]=%d must be a positive multiple of 32", i, features[i]);
-    }
+    if (features[i] <= 0 || features[i] > 4096) return fail(UB_ERR_ARG, "features[%d]=%d must be in [1,4096]", i, features[i]);
     if (precision == UB_PRECISION_FP32 && features[i] % 64 != 0) {
       return fail(UB_ERR_ARG, "the fp32-class plan needs features that are multiples of 64 (features[%d]=%d)", i, features[i]);
     }
   }
   if (precision == UB_PRECISION_FP32 && out_channels != 1) return fail(UB_ERR_ARG, "the fp32-class plan needs out_channels == 1");
+  if (features[0] > 256) return fail(UB_ERR_ARG, "features[0]=%d: the first block's width must be <= 256 (stem kernel)", features[0]);
   // physical channel counts: 64-aligned (one 128-byte swizzled row per pixel and channel block); a logical width such as
   // the deployed topology's 32 is stored zero-extended, see pack_conv3x3_pad_kernel
   int fp[UB_MAX_LEVELS];
@@ -1104,7 +1103,7 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
   if (p->split) {
     if (l.kind == L_STEM) {   // fp32 weights, no bf16 rounding
       ub_launch(ub::pack_stem_kernel, grid_for(36 * l.Cout, 256), 256, 0, st, w, gamma, beta, mean, var, eps, l.Cout, l.C0,
-                reinterpret_cast<float*>(p->wt + l.w_off), bias, 1);
+                reinterpret_cast<float*>(p->wt + l.w_off), bias, 1, l.lCout);
     } else {
       ub_launch(ub::pack_conv3x3_split_kernel, grid_for((size_t)l.Cout * 27 * (l.C0 + l.C1), 256), 256, 0, st, w, gamma, beta, mean,
                 var, eps, l.Cout, l.C0, l.C1, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
@@ -1120,9 +1119,8 @@ int unet_b200_plan_set_conv(unet_b200_plan* p, int idx, const float* w, const fl
     ub_launch(ub::pack_stem_umma_kernel, grid_for(64 * l.lCout, 256), 256, 0, st, 
         w, gamma, beta, mean, var, eps, l.lCout, l.C0, reinterpret_cast<__nv_bfloat16*>(p->wt + l.w_off), bias);
   } else if (l.kind == L_STEM) {
-    if (l.lCout != l.Cout) return fail(UB_ERR_ARG, "stem width %d needs the tensor-core stem (option stem_umma)", l.lCout);
     ub_launch(ub::pack_stem_kernel, grid_for(36 * l.Cout, 256), 256, 0, st, w, gamma, beta, mean, var, eps, l.Cout, l.C0,
-                                                                     reinterpret_cast<float*>(p->wt + l.w_off), bias, 0);
+                                                                     reinterpret_cast<float*>(p->wt + l.w_off), bias, 0, l.lCout);
   } else {
     const int cin = l.C0 + l.C1;
     ub_launch(ub::pack_conv3x3_pad_kernel, grid_for((size_t)l.Cout * 9 * cin, 256), 256, 0, st, 
@@ -1957,7 +1955,7 @@ int unet_b200_pack_stem(const float* w, const float* gamma, const float* beta, c
   if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
   ub_launch(ub::pack_stem_kernel, grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
-      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 0);
+      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 0, Cout);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }
@@ -2102,7 +2100,7 @@ int unet_b200_pack_stem_fp32(const float* w, const float* gamma, const float* be
   if (w == nullptr || ws == nullptr || bias == nullptr) return fail(UB_ERR_ARG, "null argument");
   if (Cin < 1 || Cin > 4) return fail(UB_ERR_ARG, "stem Cin must be in [1,4]");
   ub_launch(ub::pack_stem_kernel, grid_for((size_t)36 * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream), 
-      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 1);
+      w, gamma, beta, mean, var, eps, Cout, Cin, ws, bias, 1, Cout);
   UB_CUDA(cudaGetLastError());
   return UB_OK;
 }

@@ -994,7 +994,7 @@ int unet_b200_train_forward(unet_b200_trainer* t, const void* x_nhwc4, const flo
   for (TConv& c : t->convs) {
     if (c.stem && c.Cout != 64) {   // FP32-pipe stem (widths other than 64): fp32 weights, its own small kernel
       ub_launch(ub::pack_stem_kernel, grid_for(36 * c.Cout, 256), 256, 0, st, params + c.w_off, nullptr, nullptr, nullptr, nullptr, 0.f,
-                                                                       c.Cout, c.C0, reinterpret_cast<float*>(c.wp), c.s1, 0);
+                                                                       c.Cout, c.C0, reinterpret_cast<float*>(c.wp), c.s1, 0, c.Cout);
       UB_CUDA(cudaGetLastError());
     }
   }
