@@ -144,7 +144,8 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *                           inside every pass; 0 = pass-granular pipeline without pieces for such frames
  *   "pre_bulk" (default 1)  resizing preprocess: the source rows of a tile are staged by the copy engine (cp.async.bulk
  *                           into two shared-memory stages, preprocess_bulk_u8_kernel); 0 = the thread-staged tile kernel.
- *                           Bit-identical results.
+ *                           Bit-identical results. "pre_rows" / "pre_stages" (default 0 = 8 rows per tile, halved until the
+ *                           stages fit 72 KB / 2 stages) override the tile shape for A/B runs.
  *   "stem_fuse" (default 0) inference plans: the stem is computed inside the patch producer of the first block's second
  *                           conv (stem_halo2_kernel: a small tensor-core GEMM per tile fills the halo'd shared-memory patch), so
  *                           the stem's 64-channel output is never written to or read from HBM; bit-identical results.

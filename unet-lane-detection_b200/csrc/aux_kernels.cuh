@@ -470,8 +470,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_u8_kernel(const Pre
 // Same arithmetic as preprocess_u8_kernel (bit-equal to cv2, test_preprocess_bulk_kernel_*).
 constexpr int PREB_THREADS = 256;
 __host__ __device__ constexpr int preb_slot_pitch(int Ws) { return ((Ws * 3 + 15 + 15) >> 4) << 4; }
-__host__ __device__ constexpr size_t preb_smem_bytes(int Ws, int W, int H, int rows) {
-  return static_cast<size_t>(2) * (2 * rows) * preb_slot_pitch(Ws) + static_cast<size_t>(W + H) * 16;
+constexpr int PREB_MAX_STAGES = 4;
+__host__ __device__ constexpr size_t preb_smem_bytes(int Ws, int W, int H, int rows, int stages = 2) {
+  return static_cast<size_t>(stages) * (2 * rows) * preb_slot_pitch(Ws) + static_cast<size_t>(W + H) * 16;
 }
 __device__ __forceinline__ void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -481,39 +482,51 @@ __device__ __forceinline__ void mbar_add_tx(uint64_t* bar, uint32_t bytes) {   /
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(const PreArgs a, int rows_per_cta) {
+// Template switches keep the per-pixel instruction count down (ncu of the first, all-runtime version: 130 instructions per
+// output pixel, issue-bound at 59 % of the issue slots and 30 % occupancy; 18 % of the stall samples at the end-of-tile
+// __syncthreads): AREA2 = the exact 2x2 decimation, SWAP = R<->B, GENERIC = optional outputs present (resized uint8 copy
+// or fp32 NHWC4) - only then are the output pointers tested per pixel. The vertical blend's ((b * (h >> 4)) >> 16) is one
+// multiply-high with b pre-shifted by 16 (exact: both factors are non-negative), and its result needs no clamp:
+// (b0 + b1) <= 2049 and h >> 4 <= 32655 bound the sum by 1020, so (sum + 2) >> 2 <= 255.
+// Stage hand-back without a CTA barrier: every warp arrives on the stage's `empty` mbarrier when it has finished a tile, and
+// only warp 0 - before it requests the tile after next into that stage - waits for it.
+template <bool AREA2, bool SWAP, bool GENERIC>
+__global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(const PreArgs a, int rows_per_cta, int stages) {
   pdl_enter();
   extern __shared__ __align__(128) uint8_t preb_smem[];
-  __shared__ __align__(8) uint64_t full[2];
-  __shared__ int s_off[2][2 * PRE_ROWS];     // where slot i's row starts inside its stage
+  __shared__ __align__(8) uint64_t full[PREB_MAX_STAGES], empty[PREB_MAX_STAGES];
+  __shared__ int s_off[PREB_MAX_STAGES][2 * PRE_ROWS];     // where slot i's row starts inside its stage
   const int R = rows_per_cta;
+  const int S = stages;        // 2 .. PREB_MAX_STAGES: the rows of the next S - 1 tiles are in flight while one is blended
   const int row_bytes = a.Ws * 3;
   const int P = preb_slot_pitch(a.Ws);
   const int stage_bytes = 2 * R * P;
-  int4* xtab = reinterpret_cast<int4*>(preb_smem + static_cast<size_t>(2) * stage_bytes);
+  int4* xtab = reinterpret_cast<int4*>(preb_smem + static_cast<size_t>(S) * stage_bytes);
   int4* ytab = xtab + a.W;
-  const bool area2 = (a.Hs == 2 * a.H) && (a.Ws == 2 * a.W);
   for (int x = threadIdx.x; x < a.W; x += blockDim.x) {     // {3*sx0, 3*sx1, ax0, ax1}
     int sx0, sx1, ax0, ax1;
     resize_coef(x, a.W, a.Ws, true, sx0, sx1, ax0, ax1);
-    if (area2) {
+    if (AREA2) {
       sx0 = 2 * x;
       sx1 = 2 * x + 1;
     }
     xtab[x] = make_int4(3 * sx0, 3 * sx1, ax0, ax1);
   }
-  for (int y = threadIdx.x; y < a.H; y += blockDim.x) {     // {sy0, sy1, by0, by1}
+  for (int y = threadIdx.x; y < a.H; y += blockDim.x) {     // {sy0, sy1, by0 << 16, by1 << 16}
     int sy0, sy1, by0, by1;
     resize_coef(y, a.H, a.Hs, false, sy0, sy1, by0, by1);
-    if (area2) {
+    if (AREA2) {
       sy0 = 2 * y;
       sy1 = 2 * y + 1;
     }
-    ytab[y] = make_int4(sy0, sy1, by0, by1);
+    ytab[y] = make_int4(sy0, sy1, by0 << 16, by1 << 16);
   }
+  const int nwarps = blockDim.x >> 5;
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 32);
-    mbar_init(&full[1], 32);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 32);
+      mbar_init(&empty[i], nwarps);
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -565,12 +578,26 @@ __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(con
     }
     mbar_arrive(bar);
   };
-  if (threadIdx.x < 32 && static_cast<int>(blockIdx.x) < total) request(blockIdx.x, 0);
-  uint32_t phase = 0;   // bit s: parity of the next completion of stage s
+  const bool producer = threadIdx.x < 32;
+  const int G = gridDim.x;
+  if (producer) {
+    for (int i = 0; i < S - 1; ++i) {
+      if (static_cast<int>(blockIdx.x) + i * G < total) request(blockIdx.x + i * G, i);
+    }
+  }
+  uint32_t phase = 0;    // bit s: parity of the next completion of full[s]
+  uint32_t ephase = 0;   // warp 0, bit s: parity of the completion of empty[s] that frees stage s for its next request
   int stage = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x, stage ^= 1) {
-    // the other stage was last read before the barrier that ended the previous iteration
-    if (threadIdx.x < 32 && t + static_cast<int>(gridDim.x) < total) request(t + gridDim.x, stage ^ 1);
+  for (int t = blockIdx.x, it = 0; t < total; t += G, ++it, stage = (stage + 1 == S) ? 0 : stage + 1) {
+    if (producer && t + (S - 1) * G < total) {
+      // tile it + S - 1 goes to the stage tile it - 1 was read from (none before the first): wait until every warp has left it
+      const int ps = (stage == 0) ? S - 1 : stage - 1;
+      if (it > 0) {
+        mbar_wait(&empty[ps], (ephase >> ps) & 1u);
+        ephase ^= 1u << ps;
+      }
+      request(t + (S - 1) * G, ps);
+    }
     const int b = t / tiles_h;
     const int y0 = (t - b * tiles_h) * R;
     const int nrows = min(R, a.H - y0);
@@ -581,36 +608,43 @@ __global__ void __launch_bounds__(PREB_THREADS, 3) preprocess_bulk_u8_kernel(con
     phase ^= 1u << stage;
     for (int x = threadIdx.x; x < a.W; x += blockDim.x) {
       const int4 xt = xtab[x];
+      const uint32_t ax0 = static_cast<uint32_t>(xt.z), ax1 = static_cast<uint32_t>(xt.w);
+      size_t o = (static_cast<size_t>(b) * a.H + y0) * a.W + x;
 #pragma unroll 4
-      for (int r = 0; r < nrows; ++r) {
+      for (int r = 0; r < nrows; ++r, o += a.W) {
         const int4 yt = ytab[y0 + r];
         const uint8_t* r0 = base + s_off[stage][span ? yt.x - lo : 2 * r];
         const uint8_t* r1 = base + s_off[stage][span ? yt.y - lo : 2 * r + 1];
-        int px[3];
+        const uint8_t *p00 = r0 + xt.x, *p01 = r0 + xt.y, *p10 = r1 + xt.x, *p11 = r1 + xt.y;
+        uint32_t px[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          if (area2) {
-            px[c] = (r0[xt.x + c] + r0[xt.y + c] + r1[xt.x + c] + r1[xt.y + c] + 2) >> 2;
+          const int cs = SWAP ? 2 - c : c;     // source channel of output channel c
+          if (AREA2) {
+            px[c] = (static_cast<uint32_t>(p00[cs]) + p01[cs] + p10[cs] + p11[cs] + 2u) >> 2;
           } else {
-            const int h0 = r0[xt.x + c] * xt.z + r0[xt.y + c] * xt.w;
-            const int h1 = r1[xt.x + c] * xt.z + r1[xt.y + c] * xt.w;
-            px[c] = resize_blend(h0, h1, yt.z, yt.w);
+            const uint32_t h0 = p00[cs] * ax0 + p01[cs] * ax1;
+            const uint32_t h1 = p10[cs] * ax0 + p11[cs] * ax1;
+            px[c] = (__umulhi(static_cast<uint32_t>(yt.z), h0 >> 4) + __umulhi(static_cast<uint32_t>(yt.w), h1 >> 4) + 2u) >> 2;
           }
         }
-        if (a.swap_rb) { const int tt = px[0]; px[0] = px[2]; px[2] = tt; }
-        const size_t o = (static_cast<size_t>(b) * a.H + y0 + r) * a.W + x;
-        if (a.dst_u8 != nullptr) {
-          a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
-          a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
-          a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+        const float f0 = (static_cast<int>(px[0]) - a.mean[0]) * a.inv_std[0];
+        const float f1 = (static_cast<int>(px[1]) - a.mean[1]) * a.inv_std[1];
+        const float f2 = (static_cast<int>(px[2]) - a.mean[2]) * a.inv_std[2];
+        if (GENERIC) {
+          if (a.dst_u8 != nullptr) {
+            a.dst_u8[o * 3 + 0] = static_cast<uint8_t>(px[0]);
+            a.dst_u8[o * 3 + 1] = static_cast<uint8_t>(px[1]);
+            a.dst_u8[o * 3 + 2] = static_cast<uint8_t>(px[2]);
+          }
+          pre_store(a, o, f0, f1, f2);
+        } else {
+          a.dst[o] = make_uint2(pack_bf16x2(f0, f1), pack_bf16x2(f2, 0.f));
         }
-        const float f0 = (px[0] - a.mean[0]) * a.inv_std[0];
-        const float f1 = (px[1] - a.mean[1]) * a.inv_std[1];
-        const float f2 = (px[2] - a.mean[2]) * a.inv_std[2];
-        pre_store(a, o, f0, f1, f2);
       }
     }
-    __syncthreads();   // every thread has read this stage (and its offset table): the next iteration may refill it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage]);   // this warp has read the stage and its offset table
   }
 }
 

@@ -69,6 +69,8 @@ struct Opts {
   int host_geometric = 1; // host-buffer entry point: pieces of 16, 32, 64, ... frames (largest first at the output end) instead of equal ones
   int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
                          // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
+  int pre_rows = 0;      // resizing preprocess, bulk form: output rows per tile (0: 8, halved until the stages fit)
+  int pre_stages = 0;    // resizing preprocess, bulk form: shared-memory stages (0: 2)
   int pre_bulk = 1;      // resizing preprocess: source rows staged by the copy engine (cp.async.bulk, two stages) instead of by the threads
 };
 Opts g_opts;
@@ -100,7 +102,7 @@ enum AttrSlot : int {
   AT_STEM_WIDE = 22,
   AT_WGRAD_HALO = 23,
   AT_STEM_HALO = 24,
-  AT_PRE_BULK = 25,
+  AT_PRE_BULK = 25,   // + {0..7}: {2x2 decimation, swap, generic outputs} instantiations
 };
 struct DevState {
   std::atomic<int> num_sms{0};
@@ -1190,7 +1192,7 @@ int unet_b200_set_option(const char* name, int value) {
       {"wgrad2", &g_opts.wgrad2}, {"wgrad_stream", &g_opts.wgrad_stream}, {"bwd_fuse", &g_opts.bwd_fuse},
       {"stem_wide", &g_opts.stem_wide}, {"dgrad_fuse", &g_opts.dgrad_fuse},
       {"wgrad_halo", &g_opts.wgrad_halo}, {"pack_split", &g_opts.pack_split},
-      {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}, {"pre_bulk", &g_opts.pre_bulk},
+      {"host_pieces", &g_opts.host_pieces}, {"stem_fuse", &g_opts.stem_fuse}, {"pre_bulk", &g_opts.pre_bulk}, {"pre_rows", &g_opts.pre_rows}, {"pre_stages", &g_opts.pre_stages},
       {"host_hybrid", &g_opts.host_hybrid}, {"host_geometric", &g_opts.host_geometric},
       {"small_n", &g_opts.small_n}};
   for (auto& e : tab) {
@@ -1512,22 +1514,39 @@ static int preprocess_impl(const uint8_t* src, int batch, int Hs, int Ws, size_t
   }
   // the copy engine stages the rows (two stages in flight), see preprocess_bulk_u8_kernel
   if (tl_opts->pre_bulk) {
-    int rb = ub::PRE_ROWS;
-    while (rb > 1 && ub::preb_smem_bytes(Ws, W, H, rb) > 72 * 1024) rb >>= 1;
-    const size_t smem_b = ub::preb_smem_bytes(Ws, W, H, rb);
+    // tile rows / stages: the staged rows of all stages within ~72 KB (three CTAs per SM). Options pre_rows / pre_stages
+    // override the choice for A/B runs.
+    int st_b = tl_opts->pre_stages >= 2 && tl_opts->pre_stages <= ub::PREB_MAX_STAGES ? tl_opts->pre_stages : 2;
+    int rb = tl_opts->pre_rows >= 1 && tl_opts->pre_rows <= ub::PRE_ROWS ? tl_opts->pre_rows : ub::PRE_ROWS;
+    const size_t cap_b = (tl_opts->pre_rows >= 1 ? 200 : 72) * 1024;     // explicit rows: only the hardware limit
+    while (rb > 1 && ub::preb_smem_bytes(Ws, W, H, rb, st_b) > cap_b) rb >>= 1;
+    const size_t smem_b = ub::preb_smem_bytes(Ws, W, H, rb, st_b);
     if (smem_b <= 200 * 1024) {
-      if (smem_b > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_bulk_u8_kernel, AT_PRE_BULK, 200 * 1024));
       int threads = ((W + 31) / 32) * 32;       // a thread owns output columns: no idle warps for W < 256
       if (threads > ub::PREB_THREADS) threads = ub::PREB_THREADS;
       const int tiles_b = batch * ((H + rb - 1) / rb);
-      int per_sm_b = 0;
-      UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, ub::preprocess_bulk_u8_kernel, threads, smem_b));
-      per_sm_b = per_sm_b < 1 ? 1 : per_sm_b;
-      const int resident_b = cur_sms() * per_sm_b;
-      ub_launch(ub::preprocess_bulk_u8_kernel, tiles_b < resident_b ? tiles_b : resident_b, threads, smem_b,
-                static_cast<cudaStream_t>(stream), a, rb);
-      UB_CUDA(cudaGetLastError());
-      return UB_OK;
+      const bool area2 = Hs == 2 * H && Ws == 2 * W, generic = resized != nullptr || y_f32;
+      // instantiation: optional outputs -> the generic form; else {2x2 decimation} x {R<->B swap}
+      auto go = [&](auto kernel, int slot) -> int {
+        if (smem_b > 48 * 1024) UB_CUDA(ensure_smem(kernel, slot, 200 * 1024));
+        int per_sm_b = 0;
+        UB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, kernel, threads, smem_b));
+        per_sm_b = per_sm_b < 1 ? 1 : per_sm_b;
+        const int resident_b = cur_sms() * per_sm_b;
+        ub_launch(kernel, tiles_b < resident_b ? tiles_b : resident_b, threads, smem_b, static_cast<cudaStream_t>(stream), a, rb, st_b);
+        UB_CUDA(cudaGetLastError());
+        return UB_OK;
+      };
+      if (generic) {
+        if (area2) return swap_rb ? go(ub::preprocess_bulk_u8_kernel<true, true, true>, AT_PRE_BULK + 4)
+                                  : go(ub::preprocess_bulk_u8_kernel<true, false, true>, AT_PRE_BULK + 5);
+        return swap_rb ? go(ub::preprocess_bulk_u8_kernel<false, true, true>, AT_PRE_BULK + 6)
+                       : go(ub::preprocess_bulk_u8_kernel<false, false, true>, AT_PRE_BULK + 7);
+      }
+      if (area2) return swap_rb ? go(ub::preprocess_bulk_u8_kernel<true, true, false>, AT_PRE_BULK + 0)
+                                : go(ub::preprocess_bulk_u8_kernel<true, false, false>, AT_PRE_BULK + 1);
+      return swap_rb ? go(ub::preprocess_bulk_u8_kernel<false, true, false>, AT_PRE_BULK + 2)
+                     : go(ub::preprocess_bulk_u8_kernel<false, false, false>, AT_PRE_BULK + 3);
     }
   }
   if (smem > 48 * 1024) UB_CUDA(ensure_smem(ub::preprocess_u8_kernel, AT_PRE, 200 * 1024));
