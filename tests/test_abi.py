@@ -146,3 +146,35 @@ def rs_default():
         rs.append((lo.value, hi.value))
     lib.unet_b200_trainer_destroy(h)
     return rs
+
+
+def test_host_pipeline_schedule_without_gpu():
+    """Pass / piece schedule of unet_b200_infer_u8_host_stream (pure host logic, include/unet_b200.h): a pass of 256 frames is
+    cut into the geometric pieces 16 + 32 + 64 + 144; the preprocess, the stem, enc0.conv1 and the fused-head conv run once
+    per piece, every other layer once per pass. Camera-size sources (copy-bound) get a short first pass (64 = 16 + 48) and
+    then 192 = 16 + 32 + 64 + 80; 600 frames are 256 + 256 + 88 (16 + 32 + 40)."""
+    from unet_lane_detection_b200._lib import check, lib
+    h = C.c_void_p()
+    feats = (C.c_int * 4)(64, 128, 256, 512)
+    assert lib.unet_b200_plan_create(C.byref(h), 256, 224, 224, 3, 1, feats, 4) == 0
+    per_pass = lib.unet_b200_forward_launches(h) + 1          # + preprocess
+    assert per_pass == 23 and lib.unet_b200_plan_host_pieces(h) == 4
+    assert lib.unet_b200_infer_stream_launches(h, 256, 224, 224) == per_pass + 4 * 3
+    assert lib.unet_b200_infer_stream_launches(h, 256, 480, 640) == (per_pass + 4 * 1) + (per_pass + 4 * 3)
+    assert lib.unet_b200_infer_stream_launches(h, 600, 224, 224) == 2 * (per_pass + 4 * 3) + (per_pass + 4 * 2)
+    assert lib.unet_b200_infer_stream_launches(h, 1, 224, 224) == per_pass
+    lib.unet_b200_plan_destroy(h)
+    try:    # equal pieces (host_geometric = 0): eight pieces of 32; plans copy the defaults when they are created
+        check(lib.unet_b200_set_option(b"host_geometric", 0))
+        assert lib.unet_b200_plan_create(C.byref(h), 256, 224, 224, 3, 1, feats, 4) == 0
+        assert lib.unet_b200_plan_host_pieces(h) == 8
+        assert lib.unet_b200_infer_stream_launches(h, 256, 224, 224) == per_pass + 4 * 7
+        lib.unet_b200_plan_destroy(h)
+        check(lib.unet_b200_set_option(b"host_pieces", 0))
+        assert lib.unet_b200_plan_create(C.byref(h), 256, 224, 224, 3, 1, feats, 4) == 0
+        assert lib.unet_b200_plan_host_pieces(h) == 0
+        assert lib.unet_b200_infer_stream_launches(h, 256, 224, 224) == 2 * per_pass     # pass-granular: 64 + 192
+        lib.unet_b200_plan_destroy(h)
+    finally:
+        check(lib.unet_b200_set_option(b"host_geometric", 1))
+        check(lib.unet_b200_set_option(b"host_pieces", 8))
