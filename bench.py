@@ -161,12 +161,12 @@ def cpu_reference_pipeline(model_cpu, frames_u8_nhwc, threshold=0.5):
     return [O.postprocess_oracle([logits[i:i + 1]], (224, 224), threshold) for i in range(len(frames_u8_nhwc))]
 
 
-def time_cpu_reference(frames_per_step, steps, warmup):
-    """frames/s of the oracle pipeline on the host cores, all threads."""
+def time_cpu_reference(frames_per_step, steps, warmup, threads=None):
+    """frames/s of the oracle pipeline on the host cores, all threads (or `threads`)."""
     import numpy as np
     import torch
     from oracle import unet_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
     m = O.UNetOracle(3, 1, FEATURES).eval()
     O.randomize_bn_(m, 1)
@@ -669,6 +669,8 @@ def main():
         v, sps, threads = time_cpu_reference(32, 6, 1)      # about 10-15 s of CPU work on the box's host cores
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"32 frames/step x 6 steps ({sps * 6:.1f} s) of the oracle fp32 PyTorch CPU pipeline"}
+        v1, sps1, _ = time_cpu_reference(2, 2, 1, threads=1)      # the single-thread figure as well
+        line["cpu_baseline"]["one_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": f"2 frames/step x 2 steps ({sps1 * 2:.1f} s)"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:
