@@ -132,9 +132,11 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad_halo" (default 1) training: weight gradients of the 3x3 convs with Cout == 64 (the full-resolution level) run on
  *                           wgrad_halo_kernel - one halo'd activation patch serves all nine taps - instead of one CTA per tap pair
  *   "host_pieces" (default 8) unet_b200_infer_u8_host_stream: pieces per pass (see there); 0 or 1 = pass-granular pipeline
- *   "small_n" (default 1)   plans whose capacity cannot give every SM a 128 x 256 output tile (the per-frame executor path:
- *                           a 14 x 14 level at batch 1 is 16 such tiles on 148 SMs) run their per-tap layers with column
- *                           blocks of 128 or 64 instead; bit-identical logits. run() latency at batch 1: 0.58 -> 0.46 ms
+ *   "small_n" (default 1)   small plans (the per-frame executor path: a 14 x 14 level at batch 1 is 16 tiles of 128 x 256
+ *                           on 148 SMs) run their per-tap layers with column blocks of 128 or 64 where a wave model
+ *                           (rounds of the persistent grid x measured tile cost 1 : 0.56 : 0.375) says that is faster;
+ *                           2 = narrower blocks only while a layer cannot give every SM a tile (the first rule: 5-8 %
+ *                           slower at batches 2-8), 0 = always 256; bit-identical logits. Pass of one frame 0.38 -> 0.27 ms
  *   "host_geometric" (default 1) unet_b200_infer_u8_host_stream: the pieces of a pass are 16, 32, 64, ... frames (the copy of a
  *                           piece hides behind the front layers of the piece half its size before it) and the last layer
  *                           runs them largest first: 16 frames of input / output copy exposed and 4 instead of 8 launches per

@@ -65,7 +65,8 @@ struct Opts {
   int host_pieces = 8;   // host-buffer entry point: pieces per pass whose copies are pipelined with the first / last layers (0: off)
   int stem_fuse = 0;     // inference: the stem runs inside enc0.conv1's patch producer (stem_halo2_kernel), its output never stored
                          // (bit-identical; measured the same speed as the two kernels - shared-memory bound - so off)
-  int small_n = 1;       // plans too small to give every SM a 128 x 256 tile (per-frame executor): narrower column blocks (BLOCK_N 128 / 64)
+  int small_n = 1;       // small plans (per-frame executor, batches up to ~32): narrower column blocks (BLOCK_N 128 / 64) where the
+                         // wave model says they are faster; 2 = only while a layer cannot give every SM a tile; 0 = always 256
   int host_geometric = 1; // host-buffer entry point: pieces of 16, 32, 64, ... frames (largest first at the output end) instead of equal ones
   int host_hybrid = 1;   // host-buffer entry point, source frames much larger than the network input (copy-bound): short first pass
                          // AND pieces inside every pass (0: pass-granular pipeline without pieces, the earlier form)
@@ -620,12 +621,34 @@ void add_conv(unet_b200_plan* p, LayerKind kind, int H, int W, int C0, int C1, i
     l.halo = !p->split && (kind == L_CONV) && halo_eligible(H, W, C0, C1, Cout);   // split plan: per-tap kernel only (4 K sources)
     if (l.halo) l.block_n = Cout;
     // Small plans (the per-frame executor path): a 14 x 14 level at batch 1 is 4 pixel tiles x 4 column blocks of 256 = 16
-    // CTAs on 148 SMs. Narrower column blocks multiply the CTAs (the pixel tile is re-read from L2, which costs nothing at
-    // this size): halve BLOCK_N while the layer cannot give every SM a tile. Large plans keep 256 (one wave >= 148 tiles).
+    // CTAs on 148 SMs. Narrower column blocks multiply the CTAs (the pixel tile is re-read from L2, which costs little at
+    // this size). small_n = 1 (default): the block width with the lowest modelled time; 2: the first rule - halve BLOCK_N
+    // while the layer cannot give every SM a tile. Plans of 64 frames and more keep 256 under both.
     if (!l.halo && tl_opts->small_n) {
       const int m_tiles = ((W + l.TW - 1) / l.TW) * ((H + l.TH - 1) / l.TH) * ((p->Bc + l.TB - 1) / l.TB);
       const int N = kind == L_CONV ? Cout : 4 * Cout;
-      while (l.block_n > 64 && m_tiles * (N / l.block_n) < cur_sms()) l.block_n /= 2;
+      if (tl_opts->small_n == 1) {
+        // wave model: rounds of the persistent grid x cost of one tile. Measured (tools/ab_small_n.py): a 128-wide tile
+        // costs 0.56 of a 256-wide one, not 0.5 (the pixel tile is fetched twice as often per FLOP) - with 0.5 the model moved
+        // a 16-frame 480 x 640 plan to 128-wide tiles and lost 7 %; a 64-wide tile 3/8 (its MMAs are bound by the A operand's
+        // shared-memory reads)
+        const bool pair = tl_opts->umma2 && m_tiles >= 2;
+        const int slots = pair ? cur_sms() / 2 : cur_sms();
+        long best_cost = -1;
+        int best_bn = l.block_n;
+        for (int bn = l.block_n; bn >= 64; bn /= 2) {
+          if (N % bn != 0) continue;
+          const long tiles = (long)(pair ? (m_tiles + 1) / 2 : m_tiles) * (N / bn);
+          const long cost = ((tiles + slots - 1) / slots) * (bn == 256 ? 16 : bn == 128 ? 9 : 6);
+          if (best_cost < 0 || cost * 103 < best_cost * 100) {    // narrower only for a gain of more than 3 %
+            best_cost = cost;
+            best_bn = bn;
+          }
+        }
+        l.block_n = best_bn;
+      } else {
+        while (l.block_n > 64 && m_tiles * (N / l.block_n) < cur_sms()) l.block_n /= 2;
+      }
     }
   }
   p->layers.push_back(l);
