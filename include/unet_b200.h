@@ -120,7 +120,10 @@ int unet_b200_plan_layer_info(const unet_b200_plan* p, int idx, int* info8);
  *   "wgrad_rows64" (default 1) 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
  *   "wgrad2" (default 1)    CTA-pair weight-gradient kernel for Cout >= 128 (read when a trainer / wgrad call is set up)
  *   "wgrad_stream" (default 1) backward: weight-gradient GEMMs on a side stream, overlapping the elementwise backward passes
- *   "pdl" (default 0)       programmatic dependent launch for every kernel (measured slower on B200)
+ *   "pdl" (default -1)      programmatic dependent launch for every kernel: the conv / stem kernels run their prologue before
+ *                           griddepcontrol.wait, so it overlaps the predecessor's tail. -1 = per plan: on for plans of up to
+ *                           600 k pixels (one 224 x 224 frame: 0.319 -> 0.262 ms per pass), off above (2-3 % slower from 32
+ *                           frames on; trainers and the single-layer entry points: off); 0 / 1 force it
  *   "bwd_fuse" (default 2)  training: the BatchNorm-backward reduction of a layer runs inside the pass that produces its
  *                           incoming gradient where that pass is an elementwise kernel: 2 = the head backward only
  *                           (measured 16.81-16.99 against 17.00-17.24 ms/step), 1 = also the four max-pool backward passes

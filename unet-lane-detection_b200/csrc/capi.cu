@@ -51,7 +51,7 @@ struct Opts {
   int stem_umma = 1;     // Cout == 64 stem on tensor cores (stem_umma.cuh) instead of the FP32-pipe kernel
   int halo2 = 1;         // halo layers on the CTA-pair kernel when at least two tiles exist
   int umma2 = 1;         // per-tap layers on the CTA-pair kernel when at least two pixel tiles exist
-  int pdl = 0;           // programmatic dependent launch (measured slower, see below)
+  int pdl = -1;          // programmatic dependent launch: -1 = per plan (on for small plans, see plan_create), 0 / 1 = off / on
   int wgrad_rows64 = 1;  // 64-pixel reduction tiles in the BLOCK_N = 256 weight-gradient kernel
   int wgrad2 = 1;        // CTA-pair weight-gradient kernel for BLOCK_N >= 128
   int wgrad_stream = 1;  // weight-gradient GEMMs on a side stream
@@ -134,10 +134,11 @@ cudaError_t ensure_smem(K kernel, int slot, int bytes) {
 }
 
 // Every kernel launch of the library. With the "pdl" option a kernel may be scheduled before its
-// stream predecessor has drained (programmatic dependent launch; every kernel starts with pdl_enter(), ptx.cuh, so the ordering
-// of the data is unchanged). OFF by default: measured on B200 (tools/ab_option.py pdl, same box, alternating) it is SLOWER -
-// inference 17.0 k -> 16.4 k frames/s, training 18.9 -> 19.3 ms/step - the persistent one-CTA-per-SM kernels leave no room for
-// an early dependent, and its parked CTAs only get in the way of the tail.
+// stream predecessor has drained (programmatic dependent launch; every kernel executes griddepcontrol.wait before its first
+// global access - pdl_enter() / pdl_wait(), ptx.cuh - so the ordering of the data is unchanged). For LARGE batches it is
+// slower (tools/ab_option.py pdl, same box, alternating: inference 17.0 k -> 16.4 k frames/s, training 18.9 -> 19.3 ms/step -
+// the persistent one-CTA-per-SM kernels leave no room for an early dependent, and its parked CTAs only get in the way of the
+// tail); for small plans it hides the kernels' prologues: the default (-1) lets plan_create decide.
 template <typename... KArgs, typename... Args>
 void ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -148,7 +149,7 @@ void ub_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = tl_opts->pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = tl_opts->pdl > 0 ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError() at the call site
@@ -948,6 +949,12 @@ int unet_b200_plan_create_ex(unet_b200_plan** out, int max_batch, int H, int W, 
   p->levels = levels;
   p->split = precision == UB_PRECISION_FP32 ? 1 : 0;
   p->opt = g_opts;                // this plan's switches from here on
+  // Programmatic dependent launch: the conv / stem kernels run their prologue (barrier init, TMEM allocation, descriptor
+  // prefetch) before griddepcontrol.wait, so with the launch attribute set it overlaps the predecessor's tail. That pays
+  // when kernels are short - one 224 x 224 frame: 0.319 -> 0.262 ms per pass, 8 frames 0.62 -> 0.59 - is neutral at 16
+  // frames and costs 2-3 % from 32 frames on (an early dependent's parked CTAs get in the way of a persistent grid's tail;
+  // tools/ab_plan_option.py pdl 0 1, profiles/r2_ab_pdl.log): on by default for plans of up to 600 k pixels.
+  if (p->opt.pdl < 0) p->opt.pdl = (size_t)max_batch * H * W <= 600000 ? 1 : 0;
   OptScope opt_scope(&p->opt);
   p->ws_bytes = 0;
   p->wt_bytes = 0;

@@ -135,6 +135,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   tc_fence_before();
   cta_sync_p<PAIR>();   // (pair: the peer's barriers are initialised before anything signals them)
   tc_fence_after();
+  pdl_wait();           // programmatic dependent launch: everything above overlapped the predecessor's tail
   const uint32_t tmem_base = *tmem_slot;
 
   const int KC = a.kc0 + a.kc1;
@@ -385,13 +386,13 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(UB_CONV_HALO_PARAMS) {
-  pdl_enter();
+  pdl_launch();
   conv_halo_body<BLOCK_N, false>(tmA0, tmA1, tmW, tmOut, tmY, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1) conv_halo2_kernel(UB_CONV_HALO_PARAMS) {
-  pdl_enter();
+  pdl_launch();
   conv_halo_body<BLOCK_N, true>(tmA0, tmA1, tmW, tmOut, tmY, a);
 }
 

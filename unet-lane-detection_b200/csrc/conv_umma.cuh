@@ -132,6 +132,7 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
   tc_fence_before();
   cta_sync_p<PAIR>();   // (pair: the peer's barriers are initialised before anything signals them)
   tc_fence_after();
+  pdl_wait();           // programmatic dependent launch: everything above overlapped the predecessor's tail
   const uint32_t tmem_base = *tmem_slot;
 
   const int kchunks = a.kc0 + a.kc1 + a.kc2 + a.kc3;
@@ -430,13 +431,13 @@ __device__ __forceinline__ void conv_umma_body(const CUtensorMap& tmA0, const CU
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(UB_CONV_UMMA_PARAMS) {
-  pdl_enter();
+  pdl_launch();
   conv_umma_body<BLOCK_N, false>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, tmY, a);
 }
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv_umma2_kernel(UB_CONV_UMMA_PARAMS) {
-  pdl_enter();
+  pdl_launch();
   conv_umma_body<BLOCK_N, true>(tmA0, tmA1, tmA2, tmA3, tmW, tmO0, tmO1, tmO2, tmO3, tmY, a);
 }
 

@@ -35,6 +35,11 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves, for kernels with a prologue worth overlapping (barrier init, TMEM allocation, descriptor prefetch - none of
+// which touches global memory): pdl_launch() first thing, pdl_wait() by EVERY thread after the prologue's barrier and before
+// the first global access of any role (loads AND stores: an output buffer may alias one the predecessor still reads).
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

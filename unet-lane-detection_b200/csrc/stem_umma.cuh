@@ -68,7 +68,7 @@ __global__ void pack_stem_umma_kernel(const float* __restrict__ w, const float* 
 template <int TW>
 __global__ void __launch_bounds__(StemCfg::THREADS, 1)
 stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
-  pdl_enter();
+  pdl_launch();
   using Cfg = StemCfg;
   constexpr int TH = 128 / TW;             // tile rows
   constexpr int PW = TW + 2;               // patch pitch in pixels
@@ -114,6 +114,7 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = a.tiles_w * a.tiles_h;
