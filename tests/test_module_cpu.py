@@ -141,3 +141,33 @@ def test_deployed_topology_key_remap_round_trip():
     assert remap_milesial_state_dict(sd) is sd
     with pytest.raises(ValueError):
         remap_milesial_state_dict({"foo.weight": torch.zeros(1)})
+
+
+def test_weights_key_and_copies_of_the_module():
+    """The per-call staleness key of a live module (identity + in-place version of all 118 tensors, read through cached
+    (dict, name) slots) notices in-place updates, load_state_dict and a replaced Parameter object; copy.deepcopy / torch.save
+    of the module leave the plans and other runtime state behind (a copy builds its own)."""
+    import copy
+    import io
+    net = U.UNet(3, 1, [64, 128]).eval()
+    k0 = net._weights_key()
+    assert len(k0) == 1 + len(list(net.parameters())) + len(list(net.buffers())) and net._weights_key() == k0
+    with torch.no_grad():
+        net.output.bias.add_(1.0)
+    k1 = net._weights_key()
+    assert k1 != k0
+    net.load_state_dict(copy.deepcopy(net.state_dict()))
+    k2 = net._weights_key()
+    assert k2 != k1
+    net.output.weight = torch.nn.Parameter(torch.zeros_like(net.output.weight))
+    assert net._weights_key() != k2
+    net._engines["stand-in"] = object()
+    twin = copy.deepcopy(net)
+    assert len(twin._engines) == 0 and twin._last_engine is None and "_b200_key_slots" not in twin.__dict__
+    assert twin._weights_key() != net._weights_key()          # its own tensors
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), twin.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert len(back._engines) == 0 and back.features == net.features and back.b200_chunk == net.b200_chunk

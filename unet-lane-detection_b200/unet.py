@@ -76,6 +76,21 @@ class UNet(nn.Module):
         self._last_engine = None
         self.gpu_launches = 0
 
+    # copy.deepcopy(model) / torch.save(model): the plans, their workspaces and the flat training buffers belong to THIS object
+    # (ctypes handles, CUDA graphs) - a copy starts without them and builds its own on first use
+    _RUNTIME_STATE = ("_engines", "_last_engine", "_b200_key_slots", "_b200_flat", "_b200_flat_symm")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._RUNTIME_STATE:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._engines = OrderedDict()
+        self._last_engine = None
+
     def _conv_block(self, in_channels, out_channels):
         return nn.Sequential(
             nn.Conv2d(in_channels, out_channels, 3, padding=1, bias=False),
@@ -95,7 +110,16 @@ class UNet(nn.Module):
             yield blk[3], blk[4]
 
     def _weights_key(self):
-        return (self._b200_epoch,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        """Identity + in-place version of every parameter and buffer: a changed key means the plan's packed weights are stale.
+        Runs on every eval call of a live (not frozen) module, so the module tree is walked once and the key is read through
+        the registered (dict, name) slots - a replaced Parameter object is still seen, the generators of `parameters()` /
+        `buffers()` (most of the former 0.14 ms) are not re-run."""
+        slots = self.__dict__.get("_b200_key_slots")
+        if slots is None:
+            slots = [(m._parameters, n) for m in self.modules() for n, p in m._parameters.items() if p is not None]
+            slots += [(m._buffers, n) for m in self.modules() for n, b in m._buffers.items() if b is not None]
+            self.__dict__["_b200_key_slots"] = slots
+        return (self._b200_epoch,) + tuple((d[n].data_ptr(), d[n]._version) for d, n in slots)
 
     def _engine(self, device, H, W, batch, pipelined=False):
         prec = self.b200_precision
