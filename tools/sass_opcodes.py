@@ -1,7 +1,8 @@
 """Opcode evidence for the shipped library: per kernel, how many tcgen05 / TMEM / TMA / cluster instructions its SASS holds.
     python tools/sass_opcodes.py > profiles/r2_sass_opcodes.txt
 Runs on the build machine (cuobjdump needs no GPU). Mnemonics: UTCHMMA = tcgen05.mma (.2CTA = cta_group::2), LDTM = tcgen05.ld,
-UTCBAR = tcgen05.commit, UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA), UCGABAR = barrier.cluster,
+UTCBAR = tcgen05.commit, UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA), UBLKCP = cp.async.bulk (untiled bulk copy,
+the resizing preprocess), UCGABAR = barrier.cluster,
 SYNCS = mbarrier, UTCATOMSWS = tcgen05.alloc / dealloc, LDGMC = multimem.ld_reduce (NVLS; multimem.st lowers to a plain STG.E.STRONG.SYS on the multicast address) - /opt/skills/guides/B200_PROFILING.md."""
 import collections
 import os
@@ -11,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "unet-lane-detection_b200", "libunet_b200.so")
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "UCGABAR", "SYNCS", "UTCATOMSWS", "LDGMC", "HMMA", "FFMA", "DFMA"]
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "UCGABAR", "SYNCS", "UTCATOMSWS", "LDGMC", "HMMA", "FFMA", "DFMA"]
 
 
 def main():
