@@ -106,4 +106,22 @@ def test_lane_pipeline_matches_reference_callback(U, G, tmp_path):
         assert (masks[i] == want).mean() >= 0.999
     single = pipe.process(frames[0])
     assert np.array_equal(single, masks[0])
+    # per-frame calls replay one captured pass: a different frame through the same graph, then the first one again
+    assert np.array_equal(pipe.process(frames[1]), masks[1])
+    assert np.array_equal(pipe.process(frames[0]), masks[0])
+    # (these weights put every pixel above 0.5; a threshold at the median probability makes the mask depend on the frame)
+    thr = float(torch.sigmoid(z.median()))
+    pipe2 = U.B200LanePipeline(str(path), g["M"], threshold=thr)
+    rnd = np.random.default_rng(5).integers(0, 256, frames[0].shape, dtype=np.uint8)
+    got = [pipe2.process(f) for f in (frames[0], rnd, frames[0])]
+    eager = [pipe2.process_device(torch.from_numpy(f[None]).cuda())[0].cpu().numpy() for f in (frames[0], rnd)]
+    assert np.array_equal(got[0], eager[0]) and np.array_equal(got[1], eager[1]) and np.array_equal(got[2], eager[0])
+    assert 0.02 < (got[0] > 0).mean() < 0.98 and not np.array_equal(got[0], got[1])
+    pipe2.release()
+    launches = pipe.container.model.gpu_launches
+    pipe.process(frames[1])
+    assert pipe.container.model.gpu_launches - launches == 24     # warp-preprocess + 22 network kernels + mask resize
+    # more frames than the graph path takes (eager), same masks
+    many = pipe.process(np.concatenate([frames] * 5))
+    assert many.shape[0] == 10 and np.array_equal(many[4], masks[0]) and np.array_equal(many[9], masks[1])
     pipe.release()

@@ -48,3 +48,21 @@ for _ in range(200):
     ts.append((time.perf_counter() - t0) * 1e3)
 ts.sort()
 print(f"captured pass alone: {gpu_ms:.3f} ms of GPU time per replay (back to back); replay + synchronize from the host: median {ts[100]:.3f} ms")
+
+# the ROS callback as INTEGRATION.md wires it: B200LanePipeline.process(bgr 480x640 frame) -> uint8 mask 685x1055 (IPM warp,
+# resize, network, threshold and mask up-resize on the GPU; one captured pass per call)
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ipm.npz"))
+with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, "unet.pth")
+    torch.save({"model_state_dict": U.UNet(3, 1, [64, 128, 256, 512]).state_dict()}, path)
+    pipe = U.B200LanePipeline(path, g["M"], threshold=0.5)
+cam = np.random.default_rng(1).integers(0, 256, (480, 640, 3), dtype=np.uint8)
+for _ in range(20):
+    pipe.process(cam)
+ts = []
+for _ in range(200):
+    t0 = time.perf_counter()
+    m = pipe.process(cam)
+    ts.append((time.perf_counter() - t0) * 1e3)
+ts.sort()
+print(f"B200LanePipeline.process, one 480x640 camera frame -> mask {m.shape}: median {ts[100]:.3f} ms, p10 {ts[20]:.3f}, p90 {ts[180]:.3f}")

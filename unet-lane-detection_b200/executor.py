@@ -192,6 +192,7 @@ class B200LanePipeline:
         self.container = B200_model_container(model_path, target, device_id)
         self.matrix = np.asarray(perspective_matrix, dtype=np.float64).reshape(3, 3)
         self.threshold, self.warp_size, self.input_size = threshold, tuple(warp_size), tuple(input_size)
+        self._graphs = {}       # one captured per-frame pass (key: frame shape, matrix, threshold, sizes[, weights])
 
     @torch.no_grad()
     def process_device(self, frames_bgr):
@@ -206,9 +207,46 @@ class B200LanePipeline:
     def process(self, frames_bgr):
         single = frames_bgr.ndim == 3
         arr = np.ascontiguousarray(frames_bgr[None] if single else frames_bgr)
-        with torch.cuda.device(self.container.device):
-            out = self.process_device(torch.from_numpy(arr).to(self.container.device)).cpu().numpy()
-        return out[0] if single else out
+        c = self.container
+        if c.model is None:
+            raise RuntimeError("B200LanePipeline: the container has been released")
+        with torch.cuda.device(c.device):
+            if arr.shape[0] > c.graph_max_batch:
+                out = self.process_device(torch.from_numpy(arr).to(c.device)).cpu().numpy()
+                return out[0] if single else out
+            # the ROS callback's case - one camera frame per call, same shape every time: the ~25 launches between the two copies
+            # (warp + preprocess, the network, the mask resize) are captured once and replayed, with pinned staging on both sides
+            net = c.model
+            key = (arr.shape, self.matrix.tobytes(), float(self.threshold), self.warp_size, self.input_size)
+            if not net.b200_frozen:
+                key += (net._weights_key(),)
+            entry = self._graphs.get(key)
+            if entry is None:
+                self._graphs.clear()
+                static_in = torch.empty(arr.shape, dtype=torch.uint8, device=c.device)
+                static_in.copy_(torch.from_numpy(arr))
+                before = net.gpu_launches
+                self.process_device(static_in)           # eager once: builds the plan, packs the weights
+                launches = net.gpu_launches - before
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=c.device)):
+                    out = self.process_device(static_in)
+                net.gpu_launches -= launches             # (the capture enqueued nothing)
+                pin_in = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
+                pin_out = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+                entry = (graph, static_in, out, net._last_engine, pin_in, pin_out, launches)
+                self._graphs[key] = entry
+            graph, static_in, out, _, pin_in, pin_out, launches = entry
+            pin_in.numpy()[...] = arr
+            static_in.copy_(pin_in, non_blocking=True)
+            graph.replay()
+            net.gpu_launches += launches
+            pin_out.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            res = pin_out.numpy().copy()
+        return res[0] if single else res
 
     def release(self):
+        self._graphs = {}
         self.container.release()
