@@ -125,3 +125,37 @@ def test_lane_pipeline_matches_reference_callback(U, G, tmp_path):
     many = pipe.process(np.concatenate([frames] * 5))
     assert many.shape[0] == 10 and np.array_equal(many[4], masks[0]) and np.array_equal(many[9], masks[1])
     pipe.release()
+
+
+def test_lane_inference_predict_matches_reference_class(U, tmp_path):
+    """B200LaneInference.predict == RKNNLaneInference.predict (src/unet.py:74-97): image -> resize to 224 x 224 -> network ->
+    sigmoid -> strict > threshold -> x255 -> cv2.resize back to the image size; returns (mask, seconds). Per-image calls replay
+    one captured pass: changing images and a changed threshold go through it correctly."""
+    torch.manual_seed(0)
+    ref = O.UNetOracle(3, 1, [64, 128, 256, 512]).eval()
+    O.randomize_bn_(ref, seed=1)
+    O.scale_head_(ref, 40.0)
+    path = tmp_path / "best_model.pth"
+    torch.save({"epoch": 3, "model_state_dict": ref.state_dict()}, path)
+    inf = U.B200LaneInference(str(path))
+    rng = np.random.default_rng(9)
+    imgs = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(2)] + [rng.integers(0, 256, (224, 224, 3), dtype=np.uint8)]
+    zs = []
+    for im in imgs:
+        x, shape = O.preprocess_oracle(im, (224, 224))
+        with torch.no_grad():
+            zs.append((ref(torch.from_numpy(O.normalize_oracle(x))), shape))
+    thr = float(torch.sigmoid(zs[0][0].median()))          # (a threshold that splits the pixels: the mask depends on the image)
+    for rounds in range(2):                                # second round: replays
+        for im, (z, shape) in zip(imgs, zs):
+            mask, dt = inf.predict(im, threshold=thr)
+            assert mask.shape == im.shape[:2] and mask.dtype == np.uint8 and dt > 0     # (the bilinear up-resize blends 0 / 255)
+            want = O.postprocess_oracle([z.numpy()], shape, thr)
+            assert (mask == want).mean() >= 0.95, (rounds, im.shape, (mask == want).mean())   # (threshold in the thick of the logits)
+    m0, _ = inf.predict(imgs[0], threshold=thr)
+    m1, _ = inf.predict(imgs[1], threshold=thr)
+    assert not np.array_equal(m0, m1)
+    all_on, _ = inf.predict(imgs[0], threshold=0.0)
+    assert (all_on == 255).all()
+    bad, dt = inf.predict(np.zeros((480, 640, 4), dtype=np.uint8))      # reference behaviour on an error: zero mask + elapsed time
+    assert bad.shape == (480, 640) and not bad.any() and dt >= 0

@@ -159,6 +159,18 @@ class B200LaneInference:
     def __init__(self, model_path, target=None, device_id=None, input_size=(224, 224)):
         self.model = B200_model_container(model_path, target, device_id)
         self.input_size = input_size
+        self._graphs = {}       # one captured per-image pass (key: image shape, threshold[, weights])
+
+    def _mask_device(self, d, threshold, original_shape):
+        """uint8 image [1,Hs,Ws,3] on the GPU -> uint8 mask [1,Hs,Ws] on the GPU (resize, normalise, network, sigmoid, threshold,
+        mask back to the source size - src/unet.py:24-72)."""
+        net = self.model.model
+        _, _, mask = net.predict_mask(d, threshold=threshold, size=self.input_size, want=("mask",))
+        if tuple(original_shape) != tuple(self.input_size):
+            # mask back to the source size (src/unet.py:70), cv2-exact, on the device
+            mask = resize_gray_u8(mask, (int(original_shape[0]), int(original_shape[1])))
+            net.gpu_launches += 1
+        return mask
 
     def predict(self, image, threshold=0.5):
         import time
@@ -166,13 +178,38 @@ class B200LaneInference:
         t0 = time.time()
         try:
             net = self.model.model
+            arr = np.ascontiguousarray(image)[None]
             with torch.cuda.device(self.model.device):
-                d = torch.from_numpy(np.ascontiguousarray(image)[None]).to(self.model.device)
-                _, _, mask = net.predict_mask(d, threshold=threshold, size=self.input_size, want=("mask",))
-                if tuple(original_shape) != tuple(self.input_size):
-                    # mask back to the source size (src/unet.py:70), cv2-exact, on the device
-                    mask = resize_gray_u8(mask, (int(original_shape[0]), int(original_shape[1])))
-                mask = mask[0].cpu().numpy()
+                # one image per call, same shape every time (the ROS callback): the launches between the two copies are captured
+                # once per (shape, threshold) and replayed, with pinned staging on both sides
+                key = (arr.shape, float(threshold), tuple(self.input_size))
+                if not net.b200_frozen:
+                    key += (net._weights_key(),)
+                entry = self._graphs.get(key)
+                if entry is None:
+                    self._graphs.clear()
+                    static_in = torch.empty(arr.shape, dtype=torch.uint8, device=self.model.device)
+                    static_in.copy_(torch.from_numpy(arr))
+                    before = net.gpu_launches
+                    self._mask_device(static_in, threshold, original_shape)     # eager once: builds the plan, packs the weights
+                    launches = net.gpu_launches - before
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.model.device)):
+                        out = self._mask_device(static_in, threshold, original_shape)
+                    net.gpu_launches -= launches
+                    pin_in = torch.empty(arr.shape, dtype=torch.uint8).pin_memory()
+                    pin_out = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+                    entry = (graph, static_in, out, net._last_engine, pin_in, pin_out, launches)
+                    self._graphs[key] = entry
+                graph, static_in, out, _, pin_in, pin_out, launches = entry
+                pin_in.numpy()[...] = arr
+                static_in.copy_(pin_in, non_blocking=True)
+                graph.replay()
+                net.gpu_launches += launches
+                pin_out.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                mask = pin_out.numpy()[0].copy()
         except Exception as e:  # reference behaviour: zero mask + elapsed time (src/unet.py:89-92)
             print(f"Inference error: {e}")
             return np.zeros(original_shape, dtype=np.uint8), time.time() - t0

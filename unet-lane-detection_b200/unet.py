@@ -233,6 +233,10 @@ class UNet(nn.Module):
         cv2-exact resize + normalise (src/unet.py:24-42, README.md:3110-3111) -> U-Net -> sigmoid ->
         (p > threshold)*255 (src/unet.py:63-67). Returns (logits, probs, mask) like forward_nhwc4."""
         self._check_input(frames_u8, "frames")
+        if frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or frames_u8.dtype != torch.uint8 or not frames_u8.is_contiguous():
+            raise ValueError(f"expected contiguous uint8 frames [B,Hs,Ws,3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+        if self.in_channels != 3:
+            raise ValueError(f"predict_mask feeds 3-channel frames; this model has in_channels={self.in_channels}")
         B, Hs, Ws, _ = frames_u8.shape
         fp32 = self.b200_precision == "fp32"
         x4 = torch.empty(B, size[0], size[1], 4, dtype=torch.float32 if fp32 else torch.bfloat16, device=frames_u8.device)
@@ -249,7 +253,8 @@ class UNet(nn.Module):
         """Reference-facing call with HOST buffers (RKNN_model_container.run contract): uint8 frames
         [B,Hs,Ws,3] on the host (pinned for full PCIe speed) -> host outputs. H2D copy, preprocess, U-Net,
         mask and D2H copy all go through unet_b200_infer_u8_host; returns after the results are on the host."""
-        if frames_host.is_cuda or frames_host.dtype != torch.uint8 or not frames_host.is_contiguous():
+        if (frames_host.is_cuda or frames_host.dtype != torch.uint8 or not frames_host.is_contiguous() or frames_host.dim() != 4
+                or frames_host.shape[3] != 3):
             raise ValueError("frames_host must be a contiguous uint8 CPU tensor [B,Hs,Ws,3]")
         B, Hs, Ws, _ = frames_host.shape
         dev = next(self.parameters()).device
