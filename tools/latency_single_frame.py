@@ -66,3 +66,18 @@ for _ in range(200):
     ts.append((time.perf_counter() - t0) * 1e3)
 ts.sort()
 print(f"B200LanePipeline.process, one 480x640 camera frame -> mask {m.shape}: median {ts[100]:.3f} ms, p10 {ts[20]:.3f}, p90 {ts[180]:.3f}")
+
+# RKNNLaneInference.predict's mirror: image -> mask at the image's own size (resize to 224 x 224 inside, mask resized back)
+with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, "unet.pth")
+    torch.save({"model_state_dict": U.UNet(3, 1, [64, 128, 256, 512]).state_dict()}, path)
+    inf = U.B200LaneInference(path)
+for _ in range(20):
+    inf.predict(cam, 0.5)
+ts = []
+for _ in range(200):
+    t0 = time.perf_counter()
+    m, _ = inf.predict(cam, 0.5)
+    ts.append((time.perf_counter() - t0) * 1e3)
+ts.sort()
+print(f"B200LaneInference.predict, one 480x640 image -> mask {m.shape}: median {ts[100]:.3f} ms, p10 {ts[20]:.3f}, p90 {ts[180]:.3f}")
