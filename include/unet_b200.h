@@ -205,8 +205,9 @@ int unet_b200_infer_u8_host(unet_b200_plan* p, void* staging_dev, const uint8_t*
 /* Same contract for ANY number of frames: the batch is cut into passes of the plan's capacity; the H2D copies of pass
  * i+1 and the D2H copies of pass i-1 overlap the kernels of pass i (two staging slots, two internal copy streams created
  * on first use). Inside a pass the input copy, the preprocess and the two full-resolution layers at the start of the
- * network, and the fused-head conv and the output copies at its end, run per PIECE of the pass (option "host_pieces",
- * default 8 pieces; bf16 plans whose stem / first conv / last conv run on the tensor-core stem and halo kernels), so only
+ * network, and the fused-head conv and the output copies at its end, run per PIECE of the pass (pieces of 16, 32, 64, ...
+ * frames, options "host_geometric" / "host_pieces"; bf16 plans whose stem / first conv / last conv run on the tensor-core
+ * stem and halo kernels), so only
  * the first piece's input copy and the last piece's output copy are not hidden behind kernels. Source frames more than
  * 1.5x the size of the network input (whose copies take longer than those two layers) additionally get a SHORT first
  * pass (a quarter of the capacity) whose kernels cover the copies of the rest (option "host_hybrid"); plans without
